@@ -1,0 +1,217 @@
+"""Generate tests/golden/*.npz from the REAL reference (/root/reference) -- TEST INFRASTRUCTURE.
+
+Run in the build container only:  ``python -m oracle.make_golden``.
+The fixtures hold seeded inputs *and* the reference's outputs, so the GPU box (which has no
+/root/reference) can check both the NumPy oracle and the CUDA path against the reference.
+Also dumps the Ghia et al. tables (data, cavity_flow.py:29-124) to naviflow_b200/ghia_tables.json.
+"""
+import contextlib
+import io
+import json
+import os
+import warnings
+
+import numpy as np
+
+from . import reference_loader as rl
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "..", "tests", "golden")
+
+
+def _quiet(f, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return f(*a, **k)
+
+
+def synth_pressure_inputs(n, seed, mu=1e-3):
+    """SURVEY.md section 8d C4 synthetic inputs (seeded)."""
+    rng = np.random.default_rng(seed)
+    dx = dy = 1.0 / (n - 1)
+    d_u = (0.7 * dy / (4 * mu)) * (1 + 0.1 * rng.random((n + 1, n)))
+    d_v = (0.7 * dx / (4 * mu)) * (1 + 0.1 * rng.random((n, n + 1)))
+    d_u[0, :] = np.nan; d_u[n, :] = np.nan      # as JacobiMatrixMomentumSolver leaves them
+    d_v[:, 0] = np.nan; d_v[:, n] = np.nan
+    us = 1e-2 * rng.standard_normal((n + 1, n)); us[0, :] = us[n, :] = 0
+    vs = 1e-2 * rng.standard_normal((n, n + 1)); vs[:, 0] = vs[:, n] = 0
+    x = rng.standard_normal((n, n))
+    u = 0.1 * rng.standard_normal((n + 1, n))
+    v = 0.1 * rng.standard_normal((n, n + 1))
+    p = rng.standard_normal((n, n))
+    return dict(d_u=d_u, d_v=d_v, u_star=us, v_star=vs, x=x, u=u, v=v, p=p)
+
+
+def cavity_bc(R):
+    bc = R.BoundaryConditionManager()
+    bc.set_condition("top", "velocity", {"u": 1.0, "v": 0.0})
+    for b in ("bottom", "left", "right"):
+        bc.set_condition(b, "wall")
+    return bc
+
+
+def kernel_kats(R, n, seed):
+    out = synth_pressure_inputs(n, seed)
+    nx = ny = n
+    mesh = R.StructuredMesh(nx, ny, 1.0, 1.0)
+    dx, dy = mesh.get_cell_sizes()
+    fluid = R.FluidProperties(density=1.0, reynolds_number=1000, characteristic_velocity=1.0)
+    bc = cavity_bc(R)
+    rho = 1.0
+    d_u, d_v, us, vs, x, u, v, p = (out[k] for k in ("d_u", "d_v", "u_star", "v_star", "x", "u", "v", "p"))
+    # a2
+    ub, vb = bc.apply_velocity_boundary_conditions(u.copy(), v.copy(), nx, ny)
+    out["bc_u"], out["bc_v"] = ub, vb
+    ub1, vb1 = bc.apply_velocity_boundary_conditions(u.copy(), v.copy(), nx + 1, ny)
+    out["bc1_u"], out["bc1_v"] = ub1, vb1
+    # a3/a4
+    pl = R.PowerLawDiscretization()
+    for nm, c in (("cu", pl.calculate_u_coefficients(mesh, fluid, ub, vb, p, bc)),
+                  ("cv", pl.calculate_v_coefficients(mesh, fluid, ub, vb, p, bc))):
+        for k, a in c.items():
+            out[f"{nm}_{k}"] = a
+    # a6
+    ms = R.JacobiMatrixMomentumSolver(n_jacobi_sweeps=4)
+    r = ms.solve_u_momentum(mesh, fluid, u, v, p, 0.7, bc)
+    out["mom_u_star"], out["mom_d_u"], out["mom_u_norm"], out["mom_u_field"] = r[0], r[1], np.float64(r[2]), r[3]
+    r = ms.solve_v_momentum(mesh, fluid, u, v, p, 0.7, bc)
+    out["mom_v_star"], out["mom_d_v"], out["mom_v_norm"], out["mom_v_field"] = r[0], r[1], np.float64(r[2]), r[3]
+    # a8/a9
+    b = R.get_rhs(nx, ny, dx, dy, rho, us, vs).reshape((nx, ny), order="F")
+    out["rhs"] = b
+    out["Ax"] = R.compute_Ap_product(x.flatten("F"), nx, ny, dx, dy, rho, d_u, d_v).reshape((nx, ny), order="F")
+    # a10/a11
+    js = R.JacobiSolver(omega=0.8)
+    out["jacobi_diag"] = js._get_diagonal_elements(nx, ny, dx, dy, rho, d_u, d_v)
+    out["jacobi3"] = js.solve(mesh=mesh, p=x.copy(), b=b.copy(), d_u=d_u, d_v=d_v, rho=rho, num_iterations=3,
+                              track_residuals=False, return_dict=False)
+    gs = R.GaussSeidelSolver(omega=1.5, method_type="red_black")
+    out["rbsor3"] = gs.solve(mesh=mesh, p=x.copy(), b=b.copy(), d_u=d_u, d_v=d_v, rho=rho, num_iterations=3,
+                             track_residuals=False, return_dict=False)
+    # a12 transfer operators
+    H = R.multigrid_helpers
+    out["fw"] = H.restrict_full_weighting(x)
+    out["inject"] = H.restrict_inject(x)
+    out["lin_from_fw"] = H.interpolate_linear(out["fw"], nx)
+    out["lin_from_inject"] = H.interpolate_linear(out["inject"], nx)
+    if out["fw"].shape[0] >= 4:
+        out["cub_from_fw"] = H.interpolate_cubic(out["fw"], nx)
+    nc = out["fw"].shape[0]
+    out["rc_du_fw"], out["rc_dv_fw"] = H.restrict_coefficients(d_u, d_v, nx, ny, nc, nc, dx, dy)
+    nci = out["inject"].shape[0]
+    out["rc_du_inject"], out["rc_dv_inject"] = H.restrict_coefficients(d_u, d_v, nx, ny, nci, nci, dx, dy)
+    # coarse direct solve (multigrid.py:268-302)
+    if n <= 15:
+        A = R.get_coeff_mat(nx, ny, dx, dy, rho, d_u, d_v)
+        from scipy.sparse.linalg import spsolve
+        out["direct"] = spsolve(A, b.flatten("F")).reshape((nx, ny), order="F")
+    # a14
+    vu = R.StandardVelocityUpdater()
+    out["corr_u"], out["corr_v"] = vu.update_velocity(mesh, us, vs, x, d_u, d_v, bc)
+    return out
+
+
+def mg_kats(R, n, seed):
+    inp = synth_pressure_inputs(n, seed)
+    d_u, d_v, us, vs = inp["d_u"], inp["d_v"], inp["u_star"], inp["v_star"]
+    mesh = R.StructuredMesh(n, n, 1.0, 1.0)
+    out = dict(d_u=d_u, d_v=d_v, u_star=us, v_star=vs)
+    cfgs = {
+        "v_lin_fw": dict(cycle_type="v", max_iterations=3, tolerance=1e-14),
+        "v_cub_fw": dict(cycle_type="v", max_iterations=2, tolerance=1e-14, interpolation_method="interpolate_cubic"),
+        "w_lin_fw": dict(cycle_type="w", max_iterations=2, tolerance=1e-14),
+        "fmg_cub_v": dict(cycle_type="fmg", cycle_type_final="v", max_iterations=100, tolerance=1e-3,
+                          interpolation_method="interpolate_cubic"),
+        "v_tol": dict(cycle_type="v", max_iterations=100, tolerance=1e-3),
+    }
+    if n % 2 == 1:
+        cfgs["v_lin_inject"] = dict(cycle_type="v", max_iterations=2, tolerance=1e-14,
+                                    restriction_method="restrict_inject")
+    for name, kw in cfgs.items():
+        ps = R.MultiGridSolver(smoother=R.GaussSeidelSolver(omega=1.5, method_type="red_black"),
+                               pre_smoothing=3, post_smoothing=3, coarsest_grid_size=7, **kw)
+        p1, i1 = _quiet(ps.solve, mesh, us, vs, d_u, d_v, None)
+        out[name + "_p"] = p1
+        out[name + "_relnorm"] = np.float64(i1["rel_norm"])
+        out[name + "_ncycles"] = np.int64(len(ps.residual_history))
+    ps = R.MultiGridSolver(smoother=R.JacobiSolver(omega=0.8), max_iterations=2, tolerance=1e-14,
+                           pre_smoothing=2, post_smoothing=2)
+    p1, _ = _quiet(ps.solve, mesh, us, vs, d_u, d_v, None)
+    out["v_jacobi_smoother_p"] = p1
+    bs = R.MatrixFreeBiCGSTABSolver(tolerance=1e-7, max_iterations=1000)
+    p1, i1 = _quiet(bs.solve, mesh, us, vs, d_u, d_v, None)
+    out["bicgstab_p"] = p1
+    out["bicgstab_relnorm"] = np.float64(i1["rel_norm"])
+    out["bicgstab_iters"] = np.int64(len(bs.residual_history))
+    return out
+
+
+def simple_runs(R):
+    out = {}
+
+    def run(n, Re, ps, k, N):
+        mesh = R.StructuredMesh(n, n, 1.0, 1.0)
+        fluid = R.FluidProperties(density=1.0, reynolds_number=Re, characteristic_velocity=1.0)
+        alg = R.SimpleSolver(mesh, fluid, ps, R.JacobiMatrixMomentumAdapter(n_jacobi_sweeps=k),
+                             R.StandardVelocityUpdater(), alpha_p=0.3, alpha_u=0.7)
+        alg.set_boundary_condition("top", "velocity", {"u": 1.0, "v": 0.0})
+        for b in ("bottom", "left", "right"):
+            alg.set_boundary_condition(b, "wall")
+        _quiet(alg.solve, max_iterations=N, tolerance=0.0, save_profile=False, track_infinity_norm=False)
+        return alg
+
+    def mk(name):
+        GS = R.GaussSeidelSolver
+        if name == "fmg":
+            return R.MultiGridSolver(smoother=GS(omega=1.5, method_type="red_black"), max_iterations=100,
+                                     tolerance=1e-3, pre_smoothing=3, post_smoothing=3, cycle_type="fmg",
+                                     cycle_type_buildup="v", cycle_type_final="v", max_cycles_buildup=1,
+                                     restriction_method="restrict_full_weighting",
+                                     interpolation_method="interpolate_cubic", coarsest_grid_size=7)
+        if name == "v":
+            return R.MultiGridSolver(smoother=GS(omega=1.5, method_type="red_black"), max_iterations=100,
+                                     tolerance=1e-3, pre_smoothing=3, post_smoothing=3)
+        if name == "jacobi":
+            return R.JacobiSolver(tolerance=0.0, max_iterations=50, omega=0.8)
+        if name == "rbsor":
+            return GS(tolerance=0.0, max_iterations=30, omega=1.5, method_type="red_black")
+        if name == "direct":
+            return R.DirectPressureSolver()
+        raise ValueError(name)
+
+    for n, Re, k, N, names in ((31, 100, 5, 40, ("fmg", "v", "jacobi", "rbsor", "direct")),
+                               (63, 1000, 20, 25, ("fmg", "v")),
+                               (64, 1000, 3, 12, ("v",)),
+                               (127, 1000, 5, 8, ("v",))):
+        for name in names:
+            alg = run(n, Re, mk(name), k, N)
+            key = f"n{n}_Re{Re}_k{k}_N{N}_{name}"
+            out[key + "_u"], out[key + "_v"], out[key + "_p"] = alg.u, alg.v, alg.p
+            out[key + "_hist"] = np.array(alg.residual_history[::2])  # appended twice per iteration (simple.py:177,196)
+            if n <= 63:
+                cf = R.cavity_flow
+                out[key + "_ghia"] = np.array([cf.calculate_infinity_norm_error(alg.u, alg.v, alg.mesh, Re),
+                                               cf.calculate_l2_norm_error(alg.u, alg.v, alg.mesh, Re)])
+    return out
+
+
+def main():
+    warnings.filterwarnings("ignore")
+    R = rl.ref()
+    os.makedirs(GOLD, exist_ok=True)
+    for n, seed in ((8, 108), (15, 115), (31, 131), (32, 132)):
+        np.savez_compressed(os.path.join(GOLD, f"kernels_n{n}.npz"), **kernel_kats(R, n, seed))
+    for n, seed in ((31, 231), (33, 233), (64, 264)):
+        np.savez_compressed(os.path.join(GOLD, f"mg_n{n}.npz"), **mg_kats(R, n, seed))
+    np.savez_compressed(os.path.join(GOLD, "simple_runs.npz"), **simple_runs(R))
+    cf = R.cavity_flow.BenchmarkData
+    tables = {}
+    for Re in (100, 400, 1000, 3200, 5000, 7500, 10000):
+        t = cf.get_ghia_data(Re)
+        tables[str(Re)] = {k: [float(x) for x in t[k]] for k in ("x", "v", "y", "u")}
+    with open(os.path.join(HERE, "..", "naviflow_b200", "ghia_tables.json"), "w") as f:
+        json.dump(tables, f, indent=1)
+    print("golden fixtures written to", os.path.normpath(GOLD))
+
+
+if __name__ == "__main__":
+    main()

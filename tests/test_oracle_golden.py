@@ -1,0 +1,138 @@
+"""CPU: the NumPy oracle reproduces the reference's golden vectors (tests/golden/*.npz,
+generated from the real reference by oracle/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import np_oracle as O
+
+COND = O.bc_conditions()
+RHO = 1.0
+MU = 1.0 / 1000.0
+
+
+def load(golden_dir, name):
+    return dict(np.load(os.path.join(golden_dir, name)))
+
+
+def same(a, b):
+    np.testing.assert_array_equal(np.asarray(a), np.asarray(b))
+
+
+def close(a, b, tol):
+    a, b = np.asarray(a), np.asarray(b)
+    assert np.linalg.norm(a - b) <= tol * max(np.linalg.norm(b), 1e-300), \
+        f"rel L2 {np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300):.3e} > {tol}"
+
+
+@pytest.mark.parametrize("n", [8, 15, 31, 32])
+def test_kernel_kats_bit_exact(golden_dir, n):
+    g = load(golden_dir, f"kernels_n{n}.npz")
+    nx = ny = n
+    dx, dy = O.mesh_spacing(nx, ny)
+    d_u, d_v, us, vs, x, u, v, p = (g[k] for k in ("d_u", "d_v", "u_star", "v_star", "x", "u", "v", "p"))
+    ub, vb = O.apply_velocity_bc(u.copy(), v.copy(), nx, ny, COND)
+    same(ub, g["bc_u"]); same(vb, g["bc_v"])
+    ub1, vb1 = O.apply_velocity_bc(u.copy(), v.copy(), nx + 1, ny, COND)
+    same(ub1, g["bc1_u"]); same(vb1, g["bc1_v"])
+    cu = O.u_coefficients(nx, ny, dx, dy, RHO, MU, ub, vb, p)
+    cv = O.v_coefficients(nx, ny, dx, dy, RHO, MU, ub, vb, p)
+    for k in cu:
+        same(cu[k], g["cu_" + k]); same(cv[k], g["cv_" + k])
+    r = O.solve_u_momentum(nx, ny, dx, dy, RHO, MU, u, v, p, 0.7, COND, 4)
+    same(r[0], g["mom_u_star"]); same(r[1], g["mom_d_u"]); same(r[2], g["mom_u_norm"]); same(r[3], g["mom_u_field"])
+    r = O.solve_v_momentum(nx, ny, dx, dy, RHO, MU, u, v, p, 0.7, COND, 4)
+    same(r[0], g["mom_v_star"]); same(r[1], g["mom_d_v"]); same(r[2], g["mom_v_norm"]); same(r[3], g["mom_v_field"])
+    b = O.continuity_rhs(nx, ny, dx, dy, RHO, us, vs)
+    same(b, g["rhs"])
+    same(O.apply_A(x, dx, dy, RHO, d_u, d_v), g["Ax"])
+    same(O.jacobi_diag(nx, ny, dx, dy, RHO, d_u, d_v), g["jacobi_diag"])
+    same(O.jacobi_iterate(x, b, dx, dy, RHO, d_u, d_v, 0.8, 3), g["jacobi3"])
+    same(O.rb_sor(x, b, dx, dy, RHO, d_u, d_v, 1.5, 3), g["rbsor3"])
+    same(O.restrict_full_weighting(x), g["fw"])
+    same(O.restrict_inject(x), g["inject"])
+    same(O.prolong_linear(g["fw"], nx), g["lin_from_fw"])
+    same(O.prolong_linear(g["inject"], nx), g["lin_from_inject"])
+    if "cub_from_fw" in g:
+        same(O.prolong_cubic(g["fw"], nx), g["cub_from_fw"])
+        P = O.notaknot_matrix(g["fw"].shape[0], nx)
+        close(P @ g["fw"] @ P.T, g["cub_from_fw"], 1e-13)
+    nc = g["fw"].shape[0]
+    duc, dvc = O.restrict_coefficients(d_u, d_v, nx, ny, nc, nc)
+    np.testing.assert_array_equal(duc, g["rc_du_fw"]); np.testing.assert_array_equal(dvc, g["rc_dv_fw"])
+    nci = g["inject"].shape[0]
+    duc, dvc = O.restrict_coefficients(d_u, d_v, nx, ny, nci, nci)
+    np.testing.assert_array_equal(duc, g["rc_du_inject"]); np.testing.assert_array_equal(dvc, g["rc_dv_inject"])
+    if "direct" in g:
+        close(O.direct_solve(b, dx, dy, RHO, d_u, d_v), g["direct"], 1e-12)
+    cu_, cv_ = O.correct_velocity(nx, ny, us, vs, x, d_u, d_v, COND)
+    same(cu_, g["corr_u"]); same(cv_, g["corr_v"])
+
+
+@pytest.mark.parametrize("n", [31, 33, 64])
+def test_multigrid_and_krylov_golden(golden_dir, n):
+    g = load(golden_dir, f"mg_n{n}.npz")
+    d_u, d_v, us, vs = g["d_u"], g["d_v"], g["u_star"], g["v_star"]
+    dx, dy = O.mesh_spacing(n, n)
+    base = dict(smoother="red_black", omega=1.5, pre=3, post=3, coarsest=7)
+    cfgs = {
+        "v_lin_fw": dict(cycle_type="v", max_iterations=3, tolerance=1e-14),
+        "v_cub_fw": dict(cycle_type="v", max_iterations=2, tolerance=1e-14, interpolation="interpolate_cubic"),
+        "w_lin_fw": dict(cycle_type="w", max_iterations=2, tolerance=1e-14),
+        "fmg_cub_v": dict(cycle_type="fmg", cycle_type_final="v", max_iterations=100, tolerance=1e-3,
+                          interpolation="interpolate_cubic"),
+        "v_tol": dict(cycle_type="v", max_iterations=100, tolerance=1e-3),
+        "v_lin_inject": dict(cycle_type="v", max_iterations=2, tolerance=1e-14, restriction="restrict_inject"),
+    }
+    for name, kw in cfgs.items():
+        if name + "_p" not in g:
+            continue
+        cfg = O.MGConfig(**base, **kw)
+        p, info = O.mg_solve(cfg, n, n, dx, dy, us, vs, d_u, d_v)
+        close(p, g[name + "_p"], 1e-13)
+        assert abs(info["rel_norm"] - g[name + "_relnorm"]) <= 1e-10 * g[name + "_relnorm"]
+        if name == "v_tol":
+            assert info["cycles"] == int(g[name + "_ncycles"])
+    cfg = O.MGConfig(smoother="jacobi", omega=0.8, pre=2, post=2, max_iterations=2, tolerance=1e-14)
+    p, _ = O.mg_solve(cfg, n, n, dx, dy, us, vs, d_u, d_v)
+    close(p, g["v_jacobi_smoother_p"], 1e-13)
+    p, info = O.krylov_pressure_solve("bicgstab", n, n, dx, dy, us, vs, d_u, d_v, tol=1e-7, maxiter=1000)
+    same(p, g["bicgstab_p"])
+    assert abs(info["rel_norm"] - g["bicgstab_relnorm"]) <= 1e-12 * g["bicgstab_relnorm"]
+
+
+def _ps(name):
+    if name == "fmg":
+        return O.make_pressure_solver("mg", cfg=O.MGConfig(omega=1.5, pre=3, post=3, cycle_type="fmg",
+                                                           cycle_type_final="v", interpolation="interpolate_cubic",
+                                                           tolerance=1e-3))
+    if name == "v":
+        return O.make_pressure_solver("mg", cfg=O.MGConfig(omega=1.5, pre=3, post=3, tolerance=1e-3))
+    if name == "jacobi":
+        return O.make_pressure_solver("jacobi", omega=0.8, n_iter=50)
+    if name == "rbsor":
+        return O.make_pressure_solver("rb_sor", omega=1.5, n_iter=30)
+    return O.make_pressure_solver("direct")
+
+
+@pytest.mark.parametrize("n,Re,k,N,name", [
+    (31, 100, 5, 40, "fmg"), (31, 100, 5, 40, "v"), (31, 100, 5, 40, "jacobi"),
+    (31, 100, 5, 40, "rbsor"), (31, 100, 5, 40, "direct"),
+    (63, 1000, 20, 25, "fmg"), (63, 1000, 20, 25, "v"), (64, 1000, 3, 12, "v"), (127, 1000, 5, 8, "v")])
+def test_simple_loop_golden(golden_dir, n, Re, k, N, name):
+    g = load(golden_dir, "simple_runs.npz")
+    key = f"n{n}_Re{Re}_k{k}_N{N}_{name}"
+    st, h = O.simple_solve(n, n, Re, _ps(name), n_sweeps=k, max_iterations=N, tolerance=0.0)
+    tol = 0.0 if name in ("jacobi", "rbsor") else 1e-12
+    for fld, arr in (("u", st.u), ("v", st.v), ("p", st.p)):
+        if tol == 0.0:
+            same(arr, g[f"{key}_{fld}"])
+        else:
+            close(arr, g[f"{key}_{fld}"], tol)
+    np.testing.assert_allclose(h["total_rel_norm"], g[key + "_hist"], rtol=1e-9)
+    if key + "_ghia" in g:
+        import json
+        tables = json.load(open(os.path.join(os.path.dirname(golden_dir), "..", "naviflow_b200", "ghia_tables.json")))
+        inf, l2 = O.ghia_errors(st.u, st.v, n, n, tables[str(Re)])
+        np.testing.assert_allclose([inf, l2], g[key + "_ghia"], rtol=1e-9)
