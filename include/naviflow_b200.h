@@ -1,0 +1,242 @@
+/*
+ * naviflow_b200.h -- C-ABI of libnaviflow_b200.so (sm_100a, fp64).
+ *
+ * Drop-in boundary for ONE hot path of philipnickel/NaviFlow: the SIMPLE outer loop of the 2-D
+ * lid-driven cavity (momentum link-coefficient assembly + Jacobi sweeps, matrix-free
+ * pressure-correction operator, Jacobi / red-black SOR / geometric multigrid / CG / BiCGSTAB
+ * pressure solvers, u/v/p correction, residual norms).  The reference is pure Python
+ * (NumPy/SciPy); each entry point below names the reference function it replaces
+ * (paths relative to /root/reference/naviflow_oo).  The Python plugin classes in
+ * naviflow_b200/ bind these symbols with ctypes (see INTEGRATION.md for the stub a
+ * reference maintainer would add).
+ *
+ * Conventions
+ *  - All pointers are DEVICE pointers to fp64 unless the name ends in _host.
+ *  - Fields are C-ordered 2-D arrays with a common row pitch `ld` (in doubles, ld >= ny+1):
+ *      p-like (nx rows, ny cols), u (nx+1 rows, ny cols), v (nx rows, ny+1 cols);
+ *      element [i][j] lives at base[(i - row0)*ld + j].  Pad columns are never read as data.
+ *  - `nf_grid` describes one multigrid level / one slab of it.  On a single GPU row0=0,
+ *      gb=0, ge=nx.  On a slab-decomposed run row0 is the global index of the first stored
+ *      row (halo included) and [gb,ge) the global cell rows this rank computes.
+ *  - Every function returns 0 on success or a negative nf_status; nf_last_error() gives text.
+ *  - No function allocates device memory except the *_create calls; hot calls are asynchronous
+ *      on the context's stream unless they return a host scalar.
+ *  - One host thread per context.
+ */
+#ifndef NAVIFLOW_B200_H
+#define NAVIFLOW_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nf_ctx nf_ctx;       /* stream, reduction scratch, error text           */
+typedef struct nf_mg nf_mg;         /* multigrid hierarchy (levels, coarse inverse)     */
+typedef struct nf_simple nf_simple; /* device-resident SIMPLE state (all fields + work) */
+
+enum nf_status {
+  NF_OK = 0,
+  NF_ERR_CUDA = -1,
+  NF_ERR_ARG = -2,
+  NF_ERR_ALLOC = -3,
+  NF_ERR_UNSUPPORTED = -4
+};
+
+typedef struct nf_grid {
+  int32_t nx, ny;   /* global number of cells                      */
+  int32_t ld;       /* row pitch in doubles                        */
+  int32_t row0;     /* global index of the first stored row        */
+  int32_t gb, ge;   /* global cell-row range [gb,ge) to compute    */
+  double dx, dy;    /* StructuredMesh spacing: L/(nx-1), H/(ny-1)  (preprocessing/mesh/structured.py:27-28) */
+  double rho;
+} nf_grid;
+
+/* Edge program of BoundaryConditionManager.apply_velocity_boundary_conditions
+ * (constructor/boundary_conditions.py:164-260) after evaluating the insertion-ordered
+ * conditions on the host: final value per edge line / corner, NaN = "leave untouched".
+ * Index order: 0 left(i=0) 1 right(i=last) 2 bottom(j=0) 3 top(j=last);
+ * corners: 0 (left,bottom) 1 (left,top) 2 (right,bottom) 3 (right,top). */
+typedef struct nf_bc_program {
+  double u_edge[4], u_corner[4];
+  double v_edge[4], v_corner[4];
+  int32_t v_right_row; /* row index the "right" v edge applies to (nx-1), or -1 if skipped
+                          (callers that pass nx+1, matrix_free_momentum.py:419) */
+  int32_t pad;
+} nf_bc_program;
+
+/* ---- context ------------------------------------------------------------------------ */
+int nf_ctx_create(nf_ctx** out, int device, void* cuda_stream /* cudaStream_t or NULL */);
+int nf_ctx_destroy(nf_ctx* ctx);
+const char* nf_last_error(nf_ctx* ctx);
+int nf_sync(nf_ctx* ctx);
+int nf_version(void);
+/* number of kernel launches issued through this context since creation (bench gpu_launches) */
+int64_t nf_launch_count(nf_ctx* ctx);
+
+/* ---- K1  velocity BCs: boundary_conditions.py:164-260 -------------------------------- */
+int nf_apply_velocity_bc(nf_ctx*, const nf_grid*, const nf_bc_program*, double* u, double* v);
+
+/* ---- K5  continuity RHS: pressure_solver/helpers/rhs_construction.py:3-21 ------------ */
+int nf_continuity_rhs(nf_ctx*, const nf_grid*, const double* u_star, const double* v_star, double* b);
+
+/* ---- K6  A*p and b-A*p: pressure_solver/helpers/matrix_free.py:6-135 ------------------ */
+int nf_pressure_apply(nf_ctx*, const nf_grid*, const double* p, const double* d_u, const double* d_v,
+                      double* out);
+int nf_pressure_residual(nf_ctx*, const nf_grid*, const double* p, const double* b, const double* d_u,
+                         const double* d_v, double* r);
+
+/* ---- K7  weighted Jacobi: pressure_solver/jacobi.py:38-78,160-203 --------------------- */
+/* n_iter iterations; p is updated in place (tmp is a same-shape scratch array). p[0,0]:=0. */
+int nf_jacobi_iterate(nf_ctx*, const nf_grid*, double* p, double* tmp, const double* b, const double* d_u,
+                      const double* d_v, double omega, int n_iter);
+int nf_jacobi_diag(nf_ctx*, const nf_grid*, const double* d_u, const double* d_v, double* diag);
+
+/* ---- K8  red-black SOR: pressure_solver/gauss_seidel.py:214-305 ----------------------- */
+int nf_rbsor_sweeps(nf_ctx*, const nf_grid*, double* p, const double* b, const double* d_u,
+                    const double* d_v, double omega, int n_sweeps);
+
+/* ---- K9-K12 transfer operators: pressure_solver/helpers/multigrid_helpers.py ---------- */
+int nf_restrict_fw(nf_ctx*, const nf_grid* fine, const double* f, const nf_grid* coarse, double* c);     /* :23-70  */
+int nf_restrict_inject(nf_ctx*, const nf_grid* fine, const double* f, const nf_grid* coarse, double* c); /* :8-21   */
+int nf_restrict_coeffs(nf_ctx*, const nf_grid* fine, const double* d_u, const double* d_v,
+                       const nf_grid* coarse, double* d_u_c, double* d_v_c);                             /* :196-329 */
+/* fine = P*coarse (add=0) or fine += P*coarse (add=1); bilinear with the reference's index rules */
+int nf_prolong_linear(nf_ctx*, const nf_grid* coarse, const double* c, const nf_grid* fine, double* f,
+                      int add);                                                                          /* :73-192 */
+/* interpolate_cubic (:333-391): separable not-a-knot spline on linspace(0,1,.) coordinates, square grids.
+ * Builds the banded 1-D operator on the host on every call (setup cost); the multigrid driver caches it. */
+int nf_prolong_cubic(nf_ctx*, const nf_grid* coarse, const double* c, const nf_grid* fine, double* f,
+                     int add);
+
+/* ---- reductions (K18) ------------------------------------------------------------------ */
+/* sqrt(sum x^2) over the nx*ny cells (rows [gb,ge)); interior_only!=0 masks the boundary ring */
+int nf_norm2(nf_ctx*, const nf_grid*, const double* x, int interior_only, double* out_host);
+int nf_dot(nf_ctx*, const nf_grid*, const double* x, const double* y, double* out_host);
+
+/* ---- K13 + multigrid driver: pressure_solver/multigrid.py:121-688 ---------------------- */
+typedef struct nf_mg_config {
+  int32_t smoother;        /* 0 = red-black SOR (gauss_seidel.py), 1 = weighted Jacobi (jacobi.py) */
+  int32_t pre, post;       /* pre_smoothing, post_smoothing                                       */
+  int32_t cycle_type;      /* 0 'v', 1 'w', 2 'fmg'                                               */
+  int32_t cycle_buildup;   /* 0 'v', 1 'w'                                                        */
+  int32_t cycle_final;     /* -1 None, 0 'v', 1 'w'                                               */
+  int32_t max_cycles_buildup;
+  int32_t restriction;     /* 0 full weighting, 1 injection                                       */
+  int32_t interpolation;   /* 0 linear, 1 cubic (not-a-knot spline)                               */
+  int32_t coarsest;        /* coarsest_grid_size                                                  */
+  int32_t max_iterations;
+  int32_t pad;
+  double omega;
+  double tolerance;
+  double length, height;   /* mesh.length, mesh.height (coarse meshes: multigrid.py:373)          */
+  double rho;
+} nf_mg_config;
+
+typedef struct nf_mg_info {
+  double r_norm;     /* ||b - A x||_2 after the last cycle (multigrid.py:257 'rel_norm') */
+  double b_norm;
+  int32_t cycles;    /* V/W cycles run at the finest level ('v'/'w' mode)                 */
+  int32_t levels;
+} nf_mg_info;
+
+int nf_mg_create(nf_ctx*, nf_mg** out, int nx, int ny, int ld, const nf_mg_config* cfg);
+int nf_mg_destroy(nf_mg*);
+int nf_mg_num_levels(nf_mg*);
+int nf_mg_level_shape(nf_mg*, int level, int* nx, int* ny, int* ld);
+/* device array of a level (tests / inspection): which = 0 d_u, 1 d_v, 2 x, 3 b, 4 r */
+const double* nf_mg_level_array(nf_mg*, int level, int which);
+/* hierarchy of restricted coefficients + coarse inverse for this (d_u, d_v) (multigrid.py:380-385) */
+int nf_mg_setup(nf_mg*, const double* d_u, const double* d_v);
+/* MultiGridSolver.solve without get_rhs: x (out), b (in), r (out, residual field b-Ax) */
+int nf_mg_solve(nf_mg*, const double* b, double* x, double* r, nf_mg_info* info_host);
+/* one cycle (kind 0 'v' / 1 'w') at the finest level on (x, b): multigrid.py:304-560 */
+int nf_mg_cycle(nf_mg*, double* x, const double* b, int kind);
+
+/* ---- K14/K15 Krylov solvers in scipy's operation order (scipy _isolve/iterative.py) ------ */
+typedef struct nf_krylov_info {
+  double r_norm;      /* ||r|| of the recurrence at exit                   */
+  double b_norm;
+  int32_t iterations;
+  int32_t info;       /* scipy's info: 0 converged, >0 maxiter, <0 breakdown */
+} nf_krylov_info;
+/* work: 4 (cg) / 7 (bicgstab) same-shape scratch arrays, contiguous, each nx*ld doubles */
+int nf_cg_solve(nf_ctx*, const nf_grid*, const double* b, double* x, const double* d_u, const double* d_v,
+                double atol, double rtol, int maxiter, int check_every, double* work, nf_krylov_info* info_host);
+int nf_bicgstab_solve(nf_ctx*, const nf_grid*, const double* b, double* x, const double* d_u,
+                      const double* d_v, double atol, double rtol, int maxiter, int check_every, double* work,
+                      nf_krylov_info* info_host);
+
+/* ---- K2-K4 momentum: discretization/power_law.py:46-365, jacobi_matrix_solver.py:153-375 -- */
+typedef struct nf_links {  /* six same-shape coefficient arrays of one momentum component */
+  double *a_e, *a_w, *a_n, *a_s, *a_p, *src;
+} nf_links;
+/* u_bc/v_bc: velocities with BCs applied; writes relaxed a_p (=a_p/alpha), relaxed source and d
+ * (= dy/a_p or dx/a_p, NaN where |a_p|<=1e-12).  sides bit mask: 1 left, 2 right, 4 bottom, 8 top
+ * (boundaries with a registered condition -> Practice-B folding). */
+int nf_momentum_links_u(nf_ctx*, const nf_grid*, const double* u_bc, const double* v_bc, const double* p,
+                        double mu, double alpha, int sides, nf_links out, double* d_u);
+int nf_momentum_links_v(nf_ctx*, const nf_grid*, const double* u_bc, const double* v_bc, const double* p,
+                        double mu, double alpha, int sides, nf_links out, double* d_v);
+/* n_sweeps Jacobi sweeps x <- D^-1 (b - (A-D) x); is_u selects the (nx+1,ny) / (nx,ny+1) shape.
+ * Result ends in x (tmp is scratch). */
+int nf_momentum_jacobi(nf_ctx*, const nf_grid*, int is_u, nf_links L, double* x, double* tmp, int n_sweeps);
+/* r = b - A x (field_out, with the reference's boundary zeroing) and ||r_masked||/(||b_masked||+1e-15) */
+int nf_momentum_residual(nf_ctx*, const nf_grid*, int is_u, nf_links L, const double* x, double* field_out,
+                         double* rel_norm_host);
+
+/* ---- K16/K17 corrections: velocity_solver/standard.py:10-69, Algorithms/simple.py:148-150,
+ *      Algorithms/base_algorithm.py:161-197 ------------------------------------------------- */
+int nf_correct_velocity(nf_ctx*, const nf_grid*, const nf_bc_program*, const double* u_star,
+                        const double* v_star, const double* p_prime, const double* d_u, const double* d_v,
+                        double* u, double* v);
+int nf_update_pressure(nf_ctx*, const nf_grid*, const double* p_star, const double* p_prime, double alpha_p,
+                       double* p);
+int nf_max_abs_divergence(nf_ctx*, const nf_grid*, const double* u, const double* v, double* out_host);
+
+/* ---- device-resident SIMPLE outer loop: Algorithms/simple.py:78-269 ------------------------ */
+typedef struct nf_simple_config {
+  int32_t nx, ny;
+  int32_t n_momentum_sweeps;    /* JacobiMatrixMomentumSolver(n_jacobi_sweeps)                          */
+  int32_t pressure_solver;      /* 0 multigrid, 1 Jacobi, 2 red-black SOR, 3 CG, 4 BiCGSTAB             */
+  int32_t pressure_iterations;  /* fixed iteration count of the Jacobi / SOR pressure solvers          */
+  int32_t sides;                /* boundaries with a registered condition: 1 left 2 right 4 bottom 8 top */
+  int32_t krylov_maxiter;
+  int32_t pad;
+  double length, height, rho, mu;
+  double alpha_p, alpha_u;      /* simple.py:23-76                                                      */
+  double pressure_omega;        /* Jacobi / SOR relaxation                                              */
+  double pressure_tolerance;    /* Krylov atol (matrix_free_BiCGSTAB.py:234-242)                        */
+  nf_bc_program bc;             /* velocity BC program evaluated with the true (nx, ny)                 */
+  nf_mg_config mg;
+} nf_simple_config;
+
+typedef struct nf_simple_info {   /* one record per outer iteration */
+  double u_rel_norm, v_rel_norm;  /* momentum_solver rel_norm (jacobi_matrix_solver.py:246-250)          */
+  double p_rel_norm;              /* pressure solver rel_norm (its own convention)           */
+  double u_abs_res, v_abs_res;    /* sqrt(sum r^2) of the relaxed momentum residual over the interior   */
+  int32_t pressure_iterations;    /* multigrid cycles / Krylov iterations used                          */
+  int32_t pad;
+} nf_simple_info;
+
+int nf_simple_create(nf_ctx*, nf_simple** out, const nf_simple_config* cfg);
+int nf_simple_destroy(nf_simple*);
+int nf_simple_ld(nf_simple*);
+/* device arrays (row pitch nf_simple_ld): which = 0 u, 1 v, 2 p, 3 u_star, 4 v_star, 5 d_u, 6 d_v,
+ * 7 p_prime, 8 b, 9 pressure residual field, 10 u residual field, 11 v residual field */
+double* nf_simple_field(nf_simple*, int which);
+/* host <-> device copies of a field; host arrays are C-contiguous (rows, cols) */
+int nf_simple_upload(nf_simple*, int which, const double* host, int rows, int cols);
+int nf_simple_download(nf_simple*, int which, double* host, int rows, int cols);
+/* runs outer iterations until max(u_rel_norm, v_rel_norm) <= tolerance or n_iterations are done
+ * (simple.py:114); writes one nf_simple_info per iteration, returns the count in *n_done.
+ * tolerance <= 0: no host synchronisation inside the loop. want_fields != 0 also stores the momentum
+ * residual fields. */
+int nf_simple_iterate(nf_simple*, int n_iterations, double tolerance, int want_fields, nf_simple_info* info_host,
+                      int* n_done);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NAVIFLOW_B200_H */

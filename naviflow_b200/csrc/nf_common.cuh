@@ -1,0 +1,192 @@
+// nf_common.cuh -- shared device/host helpers for libnaviflow_b200 (sm_100a, fp64).
+// Compiled with -fmad=false: every expression keeps the reference's (NumPy) operation order and
+// rounding, so elementwise kernels are bit-identical to the reference's CPU arithmetic.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/naviflow_b200.h"
+
+#define NF_SM_COUNT 148  // B200: 2 dies x 74 SMs
+
+struct nf_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool owns_stream = false;
+  // deterministic two-stage reductions: per-block partials + ticket counter + result slots
+  double* partials = nullptr;   // NF_MAX_PARTIALS * NF_MAX_RED doubles
+  unsigned int* ticket = nullptr;
+  double* scalars = nullptr;    // device scalars (64 doubles)
+  double* scalars_host = nullptr;  // pinned mirror
+  int64_t launches = 0;
+  std::string err;
+};
+
+#define NF_MAX_PARTIALS 4096
+#define NF_MAX_RED 4
+#define NF_NUM_SCALARS 64
+
+#define NF_CHECK_CUDA(ctx, expr)                                                        \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                  \
+      return NF_ERR_CUDA;                                                               \
+    }                                                                                   \
+  } while (0)
+
+#define NF_REQUIRE(ctx, cond, msg)                                                      \
+  do {                                                                                  \
+    if (!(cond)) {                                                                      \
+      (ctx)->err = std::string("argument error: ") + (msg);                             \
+      return NF_ERR_ARG;                                                                \
+    }                                                                                   \
+  } while (0)
+
+#define NF_LAUNCH_CHECK(ctx)                                                            \
+  do {                                                                                  \
+    (ctx)->launches++;                                                                  \
+    cudaError_t _e = cudaGetLastError();                                                \
+    if (_e != cudaSuccess) {                                                            \
+      (ctx)->err = std::string("kernel launch: ") + cudaGetErrorString(_e);             \
+      return NF_ERR_CUDA;                                                               \
+    }                                                                                   \
+  } while (0)
+
+// element [i][j] of a field stored from global row g.row0 with pitch g.ld
+__device__ __forceinline__ size_t nf_idx(const nf_grid& g, int i, int j) {
+  return (size_t)(i - g.row0) * (size_t)g.ld + (size_t)j;
+}
+
+// 2-D launch geometry: x along j (contiguous), y along rows
+struct NfLaunch2D {
+  dim3 grid, block;
+};
+static inline NfLaunch2D nf_launch2d(int rows, int cols, int bx = 128, int by = 2) {
+  NfLaunch2D l;
+  l.block = dim3(bx, by, 1);
+  l.grid = dim3((cols + bx - 1) / bx, (rows + by - 1) / by, 1);
+  if (l.grid.x == 0) l.grid.x = 1;
+  if (l.grid.y == 0) l.grid.y = 1;
+  return l;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Deterministic grid reduction of up to NF_MAX_RED sums.
+// Each block reduces its threads' values in a fixed tree (warp shuffles, then warp 0), writes one
+// partial per sum, takes a ticket; the last block sums the partials in index order and stores the
+// results to out[0..NRED).  Same launch geometry => bit-identical result run to run.
+// ---------------------------------------------------------------------------------------------
+template <int NRED>
+__device__ __forceinline__ bool nf_block_reduce_store(double (&val)[NRED], double* partials,
+                                                      unsigned int* ticket, double* out) {
+  __shared__ double s_warp[NRED][32];
+  __shared__ bool s_last;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const int nthreads = blockDim.x * blockDim.y;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int nwarps = (nthreads + 31) >> 5;
+#pragma unroll
+  for (int k = 0; k < NRED; ++k) {
+    double v = val[k];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    if (lane == 0) s_warp[k][warp] = v;
+  }
+  __syncthreads();
+  const int nblocks = gridDim.x * gridDim.y;
+  const int bid = blockIdx.y * gridDim.x + blockIdx.x;
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < NRED; ++k) {
+      double v = (lane < nwarps) ? s_warp[k][lane] : 0.0;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+      if (lane == 0) partials[(size_t)k * NF_MAX_PARTIALS + bid] = v;
+    }
+    if (lane == 0) {
+      __threadfence();
+      unsigned int t = atomicAdd(ticket, 1u);
+      s_last = (t == (unsigned int)(nblocks - 1));
+    }
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    // fixed-order final sum: thread t accumulates partials t, t+T, ...; then the same tree
+#pragma unroll
+    for (int k = 0; k < NRED; ++k) {
+      double v = 0.0;
+      for (int b = tid; b < nblocks; b += nthreads)
+        v += ((volatile double*)partials)[(size_t)k * NF_MAX_PARTIALS + b];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+      __syncthreads();
+      if (lane == 0) s_warp[k][warp] = v;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+      for (int k = 0; k < NRED; ++k) {
+        double v = (lane < nwarps) ? s_warp[k][lane] : 0.0;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+        if (lane == 0) out[k] = v;
+      }
+      if (lane == 0) *ticket = 0u;
+    }
+  }
+  // true on exactly one thread: thread 0 of the last block, after out[] holds the final sums
+  return s_last && tid == 0;
+}
+
+// grid for reduction kernels: bounded number of blocks (<= NF_MAX_PARTIALS), grid-stride rows
+static inline NfLaunch2D nf_launch_reduce(int rows, int cols) {
+  NfLaunch2D l;
+  l.block = dim3(128, 2, 1);
+  int gx = (cols + 127) / 128;
+  if (gx < 1) gx = 1;
+  int gy = (rows + 1) / 2;
+  if (gy < 1) gy = 1;
+  int max_gy = NF_MAX_PARTIALS / gx;
+  if (max_gy < 1) max_gy = 1;
+  int target = (NF_SM_COUNT * 8 + gx - 1) / gx;  // ~8 blocks per SM
+  if (target < 1) target = 1;
+  if (gy > target) gy = target;
+  if (gy > max_gy) gy = max_gy;
+  l.grid = dim3(gx, gy, 1);
+  return l;
+}
+
+int nf_read_scalars(nf_ctx* ctx, int first, int count, double* out_host);
+
+// ---- internal launchers (no argument validation; used by the multigrid / Krylov / SIMPLE drivers) ----
+int nf_check_grid(nf_ctx* ctx, const nf_grid* g);
+#define NF_GRID_OK(ctx, g)            \
+  do {                                \
+    int _s = nf_check_grid(ctx, g);   \
+    if (_s != NF_OK) return _s;       \
+  } while (0)
+#define NF_TRY(expr)                  \
+  do {                                \
+    int _s = (expr);                  \
+    if (_s != NF_OK) return _s;       \
+  } while (0)
+
+int nfi_rbsor(nf_ctx*, const nf_grid*, double* p, const double* b, const double* d_u, const double* d_v,
+              double omega, int n_sweeps);
+int nfi_jacobi(nf_ctx*, const nf_grid*, double* p, double* tmp, const double* b, const double* d_u,
+               const double* d_v, double omega, int n_iter);
+int nfi_residual(nf_ctx*, const nf_grid*, const double* p, const double* b, const double* d_u, const double* d_v,
+                 double* r);
+int nfi_apply(nf_ctx*, const nf_grid*, const double* p, const double* d_u, const double* d_v, double* out);
+// sum of squares of x over the cells of g -> device scalar ctx->scalars[slot] (asynchronous)
+int nfi_sumsq_dev(nf_ctx*, const nf_grid*, const double* x, int interior_only, int slot);
+int nfi_fill(nf_ctx*, double* x, size_t count, double value);
+int nfi_restrict_fw(nf_ctx*, const nf_grid* fine, const double* f, const nf_grid* coarse, double* c);
+int nfi_restrict_inject(nf_ctx*, const nf_grid* fine, const double* f, const nf_grid* coarse, double* c);
+int nfi_restrict_coeffs(nf_ctx*, const nf_grid* fine, const double* d_u, const double* d_v, const nf_grid* coarse,
+                        double* d_u_c, double* d_v_c);
+int nfi_prolong_linear(nf_ctx*, const nf_grid* coarse, const double* c, const nf_grid* fine, double* f, int add);

@@ -1,0 +1,260 @@
+// nf_transfer.cu -- multigrid transfer operators K9-K12 (fp64, HBM-bound gathers).
+//
+// Reference arithmetic (paths relative to /root/reference/naviflow_oo):
+//   K9  restrict_full_weighting / restrict_inject   pressure_solver/helpers/multigrid_helpers.py:8-70
+//   K10 restrict_coefficients                       pressure_solver/helpers/multigrid_helpers.py:196-329
+//   K11 interpolate_linear                          pressure_solver/helpers/multigrid_helpers.py:73-192
+//   K12 interpolate_cubic (separable not-a-knot spline, applied as a banded operator P C P^T)
+//                                                   pressure_solver/helpers/multigrid_helpers.py:333-391
+// The index rules are the reference's own (coarse k <-> fine 2k+1, the (nf-1)//2 coarse size, the
+// untouched last rows/cols on even-sized fine grids); they are reproduced, not "cleaned up".
+#include "nf_pressure.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// K9  full weighting: c[I,J] = f[2I+1,2J+1]/4 + (N+S+E+W)/8 + (NE+NW+SE+SW)/16   (:63-68)
+//     with N=(2I+1,2J+2) S=(2I+1,2J) E=(2I+2,2J+1) W=(2I,2J+1) NE=(2I+2,2J+2) NW=(2I,2J+2)
+//     SE=(2I+2,2J) SW=(2I,2J); coarse size (nf-1)//2.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double nf_fw_cell(const nf_grid& gf, const double* __restrict__ f, int I, int J) {
+  const size_t k = nf_idx(gf, 2 * I + 1, 2 * J + 1);
+  const size_t ld = gf.ld;
+  const double c = f[k];
+  const double n = f[k + 1], s = f[k - 1], e = f[k + ld], w = f[k - ld];
+  const double ne = f[k + ld + 1], nw = f[k - ld + 1], se = f[k + ld - 1], sw = f[k - ld - 1];
+  return (c / 4.0 + (((n + s) + e) + w) / 8.0) + (((ne + nw) + se) + sw) / 16.0;
+}
+
+__global__ void k_restrict_fw(nf_grid gf, const double* __restrict__ f, nf_grid gc, double* __restrict__ c) {
+  const int J = blockIdx.x * blockDim.x + threadIdx.x;
+  const int I = gc.gb + blockIdx.y * blockDim.y + threadIdx.y;
+  if (J >= gc.ny || I >= gc.ge) return;
+  c[nf_idx(gc, I, J)] = nf_fw_cell(gf, f, I, J);
+}
+
+// fused: c = FW(b - A p) without materialising the fine residual (9 fine A*p evaluations per coarse
+// cell; neighbours come from L1/L2).  Saves the 16 B/fine-cell write+read of r.
+__global__ void k_residual_restrict_fw(nf_grid gf, const double* __restrict__ p, const double* __restrict__ b,
+                                       const double* __restrict__ d_u, const double* __restrict__ d_v,
+                                       nf_grid gc, double* __restrict__ c) {
+  const int J = blockIdx.x * blockDim.x + threadIdx.x;
+  const int I = gc.gb + blockIdx.y * blockDim.y + threadIdx.y;
+  if (J >= gc.ny || I >= gc.ge) return;
+  double r[3][3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const int i = 2 * I + a, j = 2 * J + q;
+      r[a][q] = b[nf_idx(gf, i, j)] - nf_Ap_cell(gf, p, d_u, d_v, i, j);
+    }
+  const double cc = r[1][1], n = r[1][2], s = r[1][0], e = r[2][1], w = r[0][1];
+  const double ne = r[2][2], nw = r[0][2], se = r[2][0], sw = r[0][0];
+  c[nf_idx(gc, I, J)] = (cc / 4.0 + (((n + s) + e) + w) / 8.0) + (((ne + nw) + se) + sw) / 16.0;
+}
+
+// injection: c[I,J] = f[2I+1,2J+1]; coarse size nf//2  (:20)
+__global__ void k_restrict_inject(nf_grid gf, const double* __restrict__ f, nf_grid gc, double* __restrict__ c) {
+  const int J = blockIdx.x * blockDim.x + threadIdx.x;
+  const int I = gc.gb + blockIdx.y * blockDim.y + threadIdx.y;
+  if (J >= gc.ny || I >= gc.ge) return;
+  c[nf_idx(gc, I, J)] = f[nf_idx(gf, 2 * I + 1, 2 * J + 1)];
+}
+
+// ---------------------------------------------------------------------------------------------
+// K10 coefficient coarsening (:229-327): harmonic mean of the two fine faces (arithmetic mean unless
+//     both are > 0), boundary faces copied, everything x0.25; entries the reference never writes are 0.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double nf_hmean(double d1, double d2) {
+  if (d1 > 0.0 && d2 > 0.0) return 2.0 / (1.0 / d1 + 1.0 / d2);
+  return 0.5 * (d1 + d2);
+}
+
+__global__ void k_restrict_coeffs(nf_grid gf, const double* __restrict__ d_u, const double* __restrict__ d_v,
+                                  nf_grid gc, double* __restrict__ duc, double* __restrict__ dvc) {
+  // thread (I,J) over the (nxc+1) x (nyc+1) index box: writes duc[I,J] (J<nyc) and dvc[I,J] (I<nxc)
+  const int J = blockIdx.x * blockDim.x + threadIdx.x;
+  const int I = gc.gb + blockIdx.y * blockDim.y + threadIdx.y;
+  const int nxc = gc.nx, nyc = gc.ny;
+  const int i_end = (gc.ge == nxc) ? nxc + 1 : gc.ge;  // the rank owning the last cell row also owns face row nxc
+  if (J > nyc || I >= i_end) return;
+  if (J < nyc) {  // d_u^c (nxc+1, nyc)
+    double val = 0.0;
+    if (2 * J < gf.ny) {
+      if (I == 0) val = d_u[nf_idx(gf, 0, 2 * J)];
+      else if (I == nxc) val = d_u[nf_idx(gf, gf.nx, 2 * J)];
+      else if (2 * I < gf.nx) val = nf_hmean(d_u[nf_idx(gf, 2 * I, 2 * J)], d_u[nf_idx(gf, 2 * I + 1, 2 * J)]);
+    }
+    duc[nf_idx(gc, I, J)] = val * 0.25;
+  }
+  if (I < nxc) {  // d_v^c (nxc, nyc+1)
+    double val = 0.0;
+    if (2 * I < gf.nx) {
+      if (J == 0) val = d_v[nf_idx(gf, 2 * I, 0)];
+      else if (J == nyc) val = d_v[nf_idx(gf, 2 * I, gf.ny)];
+      else if (2 * J < gf.ny) val = nf_hmean(d_v[nf_idx(gf, 2 * I, 2 * J)], d_v[nf_idx(gf, 2 * I, 2 * J + 1)]);
+    }
+    dvc[nf_idx(gc, I, J)] = val * 0.25;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K11 bilinear prolongation (:116-186) as a gather.  Interior value V(i,j), 1<=i,j<=m-2:
+//       i odd  -> coarse I=(i-1)/2 (needs I<mc);  i even -> between I=(i-2)/2 and I+1 (needs I<=mc-2)
+//     points outside those rules stay 0 (last two rows/cols of an even-sized fine grid).
+//     Ring cells copy ring 1: f[i,j] = V(clamp(i,1,m-2), clamp(j,1,m-2))  (:170-186).
+//     m <= 3: only the coincident points, no ring copy (:127-128).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double nf_prolong_linear_value(const nf_grid& gc, const double* __restrict__ c,
+                                                          int mx, int my, int i, int j) {
+  const int mcx = gc.nx, mcy = gc.ny;
+  if (mx <= 3 || my <= 3) {
+    if ((i & 1) && (j & 1) && (i - 1) / 2 < mcx && (j - 1) / 2 < mcy) return c[nf_idx(gc, (i - 1) / 2, (j - 1) / 2)];
+    return 0.0;
+  }
+  i = min(max(i, 1), mx - 2);
+  j = min(max(j, 1), my - 2);
+  const bool io = i & 1, jo = j & 1;
+  const int I = io ? (i - 1) / 2 : (i - 2) / 2;
+  const int J = jo ? (j - 1) / 2 : (j - 2) / 2;
+  const bool iok = io ? (I < mcx) : (I <= mcx - 2);
+  const bool jok = jo ? (J < mcy) : (J <= mcy - 2);
+  if (!iok || !jok) return 0.0;
+  const size_t k = nf_idx(gc, I, J);
+  if (io && jo) return c[k];
+  if (io && !jo) return 0.5 * (c[k] + c[k + 1]);
+  if (!io && jo) return 0.5 * (c[k] + c[k + gc.ld]);
+  return 0.25 * (((c[k] + c[k + gc.ld]) + c[k + 1]) + c[k + gc.ld + 1]);
+}
+
+template <bool ADD>
+__global__ void k_prolong_linear(nf_grid gc, const double* __restrict__ c, nf_grid gf, double* __restrict__ f) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = gf.gb + blockIdx.y * blockDim.y + threadIdx.y;
+  if (j >= gf.ny || i >= gf.ge) return;
+  const double v = nf_prolong_linear_value(gc, c, gf.nx, gf.ny, i, j);
+  const size_t k = nf_idx(gf, i, j);
+  if (ADD) f[k] = f[k] + v;
+  else f[k] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K12 "cubic" prolongation F = P C P^T with P (m x mc) the 1-D interpolation matrix of the reference's
+//     interpolator (not-a-knot cubic spline for mc>=4), stored banded: row i holds W taps starting at
+//     coarse column start[i].  Two passes: T = P C  (m x mc), then F (+)= T P^T.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_band_rows(int m, int mc_cols, int ldc, const double* __restrict__ c, int ldt, double* __restrict__ t,
+                            const double* __restrict__ band, const int* __restrict__ start, int W) {
+  // t[i, J] = sum_w band[i,w] * c[start[i]+w, J]
+  const int J = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y * blockDim.y + threadIdx.y;
+  if (J >= mc_cols || i >= m) return;
+  const int s = start[i];
+  const double* bw = band + (size_t)i * W;
+  double acc = 0.0;
+  for (int w = 0; w < W; ++w) acc += bw[w] * c[(size_t)(s + w) * ldc + J];
+  t[(size_t)i * ldt + J] = acc;
+}
+
+template <bool ADD>
+__global__ void k_band_cols(int m_rows, int m_cols, int ldt, const double* __restrict__ t, int ldf,
+                            double* __restrict__ f, const double* __restrict__ band, const int* __restrict__ start,
+                            int W) {
+  // f[i, j] (+)= sum_w band[j,w] * t[i, start[j]+w]
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y * blockDim.y + threadIdx.y;
+  if (j >= m_cols || i >= m_rows) return;
+  const int s = start[j];
+  const double* bw = band + (size_t)j * W;
+  const double* tr = t + (size_t)i * ldt + s;
+  double acc = 0.0;
+  for (int w = 0; w < W; ++w) acc += bw[w] * tr[w];
+  const size_t k = (size_t)i * ldf + j;
+  if (ADD) f[k] = f[k] + acc;
+  else f[k] = acc;
+}
+
+// =============================================================================================
+// host entry points
+// =============================================================================================
+int nfi_restrict_fw(nf_ctx* ctx, const nf_grid* gf, const double* f, const nf_grid* gc, double* c) {
+  NfLaunch2D l = nf_launch2d(gc->ge - gc->gb, gc->ny);
+  k_restrict_fw<<<l.grid, l.block, 0, ctx->stream>>>(*gf, f, *gc, c);
+  NF_LAUNCH_CHECK(ctx);
+  return NF_OK;
+}
+
+int nfi_residual_restrict_fw(nf_ctx* ctx, const nf_grid* gf, const double* p, const double* b, const double* d_u,
+                             const double* d_v, const nf_grid* gc, double* c) {
+  NfLaunch2D l = nf_launch2d(gc->ge - gc->gb, gc->ny, 64, 4);
+  k_residual_restrict_fw<<<l.grid, l.block, 0, ctx->stream>>>(*gf, p, b, d_u, d_v, *gc, c);
+  NF_LAUNCH_CHECK(ctx);
+  return NF_OK;
+}
+
+int nfi_restrict_inject(nf_ctx* ctx, const nf_grid* gf, const double* f, const nf_grid* gc, double* c) {
+  NfLaunch2D l = nf_launch2d(gc->ge - gc->gb, gc->ny);
+  k_restrict_inject<<<l.grid, l.block, 0, ctx->stream>>>(*gf, f, *gc, c);
+  NF_LAUNCH_CHECK(ctx);
+  return NF_OK;
+}
+
+int nfi_restrict_coeffs(nf_ctx* ctx, const nf_grid* gf, const double* d_u, const double* d_v, const nf_grid* gc,
+                        double* duc, double* dvc) {
+  NfLaunch2D l = nf_launch2d(gc->ge - gc->gb + 1, gc->ny + 1);
+  k_restrict_coeffs<<<l.grid, l.block, 0, ctx->stream>>>(*gf, d_u, d_v, *gc, duc, dvc);
+  NF_LAUNCH_CHECK(ctx);
+  return NF_OK;
+}
+
+int nfi_prolong_linear(nf_ctx* ctx, const nf_grid* gc, const double* c, const nf_grid* gf, double* f, int add) {
+  NfLaunch2D l = nf_launch2d(gf->ge - gf->gb, gf->ny);
+  if (add) k_prolong_linear<true><<<l.grid, l.block, 0, ctx->stream>>>(*gc, c, *gf, f);
+  else k_prolong_linear<false><<<l.grid, l.block, 0, ctx->stream>>>(*gc, c, *gf, f);
+  NF_LAUNCH_CHECK(ctx);
+  return NF_OK;
+}
+
+int nfi_prolong_banded(nf_ctx* ctx, const nf_grid* gc, const double* c, const nf_grid* gf, double* f, double* tmp,
+                       int ldt, const double* band, const int* start, int W, int add) {
+  // tmp: gf->nx rows x ldt (>= gc->ny)
+  NfLaunch2D l1 = nf_launch2d(gf->nx, gc->ny);
+  k_band_rows<<<l1.grid, l1.block, 0, ctx->stream>>>(gf->nx, gc->ny, gc->ld, c, ldt, tmp, band, start, W);
+  NF_LAUNCH_CHECK(ctx);
+  NfLaunch2D l2 = nf_launch2d(gf->nx, gf->ny);
+  if (add) k_band_cols<true><<<l2.grid, l2.block, 0, ctx->stream>>>(gf->nx, gf->ny, ldt, tmp, gf->ld, f, band, start, W);
+  else k_band_cols<false><<<l2.grid, l2.block, 0, ctx->stream>>>(gf->nx, gf->ny, ldt, tmp, gf->ld, f, band, start, W);
+  NF_LAUNCH_CHECK(ctx);
+  return NF_OK;
+}
+
+static int check_pair(nf_ctx* ctx, const nf_grid* gf, const nf_grid* gc) {
+  NF_REQUIRE(ctx, gf && gc, "grid is NULL");
+  NF_REQUIRE(ctx, gf->nx >= 3 && gf->ny >= 3 && gc->nx >= 1 && gc->ny >= 1, "grid too small");
+  NF_REQUIRE(ctx, gf->ld >= gf->ny + 1 && gc->ld >= gc->ny + 1, "ld must be >= ny+1");
+  return NF_OK;
+}
+
+extern "C" int nf_restrict_fw(nf_ctx* ctx, const nf_grid* gf, const double* f, const nf_grid* gc, double* c) {
+  NF_TRY(check_pair(ctx, gf, gc));
+  NF_REQUIRE(ctx, gc->nx == (gf->nx - 1) / 2 && gc->ny == (gf->ny - 1) / 2, "coarse size must be (nf-1)//2");
+  return nfi_restrict_fw(ctx, gf, f, gc, c);
+}
+
+extern "C" int nf_restrict_inject(nf_ctx* ctx, const nf_grid* gf, const double* f, const nf_grid* gc, double* c) {
+  NF_TRY(check_pair(ctx, gf, gc));
+  NF_REQUIRE(ctx, gc->nx == gf->nx / 2 && gc->ny == gf->ny / 2, "coarse size must be nf//2");
+  return nfi_restrict_inject(ctx, gf, f, gc, c);
+}
+
+extern "C" int nf_restrict_coeffs(nf_ctx* ctx, const nf_grid* gf, const double* d_u, const double* d_v,
+                                  const nf_grid* gc, double* duc, double* dvc) {
+  NF_TRY(check_pair(ctx, gf, gc));
+  NF_REQUIRE(ctx, 2 * gc->nx <= gf->nx && 2 * gc->ny <= gf->ny, "coarse grid larger than nf//2");
+  return nfi_restrict_coeffs(ctx, gf, d_u, d_v, gc, duc, dvc);
+}
+
+extern "C" int nf_prolong_linear(nf_ctx* ctx, const nf_grid* gc, const double* c, const nf_grid* gf, double* f,
+                                 int add) {
+  NF_TRY(check_pair(ctx, gf, gc));
+  return nfi_prolong_linear(ctx, gc, c, gf, f, add);
+}

@@ -1,0 +1,229 @@
+"""GpuSimpleSolver -- the SIMPLE outer loop, device resident.
+
+Twin of ``SimpleSolver(BaseAlgorithm)`` (solver/Algorithms/simple.py:16-269, base_algorithm.py:13-235 of
+/root/reference/naviflow_oo): same constructor, ``set_boundary_condition``, ``solve`` signature, result
+histories (``u_rel_norm``, ``v_rel_norm``, ``p_rel_norm``, ``total_rel_norm``) and stopping test
+(``max(u_rel_norm, v_rel_norm) > tolerance``).  The whole iteration runs in libnaviflow_b200
+(``nf_simple_iterate``): fields are uploaded once at ``solve()`` entry and downloaded once at exit.
+
+The plugin objects select the device kernels:
+  momentum_solver  GpuJacobiMomentumSolver(n_jacobi_sweeps)        -> fixed Jacobi sweeps
+  pressure_solver  GpuMultiGridSolver | GpuJacobiSolver | GpuGaussSeidelSolver | GpuCGSolver | GpuBiCGSTABSolver
+  velocity_updater GpuVelocityUpdater (or None)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+
+import numpy as np
+
+from ._lib import NfSimpleConfig, NfSimpleInfo
+from .device import bc_program_struct, get_context, mesh_scalars
+from .host import BoundaryConditionManager, SimulationResult, ghia_errors, practice_b_sides
+from .momentum import GpuJacobiMomentumSolver
+from .pressure import (GpuBiCGSTABSolver, GpuCGSolver, GpuGaussSeidelSolver, GpuJacobiSolver,
+                       GpuMultiGridSolver)
+from .velocity import GpuVelocityUpdater
+
+_FIELD = {"u": 0, "v": 1, "p": 2, "u_star": 3, "v_star": 4, "d_u": 5, "d_v": 6, "p_prime": 7, "b": 8,
+          "p_res": 9, "u_res": 10, "v_res": 11}
+
+
+class GpuSimpleSolver:
+    def __init__(self, mesh, fluid, pressure_solver=None, momentum_solver=None, velocity_updater=None,
+                 boundary_conditions=None, alpha_p=0.3, alpha_u=0.7, fix_lid_corners=False, device=None):
+        self.mesh, self.fluid = mesh, fluid
+        self.pressure_solver = pressure_solver
+        self.momentum_solver = momentum_solver if momentum_solver is not None else GpuJacobiMomentumSolver()
+        self.velocity_updater = velocity_updater if velocity_updater is not None else GpuVelocityUpdater()
+        self.alpha_p, self.alpha_u = alpha_p, alpha_u
+        self.fix_lid_corners = fix_lid_corners
+        if boundary_conditions is not None and hasattr(boundary_conditions, "apply_velocity_boundary_conditions"):
+            self.bc_manager = boundary_conditions
+        else:
+            self.bc_manager = BoundaryConditionManager()
+            if isinstance(boundary_conditions, dict):
+                for loc, conds in boundary_conditions.items():
+                    for typ, vals in conds.items():
+                        self.bc_manager.set_condition(loc, typ, vals)
+        self.boundary_conditions = self.bc_manager.to_dict()
+        self.profiler = None
+        self.residual_history = []
+        self._device = device
+        self._state = None
+        self._state_key = None
+        self._final_u_residual_field = self._final_v_residual_field = self._final_p_residual_field = None
+        self.initialize_fields()
+
+    # ---- BaseAlgorithm interface ------------------------------------------------------------------
+    def initialize_fields(self):
+        nx, ny = self.mesh.get_dimensions()
+        self.p = np.zeros((nx, ny))
+        self.u = np.zeros((nx + 1, ny))
+        self.v = np.zeros((nx, ny + 1))
+        self.apply_boundary_conditions()
+
+    def apply_boundary_conditions(self):
+        nx, ny = self.mesh.get_dimensions()
+        self.u, self.v = self.bc_manager.apply_velocity_boundary_conditions(self.u, self.v, nx, ny)
+
+    def set_boundary_condition(self, boundary, condition_type, values=None):
+        self.bc_manager.set_condition(boundary, condition_type, values)
+        self.boundary_conditions = self.bc_manager.to_dict()
+        self.apply_boundary_conditions()
+
+    def get_max_divergence(self):
+        dx, dy = self.mesh.get_cell_sizes()
+        div = (self.u[1:, :] - self.u[:-1, :]) / dx + (self.v[:, 1:] - self.v[:, :-1]) / dy
+        return float(np.max(np.abs(div[1:-1, 1:-1])))
+
+    # ---- device state -----------------------------------------------------------------------------
+    def _config(self):
+        nx, ny, dx, dy, length, height = mesh_scalars(self.mesh)
+        c = NfSimpleConfig()
+        c.nx, c.ny = nx, ny
+        ms = self.momentum_solver
+        if not isinstance(ms, GpuJacobiMomentumSolver):
+            raise TypeError("GpuSimpleSolver needs a GpuJacobiMomentumSolver (fixed Jacobi sweeps on the device)")
+        c.n_momentum_sweeps = ms.n_jacobi_sweeps
+        ps = self.pressure_solver
+        c.krylov_maxiter = 0
+        c.pressure_iterations = 0
+        c.pressure_omega = 1.0
+        c.pressure_tolerance = 0.0
+        if isinstance(ps, GpuMultiGridSolver):
+            c.pressure_solver = 0
+            c.mg = ps.config_struct(length, height)
+        elif isinstance(ps, (GpuJacobiSolver, GpuGaussSeidelSolver)):
+            if ps.tolerance > 0:
+                raise NotImplementedError(
+                    "device-resident Jacobi / SOR pressure solves run a fixed number of iterations: pass tolerance=0")
+            c.pressure_solver = 1 if isinstance(ps, GpuJacobiSolver) else 2
+            c.pressure_iterations = int(ps.max_iterations)
+            c.pressure_omega = float(ps.omega)
+        elif isinstance(ps, (GpuCGSolver, GpuBiCGSTABSolver)):
+            c.pressure_solver = 3 if isinstance(ps, GpuCGSolver) else 4
+            c.krylov_maxiter = int(ps.max_iterations)
+            c.pressure_tolerance = float(ps.tolerance)
+        else:
+            raise TypeError("pressure_solver must be one of the naviflow_b200 Gpu*Solver classes")
+        c.sides = practice_b_sides(self.bc_manager)
+        c.length, c.height = length, height
+        c.rho, c.mu = float(self.fluid.get_density()), float(self.fluid.get_viscosity())
+        c.alpha_p, c.alpha_u = float(self.alpha_p), float(self.alpha_u)
+        c.bc = bc_program_struct(self.bc_manager, nx, ny)
+        return c
+
+    def _ensure_state(self):
+        ctx = get_context(self._device)
+        cfg = self._config()
+        key = bytes(cfg)
+        if self._state is None or key != self._state_key:
+            self._free()
+            h = C.c_void_p()
+            ctx.check(ctx.lib.nf_simple_create(ctx.handle, C.byref(h), C.byref(cfg)), "nf_simple_create")
+            self._state, self._state_key = h, key
+        return ctx, self._state
+
+    def _free(self):
+        if self._state is not None:
+            get_context(self._device).lib.nf_simple_destroy(self._state)
+            self._state, self._state_key = None, None
+
+    def __del__(self):
+        try:
+            self._free()
+        except Exception:
+            pass
+
+    def _upload(self, ctx, st, name, arr):
+        a = np.ascontiguousarray(arr, dtype=np.float64)
+        ctx.check(ctx.lib.nf_simple_upload(st, _FIELD[name], a.ctypes.data_as(C.c_void_p), a.shape[0], a.shape[1]),
+                  "nf_simple_upload")
+
+    def _download(self, ctx, st, name, rows, cols):
+        out = np.empty((rows, cols), dtype=np.float64)
+        ctx.check(ctx.lib.nf_simple_download(st, _FIELD[name], out.ctypes.data_as(C.c_void_p), rows, cols),
+                  "nf_simple_download")
+        return out
+
+    def device_field(self, name):
+        """Raw device pointer of a resident field (after the first solve())."""
+        ctx, st = self._ensure_state()
+        return ctx.lib.nf_simple_field(st, _FIELD[name])
+
+    def iterate_resident(self, n_iterations, tolerance=0.0, want_fields=False):
+        """Runs outer iterations on the resident state without touching the host fields.  Returns the list
+        of per-iteration records (dicts).  Used by solve() and by bench.py."""
+        ctx, st = self._ensure_state()
+        infos = (NfSimpleInfo * max(n_iterations, 1))()
+        done = C.c_int(0)
+        ctx.check(ctx.lib.nf_simple_iterate(st, int(n_iterations), float(tolerance), 1 if want_fields else 0, infos,
+                                            C.byref(done)), "nf_simple_iterate")
+        return [dict(u_rel_norm=r.u_rel_norm, v_rel_norm=r.v_rel_norm, p_rel_norm=r.p_rel_norm,
+                     u_abs_res=r.u_abs_res, v_abs_res=r.v_abs_res, pressure_iterations=r.pressure_iterations)
+                for r in infos[: done.value]]
+
+    def push_fields(self):
+        ctx, st = self._ensure_state()
+        for name in ("u", "v", "p"):
+            self._upload(ctx, st, name, getattr(self, name))
+
+    def pull_fields(self):
+        ctx, st = self._ensure_state()
+        nx, ny = self.mesh.get_dimensions()
+        self.u = self._download(ctx, st, "u", nx + 1, ny)
+        self.v = self._download(ctx, st, "v", nx, ny + 1)
+        self.p = self._download(ctx, st, "p", nx, ny)
+
+    # ---- SimpleSolver.solve -----------------------------------------------------------------------
+    def solve(self, max_iterations=1000, tolerance=1e-6, save_profile=False, profile_dir="results/profiles",
+              track_infinity_norm=False, infinity_norm_interval=10, use_l2_norm=False, chunk=None):
+        if save_profile:
+            raise NotImplementedError("HDF5 profile output is out of scope (SURVEY.md section 2, row 12)")
+        t0 = time.perf_counter()
+        ctx, st = self._ensure_state()
+        nx, ny = self.mesh.get_dimensions()
+        self.push_fields()
+        self.residual_history = []
+        self.x_momentum_rel_norms, self.y_momentum_rel_norms, self.pressure_rel_norms = [], [], []
+        self.infinity_norm_history = []
+        self.pressure_iterations_history = []
+        iteration = 1
+        total = 1.0
+        if chunk is None:
+            chunk = infinity_norm_interval if track_infinity_norm else (1 if tolerance > 0 else max_iterations)
+        try:
+            while iteration <= max_iterations and total > tolerance:
+                n = min(chunk, max_iterations - iteration + 1)
+                recs = self.iterate_resident(n, tolerance, want_fields=False)
+                for r in recs:
+                    total = max(r["u_rel_norm"], r["v_rel_norm"])
+                    self.x_momentum_rel_norms.append(r["u_rel_norm"])
+                    self.y_momentum_rel_norms.append(r["v_rel_norm"])
+                    self.pressure_rel_norms.append(r["p_rel_norm"])
+                    self.pressure_iterations_history.append(r["pressure_iterations"])
+                    self.residual_history.append(total)
+                    self.residual_history.append(total)  # the reference appends twice (simple.py:177, :196)
+                iteration += len(recs)
+                if track_infinity_norm and (iteration - 1) % infinity_norm_interval == 0:
+                    self.pull_fields()
+                    inf, l2 = ghia_errors(self.u, self.v, self.mesh, self.fluid.get_reynolds_number())
+                    self.infinity_norm_history.append(l2 if use_l2_norm else inf)
+                if len(recs) < n:
+                    break
+        except KeyboardInterrupt:
+            print("Interrupted by user.")
+        self.pull_fields()
+        self._final_p_residual_field = self._download(ctx, st, "p_res", nx, ny)
+        result = SimulationResult(self.u, self.v, self.p, self.mesh, iterations=iteration - 1,
+                                  residuals=self.residual_history, reynolds=self.fluid.get_reynolds_number(),
+                                  wall_time=time.perf_counter() - t0)
+        result.add_history("u_rel_norm", self.x_momentum_rel_norms)
+        result.add_history("v_rel_norm", self.y_momentum_rel_norms)
+        result.add_history("p_rel_norm", self.pressure_rel_norms)
+        result.add_history("total_rel_norm", self.residual_history)
+        if self.infinity_norm_history:
+            result.add_history("infinity_norm_error", self.infinity_norm_history)
+        return result

@@ -1,0 +1,229 @@
+"""GPU parity, tiers T1/T2: pressure solvers and the whole SIMPLE loop through the plugin classes,
+against the reference's outputs in tests/golden (mg_n*.npz, simple_runs.npz) and the NumPy oracle."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import np_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300)
+
+
+def load(golden_dir, name):
+    return dict(np.load(os.path.join(golden_dir, name)))
+
+
+def cavity(n, Re):
+    import naviflow_b200 as nb
+    mesh = nb.StructuredMesh(n, n, 1.0, 1.0)
+    fluid = nb.FluidProperties(density=1.0, reynolds_number=Re, characteristic_velocity=1.0)
+    return mesh, fluid
+
+
+MG_CASES = {
+    "v_lin_fw": dict(cycle_type="v", max_iterations=3, tolerance=1e-14),
+    "v_cub_fw": dict(cycle_type="v", max_iterations=2, tolerance=1e-14, interpolation_method="interpolate_cubic"),
+    "w_lin_fw": dict(cycle_type="w", max_iterations=2, tolerance=1e-14),
+    "fmg_cub_v": dict(cycle_type="fmg", cycle_type_final="v", max_iterations=100, tolerance=1e-3,
+                      interpolation_method="interpolate_cubic"),
+    "v_tol": dict(cycle_type="v", max_iterations=100, tolerance=1e-3),
+    "v_lin_inject": dict(cycle_type="v", max_iterations=2, tolerance=1e-14, restriction_method="restrict_inject"),
+}
+
+
+@pytest.mark.parametrize("n", [31, 33, 64])
+def test_multigrid_vs_reference_golden(golden_dir, n):
+    import naviflow_b200 as nb
+    g = load(golden_dir, f"mg_n{n}.npz")
+    mesh, _ = cavity(n, 1000)
+    for name, kw in MG_CASES.items():
+        if name + "_p" not in g:
+            continue
+        ps = nb.GpuMultiGridSolver(smoother=nb.GpuGaussSeidelSolver(omega=1.5, method_type="red_black"),
+                                   pre_smoothing=3, post_smoothing=3, coarsest_grid_size=7, **kw)
+        p, info = ps.solve(mesh, g["u_star"], g["v_star"], g["d_u"], g["d_v"], None)
+        assert rel(p, g[name + "_p"]) < 1e-11, (name, rel(p, g[name + "_p"]))
+        assert abs(info["rel_norm"] - g[name + "_relnorm"]) <= 1e-9 * g[name + "_relnorm"], name
+        if name == "v_tol":
+            assert ps.last_info.cycles == int(g[name + "_ncycles"])
+    ps = nb.GpuMultiGridSolver(smoother=nb.GpuJacobiSolver(omega=0.8), max_iterations=2, tolerance=1e-14,
+                               pre_smoothing=2, post_smoothing=2)
+    p, _ = ps.solve(mesh, g["u_star"], g["v_star"], g["d_u"], g["d_v"], None)
+    assert rel(p, g["v_jacobi_smoother_p"]) < 1e-11
+
+
+@pytest.mark.parametrize("n", [31, 33, 64])
+def test_bicgstab_vs_reference_golden(golden_dir, n):
+    import naviflow_b200 as nb
+    g = load(golden_dir, f"mg_n{n}.npz")
+    mesh, _ = cavity(n, 1000)
+    bs = nb.GpuBiCGSTABSolver(tolerance=1e-7, max_iterations=1000, check_every=7)
+    p, info = bs.solve(mesh, g["u_star"], g["v_star"], g["d_u"], g["d_v"], None)
+    # same stopping iteration as scipy; iterates agree to the conditioning of the recurrence
+    assert bs.last_info.info == 0
+    assert abs(bs.last_info.iterations - int(g["bicgstab_iters"])) <= 2
+    assert rel(p, g["bicgstab_p"]) < 1e-6
+    assert info["rel_norm"] < 2e-5
+
+
+@pytest.mark.parametrize("n,kind", [(31, "cg"), (64, "cg"), (31, "bicgstab"), (65, "bicgstab")])
+def test_krylov_iterates_vs_oracle(n, kind):
+    """First k iterations against scipy's operation order restated in the oracle (T1: 1e-10)."""
+    import naviflow_b200 as nb
+    from oracle.make_golden import synth_pressure_inputs
+    s = synth_pressure_inputs(n, 500 + n)
+    mesh, _ = cavity(n, 1000)
+    dx = dy = 1.0 / (n - 1)
+    b = O.continuity_rhs(n, n, dx, dy, 1.0, s["u_star"], s["v_star"])
+    mv = lambda z: O.apply_A(z, dx, dy, 1.0, s["d_u"], s["d_v"])
+    for k in (1, 5, 20):
+        fn = O.cg if kind == "cg" else O.bicgstab
+        x_ref, info_ref, it_ref = fn(mv, b, atol=0.0, rtol=0.0, maxiter=k)
+        cls = nb.GpuCGSolver if kind == "cg" else nb.GpuBiCGSTABSolver
+        sol = cls(tolerance=0.0, max_iterations=k)
+        ctx = sol.ctx
+        # rtol is fixed at scipy's default 1e-5 in the plugin; call the C-ABI directly for rtol = 0
+        import ctypes as C
+        from naviflow_b200._lib import NfKrylovInfo
+        from naviflow_b200.device import pad_ld, ptr
+        g, bd, du, dv = sol._stage(n, n, dx, dy, 1.0, s["u_star"], s["v_star"], s["d_u"], s["d_v"])
+        x = ctx.empty(n, n)
+        work = ctx.torch.zeros((sol._nwork * (n + 1), pad_ld(n)), dtype=ctx.torch.float64, device=x.device)
+        info = NfKrylovInfo()
+        ctx.check(getattr(ctx.lib, sol._fn)(ctx.handle, C.byref(g), ptr(bd), ptr(x), ptr(du), ptr(dv), 0.0, 0.0, k, 3,
+                                            ptr(work), C.byref(info)))
+        assert info.iterations == k and info.info == k
+        assert rel(ctx.download(x, n, n), x_ref) < 1e-10, (k, rel(ctx.download(x, n, n), x_ref))
+
+
+@pytest.mark.parametrize("n,kind", [(63, "cg"), (63, "bicgstab")])
+def test_krylov_converges_like_scipy(n, kind):
+    import naviflow_b200 as nb
+    from oracle.make_golden import synth_pressure_inputs
+    s = synth_pressure_inputs(n, 900 + n)
+    mesh, _ = cavity(n, 1000)
+    dx = dy = 1.0 / (n - 1)
+    x_ref, info_ref = O.krylov_pressure_solve(kind, n, n, dx, dy, s["u_star"], s["v_star"], s["d_u"], s["d_v"],
+                                              tol=1e-7, maxiter=5000)
+    cls = nb.GpuCGSolver if kind == "cg" else nb.GpuBiCGSTABSolver
+    sol = cls(tolerance=1e-7, max_iterations=5000)
+    p, info = sol.solve(mesh, s["u_star"], s["v_star"], s["d_u"], s["d_v"], None)
+    assert sol.last_info.info == 0 and info_ref["info"] == 0
+    assert abs(sol.last_info.iterations - info_ref["iterations"]) <= max(3, 0.05 * info_ref["iterations"])
+    assert info["rel_norm"] < 2e-5
+    assert rel(p, x_ref) < 1e-3
+
+
+def make_ps(name):
+    import naviflow_b200 as nb
+    GS = nb.GpuGaussSeidelSolver
+    if name == "fmg":
+        return nb.GpuMultiGridSolver(smoother=GS(omega=1.5, method_type="red_black"), max_iterations=100,
+                                     tolerance=1e-3, pre_smoothing=3, post_smoothing=3, cycle_type="fmg",
+                                     cycle_type_buildup="v", cycle_type_final="v", max_cycles_buildup=1,
+                                     restriction_method="restrict_full_weighting",
+                                     interpolation_method="interpolate_cubic", coarsest_grid_size=7)
+    if name == "v":
+        return nb.GpuMultiGridSolver(smoother=GS(omega=1.5, method_type="red_black"), max_iterations=100,
+                                     tolerance=1e-3, pre_smoothing=3, post_smoothing=3)
+    if name == "jacobi":
+        return nb.GpuJacobiSolver(tolerance=0.0, max_iterations=50, omega=0.8)
+    if name == "rbsor":
+        return GS(tolerance=0.0, max_iterations=30, omega=1.5, method_type="red_black")
+    raise ValueError(name)
+
+
+def run_gpu_simple(n, Re, name, k, N):
+    import naviflow_b200 as nb
+    mesh, fluid = cavity(n, Re)
+    alg = nb.GpuSimpleSolver(mesh, fluid, make_ps(name), nb.GpuJacobiMomentumSolver(n_jacobi_sweeps=k),
+                             nb.GpuVelocityUpdater(), alpha_p=0.3, alpha_u=0.7)
+    alg.set_boundary_condition("top", "velocity", {"u": 1.0, "v": 0.0})
+    for b in ("bottom", "left", "right"):
+        alg.set_boundary_condition(b, "wall")
+    res = alg.solve(max_iterations=N, tolerance=0.0, save_profile=False, track_infinity_norm=False)
+    return alg, res
+
+
+@pytest.mark.parametrize("n,Re,k,N,name", [
+    (31, 100, 5, 40, "fmg"), (31, 100, 5, 40, "v"), (31, 100, 5, 40, "jacobi"), (31, 100, 5, 40, "rbsor"),
+    (63, 1000, 20, 25, "fmg"), (63, 1000, 20, 25, "v"), (64, 1000, 3, 12, "v"), (127, 1000, 5, 8, "v")])
+def test_simple_loop_vs_reference_golden(golden_dir, n, Re, k, N, name):
+    """T2: u, v, p after N outer iterations equal the reference's to 1e-10 relative L2 (BASELINE north_star)."""
+    import naviflow_b200 as nb
+    g = load(golden_dir, "simple_runs.npz")
+    key = f"n{n}_Re{Re}_k{k}_N{N}_{name}"
+    alg, res = run_gpu_simple(n, Re, name, k, N)
+    for fld in ("u", "v", "p"):
+        e = rel(getattr(alg, fld), g[f"{key}_{fld}"])
+        assert e < 1e-10, (fld, e)
+    np.testing.assert_allclose(res.get_history("total_rel_norm")[::2], g[key + "_hist"], rtol=1e-8)
+    assert res.iterations == N
+    if key + "_ghia" in g:
+        inf, l2 = nb.ghia_errors(alg.u, alg.v, alg.mesh, Re)
+        np.testing.assert_allclose([inf, l2], g[key + "_ghia"], rtol=1e-8)
+
+
+def test_simple_loop_krylov_pressure_vs_oracle():
+    """SIMPLE with the GPU CG / BiCGSTAB pressure solve tracks the oracle loop (scipy stopping rule)."""
+    n, Re, k, N = 31, 100, 5, 10
+    import naviflow_b200 as nb
+    for kind, cls in (("cg", nb.GpuCGSolver), ("bicgstab", nb.GpuBiCGSTABSolver)):
+        st, h = O.simple_solve(n, n, Re, O.make_pressure_solver(kind, tol=1e-7, maxiter=2000), n_sweeps=k,
+                               max_iterations=N, tolerance=0.0)
+        mesh, fluid = cavity(n, Re)
+        alg = nb.GpuSimpleSolver(mesh, fluid, cls(tolerance=1e-7, max_iterations=2000),
+                                 nb.GpuJacobiMomentumSolver(n_jacobi_sweeps=k), alpha_p=0.3, alpha_u=0.7)
+        alg.set_boundary_condition("top", "velocity", {"u": 1.0, "v": 0.0})
+        for b in ("bottom", "left", "right"):
+            alg.set_boundary_condition(b, "wall")
+        alg.solve(max_iterations=N, tolerance=0.0)
+        # Krylov solves stop at rtol 1e-5, so iterates agree to about that level, not 1e-10
+        assert rel(alg.u, st.u) < 1e-4 and rel(alg.v, st.v) < 1e-4, kind
+
+
+def test_simple_stops_on_tolerance_like_reference():
+    """Stopping rule of simple.py:114: iterate while max(u_rel_norm, v_rel_norm) > tolerance."""
+    n, Re, k = 31, 100, 5
+    st, h = O.simple_solve(n, n, Re, O.make_pressure_solver("rb_sor", omega=1.5, n_iter=30), n_sweeps=k,
+                           max_iterations=500, tolerance=1e-3)
+    alg, res = None, None
+    import naviflow_b200 as nb
+    mesh, fluid = cavity(n, Re)
+    alg = nb.GpuSimpleSolver(mesh, fluid, make_ps("rbsor"), nb.GpuJacobiMomentumSolver(n_jacobi_sweeps=k))
+    alg.set_boundary_condition("top", "velocity", {"u": 1.0, "v": 0.0})
+    for b in ("bottom", "left", "right"):
+        alg.set_boundary_condition(b, "wall")
+    res = alg.solve(max_iterations=500, tolerance=1e-3)
+    assert res.iterations == h["iterations"]
+    assert rel(alg.u, st.u) < 1e-10 and rel(alg.p, st.p) < 1e-10
+
+
+def test_plugins_drop_into_a_host_loop():
+    """The NumPy-in/NumPy-out plugin calls compose into the oracle's SIMPLE loop (what dropping the GPU
+    solvers into the reference's SimpleSolver does): one iteration equals the resident loop's."""
+    import naviflow_b200 as nb
+    n, Re, k = 33, 400, 4
+    mesh, fluid = cavity(n, Re)
+    bc = nb.BoundaryConditionManager()
+    bc.set_condition("top", "velocity", {"u": 1.0, "v": 0.0})
+    for b in ("bottom", "left", "right"):
+        bc.set_condition(b, "wall")
+    u = np.zeros((n + 1, n)); v = np.zeros((n, n + 1)); p = np.zeros((n, n))
+    bc.apply_velocity_boundary_conditions(u, v, n, n)
+    ms, ps, vu = nb.GpuJacobiMomentumSolver(n_jacobi_sweeps=k), make_ps("v"), nb.GpuVelocityUpdater()
+    for _ in range(3):
+        us, du, _ = ms.solve_u_momentum(mesh, fluid, u, v, p, 0.7, bc)
+        vs, dv, _ = ms.solve_v_momentum(mesh, fluid, u, v, p, 0.7, bc)
+        pp, _ = ps.solve(mesh, us, vs, du, dv, p)
+        p = O.update_pressure(p, pp, 0.3, O.bc_conditions())
+        u, v = vu.update_velocity(mesh, us, vs, pp, du, dv, bc)
+    alg = nb.GpuSimpleSolver(mesh, fluid, make_ps("v"), nb.GpuJacobiMomentumSolver(n_jacobi_sweeps=k), boundary_conditions=bc)
+    alg.apply_boundary_conditions()
+    alg.solve(max_iterations=3, tolerance=0.0)
+    assert rel(alg.u, u) < 1e-12 and rel(alg.v, v) < 1e-12 and rel(alg.p, p) < 1e-12

@@ -1,0 +1,143 @@
+"""CPU tests: the C-ABI library loads and exports every symbol include/naviflow_b200.h declares (no compute
+calls without a GPU), and the host-side mirror of the reference's objects behaves like the reference
+(checked against the oracle and the reference's golden vectors)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import np_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, "include", "naviflow_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(nf_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_loads_and_exports_every_header_symbol():
+    from naviflow_b200 import _lib
+    lib = _lib.lib()
+    syms = header_symbols()
+    assert len(syms) >= 40
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, missing
+    # the ctypes table covers the header one to one
+    assert sorted(_lib.SIGNATURES) == syms
+    assert lib.nf_version() >= 100
+
+
+def test_ctypes_struct_layouts_match_the_header():
+    from naviflow_b200 import _lib
+    import ctypes as C
+    assert C.sizeof(_lib.NfGrid) == 6 * 4 + 3 * 8
+    assert C.sizeof(_lib.NfBcProgram) == 16 * 8 + 8
+    assert C.sizeof(_lib.NfMgConfig) == 12 * 4 + 5 * 8
+    assert C.sizeof(_lib.NfSimpleConfig) == 8 * 4 + 8 * 8 + C.sizeof(_lib.NfBcProgram) + C.sizeof(_lib.NfMgConfig)
+    assert C.sizeof(_lib.NfSimpleInfo) == 5 * 8 + 8
+
+
+def test_no_gpu_means_loud_failure():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import naviflow_b200 as nb
+    ps = nb.GpuJacobiSolver()
+    with pytest.raises(RuntimeError, match="CUDA device"):
+        ps.ctx
+
+
+def cavity_bc():
+    import naviflow_b200 as nb
+    bc = nb.BoundaryConditionManager()
+    bc.set_condition("top", "velocity", {"u": 1.0, "v": 0.0})
+    for b in ("bottom", "left", "right"):
+        bc.set_condition(b, "wall")
+    return bc
+
+
+@pytest.mark.parametrize("n", [8, 15, 31, 32])
+def test_boundary_manager_matches_reference_golden(golden_dir, n):
+    g = dict(np.load(os.path.join(golden_dir, f"kernels_n{n}.npz")))
+    bc = cavity_bc()
+    u, v = bc.apply_velocity_boundary_conditions(g["u"].copy(), g["v"].copy(), n, n)
+    np.testing.assert_array_equal(u, g["bc_u"]); np.testing.assert_array_equal(v, g["bc_v"])
+    u, v = bc.apply_velocity_boundary_conditions(g["u"].copy(), g["v"].copy(), n + 1, n)
+    np.testing.assert_array_equal(u, g["bc1_u"]); np.testing.assert_array_equal(v, g["bc1_v"])
+    assert bc.get_boundary_types() == O.boundary_types(O.bc_conditions())
+    assert list(bc.get_boundary_types()) == ["top", "bottom", "left", "right"]
+
+
+@pytest.mark.parametrize("order", [("top", "bottom", "left", "right"), ("left", "right", "top", "bottom"),
+                                   ("bottom", "top")])
+def test_boundary_program_is_the_routine_evaluated_symbolically(order):
+    """nf_bc_program (edge / corner constants) reproduces the insertion-order dependent corner values."""
+    import naviflow_b200 as nb
+    from naviflow_b200.host import boundary_program, practice_b_sides
+    bc = nb.BoundaryConditionManager()
+    entries = []
+    for loc in order:
+        if loc == "top":
+            bc.set_condition("top", "velocity", {"u": 1.0, "v": 0.25}); entries.append(("top", "velocity", {"u": 1.0, "v": 0.25}))
+        else:
+            bc.set_condition(loc, "wall"); entries.append((loc, "wall", None))
+    cond = O.bc_conditions(entries)
+    for nx_arg_off in (0, 1):
+        n = 11
+        u = np.full((n + 1, n), 7.0); v = np.full((n, n + 1), 7.0)
+        O.apply_velocity_bc(u, v, n + nx_arg_off, n, cond)
+        prog = boundary_program(bc, n, n, n + nx_arg_off)
+        got_u = [u[0, 4], u[n, 4], u[4, 0], u[4, n - 1]]
+        assert prog["u_edge"] == got_u
+        assert prog["u_corner"] == [u[0, 0], u[0, n - 1], u[n, 0], u[n, n - 1]]
+        ve = [v[0, 4], v[n - 1, 4], v[4, 0], v[4, n]]
+        for a, b in zip(prog["v_edge"], ve):
+            assert (np.isnan(a) and b == 7.0) or a == b
+        assert prog["v_corner"] == [v[0, 0], v[0, n], v[n - 1, 0], v[n - 1, n]]
+        assert prog["v_right_row"] == (n - 1 if nx_arg_off == 0 else -1)
+    mask = practice_b_sides(bc)
+    assert mask == sum(bit for bit, loc in ((1, "left"), (2, "right"), (4, "bottom"), (8, "top")) if loc in order)
+
+
+def test_mesh_and_fluid_quirks():
+    import naviflow_b200 as nb
+    m = nb.StructuredMesh(63, 63, 1.0, 1.0)
+    assert m.get_cell_sizes() == (1.0 / 62, 1.0 / 62)          # dx = L/(nx-1): structured.py:27-28
+    assert m.get_dimensions() == (63, 63)
+    f = nb.FluidProperties(density=1.0, reynolds_number=1000, characteristic_velocity=1.0)
+    assert f.get_viscosity() == 1e-3 and f.get_reynolds_number() == 1000
+    with pytest.raises(ValueError):
+        nb.FluidProperties()
+    with pytest.raises(ValueError):
+        nb.BoundaryConditionManager().set_condition("north", "wall")
+
+
+def test_constructor_validation_matches_reference():
+    import naviflow_b200 as nb
+    gs = nb.GpuGaussSeidelSolver(omega=1.5)
+    with pytest.raises(ValueError):
+        nb.GpuMultiGridSolver(gs, coarsest_grid_size=2)
+    with pytest.raises(ValueError):
+        nb.GpuMultiGridSolver(gs, coarsest_grid_size=8)
+    with pytest.raises(ValueError):
+        nb.GpuMultiGridSolver(gs, restriction_method="nope")
+    with pytest.raises(ValueError):
+        nb.GpuMultiGridSolver(gs, interpolation_method="nope")
+    with pytest.raises(ValueError):
+        nb.GpuGaussSeidelSolver(method_type="zebra")
+    cfg = nb.GpuMultiGridSolver(gs, pre_smoothing=3, post_smoothing=3, cycle_type="fmg", cycle_type_final="v",
+                                interpolation_method="interpolate_cubic").config_struct()
+    assert (cfg.smoother, cfg.pre, cfg.post, cfg.cycle_type, cfg.cycle_final, cfg.interpolation, cfg.omega) == \
+           (0, 3, 3, 2, 0, 1, 1.5)
+
+
+def test_ghia_errors_match_reference_golden(golden_dir):
+    import naviflow_b200 as nb
+    g = dict(np.load(os.path.join(golden_dir, "simple_runs.npz")))
+    key = "n63_Re1000_k20_N25_fmg"
+    mesh = nb.StructuredMesh(63, 63)
+    inf, l2 = nb.ghia_errors(g[key + "_u"], g[key + "_v"], mesh, 1000)
+    np.testing.assert_allclose([inf, l2], g[key + "_ghia"], rtol=1e-12)
