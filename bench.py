@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""bench.py -- SIMPLE outer-iteration throughput on the BASELINE.json workload.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--n 4097]
+
+Workload (config.workload): lid-driven cavity n x n (default 4097, BASELINE configs[2]), Re = 1000, from rest,
+SIMPLE (alpha_p 0.3, alpha_u 0.7) with JacobiMatrixMomentumSolver-style fixed Jacobi momentum sweeps and the
+geometric-multigrid pressure solve: V-cycles, red-black SOR smoother omega 1.5, 3 pre + 3 post sweeps, full
+weighting + bilinear prolongation, coarsest 7, cycles until ||r||/||b|| < 1e-3 (at most `--mg-cycles`).
+A step = one SIMPLE outer iteration.  value = cells * iterations / time (MLUPS), device resident.
+e2e = the same through GpuSimpleSolver.solve() with host arrays (H2D of u,v,p and D2H of u,v,p,residual
+inside the timed region, one outer iteration per call).
+--impl reference: the reference algorithm's CPU path (NumPy oracle port, oracle/np_oracle.py) on a bounded
+sample grid of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+RE = 1000.0
+MG = dict(omega=1.5, pre=3, post=3, tol=1e-3)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=4097, help="grid size (cells per side)")
+    ap.add_argument("--momentum-sweeps", type=int, default=5)
+    ap.add_argument("--mg-cycles", type=int, default=100, help="max V-cycles per pressure solve")
+    ap.add_argument("--cpu-sample-n", type=int, default=513, help="grid of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for nm, val in zip(names, r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_solver(n, args):
+    import naviflow_b200 as nb
+    mesh = nb.StructuredMesh(n, n, 1.0, 1.0)
+    fluid = nb.FluidProperties(density=1.0, reynolds_number=RE, characteristic_velocity=1.0)
+    ps = nb.GpuMultiGridSolver(smoother=nb.GpuGaussSeidelSolver(omega=MG["omega"], method_type="red_black"),
+                               max_iterations=args.mg_cycles, tolerance=MG["tol"], pre_smoothing=MG["pre"],
+                               post_smoothing=MG["post"], cycle_type="v",
+                               restriction_method="restrict_full_weighting",
+                               interpolation_method="interpolate_linear", coarsest_grid_size=7)
+    alg = nb.GpuSimpleSolver(mesh, fluid, ps, nb.GpuJacobiMomentumSolver(n_jacobi_sweeps=args.momentum_sweeps),
+                             nb.GpuVelocityUpdater(), alpha_p=0.3, alpha_u=0.7)
+    alg.set_boundary_condition("top", "velocity", {"u": 1.0, "v": 0.0})
+    for b in ("bottom", "left", "right"):
+        alg.set_boundary_condition(b, "wall")
+    return alg
+
+
+def cpu_oracle_step_fn(n, args):
+    """One SIMPLE outer iteration of the reference algorithm on the host (NumPy port), same settings."""
+    from oracle import np_oracle as O
+    cfg = O.MGConfig(omega=MG["omega"], pre=MG["pre"], post=MG["post"], tolerance=MG["tol"],
+                     max_iterations=args.mg_cycles)
+    ps = O.make_pressure_solver("mg", cfg=cfg)
+    state = {"st": None}
+
+    def step():
+        st, h = O.simple_solve(n, n, RE, ps, n_sweeps=args.momentum_sweeps, max_iterations=1, tolerance=0.0,
+                               state=state["st"])
+        state["st"] = st
+        return h
+    return step
+
+
+def cpu_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        t = [p.get("num_threads", 1) for p in threadpool_info()]
+        return max(t) if t else 1
+    except Exception:
+        return 1
+
+
+def run_reference(args, rank):
+    """Reference arm: the reference's CPU algorithm (oracle port) on the host cores; rank 0 only."""
+    if rank != 0:
+        return
+    n = args.cpu_sample_n
+    step = cpu_oracle_step_fn(n, args)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    mlups = n * n * args.steps / dt / 1e6
+    line = {
+        "impl": "reference", "metric": "simple_outer_mlups", "value": mlups, "unit": "MLUPS",
+        "iter_per_s": args.steps / dt, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, args.n),
+        "cpu_baseline": {"value": mlups, "unit": "MLUPS", "cores": 1, "kind": "port",
+                         "sample": f"{n}x{n} grid of the same workload, {args.steps} outer iterations after "
+                                   f"{args.warmup} warm-up (NumPy is single threaded; host has {os.cpu_count()} cores, "
+                                   f"BLAS threads {cpu_threads()})"},
+        "e2e": {"value": mlups, "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, n):
+    return {"workload": f"lid-driven cavity {n}x{n} Re=1000 SIMPLE from rest, {args.momentum_sweeps} Jacobi momentum "
+                        f"sweeps/component, multigrid V(3,3) RB-SOR omega 1.5 FW+bilinear coarsest 7, cycles to "
+                        f"||r||/||b||<1e-3 (max {args.mg_cycles})",
+            "n": n, "reynolds": RE, "alpha_p": 0.3, "alpha_u": 0.7,
+            "l2_policy": "fields (134 MB each at 4097^2, ~25 live arrays) exceed the 126 MB L2; no explicit flush"}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: naviflow_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    import ctypes as C
+    from naviflow_b200.device import get_context, ptr
+    n = args.n
+    alg = build_solver(n, args)
+    ctx = get_context(local)
+    alg.push_fields()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timed region -------------------------------------------------------------
+    if args.warmup > 0:
+        alg.iterate_resident(args.warmup, 0.0)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    recs = alg.iterate_resident(args.steps, 0.0)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launches() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    cells = float(n) * n * world          # replicas: every rank runs the whole grid (see config.parallelism)
+    mlups = cells * args.steps / (ms * 1e-3) / 1e6
+
+    # ---- roofline of the dominant kernel (red-black SOR colour pass on the finest level) ------------
+    peak, peak_src = measured_peaks()
+    lib = ctx.lib
+    g = ctx.grid(n, n, 1.0 / (n - 1), 1.0 / (n - 1), 1.0)
+    fld = lambda name: C.c_void_p(alg.device_field(name))
+    scratch = ctx.empty(n, n)
+    nsw = 10
+    lib.nf_rbsor_sweeps(ctx.handle, C.byref(g), ptr(scratch), fld("b"), fld("d_u"), fld("d_v"), 1.5, 2)
+    torch.cuda.synchronize()
+    e0.record()
+    lib.nf_rbsor_sweeps(ctx.handle, C.byref(g), ptr(scratch), fld("b"), fld("d_u"), fld("d_v"), 1.5, nsw)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_launch = e0.elapsed_time(e1) / (2 * nsw)
+    alg_bytes = 20.0 * n * n                 # 40 B/cell per full sweep = 20 B/cell per colour launch
+    achieved = alg_bytes / (ms_launch * 1e-3) / 1e9
+    roofline = {"kernel": "k_rbsor_color (finest level, one colour pass)", "bound": "hbm", "achieved": achieved,
+                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms_launch, "traffic": None}
+
+    # ---- end to end through the public API (host arrays in, host arrays out) --------------------------
+    e2e = None
+    if not args.no_e2e:
+        ksteps = max(1, min(args.steps, 5))
+        alg.solve(max_iterations=1, tolerance=0.0)  # warm the path (pinned buffers, first-touch)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ksteps):
+            alg.solve(max_iterations=1, tolerance=0.0)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=f"cuda:{local}")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        fb = 8.0 * n * (n + 1)
+        e2e = {"value": cells * ksteps / dt / 1e6, "unit": "MLUPS", "steps": ksteps,
+               "h2d_bytes_per_step": int(2 * fb + 8.0 * n * n), "d2h_bytes_per_step": int(2 * fb + 2 * 8.0 * n * n)}
+
+    # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload ------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ns = args.cpu_sample_n
+        step = cpu_oracle_step_fn(ns, args)
+        step()
+        t0 = time.perf_counter()
+        k = 0
+        while k < 8 and (time.perf_counter() - t0) < 15.0:
+            step(); k += 1
+        dt = time.perf_counter() - t0
+        cpu = {"value": ns * ns * k / dt / 1e6, "unit": "MLUPS", "cores": 1, "kind": "port",
+               "sample": f"{ns}x{ns} grid of the same workload, {k} outer iterations after 1 warm-up, NumPy oracle port "
+                         f"(single threaded; host has {os.cpu_count()} cores)"}
+
+    if rank == 0:
+        cycles = [r["pressure_iterations"] for r in recs]
+        line = {
+            "metric": "simple_outer_mlups", "value": mlups, "unit": "MLUPS", "iter_per_s": args.steps / (ms * 1e-3) * world,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": dict(workload_config(args, n),
+                           parallelism="single GPU" if world == 1 else f"{world} independent replicas (slab decomposition pending)"),
+            "gpu_launches": int(launches), "mg_cycles_per_step": float(np.mean(cycles)) if cycles else None,
+            "final_u_rel_norm": recs[-1]["u_rel_norm"] if recs else None,
+            "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

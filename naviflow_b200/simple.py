@@ -57,11 +57,23 @@ class GpuSimpleSolver:
         self.initialize_fields()
 
     # ---- BaseAlgorithm interface ------------------------------------------------------------------
+    @staticmethod
+    def _host_zeros(shape):
+        """Host field; page-locked when a CUDA device is present so that solve()'s H2D/D2H run at PCIe speed."""
+        try:
+            import torch
+            if torch.cuda.is_available():
+                t = torch.zeros(shape, dtype=torch.float64).pin_memory()
+                return t.numpy()  # the array keeps the pinned tensor alive through its base
+        except Exception:
+            pass
+        return np.zeros(shape)
+
     def initialize_fields(self):
         nx, ny = self.mesh.get_dimensions()
-        self.p = np.zeros((nx, ny))
-        self.u = np.zeros((nx + 1, ny))
-        self.v = np.zeros((nx, ny + 1))
+        self.p = self._host_zeros((nx, ny))
+        self.u = self._host_zeros((nx + 1, ny))
+        self.v = self._host_zeros((nx, ny + 1))
         self.apply_boundary_conditions()
 
     def apply_boundary_conditions(self):
@@ -142,8 +154,9 @@ class GpuSimpleSolver:
         ctx.check(ctx.lib.nf_simple_upload(st, _FIELD[name], a.ctypes.data_as(C.c_void_p), a.shape[0], a.shape[1]),
                   "nf_simple_upload")
 
-    def _download(self, ctx, st, name, rows, cols):
-        out = np.empty((rows, cols), dtype=np.float64)
+    def _download(self, ctx, st, name, rows, cols, out=None):
+        if out is None or out.shape != (rows, cols) or out.dtype != np.float64 or not out.flags.c_contiguous:
+            out = np.empty((rows, cols), dtype=np.float64)
         ctx.check(ctx.lib.nf_simple_download(st, _FIELD[name], out.ctypes.data_as(C.c_void_p), rows, cols),
                   "nf_simple_download")
         return out
@@ -173,9 +186,9 @@ class GpuSimpleSolver:
     def pull_fields(self):
         ctx, st = self._ensure_state()
         nx, ny = self.mesh.get_dimensions()
-        self.u = self._download(ctx, st, "u", nx + 1, ny)
-        self.v = self._download(ctx, st, "v", nx, ny + 1)
-        self.p = self._download(ctx, st, "p", nx, ny)
+        self.u = self._download(ctx, st, "u", nx + 1, ny, self.u)
+        self.v = self._download(ctx, st, "v", nx, ny + 1, self.v)
+        self.p = self._download(ctx, st, "p", nx, ny, self.p)
 
     # ---- SimpleSolver.solve -----------------------------------------------------------------------
     def solve(self, max_iterations=1000, tolerance=1e-6, save_profile=False, profile_dir="results/profiles",
@@ -216,7 +229,7 @@ class GpuSimpleSolver:
         except KeyboardInterrupt:
             print("Interrupted by user.")
         self.pull_fields()
-        self._final_p_residual_field = self._download(ctx, st, "p_res", nx, ny)
+        self._final_p_residual_field = self._download(ctx, st, "p_res", nx, ny, self._final_p_residual_field)
         result = SimulationResult(self.u, self.v, self.p, self.mesh, iterations=iteration - 1,
                                   residuals=self.residual_history, reynolds=self.fluid.get_reynolds_number(),
                                   wall_time=time.perf_counter() - t0)
