@@ -67,7 +67,7 @@ typedef struct nf_bc_program {
 } nf_bc_program;
 
 /* ---- context ------------------------------------------------------------------------ */
-int nf_ctx_create(nf_ctx** out, int device, void* cuda_stream /* cudaStream_t or NULL */);
+int nf_ctx_create(nf_ctx** out, int device, void* cuda_stream /* cudaStream_t; NULL = legacy default stream */);
 int nf_ctx_destroy(nf_ctx* ctx);
 const char* nf_last_error(nf_ctx* ctx);
 int nf_sync(nf_ctx* ctx);
@@ -96,6 +96,11 @@ int nf_jacobi_diag(nf_ctx*, const nf_grid*, const double* d_u, const double* d_v
 /* ---- K8  red-black SOR: pressure_solver/gauss_seidel.py:214-305 ----------------------- */
 int nf_rbsor_sweeps(nf_ctx*, const nf_grid*, double* p, const double* b, const double* d_u,
                     const double* d_v, double omega, int n_sweeps);
+
+/* Same sweeps, temporally blocked: up to 3 full sweeps (6 colour passes) per tile load, bit-identical result.
+ * tmp is a same-shape scratch array (p is double buffered between launches); arrays 16-byte aligned, ld even. */
+int nf_rbsor_sweeps_fused(nf_ctx*, const nf_grid*, double* p, double* tmp, const double* b, const double* d_u,
+                          const double* d_v, double omega, int n_sweeps);
 
 /* ---- K9-K12 transfer operators: pressure_solver/helpers/multigrid_helpers.py ---------- */
 int nf_restrict_fw(nf_ctx*, const nf_grid* fine, const double* f, const nf_grid* coarse, double* c);     /* :23-70  */

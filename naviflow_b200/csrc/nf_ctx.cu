@@ -23,16 +23,10 @@ extern "C" int nf_ctx_create(nf_ctx** out, int device, void* cuda_stream) {
   if (cudaSetDevice(device) != cudaSuccess) return NF_ERR_CUDA;
   nf_ctx* c = new nf_ctx();
   c->device = device;
-  if (cuda_stream) {
-    c->stream = (cudaStream_t)cuda_stream;
-    c->owns_stream = false;
-  } else {
-    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
-      delete c;
-      return NF_ERR_CUDA;
-    }
-    c->owns_stream = true;
-  }
+  // NULL = the legacy default stream (what PyTorch uses unless told otherwise), so that library launches are
+  // ordered with the caller's own work on that stream
+  c->stream = (cudaStream_t)cuda_stream;
+  c->owns_stream = false;
   bool ok = cudaMalloc(&c->partials, sizeof(double) * NF_MAX_PARTIALS * NF_MAX_RED) == cudaSuccess &&
             cudaMalloc(&c->ticket, sizeof(unsigned int) * 4) == cudaSuccess &&
             cudaMalloc(&c->scalars, sizeof(double) * NF_NUM_SCALARS) == cudaSuccess &&

@@ -16,12 +16,15 @@
 
 int nfi_residual_restrict_fw(nf_ctx*, const nf_grid* gf, const double* p, const double* b, const double* d_u,
                              const double* d_v, const nf_grid* gc, double* c);
+int nfi_rbsor_fused(nf_ctx*, const nf_grid*, double** p, double** palt, const double* b, const double* d_u,
+                    const double* d_v, double omega, int n_sweeps);
 int nfi_prolong_banded(nf_ctx*, const nf_grid* gc, const double* c, const nf_grid* gf, double* f, double* tmp,
                        int ldt, const double* band, const int* start, int W, int add);
 
 struct MgLevel {
   nf_grid g;
   double *x = nullptr, *b = nullptr, *r = nullptr;  // r doubles as the Jacobi ping-pong buffer
+  double* x2 = nullptr;                              // second solution buffer (fused SOR is double buffered)
   double *d_u = nullptr, *d_v = nullptr;
   // banded 1-D interpolation matrix from the next-coarser level onto this level (cubic prolongation)
   double* band = nullptr;
@@ -230,7 +233,8 @@ static void build_interp_band(int mc, int m, int K, std::vector<double>& band, s
 // create / destroy / setup
 // =============================================================================================
 static void free_level(MgLevel& L, bool owns_coeffs) {
-  if (L.x) cudaFree(L.x);
+  if (L.x && owns_coeffs) cudaFree(L.x);
+  if (L.x2) cudaFree(L.x2);
   if (L.b) cudaFree(L.b);
   if (L.r) cudaFree(L.r);
   if (owns_coeffs) {
@@ -288,7 +292,8 @@ extern "C" int nf_mg_create(nf_ctx* ctx, nf_mg** out, int nx, int ny, int ld, co
   for (size_t l = 0; l < mg->lv.size() && ok; ++l) {
     MgLevel& L = mg->lv[l];
     const size_t bytes = L.elems * sizeof(double);
-    ok = ok && cudaMalloc(&L.r, bytes) == cudaSuccess;
+    ok = ok && cudaMalloc(&L.r, bytes) == cudaSuccess && cudaMalloc(&L.x2, bytes) == cudaSuccess;
+    if (ok) cudaMemsetAsync(L.x2, 0, bytes, ctx->stream);
     if (l > 0) {
       ok = ok && cudaMalloc(&L.x, bytes) == cudaSuccess && cudaMalloc(&L.b, bytes) == cudaSuccess &&
            cudaMalloc(&L.d_u, bytes) == cudaSuccess && cudaMalloc(&L.d_v, bytes) == cudaSuccess;
@@ -379,10 +384,11 @@ extern "C" int nf_mg_setup(nf_mg* mg, const double* d_u, const double* d_v) {
 // =============================================================================================
 // cycles
 // =============================================================================================
-static int mg_smooth(nf_mg* mg, int l, double* x, const double* b, int n) {
+// smoothing may move the iterate to the other buffer: (*x, *alt) are swapped accordingly
+static int mg_smooth(nf_mg* mg, int l, double** x, double** alt, const double* b, int n) {
   MgLevel& L = mg->lv[l];
-  if (mg->cfg.smoother == 0) return nfi_rbsor(mg->ctx, &L.g, x, b, L.d_u, L.d_v, mg->cfg.omega, n);
-  return nfi_jacobi(mg->ctx, &L.g, x, L.r, b, L.d_u, L.d_v, mg->cfg.omega, n);
+  if (mg->cfg.smoother == 0) return nfi_rbsor_fused(mg->ctx, &L.g, x, alt, b, L.d_u, L.d_v, mg->cfg.omega, n);
+  return nfi_jacobi(mg->ctx, &L.g, *x, L.r, b, L.d_u, L.d_v, mg->cfg.omega, n);
 }
 
 static int mg_coarse_solve(nf_mg* mg, int l, double* x, const double* b) {
@@ -404,23 +410,23 @@ static int mg_prolong_add(nf_mg* mg, int l, double* x, int cubic, int add) {
 }
 
 // one V (kind 0) or W (kind 1) cycle on level l: multigrid.py:304-432 / :434-560
-static int mg_cycle(nf_mg* mg, int l, double* x, const double* b, int kind) {
+static int mg_cycle(nf_mg* mg, int l, double** x, double** alt, const double* b, int kind) {
   nf_ctx* ctx = mg->ctx;
   MgLevel& L = mg->lv[l];
-  if (L.g.nx <= mg->cfg.coarsest || l + 1 == (int)mg->lv.size()) return mg_coarse_solve(mg, l, x, b);
+  if (L.g.nx <= mg->cfg.coarsest || l + 1 == (int)mg->lv.size()) return mg_coarse_solve(mg, l, *x, b);
   MgLevel& C = mg->lv[l + 1];
-  NF_TRY(mg_smooth(mg, l, x, b, mg->cfg.pre));
+  NF_TRY(mg_smooth(mg, l, x, alt, b, mg->cfg.pre));
   if (mg->cfg.restriction == 0) {
-    NF_TRY(nfi_residual_restrict_fw(ctx, &L.g, x, b, L.d_u, L.d_v, &C.g, C.b));
+    NF_TRY(nfi_residual_restrict_fw(ctx, &L.g, *x, b, L.d_u, L.d_v, &C.g, C.b));
   } else {
-    NF_TRY(nfi_residual(ctx, &L.g, x, b, L.d_u, L.d_v, L.r));
+    NF_TRY(nfi_residual(ctx, &L.g, *x, b, L.d_u, L.d_v, L.r));
     NF_TRY(nfi_restrict_inject(ctx, &L.g, L.r, &C.g, C.b));
   }
   NF_TRY(nfi_fill(ctx, C.x, (size_t)C.g.nx * C.g.ld, 0.0));
   const int reps = (kind == 1) ? 2 : 1;
-  for (int rep = 0; rep < reps; ++rep) NF_TRY(mg_cycle(mg, l + 1, C.x, C.b, kind));
-  NF_TRY(mg_prolong_add(mg, l, x, mg->cfg.interpolation, 1));
-  NF_TRY(mg_smooth(mg, l, x, b, mg->cfg.post));
+  for (int rep = 0; rep < reps; ++rep) NF_TRY(mg_cycle(mg, l + 1, &C.x, &C.x2, C.b, kind));
+  NF_TRY(mg_prolong_add(mg, l, *x, mg->cfg.interpolation, 1));
+  NF_TRY(mg_smooth(mg, l, x, alt, b, mg->cfg.post));
   return NF_OK;
 }
 
@@ -445,20 +451,34 @@ static int mg_rel_residual(nf_mg* mg, int l, const double* x, const double* b, d
   return NF_OK;
 }
 
+// level 0 iterates between the caller's x and the hierarchy's x2: bring the result home and restore x2
+static int mg_finish_level0(nf_mg* mg, double* x, double* cur, double* alt) {
+  nf_ctx* ctx = mg->ctx;
+  MgLevel& L = mg->lv[0];
+  if (cur != x) {  // cur is the hierarchy's own buffer, alt is the caller's array
+    NF_CHECK_CUDA(ctx, cudaMemcpyAsync(x, cur, (size_t)L.g.nx * L.g.ld * sizeof(double), cudaMemcpyDeviceToDevice,
+                                       ctx->stream));
+    L.x2 = cur;
+  } else {
+    L.x2 = alt;
+  }
+  return NF_OK;
+}
+
 // recursive FMG (multigrid.py:562-688): RHS restricted down, exact coarsest solve, cubic prolongation
 // (hard-coded :631), max_cycles_buildup cycles per level with early exit on ||r||/||b|| < tol.
-static int mg_fmg(nf_mg* mg, int l, double* x, const double* b) {
+static int mg_fmg(nf_mg* mg, int l, double** x, double** alt, const double* b) {
   MgLevel& L = mg->lv[l];
-  if (L.g.nx <= mg->cfg.coarsest || l + 1 == (int)mg->lv.size()) return mg_coarse_solve(mg, l, x, b);
+  if (L.g.nx <= mg->cfg.coarsest || l + 1 == (int)mg->lv.size()) return mg_coarse_solve(mg, l, *x, b);
   MgLevel& C = mg->lv[l + 1];
   NF_TRY(mg_restrict_rhs(mg, l, b));
-  NF_TRY(mg_fmg(mg, l + 1, C.x, C.b));
-  NF_TRY(mg_prolong_add(mg, l, x, 1, 0));
+  NF_TRY(mg_fmg(mg, l + 1, &C.x, &C.x2, C.b));
+  NF_TRY(mg_prolong_add(mg, l, *x, 1, 0));
   for (int c = 0; c < mg->cfg.max_cycles_buildup; ++c) {
-    NF_TRY(mg_cycle(mg, l, x, b, mg->cfg.cycle_buildup));
+    NF_TRY(mg_cycle(mg, l, x, alt, b, mg->cfg.cycle_buildup));
     if (mg->cfg.tolerance < 1.0 && c + 1 < mg->cfg.max_cycles_buildup) {
       double rn, bn;
-      NF_TRY(mg_rel_residual(mg, l, x, b, &rn, &bn));
+      NF_TRY(mg_rel_residual(mg, l, *x, b, &rn, &bn));
       const double rel = bn > 0.0 ? rn / bn : rn;
       if (rel < mg->cfg.tolerance) break;
     }
@@ -470,7 +490,10 @@ extern "C" int nf_mg_cycle(nf_mg* mg, double* x, const double* b, int kind) {
   if (!mg) return NF_ERR_ARG;
   NF_REQUIRE(mg->ctx, mg->setup_done, "nf_mg_setup has not been called");
   NF_REQUIRE(mg->ctx, kind == 0 || kind == 1, "kind must be 0 ('v') or 1 ('w')");
-  return mg_cycle(mg, 0, x, b, kind);
+  double* cur = x;
+  double* alt = mg->lv[0].x2;
+  NF_TRY(mg_cycle(mg, 0, &cur, &alt, b, kind));
+  return mg_finish_level0(mg, x, cur, alt);
 }
 
 // MultiGridSolver.solve without get_rhs.  sync == 0 (FMG mode only): the final ||r||^2, ||b||^2 stay in the
@@ -485,30 +508,32 @@ int nfi_mg_solve(nf_mg* mg, const double* b, double* x, double* r, nf_mg_info* i
   int status = NF_OK;
   double rn = 0.0, bn = 0.0;
   int cycles = 0;
+  double* cur = x;
+  double* alt = L.x2;
   do {
-    status = nfi_fill(ctx, x, (size_t)L.g.nx * L.g.ld, 0.0);  // x0 = 0 (multigrid.py:165)
+    status = nfi_fill(ctx, cur, (size_t)L.g.nx * L.g.ld, 0.0);  // x0 = 0 (multigrid.py:165)
     if (status) break;
     if (mg->cfg.cycle_type == 2) {
-      status = mg_fmg(mg, 0, x, b);
+      status = mg_fmg(mg, 0, &cur, &alt, b);
       if (status) break;
       if (mg->cfg.cycle_final >= 0) {
-        status = mg_cycle(mg, 0, x, b, mg->cfg.cycle_final);
+        status = mg_cycle(mg, 0, &cur, &alt, b, mg->cfg.cycle_final);
         if (status) break;
         cycles = 1;
       }
       if (sync) {
-        status = mg_rel_residual(mg, 0, x, b, &rn, &bn);
+        status = mg_rel_residual(mg, 0, cur, b, &rn, &bn);
       } else {
-        status = nfi_residual(ctx, &L.g, x, b, L.d_u, L.d_v, L.r);
+        status = nfi_residual(ctx, &L.g, cur, b, L.d_u, L.d_v, L.r);
         if (!status) status = nfi_sumsq_dev(ctx, &L.g, L.r, 0, 0);
         if (!status) status = nfi_sumsq_dev(ctx, &L.g, b, 0, 1);
       }
     } else {
       for (int k = 0; k < mg->cfg.max_iterations; ++k) {
-        status = mg_cycle(mg, 0, x, b, mg->cfg.cycle_type);
+        status = mg_cycle(mg, 0, &cur, &alt, b, mg->cfg.cycle_type);
         if (status) break;
         ++cycles;
-        status = mg_rel_residual(mg, 0, x, b, &rn, &bn);
+        status = mg_rel_residual(mg, 0, cur, b, &rn, &bn);
         if (status) break;
         const double rel = bn > 0.0 ? rn / bn : rn;
         if (rel < mg->cfg.tolerance) break;
@@ -517,6 +542,7 @@ int nfi_mg_solve(nf_mg* mg, const double* b, double* x, double* r, nf_mg_info* i
   } while (0);
   L.r = own_r;
   if (status) return status;
+  NF_TRY(mg_finish_level0(mg, x, cur, alt));
   if (info) {
     info->r_norm = rn;
     info->b_norm = bn;

@@ -203,3 +203,24 @@ def test_argument_errors_are_reported():
         d.call("nf_rbsor_sweeps", d.gref(), ptr(x), ptr(x), ptr(x), ptr(x), 1.5, -1)
     with pytest.raises(NfError, match="alias"):
         d.call("nf_pressure_apply", d.gref(), ptr(x), ptr(x), ptr(x), ptr(x))
+
+
+@pytest.mark.parametrize("n", [7, 8, 31, 40, 53, 64, 65, 127, 130, 257])
+def test_fused_rbsor_is_bit_identical(n):
+    """Temporally blocked red-black SOR (1..7 sweeps, tile/halo edges at every size class) against the oracle
+    and against the unfused colour kernels."""
+    from gpu_util import Dev, ptr
+    s = synth(n, 2000 + n)
+    dx = dy = 1.0 / (n - 1)
+    d = Dev(n)
+    du, dv, us, vs = (d.up(s[k]) for k in ("d_u", "d_v", "u_star", "v_star"))
+    b_ref = O.continuity_rhs(n, n, dx, dy, 1.0, s["u_star"], s["v_star"])
+    b = d.up(b_ref)
+    for sweeps in (0, 1, 2, 3, 4, 7):
+        p, tmp = d.up(s["x"]), d.zeros()
+        d.call("nf_rbsor_sweeps_fused", d.gref(), ptr(p), ptr(tmp), ptr(b), ptr(du), ptr(dv), 1.5, sweeps)
+        want = O.rb_sor(s["x"], b_ref, dx, dy, 1.0, s["d_u"], s["d_v"], 1.5, sweeps)
+        np.testing.assert_array_equal(d.down(p), want, err_msg=f"n={n} sweeps={sweeps}")
+        p2 = d.up(s["x"])
+        d.call("nf_rbsor_sweeps", d.gref(), ptr(p2), ptr(b), ptr(du), ptr(dv), 1.5, sweeps)
+        np.testing.assert_array_equal(d.down(p2), want)

@@ -70,9 +70,9 @@ def test_bicgstab_vs_reference_golden(golden_dir, n):
     # summation order changes, so the count is compared with a 10 % band
     assert abs(bs.last_info.iterations - int(g["bicgstab_iters"])) <= max(3, 0.1 * int(g["bicgstab_iters"])), \
         (bs.last_info.iterations, int(g["bicgstab_iters"]))
-    # both stop at scipy's rtol = 1e-5; BiCGSTAB amplifies rounding differences of the dot products, so the
-    # converged answers agree to the stopping tolerance (the first iterates are checked at 1e-10 below)
-    assert rel(p, g["bicgstab_p"]) < 5e-5
+    # both stop at scipy's residual rtol = 1e-5; with cond(A) ~ 1e2 the two converged answers agree to ~1e-3
+    # (the first 20 iterates are checked at 1e-10 in test_krylov_iterates_vs_oracle)
+    assert rel(p, g["bicgstab_p"]) < 5e-3
     assert info["rel_norm"] < 2e-5
 
 
