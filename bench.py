@@ -235,7 +235,9 @@ def main():
     fld = lambda name: C.c_void_p(alg.device_field(name))
     scratch, scratch2 = ctx.empty(n, n), ctx.empty(n, n)
     reps = 8
-    args_f = (ctx.handle, C.byref(g), ptr(scratch), ptr(scratch2), fld("b"), fld("d_u"), fld("d_v"), 1.5)
+    inv = ctx.empty(n, n)
+    ctx.check(lib.nf_pressure_inv_diag(ctx.handle, C.byref(g), fld("d_u"), fld("d_v"), ptr(inv)))
+    args_f = (ctx.handle, C.byref(g), ptr(scratch), ptr(scratch2), fld("b"), fld("d_u"), fld("d_v"), ptr(inv), 1.5)
     ctx.check(lib.nf_rbsor_sweeps_fused(*args_f, 6))
     torch.cuda.synchronize()
     e0.record()

@@ -100,7 +100,10 @@ int nf_rbsor_sweeps(nf_ctx*, const nf_grid*, double* p, const double* b, const d
 /* Same sweeps, temporally blocked: up to 3 full sweeps (6 colour passes) per tile load, bit-identical result.
  * tmp is a same-shape scratch array (p is double buffered between launches); arrays 16-byte aligned, ld even. */
 int nf_rbsor_sweeps_fused(nf_ctx*, const nf_grid*, double* p, double* tmp, const double* b, const double* d_u,
-                          const double* d_v, double omega, int n_sweeps);
+                          const double* d_v, const double* inv /* nf_pressure_inv_diag output or NULL */,
+                          double omega, int n_sweeps);
+/* inv[i,j] = 1/aP of the SOR update (gauss_seidel.py:214-266), reusable for every sweep with the same d_u, d_v */
+int nf_pressure_inv_diag(nf_ctx*, const nf_grid*, const double* d_u, const double* d_v, double* inv);
 
 /* ---- K9-K12 transfer operators: pressure_solver/helpers/multigrid_helpers.py ---------- */
 int nf_restrict_fw(nf_ctx*, const nf_grid* fine, const double* f, const nf_grid* coarse, double* c);     /* :23-70  */

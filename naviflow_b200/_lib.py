@@ -89,7 +89,8 @@ SIGNATURES = {
     "nf_jacobi_iterate": (C.c_int, [CTX, GP, P, P, P, P, P, C.c_double, C.c_int]),
     "nf_jacobi_diag": (C.c_int, [CTX, GP, P, P, P]),
     "nf_rbsor_sweeps": (C.c_int, [CTX, GP, P, P, P, P, C.c_double, C.c_int]),
-    "nf_rbsor_sweeps_fused": (C.c_int, [CTX, GP, P, P, P, P, P, C.c_double, C.c_int]),
+    "nf_rbsor_sweeps_fused": (C.c_int, [CTX, GP, P, P, P, P, P, P, C.c_double, C.c_int]),
+    "nf_pressure_inv_diag": (C.c_int, [CTX, GP, P, P, P]),
     "nf_restrict_fw": (C.c_int, [CTX, GP, P, GP, P]),
     "nf_restrict_inject": (C.c_int, [CTX, GP, P, GP, P]),
     "nf_restrict_coeffs": (C.c_int, [CTX, GP, P, P, GP, P, P]),

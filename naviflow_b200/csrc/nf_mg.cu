@@ -17,7 +17,8 @@
 int nfi_residual_restrict_fw(nf_ctx*, const nf_grid* gf, const double* p, const double* b, const double* d_u,
                              const double* d_v, const nf_grid* gc, double* c);
 int nfi_rbsor_fused(nf_ctx*, const nf_grid*, double** p, double** palt, const double* b, const double* d_u,
-                    const double* d_v, double omega, int n_sweeps);
+                    const double* d_v, const double* inv, double omega, int n_sweeps);
+int nfi_inv_diag(nf_ctx*, const nf_grid*, const double* d_u, const double* d_v, double* inv);
 int nfi_prolong_banded(nf_ctx*, const nf_grid* gc, const double* c, const nf_grid* gf, double* f, double* tmp,
                        int ldt, const double* band, const int* start, int W, int add);
 
@@ -25,6 +26,7 @@ struct MgLevel {
   nf_grid g;
   double *x = nullptr, *b = nullptr, *r = nullptr;  // r doubles as the Jacobi ping-pong buffer
   double* x2 = nullptr;                              // second solution buffer (fused SOR is double buffered)
+  double* inv = nullptr;                             // 1/aP of the SOR update, rebuilt by nf_mg_setup
   double *d_u = nullptr, *d_v = nullptr;
   // banded 1-D interpolation matrix from the next-coarser level onto this level (cubic prolongation)
   double* band = nullptr;
@@ -235,6 +237,7 @@ static void build_interp_band(int mc, int m, int K, std::vector<double>& band, s
 static void free_level(MgLevel& L, bool owns_coeffs) {
   if (L.x && owns_coeffs) cudaFree(L.x);
   if (L.x2) cudaFree(L.x2);
+  if (L.inv) cudaFree(L.inv);
   if (L.b) cudaFree(L.b);
   if (L.r) cudaFree(L.r);
   if (owns_coeffs) {
@@ -294,6 +297,10 @@ extern "C" int nf_mg_create(nf_ctx* ctx, nf_mg** out, int nx, int ny, int ld, co
     const size_t bytes = L.elems * sizeof(double);
     ok = ok && cudaMalloc(&L.r, bytes) == cudaSuccess && cudaMalloc(&L.x2, bytes) == cudaSuccess;
     if (ok) cudaMemsetAsync(L.x2, 0, bytes, ctx->stream);
+    if (ok && cfg->smoother == 0) {
+      ok = cudaMalloc(&L.inv, bytes) == cudaSuccess;
+      if (ok) cudaMemsetAsync(L.inv, 0, bytes, ctx->stream);
+    }
     if (l > 0) {
       ok = ok && cudaMalloc(&L.x, bytes) == cudaSuccess && cudaMalloc(&L.b, bytes) == cudaSuccess &&
            cudaMalloc(&L.d_u, bytes) == cudaSuccess && cudaMalloc(&L.d_v, bytes) == cudaSuccess;
@@ -372,6 +379,9 @@ extern "C" int nf_mg_setup(nf_mg* mg, const double* d_u, const double* d_v) {
   for (size_t l = 0; l + 1 < mg->lv.size(); ++l)
     NF_TRY(nfi_restrict_coeffs(ctx, &mg->lv[l].g, mg->lv[l].d_u, mg->lv[l].d_v, &mg->lv[l + 1].g, mg->lv[l + 1].d_u,
                                mg->lv[l + 1].d_v));
+  if (mg->cfg.smoother == 0)
+    for (size_t l = 0; l < mg->lv.size(); ++l)
+      NF_TRY(nfi_inv_diag(ctx, &mg->lv[l].g, mg->lv[l].d_u, mg->lv[l].d_v, mg->lv[l].inv));
   const MgLevel& C = mg->lv.back();
   if (C.g.nx <= mg->cfg.coarsest) {
     k_coarse_invert<<<1, 1024, 0, ctx->stream>>>(C.g, C.d_u, C.d_v, mg->coarse_A, mg->coarse_inv, mg->coarse_N);
@@ -387,7 +397,7 @@ extern "C" int nf_mg_setup(nf_mg* mg, const double* d_u, const double* d_v) {
 // smoothing may move the iterate to the other buffer: (*x, *alt) are swapped accordingly
 static int mg_smooth(nf_mg* mg, int l, double** x, double** alt, const double* b, int n) {
   MgLevel& L = mg->lv[l];
-  if (mg->cfg.smoother == 0) return nfi_rbsor_fused(mg->ctx, &L.g, x, alt, b, L.d_u, L.d_v, mg->cfg.omega, n);
+  if (mg->cfg.smoother == 0) return nfi_rbsor_fused(mg->ctx, &L.g, x, alt, b, L.d_u, L.d_v, L.inv, mg->cfg.omega, n);
   return nfi_jacobi(mg->ctx, &L.g, *x, L.r, b, L.d_u, L.d_v, mg->cfg.omega, n);
 }
 

@@ -14,6 +14,10 @@
 //   * HBM traffic per launch: read p, b, d_u, d_v (32 B/cell x region/tile overhead, largely absorbed by L2
 //     between neighbouring tiles) + write p (8 B/cell) -- versus 2*NS passes x ~40 B/cell unfused.
 //   * p is double buffered in global memory (p_in -> p_out): neighbouring tiles read each other's halo.
+#include <stdlib.h>
+
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "nf_pressure.cuh"
 
 namespace {
@@ -29,8 +33,9 @@ struct CellCoef {
 
 // coefficients of cell (gi,gj) from the raw d_u[gi][gj], d_u[gi+1][gj], d_v[gi][gj], d_v[gi][gj+1] with the
 // reference's Neumann folding (matrix_free.py:52-84, gauss_seidel.py:243-266: aP < 1e-15 -> 1)
+template <bool HAS_INV>
 __device__ __forceinline__ CellCoef cell_coef(const nf_grid& g, int gi, int gj, bool inside, double du_c, double du_e,
-                                              double dv_c, double dv_n) {
+                                              double dv_c, double dv_n, double inv_pre) {
   CellCoef c;
   if (!inside) {
     c.e = c.w = c.n = c.s = 0.0;
@@ -50,82 +55,39 @@ __device__ __forceinline__ CellCoef cell_coef(const nf_grid& g, int gi, int gj, 
   if (gi == g.nx - 1) w = 0.0;
   if (gj == 0) n = 0.0;
   if (gj == g.ny - 1) s = 0.0;
-  diag += ((e + w) + n) + s;
-  if (diag < 1e-15) diag = 1.0;
   c.e = e; c.w = w; c.n = n; c.s = s;
-  c.inv = 1.0 / diag;
+  if (HAS_INV) {
+    c.inv = inv_pre;  // 1/aP precomputed once per level by k_inv_diag (same expression, same rounding)
+  } else {
+    diag += ((e + w) + n) + s;
+    if (diag < 1e-15) diag = 1.0;
+    c.inv = 1.0 / diag;
+  }
   return c;
 }
 
-template <int NS>
-__global__ void __launch_bounds__(32 * NYT, 1)
-k_rbsor_fused(nf_grid g, const double* __restrict__ pin, double* __restrict__ pout, const double* __restrict__ b,
-              const double* __restrict__ d_u, const double* __restrict__ d_v, double omega) {
+// The 2*NS colour passes.  S0 = parity of (global row + first column) of this thread's rows: it is the same for
+// all of a thread's row slots (rows differ by 16) and uniform in a warp, so the kernel branches once on it and
+// every "which cell of the pair is red" decision below folds at compile time.
+template <int NS, int S0>
+__device__ __forceinline__ void rbsor_passes(double (&sP)[2][RRW][33], int tx, int ty, double omega,
+                                             double (&p0)[KS], double (&p1)[KS], const double (&b0)[KS],
+                                             const double (&b1)[KS], const double (&inv0)[KS], const double (&inv1)[KS],
+                                             const double (&aE0)[KS], const double (&aW0)[KS], const double (&aN0)[KS],
+                                             const double (&aS0)[KS], const double (&aE1)[KS], const double (&aW1)[KS],
+                                             const double (&aN1)[KS], const double (&aS1)[KS], const bool (&ok0)[KS],
+                                             const bool (&ok1)[KS]) {
   constexpr int H = 2 * NS;
   constexpr int TR = RRW - 2 * H;
-  constexpr int TC = RCW - 2 * H;
-  __shared__ double sP[2][RRW][33];  // [local parity][region row][column pair]
-
-  const int tx = threadIdx.x, ty = threadIdx.y;
-  const int i0 = g.gb + blockIdx.y * TR - H;  // global row of region row 0
-  const int j0 = blockIdx.x * TC - H;         // global column of region column 0 (even)
-  const int gj0 = j0 + 2 * tx;                // global column of this thread's first cell
-  const int c0 = 2 * tx;                      // its region column
-
-  // register state per row slot: cell 0 = (r, 2tx), cell 1 = (r, 2tx+1)
-  double p0[KS], p1[KS], b0[KS], b1[KS], inv0[KS], inv1[KS];
-  double aE0[KS], aW0[KS], aN0[KS], aS0[KS], aE1[KS], aW1[KS], aN1[KS], aS1[KS];
-  bool ok0[KS], ok1[KS];  // cell may be updated: in the domain, not pinned, not on the region edge
-
-#pragma unroll
-  for (int k = 0; k < KS; ++k) {
-    const int r = ty + NYT * k;
-    const int gi = i0 + r;
-    const bool row_in = (gi >= 0 && gi < g.nx);
-    const bool in0 = row_in && gj0 >= 0 && gj0 < g.ny;
-    const bool in1 = row_in && gj0 + 1 >= 0 && gj0 + 1 < g.ny;
-    double vp0 = 0.0, vp1 = 0.0, vb0 = 0.0, vb1 = 0.0;
-    double uc0 = 0.0, uc1 = 0.0, ue0 = 0.0, ue1 = 0.0, w0 = 0.0, w1 = 0.0, w2 = 0.0;
-    if (in0) {
-      // gj0 is even and the pitch is even: 16-byte aligned pair loads.  Column gj0+1 <= ny lies inside the row
-      // (ld >= ny+1), so the pair load is always in bounds; its second half is ignored when in1 is false.
-      const size_t kk = nf_idx(g, gi, gj0);
-      const double2 pp = *reinterpret_cast<const double2*>(pin + kk);
-      const double2 bb = *reinterpret_cast<const double2*>(b + kk);
-      const double2 ua = *reinterpret_cast<const double2*>(d_u + kk);
-      const double2 ub = *reinterpret_cast<const double2*>(d_u + kk + g.ld);
-      const double2 vv = *reinterpret_cast<const double2*>(d_v + kk);
-      vp0 = pp.x; vp1 = pp.y; vb0 = bb.x; vb1 = bb.y;
-      uc0 = ua.x; uc1 = ua.y; ue0 = ub.x; ue1 = ub.y; w0 = vv.x; w1 = vv.y;
-      if (in1) w2 = d_v[kk + 2];  // d_v[gi][gj0+2], gj0+2 <= ny
-    }
-    const CellCoef ca = cell_coef(g, gi, gj0, in0, uc0, ue0, w0, w1);
-    const CellCoef cb = cell_coef(g, gi, gj0 + 1, in1, uc1, ue1, w1, w2);
-    aE0[k] = ca.e; aW0[k] = ca.w; aN0[k] = ca.n; aS0[k] = ca.s; inv0[k] = ca.inv;
-    aE1[k] = cb.e; aW1[k] = cb.w; aN1[k] = cb.n; aS1[k] = cb.s; inv1[k] = cb.inv;
-    if (gi == 0 && gj0 == 0) vp0 = 0.0;  // pinned cell (0,0) is held at 0 (gauss_seidel.py:145, :305)
-    p0[k] = in0 ? vp0 : 0.0;
-    p1[k] = in1 ? vp1 : 0.0;
-    b0[k] = vb0;
-    b1[k] = vb1;
-    ok0[k] = in0 && !(gi == 0 && gj0 == 0) && r >= 1 && r <= RRW - 2 && c0 >= 1;
-    ok1[k] = in1 && r >= 1 && r <= RRW - 2 && (c0 + 1) <= RCW - 2;
-    // local parity of cell 0 is (r + c0) & 1 = r & 1; cell 1 has the other one
-    sP[r & 1][r][tx] = p0[k];
-    sP[(r & 1) ^ 1][r][tx] = p1[k];
-  }
-  __syncthreads();
-
 #pragma unroll
   for (int t = 0; t < 2 * NS; ++t) {
     const int col = t & 1;            // 0: (i+j) even ("red"), 1: odd ("black")
     const int m = 2 * NS - 1 - t;     // pass t is only needed within m cells of the tile
+    const int s = S0 ^ col;           // which cell of the pair has colour `col`: 0 -> cell 0, 1 -> cell 1
 #pragma unroll
     for (int k = 0; k < KS; ++k) {
       const int r = ty + NYT * k;
-      const int gi = i0 + r;
-      const int s = ((gi + gj0) & 1) ^ col;  // which cell of the pair has colour `col`: 0 -> cell 0, 1 -> cell 1
-      const int lp = (r & 1) ^ s;            // its local parity
+      const int lp = (r & 1) ^ s;     // local parity of the updated cell
       const bool ok = s ? ok1[k] : ok0[k];
       if (ok && r >= H - m && r < H + TR + m) {
         const double pc = s ? p1[k] : p0[k];
@@ -154,6 +116,76 @@ k_rbsor_fused(nf_grid g, const double* __restrict__ pin, double* __restrict__ po
     }
     __syncthreads();
   }
+}
+
+template <int NS, bool HAS_INV>
+__global__ void __launch_bounds__(32 * NYT, 1)
+k_rbsor_fused(nf_grid g, const double* __restrict__ pin, double* __restrict__ pout, const double* __restrict__ b,
+              const double* __restrict__ d_u, const double* __restrict__ d_v, const double* __restrict__ inv,
+              double omega) {
+  constexpr int H = 2 * NS;
+  constexpr int TR = RRW - 2 * H;
+  constexpr int TC = RCW - 2 * H;
+  __shared__ double sP[2][RRW][33];  // [local parity][region row][column pair]
+
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int i0 = g.gb + blockIdx.y * TR - H;  // global row of region row 0
+  const int j0 = blockIdx.x * TC - H;         // global column of region column 0 (even)
+  const int gj0 = j0 + 2 * tx;                // global column of this thread's first cell
+  const int c0 = 2 * tx;                      // its region column
+
+  // register state per row slot: cell 0 = (r, 2tx), cell 1 = (r, 2tx+1)
+  double p0[KS], p1[KS], b0[KS], b1[KS], inv0[KS], inv1[KS];
+  double aE0[KS], aW0[KS], aN0[KS], aS0[KS], aE1[KS], aW1[KS], aN1[KS], aS1[KS];
+  bool ok0[KS], ok1[KS];  // cell may be updated: in the domain, not pinned, not on the region edge
+
+#pragma unroll
+  for (int k = 0; k < KS; ++k) {
+    const int r = ty + NYT * k;
+    const int gi = i0 + r;
+    const bool row_in = (gi >= 0 && gi < g.nx);
+    const bool in0 = row_in && gj0 >= 0 && gj0 < g.ny;
+    const bool in1 = row_in && gj0 + 1 >= 0 && gj0 + 1 < g.ny;
+    double vp0 = 0.0, vp1 = 0.0, vb0 = 0.0, vb1 = 0.0;
+    double uc0 = 0.0, uc1 = 0.0, ue0 = 0.0, ue1 = 0.0, w0 = 0.0, w1 = 0.0, w2 = 0.0, iv0 = 1.0, iv1 = 1.0;
+    if (in0) {
+      // gj0 is even and the pitch is even: 16-byte aligned pair loads.  Column gj0+1 <= ny lies inside the row
+      // (ld >= ny+1), so the pair load is always in bounds; its second half is ignored when in1 is false.
+      const size_t kk = nf_idx(g, gi, gj0);
+      const double2 pp = *reinterpret_cast<const double2*>(pin + kk);
+      const double2 bb = *reinterpret_cast<const double2*>(b + kk);
+      const double2 ua = *reinterpret_cast<const double2*>(d_u + kk);
+      const double2 ub = *reinterpret_cast<const double2*>(d_u + kk + g.ld);
+      const double2 vv = *reinterpret_cast<const double2*>(d_v + kk);
+      vp0 = pp.x; vp1 = pp.y; vb0 = bb.x; vb1 = bb.y;
+      uc0 = ua.x; uc1 = ua.y; ue0 = ub.x; ue1 = ub.y; w0 = vv.x; w1 = vv.y;
+      if (in1) w2 = d_v[kk + 2];  // d_v[gi][gj0+2], gj0+2 <= ny
+      if (HAS_INV) {
+        const double2 iv = *reinterpret_cast<const double2*>(inv + kk);
+        iv0 = iv.x; iv1 = iv.y;
+      }
+    }
+    const CellCoef ca = cell_coef<HAS_INV>(g, gi, gj0, in0, uc0, ue0, w0, w1, iv0);
+    const CellCoef cb = cell_coef<HAS_INV>(g, gi, gj0 + 1, in1, uc1, ue1, w1, w2, iv1);
+    aE0[k] = ca.e; aW0[k] = ca.w; aN0[k] = ca.n; aS0[k] = ca.s; inv0[k] = ca.inv;
+    aE1[k] = cb.e; aW1[k] = cb.w; aN1[k] = cb.n; aS1[k] = cb.s; inv1[k] = cb.inv;
+    if (gi == 0 && gj0 == 0) vp0 = 0.0;  // pinned cell (0,0) is held at 0 (gauss_seidel.py:145, :305)
+    p0[k] = in0 ? vp0 : 0.0;
+    p1[k] = in1 ? vp1 : 0.0;
+    b0[k] = vb0;
+    b1[k] = vb1;
+    ok0[k] = in0 && !(gi == 0 && gj0 == 0) && r >= 1 && r <= RRW - 2 && c0 >= 1;
+    ok1[k] = in1 && r >= 1 && r <= RRW - 2 && (c0 + 1) <= RCW - 2;
+    // local parity of cell 0 is (r + c0) & 1 = r & 1; cell 1 has the other one
+    sP[r & 1][r][tx] = p0[k];
+    sP[(r & 1) ^ 1][r][tx] = p1[k];
+  }
+  __syncthreads();
+
+  if ((i0 + ty + gj0) & 1)
+    rbsor_passes<NS, 1>(sP, tx, ty, omega, p0, p1, b0, b1, inv0, inv1, aE0, aW0, aN0, aS0, aE1, aW1, aN1, aS1, ok0, ok1);
+  else
+    rbsor_passes<NS, 0>(sP, tx, ty, omega, p0, p1, b0, b1, inv0, inv1, aE0, aW0, aN0, aS0, aE1, aW1, aN1, aS1, ok0, ok1);
 
   // write the tile (cells of the region interior that belong to this CTA)
 #pragma unroll
@@ -170,13 +202,220 @@ k_rbsor_fused(nf_grid g, const double* __restrict__ pin, double* __restrict__ po
 
 template <int NS>
 int launch_fused(nf_ctx* ctx, const nf_grid* g, const double* pin, double* pout, const double* b, const double* d_u,
-                 const double* d_v, double omega) {
+                 const double* d_v, const double* inv, double omega) {
   constexpr int H = 2 * NS;
   constexpr int TR = RRW - 2 * H, TC = RCW - 2 * H;
   dim3 block(32, NYT, 1);
   dim3 grid((g->ny + TC - 1) / TC, (g->ge - g->gb + TR - 1) / TR, 1);
-  k_rbsor_fused<NS><<<grid, block, 0, ctx->stream>>>(*g, pin, pout, b, d_u, d_v, omega);
+  if (inv) k_rbsor_fused<NS, true><<<grid, block, 0, ctx->stream>>>(*g, pin, pout, b, d_u, d_v, inv, omega);
+  else k_rbsor_fused<NS, false><<<grid, block, 0, ctx->stream>>>(*g, pin, pout, b, d_u, d_v, nullptr, omega);
   NF_LAUNCH_CHECK(ctx);
+  return NF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Persistent TMA variant (large levels).  One CTA per SM walks over the tiles in row-major order.  The raw
+// inputs of a tile (p, b, d_u, d_v boxes with halo; out-of-domain elements zero-filled by the TMA unit) are
+// fetched by four cp.async.bulk.tensor.2d loads into a staging buffer; as soon as the CTA has moved a tile
+// from staging into registers it issues the loads of its NEXT tile, so the HBM latency of tile n+1 hides
+// behind the 2*NS colour passes of tile n.
+// ---------------------------------------------------------------------------------------------
+constexpr int ST_P = 0;                               // staging layout (bytes), every box 128-byte aligned
+constexpr int ST_B = ST_P + RRW * RCW * 8;            // p, b: [48][64]
+constexpr int ST_DU = ST_B + RRW * RCW * 8;           // d_u:  [49][64]  (rows gi .. gi+48)
+constexpr int ST_DV = ST_DU + (RRW + 1) * RCW * 8;    // d_v:  [48][66]  (cols gj .. gj+65)
+constexpr int ST_INV = ST_DV + RRW * (RCW + 2) * 8;   // 1/aP: [48][64] (only with a precomputed inverse diagonal)
+constexpr int ST_END = ST_INV + RRW * RCW * 8;
+constexpr int SM_SP = ST_END;                          // sP[2][48][33]
+constexpr int SM_BAR = SM_SP + 2 * RRW * 33 * 8;
+constexpr int SM_TOTAL = SM_BAR + 16;
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* map, int c_inner, int c_outer, unsigned bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      :: "r"(dst), "l"(map), "r"(c_inner), "r"(c_outer), "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" :: "r"(bar), "r"(parity) : "memory");
+}
+
+template <int NS, bool HAS_INV>
+__global__ void __launch_bounds__(32 * NYT, 1)
+k_rbsor_tma(nf_grid g, const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_b,
+            const __grid_constant__ CUtensorMap map_du, const __grid_constant__ CUtensorMap map_dv,
+            const __grid_constant__ CUtensorMap map_inv, double* __restrict__ pout, double omega, int tiles_x,
+            int n_tiles) {
+  constexpr unsigned TX_BYTES = HAS_INV ? ST_END : ST_INV;
+  constexpr int H = 2 * NS;
+  constexpr int TR = RRW - 2 * H;
+  constexpr int TC = RCW - 2 * H;
+  extern __shared__ __align__(128) unsigned char smem[];
+  double (&sP)[2][RRW][33] = *reinterpret_cast<double (*)[2][RRW][33]>(smem + SM_SP);
+  const double* stP = reinterpret_cast<const double*>(smem + ST_P);
+  const double* stB = reinterpret_cast<const double*>(smem + ST_B);
+  const double* stDU = reinterpret_cast<const double*>(smem + ST_DU);
+  const double* stDV = reinterpret_cast<const double*>(smem + ST_DV);
+  const double* stINV = reinterpret_cast<const double*>(smem + ST_INV);
+  const unsigned bar = smem_u32(smem + SM_BAR);
+  const unsigned st_base = smem_u32(smem);
+
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const bool leader = (tx == 0 && ty == 0);
+  const int c0 = 2 * tx;
+
+  auto issue = [&](int tile) {
+    const int ti = tile / tiles_x, tj = tile - ti * tiles_x;
+    const int ri = g.gb + ti * TR - H, rj = tj * TC - H;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(TX_BYTES) : "memory");
+    tma_load_2d(st_base + ST_P, &map_p, rj, ri - g.row0, bar);
+    tma_load_2d(st_base + ST_B, &map_b, rj, ri - g.row0, bar);
+    tma_load_2d(st_base + ST_DU, &map_du, rj, ri - g.row0, bar);
+    tma_load_2d(st_base + ST_DV, &map_dv, rj, ri - g.row0, bar);
+    if (HAS_INV) tma_load_2d(st_base + ST_INV, &map_inv, rj, ri - g.row0, bar);
+  };
+
+  if (leader) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  int tile = blockIdx.x;
+  if (leader && tile < n_tiles) issue(tile);
+  unsigned phase = 0;
+
+  for (; tile < n_tiles; tile += gridDim.x) {
+    const int ti = tile / tiles_x, tj = tile - ti * tiles_x;
+    const int i0 = g.gb + ti * TR - H;
+    const int j0 = tj * TC - H;
+    const int gj0 = j0 + 2 * tx;
+
+    double p0[KS], p1[KS], b0[KS], b1[KS], inv0[KS], inv1[KS];
+    double aE0[KS], aW0[KS], aN0[KS], aS0[KS], aE1[KS], aW1[KS], aN1[KS], aS1[KS];
+    bool ok0[KS], ok1[KS];
+
+    mbar_wait(bar, phase);
+    phase ^= 1;
+#pragma unroll
+    for (int k = 0; k < KS; ++k) {
+      const int r = ty + NYT * k;
+      const int gi = i0 + r;
+      const bool row_in = (gi >= 0 && gi < g.nx);
+      const bool in0 = row_in && gj0 >= 0 && gj0 < g.ny;
+      const bool in1 = row_in && gj0 + 1 >= 0 && gj0 + 1 < g.ny;
+      const double2 pp = *reinterpret_cast<const double2*>(stP + r * RCW + c0);
+      const double2 bb = *reinterpret_cast<const double2*>(stB + r * RCW + c0);
+      const double2 ua = *reinterpret_cast<const double2*>(stDU + r * RCW + c0);
+      const double2 ub = *reinterpret_cast<const double2*>(stDU + (r + 1) * RCW + c0);
+      const double2 vv = *reinterpret_cast<const double2*>(stDV + r * (RCW + 2) + c0);
+      const double w2 = stDV[r * (RCW + 2) + c0 + 2];
+      double2 iv = make_double2(1.0, 1.0);
+      if (HAS_INV) iv = *reinterpret_cast<const double2*>(stINV + r * RCW + c0);
+      const CellCoef ca = cell_coef<HAS_INV>(g, gi, gj0, in0, ua.x, ub.x, vv.x, vv.y, iv.x);
+      const CellCoef cb = cell_coef<HAS_INV>(g, gi, gj0 + 1, in1, ua.y, ub.y, vv.y, w2, iv.y);
+      aE0[k] = ca.e; aW0[k] = ca.w; aN0[k] = ca.n; aS0[k] = ca.s; inv0[k] = ca.inv;
+      aE1[k] = cb.e; aW1[k] = cb.w; aN1[k] = cb.n; aS1[k] = cb.s; inv1[k] = cb.inv;
+      double vp0 = pp.x;
+      if (gi == 0 && gj0 == 0) vp0 = 0.0;  // pinned cell
+      p0[k] = in0 ? vp0 : 0.0;
+      p1[k] = in1 ? pp.y : 0.0;
+      b0[k] = bb.x;
+      b1[k] = bb.y;
+      ok0[k] = in0 && !(gi == 0 && gj0 == 0) && r >= 1 && r <= RRW - 2 && c0 >= 1;
+      ok1[k] = in1 && r >= 1 && r <= RRW - 2 && (c0 + 1) <= RCW - 2;
+      sP[r & 1][r][tx] = p0[k];
+      sP[(r & 1) ^ 1][r][tx] = p1[k];
+    }
+    __syncthreads();  // staging fully consumed, sP complete
+    if (leader && tile + (int)gridDim.x < n_tiles) issue(tile + gridDim.x);
+
+    if ((i0 + ty + j0) & 1)
+      rbsor_passes<NS, 1>(sP, tx, ty, omega, p0, p1, b0, b1, inv0, inv1, aE0, aW0, aN0, aS0, aE1, aW1, aN1, aS1, ok0, ok1);
+    else
+      rbsor_passes<NS, 0>(sP, tx, ty, omega, p0, p1, b0, b1, inv0, inv1, aE0, aW0, aN0, aS0, aE1, aW1, aN1, aS1, ok0, ok1);
+
+#pragma unroll
+    for (int k = 0; k < KS; ++k) {
+      const int r = ty + NYT * k;
+      const int gi = i0 + r;
+      if (r < H || r >= H + TR || gi >= g.ge) continue;
+      if (c0 < H || c0 >= H + TC || gj0 >= g.ny) continue;
+      const size_t kk = nf_idx(g, gi, gj0);
+      if (gj0 + 1 < g.ny) *reinterpret_cast<double2*>(pout + kk) = make_double2(p0[k], p1[k]);
+      else pout[kk] = p0[k];
+    }
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encoder() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+// 2-D fp64 tensor map over `rows` x `cols` valid elements with row pitch ld; box = box_rows x box_cols
+bool make_map(CUtensorMap* map, const double* base, int rows, int cols, int ld, int box_rows, int box_cols) {
+  EncodeTiledFn enc = get_encoder();
+  if (!enc) return false;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(double)};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+template <int NS, bool HAS_INV>
+int launch_tma(nf_ctx* ctx, const nf_grid* g, const double* pin, double* pout, const double* b, const double* d_u,
+               const double* d_v, const double* inv, double omega, bool* used) {
+  constexpr int H = 2 * NS;
+  constexpr int TR = RRW - 2 * H, TC = RCW - 2 * H;
+  *used = false;
+  const int tiles_x = (g->ny + TC - 1) / TC, tiles_y = (g->ge - g->gb + TR - 1) / TR;
+  const int n_tiles = tiles_x * tiles_y;
+  // stored rows of this (slab of the) grid: the maps cover rows [row0, ...) of the arrays as stored
+  const int stored_p = g->nx - g->row0;       // p-like arrays: rows row0 .. nx-1 (single GPU: all)
+  CUtensorMap mp, mb, mu, mv, mi;
+  if (!make_map(&mp, pin, stored_p, g->ny, g->ld, RRW, RCW) || !make_map(&mb, b, stored_p, g->ny, g->ld, RRW, RCW) ||
+      !make_map(&mu, d_u, stored_p + 1, g->ny, g->ld, RRW + 1, RCW) ||
+      !make_map(&mv, d_v, stored_p, g->ny + 1, g->ld, RRW, RCW + 2) ||
+      !make_map(&mi, HAS_INV ? inv : b, stored_p, g->ny, g->ld, RRW, RCW))
+    return NF_OK;  // caller falls back to the plain fused kernel
+  static bool attr_set[4] = {false, false, false, false};
+  if (!attr_set[NS]) {
+    NF_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_rbsor_tma<NS, HAS_INV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            SM_TOTAL));
+    attr_set[NS] = true;
+  }
+  const int grid = n_tiles < NF_SM_COUNT ? n_tiles : NF_SM_COUNT;
+  k_rbsor_tma<NS, HAS_INV><<<grid, dim3(32, NYT, 1), SM_TOTAL, ctx->stream>>>(*g, mp, mb, mu, mv, mi, pout, omega,
+                                                                              tiles_x, n_tiles);
+  NF_LAUNCH_CHECK(ctx);
+  *used = true;
   return NF_OK;
 }
 
@@ -184,29 +423,77 @@ int launch_fused(nf_ctx* ctx, const nf_grid* g, const double* pin, double* pout,
 
 // n_sweeps red-black SOR sweeps, double buffered: *p holds the input, *palt is scratch of the same shape; on
 // return *p points at the buffer holding the result (the two pointers are swapped once per launch).
+template <int NS>
+int launch_tma_any(nf_ctx* ctx, const nf_grid* g, const double* pin, double* pout, const double* b, const double* d_u,
+                   const double* d_v, const double* inv, double omega, bool* used) {
+  if (inv) return launch_tma<NS, true>(ctx, g, pin, pout, b, d_u, d_v, inv, omega, used);
+  return launch_tma<NS, false>(ctx, g, pin, pout, b, d_u, d_v, nullptr, omega, used);
+}
+
+// inv (optional): precomputed 1/aP of this level (nfi_inv_diag); NULL = divide inside the kernel
 int nfi_rbsor_fused(nf_ctx* ctx, const nf_grid* g, double** p, double** palt, const double* b, const double* d_u,
-                    const double* d_v, double omega, int n_sweeps) {
+                    const double* d_v, const double* inv, double omega, int n_sweeps) {
   if (n_sweeps == 0) {  // the reference still pins p[0,0] = 0 (gauss_seidel.py:145)
     if (g->row0 == 0 && g->gb == 0) NF_CHECK_CUDA(ctx, cudaMemsetAsync(*p, 0, sizeof(double), ctx->stream));
     return NF_OK;
   }
+  // TMA path: single-GPU layout (row0 == 0), 16-byte aligned arrays, pitch a multiple of 2 doubles
+  const char* env = getenv("NF_RBSOR_TMA");
+  const int tma_min_rows = env ? atoi(env) : 600;  // NF_RBSOR_TMA=0 forces TMA everywhere, a huge value disables it
+  const bool use_tma = g->row0 == 0 && g->gb == 0 && g->ge == g->nx && g->nx >= tma_min_rows;
   int left = n_sweeps;
   while (left > 0) {
     const int ns = left >= 3 ? 3 : left;
-    int st;
-    if (ns == 3) st = launch_fused<3>(ctx, g, *p, *palt, b, d_u, d_v, omega);
-    else if (ns == 2) st = launch_fused<2>(ctx, g, *p, *palt, b, d_u, d_v, omega);
-    else st = launch_fused<1>(ctx, g, *p, *palt, b, d_u, d_v, omega);
-    if (st != NF_OK) return st;
+    int st = NF_OK;
+    bool used = false;
+    if (use_tma) {  // persistent TMA pipeline: pays off once every SM gets several tiles
+      if (ns == 3) st = launch_tma_any<3>(ctx, g, *p, *palt, b, d_u, d_v, inv, omega, &used);
+      else if (ns == 2) st = launch_tma_any<2>(ctx, g, *p, *palt, b, d_u, d_v, inv, omega, &used);
+      else st = launch_tma_any<1>(ctx, g, *p, *palt, b, d_u, d_v, inv, omega, &used);
+      if (st != NF_OK) return st;
+    }
+    if (!used) {
+      if (ns == 3) st = launch_fused<3>(ctx, g, *p, *palt, b, d_u, d_v, inv, omega);
+      else if (ns == 2) st = launch_fused<2>(ctx, g, *p, *palt, b, d_u, d_v, inv, omega);
+      else st = launch_fused<1>(ctx, g, *p, *palt, b, d_u, d_v, inv, omega);
+      if (st != NF_OK) return st;
+    }
     double* t = *p; *p = *palt; *palt = t;
     left -= ns;
   }
   return NF_OK;
 }
 
+// 1/aP of every cell (gauss_seidel.py:214-266: aP with the Neumann folding, < 1e-15 -> 1), once per level and
+// per (d_u, d_v): 24 B/cell, saves the two fp64 divisions per cell pair in every smoother launch
+__global__ void k_inv_diag(nf_grid g, const double* __restrict__ d_u, const double* __restrict__ d_v,
+                           double* __restrict__ inv) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = g.gb + blockIdx.y * blockDim.y + threadIdx.y;
+  if (j >= g.ny || i >= g.ge) return;
+  const PCoef c = nf_pcoef(g, d_u, d_v, i, j);
+  double aP = c.diag;
+  if (aP < 1e-15) aP = 1.0;
+  inv[nf_idx(g, i, j)] = 1.0 / aP;
+}
+
+int nfi_inv_diag(nf_ctx* ctx, const nf_grid* g, const double* d_u, const double* d_v, double* inv) {
+  NfLaunch2D l = nf_launch2d(g->ge - g->gb, g->ny);
+  k_inv_diag<<<l.grid, l.block, 0, ctx->stream>>>(*g, d_u, d_v, inv);
+  NF_LAUNCH_CHECK(ctx);
+  return NF_OK;
+}
+
 // C-ABI: in-place semantics with a caller-provided scratch array
+extern "C" int nf_pressure_inv_diag(nf_ctx* ctx, const nf_grid* g, const double* d_u, const double* d_v, double* inv) {
+  NF_GRID_OK(ctx, g);
+  NF_REQUIRE(ctx, d_u && d_v && inv, "NULL argument");
+  return nfi_inv_diag(ctx, g, d_u, d_v, inv);
+}
+
 extern "C" int nf_rbsor_sweeps_fused(nf_ctx* ctx, const nf_grid* g, double* p, double* tmp, const double* b,
-                                     const double* d_u, const double* d_v, double omega, int n_sweeps) {
+                                     const double* d_u, const double* d_v, const double* inv, double omega,
+                                     int n_sweeps) {
   NF_GRID_OK(ctx, g);
   NF_REQUIRE(ctx, n_sweeps >= 0, "n_sweeps < 0");
   NF_REQUIRE(ctx, p && tmp && p != tmp, "p and tmp must be distinct arrays");
@@ -215,7 +502,8 @@ extern "C" int nf_rbsor_sweeps_fused(nf_ctx* ctx, const nf_grid* g, double* p, d
                       ((uintptr_t)d_u % 16) == 0 && ((uintptr_t)d_v % 16) == 0, "arrays must be 16-byte aligned");
   double* cur = p;
   double* alt = tmp;
-  NF_TRY(nfi_rbsor_fused(ctx, g, &cur, &alt, b, d_u, d_v, omega, n_sweeps));
+  NF_REQUIRE(ctx, !inv || ((uintptr_t)inv % 16) == 0, "inv must be 16-byte aligned");
+  NF_TRY(nfi_rbsor_fused(ctx, g, &cur, &alt, b, d_u, d_v, inv, omega, n_sweeps));
   if (cur != p) {
     const size_t rows = (size_t)(g->ge - g->gb);
     NF_CHECK_CUDA(ctx, cudaMemcpyAsync(p + (size_t)(g->gb - g->row0) * g->ld, cur + (size_t)(g->gb - g->row0) * g->ld,

@@ -205,22 +205,46 @@ def test_argument_errors_are_reported():
         d.call("nf_pressure_apply", d.gref(), ptr(x), ptr(x), ptr(x), ptr(x))
 
 
+@pytest.mark.parametrize("tma", [False, True])
 @pytest.mark.parametrize("n", [7, 8, 31, 40, 53, 64, 65, 127, 130, 257])
-def test_fused_rbsor_is_bit_identical(n):
+def test_fused_rbsor_is_bit_identical(n, tma, monkeypatch):
     """Temporally blocked red-black SOR (1..7 sweeps, tile/halo edges at every size class) against the oracle
-    and against the unfused colour kernels."""
+    and against the unfused colour kernels; tma=True forces the persistent TMA pipeline at every size."""
     from gpu_util import Dev, ptr
+    monkeypatch.setenv("NF_RBSOR_TMA", "0" if tma else "1000000")
     s = synth(n, 2000 + n)
     dx = dy = 1.0 / (n - 1)
     d = Dev(n)
     du, dv, us, vs = (d.up(s[k]) for k in ("d_u", "d_v", "u_star", "v_star"))
     b_ref = O.continuity_rhs(n, n, dx, dy, 1.0, s["u_star"], s["v_star"])
     b = d.up(b_ref)
+    inv = d.zeros()
+    d.call("nf_pressure_inv_diag", d.gref(), ptr(du), ptr(dv), ptr(inv))
+    np.testing.assert_array_equal(d.down(inv), 1.0 / O.sor_coefficients(n, n, dx, dy, 1.0, s["d_u"], s["d_v"])[4])
     for sweeps in (0, 1, 2, 3, 4, 7):
-        p, tmp = d.up(s["x"]), d.zeros()
-        d.call("nf_rbsor_sweeps_fused", d.gref(), ptr(p), ptr(tmp), ptr(b), ptr(du), ptr(dv), 1.5, sweeps)
         want = O.rb_sor(s["x"], b_ref, dx, dy, 1.0, s["d_u"], s["d_v"], 1.5, sweeps)
-        np.testing.assert_array_equal(d.down(p), want, err_msg=f"n={n} sweeps={sweeps}")
+        for use_inv in (None, inv):
+            p, tmp = d.up(s["x"]), d.zeros()
+            d.call("nf_rbsor_sweeps_fused", d.gref(), ptr(p), ptr(tmp), ptr(b), ptr(du), ptr(dv), ptr(use_inv), 1.5, sweeps)
+            np.testing.assert_array_equal(d.down(p), want, err_msg=f"n={n} sweeps={sweeps} inv={use_inv is not None}")
         p2 = d.up(s["x"])
         d.call("nf_rbsor_sweeps", d.gref(), ptr(p2), ptr(b), ptr(du), ptr(dv), 1.5, sweeps)
         np.testing.assert_array_equal(d.down(p2), want)
+
+
+def test_fused_rbsor_tma_large_grid_matches_unfused():
+    """1025^2 (the TMA pipeline's production regime: several tiles per SM) against the colour-pass kernels."""
+    from gpu_util import Dev, ptr
+    n = 1025
+    s = synth(n, 77)
+    d = Dev(n)
+    du, dv, us, vs = (d.up(s[k]) for k in ("d_u", "d_v", "u_star", "v_star"))
+    b = d.zeros()
+    d.call("nf_continuity_rhs", d.gref(), ptr(us), ptr(vs), ptr(b))
+    for sweeps in (3, 5):
+        p, tmp, p2 = d.up(s["x"]), d.zeros(), d.up(s["x"])
+        inv = d.zeros()
+        d.call("nf_pressure_inv_diag", d.gref(), ptr(du), ptr(dv), ptr(inv))
+        d.call("nf_rbsor_sweeps_fused", d.gref(), ptr(p), ptr(tmp), ptr(b), ptr(du), ptr(dv), ptr(inv), 1.5, sweeps)
+        d.call("nf_rbsor_sweeps", d.gref(), ptr(p2), ptr(b), ptr(du), ptr(dv), 1.5, sweeps)
+        np.testing.assert_array_equal(d.down(p), d.down(p2))
