@@ -448,16 +448,16 @@ static int mg_restrict_rhs(nf_mg* mg, int l, const double* f) {
 }
 
 // ||b - A x|| / ||b|| on level l (host value; multigrid.py:652-676)
+// *b_norm < 0 on entry: ||b|| is not known yet and is computed in the same pass; otherwise it is kept
 static int mg_rel_residual(nf_mg* mg, int l, const double* x, const double* b, double* r_norm, double* b_norm) {
   nf_ctx* ctx = mg->ctx;
   MgLevel& L = mg->lv[l];
-  NF_TRY(nfi_residual(ctx, &L.g, x, b, L.d_u, L.d_v, L.r));
-  NF_TRY(nfi_sumsq_dev(ctx, &L.g, L.r, 0, 0));
-  NF_TRY(nfi_sumsq_dev(ctx, &L.g, b, 0, 1));
+  const int with_b = (*b_norm < 0.0) ? 1 : 0;
+  NF_TRY(nfi_residual_norms(ctx, &L.g, x, b, L.d_u, L.d_v, L.r, with_b, 0));
   double s[2];
-  NF_TRY(nf_read_scalars(ctx, 0, 2, s));
+  NF_TRY(nf_read_scalars(ctx, 0, with_b ? 2 : 1, s));
   *r_norm = sqrt(s[0]);
-  *b_norm = sqrt(s[1]);
+  if (with_b) *b_norm = sqrt(s[1]);
   return NF_OK;
 }
 
@@ -487,7 +487,7 @@ static int mg_fmg(nf_mg* mg, int l, double** x, double** alt, const double* b) {
   for (int c = 0; c < mg->cfg.max_cycles_buildup; ++c) {
     NF_TRY(mg_cycle(mg, l, x, alt, b, mg->cfg.cycle_buildup));
     if (mg->cfg.tolerance < 1.0 && c + 1 < mg->cfg.max_cycles_buildup) {
-      double rn, bn;
+      double rn, bn = -1.0;
       NF_TRY(mg_rel_residual(mg, l, *x, b, &rn, &bn));
       const double rel = bn > 0.0 ? rn / bn : rn;
       if (rel < mg->cfg.tolerance) break;
@@ -516,7 +516,7 @@ int nfi_mg_solve(nf_mg* mg, const double* b, double* x, double* r, nf_mg_info* i
   double* own_r = L.r;
   if (r) L.r = r;  // residual field goes straight to the caller's array
   int status = NF_OK;
-  double rn = 0.0, bn = 0.0;
+  double rn = 0.0, bn = -1.0;  // bn < 0: ||b|| not computed yet
   int cycles = 0;
   double* cur = x;
   double* alt = L.x2;
@@ -534,9 +534,7 @@ int nfi_mg_solve(nf_mg* mg, const double* b, double* x, double* r, nf_mg_info* i
       if (sync) {
         status = mg_rel_residual(mg, 0, cur, b, &rn, &bn);
       } else {
-        status = nfi_residual(ctx, &L.g, cur, b, L.d_u, L.d_v, L.r);
-        if (!status) status = nfi_sumsq_dev(ctx, &L.g, L.r, 0, 0);
-        if (!status) status = nfi_sumsq_dev(ctx, &L.g, b, 0, 1);
+        status = nfi_residual_norms(ctx, &L.g, cur, b, L.d_u, L.d_v, L.r, 1, 0);
       }
     } else {
       for (int k = 0; k < mg->cfg.max_iterations; ++k) {
@@ -555,7 +553,7 @@ int nfi_mg_solve(nf_mg* mg, const double* b, double* x, double* r, nf_mg_info* i
   NF_TRY(mg_finish_level0(mg, x, cur, alt));
   if (info) {
     info->r_norm = rn;
-    info->b_norm = bn;
+    info->b_norm = bn < 0.0 ? 0.0 : bn;
     info->cycles = cycles;
     info->levels = (int)mg->lv.size();
   }

@@ -122,9 +122,17 @@ __global__ void k_sumsq(nf_grid g, const double* __restrict__ x, int interior_on
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j < g.ny) {
     const bool jin = !interior_only || (j > 0 && j < g.ny - 1);
-    for (int i = g.gb + blockIdx.y * blockDim.y + threadIdx.y; i < g.ge; i += gridDim.y * blockDim.y) {
-      const bool iin = !interior_only || (i > 0 && i < g.nx - 1);
-      if (jin && iin) {
+    const int lo = interior_only ? max(g.gb, 1) : g.gb;
+    const int hi = interior_only ? min(g.ge, g.nx - 1) : g.ge;
+    const int st = gridDim.y * blockDim.y;
+    int i = lo + blockIdx.y * blockDim.y + threadIdx.y;
+    if (jin) {
+      for (; i + 3 * st < hi; i += 4 * st) {  // four loads in flight per thread; summation order unchanged
+        const double v0 = x[nf_idx(g, i, j)], v1 = x[nf_idx(g, i + st, j)];
+        const double v2 = x[nf_idx(g, i + 2 * st, j)], v3 = x[nf_idx(g, i + 3 * st, j)];
+        acc[0] += v0 * v0; acc[0] += v1 * v1; acc[0] += v2 * v2; acc[0] += v3 * v3;
+      }
+      for (; i < hi; i += st) {
         const double v = x[nf_idx(g, i, j)];
         acc[0] += v * v;
       }
@@ -133,12 +141,42 @@ __global__ void k_sumsq(nf_grid g, const double* __restrict__ x, int interior_on
   nf_block_reduce_store<1>(acc, partials, ticket, out);
 }
 
+// r = b - A p (stored when r != NULL) fused with sum r^2 (and sum b^2 when WITH_B): the multigrid convergence test
+// of multigrid.py:201-240 in one pass over the level (32-40 B/cell instead of 40 + 8 + 8 in three kernels)
+template <bool WITH_B>
+__global__ void k_residual_norms(nf_grid g, const double* __restrict__ p, const double* __restrict__ b,
+                                 const double* __restrict__ d_u, const double* __restrict__ d_v,
+                                 double* __restrict__ r, double* partials, unsigned int* ticket, double* out) {
+  double acc[WITH_B ? 2 : 1];
+  acc[0] = 0.0;
+  if (WITH_B) acc[WITH_B ? 1 : 0] = 0.0;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < g.ny) {
+    for (int i = g.gb + blockIdx.y * blockDim.y + threadIdx.y; i < g.ge; i += gridDim.y * blockDim.y) {
+      const size_t k = nf_idx(g, i, j);
+      const double bv = b[k];
+      const double rv = bv - nf_Ap_cell(g, p, d_u, d_v, i, j);
+      if (r) r[k] = rv;
+      acc[0] += rv * rv;
+      if (WITH_B) acc[WITH_B ? 1 : 0] += bv * bv;
+    }
+  }
+  nf_block_reduce_store<(WITH_B ? 2 : 1)>(acc, partials, ticket, out);
+}
+
 __global__ void k_dot(nf_grid g, const double* __restrict__ x, const double* __restrict__ y, double* partials,
                       unsigned int* ticket, double* out) {
   double acc[1] = {0.0};
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j < g.ny) {
-    for (int i = g.gb + blockIdx.y * blockDim.y + threadIdx.y; i < g.ge; i += gridDim.y * blockDim.y) {
+    const int st = gridDim.y * blockDim.y;
+    int i = g.gb + blockIdx.y * blockDim.y + threadIdx.y;
+    for (; i + st < g.ge; i += 2 * st) {
+      const size_t k0 = nf_idx(g, i, j), k1 = nf_idx(g, i + st, j);
+      const double a0 = x[k0], b0 = y[k0], a1 = x[k1], b1 = y[k1];
+      acc[0] += a0 * b0; acc[0] += a1 * b1;
+    }
+    for (; i < g.ge; i += st) {
       const size_t k = nf_idx(g, i, j);
       acc[0] += x[k] * y[k];
     }
@@ -282,6 +320,20 @@ extern "C" int nf_update_pressure(nf_ctx* ctx, const nf_grid* g, const double* p
   NF_REQUIRE(ctx, p != ps && p != pp, "p must not alias p_star / p_prime");
   NfLaunch2D l = nf_launch2d(g->ge - g->gb, g->ny);
   k_update_pressure<<<l.grid, l.block, 0, ctx->stream>>>(*g, ps, pp, alpha_p, p);
+  NF_LAUNCH_CHECK(ctx);
+  return NF_OK;
+}
+
+// sum r^2 -> scalars[slot], (with_b) sum b^2 -> scalars[slot+1]
+int nfi_residual_norms(nf_ctx* ctx, const nf_grid* g, const double* p, const double* b, const double* d_u,
+                       const double* d_v, double* r, int with_b, int slot) {
+  NfLaunch2D l = nf_launch_reduce(g->ge - g->gb, g->ny);
+  if (with_b)
+    k_residual_norms<true><<<l.grid, l.block, 0, ctx->stream>>>(*g, p, b, d_u, d_v, r, ctx->partials, ctx->ticket,
+                                                                ctx->scalars + slot);
+  else
+    k_residual_norms<false><<<l.grid, l.block, 0, ctx->stream>>>(*g, p, b, d_u, d_v, r, ctx->partials, ctx->ticket,
+                                                                 ctx->scalars + slot);
   NF_LAUNCH_CHECK(ctx);
   return NF_OK;
 }

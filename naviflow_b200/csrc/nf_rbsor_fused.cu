@@ -34,6 +34,26 @@ struct CellCoef {
 // coefficients of cell (gi,gj) from the raw d_u[gi][gj], d_u[gi+1][gj], d_v[gi][gj], d_v[gi][gj+1] with the
 // reference's Neumann folding (matrix_free.py:52-84, gauss_seidel.py:243-266: aP < 1e-15 -> 1)
 template <bool HAS_INV>
+__device__ __forceinline__ CellCoef cell_coef_interior(const nf_grid& g, double du_c, double du_e, double dv_c,
+                                                       double dv_n, double inv_pre) {
+  // every cell of the region is strictly inside the domain: no folding, no masks
+  CellCoef c;
+  c.e = g.rho * du_e * g.dy;
+  c.w = g.rho * du_c * g.dy;
+  c.n = g.rho * dv_n * g.dx;
+  c.s = g.rho * dv_c * g.dx;
+  if (HAS_INV) {
+    c.inv = inv_pre;
+  } else {
+    double diag = 0.0;
+    diag += ((c.e + c.w) + c.n) + c.s;
+    if (diag < 1e-15) diag = 1.0;
+    c.inv = 1.0 / diag;
+  }
+  return c;
+}
+
+template <bool HAS_INV>
 __device__ __forceinline__ CellCoef cell_coef(const nf_grid& g, int gi, int gj, bool inside, double du_c, double du_e,
                                               double dv_c, double dv_n, double inv_pre) {
   CellCoef c;
@@ -89,7 +109,7 @@ __device__ __forceinline__ void rbsor_passes(double (&sP)[2][RRW][33], int tx, i
       const int r = ty + NYT * k;
       const int lp = (r & 1) ^ s;     // local parity of the updated cell
       const bool ok = s ? ok1[k] : ok0[k];
-      if (ok && r >= H - m && r < H + TR + m) {
+      if (r >= H - m && r < H + TR + m) {  // warp-uniform (one region row per warp and slot); rows 1..46 only
         const double pc = s ? p1[k] : p0[k];
         const double bc = s ? b1[k] : b0[k];
         const double ic = s ? inv1[k] : inv0[k];
@@ -98,7 +118,8 @@ __device__ __forceinline__ void rbsor_passes(double (&sP)[2][RRW][33], int tx, i
         const double aN = s ? aN1[k] : aN0[k];
         const double aS = s ? aS1[k] : aS0[k];
         // opposite-colour neighbours: rows r+-1 from shared memory; in the row, one is the thread's own partner
-        // cell (register) and the other belongs to the neighbouring pair
+        // cell (register) and the other belongs to the neighbouring pair (lanes 0 / 31 read the row padding:
+        // their result is discarded because ok is false on the region edge)
         const double pE = sP[lp ^ 1][r + 1][tx];
         const double pW = sP[lp ^ 1][r - 1][tx];
         const double pN = s ? sP[lp ^ 1][r][tx + 1] : p1[k];
@@ -110,8 +131,10 @@ __device__ __forceinline__ void rbsor_passes(double (&sP)[2][RRW][33], int tx, i
         acc += aS * pS;
         const double pn = acc * ic;
         const double pnew = pc + omega * (pn - pc);
-        if (s) p1[k] = pnew; else p0[k] = pnew;
-        sP[lp][r][tx] = pnew;
+        if (ok) {
+          if (s) p1[k] = pnew; else p0[k] = pnew;
+          sP[lp][r][tx] = pnew;
+        }
       }
     }
     __syncthreads();
@@ -306,6 +329,31 @@ k_rbsor_tma(nf_grid g, const __grid_constant__ CUtensorMap map_p, const __grid_c
 
     mbar_wait(bar, phase);
     phase ^= 1;
+    // region strictly inside the domain (no boundary row/column, not the pinned cell): branch-free set-up
+    const bool interior = (i0 >= 1) && (i0 + RRW < g.nx - 1) && (j0 >= 1) && (j0 + RCW < g.ny - 1);
+    if (interior) {
+#pragma unroll
+      for (int k = 0; k < KS; ++k) {
+        const int r = ty + NYT * k;
+        const double2 pp = *reinterpret_cast<const double2*>(stP + r * RCW + c0);
+        const double2 bb = *reinterpret_cast<const double2*>(stB + r * RCW + c0);
+        const double2 ua = *reinterpret_cast<const double2*>(stDU + r * RCW + c0);
+        const double2 ub = *reinterpret_cast<const double2*>(stDU + (r + 1) * RCW + c0);
+        const double2 vv = *reinterpret_cast<const double2*>(stDV + r * (RCW + 2) + c0);
+        const double w2 = stDV[r * (RCW + 2) + c0 + 2];
+        double2 iv = make_double2(1.0, 1.0);
+        if (HAS_INV) iv = *reinterpret_cast<const double2*>(stINV + r * RCW + c0);
+        const CellCoef ca = cell_coef_interior<HAS_INV>(g, ua.x, ub.x, vv.x, vv.y, iv.x);
+        const CellCoef cb = cell_coef_interior<HAS_INV>(g, ua.y, ub.y, vv.y, w2, iv.y);
+        aE0[k] = ca.e; aW0[k] = ca.w; aN0[k] = ca.n; aS0[k] = ca.s; inv0[k] = ca.inv;
+        aE1[k] = cb.e; aW1[k] = cb.w; aN1[k] = cb.n; aS1[k] = cb.s; inv1[k] = cb.inv;
+        p0[k] = pp.x; p1[k] = pp.y; b0[k] = bb.x; b1[k] = bb.y;
+        ok0[k] = r >= 1 && r <= RRW - 2 && c0 >= 1;
+        ok1[k] = r >= 1 && r <= RRW - 2 && (c0 + 1) <= RCW - 2;
+        sP[r & 1][r][tx] = p0[k];
+        sP[(r & 1) ^ 1][r][tx] = p1[k];
+      }
+    } else {
 #pragma unroll
     for (int k = 0; k < KS; ++k) {
       const int r = ty + NYT * k;
@@ -335,6 +383,7 @@ k_rbsor_tma(nf_grid g, const __grid_constant__ CUtensorMap map_p, const __grid_c
       ok1[k] = in1 && r >= 1 && r <= RRW - 2 && (c0 + 1) <= RCW - 2;
       sP[r & 1][r][tx] = p0[k];
       sP[(r & 1) ^ 1][r][tx] = p1[k];
+    }
     }
     __syncthreads();  // staging fully consumed, sP complete
     if (leader && tile + (int)gridDim.x < n_tiles) issue(tile + gridDim.x);

@@ -31,25 +31,37 @@ __global__ void k_restrict_fw(nf_grid gf, const double* __restrict__ f, nf_grid 
   c[nf_idx(gc, I, J)] = nf_fw_cell(gf, f, I, J);
 }
 
-// fused: c = FW(b - A p) without materialising the fine residual (9 fine A*p evaluations per coarse
-// cell; neighbours come from L1/L2).  Saves the 16 B/fine-cell write+read of r.
-__global__ void k_residual_restrict_fw(nf_grid gf, const double* __restrict__ p, const double* __restrict__ b,
-                                       const double* __restrict__ d_u, const double* __restrict__ d_v,
-                                       nf_grid gc, double* __restrict__ c) {
-  const int J = blockIdx.x * blockDim.x + threadIdx.x;
-  const int I = gc.gb + blockIdx.y * blockDim.y + threadIdx.y;
-  if (J >= gc.ny || I >= gc.ge) return;
-  double r[3][3];
-#pragma unroll
-  for (int a = 0; a < 3; ++a)
-#pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      const int i = 2 * I + a, j = 2 * J + q;
-      r[a][q] = b[nf_idx(gf, i, j)] - nf_Ap_cell(gf, p, d_u, d_v, i, j);
+// fused: c = FW(b - A p) without materialising the fine residual in HBM.  A CTA owns CR x CC coarse cells: it
+// evaluates the fine residual once per fine cell of the (2CR+1) x (2CC+1) patch into shared memory, then applies
+// the full-weighting stencil from there (34 B/fine cell of HBM traffic instead of 40 + 8 + 8 + 2).
+constexpr int RR_CR = 8, RR_CC = 64;
+__global__ void __launch_bounds__(256)
+k_residual_restrict_fw(nf_grid gf, const double* __restrict__ p, const double* __restrict__ b,
+                       const double* __restrict__ d_u, const double* __restrict__ d_v, nf_grid gc,
+                       double* __restrict__ c) {
+  __shared__ double sR[2 * RR_CR + 1][2 * RR_CC + 2];
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 128 x 2
+  const int I0 = gc.gb + blockIdx.y * RR_CR, J0 = blockIdx.x * RR_CC;
+  const int fi0 = 2 * I0, fj0 = 2 * J0;
+  for (int fr = ty; fr < 2 * RR_CR + 1; fr += 2) {
+    const int i = fi0 + fr;
+    for (int fc = tx; fc < 2 * RR_CC + 1; fc += 128) {
+      const int j = fj0 + fc;
+      double rv = 0.0;
+      if (i < gf.nx && j < gf.ny) rv = b[nf_idx(gf, i, j)] - nf_Ap_cell(gf, p, d_u, d_v, i, j);
+      sR[fr][fc] = rv;
     }
-  const double cc = r[1][1], n = r[1][2], s = r[1][0], e = r[2][1], w = r[0][1];
-  const double ne = r[2][2], nw = r[0][2], se = r[2][0], sw = r[0][0];
-  c[nf_idx(gc, I, J)] = (cc / 4.0 + (((n + s) + e) + w) / 8.0) + (((ne + nw) + se) + sw) / 16.0;
+  }
+  __syncthreads();
+  for (int t = ty * 128 + tx; t < RR_CR * RR_CC; t += 256) {
+    const int ci = t / RR_CC, cj = t % RR_CC;
+    const int I = I0 + ci, J = J0 + cj;
+    if (I >= gc.ge || J >= gc.ny) continue;
+    const int a = 2 * ci, q = 2 * cj;
+    const double cc = sR[a + 1][q + 1], n = sR[a + 1][q + 2], s = sR[a + 1][q], e = sR[a + 2][q + 1], w = sR[a][q + 1];
+    const double ne = sR[a + 2][q + 2], nw = sR[a][q + 2], se = sR[a + 2][q], sw = sR[a][q];
+    c[nf_idx(gc, I, J)] = (cc / 4.0 + (((n + s) + e) + w) / 8.0) + (((ne + nw) + se) + sw) / 16.0;
+  }
 }
 
 // injection: c[I,J] = f[2I+1,2J+1]; coarse size nf//2  (:20)
@@ -126,11 +138,56 @@ __device__ __forceinline__ double nf_prolong_linear_value(const nf_grid& gc, con
   return 0.25 * (((c[k] + c[k + gc.ld]) + c[k + 1]) + c[k + gc.ld + 1]);
 }
 
+// Bulk of the fine grid: one thread per coarse cell (I,J) writes the 2x2 fine block (2I+1..2I+2, 2J+1..2J+2) from
+// c[I..I+1][J..J+1] (each coarse value loaded once per thread, no per-cell index logic).  The thin strips the
+// block rule does not cover (ring rows/cols, trailing rows/cols of even-sized grids) are done by extra CTAs of the
+// same launch through the generic gather nf_prolong_linear_value.
 template <bool ADD>
-__global__ void k_prolong_linear(nf_grid gc, const double* __restrict__ c, nf_grid gf, double* __restrict__ f) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  const int i = gf.gb + blockIdx.y * blockDim.y + threadIdx.y;
-  if (j >= gf.ny || i >= gf.ge) return;
+__global__ void __launch_bounds__(256)
+k_prolong_linear(nf_grid gc, const double* __restrict__ c, nf_grid gf, double* __restrict__ f, int nI, int nJ,
+                 int nby_fast) {
+  if ((int)blockIdx.y < nby_fast) {
+    const int J = blockIdx.x * 32 + threadIdx.x;
+    const int I = blockIdx.y * 8 + threadIdx.y;
+    if (I >= nI || J >= nJ) return;
+    const size_t k = nf_idx(gc, I, J);
+    const double c00 = c[k], c01 = c[k + 1], c10 = c[k + gc.ld], c11 = c[k + gc.ld + 1];
+    const double v00 = c00;
+    const double v01 = 0.5 * (c00 + c01);
+    const double v10 = 0.5 * (c00 + c10);
+    const double v11 = 0.25 * (((c00 + c10) + c01) + c11);
+    const size_t kf = nf_idx(gf, 2 * I + 1, 2 * J + 1);
+    if (ADD) {
+      f[kf] = f[kf] + v00;
+      f[kf + 1] = f[kf + 1] + v01;
+      f[kf + gf.ld] = f[kf + gf.ld] + v10;
+      f[kf + gf.ld + 1] = f[kf + gf.ld + 1] + v11;
+    } else {
+      f[kf] = v00;
+      f[kf + 1] = v01;
+      f[kf + gf.ld] = v10;
+      f[kf + gf.ld + 1] = v11;
+    }
+    return;
+  }
+  // strips: rows {0} u [2nI+1, nx) over all columns, then columns {0} u [2nJ+1, ny) over rows 1..2nI
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  const long long t = ((long long)(blockIdx.y - nby_fast) * gridDim.x + blockIdx.x) * 256 + tid;
+  const int srows = 1 + (gf.nx - (2 * nI + 1));
+  const int scols = 1 + (gf.ny - (2 * nJ + 1));
+  int i, j;
+  if (t < (long long)srows * gf.ny) {
+    const int a = (int)(t / gf.ny);
+    j = (int)(t % gf.ny);
+    i = (a == 0) ? 0 : 2 * nI + a;
+  } else {
+    const long long t2 = t - (long long)srows * gf.ny;
+    if (t2 >= (long long)scols * (2 * nI)) return;
+    const int a = (int)(t2 % scols);
+    i = 1 + (int)(t2 / scols);
+    j = (a == 0) ? 0 : 2 * nJ + a;
+  }
+  if (i < gf.gb || i >= gf.ge) return;
   const double v = nf_prolong_linear_value(gc, c, gf.nx, gf.ny, i, j);
   const size_t k = nf_idx(gf, i, j);
   if (ADD) f[k] = f[k] + v;
@@ -185,8 +242,8 @@ int nfi_restrict_fw(nf_ctx* ctx, const nf_grid* gf, const double* f, const nf_gr
 
 int nfi_residual_restrict_fw(nf_ctx* ctx, const nf_grid* gf, const double* p, const double* b, const double* d_u,
                              const double* d_v, const nf_grid* gc, double* c) {
-  NfLaunch2D l = nf_launch2d(gc->ge - gc->gb, gc->ny, 64, 4);
-  k_residual_restrict_fw<<<l.grid, l.block, 0, ctx->stream>>>(*gf, p, b, d_u, d_v, *gc, c);
+  dim3 grid((gc->ny + RR_CC - 1) / RR_CC, (gc->ge - gc->gb + RR_CR - 1) / RR_CR, 1);
+  k_residual_restrict_fw<<<grid, dim3(128, 2, 1), 0, ctx->stream>>>(*gf, p, b, d_u, d_v, *gc, c);
   NF_LAUNCH_CHECK(ctx);
   return NF_OK;
 }
@@ -207,9 +264,22 @@ int nfi_restrict_coeffs(nf_ctx* ctx, const nf_grid* gf, const double* d_u, const
 }
 
 int nfi_prolong_linear(nf_ctx* ctx, const nf_grid* gc, const double* c, const nf_grid* gf, double* f, int add) {
-  NfLaunch2D l = nf_launch2d(gf->ge - gf->gb, gf->ny);
-  if (add) k_prolong_linear<true><<<l.grid, l.block, 0, ctx->stream>>>(*gc, c, *gf, f);
-  else k_prolong_linear<false><<<l.grid, l.block, 0, ctx->stream>>>(*gc, c, *gf, f);
+  // block rule valid for coarse I in [0, nI): needs c[I+1] and fine row 2I+2 <= m-2
+  int nI = 0, nJ = 0;
+  if (gf->nx > 3 && gf->ny > 3) {
+    nI = gc->nx - 1 < (gf->nx - 2) / 2 ? gc->nx - 1 : (gf->nx - 2) / 2;
+    nJ = gc->ny - 1 < (gf->ny - 2) / 2 ? gc->ny - 1 : (gf->ny - 2) / 2;
+    if (nI < 0) nI = 0;
+    if (nJ < 0) nJ = 0;
+    if (nI == 0 || nJ == 0) nI = nJ = 0;
+  }
+  const int gx = nJ > 0 ? (nJ + 31) / 32 : 1;
+  const int nby_fast = nI > 0 ? (nI + 7) / 8 : 0;
+  const long long strip = (long long)(1 + gf->nx - (2 * nI + 1)) * gf->ny + (long long)(1 + gf->ny - (2 * nJ + 1)) * (2 * nI);
+  const int nby_strip = (int)((strip + (long long)gx * 256 - 1) / ((long long)gx * 256));
+  dim3 grid(gx, nby_fast + nby_strip, 1), block(32, 8, 1);
+  if (add) k_prolong_linear<true><<<grid, block, 0, ctx->stream>>>(*gc, c, *gf, f, nI, nJ, nby_fast);
+  else k_prolong_linear<false><<<grid, block, 0, ctx->stream>>>(*gc, c, *gf, f, nI, nJ, nby_fast);
   NF_LAUNCH_CHECK(ctx);
   return NF_OK;
 }
