@@ -49,6 +49,8 @@ typedef struct nf_grid {
   int32_t ld;       /* row pitch in doubles                        */
   int32_t row0;     /* global index of the first stored row        */
   int32_t gb, ge;   /* global cell-row range [gb,ge) to compute    */
+  int32_t row1;     /* one past the last stored row (u-like arrays: <= nx+1); 0 = "everything" (nx+1) */
+  int32_t pad;
   double dx, dy;    /* StructuredMesh spacing: L/(nx-1), H/(ny-1)  (preprocessing/mesh/structured.py:27-28) */
   double rho;
 } nf_grid;

@@ -20,7 +20,8 @@ class NfError(RuntimeError):
 
 class NfGrid(C.Structure):
     _fields_ = [("nx", C.c_int32), ("ny", C.c_int32), ("ld", C.c_int32), ("row0", C.c_int32),
-                ("gb", C.c_int32), ("ge", C.c_int32), ("dx", C.c_double), ("dy", C.c_double),
+                ("gb", C.c_int32), ("ge", C.c_int32), ("row1", C.c_int32), ("pad", C.c_int32),
+                ("dx", C.c_double), ("dy", C.c_double),
                 ("rho", C.c_double)]
 
 

@@ -1,0 +1,243 @@
+// nf_slab.cu -- team / halo-exchange plumbing of the row-slab decomposition (see nf_slab.cuh).
+// NCCL is reached through dlopen("libnccl.so.2") so that the library binds to the copy PyTorch has already
+// loaded into the process (no link-time dependency, no second NCCL instance).
+#include "nf_slab.cuh"
+
+#include <dlfcn.h>
+#include <string.h>
+
+// ---- minimal NCCL surface (types and enums as in nccl.h 2.x; the ABI of these entry points is stable) ----------
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclFloat64_ = 8, ncclSum_ = 0 };
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*);
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+  ncclResult_t (*CommDestroy)(ncclComm_t);
+  ncclResult_t (*GroupStart)();
+  ncclResult_t (*GroupEnd)();
+  ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t);
+  const char* (*GetErrorString)(ncclResult_t);
+  bool ok = false;
+};
+
+static NcclApi* nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (h) {
+      *(void**)&api.GetUniqueId = dlsym(h, "ncclGetUniqueId");
+      *(void**)&api.CommInitRank = dlsym(h, "ncclCommInitRank");
+      *(void**)&api.CommDestroy = dlsym(h, "ncclCommDestroy");
+      *(void**)&api.GroupStart = dlsym(h, "ncclGroupStart");
+      *(void**)&api.GroupEnd = dlsym(h, "ncclGroupEnd");
+      *(void**)&api.Send = dlsym(h, "ncclSend");
+      *(void**)&api.Recv = dlsym(h, "ncclRecv");
+      *(void**)&api.AllReduce = dlsym(h, "ncclAllReduce");
+      *(void**)&api.Broadcast = dlsym(h, "ncclBroadcast");
+      *(void**)&api.GetErrorString = dlsym(h, "ncclGetErrorString");
+      api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.GroupStart && api.GroupEnd && api.Send &&
+               api.Recv && api.AllReduce && api.Broadcast;
+    }
+  }
+  return &api;
+}
+
+#define NF_NCCL(ctx, expr)                                                                      \
+  do {                                                                                          \
+    ncclResult_t _r = (expr);                                                                   \
+    if (_r != 0) {                                                                              \
+      NcclApi* _a = nccl_api();                                                                 \
+      (ctx)->err = std::string(#expr) + ": " + (_a->GetErrorString ? _a->GetErrorString(_r) : "NCCL error"); \
+      return NF_ERR_CUDA;                                                                       \
+    }                                                                                           \
+  } while (0)
+
+// ---- partitions -------------------------------------------------------------------------------------------------
+bool nf_split_rows(int nx, int world, int min_rows, std::vector<int>& gb, std::vector<int>& ge) {
+  gb.assign(world, 0);
+  ge.assign(world, nx);
+  if (world <= 1) return false;
+  for (int r = 0; r < world; ++r) {
+    long long b = ((long long)nx * r) / world;
+    b = (b / 2) * 2;  // even boundaries keep the red-black colouring and the 2I+1 parents aligned
+    gb[r] = (int)b;
+  }
+  for (int r = 0; r < world; ++r) ge[r] = (r + 1 < world) ? gb[r + 1] : nx;
+  for (int r = 0; r < world; ++r)
+    if (ge[r] - gb[r] < min_rows) {
+      gb.assign(world, 0);
+      ge.assign(world, nx);
+      return false;
+    }
+  return true;
+}
+
+void nf_coarsen_split(const std::vector<int>& gbf, const std::vector<int>& gef, int nxc, std::vector<int>& gb,
+                      std::vector<int>& ge) {
+  const int world = (int)gbf.size();
+  gb.assign(world, 0);
+  ge.assign(world, 0);
+  for (int r = 0; r < world; ++r) {
+    // smallest I with 2I+1 >= gbf[r]
+    int b = gbf[r] <= 1 ? 0 : gbf[r] / 2;  // ceil((gbf-1)/2)
+    if (b > nxc) b = nxc;
+    gb[r] = b;
+  }
+  for (int r = 0; r < world; ++r) ge[r] = (r + 1 < world) ? gb[r + 1] : nxc;
+}
+
+// ---- exchanges --------------------------------------------------------------------------------------------------
+int nf_team_exchange(nf_team* team, const LevelGeom& geom, double* const* fields, int depth) {
+  nf_ctx* ctx = team->ctx;
+  if (!geom.dist || team->world <= 1 || depth <= 0) return NF_OK;
+  if (depth > geom.halo) depth = geom.halo;
+  NcclApi* api = team->nccl ? nccl_api() : nullptr;
+  if (api) NF_NCCL(ctx, api->GroupStart());
+  for (int r = 0; r + 1 < team->world; ++r) {
+    const int B = geom.ge[r];  // == gb[r+1]
+    int d = depth;
+    if (d > geom.ge[r] - geom.gb[r]) d = geom.ge[r] - geom.gb[r];
+    if (d > geom.ge[r + 1] - geom.gb[r + 1]) d = geom.ge[r + 1] - geom.gb[r + 1];
+    const size_t count = (size_t)d * geom.ld;
+    const int lo = team->slot_of(r), hi = team->slot_of(r + 1);
+    // rows [B-d, B) live on r (owned) and in r+1's lower halo; rows [B, B+d) live on r+1 (owned) and in r's upper halo
+    if (!api) {
+      double* flo = fields[lo];
+      double* fhi = fields[hi];
+      NF_CHECK_CUDA(ctx, cudaMemcpyAsync(fhi + (size_t)(B - d - geom.row0(r + 1)) * geom.ld,
+                                         flo + (size_t)(B - d - geom.row0(r)) * geom.ld, count * sizeof(double),
+                                         cudaMemcpyDeviceToDevice, ctx->stream));
+      NF_CHECK_CUDA(ctx, cudaMemcpyAsync(flo + (size_t)(B - geom.row0(r)) * geom.ld,
+                                         fhi + (size_t)(B - geom.row0(r + 1)) * geom.ld, count * sizeof(double),
+                                         cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+      ncclComm_t comm = (ncclComm_t)team->nccl;
+      if (lo >= 0) {
+        double* f = fields[lo];
+        NF_NCCL(ctx, api->Send(f + (size_t)(B - d - geom.row0(r)) * geom.ld, count, ncclFloat64_, r + 1, comm, ctx->stream));
+        NF_NCCL(ctx, api->Recv(f + (size_t)(B - geom.row0(r)) * geom.ld, count, ncclFloat64_, r + 1, comm, ctx->stream));
+      }
+      if (hi >= 0) {
+        double* f = fields[hi];
+        NF_NCCL(ctx, api->Send(f + (size_t)(B - geom.row0(r + 1)) * geom.ld, count, ncclFloat64_, r, comm, ctx->stream));
+        NF_NCCL(ctx, api->Recv(f + (size_t)(B - d - geom.row0(r + 1)) * geom.ld, count, ncclFloat64_, r, comm, ctx->stream));
+      }
+    }
+  }
+  if (api) NF_NCCL(ctx, api->GroupEnd());
+  return NF_OK;
+}
+
+__global__ void k_accumulate(double* __restrict__ dst, const double* __restrict__ src, size_t n) {
+  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x)
+    dst[k] = dst[k] + src[k];
+}
+
+int nf_team_allreduce(nf_team* team, double* const* bufs, size_t count) {
+  nf_ctx* ctx = team->ctx;
+  if (team->world <= 1 || count == 0) return NF_OK;
+  if (team->nccl) {
+    NcclApi* api = nccl_api();
+    NF_NCCL(ctx, api->AllReduce(bufs[0], bufs[0], count, ncclFloat64_, ncclSum_, (ncclComm_t)team->nccl, ctx->stream));
+    return NF_OK;
+  }
+  // in-process ranks: rank-ordered sum into slab 0, then copy back to everyone
+  const unsigned blocks = (unsigned)((count + 255) / 256 > 1024 ? 1024 : (count + 255) / 256);
+  for (size_t k = 1; k < team->local.size(); ++k) {
+    k_accumulate<<<blocks, 256, 0, ctx->stream>>>(bufs[0], bufs[k], count);
+    NF_LAUNCH_CHECK(ctx);
+  }
+  for (size_t k = 1; k < team->local.size(); ++k)
+    NF_CHECK_CUDA(ctx, cudaMemcpyAsync(bufs[k], bufs[0], count * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  return NF_OK;
+}
+
+int nf_team_share_rows(nf_team* team, int ld, int nx, const std::vector<int>& gb, const std::vector<int>& ge,
+                       double* const* arrays, int utype) {
+  nf_ctx* ctx = team->ctx;
+  if (team->world <= 1) return NF_OK;
+  NcclApi* api = team->nccl ? nccl_api() : nullptr;
+  if (api) NF_NCCL(ctx, api->GroupStart());
+  for (int r = 0; r < team->world; ++r) {
+    int b = gb[r], e = ge[r];
+    if (utype && r == team->world - 1) e = nx + 1;
+    if (e <= b) continue;
+    const size_t off = (size_t)b * ld, count = (size_t)(e - b) * ld;
+    if (api) {
+      double* a = arrays[0];
+      NF_NCCL(ctx, api->Broadcast(a + off, a + off, count, ncclFloat64_, r, (ncclComm_t)team->nccl, ctx->stream));
+    } else {
+      const int src = team->slot_of(r);
+      for (size_t k = 0; k < team->local.size(); ++k)
+        if ((int)k != src)
+          NF_CHECK_CUDA(ctx, cudaMemcpyAsync(arrays[k] + off, arrays[src] + off, count * sizeof(double),
+                                             cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+  }
+  if (api) NF_NCCL(ctx, api->GroupEnd());
+  return NF_OK;
+}
+
+// ---- team objects -----------------------------------------------------------------------------------------------
+int nf_team_create_local(nf_ctx* ctx, int virtual_ranks, nf_team** out) {
+  NF_REQUIRE(ctx, out && virtual_ranks >= 1 && virtual_ranks <= 64, "virtual_ranks must be in 1..64");
+  nf_team* t = new nf_team();
+  t->ctx = ctx;
+  t->world = virtual_ranks;
+  for (int r = 0; r < virtual_ranks; ++r) t->local.push_back(r);
+  *out = t;
+  return NF_OK;
+}
+
+extern "C" int nf_nccl_unique_id(nf_ctx* ctx, void* id_out_128_bytes) {
+  NcclApi* api = nccl_api();
+  NF_REQUIRE(ctx, api->ok, "libnccl.so.2 could not be loaded");
+  ncclUniqueId id;
+  NF_NCCL(ctx, api->GetUniqueId(&id));
+  memcpy(id_out_128_bytes, &id, sizeof(id));
+  return NF_OK;
+}
+
+extern "C" int nf_team_create_nccl(nf_ctx* ctx, int world, int rank, const void* id_128_bytes, nf_team** out) {
+  NF_REQUIRE(ctx, out && world >= 1 && rank >= 0 && rank < world, "bad world / rank");
+  nf_team* t = new nf_team();
+  t->ctx = ctx;
+  t->world = world;
+  t->local.push_back(rank);
+  if (world > 1) {
+    NcclApi* api = nccl_api();
+    if (!api->ok) { delete t; ctx->err = "libnccl.so.2 could not be loaded"; return NF_ERR_UNSUPPORTED; }
+    ncclUniqueId id;
+    memcpy(&id, id_128_bytes, sizeof(id));
+    ncclComm_t comm = nullptr;
+    ncclResult_t r = api->CommInitRank(&comm, world, id, rank);
+    if (r != 0) { delete t; ctx->err = "ncclCommInitRank failed"; return NF_ERR_CUDA; }
+    t->nccl = comm;
+  }
+  *out = t;
+  return NF_OK;
+}
+
+extern "C" int nf_team_create_virtual(nf_ctx* ctx, int virtual_ranks, nf_team** out) {
+  return nf_team_create_local(ctx, virtual_ranks, out);
+}
+
+int nf_team_destroy(nf_team* t) {
+  if (!t) return NF_OK;
+  if (t->nccl) {
+    NcclApi* api = nccl_api();
+    if (api->ok) api->CommDestroy((ncclComm_t)t->nccl);
+  }
+  delete t;
+  return NF_OK;
+}
+
+extern "C" int nf_team_free(nf_team* t) { return nf_team_destroy(t); }

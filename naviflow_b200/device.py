@@ -66,7 +66,7 @@ class Context:
         return t[:rows, :cols].cpu().numpy().copy()
 
     def grid(self, nx, ny, dx, dy, rho=1.0):
-        return NfGrid(nx, ny, pad_ld(ny), 0, 0, nx, dx, dy, rho)
+        return NfGrid(nx, ny, pad_ld(ny), 0, 0, nx, 0, 0, dx, dy, rho)
 
     def __del__(self):
         try:

@@ -33,7 +33,7 @@ def test_library_loads_and_exports_every_header_symbol():
 def test_ctypes_struct_layouts_match_the_header():
     from naviflow_b200 import _lib
     import ctypes as C
-    assert C.sizeof(_lib.NfGrid) == 6 * 4 + 3 * 8
+    assert C.sizeof(_lib.NfGrid) == 8 * 4 + 3 * 8
     assert C.sizeof(_lib.NfBcProgram) == 16 * 8 + 8
     assert C.sizeof(_lib.NfMgConfig) == 12 * 4 + 5 * 8
     assert C.sizeof(_lib.NfSimpleConfig) == 8 * 4 + 8 * 8 + C.sizeof(_lib.NfBcProgram) + C.sizeof(_lib.NfMgConfig)
