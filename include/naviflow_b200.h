@@ -35,6 +35,7 @@ extern "C" {
 typedef struct nf_ctx nf_ctx;       /* stream, reduction scratch, error text           */
 typedef struct nf_mg nf_mg;         /* multigrid hierarchy (levels, coarse inverse)     */
 typedef struct nf_simple nf_simple; /* device-resident SIMPLE state (all fields + work) */
+typedef struct nf_team nf_team;     /* the ranks a grid is cut into (row slabs) + their communicator */
 
 enum nf_status {
   NF_OK = 0,
@@ -231,12 +232,27 @@ typedef struct nf_simple_info {   /* one record per outer iteration */
 } nf_simple_info;
 
 int nf_simple_create(nf_ctx*, nf_simple** out, const nf_simple_config* cfg);
+
+/* ---- row-slab decomposition over the GPUs of one box (no counterpart in the reference, which is a single
+ *      process: SURVEY.md section 5).  One rank per GPU: nf_nccl_unique_id on rank 0, broadcast the 128 bytes
+ *      (torch.distributed), nf_team_create_nccl on every rank; halos travel by ncclSend/ncclRecv over NVLink,
+ *      norms by ncclAllReduce.  nf_team_create_virtual cuts the grid into ranks that all live in this process
+ *      on this device (same code path, cudaMemcpy halos): the parity tests use it on a single GPU. */
+int nf_nccl_unique_id(nf_ctx*, void* id_out_128_bytes);
+int nf_team_create_nccl(nf_ctx*, int world, int rank, const void* id_128_bytes, nf_team** out);
+int nf_team_create_virtual(nf_ctx*, int virtual_ranks, nf_team** out);
+int nf_team_free(nf_team*);
+/* SIMPLE state cut over the team (multigrid pressure solver, bilinear prolongation); the team outlives it */
+int nf_simple_create_team(nf_team*, nf_simple** out, const nf_simple_config* cfg);
+/* cell rows [*row_begin, *row_end) owned by local slab k of this process (k = 0 under torchrun) */
+int nf_simple_local_rows(nf_simple*, int k, int* row_begin, int* row_end);
 int nf_simple_destroy(nf_simple*);
 int nf_simple_ld(nf_simple*);
 /* device arrays (row pitch nf_simple_ld): which = 0 u, 1 v, 2 p, 3 u_star, 4 v_star, 5 d_u, 6 d_v,
  * 7 p_prime, 8 b, 9 pressure residual field, 10 u residual field, 11 v residual field */
 double* nf_simple_field(nf_simple*, int which);
-/* host <-> device copies of a field; host arrays are C-contiguous (rows, cols) */
+/* host <-> device copies of a field; host arrays are the FULL C-contiguous (rows, cols) fields: every local slab
+ * takes its rows (halo included) on upload and writes only the rows it owns on download */
 int nf_simple_upload(nf_simple*, int which, const double* host, int rows, int cols);
 int nf_simple_download(nf_simple*, int which, double* host, int rows, int cols);
 /* runs outer iterations until max(u_rel_norm, v_rel_norm) <= tolerance or n_iterations are done

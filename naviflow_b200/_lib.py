@@ -120,6 +120,12 @@ SIGNATURES = {
     "nf_max_abs_divergence": (C.c_int, [CTX, GP, P, P, DBL_OUT]),
     "nf_simple_create": (C.c_int, [CTX, C.POINTER(C.c_void_p), C.POINTER(NfSimpleConfig)]),
     "nf_simple_destroy": (C.c_int, [C.c_void_p]),
+    "nf_nccl_unique_id": (C.c_int, [CTX, C.c_void_p]),
+    "nf_team_create_nccl": (C.c_int, [CTX, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "nf_team_create_virtual": (C.c_int, [CTX, C.c_int, C.POINTER(C.c_void_p)]),
+    "nf_team_free": (C.c_int, [C.c_void_p]),
+    "nf_simple_create_team": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(NfSimpleConfig)]),
+    "nf_simple_local_rows": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "nf_simple_ld": (C.c_int, [C.c_void_p]),
     "nf_simple_field": (C.c_void_p, [C.c_void_p, C.c_int]),
     "nf_simple_upload": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]),

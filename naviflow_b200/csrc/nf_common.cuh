@@ -185,7 +185,8 @@ int nfi_apply(nf_ctx*, const nf_grid*, const double* p, const double* d_u, const
 // sum of squares of x over the cells of g -> device scalar ctx->scalars[slot] (asynchronous)
 int nfi_sumsq_dev(nf_ctx*, const nf_grid*, const double* x, int interior_only, int slot);
 int nfi_residual_norms(nf_ctx*, const nf_grid*, const double* p, const double* b, const double* d_u, const double* d_v,
-                       double* r, int with_b, int slot);
+                       double* r, int with_b, double* out);
+int nfi_sumsq_to(nf_ctx*, const nf_grid*, const double* x, int interior_only, double* out);
 int nfi_fill(nf_ctx*, double* x, size_t count, double value);
 int nfi_restrict_fw(nf_ctx*, const nf_grid* fine, const double* f, const nf_grid* coarse, double* c);
 int nfi_restrict_inject(nf_ctx*, const nf_grid* fine, const double* f, const nf_grid* coarse, double* c);

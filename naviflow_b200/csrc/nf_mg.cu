@@ -1,4 +1,4 @@
-// nf_mg.cu -- geometric multigrid driver (K13 + cycle control), fp64.
+// nf_mg.cu -- geometric multigrid driver (K13 + cycle control), fp64, single GPU or row slabs.
 //
 // Reference: pressure_solver/multigrid.py (paths relative to /root/reference/naviflow_oo)
 //   solve :121-266, _solve_residual_direct :268-302, _v_cycle :304-432, _w_cycle :434-560,
@@ -8,11 +8,20 @@
 // the reference's.  The coarsest level (nx <= coarsest_grid_size) is solved exactly: the reference
 // uses SuperLU (spsolve); here the dense matrix is inverted once per setup by Gauss-Jordan with
 // partial pivoting in one thread block and applied as a mat-vec.
+//
+// Every phase of a cycle is written as "for each slab this process owns: launch; then exchange halos"
+// (nf_slab.cuh).  Fine levels are cut into row slabs; once a slab would get thinner than NF_MIN_SLAB_ROWS the
+// level (and all coarser ones) is replicated on every rank: the restricted right-hand side is shared once
+// and the coarse part of the cycle runs redundantly, so the way back up needs no communication.
 #include <math.h>
 
 #include <vector>
 
 #include "nf_pressure.cuh"
+#include "nf_slab.cuh"
+
+#define NF_MIN_SLAB_ROWS 64   // a level is cut only while every rank keeps at least this many rows
+#define NF_SMOOTH_HALO 6      // halo depth consumed by one fused smoother launch (2 * 3 sweeps)
 
 int nfi_residual_restrict_fw(nf_ctx*, const nf_grid* gf, const double* p, const double* b, const double* d_u,
                              const double* d_v, const nf_grid* gc, double* c);
@@ -22,32 +31,35 @@ int nfi_inv_diag(nf_ctx*, const nf_grid*, const double* d_u, const double* d_v, 
 int nfi_prolong_banded(nf_ctx*, const nf_grid* gc, const double* c, const nf_grid* gf, double* f, double* tmp,
                        int ldt, const double* band, const int* start, int W, int add);
 
+struct MgSlab {  // arrays of one (level, local rank)
+  double *x = nullptr, *x2 = nullptr, *b = nullptr, *r = nullptr;  // r doubles as the Jacobi ping-pong buffer
+  double *d_u = nullptr, *d_v = nullptr, *inv = nullptr;
+  bool owns_x = false, owns_b = false, owns_d = false;
+};
+
 struct MgLevel {
-  nf_grid g;
-  double *x = nullptr, *b = nullptr, *r = nullptr;  // r doubles as the Jacobi ping-pong buffer
-  double* x2 = nullptr;                              // second solution buffer (fused SOR is double buffered)
-  double* inv = nullptr;                             // 1/aP of the SOR update, rebuilt by nf_mg_setup
-  double *d_u = nullptr, *d_v = nullptr;
+  LevelGeom geom;
+  std::vector<int> rgb, rge;   // rows of THIS level each rank restricts into (ownership induced by the finer level)
+  std::vector<MgSlab> s;       // one per local rank
   // banded 1-D interpolation matrix from the next-coarser level onto this level (cubic prolongation)
   double* band = nullptr;
   int* start = nullptr;
   int W = 0;
-  double* ptmp = nullptr;  // (nx x ld_coarse) scratch of the separable prolongation
-  size_t elems = 0;        // allocation size of p-like arrays, (nx+1)*ld
+  double* ptmp = nullptr;
 };
 
 struct nf_mg {
   nf_ctx* ctx = nullptr;
+  nf_team* team = nullptr;
+  bool owns_team = false;
   nf_mg_config cfg;
   std::vector<MgLevel> lv;
-  double* coarse_A = nullptr;    // N x N work matrix
-  double* coarse_inv = nullptr;  // N x N inverse
+  std::vector<double*> coarse_A, coarse_inv;  // per local rank
+  std::vector<double*> scal;                  // per local rank: 8 device doubles for the norms
+  double* scal_host = nullptr;                // pinned
   int coarse_N = 0;
   bool setup_done = false;
-  const double *fine_du = nullptr, *fine_dv = nullptr;
 };
-
-static inline int pad_ld(int ny) { return ((ny + 1 + 15) / 16) * 16; }
 
 // ---------------------------------------------------------------------------------------------
 // K13 coarsest-level matrix (helpers/coeff_matrix.py:6-121 with the pin row :114-119), unknown
@@ -234,37 +246,58 @@ static void build_interp_band(int mc, int m, int K, std::vector<double>& band, s
 // =============================================================================================
 // create / destroy / setup
 // =============================================================================================
-static void free_level(MgLevel& L, bool owns_coeffs) {
-  if (L.x && owns_coeffs) cudaFree(L.x);
-  if (L.x2) cudaFree(L.x2);
-  if (L.inv) cudaFree(L.inv);
-  if (L.b) cudaFree(L.b);
-  if (L.r) cudaFree(L.r);
-  if (owns_coeffs) {
-    if (L.d_u) cudaFree(L.d_u);
-    if (L.d_v) cudaFree(L.d_v);
-  }
-  if (L.band) cudaFree(L.band);
-  if (L.start) cudaFree(L.start);
-  if (L.ptmp) cudaFree(L.ptmp);
-}
+static int nlocal(const nf_mg* mg) { return (int)mg->team->local.size(); }
 
 extern "C" int nf_mg_destroy(nf_mg* mg) {
   if (!mg) return NF_OK;
   cudaSetDevice(mg->ctx->device);
   cudaStreamSynchronize(mg->ctx->stream);
-  for (size_t l = 0; l < mg->lv.size(); ++l) free_level(mg->lv[l], l > 0);
-  if (mg->coarse_A) cudaFree(mg->coarse_A);
-  if (mg->coarse_inv) cudaFree(mg->coarse_inv);
+  for (MgLevel& L : mg->lv) {
+    for (MgSlab& S : L.s) {
+      if (S.owns_x && S.x) cudaFree(S.x);
+      if (S.x2) cudaFree(S.x2);
+      if (S.owns_b && S.b) cudaFree(S.b);
+      if (S.r) cudaFree(S.r);
+      if (S.owns_d) { if (S.d_u) cudaFree(S.d_u); if (S.d_v) cudaFree(S.d_v); }
+      if (S.inv) cudaFree(S.inv);
+    }
+    if (L.band) cudaFree(L.band);
+    if (L.start) cudaFree(L.start);
+    if (L.ptmp) cudaFree(L.ptmp);
+  }
+  for (double* p : mg->coarse_A) if (p) cudaFree(p);
+  for (double* p : mg->coarse_inv) if (p) cudaFree(p);
+  for (double* p : mg->scal) if (p) cudaFree(p);
+  if (mg->scal_host) cudaFreeHost(mg->scal_host);
+  if (mg->owns_team) nf_team_destroy(mg->team);
   delete mg;
   return NF_OK;
 }
 
-extern "C" int nf_mg_create(nf_ctx* ctx, nf_mg** out, int nx, int ny, int ld, const nf_mg_config* cfg) {
+static bool dev_alloc(nf_ctx* ctx, double** p, size_t elems) {
+  if (cudaMalloc(p, elems * sizeof(double)) != cudaSuccess) return false;
+  cudaMemsetAsync(*p, 0, elems * sizeof(double), ctx->stream);
+  return true;
+}
+
+// level-0 geometry of a team (shared with the SIMPLE driver)
+LevelGeom nf_level0_geom(const nf_team* team, int nx, int ny, int ld, double length, double height, double rho) {
+  LevelGeom g;
+  g.nx = nx; g.ny = ny; g.ld = ld;
+  g.dx = length / (nx - 1);  // StructuredMesh(n, n, L, H): structured.py:27-28
+  g.dy = height / (ny - 1);
+  g.rho = rho;
+  g.dist = nf_split_rows(nx, team->world, NF_MIN_SLAB_ROWS, g.gb, g.ge);
+  g.halo = g.dist ? NF_HALO : 0;
+  return g;
+}
+
+int nfi_mg_create(nf_team* team, nf_mg** out, int nx, int ny, int ld, const nf_mg_config* cfg) {
+  nf_ctx* ctx = team->ctx;
   NF_REQUIRE(ctx, out && cfg, "NULL argument");
   *out = nullptr;
   NF_REQUIRE(ctx, nx == ny, "multigrid needs a square grid (the reference's transfer operators assume it)");
-  NF_REQUIRE(ctx, nx >= 3 && ld >= ny + 1, "bad grid");
+  NF_REQUIRE(ctx, nx >= 3 && ld >= ny + 1 && (ld % 2) == 0, "bad grid (ld must be even and >= ny+1)");
   NF_REQUIRE(ctx, cfg->coarsest >= 3 && (cfg->coarsest % 2) == 1, "coarsest_grid_size must be odd and >= 3");  // multigrid.py:82-85
   NF_REQUIRE(ctx, cfg->smoother == 0 || cfg->smoother == 1, "smoother must be 0 (red-black SOR) or 1 (Jacobi)");
   NF_REQUIRE(ctx, cfg->restriction == 0 || cfg->restriction == 1, "bad restriction");
@@ -273,47 +306,62 @@ extern "C" int nf_mg_create(nf_ctx* ctx, nf_mg** out, int nx, int ny, int ld, co
   NF_REQUIRE(ctx, cfg->pre >= 0 && cfg->post >= 0, "negative smoothing count");
   nf_mg* mg = new nf_mg();
   mg->ctx = ctx;
+  mg->team = team;
   mg->cfg = *cfg;
+  const int nl = (int)team->local.size();
+  // level chain
   int n = nx;
-  int cur_ld = ld;
   for (;;) {
     MgLevel L;
-    L.g.nx = n; L.g.ny = n; L.g.ld = cur_ld; L.g.row0 = 0; L.g.gb = 0; L.g.ge = n;
-    L.g.dx = cfg->length / (n - 1);  // StructuredMesh(nc, nc, L, H): structured.py:27-28
-    L.g.dy = cfg->height / (n - 1);
-    L.g.rho = cfg->rho;
-    L.elems = (size_t)(n + 1) * cur_ld;
+    if (mg->lv.empty()) {
+      L.geom = nf_level0_geom(team, n, n, ld, cfg->length, cfg->height, cfg->rho);
+      L.rgb = L.geom.gb; L.rge = L.geom.ge;
+    } else {
+      const MgLevel& F = mg->lv.back();
+      LevelGeom g;
+      g.nx = n; g.ny = n; g.ld = nf_pad_ld(n);
+      g.dx = cfg->length / (n - 1); g.dy = cfg->height / (n - 1); g.rho = cfg->rho;
+      // rows each rank produces when it restricts its part of the finer level
+      if (F.geom.dist) nf_coarsen_split(F.geom.gb, F.geom.ge, n, L.rgb, L.rge);
+      else { L.rgb.assign(team->world, 0); L.rge.assign(team->world, n); }
+      bool cut = F.geom.dist;
+      if (cut)
+        for (int r = 0; r < team->world; ++r)
+          if (L.rge[r] - L.rgb[r] < NF_MIN_SLAB_ROWS) cut = false;
+      g.dist = cut;
+      g.halo = cut ? NF_HALO : 0;
+      if (cut) { g.gb = L.rgb; g.ge = L.rge; }
+      else { g.gb.assign(team->world, 0); g.ge.assign(team->world, n); }
+      L.geom = g;
+    }
     mg->lv.push_back(L);
     if (n <= cfg->coarsest) break;
     const int nc = cfg->restriction == 0 ? (n - 1) / 2 : n / 2;
-    if (nc < 2) break;  // cannot coarsen further (degenerate; reference would fail as well)
+    if (nc < 2) break;  // cannot coarsen further (degenerate; the reference would fail as well)
     n = nc;
-    cur_ld = pad_ld(n);
   }
   const bool need_cubic = (cfg->interpolation == 1) || (cfg->cycle_type == 2);  // FMG hard-codes cubic (:631)
+  if (need_cubic && mg->lv[0].geom.dist) {
+    ctx->err = "cubic prolongation (interpolate_cubic / FMG) is a whole-grid spline: not available on a slab-decomposed grid";
+    nf_mg_destroy(mg);
+    return NF_ERR_UNSUPPORTED;
+  }
   bool ok = true;
   for (size_t l = 0; l < mg->lv.size() && ok; ++l) {
     MgLevel& L = mg->lv[l];
-    const size_t bytes = L.elems * sizeof(double);
-    ok = ok && cudaMalloc(&L.r, bytes) == cudaSuccess && cudaMalloc(&L.x2, bytes) == cudaSuccess;
-    if (ok) cudaMemsetAsync(L.x2, 0, bytes, ctx->stream);
-    if (ok && cfg->smoother == 0) {
-      ok = cudaMalloc(&L.inv, bytes) == cudaSuccess;
-      if (ok) cudaMemsetAsync(L.inv, 0, bytes, ctx->stream);
-    }
-    if (l > 0) {
-      ok = ok && cudaMalloc(&L.x, bytes) == cudaSuccess && cudaMalloc(&L.b, bytes) == cudaSuccess &&
-           cudaMalloc(&L.d_u, bytes) == cudaSuccess && cudaMalloc(&L.d_v, bytes) == cudaSuccess;
-      if (ok) {
-        cudaMemsetAsync(L.x, 0, bytes, ctx->stream);
-        cudaMemsetAsync(L.b, 0, bytes, ctx->stream);
-        cudaMemsetAsync(L.d_u, 0, bytes, ctx->stream);
-        cudaMemsetAsync(L.d_v, 0, bytes, ctx->stream);
+    L.s.resize(nl);
+    for (int k = 0; k < nl && ok; ++k) {
+      MgSlab& S = L.s[k];
+      const size_t e = L.geom.elems(team->local[k]);
+      ok = ok && dev_alloc(ctx, &S.r, e) && dev_alloc(ctx, &S.x2, e);
+      if (l > 0) {
+        ok = ok && dev_alloc(ctx, &S.x, e) && dev_alloc(ctx, &S.b, e) && dev_alloc(ctx, &S.d_u, e) && dev_alloc(ctx, &S.d_v, e);
+        S.owns_x = S.owns_b = S.owns_d = true;
       }
+      if (cfg->smoother == 0) ok = ok && dev_alloc(ctx, &S.inv, e);
     }
-    if (ok) cudaMemsetAsync(L.r, 0, bytes, ctx->stream);
     if (ok && need_cubic && l + 1 < mg->lv.size()) {
-      const int mc = mg->lv[l + 1].g.nx, m = L.g.nx;
+      const int mc = mg->lv[l + 1].geom.nx, m = L.geom.nx;
       std::vector<double> band;
       std::vector<int> start;
       int W = 0;
@@ -321,22 +369,26 @@ extern "C" int nf_mg_create(nf_ctx* ctx, nf_mg** out, int nx, int ny, int ld, co
       L.W = W;
       ok = ok && cudaMalloc(&L.band, band.size() * sizeof(double)) == cudaSuccess &&
            cudaMalloc(&L.start, start.size() * sizeof(int)) == cudaSuccess &&
-           cudaMalloc(&L.ptmp, (size_t)m * mg->lv[l + 1].g.ld * sizeof(double)) == cudaSuccess;
-      if (ok) {
+           cudaMalloc(&L.ptmp, (size_t)m * mg->lv[l + 1].geom.ld * sizeof(double)) == cudaSuccess;
+      if (ok)
         ok = cudaMemcpy(L.band, band.data(), band.size() * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess &&
              cudaMemcpy(L.start, start.data(), start.size() * sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess;
-      }
     }
   }
   const MgLevel& C = mg->lv.back();
-  mg->coarse_N = C.g.nx * C.g.ny;
-  if (ok && mg->coarse_N > 4096) {
+  mg->coarse_N = C.geom.nx * C.geom.ny;
+  if (ok && (mg->coarse_N > 4096 || C.geom.dist)) {
     ctx->err = "coarsest level too large for the dense coarse solve (nx*ny must be <= 4096)";
     nf_mg_destroy(mg);
     return NF_ERR_UNSUPPORTED;
   }
-  ok = ok && cudaMalloc(&mg->coarse_A, (size_t)mg->coarse_N * mg->coarse_N * sizeof(double)) == cudaSuccess &&
-       cudaMalloc(&mg->coarse_inv, (size_t)mg->coarse_N * mg->coarse_N * sizeof(double)) == cudaSuccess;
+  mg->coarse_A.assign(nl, nullptr);
+  mg->coarse_inv.assign(nl, nullptr);
+  mg->scal.assign(nl, nullptr);
+  for (int k = 0; k < nl && ok; ++k)
+    ok = dev_alloc(ctx, &mg->coarse_A[k], (size_t)mg->coarse_N * mg->coarse_N) &&
+         dev_alloc(ctx, &mg->coarse_inv[k], (size_t)mg->coarse_N * mg->coarse_N) && dev_alloc(ctx, &mg->scal[k], 8);
+  ok = ok && cudaMallocHost(&mg->scal_host, 8 * sizeof(double)) == cudaSuccess;
   if (!ok) {
     ctx->err = std::string("multigrid allocation failed: ") + cudaGetErrorString(cudaGetLastError());
     nf_mg_destroy(mg);
@@ -346,152 +398,299 @@ extern "C" int nf_mg_create(nf_ctx* ctx, nf_mg** out, int nx, int ny, int ld, co
   return NF_OK;
 }
 
+extern "C" int nf_mg_create(nf_ctx* ctx, nf_mg** out, int nx, int ny, int ld, const nf_mg_config* cfg) {
+  nf_team* team = nullptr;
+  NF_TRY(nf_team_create_local(ctx, 1, &team));
+  int st = nfi_mg_create(team, out, nx, ny, ld, cfg);
+  if (st != NF_OK) { nf_team_destroy(team); return st; }
+  (*out)->owns_team = true;
+  return NF_OK;
+}
+
 extern "C" int nf_mg_num_levels(nf_mg* mg) { return mg ? (int)mg->lv.size() : 0; }
 
 extern "C" int nf_mg_level_shape(nf_mg* mg, int level, int* nx, int* ny, int* ld) {
   if (!mg || level < 0 || level >= (int)mg->lv.size()) return NF_ERR_ARG;
-  if (nx) *nx = mg->lv[level].g.nx;
-  if (ny) *ny = mg->lv[level].g.ny;
-  if (ld) *ld = mg->lv[level].g.ld;
+  if (nx) *nx = mg->lv[level].geom.nx;
+  if (ny) *ny = mg->lv[level].geom.ny;
+  if (ld) *ld = mg->lv[level].geom.ld;
   return NF_OK;
 }
 
-// level arrays for tests / callers that want to look at the hierarchy: which = 0 d_u, 1 d_v, 2 x, 3 b, 4 r
+// level arrays of the first local slab (tests / inspection): which = 0 d_u, 1 d_v, 2 x, 3 b, 4 r
 extern "C" const double* nf_mg_level_array(nf_mg* mg, int level, int which) {
   if (!mg || level < 0 || level >= (int)mg->lv.size()) return nullptr;
-  const MgLevel& L = mg->lv[level];
+  const MgSlab& S = mg->lv[level].s[0];
   switch (which) {
-    case 0: return L.d_u;
-    case 1: return L.d_v;
-    case 2: return L.x;
-    case 3: return L.b;
-    case 4: return L.r;
+    case 0: return S.d_u;
+    case 1: return S.d_v;
+    case 2: return S.x;
+    case 3: return S.b;
+    case 4: return S.r;
   }
   return nullptr;
 }
 
-extern "C" int nf_mg_setup(nf_mg* mg, const double* d_u, const double* d_v) {
-  if (!mg) return NF_ERR_ARG;
+static std::vector<double*> field_of(MgLevel& L, double* MgSlab::*m) {
+  std::vector<double*> v;
+  for (MgSlab& S : L.s) v.push_back(S.*m);
+  return v;
+}
+
+// grid a rank restricts INTO at level l+1: the coarse level's own slab grid when it is cut, else the full
+// (replicated) array with the row range induced by the finer partition
+static nf_grid restrict_target(const MgLevel& C, int rank) {
+  nf_grid g = C.geom.grid(rank);
+  g.gb = C.rgb[rank];
+  g.ge = C.rge[rank];
+  return g;
+}
+
+// d_u, d_v: per local slab; on a cut level they must be valid NF_HALO-1 rows beyond the owned rows
+int nfi_mg_setup(nf_mg* mg, double* const* d_u, double* const* d_v) {
   nf_ctx* ctx = mg->ctx;
-  NF_REQUIRE(ctx, d_u && d_v, "NULL coefficient array");
-  mg->lv[0].d_u = const_cast<double*>(d_u);
-  mg->lv[0].d_v = const_cast<double*>(d_v);
-  for (size_t l = 0; l + 1 < mg->lv.size(); ++l)
-    NF_TRY(nfi_restrict_coeffs(ctx, &mg->lv[l].g, mg->lv[l].d_u, mg->lv[l].d_v, &mg->lv[l + 1].g, mg->lv[l + 1].d_u,
-                               mg->lv[l + 1].d_v));
-  if (mg->cfg.smoother == 0)
-    for (size_t l = 0; l < mg->lv.size(); ++l)
-      NF_TRY(nfi_inv_diag(ctx, &mg->lv[l].g, mg->lv[l].d_u, mg->lv[l].d_v, mg->lv[l].inv));
-  const MgLevel& C = mg->lv.back();
-  if (C.g.nx <= mg->cfg.coarsest) {
-    k_coarse_invert<<<1, 1024, 0, ctx->stream>>>(C.g, C.d_u, C.d_v, mg->coarse_A, mg->coarse_inv, mg->coarse_N);
-    NF_LAUNCH_CHECK(ctx);
+  nf_team* team = mg->team;
+  const int nl = nlocal(mg);
+  for (int k = 0; k < nl; ++k) {
+    NF_REQUIRE(ctx, d_u[k] && d_v[k], "NULL coefficient array");
+    mg->lv[0].s[k].d_u = d_u[k];
+    mg->lv[0].s[k].d_v = d_v[k];
   }
+  for (size_t l = 0; l + 1 < mg->lv.size(); ++l) {
+    MgLevel& L = mg->lv[l];
+    MgLevel& C = mg->lv[l + 1];
+    for (int k = 0; k < nl; ++k) {
+      const int r = team->local[k];
+      const nf_grid gf = L.geom.grid(r), gc = restrict_target(C, r);
+      NF_TRY(nfi_restrict_coeffs(ctx, &gf, L.s[k].d_u, L.s[k].d_v, &gc, C.s[k].d_u, C.s[k].d_v));
+    }
+    if (L.geom.dist) {
+      std::vector<double*> du = field_of(C, &MgSlab::d_u), dv = field_of(C, &MgSlab::d_v);
+      if (C.geom.dist) {
+        NF_TRY(nf_team_exchange(team, C.geom, du.data(), NF_HALO));
+        NF_TRY(nf_team_exchange(team, C.geom, dv.data(), NF_HALO));
+      } else {
+        NF_TRY(nf_team_share_rows(team, C.geom.ld, C.geom.nx, C.rgb, C.rge, du.data(), 1));
+        NF_TRY(nf_team_share_rows(team, C.geom.ld, C.geom.nx, C.rgb, C.rge, dv.data(), 0));
+      }
+    }
+  }
+  if (mg->cfg.smoother == 0)
+    for (MgLevel& L : mg->lv)
+      for (int k = 0; k < nl; ++k) {
+        const nf_grid g = L.geom.grid_ext(team->local[k], NF_SMOOTH_HALO);
+        NF_TRY(nfi_inv_diag(ctx, &g, L.s[k].d_u, L.s[k].d_v, L.s[k].inv));
+      }
+  MgLevel& C = mg->lv.back();
+  if (C.geom.nx <= mg->cfg.coarsest)
+    for (int k = 0; k < nl; ++k) {
+      k_coarse_invert<<<1, 1024, 0, ctx->stream>>>(C.geom.grid(team->local[k]), C.s[k].d_u, C.s[k].d_v,
+                                                   mg->coarse_A[k], mg->coarse_inv[k], mg->coarse_N);
+      NF_LAUNCH_CHECK(ctx);
+    }
   mg->setup_done = true;
   return NF_OK;
 }
 
-// =============================================================================================
-// cycles
-// =============================================================================================
-// smoothing may move the iterate to the other buffer: (*x, *alt) are swapped accordingly
-static int mg_smooth(nf_mg* mg, int l, double** x, double** alt, const double* b, int n) {
-  MgLevel& L = mg->lv[l];
-  if (mg->cfg.smoother == 0) return nfi_rbsor_fused(mg->ctx, &L.g, x, alt, b, L.d_u, L.d_v, L.inv, mg->cfg.omega, n);
-  return nfi_jacobi(mg->ctx, &L.g, *x, L.r, b, L.d_u, L.d_v, mg->cfg.omega, n);
+extern "C" int nf_mg_setup(nf_mg* mg, const double* d_u, const double* d_v) {
+  if (!mg) return NF_ERR_ARG;
+  NF_REQUIRE(mg->ctx, nlocal(mg) == 1, "nf_mg_setup is the single-slab entry point");
+  double* du = const_cast<double*>(d_u);
+  double* dv = const_cast<double*>(d_v);
+  return nfi_mg_setup(mg, &du, &dv);
 }
 
-static int mg_coarse_solve(nf_mg* mg, int l, double* x, const double* b) {
+// =============================================================================================
+// cycles.  Level-0 solution / right-hand side live in lv[0].s[k].x / .b (set by the callers).
+// =============================================================================================
+// n smoothing sweeps on level l; on a cut level the iterate's halo is valid on entry and on return
+static int mg_smooth(nf_mg* mg, int l, int n) {
   nf_ctx* ctx = mg->ctx;
-  const MgLevel& L = mg->lv[l];
-  const int N = mg->coarse_N;
-  const int threads = 128, blocks = (N * 32 + threads - 1) / threads;
-  k_coarse_apply<<<blocks, threads, 0, ctx->stream>>>(L.g, mg->coarse_inv, b, x, N);
-  NF_LAUNCH_CHECK(ctx);
+  nf_team* team = mg->team;
+  MgLevel& L = mg->lv[l];
+  const int nl = nlocal(mg);
+  if (mg->cfg.smoother == 0) {
+    int left = n;
+    if (left == 0)
+      for (int k = 0; k < nl; ++k) {
+        const nf_grid g = L.geom.grid(team->local[k]);
+        NF_TRY(nfi_rbsor_fused(ctx, &g, &L.s[k].x, &L.s[k].x2, L.s[k].b, L.s[k].d_u, L.s[k].d_v, L.s[k].inv,
+                               mg->cfg.omega, 0));
+      }
+    while (left > 0) {
+      const int ns = left >= 3 ? 3 : left;
+      for (int k = 0; k < nl; ++k) {
+        const nf_grid g = L.geom.grid(team->local[k]);
+        NF_TRY(nfi_rbsor_fused(ctx, &g, &L.s[k].x, &L.s[k].x2, L.s[k].b, L.s[k].d_u, L.s[k].d_v, L.s[k].inv,
+                               mg->cfg.omega, ns));
+      }
+      if (L.geom.dist) {
+        std::vector<double*> x = field_of(L, &MgSlab::x);
+        NF_TRY(nf_team_exchange(team, L.geom, x.data(), NF_SMOOTH_HALO));
+      }
+      left -= ns;
+    }
+    return NF_OK;
+  }
+  // weighted Jacobi: one halo row per iteration
+  for (int it = 0; it < (n > 0 ? n : 1); ++it) {
+    for (int k = 0; k < nl; ++k) {
+      const nf_grid g = L.geom.grid(team->local[k]);
+      NF_TRY(nfi_jacobi(ctx, &g, L.s[k].x, L.s[k].r, L.s[k].b, L.s[k].d_u, L.s[k].d_v, mg->cfg.omega, n > 0 ? 1 : 0));
+    }
+    if (L.geom.dist) {
+      std::vector<double*> x = field_of(L, &MgSlab::x);
+      NF_TRY(nf_team_exchange(team, L.geom, x.data(), NF_SMOOTH_HALO));
+    }
+  }
   return NF_OK;
 }
 
-static int mg_prolong_add(nf_mg* mg, int l, double* x, int cubic, int add) {
-  // x_l (+)= P x_{l+1}
+static int mg_coarse_solve(nf_mg* mg, int l) {
+  nf_ctx* ctx = mg->ctx;
+  MgLevel& L = mg->lv[l];
+  const int N = mg->coarse_N;
+  const int threads = 128, blocks = (N * 32 + threads - 1) / threads;
+  for (int k = 0; k < nlocal(mg); ++k) {
+    k_coarse_apply<<<blocks, threads, 0, ctx->stream>>>(L.geom.grid(mg->team->local[k]), mg->coarse_inv[k], L.s[k].b,
+                                                        L.s[k].x, N);
+    NF_LAUNCH_CHECK(ctx);
+  }
+  return NF_OK;
+}
+
+// x_l (+)= P x_{l+1}; on a cut level the halo rows the smoother reads are produced locally as well
+static int mg_prolong(nf_mg* mg, int l, int cubic, int add) {
+  nf_team* team = mg->team;
   MgLevel& L = mg->lv[l];
   MgLevel& C = mg->lv[l + 1];
-  if (!cubic) return nfi_prolong_linear(mg->ctx, &C.g, C.x, &L.g, x, add);
-  return nfi_prolong_banded(mg->ctx, &C.g, C.x, &L.g, x, L.ptmp, C.g.ld, L.band, L.start, L.W, add);
+  for (int k = 0; k < nlocal(mg); ++k) {
+    const int r = team->local[k];
+    const nf_grid gc = C.geom.grid(r), gf = L.geom.grid_ext(r, NF_SMOOTH_HALO);
+    if (!cubic) NF_TRY(nfi_prolong_linear(mg->ctx, &gc, C.s[k].x, &gf, L.s[k].x, add));
+    else NF_TRY(nfi_prolong_banded(mg->ctx, &gc, C.s[k].x, &gf, L.s[k].x, L.ptmp, gc.ld, L.band, L.start, L.W, add));
+  }
+  return NF_OK;
+}
+
+// after a restriction into level l+1: make the new right-hand side visible where the coarse level needs it
+static int mg_publish_rhs(nf_mg* mg, int l) {
+  MgLevel& L = mg->lv[l];
+  MgLevel& C = mg->lv[l + 1];
+  if (!L.geom.dist) return NF_OK;
+  std::vector<double*> b = field_of(C, &MgSlab::b);
+  if (C.geom.dist) return nf_team_exchange(mg->team, C.geom, b.data(), NF_SMOOTH_HALO);
+  return nf_team_share_rows(mg->team, C.geom.ld, C.geom.nx, C.rgb, C.rge, b.data(), 0);
 }
 
 // one V (kind 0) or W (kind 1) cycle on level l: multigrid.py:304-432 / :434-560
-static int mg_cycle(nf_mg* mg, int l, double** x, double** alt, const double* b, int kind) {
+static int mg_cycle(nf_mg* mg, int l, int kind) {
   nf_ctx* ctx = mg->ctx;
+  nf_team* team = mg->team;
   MgLevel& L = mg->lv[l];
-  if (L.g.nx <= mg->cfg.coarsest || l + 1 == (int)mg->lv.size()) return mg_coarse_solve(mg, l, *x, b);
+  const int nl = nlocal(mg);
+  if (L.geom.nx <= mg->cfg.coarsest || l + 1 == (int)mg->lv.size()) return mg_coarse_solve(mg, l);
   MgLevel& C = mg->lv[l + 1];
-  NF_TRY(mg_smooth(mg, l, x, alt, b, mg->cfg.pre));
-  if (mg->cfg.restriction == 0) {
-    NF_TRY(nfi_residual_restrict_fw(ctx, &L.g, *x, b, L.d_u, L.d_v, &C.g, C.b));
-  } else {
-    NF_TRY(nfi_residual(ctx, &L.g, *x, b, L.d_u, L.d_v, L.r));
-    NF_TRY(nfi_restrict_inject(ctx, &L.g, L.r, &C.g, C.b));
+  NF_TRY(mg_smooth(mg, l, mg->cfg.pre));
+  for (int k = 0; k < nl; ++k) {
+    const int r = team->local[k];
+    const nf_grid gf = L.geom.grid(r), gc = restrict_target(C, r);
+    if (mg->cfg.restriction == 0) {
+      NF_TRY(nfi_residual_restrict_fw(ctx, &gf, L.s[k].x, L.s[k].b, L.s[k].d_u, L.s[k].d_v, &gc, C.s[k].b));
+    } else {
+      NF_TRY(nfi_residual(ctx, &gf, L.s[k].x, L.s[k].b, L.s[k].d_u, L.s[k].d_v, L.s[k].r));
+      NF_TRY(nfi_restrict_inject(ctx, &gf, L.s[k].r, &gc, C.s[k].b));
+    }
+    NF_TRY(nfi_fill(ctx, C.s[k].x, C.geom.elems(r), 0.0));
   }
-  NF_TRY(nfi_fill(ctx, C.x, (size_t)C.g.nx * C.g.ld, 0.0));
+  NF_TRY(mg_publish_rhs(mg, l));
   const int reps = (kind == 1) ? 2 : 1;
-  for (int rep = 0; rep < reps; ++rep) NF_TRY(mg_cycle(mg, l + 1, &C.x, &C.x2, C.b, kind));
-  NF_TRY(mg_prolong_add(mg, l, *x, mg->cfg.interpolation, 1));
-  NF_TRY(mg_smooth(mg, l, x, alt, b, mg->cfg.post));
+  for (int rep = 0; rep < reps; ++rep) NF_TRY(mg_cycle(mg, l + 1, kind));
+  NF_TRY(mg_prolong(mg, l, mg->cfg.interpolation, 1));
+  NF_TRY(mg_smooth(mg, l, mg->cfg.post));
   return NF_OK;
 }
 
-static int mg_restrict_rhs(nf_mg* mg, int l, const double* f) {
-  MgLevel& L = mg->lv[l];
-  MgLevel& C = mg->lv[l + 1];
-  if (mg->cfg.restriction == 0) return nfi_restrict_fw(mg->ctx, &L.g, f, &C.g, C.b);
-  return nfi_restrict_inject(mg->ctx, &L.g, f, &C.g, C.b);
-}
-
-// ||b - A x|| / ||b|| on level l (host value; multigrid.py:652-676)
-// *b_norm < 0 on entry: ||b|| is not known yet and is computed in the same pass; otherwise it is kept
-static int mg_rel_residual(nf_mg* mg, int l, const double* x, const double* b, double* r_norm, double* b_norm) {
+// ||b - A x|| and ||b|| on level l over the whole grid (host values; multigrid.py:185-189, :652-676).
+// *b_norm < 0 on entry: ||b|| is not known yet and is computed in the same pass; otherwise it is kept.
+// sync == 0: leave sum r^2, sum b^2 in scal[k][0..1] (already reduced over the team) and do not synchronise.
+static int mg_rel_residual(nf_mg* mg, int l, double* r_norm, double* b_norm, int sync) {
   nf_ctx* ctx = mg->ctx;
+  nf_team* team = mg->team;
   MgLevel& L = mg->lv[l];
+  const int nl = nlocal(mg);
   const int with_b = (*b_norm < 0.0) ? 1 : 0;
-  NF_TRY(nfi_residual_norms(ctx, &L.g, x, b, L.d_u, L.d_v, L.r, with_b, 0));
-  double s[2];
-  NF_TRY(nf_read_scalars(ctx, 0, with_b ? 2 : 1, s));
-  *r_norm = sqrt(s[0]);
-  if (with_b) *b_norm = sqrt(s[1]);
-  return NF_OK;
-}
-
-// level 0 iterates between the caller's x and the hierarchy's x2: bring the result home and restore x2
-static int mg_finish_level0(nf_mg* mg, double* x, double* cur, double* alt) {
-  nf_ctx* ctx = mg->ctx;
-  MgLevel& L = mg->lv[0];
-  if (cur != x) {  // cur is the hierarchy's own buffer, alt is the caller's array
-    NF_CHECK_CUDA(ctx, cudaMemcpyAsync(x, cur, (size_t)L.g.nx * L.g.ld * sizeof(double), cudaMemcpyDeviceToDevice,
-                                       ctx->stream));
-    L.x2 = cur;
-  } else {
-    L.x2 = alt;
+  for (int k = 0; k < nl; ++k) {
+    const nf_grid g = L.geom.grid(team->local[k]);
+    NF_TRY(nfi_residual_norms(ctx, &g, L.s[k].x, L.s[k].b, L.s[k].d_u, L.s[k].d_v, L.s[k].r, with_b, mg->scal[k]));
   }
+  if (L.geom.dist) NF_TRY(nf_team_allreduce(team, mg->scal.data(), with_b ? 2 : 1));
+  if (!sync) return NF_OK;
+  NF_CHECK_CUDA(ctx, cudaMemcpyAsync(mg->scal_host, mg->scal[0], 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  NF_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *r_norm = sqrt(mg->scal_host[0]);
+  if (with_b) *b_norm = sqrt(mg->scal_host[1]);
   return NF_OK;
 }
 
 // recursive FMG (multigrid.py:562-688): RHS restricted down, exact coarsest solve, cubic prolongation
 // (hard-coded :631), max_cycles_buildup cycles per level with early exit on ||r||/||b|| < tol.
-static int mg_fmg(nf_mg* mg, int l, double** x, double** alt, const double* b) {
+static int mg_fmg(nf_mg* mg, int l) {
+  nf_ctx* ctx = mg->ctx;
+  nf_team* team = mg->team;
   MgLevel& L = mg->lv[l];
-  if (L.g.nx <= mg->cfg.coarsest || l + 1 == (int)mg->lv.size()) return mg_coarse_solve(mg, l, *x, b);
+  if (L.geom.nx <= mg->cfg.coarsest || l + 1 == (int)mg->lv.size()) return mg_coarse_solve(mg, l);
   MgLevel& C = mg->lv[l + 1];
-  NF_TRY(mg_restrict_rhs(mg, l, b));
-  NF_TRY(mg_fmg(mg, l + 1, &C.x, &C.x2, C.b));
-  NF_TRY(mg_prolong_add(mg, l, *x, 1, 0));
+  for (int k = 0; k < nlocal(mg); ++k) {
+    const int r = team->local[k];
+    const nf_grid gf = L.geom.grid(r), gc = restrict_target(C, r);
+    if (mg->cfg.restriction == 0) NF_TRY(nfi_restrict_fw(ctx, &gf, L.s[k].b, &gc, C.s[k].b));
+    else NF_TRY(nfi_restrict_inject(ctx, &gf, L.s[k].b, &gc, C.s[k].b));
+  }
+  NF_TRY(mg_publish_rhs(mg, l));
+  NF_TRY(mg_fmg(mg, l + 1));
+  NF_TRY(mg_prolong(mg, l, 1, 0));
   for (int c = 0; c < mg->cfg.max_cycles_buildup; ++c) {
-    NF_TRY(mg_cycle(mg, l, x, alt, b, mg->cfg.cycle_buildup));
+    NF_TRY(mg_cycle(mg, l, mg->cfg.cycle_buildup));
     if (mg->cfg.tolerance < 1.0 && c + 1 < mg->cfg.max_cycles_buildup) {
-      double rn, bn = -1.0;
-      NF_TRY(mg_rel_residual(mg, l, *x, b, &rn, &bn));
+      double rn = 0.0, bn = -1.0;
+      NF_TRY(mg_rel_residual(mg, l, &rn, &bn, 1));
       const double rel = bn > 0.0 ? rn / bn : rn;
       if (rel < mg->cfg.tolerance) break;
     }
+  }
+  return NF_OK;
+}
+
+// Level 0 iterates between the caller's x and the hierarchy's x2: bring the result home, restore x2.
+static int mg_bind_level0(nf_mg* mg, double* const* b, double* const* x, double* const* r, std::vector<double*>& keep_x2,
+                          std::vector<double*>& keep_r) {
+  MgLevel& L = mg->lv[0];
+  keep_x2.clear(); keep_r.clear();
+  for (int k = 0; k < nlocal(mg); ++k) {
+    keep_x2.push_back(L.s[k].x2);
+    keep_r.push_back(L.s[k].r);
+    L.s[k].x = x[k];
+    L.s[k].b = const_cast<double*>(b[k]);
+    if (r && r[k]) L.s[k].r = r[k];  // residual field goes straight to the caller's array
+  }
+  return NF_OK;
+}
+
+static int mg_unbind_level0(nf_mg* mg, double* const* x, const std::vector<double*>& keep_x2,
+                            const std::vector<double*>& keep_r) {
+  nf_ctx* ctx = mg->ctx;
+  MgLevel& L = mg->lv[0];
+  for (int k = 0; k < nlocal(mg); ++k) {
+    MgSlab& S = L.s[k];
+    if (S.x != x[k]) {  // the result sits in the hierarchy's buffer: copy it into the caller's array
+      NF_CHECK_CUDA(ctx, cudaMemcpyAsync(x[k], S.x, L.geom.elems(mg->team->local[k]) * sizeof(double),
+                                         cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    S.x2 = keep_x2[k];
+    S.x = nullptr;
+    S.b = nullptr;
+    S.r = keep_r[k];
   }
   return NF_OK;
 }
@@ -500,57 +699,54 @@ extern "C" int nf_mg_cycle(nf_mg* mg, double* x, const double* b, int kind) {
   if (!mg) return NF_ERR_ARG;
   NF_REQUIRE(mg->ctx, mg->setup_done, "nf_mg_setup has not been called");
   NF_REQUIRE(mg->ctx, kind == 0 || kind == 1, "kind must be 0 ('v') or 1 ('w')");
-  double* cur = x;
-  double* alt = mg->lv[0].x2;
-  NF_TRY(mg_cycle(mg, 0, &cur, &alt, b, kind));
-  return mg_finish_level0(mg, x, cur, alt);
+  NF_REQUIRE(mg->ctx, nlocal(mg) == 1, "nf_mg_cycle is the single-slab entry point");
+  std::vector<double*> k2, kr;
+  double* bb = const_cast<double*>(b);
+  NF_TRY(mg_bind_level0(mg, &bb, &x, nullptr, k2, kr));
+  int st = mg_cycle(mg, 0, kind);
+  int st2 = mg_unbind_level0(mg, &x, k2, kr);
+  return st ? st : st2;
 }
 
-// MultiGridSolver.solve without get_rhs.  sync == 0 (FMG mode only): the final ||r||^2, ||b||^2 stay in the
-// context's device scalars 0,1 and no host synchronisation happens.
-int nfi_mg_solve(nf_mg* mg, const double* b, double* x, double* r, nf_mg_info* info, int sync) {
+// MultiGridSolver.solve without get_rhs, per local slab arrays.  sync == 0 (FMG mode only): the final ||r||^2,
+// ||b||^2 stay in mg->scal[k][0..1] and no host synchronisation happens.
+int nfi_mg_solve(nf_mg* mg, double* const* b, double* const* x, double* const* r, nf_mg_info* info, int sync) {
   nf_ctx* ctx = mg->ctx;
   NF_REQUIRE(ctx, mg->setup_done, "nf_mg_setup has not been called");
-  NF_REQUIRE(ctx, b && x, "NULL argument");
   MgLevel& L = mg->lv[0];
-  double* own_r = L.r;
-  if (r) L.r = r;  // residual field goes straight to the caller's array
+  std::vector<double*> k2, kr;
+  NF_TRY(mg_bind_level0(mg, b, x, r, k2, kr));
   int status = NF_OK;
   double rn = 0.0, bn = -1.0;  // bn < 0: ||b|| not computed yet
   int cycles = 0;
-  double* cur = x;
-  double* alt = L.x2;
   do {
-    status = nfi_fill(ctx, cur, (size_t)L.g.nx * L.g.ld, 0.0);  // x0 = 0 (multigrid.py:165)
+    for (int k = 0; k < nlocal(mg) && !status; ++k)
+      status = nfi_fill(ctx, L.s[k].x, L.geom.elems(mg->team->local[k]), 0.0);  // x0 = 0 (multigrid.py:165)
     if (status) break;
     if (mg->cfg.cycle_type == 2) {
-      status = mg_fmg(mg, 0, &cur, &alt, b);
+      status = mg_fmg(mg, 0);
       if (status) break;
       if (mg->cfg.cycle_final >= 0) {
-        status = mg_cycle(mg, 0, &cur, &alt, b, mg->cfg.cycle_final);
+        status = mg_cycle(mg, 0, mg->cfg.cycle_final);
         if (status) break;
         cycles = 1;
       }
-      if (sync) {
-        status = mg_rel_residual(mg, 0, cur, b, &rn, &bn);
-      } else {
-        status = nfi_residual_norms(ctx, &L.g, cur, b, L.d_u, L.d_v, L.r, 1, 0);
-      }
+      status = mg_rel_residual(mg, 0, &rn, &bn, sync);
     } else {
-      for (int k = 0; k < mg->cfg.max_iterations; ++k) {
-        status = mg_cycle(mg, 0, &cur, &alt, b, mg->cfg.cycle_type);
+      for (int it = 0; it < mg->cfg.max_iterations; ++it) {
+        status = mg_cycle(mg, 0, mg->cfg.cycle_type);
         if (status) break;
         ++cycles;
-        status = mg_rel_residual(mg, 0, cur, b, &rn, &bn);
+        status = mg_rel_residual(mg, 0, &rn, &bn, 1);
         if (status) break;
         const double rel = bn > 0.0 ? rn / bn : rn;
         if (rel < mg->cfg.tolerance) break;
       }
     }
   } while (0);
-  L.r = own_r;
+  int st2 = mg_unbind_level0(mg, x, k2, kr);
   if (status) return status;
-  NF_TRY(mg_finish_level0(mg, x, cur, alt));
+  if (st2) return st2;
   if (info) {
     info->r_norm = rn;
     info->b_norm = bn < 0.0 ? 0.0 : bn;
@@ -560,12 +756,15 @@ int nfi_mg_solve(nf_mg* mg, const double* b, double* x, double* r, nf_mg_info* i
   return NF_OK;
 }
 
+double* nfi_mg_scalars(nf_mg* mg, int k) { return mg->scal[k]; }
+
 extern "C" int nf_mg_solve(nf_mg* mg, const double* b, double* x, double* r, nf_mg_info* info) {
   if (!mg) return NF_ERR_ARG;
-  return nfi_mg_solve(mg, b, x, r, info, 1);
+  NF_REQUIRE(mg->ctx, nlocal(mg) == 1, "nf_mg_solve is the single-slab entry point");
+  NF_REQUIRE(mg->ctx, b && x, "NULL argument");
+  double* bb = const_cast<double*>(b);
+  return nfi_mg_solve(mg, &bb, &x, &r, info, 1);
 }
-
-nf_mg_config* nfi_mg_config(nf_mg* mg) { return &mg->cfg; }
 
 // standalone interpolate_cubic (tests, Python-level callers): builds the band on every call
 extern "C" int nf_prolong_cubic(nf_ctx* ctx, const nf_grid* gc, const double* c, const nf_grid* gf, double* f,

@@ -356,28 +356,12 @@ int nfi_momentum_jacobi(nf_ctx* ctx, const nf_grid* g, int is_u, nf_links L, dou
   return NF_OK;
 }
 
-// ping-pong variant for the device-resident loop: x0 is read-only, sweeps alternate between a and b,
-// *result points at the buffer holding the last iterate (n_sweeps == 0: a = copy of x0).
-int nfi_momentum_jacobi_pp(nf_ctx* ctx, const nf_grid* g, int is_u, nf_links L, const double* x0, double* a, double* b,
-                           int n_sweeps, double** result) {
-  if (n_sweeps == 0) {
-    const size_t rows = (size_t)(nf_row_end(*g, is_u) - g->gb);
-    NF_CHECK_CUDA(ctx, cudaMemcpyAsync(a + (size_t)(g->gb - g->row0) * g->ld, x0 + (size_t)(g->gb - g->row0) * g->ld,
-                                       rows * g->ld * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-    *result = a;
-    return NF_OK;
-  }
+// one sweep src -> dst over the rows [g.gb, g.ge) of the grid descriptor (slab runs pass a grown range)
+int nfi_momentum_sweep(nf_ctx* ctx, const nf_grid* g, int is_u, nf_links L, const double* src, double* dst) {
   NfLaunch2D l = nf_launch2d(nf_row_end(*g, is_u) - g->gb, nf_cols(*g, is_u));
-  const double* src = x0;
-  double* dst = a;
-  for (int s = 0; s < n_sweeps; ++s) {
-    if (is_u) k_momentum_jacobi<1><<<l.grid, l.block, 0, ctx->stream>>>(*g, L, src, dst);
-    else k_momentum_jacobi<0><<<l.grid, l.block, 0, ctx->stream>>>(*g, L, src, dst);
-    NF_LAUNCH_CHECK(ctx);
-    src = dst;
-    dst = (dst == a) ? b : a;
-  }
-  *result = const_cast<double*>(src);
+  if (is_u) k_momentum_jacobi<1><<<l.grid, l.block, 0, ctx->stream>>>(*g, L, src, dst);
+  else k_momentum_jacobi<0><<<l.grid, l.block, 0, ctx->stream>>>(*g, L, src, dst);
+  NF_LAUNCH_CHECK(ctx);
   return NF_OK;
 }
 
@@ -389,16 +373,19 @@ extern "C" int nf_momentum_jacobi(nf_ctx* ctx, const nf_grid* g, int is_u, nf_li
   return nfi_momentum_jacobi(ctx, g, is_u, L, x, tmp, n_sweeps);
 }
 
-// sums -> device scalars [slot, slot+1] = (sum r^2, sum b^2) over the masked interior
-int nfi_momentum_residual_dev(nf_ctx* ctx, const nf_grid* g, int is_u, nf_links L, const double* x, double* field,
-                              int slot) {
+// sums -> out[0..1] (device memory) = (sum r^2, sum b^2) over the masked interior of the rows [g.gb, g.ge)
+int nfi_momentum_residual_to(nf_ctx* ctx, const nf_grid* g, int is_u, nf_links L, const double* x, double* field,
+                             double* out) {
   NfLaunch2D l = nf_launch_reduce(nf_row_end(*g, is_u) - g->gb, nf_cols(*g, is_u));
-  if (is_u) k_momentum_residual<1><<<l.grid, l.block, 0, ctx->stream>>>(*g, L, x, field, ctx->partials, ctx->ticket,
-                                                                        ctx->scalars + slot);
-  else k_momentum_residual<0><<<l.grid, l.block, 0, ctx->stream>>>(*g, L, x, field, ctx->partials, ctx->ticket,
-                                                                   ctx->scalars + slot);
+  if (is_u) k_momentum_residual<1><<<l.grid, l.block, 0, ctx->stream>>>(*g, L, x, field, ctx->partials, ctx->ticket, out);
+  else k_momentum_residual<0><<<l.grid, l.block, 0, ctx->stream>>>(*g, L, x, field, ctx->partials, ctx->ticket, out);
   NF_LAUNCH_CHECK(ctx);
   return NF_OK;
+}
+
+int nfi_momentum_residual_dev(nf_ctx* ctx, const nf_grid* g, int is_u, nf_links L, const double* x, double* field,
+                              int slot) {
+  return nfi_momentum_residual_to(ctx, g, is_u, L, x, field, ctx->scalars + slot);
 }
 
 extern "C" int nf_momentum_residual(nf_ctx* ctx, const nf_grid* g, int is_u, nf_links L, const double* x,

@@ -324,26 +324,27 @@ extern "C" int nf_update_pressure(nf_ctx* ctx, const nf_grid* g, const double* p
   return NF_OK;
 }
 
-// sum r^2 -> scalars[slot], (with_b) sum b^2 -> scalars[slot+1]
+// sum r^2 -> out[0], (with_b) sum b^2 -> out[1]   (out: device memory)
 int nfi_residual_norms(nf_ctx* ctx, const nf_grid* g, const double* p, const double* b, const double* d_u,
-                       const double* d_v, double* r, int with_b, int slot) {
+                       const double* d_v, double* r, int with_b, double* out) {
   NfLaunch2D l = nf_launch_reduce(g->ge - g->gb, g->ny);
   if (with_b)
-    k_residual_norms<true><<<l.grid, l.block, 0, ctx->stream>>>(*g, p, b, d_u, d_v, r, ctx->partials, ctx->ticket,
-                                                                ctx->scalars + slot);
+    k_residual_norms<true><<<l.grid, l.block, 0, ctx->stream>>>(*g, p, b, d_u, d_v, r, ctx->partials, ctx->ticket, out);
   else
-    k_residual_norms<false><<<l.grid, l.block, 0, ctx->stream>>>(*g, p, b, d_u, d_v, r, ctx->partials, ctx->ticket,
-                                                                 ctx->scalars + slot);
+    k_residual_norms<false><<<l.grid, l.block, 0, ctx->stream>>>(*g, p, b, d_u, d_v, r, ctx->partials, ctx->ticket, out);
+  NF_LAUNCH_CHECK(ctx);
+  return NF_OK;
+}
+
+int nfi_sumsq_to(nf_ctx* ctx, const nf_grid* g, const double* x, int interior_only, double* out) {
+  NfLaunch2D l = nf_launch_reduce(g->ge - g->gb, g->ny);
+  k_sumsq<<<l.grid, l.block, 0, ctx->stream>>>(*g, x, interior_only, ctx->partials, ctx->ticket, out);
   NF_LAUNCH_CHECK(ctx);
   return NF_OK;
 }
 
 int nfi_sumsq_dev(nf_ctx* ctx, const nf_grid* g, const double* x, int interior_only, int slot) {
-  NfLaunch2D l = nf_launch_reduce(g->ge - g->gb, g->ny);
-  k_sumsq<<<l.grid, l.block, 0, ctx->stream>>>(*g, x, interior_only, ctx->partials, ctx->ticket,
-                                               ctx->scalars + slot);
-  NF_LAUNCH_CHECK(ctx);
-  return NF_OK;
+  return nfi_sumsq_to(ctx, g, x, interior_only, ctx->scalars + slot);
 }
 
 __global__ void k_fill(double* __restrict__ x, size_t n, double v) {

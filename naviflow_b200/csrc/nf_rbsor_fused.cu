@@ -447,10 +447,13 @@ int launch_tma(nf_ctx* ctx, const nf_grid* g, const double* pin, double* pout, c
   const int tiles_x = (g->ny + TC - 1) / TC, tiles_y = (g->ge - g->gb + TR - 1) / TR;
   const int n_tiles = tiles_x * tiles_y;
   // stored rows of this (slab of the) grid: the maps cover rows [row0, ...) of the arrays as stored
-  const int stored_p = g->nx - g->row0;       // p-like arrays: rows row0 .. nx-1 (single GPU: all)
+  // rows the arrays hold (slab runs store [row0, row1); row1 == 0 means the whole grid)
+  const int row_end = g->row1 > 0 ? g->row1 : g->nx + 1;
+  const int stored_p = (row_end < g->nx ? row_end : g->nx) - g->row0;  // p-like arrays
+  const int stored_u = row_end - g->row0;                               // d_u (face rows)
   CUtensorMap mp, mb, mu, mv, mi;
   if (!make_map(&mp, pin, stored_p, g->ny, g->ld, RRW, RCW) || !make_map(&mb, b, stored_p, g->ny, g->ld, RRW, RCW) ||
-      !make_map(&mu, d_u, stored_p + 1, g->ny, g->ld, RRW + 1, RCW) ||
+      !make_map(&mu, d_u, stored_u, g->ny, g->ld, RRW + 1, RCW) ||
       !make_map(&mv, d_v, stored_p, g->ny + 1, g->ld, RRW, RCW + 2) ||
       !make_map(&mi, HAS_INV ? inv : b, stored_p, g->ny, g->ld, RRW, RCW))
     return NF_OK;  // caller falls back to the plain fused kernel
@@ -489,7 +492,7 @@ int nfi_rbsor_fused(nf_ctx* ctx, const nf_grid* g, double** p, double** palt, co
   // TMA path: single-GPU layout (row0 == 0), 16-byte aligned arrays, pitch a multiple of 2 doubles
   const char* env = getenv("NF_RBSOR_TMA");
   const int tma_min_rows = env ? atoi(env) : 600;  // NF_RBSOR_TMA=0 forces TMA everywhere, a huge value disables it
-  const bool use_tma = g->row0 == 0 && g->gb == 0 && g->ge == g->nx && g->nx >= tma_min_rows;
+  const bool use_tma = g->nx >= tma_min_rows && (g->ge - g->gb) >= 64;
   int left = n_sweeps;
   while (left > 0) {
     const int ns = left >= 3 ? 3 : left;

@@ -1,4 +1,4 @@
-// nf_simple.cu -- device-resident SIMPLE outer loop (fp64).
+// nf_simple.cu -- device-resident SIMPLE outer loop (fp64), single GPU or row slabs.
 //
 // Reference: solver/Algorithms/simple.py:78-269 (paths relative to /root/reference/naviflow_oo) with
 //   momentum predictor     solver/momentum_solver/jacobi_matrix_solver.py:153-375 (fixed Jacobi sweeps)
@@ -6,30 +6,34 @@
 //   p update + Neumann     simple.py:148-150, base_algorithm.py:161-197
 //   velocity correction    solver/velocity_solver/standard.py:10-69
 // All fields stay in HBM between outer iterations; the host sees one record of norms per iteration.
+//
+// Slab runs (nf_slab.cuh): every rank keeps NF_HALO = 8 halo rows.  The momentum phase needs NO communication:
+// the link coefficients are evaluated NF_HALO-1 rows beyond the owned rows and each Jacobi sweep is computed on a
+// region that shrinks by one row, so after up to 6 sweeps the owned rows (+1) are exact.  Per outer iteration the
+// ranks exchange: the halo of b (once), the multigrid halos (nf_mg.cu), p, u, v (once each) and 6 scalars.
 #include <math.h>
 
 #include <vector>
 
-#include "nf_common.cuh"
+#include "nf_slab.cuh"
 
 // internal entry points of the other translation units
 int nfi_apply_velocity_bc(nf_ctx*, const nf_grid*, const nf_bc_program*, double* u, double* v);
 int nfi_momentum_links(nf_ctx*, const nf_grid*, int is_u, const double* u, const double* v, const double* p,
                        double mu, double alpha, int sides, nf_links out, double* d);
-int nfi_momentum_jacobi_pp(nf_ctx*, const nf_grid*, int is_u, nf_links L, const double* x0, double* a, double* b,
-                           int n_sweeps, double** result);
-int nfi_momentum_residual_dev(nf_ctx*, const nf_grid*, int is_u, nf_links L, const double* x, double* field, int slot);
+int nfi_momentum_sweep(nf_ctx*, const nf_grid*, int is_u, nf_links L, const double* src, double* dst);
+int nfi_momentum_residual_to(nf_ctx*, const nf_grid*, int is_u, nf_links L, const double* x, double* field, double* out);
 int nfi_correct_velocity(nf_ctx*, const nf_grid*, const nf_bc_program*, const double* us, const double* vs,
                          const double* pp, const double* d_u, const double* d_v, double* u, double* v);
-int nfi_mg_solve(nf_mg* mg, const double* b, double* x, double* r, nf_mg_info* info, int sync);
+int nfi_mg_create(nf_team* team, nf_mg** out, int nx, int ny, int ld, const nf_mg_config* cfg);
+int nfi_mg_setup(nf_mg* mg, double* const* d_u, double* const* d_v);
+int nfi_mg_solve(nf_mg* mg, double* const* b, double* const* x, double* const* r, nf_mg_info* info, int sync);
+double* nfi_mg_scalars(nf_mg* mg, int k);
+LevelGeom nf_level0_geom(const nf_team* team, int nx, int ny, int ld, double length, double height, double rho);
 
 enum { F_U = 0, F_V, F_P, F_USTAR, F_VSTAR, F_DU, F_DV, F_PPRIME, F_B, F_PRES, F_URES, F_VRES, F_COUNT };
 
-struct nf_simple {
-  nf_ctx* ctx = nullptr;
-  nf_simple_config cfg;
-  nf_grid g;
-  size_t elems = 0;
+struct SimpleSlab {
   std::vector<double*> owned;
   double *u = nullptr, *v = nullptr, *p = nullptr, *p_alt = nullptr;
   double *ua = nullptr, *ub = nullptr, *va = nullptr, *vb = nullptr;  // momentum ping-pong buffers
@@ -37,39 +41,59 @@ struct nf_simple {
   double *ubc = nullptr, *vbc = nullptr;                              // BC'd copies when the state is not clean
   double *d_u = nullptr, *d_v = nullptr, *pp = nullptr, *b = nullptr, *pres = nullptr;
   double *ures = nullptr, *vres = nullptr;
-  double* tmp = nullptr;  // Jacobi pressure ping-pong / Krylov work base
-  double* kwork = nullptr;
+  double* tmp = nullptr;    // Jacobi pressure ping-pong
+  double* kwork = nullptr;  // Krylov work arrays
+  double* scal = nullptr;   // 8 device doubles: [0..1] pressure norms, [2..5] momentum sums
   nf_links links;
+};
+
+struct nf_simple {
+  nf_ctx* ctx = nullptr;
+  nf_team* team = nullptr;
+  bool owns_team = false;
+  nf_simple_config cfg;
+  LevelGeom geom;
+  std::vector<SimpleSlab> s;
   nf_mg* mg = nullptr;
-  double* hist = nullptr;       // device: 8 doubles per iteration
+  double* hist = nullptr;       // device: 8 doubles per iteration (slab 0's reduced scalars)
   double* hist_host = nullptr;  // pinned
   int hist_cap = 0;
   bool bc_clean = false;
 };
 
-static inline int pad_ld(int ny) { return ((ny + 1 + 15) / 16) * 16; }
+static int nlocal(const nf_simple* s) { return (int)s->team->local.size(); }
 
 extern "C" int nf_simple_destroy(nf_simple* s) {
   if (!s) return NF_OK;
   cudaSetDevice(s->ctx->device);
   cudaStreamSynchronize(s->ctx->stream);
   if (s->mg) nf_mg_destroy(s->mg);
-  for (double* ptr : s->owned) cudaFree(ptr);
+  for (SimpleSlab& S : s->s)
+    for (double* ptr : S.owned) cudaFree(ptr);
   if (s->hist) cudaFree(s->hist);
   if (s->hist_host) cudaFreeHost(s->hist_host);
+  if (s->owns_team) nf_team_destroy(s->team);
   delete s;
   return NF_OK;
 }
 
-static double* alloc_field(nf_simple* s) {
+static double* alloc_elems(nf_simple* s, SimpleSlab& S, size_t elems) {
   double* ptr = nullptr;
-  if (cudaMalloc(&ptr, s->elems * sizeof(double)) != cudaSuccess) return nullptr;
-  cudaMemsetAsync(ptr, 0, s->elems * sizeof(double), s->ctx->stream);
-  s->owned.push_back(ptr);
+  if (cudaMalloc(&ptr, elems * sizeof(double)) != cudaSuccess) return nullptr;
+  cudaMemsetAsync(ptr, 0, elems * sizeof(double), s->ctx->stream);
+  S.owned.push_back(ptr);
   return ptr;
 }
 
-extern "C" int nf_simple_create(nf_ctx* ctx, nf_simple** out, const nf_simple_config* cfg) {
+template <class M>
+static std::vector<double*> field_of(nf_simple* s, M member) {
+  std::vector<double*> v;
+  for (SimpleSlab& S : s->s) v.push_back(S.*member);
+  return v;
+}
+
+int nfi_simple_create(nf_team* team, nf_simple** out, const nf_simple_config* cfg) {
+  nf_ctx* ctx = team->ctx;
   NF_REQUIRE(ctx, out && cfg, "NULL argument");
   *out = nullptr;
   NF_REQUIRE(ctx, cfg->nx >= 3 && cfg->ny >= 3, "nx, ny must be >= 3");
@@ -78,104 +102,156 @@ extern "C" int nf_simple_create(nf_ctx* ctx, nf_simple** out, const nf_simple_co
   NF_REQUIRE(ctx, cfg->n_momentum_sweeps >= 0, "n_momentum_sweeps < 0");
   nf_simple* s = new nf_simple();
   s->ctx = ctx;
+  s->team = team;
   s->cfg = *cfg;
-  nf_grid& g = s->g;
-  g.nx = cfg->nx; g.ny = cfg->ny; g.ld = pad_ld(cfg->ny); g.row0 = 0; g.gb = 0; g.ge = cfg->nx;
-  g.dx = cfg->length / (cfg->nx - 1);  // structured.py:27-28
-  g.dy = cfg->height / (cfg->ny - 1);
-  g.rho = cfg->rho;
-  s->elems = (size_t)(g.nx + 1) * g.ld;
-  double** fields[] = {&s->u, &s->v, &s->p, &s->p_alt, &s->ua, &s->ub, &s->va, &s->vb, &s->ubc, &s->vbc,
-                       &s->d_u, &s->d_v, &s->pp, &s->b, &s->pres, &s->ures, &s->vres, &s->tmp,
-                       &s->links.a_e, &s->links.a_w, &s->links.a_n, &s->links.a_s, &s->links.a_p, &s->links.src};
-  bool ok = true;
-  for (double** f : fields) {
-    *f = alloc_field(s);
-    if (!*f) { ok = false; break; }
+  s->geom = nf_level0_geom(team, cfg->nx, cfg->ny, nf_pad_ld(cfg->ny), cfg->length, cfg->height, cfg->rho);
+  if (s->geom.dist && cfg->pressure_solver != 0) {
+    ctx->err = "slab-decomposed runs support the multigrid pressure solver only";
+    delete s;
+    return NF_ERR_UNSUPPORTED;
   }
-  if (ok && cfg->pressure_solver >= 3) {
-    const int nwork = cfg->pressure_solver == 3 ? 4 : 5;
-    if (cudaMalloc(&s->kwork, s->elems * nwork * sizeof(double)) == cudaSuccess) {
-      s->owned.push_back(s->kwork);
-      cudaMemsetAsync(s->kwork, 0, s->elems * nwork * sizeof(double), ctx->stream);
-    } else ok = false;
+  const int nl = (int)team->local.size();
+  s->s.resize(nl);
+  bool ok = true;
+  for (int k = 0; k < nl && ok; ++k) {
+    SimpleSlab& S = s->s[k];
+    const size_t e = s->geom.elems(team->local[k]);
+    double** fields[] = {&S.u, &S.v, &S.p, &S.p_alt, &S.ua, &S.ub, &S.va, &S.vb, &S.ubc, &S.vbc,
+                         &S.d_u, &S.d_v, &S.pp, &S.b, &S.pres, &S.ures, &S.vres, &S.tmp,
+                         &S.links.a_e, &S.links.a_w, &S.links.a_n, &S.links.a_s, &S.links.a_p, &S.links.src};
+    for (double** f : fields) {
+      *f = alloc_elems(s, S, e);
+      if (!*f) { ok = false; break; }
+    }
+    if (ok) { S.scal = alloc_elems(s, S, 8); ok = S.scal != nullptr; }
+    if (ok && cfg->pressure_solver >= 3) {
+      S.kwork = alloc_elems(s, S, e * (cfg->pressure_solver == 3 ? 4 : 5));
+      ok = S.kwork != nullptr;
+    }
+    S.u_star = S.ua;
+    S.v_star = S.va;
   }
   if (!ok) {
     ctx->err = std::string("SIMPLE state allocation failed: ") + cudaGetErrorString(cudaGetLastError());
     nf_simple_destroy(s);
     return NF_ERR_ALLOC;
   }
-  s->u_star = s->ua;
-  s->v_star = s->va;
   if (cfg->pressure_solver == 0) {
     nf_mg_config mc = cfg->mg;
     mc.length = cfg->length; mc.height = cfg->height; mc.rho = 1.0;  // callers hard-code rho = 1 (multigrid.py:151)
-    int st = nf_mg_create(ctx, &s->mg, g.nx, g.ny, g.ld, &mc);
+    int st = nfi_mg_create(team, &s->mg, s->geom.nx, s->geom.ny, s->geom.ld, &mc);
     if (st != NF_OK) { nf_simple_destroy(s); return st; }
   }
-  // initial fields: zeros with the velocity BCs applied (base_algorithm.py:68-93)
-  int st = nfi_apply_velocity_bc(ctx, &g, &s->cfg.bc, s->u, s->v);
-  if (st != NF_OK) { nf_simple_destroy(s); return st; }
+  // initial fields: zeros with the velocity BCs applied on every stored row (base_algorithm.py:68-93)
+  for (int k = 0; k < nl; ++k) {
+    const nf_grid g = s->geom.grid_ext(team->local[k], NF_HALO);
+    int st = nfi_apply_velocity_bc(ctx, &g, &s->cfg.bc, s->s[k].u, s->s[k].v);
+    if (st != NF_OK) { nf_simple_destroy(s); return st; }
+  }
   s->bc_clean = true;
   *out = s;
   return NF_OK;
 }
 
-extern "C" int nf_simple_ld(nf_simple* s) { return s ? s->g.ld : 0; }
+extern "C" int nf_simple_create(nf_ctx* ctx, nf_simple** out, const nf_simple_config* cfg) {
+  nf_team* team = nullptr;
+  NF_TRY(nf_team_create_local(ctx, 1, &team));
+  int st = nfi_simple_create(team, out, cfg);
+  if (st != NF_OK) { nf_team_destroy(team); return st; }
+  (*out)->owns_team = true;
+  return NF_OK;
+}
 
-static double* field_ptr(nf_simple* s, int which) {
+// slab-decomposed state on an existing team (nf_team_create_nccl / nf_team_create_virtual); the team stays
+// owned by the caller
+extern "C" int nf_simple_create_team(nf_team* team, nf_simple** out, const nf_simple_config* cfg) {
+  if (!team) return NF_ERR_ARG;
+  return nfi_simple_create(team, out, cfg);
+}
+
+extern "C" int nf_simple_ld(nf_simple* s) { return s ? s->geom.ld : 0; }
+
+static double* field_ptr(SimpleSlab& S, int which) {
   switch (which) {
-    case F_U: return s->u;
-    case F_V: return s->v;
-    case F_P: return s->p;
-    case F_USTAR: return s->u_star;
-    case F_VSTAR: return s->v_star;
-    case F_DU: return s->d_u;
-    case F_DV: return s->d_v;
-    case F_PPRIME: return s->pp;
-    case F_B: return s->b;
-    case F_PRES: return s->pres;
-    case F_URES: return s->ures;
-    case F_VRES: return s->vres;
+    case F_U: return S.u;
+    case F_V: return S.v;
+    case F_P: return S.p;
+    case F_USTAR: return S.u_star;
+    case F_VSTAR: return S.v_star;
+    case F_DU: return S.d_u;
+    case F_DV: return S.d_v;
+    case F_PPRIME: return S.pp;
+    case F_B: return S.b;
+    case F_PRES: return S.pres;
+    case F_URES: return S.ures;
+    case F_VRES: return S.vres;
   }
   return nullptr;
 }
 
-extern "C" double* nf_simple_field(nf_simple* s, int which) { return s ? field_ptr(s, which) : nullptr; }
+// first local slab's array (single-GPU runs: the whole field)
+extern "C" double* nf_simple_field(nf_simple* s, int which) { return s ? field_ptr(s->s[0], which) : nullptr; }
 
+// rows [*row_begin, *row_end) of the cell grid owned by local slab k of this process
+extern "C" int nf_simple_local_rows(nf_simple* s, int k, int* row_begin, int* row_end) {
+  if (!s || k < 0 || k >= nlocal(s)) return NF_ERR_ARG;
+  const int r = s->team->local[k];
+  if (row_begin) *row_begin = s->geom.gb[r];
+  if (row_end) *row_end = s->geom.ge[r];
+  return NF_OK;
+}
+
+// host arrays are the FULL (rows, cols) fields; every local slab takes / returns its own rows
 extern "C" int nf_simple_upload(nf_simple* s, int which, const double* host, int rows, int cols) {
   if (!s) return NF_ERR_ARG;
   nf_ctx* ctx = s->ctx;
-  double* dst = field_ptr(s, which);
-  NF_REQUIRE(ctx, dst && host, "bad field / NULL host pointer");
-  NF_REQUIRE(ctx, rows >= 1 && rows <= s->g.nx + 1 && cols >= 1 && cols <= s->g.ld, "shape does not fit the field");
-  NF_CHECK_CUDA(ctx, cudaMemcpy2DAsync(dst, (size_t)s->g.ld * sizeof(double), host, (size_t)cols * sizeof(double),
-                                       (size_t)cols * sizeof(double), rows, cudaMemcpyHostToDevice, ctx->stream));
+  NF_REQUIRE(ctx, host && which >= 0 && which < F_COUNT, "bad field / NULL host pointer");
+  NF_REQUIRE(ctx, rows >= 1 && rows <= s->geom.nx + 1 && cols >= 1 && cols <= s->geom.ld, "shape does not fit the field");
+  for (int k = 0; k < nlocal(s); ++k) {
+    const int r = s->team->local[k];
+    const int r0 = s->geom.row0(r);
+    int r1 = s->geom.row1(r);
+    if (r1 > rows) r1 = rows;
+    if (r1 <= r0) continue;
+    NF_CHECK_CUDA(ctx, cudaMemcpy2DAsync(field_ptr(s->s[k], which), (size_t)s->geom.ld * sizeof(double),
+                                         host + (size_t)r0 * cols, (size_t)cols * sizeof(double),
+                                         (size_t)cols * sizeof(double), r1 - r0, cudaMemcpyHostToDevice, ctx->stream));
+  }
   NF_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (which == F_U || which == F_V) s->bc_clean = false;
   return NF_OK;
 }
 
+// writes the rows owned by this process's slabs into the full host array (other rows are left untouched)
 extern "C" int nf_simple_download(nf_simple* s, int which, double* host, int rows, int cols) {
   if (!s) return NF_ERR_ARG;
   nf_ctx* ctx = s->ctx;
-  const double* src = field_ptr(s, which);
-  NF_REQUIRE(ctx, src && host, "bad field / NULL host pointer");
-  NF_REQUIRE(ctx, rows >= 1 && rows <= s->g.nx + 1 && cols >= 1 && cols <= s->g.ld, "shape does not fit the field");
-  NF_CHECK_CUDA(ctx, cudaMemcpy2DAsync(host, (size_t)cols * sizeof(double), src, (size_t)s->g.ld * sizeof(double),
-                                       (size_t)cols * sizeof(double), rows, cudaMemcpyDeviceToHost, ctx->stream));
+  NF_REQUIRE(ctx, host && which >= 0 && which < F_COUNT, "bad field / NULL host pointer");
+  NF_REQUIRE(ctx, rows >= 1 && rows <= s->geom.nx + 1 && cols >= 1 && cols <= s->geom.ld, "shape does not fit the field");
+  for (int k = 0; k < nlocal(s); ++k) {
+    const int r = s->team->local[k];
+    const int r0 = s->geom.row0(r);
+    int b = s->geom.gb[r], e = s->geom.ge[r];
+    if (r == s->team->world - 1) e = rows;  // the last rank also owns face row nx of u
+    if (e > rows) e = rows;
+    if (e <= b) continue;
+    NF_CHECK_CUDA(ctx, cudaMemcpy2DAsync(host + (size_t)b * cols, (size_t)cols * sizeof(double),
+                                         field_ptr(s->s[k], which) + (size_t)(b - r0) * s->geom.ld,
+                                         (size_t)s->geom.ld * sizeof(double), (size_t)cols * sizeof(double), e - b,
+                                         cudaMemcpyDeviceToHost, ctx->stream));
+  }
   NF_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return NF_OK;
 }
 
-// history record: [0] sum r_u^2, [1] sum b_u^2, [2] sum r_v^2, [3] sum b_v^2, [4] p norm payload a, [5] payload b,
-//                 [6] pressure iterations, [7] spare
-__global__ void k_store_hist(const double* __restrict__ scalars, double* __restrict__ rec, double pa, double pb,
-                             double iters, int p_from_scalars) {
+// history record: [0] sum r_p^2 (or payload a), [1] sum b_p^2 (payload b), [2] sum r_u^2, [3] sum b_u^2,
+//                 [4] sum r_v^2, [5] sum b_v^2, [6] pressure iterations, [7] spare
+__global__ void k_store_hist(const double* __restrict__ scal, const double* __restrict__ pscal, double* __restrict__ rec,
+                             double pa, double pb, double iters, int p_from_scalars) {
   const int t = threadIdx.x;
-  if (t < 4) rec[t] = scalars[2 + t];
-  if (t == 4) rec[4] = p_from_scalars ? scalars[0] : pa;
-  if (t == 5) rec[5] = p_from_scalars ? scalars[1] : pb;
+  if (t == 0) rec[0] = p_from_scalars ? pscal[0] : pa;
+  if (t == 1) rec[1] = p_from_scalars ? pscal[1] : pb;
+  if (t >= 2 && t < 6) rec[t] = scal[t];
   if (t == 6) rec[6] = iters;
   if (t == 7) rec[7] = 0.0;
 }
@@ -193,95 +269,184 @@ static int ensure_hist(nf_simple* s, int n) {
 }
 
 static void decode_record(const nf_simple* s, const double* rec, nf_simple_info* out) {
-  out->u_abs_res = sqrt(rec[0]);
-  out->v_abs_res = sqrt(rec[2]);
-  out->u_rel_norm = sqrt(rec[0]) / (sqrt(rec[1]) + 1e-15);  // jacobi_matrix_solver.py:246-250
-  out->v_rel_norm = sqrt(rec[2]) / (sqrt(rec[3]) + 1e-15);
+  out->u_abs_res = sqrt(rec[2]);
+  out->v_abs_res = sqrt(rec[4]);
+  out->u_rel_norm = sqrt(rec[2]) / (sqrt(rec[3]) + 1e-15);  // jacobi_matrix_solver.py:246-250
+  out->v_rel_norm = sqrt(rec[4]) / (sqrt(rec[5]) + 1e-15);
   switch (s->cfg.pressure_solver) {
-    case 0: out->p_rel_norm = sqrt(rec[4]); break;                               // absolute ||r|| (multigrid.py:257)
-    case 1: case 2: out->p_rel_norm = sqrt(rec[4]); break;                       // absolute ||b - A p'||
-    default: out->p_rel_norm = rec[5] > 0.0 ? sqrt(rec[4]) / sqrt(rec[5]) : sqrt(rec[4]); break;  // ||r_int||/||b_int||
+    case 0: case 1: case 2: out->p_rel_norm = sqrt(rec[0]); break;  // absolute ||b - A p'|| (multigrid.py:257)
+    default: out->p_rel_norm = rec[1] > 0.0 ? sqrt(rec[0]) / sqrt(rec[1]) : sqrt(rec[0]); break;  // ||r_int||/||b_int||
   }
   out->pressure_iterations = (int)rec[6];
   out->pad = 0;
 }
 
+// momentum predictor of one component on every local slab (no communication, see the header comment)
+static int momentum_component(nf_simple* s, int is_u, int want_fields) {
+  nf_ctx* ctx = s->ctx;
+  nf_team* team = s->team;
+  const nf_simple_config& c = s->cfg;
+  const bool dist = s->geom.dist;
+  const int nl = nlocal(s);
+  int margin = NF_HALO - 1;  // rows beyond the owned ones on which the current iterate is exact
+  for (int k = 0; k < nl; ++k) {
+    SimpleSlab& S = s->s[k];
+    const nf_grid g = s->geom.grid_ext(team->local[k], margin);
+    const double* ubc = s->bc_clean ? S.u : S.ubc;
+    const double* vbc = s->bc_clean ? S.v : S.vbc;
+    NF_TRY(nfi_momentum_links(ctx, &g, is_u, ubc, vbc, S.p, c.mu, c.alpha_u, c.sides, S.links, is_u ? S.d_u : S.d_v));
+  }
+  // sweeps: x0 = current velocity (valid NF_HALO rows out); sweep s is exact margin-1 rows out
+  std::vector<const double*> src(nl);
+  std::vector<double*> a(nl), b(nl);
+  for (int k = 0; k < nl; ++k) {
+    SimpleSlab& S = s->s[k];
+    src[k] = is_u ? S.u : S.v;
+    a[k] = is_u ? S.ua : S.va;
+    b[k] = is_u ? S.ub : S.vb;
+  }
+  if (c.n_momentum_sweeps == 0) {
+    for (int k = 0; k < nl; ++k) {
+      NF_CHECK_CUDA(ctx, cudaMemcpyAsync(a[k], src[k], s->geom.elems(team->local[k]) * sizeof(double),
+                                         cudaMemcpyDeviceToDevice, ctx->stream));
+      src[k] = a[k];
+    }
+  }
+  for (int sw = 0; sw < c.n_momentum_sweeps; ++sw) {
+    if (dist && margin <= 1) {  // out of halo: refresh it and start shrinking again
+      std::vector<double*> f(nl);
+      for (int k = 0; k < nl; ++k) f[k] = const_cast<double*>(src[k]);
+      NF_TRY(nf_team_exchange(team, s->geom, f.data(), NF_HALO));
+      margin = NF_HALO;
+    }
+    margin -= 1;
+    for (int k = 0; k < nl; ++k) {
+      const nf_grid g = s->geom.grid_ext(team->local[k], margin);
+      double* dst = (src[k] == a[k]) ? b[k] : a[k];
+      NF_TRY(nfi_momentum_sweep(ctx, &g, is_u, s->s[k].links, src[k], dst));
+      src[k] = dst;
+    }
+  }
+  for (int k = 0; k < nl; ++k) {
+    SimpleSlab& S = s->s[k];
+    if (is_u) S.u_star = const_cast<double*>(src[k]); else S.v_star = const_cast<double*>(src[k]);
+  }
+  if (dist && margin < 1) {  // the continuity RHS and the residual read one row beyond the owned ones
+    std::vector<double*> f(nl);
+    for (int k = 0; k < nl; ++k) f[k] = const_cast<double*>(src[k]);
+    NF_TRY(nf_team_exchange(team, s->geom, f.data(), 1));
+  }
+  for (int k = 0; k < nl; ++k) {
+    SimpleSlab& S = s->s[k];
+    const nf_grid g = s->geom.grid(team->local[k]);
+    NF_TRY(nfi_momentum_residual_to(ctx, &g, is_u, S.links, src[k], want_fields ? (is_u ? S.ures : S.vres) : nullptr,
+                                    S.scal + (is_u ? 2 : 4)));
+  }
+  return NF_OK;
+}
+
 // one outer iteration; leaves its history record in hist[slot]
 static int simple_step(nf_simple* s, int slot, int want_fields) {
   nf_ctx* ctx = s->ctx;
-  const nf_grid* g = &s->g;
+  nf_team* team = s->team;
   const nf_simple_config& c = s->cfg;
+  const int nl = nlocal(s);
+  const bool dist = s->geom.dist;
   // velocities with BCs applied, used for the coefficients (jacobi_matrix_solver.py:170)
-  const double *ubc = s->u, *vbc = s->v;
   if (!s->bc_clean) {
-    NF_CHECK_CUDA(ctx, cudaMemcpyAsync(s->ubc, s->u, s->elems * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-    NF_CHECK_CUDA(ctx, cudaMemcpyAsync(s->vbc, s->v, s->elems * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-    NF_TRY(nfi_apply_velocity_bc(ctx, g, &c.bc, s->ubc, s->vbc));
-    ubc = s->ubc; vbc = s->vbc;
+    for (int k = 0; k < nl; ++k) {
+      SimpleSlab& S = s->s[k];
+      const size_t bytes = s->geom.elems(team->local[k]) * sizeof(double);
+      NF_CHECK_CUDA(ctx, cudaMemcpyAsync(S.ubc, S.u, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+      NF_CHECK_CUDA(ctx, cudaMemcpyAsync(S.vbc, S.v, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+      const nf_grid g = s->geom.grid_ext(team->local[k], NF_HALO);
+      NF_TRY(nfi_apply_velocity_bc(ctx, &g, &c.bc, S.ubc, S.vbc));
+    }
   }
-  // u-momentum: links, n sweeps from x0 = u, residual norm
-  NF_TRY(nfi_momentum_links(ctx, g, 1, ubc, vbc, s->p, c.mu, c.alpha_u, c.sides, s->links, s->d_u));
-  NF_TRY(nfi_momentum_jacobi_pp(ctx, g, 1, s->links, s->u, s->ua, s->ub, c.n_momentum_sweeps, &s->u_star));
-  NF_TRY(nfi_momentum_residual_dev(ctx, g, 1, s->links, s->u_star, want_fields ? s->ures : nullptr, 2));
-  // v-momentum (same u, v, p*: simple.py:128-133)
-  NF_TRY(nfi_momentum_links(ctx, g, 0, ubc, vbc, s->p, c.mu, c.alpha_u, c.sides, s->links, s->d_v));
-  NF_TRY(nfi_momentum_jacobi_pp(ctx, g, 0, s->links, s->v, s->va, s->vb, c.n_momentum_sweeps, &s->v_star));
-  NF_TRY(nfi_momentum_residual_dev(ctx, g, 0, s->links, s->v_star, want_fields ? s->vres : nullptr, 4));
+  NF_TRY(momentum_component(s, 1, want_fields));
+  NF_TRY(momentum_component(s, 0, want_fields));  // same u, v, p*: simple.py:128-133
   // pressure correction
-  nf_grid gp = *g;
-  gp.rho = 1.0;  // every pressure solver of the reference hard-codes rho = 1.0 (multigrid.py:151, jacobi.py, ...)
-  NF_TRY(nf_continuity_rhs(ctx, &gp, s->u_star, s->v_star, s->b));
+  std::vector<nf_grid> gp(nl);
+  for (int k = 0; k < nl; ++k) {
+    SimpleSlab& S = s->s[k];
+    gp[k] = s->geom.grid(team->local[k]);
+    gp[k].rho = 1.0;  // every pressure solver of the reference hard-codes rho = 1.0 (multigrid.py:151, jacobi.py, ...)
+    NF_TRY(nf_continuity_rhs(ctx, &gp[k], S.u_star, S.v_star, S.b));
+  }
+  if (dist) {
+    std::vector<double*> b = field_of(s, &SimpleSlab::b);
+    NF_TRY(nf_team_exchange(team, s->geom, b.data(), NF_HALO));
+  }
   double pa = 0.0, pb = 0.0, iters = 0.0;
   int p_from_scalars = 0;
+  const double* pscal = s->s[0].scal;
   switch (c.pressure_solver) {
     case 0: {
-      NF_TRY(nf_mg_setup(s->mg, s->d_u, s->d_v));
+      std::vector<double*> du = field_of(s, &SimpleSlab::d_u), dv = field_of(s, &SimpleSlab::d_v);
+      std::vector<double*> b = field_of(s, &SimpleSlab::b), x = field_of(s, &SimpleSlab::pp);
+      std::vector<double*> r = field_of(s, &SimpleSlab::pres);
+      NF_TRY(nfi_mg_setup(s->mg, du.data(), dv.data()));
       nf_mg_info mi;
       const int fmg = (c.mg.cycle_type == 2);
-      NF_TRY(nfi_mg_solve(s->mg, s->b, s->pp, s->pres, &mi, fmg ? 0 : 1));
-      if (fmg) p_from_scalars = 1;
+      NF_TRY(nfi_mg_solve(s->mg, b.data(), x.data(), r.data(), &mi, fmg ? 0 : 1));
+      if (fmg) { p_from_scalars = 1; pscal = nfi_mg_scalars(s->mg, 0); }
       else { pa = mi.r_norm * mi.r_norm; pb = mi.b_norm * mi.b_norm; }
       iters = mi.cycles;
       break;
     }
     case 1:
     case 2: {
-      NF_TRY(nfi_fill(ctx, s->pp, (size_t)g->nx * g->ld, 0.0));
+      SimpleSlab& S = s->s[0];
+      const nf_grid* g1 = &gp[0];
+      NF_TRY(nfi_fill(ctx, S.pp, (size_t)g1->nx * g1->ld, 0.0));
       if (c.pressure_solver == 1)
-        NF_TRY(nfi_jacobi(ctx, &gp, s->pp, s->tmp, s->b, s->d_u, s->d_v, c.pressure_omega, c.pressure_iterations));
+        NF_TRY(nfi_jacobi(ctx, g1, S.pp, S.tmp, S.b, S.d_u, S.d_v, c.pressure_omega, c.pressure_iterations));
       else
-        NF_TRY(nfi_rbsor(ctx, &gp, s->pp, s->b, s->d_u, s->d_v, c.pressure_omega, c.pressure_iterations));
-      NF_TRY(nfi_residual(ctx, &gp, s->pp, s->b, s->d_u, s->d_v, s->pres));
-      NF_TRY(nfi_sumsq_dev(ctx, &gp, s->pres, 0, 0));
-      NF_TRY(nfi_sumsq_dev(ctx, &gp, s->b, 0, 1));
+        NF_TRY(nfi_rbsor(ctx, g1, S.pp, S.b, S.d_u, S.d_v, c.pressure_omega, c.pressure_iterations));
+      NF_TRY(nfi_residual_norms(ctx, g1, S.pp, S.b, S.d_u, S.d_v, S.pres, 1, S.scal));
       p_from_scalars = 1;
       iters = c.pressure_iterations;
       break;
     }
     default: {
+      SimpleSlab& S = s->s[0];
+      const nf_grid* g1 = &gp[0];
       nf_krylov_info ki;
       if (c.pressure_solver == 3)
-        NF_TRY(nf_cg_solve(ctx, &gp, s->b, s->pp, s->d_u, s->d_v, c.pressure_tolerance, 1e-5, c.krylov_maxiter, 25,
-                           s->kwork, &ki));
+        NF_TRY(nf_cg_solve(ctx, g1, S.b, S.pp, S.d_u, S.d_v, c.pressure_tolerance, 1e-5, c.krylov_maxiter, 25, S.kwork, &ki));
       else
-        NF_TRY(nf_bicgstab_solve(ctx, &gp, s->b, s->pp, s->d_u, s->d_v, c.pressure_tolerance, 1e-5, c.krylov_maxiter,
-                                 10, s->kwork, &ki));
+        NF_TRY(nf_bicgstab_solve(ctx, g1, S.b, S.pp, S.d_u, S.d_v, c.pressure_tolerance, 1e-5, c.krylov_maxiter, 10,
+                                 S.kwork, &ki));
       // rel_norm = ||r_int|| / ||b_int|| of the true residual (matrix_free_BiCGSTAB.py:255-279)
-      NF_TRY(nfi_residual(ctx, &gp, s->pp, s->b, s->d_u, s->d_v, s->pres));
-      NF_TRY(nfi_sumsq_dev(ctx, &gp, s->pres, 1, 0));
-      NF_TRY(nfi_sumsq_dev(ctx, &gp, s->b, 1, 1));
+      NF_TRY(nfi_residual(ctx, g1, S.pp, S.b, S.d_u, S.d_v, S.pres));
+      NF_TRY(nfi_sumsq_to(ctx, g1, S.pres, 1, S.scal));
+      NF_TRY(nfi_sumsq_to(ctx, g1, S.b, 1, S.scal + 1));
       p_from_scalars = 1;
       iters = ki.iterations;
       break;
     }
   }
-  k_store_hist<<<1, 32, 0, ctx->stream>>>(ctx->scalars, s->hist + (size_t)slot * 8, pa, pb, iters, p_from_scalars);
+  if (dist) {  // momentum sums of all slabs (4 doubles at scal[2..5])
+    std::vector<double*> sc(nl);
+    for (int k = 0; k < nl; ++k) sc[k] = s->s[k].scal + 2;
+    NF_TRY(nf_team_allreduce(team, sc.data(), 4));
+  }
+  k_store_hist<<<1, 32, 0, ctx->stream>>>(s->s[0].scal, pscal, s->hist + (size_t)slot * 8, pa, pb, iters, p_from_scalars);
   NF_LAUNCH_CHECK(ctx);
-  // p = p* + alpha_p p' with zero-gradient edges; p* <- p
-  NF_TRY(nf_update_pressure(ctx, g, s->p, s->pp, c.alpha_p, s->p_alt));
-  { double* t = s->p; s->p = s->p_alt; s->p_alt = t; }
-  // velocity correction + BCs
-  NF_TRY(nfi_correct_velocity(ctx, g, &c.bc, s->u_star, s->v_star, s->pp, s->d_u, s->d_v, s->u, s->v));
+  // p = p* + alpha_p p' with zero-gradient edges; p* <- p.  velocity correction + BCs.
+  for (int k = 0; k < nl; ++k) {
+    SimpleSlab& S = s->s[k];
+    const nf_grid g = s->geom.grid(team->local[k]);
+    NF_TRY(nf_update_pressure(ctx, &g, S.p, S.pp, c.alpha_p, S.p_alt));
+    { double* t = S.p; S.p = S.p_alt; S.p_alt = t; }
+    NF_TRY(nfi_correct_velocity(ctx, &g, &c.bc, S.u_star, S.v_star, S.pp, S.d_u, S.d_v, S.u, S.v));
+  }
+  if (dist) {
+    std::vector<double*> p = field_of(s, &SimpleSlab::p), u = field_of(s, &SimpleSlab::u), v = field_of(s, &SimpleSlab::v);
+    NF_TRY(nf_team_exchange(team, s->geom, p.data(), NF_HALO));
+    NF_TRY(nf_team_exchange(team, s->geom, u.data(), NF_HALO));
+    NF_TRY(nf_team_exchange(team, s->geom, v.data(), NF_HALO));
+  }
   s->bc_clean = true;
   return NF_OK;
 }
@@ -292,6 +457,12 @@ extern "C" int nf_simple_iterate(nf_simple* s, int n_iterations, double toleranc
   nf_ctx* ctx = s->ctx;
   NF_REQUIRE(ctx, n_iterations >= 0, "n_iterations < 0");
   NF_TRY(ensure_hist(s, n_iterations > 0 ? n_iterations : 1));
+  if (s->geom.dist && n_iterations > 0) {  // halos of the state (uploads fill them from the host copy; cheap to redo)
+    std::vector<double*> p = field_of(s, &SimpleSlab::p), u = field_of(s, &SimpleSlab::u), v = field_of(s, &SimpleSlab::v);
+    NF_TRY(nf_team_exchange(s->team, s->geom, p.data(), NF_HALO));
+    NF_TRY(nf_team_exchange(s->team, s->geom, u.data(), NF_HALO));
+    NF_TRY(nf_team_exchange(s->team, s->geom, v.data(), NF_HALO));
+  }
   int done = 0;
   for (int it = 0; it < n_iterations; ++it) {
     NF_TRY(simple_step(s, it, want_fields));

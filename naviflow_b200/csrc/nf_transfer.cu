@@ -145,11 +145,11 @@ __device__ __forceinline__ double nf_prolong_linear_value(const nf_grid& gc, con
 template <bool ADD>
 __global__ void __launch_bounds__(256)
 k_prolong_linear(nf_grid gc, const double* __restrict__ c, nf_grid gf, double* __restrict__ f, int nI, int nJ,
-                 int nby_fast) {
+                 int nby_fast, int I_lo, int I_hi) {
   if ((int)blockIdx.y < nby_fast) {
     const int J = blockIdx.x * 32 + threadIdx.x;
-    const int I = blockIdx.y * 8 + threadIdx.y;
-    if (I >= nI || J >= nJ) return;
+    const int I = I_lo + blockIdx.y * 8 + threadIdx.y;
+    if (I >= I_hi || J >= nJ) return;
     const size_t k = nf_idx(gc, I, J);
     const double c00 = c[k], c01 = c[k + 1], c10 = c[k + gc.ld], c11 = c[k + gc.ld + 1];
     const double v00 = c00;
@@ -157,16 +157,14 @@ k_prolong_linear(nf_grid gc, const double* __restrict__ c, nf_grid gf, double* _
     const double v10 = 0.5 * (c00 + c10);
     const double v11 = 0.25 * (((c00 + c10) + c01) + c11);
     const size_t kf = nf_idx(gf, 2 * I + 1, 2 * J + 1);
+    const bool r0 = (2 * I + 1 >= gf.gb) && (2 * I + 1 < gf.ge);  // slab runs: only this rank's fine rows
+    const bool r1 = (2 * I + 2 >= gf.gb) && (2 * I + 2 < gf.ge);
     if (ADD) {
-      f[kf] = f[kf] + v00;
-      f[kf + 1] = f[kf + 1] + v01;
-      f[kf + gf.ld] = f[kf + gf.ld] + v10;
-      f[kf + gf.ld + 1] = f[kf + gf.ld + 1] + v11;
+      if (r0) { f[kf] = f[kf] + v00; f[kf + 1] = f[kf + 1] + v01; }
+      if (r1) { f[kf + gf.ld] = f[kf + gf.ld] + v10; f[kf + gf.ld + 1] = f[kf + gf.ld + 1] + v11; }
     } else {
-      f[kf] = v00;
-      f[kf + 1] = v01;
-      f[kf + gf.ld] = v10;
-      f[kf + gf.ld + 1] = v11;
+      if (r0) { f[kf] = v00; f[kf + 1] = v01; }
+      if (r1) { f[kf + gf.ld] = v10; f[kf + gf.ld + 1] = v11; }
     }
     return;
   }
@@ -273,13 +271,17 @@ int nfi_prolong_linear(nf_ctx* ctx, const nf_grid* gc, const double* c, const nf
     if (nJ < 0) nJ = 0;
     if (nI == 0 || nJ == 0) nI = nJ = 0;
   }
+  // coarse rows whose 2x2 fine blocks touch this slab's fine rows [gb, ge)
+  int I_lo = gf->gb >= 1 ? (gf->gb - 1) / 2 : 0;
+  int I_hi = gf->ge / 2 < nI ? gf->ge / 2 : nI;
+  if (I_lo > I_hi) I_lo = I_hi;
   const int gx = nJ > 0 ? (nJ + 31) / 32 : 1;
-  const int nby_fast = nI > 0 ? (nI + 7) / 8 : 0;
+  const int nby_fast = (nI > 0 && I_hi > I_lo) ? (I_hi - I_lo + 7) / 8 : 0;
   const long long strip = (long long)(1 + gf->nx - (2 * nI + 1)) * gf->ny + (long long)(1 + gf->ny - (2 * nJ + 1)) * (2 * nI);
   const int nby_strip = (int)((strip + (long long)gx * 256 - 1) / ((long long)gx * 256));
   dim3 grid(gx, nby_fast + nby_strip, 1), block(32, 8, 1);
-  if (add) k_prolong_linear<true><<<grid, block, 0, ctx->stream>>>(*gc, c, *gf, f, nI, nJ, nby_fast);
-  else k_prolong_linear<false><<<grid, block, 0, ctx->stream>>>(*gc, c, *gf, f, nI, nJ, nby_fast);
+  if (add) k_prolong_linear<true><<<grid, block, 0, ctx->stream>>>(*gc, c, *gf, f, nI, nJ, nby_fast, I_lo, I_hi);
+  else k_prolong_linear<false><<<grid, block, 0, ctx->stream>>>(*gc, c, *gf, f, nI, nJ, nby_fast, I_lo, I_hi);
   NF_LAUNCH_CHECK(ctx);
   return NF_OK;
 }

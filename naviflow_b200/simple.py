@@ -32,7 +32,11 @@ _FIELD = {"u": 0, "v": 1, "p": 2, "u_star": 3, "v_star": 4, "d_u": 5, "d_v": 6, 
 
 class GpuSimpleSolver:
     def __init__(self, mesh, fluid, pressure_solver=None, momentum_solver=None, velocity_updater=None,
-                 boundary_conditions=None, alpha_p=0.3, alpha_u=0.7, fix_lid_corners=False, device=None):
+                 boundary_conditions=None, alpha_p=0.3, alpha_u=0.7, fix_lid_corners=False, device=None,
+                 distributed=None, virtual_ranks=1):
+        """``distributed``: cut the grid into row slabs over the ranks of the initialised torch.distributed
+        (NCCL) process group (default: automatically when its world size is > 1).  ``virtual_ranks`` > 1 cuts
+        the grid into that many slabs inside this process on this device (same code path; used by the tests)."""
         self.mesh, self.fluid = mesh, fluid
         self.pressure_solver = pressure_solver
         self.momentum_solver = momentum_solver if momentum_solver is not None else GpuJacobiMomentumSolver()
@@ -53,6 +57,9 @@ class GpuSimpleSolver:
         self._device = device
         self._state = None
         self._state_key = None
+        self._team = None
+        self._virtual_ranks = int(virtual_ranks)
+        self._distributed = distributed
         self._final_u_residual_field = self._final_v_residual_field = self._final_p_residual_field = None
         self.initialize_fields()
 
@@ -127,6 +134,38 @@ class GpuSimpleSolver:
         c.bc = bc_program_struct(self.bc_manager, nx, ny)
         return c
 
+    def _world(self):
+        """(world, rank) of the process group the grid is cut over, (1, 0) when not distributed."""
+        if self._distributed is False:
+            return 1, 0
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                return dist.get_world_size(), dist.get_rank()
+        except Exception:
+            pass
+        return 1, 0
+
+    def _make_team(self, ctx):
+        world, rank = self._world()
+        team = C.c_void_p()
+        if world > 1:
+            import torch
+            import torch.distributed as dist
+            ident = (C.c_ubyte * 128)()
+            if rank == 0:
+                ctx.check(ctx.lib.nf_nccl_unique_id(ctx.handle, ident), "nf_nccl_unique_id")
+            t = torch.tensor(list(ident), dtype=torch.uint8, device=f"cuda:{ctx.device}")
+            dist.broadcast(t, src=0)
+            ident = (C.c_ubyte * 128)(*t.cpu().tolist())
+            ctx.check(ctx.lib.nf_team_create_nccl(ctx.handle, world, rank, ident, C.byref(team)), "nf_team_create_nccl")
+        elif self._virtual_ranks > 1:
+            ctx.check(ctx.lib.nf_team_create_virtual(ctx.handle, self._virtual_ranks, C.byref(team)),
+                      "nf_team_create_virtual")
+        else:
+            return None
+        return team
+
     def _ensure_state(self):
         ctx = get_context(self._device)
         cfg = self._config()
@@ -134,14 +173,30 @@ class GpuSimpleSolver:
         if self._state is None or key != self._state_key:
             self._free()
             h = C.c_void_p()
-            ctx.check(ctx.lib.nf_simple_create(ctx.handle, C.byref(h), C.byref(cfg)), "nf_simple_create")
+            self._team = self._make_team(ctx)
+            if self._team is None:
+                ctx.check(ctx.lib.nf_simple_create(ctx.handle, C.byref(h), C.byref(cfg)), "nf_simple_create")
+            else:
+                ctx.check(ctx.lib.nf_simple_create_team(self._team, C.byref(h), C.byref(cfg)), "nf_simple_create_team")
             self._state, self._state_key = h, key
         return ctx, self._state
 
     def _free(self):
         if self._state is not None:
-            get_context(self._device).lib.nf_simple_destroy(self._state)
-            self._state, self._state_key = None, None
+            lib = get_context(self._device).lib
+            lib.nf_simple_destroy(self._state)
+            if self._team is not None:
+                lib.nf_team_free(self._team)
+            self._state, self._state_key, self._team = None, None, None
+
+    def local_rows(self):
+        """Cell rows [begin, end) this process owns (the whole grid unless distributed over processes)."""
+        ctx, st = self._ensure_state()
+        b, e = C.c_int(), C.c_int()
+        ctx.check(ctx.lib.nf_simple_local_rows(st, 0, C.byref(b), C.byref(e)), "nf_simple_local_rows")
+        if self._virtual_ranks > 1 and self._world()[0] == 1:
+            return 0, self.mesh.get_dimensions()[0]
+        return b.value, e.value
 
     def __del__(self):
         try:
@@ -189,6 +244,21 @@ class GpuSimpleSolver:
         self.u = self._download(ctx, st, "u", nx + 1, ny, self.u)
         self.v = self._download(ctx, st, "v", nx, ny + 1, self.v)
         self.p = self._download(ctx, st, "p", nx, ny, self.p)
+        if self._world()[0] > 1:  # every rank holds its own rows: assemble the full fields everywhere
+            self.u, self.v, self.p = (self._assemble(a) for a in (self.u, self.v, self.p))
+
+    def _assemble(self, arr):
+        import torch
+        import torch.distributed as dist
+        world, rank = self._world()
+        b, e = self.local_rows()
+        if rank == world - 1:
+            e = arr.shape[0]
+        t = torch.zeros(arr.shape, dtype=torch.float64, device=f"cuda:{get_context(self._device).device}")
+        t[b:e].copy_(torch.from_numpy(np.ascontiguousarray(arr[b:e])))
+        dist.all_reduce(t)
+        arr[...] = t.cpu().numpy()
+        return arr
 
     # ---- SimpleSolver.solve -----------------------------------------------------------------------
     def solve(self, max_iterations=1000, tolerance=1e-6, save_profile=False, profile_dir="results/profiles",

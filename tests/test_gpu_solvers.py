@@ -237,3 +237,57 @@ def test_plugins_drop_into_a_host_loop():
     alg.apply_boundary_conditions()
     alg.solve(max_iterations=3, tolerance=0.0)
     assert rel(alg.u, u) < 1e-12 and rel(alg.v, v) < 1e-12 and rel(alg.p, p) < 1e-12
+
+
+def _slab_run(n, Re, k, N, ranks, cycles=3, kind="v", smoother="gs", pre=3, post=3):
+    import naviflow_b200 as nb
+    mesh, fluid = cavity(n, Re)
+    sm = nb.GpuGaussSeidelSolver(omega=1.5) if smoother == "gs" else nb.GpuJacobiSolver(omega=0.8)
+    ps = nb.GpuMultiGridSolver(smoother=sm, max_iterations=cycles, tolerance=1e-30, pre_smoothing=pre,
+                               post_smoothing=post, cycle_type=kind)
+    alg = nb.GpuSimpleSolver(mesh, fluid, ps, nb.GpuJacobiMomentumSolver(n_jacobi_sweeps=k), alpha_p=0.3, alpha_u=0.7,
+                             virtual_ranks=ranks)
+    alg.set_boundary_condition("top", "velocity", {"u": 1.0, "v": 0.0})
+    for b in ("bottom", "left", "right"):
+        alg.set_boundary_condition(b, "wall")
+    res = alg.solve(max_iterations=N, tolerance=0.0)
+    return alg, res
+
+
+@pytest.mark.parametrize("n,ranks,k", [(257, 2, 5), (257, 4, 5), (385, 3, 2), (513, 2, 7), (513, 4, 9), (300, 2, 0)])
+def test_slab_decomposition_is_bit_identical_to_single_slab(n, ranks, k):
+    """Row-slab runs (halo exchange, replicated coarse levels, shrinking-region momentum sweeps) reproduce the
+    single-slab fields bit for bit; only the norms (partial sums per slab) may differ in the last bits."""
+    ref, rres = _slab_run(n, 1000, k, 4, 1)
+    alg, res = _slab_run(n, 1000, k, 4, ranks)
+    for fld in ("u", "v", "p"):
+        np.testing.assert_array_equal(getattr(alg, fld), getattr(ref, fld), err_msg=fld)
+    np.testing.assert_allclose(res.get_history("total_rel_norm"), rres.get_history("total_rel_norm"), rtol=1e-12)
+    np.testing.assert_allclose(res.get_history("p_rel_norm"), rres.get_history("p_rel_norm"), rtol=1e-10)
+
+
+def test_slab_decomposition_w_cycle_and_jacobi_smoother():
+    for kw in (dict(kind="w", cycles=2), dict(smoother="jacobi", pre=2, post=2)):
+        ref, _ = _slab_run(257, 400, 3, 3, 1, **kw)
+        alg, _ = _slab_run(257, 400, 3, 3, 2, **kw)
+        for fld in ("u", "v", "p"):
+            np.testing.assert_array_equal(getattr(alg, fld), getattr(ref, fld), err_msg=str(kw) + fld)
+
+
+def test_slab_decomposition_tolerance_driven_cycles_match():
+    """cycles-to-tolerance (the production setting) agrees with the single-slab run."""
+    import naviflow_b200 as nb
+    out = []
+    for ranks in (1, 3):
+        mesh, fluid = cavity(385, 1000)
+        ps = nb.GpuMultiGridSolver(smoother=nb.GpuGaussSeidelSolver(omega=1.5), max_iterations=100, tolerance=1e-3,
+                                   pre_smoothing=3, post_smoothing=3)
+        alg = nb.GpuSimpleSolver(mesh, fluid, ps, nb.GpuJacobiMomentumSolver(n_jacobi_sweeps=5), virtual_ranks=ranks)
+        alg.set_boundary_condition("top", "velocity", {"u": 1.0, "v": 0.0})
+        for b in ("bottom", "left", "right"):
+            alg.set_boundary_condition(b, "wall")
+        alg.solve(max_iterations=5, tolerance=0.0)
+        out.append((alg.u.copy(), alg.p.copy(), list(alg.pressure_iterations_history)))
+    assert out[0][2] == out[1][2]
+    np.testing.assert_array_equal(out[0][0], out[1][0])
+    np.testing.assert_array_equal(out[0][1], out[1][1])
