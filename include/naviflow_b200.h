@@ -244,6 +244,10 @@ int nf_team_create_virtual(nf_ctx*, int virtual_ranks, nf_team** out);
 int nf_team_free(nf_team*);
 /* SIMPLE state cut over the team (multigrid pressure solver, bilinear prolongation); the team outlives it */
 int nf_simple_create_team(nf_team*, nf_simple** out, const nf_simple_config* cfg);
+/* live CUDA-event timing of the finest-level fused smoother launches (3 sweeps each) inside nf_simple_iterate /
+ * nf_mg_solve: switches the instrumentation on / off and returns + resets the accumulated time and launch count */
+int nf_mg_smoother_timing(nf_mg*, int on, double* total_ms, long long* launches);
+int nf_simple_smoother_timing(nf_simple*, int on, double* total_ms, long long* launches);
 /* cell rows [*row_begin, *row_end) owned by local slab k of this process (k = 0 under torchrun) */
 int nf_simple_local_rows(nf_simple*, int k, int* row_begin, int* row_end);
 int nf_simple_destroy(nf_simple*);

@@ -59,6 +59,13 @@ struct nf_mg {
   double* scal_host = nullptr;                // pinned
   int coarse_N = 0;
   bool setup_done = false;
+  // optional live timing of the finest-level smoother launches (bench.py roofline): event pairs, read at the
+  // synchronisation points the cycle loop already has
+  bool timing = false;
+  std::vector<cudaEvent_t> ev;
+  size_t ev_used = 0;
+  double smooth_ms = 0.0;
+  long long smooth_launches = 0;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -247,6 +254,7 @@ static void build_interp_band(int mc, int m, int K, std::vector<double>& band, s
 // create / destroy / setup
 // =============================================================================================
 static int nlocal(const nf_mg* mg) { return (int)mg->team->local.size(); }
+static void mg_harvest_timing(nf_mg* mg);
 
 extern "C" int nf_mg_destroy(nf_mg* mg) {
   if (!mg) return NF_OK;
@@ -269,6 +277,7 @@ extern "C" int nf_mg_destroy(nf_mg* mg) {
   for (double* p : mg->coarse_inv) if (p) cudaFree(p);
   for (double* p : mg->scal) if (p) cudaFree(p);
   if (mg->scal_host) cudaFreeHost(mg->scal_host);
+  for (cudaEvent_t e : mg->ev) cudaEventDestroy(e);
   if (mg->owns_team) nf_team_destroy(mg->team);
   delete mg;
   return NF_OK;
@@ -519,10 +528,23 @@ static int mg_smooth(nf_mg* mg, int l, int n) {
       }
     while (left > 0) {
       const int ns = left >= 3 ? 3 : left;
+      const bool timed = mg->timing && l == 0 && ns == 3 && nl == 1;
+      if (timed) {
+        if (mg->ev_used + 2 > mg->ev.size()) {
+          cudaEvent_t a, b;
+          cudaEventCreate(&a); cudaEventCreate(&b);
+          mg->ev.push_back(a); mg->ev.push_back(b);
+        }
+        cudaEventRecord(mg->ev[mg->ev_used], ctx->stream);
+      }
       for (int k = 0; k < nl; ++k) {
         const nf_grid g = L.geom.grid(team->local[k]);
         NF_TRY(nfi_rbsor_fused(ctx, &g, &L.s[k].x, &L.s[k].x2, L.s[k].b, L.s[k].d_u, L.s[k].d_v, L.s[k].inv,
                                mg->cfg.omega, ns));
+      }
+      if (timed) {
+        cudaEventRecord(mg->ev[mg->ev_used + 1], ctx->stream);
+        mg->ev_used += 2;
       }
       if (L.geom.dist) {
         std::vector<double*> x = field_of(L, &MgSlab::x);
@@ -628,6 +650,7 @@ static int mg_rel_residual(nf_mg* mg, int l, double* r_norm, double* b_norm, int
   if (!sync) return NF_OK;
   NF_CHECK_CUDA(ctx, cudaMemcpyAsync(mg->scal_host, mg->scal[0], 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   NF_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (mg->timing) mg_harvest_timing(mg);
   *r_norm = sqrt(mg->scal_host[0]);
   if (with_b) *b_norm = sqrt(mg->scal_host[1]);
   return NF_OK;
@@ -757,6 +780,31 @@ int nfi_mg_solve(nf_mg* mg, double* const* b, double* const* x, double* const* r
 }
 
 double* nfi_mg_scalars(nf_mg* mg, int k) { return mg->scal[k]; }
+
+// collect the finished event pairs (call after a stream synchronisation)
+static void mg_harvest_timing(nf_mg* mg) {
+  for (size_t e = 0; e + 1 < mg->ev_used; e += 2) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, mg->ev[e], mg->ev[e + 1]) == cudaSuccess) {
+      mg->smooth_ms += ms;
+      mg->smooth_launches += 1;
+    }
+  }
+  mg->ev_used = 0;
+}
+
+// live timing of the finest-level k_rbsor_* <3 sweeps> launches: enable (on = 1) / disable, read and reset
+extern "C" int nf_mg_smoother_timing(nf_mg* mg, int on, double* total_ms, long long* launches) {
+  if (!mg) return NF_ERR_ARG;
+  NF_CHECK_CUDA(mg->ctx, cudaStreamSynchronize(mg->ctx->stream));
+  mg_harvest_timing(mg);
+  if (total_ms) *total_ms = mg->smooth_ms;
+  if (launches) *launches = mg->smooth_launches;
+  mg->smooth_ms = 0.0;
+  mg->smooth_launches = 0;
+  mg->timing = on != 0;
+  return NF_OK;
+}
 
 extern "C" int nf_mg_solve(nf_mg* mg, const double* b, double* x, double* r, nf_mg_info* info) {
   if (!mg) return NF_ERR_ARG;

@@ -171,6 +171,13 @@ extern "C" int nf_simple_create_team(nf_team* team, nf_simple** out, const nf_si
 
 extern "C" int nf_simple_ld(nf_simple* s) { return s ? s->geom.ld : 0; }
 
+extern "C" int nf_mg_smoother_timing(nf_mg* mg, int on, double* total_ms, long long* launches);
+// live CUDA-event timing of the finest-level fused smoother launches inside the outer iterations (single slab)
+extern "C" int nf_simple_smoother_timing(nf_simple* s, int on, double* total_ms, long long* launches) {
+  if (!s || !s->mg) return NF_ERR_ARG;
+  return nf_mg_smoother_timing(s->mg, on, total_ms, launches);
+}
+
 static double* field_ptr(SimpleSlab& S, int which) {
   switch (which) {
     case F_U: return S.u;

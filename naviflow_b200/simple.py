@@ -69,7 +69,7 @@ class GpuSimpleSolver:
         """Host field; page-locked when a CUDA device is present so that solve()'s H2D/D2H run at PCIe speed."""
         try:
             import torch
-            if torch.cuda.is_available():
+            if torch.cuda.is_available() and int(np.prod(shape)) * 8 <= (1 << 30):
                 t = torch.zeros(shape, dtype=torch.float64).pin_memory()
                 return t.numpy()  # the array keeps the pinned tensor alive through its base
         except Exception:
@@ -233,18 +233,27 @@ class GpuSimpleSolver:
                      u_abs_res=r.u_abs_res, v_abs_res=r.v_abs_res, pressure_iterations=r.pressure_iterations)
                 for r in infos[: done.value]]
 
+    def smoother_timing(self, on):
+        """Switches the live CUDA-event timing of the finest-level smoother launches on/off; returns the
+        (total ms, launches) accumulated since the last call."""
+        ctx, st = self._ensure_state()
+        ms, cnt = C.c_double(), C.c_longlong()
+        ctx.check(ctx.lib.nf_simple_smoother_timing(st, 1 if on else 0, C.byref(ms), C.byref(cnt)),
+                  "nf_simple_smoother_timing")
+        return ms.value, cnt.value
+
     def push_fields(self):
         ctx, st = self._ensure_state()
         for name in ("u", "v", "p"):
             self._upload(ctx, st, name, getattr(self, name))
 
-    def pull_fields(self):
+    def pull_fields(self, gather=True):
         ctx, st = self._ensure_state()
         nx, ny = self.mesh.get_dimensions()
         self.u = self._download(ctx, st, "u", nx + 1, ny, self.u)
         self.v = self._download(ctx, st, "v", nx, ny + 1, self.v)
         self.p = self._download(ctx, st, "p", nx, ny, self.p)
-        if self._world()[0] > 1:  # every rank holds its own rows: assemble the full fields everywhere
+        if gather and self._world()[0] > 1:  # every rank holds its own rows: assemble the full fields everywhere
             self.u, self.v, self.p = (self._assemble(a) for a in (self.u, self.v, self.p))
 
     def _assemble(self, arr):
@@ -262,7 +271,9 @@ class GpuSimpleSolver:
 
     # ---- SimpleSolver.solve -----------------------------------------------------------------------
     def solve(self, max_iterations=1000, tolerance=1e-6, save_profile=False, profile_dir="results/profiles",
-              track_infinity_norm=False, infinity_norm_interval=10, use_l2_norm=False, chunk=None):
+              track_infinity_norm=False, infinity_norm_interval=10, use_l2_norm=False, chunk=None, gather=True):
+        """``gather=False`` (distributed runs): every rank keeps only its own rows in ``self.u/v/p`` instead of
+        assembling the full fields on all ranks at the end."""
         if save_profile:
             raise NotImplementedError("HDF5 profile output is out of scope (SURVEY.md section 2, row 12)")
         t0 = time.perf_counter()
@@ -298,7 +309,7 @@ class GpuSimpleSolver:
                     break
         except KeyboardInterrupt:
             print("Interrupted by user.")
-        self.pull_fields()
+        self.pull_fields(gather)
         self._final_p_residual_field = self._download(ctx, st, "p_res", nx, ny, self._final_p_residual_field)
         result = SimulationResult(self.u, self.v, self.p, self.mesh, iterations=iteration - 1,
                                   residuals=self.residual_history, reynolds=self.fluid.get_reynolds_number(),
