@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- SIMPLE outer-iteration throughput on the BASELINE.json workload.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--n 4097]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--grid 4097]
 
 Workload (config.workload): lid-driven cavity n x n (default 4097, BASELINE configs[2]), Re = 1000, from rest,
 SIMPLE (alpha_p 0.3, alpha_u 0.7) with JacobiMatrixMomentumSolver-style fixed Jacobi momentum sweeps and the
@@ -37,7 +37,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=0, help="grid size (cells per side); default 4097 on 1 GPU and "
+    ap.add_argument("--grid", dest="n", type=int, default=0, help="grid size (cells per side); default 4097 on 1 GPU and "
                     "4097*sqrt(N) on N GPUs (weak scaling: 16.8 M cells per GPU)")
     ap.add_argument("--momentum-sweeps", type=int, default=5)
     ap.add_argument("--mg-cycles", type=int, default=100, help="max V-cycles per pressure solve")
