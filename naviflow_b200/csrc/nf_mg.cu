@@ -14,6 +14,7 @@
 // level (and all coarser ones) is replicated on every rank: the restricted right-hand side is shared once
 // and the coarse part of the cycle runs redundantly, so the way back up needs no communication.
 #include <math.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -59,6 +60,15 @@ struct nf_mg {
   double* scal_host = nullptr;                // pinned
   int coarse_N = 0;
   bool setup_done = false;
+  // CUDA graph of one whole cycle at level 0 (single slab): captured after a warm-up cycle, replayed afterwards.
+  // Valid while the level-0 arrays stay the same and every level swaps x/x2 an even number of times per cycle.
+  cudaGraphExec_t graph_exec = nullptr;
+  cudaStream_t cap_stream = nullptr;
+  const void* graph_key[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // x, b, d_u, d_v, x2 of level 0
+  int graph_kind = -1;
+  long long graph_nodes = 0;
+  int warm_cycles = 0;
+  bool use_graph = true;
   // optional live timing of the finest-level smoother launches (bench.py roofline): event pairs, read at the
   // synchronisation points the cycle loop already has
   bool timing = false;
@@ -278,6 +288,8 @@ extern "C" int nf_mg_destroy(nf_mg* mg) {
   for (double* p : mg->scal) if (p) cudaFree(p);
   if (mg->scal_host) cudaFreeHost(mg->scal_host);
   for (cudaEvent_t e : mg->ev) cudaEventDestroy(e);
+  if (mg->graph_exec) cudaGraphExecDestroy(mg->graph_exec);
+  if (mg->cap_stream) cudaStreamDestroy(mg->cap_stream);
   if (mg->owns_team) nf_team_destroy(mg->team);
   delete mg;
   return NF_OK;
@@ -633,6 +645,65 @@ static int mg_cycle(nf_mg* mg, int l, int kind) {
   return NF_OK;
 }
 
+// One cycle at level 0 through a CUDA graph when possible (see nf_mg::graph_exec).  The launch sequence of a
+// cycle is static: ~50 launches (10 levels) collapse into one graph launch, which removes the CPU launch cost and
+// most of the inter-kernel gaps on the small levels.
+static int mg_cycle_top(nf_mg* mg, int kind) {
+  nf_ctx* ctx = mg->ctx;
+  MgLevel& L = mg->lv[0];
+  const char* env = getenv("NF_MG_GRAPH");
+  const bool allowed = mg->use_graph && !(env && env[0] == '0') && nlocal(mg) == 1 && !L.geom.dist &&
+                       mg->cfg.smoother == 0 && !mg->timing &&
+                       ((mg->cfg.pre + 2) / 3 + (mg->cfg.post + 2) / 3) % 2 == 0;  // even number of x/x2 swaps
+  if (!allowed) return mg_cycle(mg, 0, kind);
+  MgSlab& S = L.s[0];
+  const void* key[5] = {S.x, S.b, S.d_u, S.d_v, S.x2};
+  bool same = mg->graph_exec && mg->graph_kind == kind;
+  for (int q = 0; q < 5 && same; ++q) same = (key[q] == mg->graph_key[q]);
+  if (same) {
+    NF_CHECK_CUDA(ctx, cudaGraphLaunch(mg->graph_exec, ctx->stream));
+    ctx->launches += mg->graph_nodes;
+    return NF_OK;
+  }
+  if (mg->warm_cycles < 1) {  // first cycle ever: plain launches (function attributes, tensor-map encoder, ...)
+    mg->warm_cycles++;
+    return mg_cycle(mg, 0, kind);
+  }
+  if (mg->graph_exec) { cudaGraphExecDestroy(mg->graph_exec); mg->graph_exec = nullptr; }
+  if (!mg->cap_stream) NF_CHECK_CUDA(ctx, cudaStreamCreateWithFlags(&mg->cap_stream, cudaStreamNonBlocking));
+  cudaStream_t orig = ctx->stream;
+  const long long l0 = ctx->launches;
+  NF_CHECK_CUDA(ctx, cudaStreamBeginCapture(mg->cap_stream, cudaStreamCaptureModeRelaxed));
+  ctx->stream = mg->cap_stream;
+  int st = mg_cycle(mg, 0, kind);
+  ctx->stream = orig;
+  cudaGraph_t graph = nullptr;
+  cudaError_t ce = cudaStreamEndCapture(mg->cap_stream, &graph);
+  if (st != NF_OK || ce != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    mg->use_graph = false;  // fall back to plain launches for good
+    ctx->launches = l0;
+    if (st != NF_OK) return st;
+    return mg_cycle(mg, 0, kind);
+  }
+  mg->graph_nodes = ctx->launches - l0;
+  ctx->launches = l0;
+  ce = cudaGraphInstantiate(&mg->graph_exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ce != cudaSuccess) {
+    cudaGetLastError();
+    mg->graph_exec = nullptr;
+    mg->use_graph = false;
+    return mg_cycle(mg, 0, kind);
+  }
+  for (int q = 0; q < 5; ++q) mg->graph_key[q] = key[q];
+  mg->graph_kind = kind;
+  NF_CHECK_CUDA(ctx, cudaGraphLaunch(mg->graph_exec, ctx->stream));
+  ctx->launches += mg->graph_nodes;
+  return NF_OK;
+}
+
 // ||b - A x|| and ||b|| on level l over the whole grid (host values; multigrid.py:185-189, :652-676).
 // *b_norm < 0 on entry: ||b|| is not known yet and is computed in the same pass; otherwise it is kept.
 // sync == 0: leave sum r^2, sum b^2 in scal[k][0..1] (already reduced over the team) and do not synchronise.
@@ -757,7 +828,7 @@ int nfi_mg_solve(nf_mg* mg, double* const* b, double* const* x, double* const* r
       status = mg_rel_residual(mg, 0, &rn, &bn, sync);
     } else {
       for (int it = 0; it < mg->cfg.max_iterations; ++it) {
-        status = mg_cycle(mg, 0, mg->cfg.cycle_type);
+        status = mg_cycle_top(mg, mg->cfg.cycle_type);
         if (status) break;
         ++cycles;
         status = mg_rel_residual(mg, 0, &rn, &bn, 1);

@@ -152,7 +152,19 @@ __global__ void k_residual_norms(nf_grid g, const double* __restrict__ p, const 
   if (WITH_B) acc[WITH_B ? 1 : 0] = 0.0;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j < g.ny) {
-    for (int i = g.gb + blockIdx.y * blockDim.y + threadIdx.y; i < g.ge; i += gridDim.y * blockDim.y) {
+    const int st = gridDim.y * blockDim.y;
+    int i = g.gb + blockIdx.y * blockDim.y + threadIdx.y;
+    for (; i + st < g.ge; i += 2 * st) {  // two independent stencils in flight; summation order unchanged
+      const size_t k0 = nf_idx(g, i, j), k1 = nf_idx(g, i + st, j);
+      const double b0 = b[k0], b1 = b[k1];
+      const double r0 = b0 - nf_Ap_cell(g, p, d_u, d_v, i, j);
+      const double r1 = b1 - nf_Ap_cell(g, p, d_u, d_v, i + st, j);
+      if (r) { r[k0] = r0; r[k1] = r1; }
+      acc[0] += r0 * r0;
+      acc[0] += r1 * r1;
+      if (WITH_B) { acc[WITH_B ? 1 : 0] += b0 * b0; acc[WITH_B ? 1 : 0] += b1 * b1; }
+    }
+    for (; i < g.ge; i += st) {
       const size_t k = nf_idx(g, i, j);
       const double bv = b[k];
       const double rv = bv - nf_Ap_cell(g, p, d_u, d_v, i, j);

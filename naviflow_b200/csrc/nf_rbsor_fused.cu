@@ -97,44 +97,56 @@ __device__ __forceinline__ void rbsor_passes(double (&sP)[2][RRW][33], int tx, i
                                              const double (&aS0)[KS], const double (&aE1)[KS], const double (&aW1)[KS],
                                              const double (&aN1)[KS], const double (&aS1)[KS], const bool (&ok0)[KS],
                                              const bool (&ok1)[KS]) {
-  constexpr int H = 2 * NS;
-  constexpr int TR = RRW - 2 * H;
+  // All three row slots are updated in every pass without a branch (the commit is predicated on `ok`), so the
+  // compiler can interleave the three independent fp64 dependency chains.  Rows outside the shrinking trapezoid
+  // are updated too; their values are never read by cells that matter.  Neighbour rows are clamped for the two
+  // region-edge rows, whose result is discarded anyway.
+  int rm[KS], rp[KS];
+#pragma unroll
+  for (int k = 0; k < KS; ++k) {
+    const int r = ty + NYT * k;
+    rm[k] = r > 0 ? r - 1 : 0;
+    rp[k] = r < RRW - 1 ? r + 1 : RRW - 1;
+  }
+  const int txm = tx > 0 ? tx - 1 : 0;
+  const int par = ty & 1;  // r & 1 for every slot (rows differ by 16)
 #pragma unroll
   for (int t = 0; t < 2 * NS; ++t) {
     const int col = t & 1;            // 0: (i+j) even ("red"), 1: odd ("black")
-    const int m = 2 * NS - 1 - t;     // pass t is only needed within m cells of the tile
     const int s = S0 ^ col;           // which cell of the pair has colour `col`: 0 -> cell 0, 1 -> cell 1
+    const int lp = par ^ s;           // local parity of the updated cell
+    double pnew[KS];
 #pragma unroll
     for (int k = 0; k < KS; ++k) {
       const int r = ty + NYT * k;
-      const int lp = (r & 1) ^ s;     // local parity of the updated cell
+      const double pc = s ? p1[k] : p0[k];
+      const double bc = s ? b1[k] : b0[k];
+      const double ic = s ? inv1[k] : inv0[k];
+      const double aE = s ? aE1[k] : aE0[k];
+      const double aW = s ? aW1[k] : aW0[k];
+      const double aN = s ? aN1[k] : aN0[k];
+      const double aS = s ? aS1[k] : aS0[k];
+      // opposite-colour neighbours: rows r+-1 from shared memory; in the row, one is the thread's own partner
+      // cell (register) and the other belongs to the neighbouring pair
+      const double pE = sP[lp ^ 1][rp[k]][tx];
+      const double pW = sP[lp ^ 1][rm[k]][tx];
+      const double pN = s ? sP[lp ^ 1][r][tx + 1] : p1[k];
+      const double pS = s ? p0[k] : sP[lp ^ 1][r][txm];
+      double acc = bc;       // ((((b + E) + W) + N) + S) * (1/aP): gauss_seidel.py:285-299
+      acc += aE * pE;
+      acc += aW * pW;
+      acc += aN * pN;
+      acc += aS * pS;
+      const double pn = acc * ic;
+      pnew[k] = pc + omega * (pn - pc);
+    }
+#pragma unroll
+    for (int k = 0; k < KS; ++k) {
+      const int r = ty + NYT * k;
       const bool ok = s ? ok1[k] : ok0[k];
-      if (r >= H - m && r < H + TR + m) {  // warp-uniform (one region row per warp and slot); rows 1..46 only
-        const double pc = s ? p1[k] : p0[k];
-        const double bc = s ? b1[k] : b0[k];
-        const double ic = s ? inv1[k] : inv0[k];
-        const double aE = s ? aE1[k] : aE0[k];
-        const double aW = s ? aW1[k] : aW0[k];
-        const double aN = s ? aN1[k] : aN0[k];
-        const double aS = s ? aS1[k] : aS0[k];
-        // opposite-colour neighbours: rows r+-1 from shared memory; in the row, one is the thread's own partner
-        // cell (register) and the other belongs to the neighbouring pair (lanes 0 / 31 read the row padding:
-        // their result is discarded because ok is false on the region edge)
-        const double pE = sP[lp ^ 1][r + 1][tx];
-        const double pW = sP[lp ^ 1][r - 1][tx];
-        const double pN = s ? sP[lp ^ 1][r][tx + 1] : p1[k];
-        const double pS = s ? p0[k] : sP[lp ^ 1][r][tx - 1];
-        double acc = bc;       // ((((b + E) + W) + N) + S) * (1/aP): gauss_seidel.py:285-299
-        acc += aE * pE;
-        acc += aW * pW;
-        acc += aN * pN;
-        acc += aS * pS;
-        const double pn = acc * ic;
-        const double pnew = pc + omega * (pn - pc);
-        if (ok) {
-          if (s) p1[k] = pnew; else p0[k] = pnew;
-          sP[lp][r][tx] = pnew;
-        }
+      if (ok) {
+        if (s) p1[k] = pnew[k]; else p0[k] = pnew[k];
+        sP[lp][r][tx] = pnew[k];
       }
     }
     __syncthreads();
