@@ -193,6 +193,10 @@ int nf_momentum_links_v(nf_ctx*, const nf_grid*, const double* u_bc, const doubl
 /* n_sweeps Jacobi sweeps x <- D^-1 (b - (A-D) x); is_u selects the (nx+1,ny) / (nx,ny+1) shape.
  * Result ends in x (tmp is scratch). */
 int nf_momentum_jacobi(nf_ctx*, const nf_grid*, int is_u, nf_links L, double* x, double* tmp, int n_sweeps);
+/* Same sweeps, temporally blocked (up to 6 per tile load, bit-identical); with rel_norm_host != NULL the relaxed
+ * residual norm (and field, may be NULL) of the result is evaluated behind the last sweep. */
+int nf_momentum_jacobi_fused(nf_ctx*, const nf_grid*, int is_u, nf_links L, double* x, double* tmp, int n_sweeps,
+                             double* field_out, double* rel_norm_host);
 /* r = b - A x (field_out, with the reference's boundary zeroing) and ||r_masked||/(||b_masked||+1e-15) */
 int nf_momentum_residual(nf_ctx*, const nf_grid*, int is_u, nf_links L, const double* x, double* field_out,
                          double* rel_norm_host);

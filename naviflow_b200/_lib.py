@@ -114,6 +114,7 @@ SIGNATURES = {
     "nf_momentum_links_u": (C.c_int, [CTX, GP, P, P, P, C.c_double, C.c_double, C.c_int, NfLinks, P]),
     "nf_momentum_links_v": (C.c_int, [CTX, GP, P, P, P, C.c_double, C.c_double, C.c_int, NfLinks, P]),
     "nf_momentum_jacobi": (C.c_int, [CTX, GP, C.c_int, NfLinks, P, P, C.c_int]),
+    "nf_momentum_jacobi_fused": (C.c_int, [CTX, GP, C.c_int, NfLinks, P, P, C.c_int, P, DBL_OUT]),
     "nf_momentum_residual": (C.c_int, [CTX, GP, C.c_int, NfLinks, P, P, DBL_OUT]),
     "nf_correct_velocity": (C.c_int, [CTX, GP, C.POINTER(NfBcProgram), P, P, P, P, P, P, P]),
     "nf_update_pressure": (C.c_int, [CTX, GP, P, P, C.c_double, P]),

@@ -26,8 +26,15 @@
 
 int nfi_residual_restrict_fw(nf_ctx*, const nf_grid* gf, const double* p, const double* b, const double* d_u,
                              const double* d_v, const nf_grid* gc, double* c);
-int nfi_rbsor_fused(nf_ctx*, const nf_grid*, double** p, double** palt, const double* b, const double* d_u,
-                    const double* d_v, const double* inv, double omega, int n_sweeps);
+struct nf_smooth_extra {  // see nf_rbsor_fused.cu
+  int mode = 0;
+  nf_grid gc;
+  double* coarse_b = nullptr;
+  double* out = nullptr;
+  bool fused = false;
+};
+int nfi_rbsor_fused_x(nf_ctx*, const nf_grid*, double** p, double** palt, const double* b, const double* d_u,
+                      const double* d_v, const double* inv, double omega, int n_sweeps, nf_smooth_extra* extra);
 int nfi_inv_diag(nf_ctx*, const nf_grid*, const double* d_u, const double* d_v, double* inv);
 int nfi_prolong_banded(nf_ctx*, const nf_grid* gc, const double* c, const nf_grid* gf, double* f, double* tmp,
                        int ldt, const double* band, const int* start, int W, int add);
@@ -66,6 +73,7 @@ struct nf_mg {
   cudaStream_t cap_stream = nullptr;
   const void* graph_key[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // x, b, d_u, d_v, x2 of level 0
   int graph_kind = -1;
+  bool graph_norm_fused = false;
   long long graph_nodes = 0;
   int warm_cycles = 0;
   bool use_graph = true;
@@ -525,7 +533,8 @@ extern "C" int nf_mg_setup(nf_mg* mg, const double* d_u, const double* d_v) {
 // cycles.  Level-0 solution / right-hand side live in lv[0].s[k].x / .b (set by the callers).
 // =============================================================================================
 // n smoothing sweeps on level l; on a cut level the iterate's halo is valid on entry and on return
-static int mg_smooth(nf_mg* mg, int l, int n) {
+// extra (single slab only): work fused behind the last smoother launch, see nf_smooth_extra
+static int mg_smooth(nf_mg* mg, int l, int n, nf_smooth_extra* extra = nullptr) {
   nf_ctx* ctx = mg->ctx;
   nf_team* team = mg->team;
   MgLevel& L = mg->lv[l];
@@ -535,8 +544,8 @@ static int mg_smooth(nf_mg* mg, int l, int n) {
     if (left == 0)
       for (int k = 0; k < nl; ++k) {
         const nf_grid g = L.geom.grid(team->local[k]);
-        NF_TRY(nfi_rbsor_fused(ctx, &g, &L.s[k].x, &L.s[k].x2, L.s[k].b, L.s[k].d_u, L.s[k].d_v, L.s[k].inv,
-                               mg->cfg.omega, 0));
+        NF_TRY(nfi_rbsor_fused_x(ctx, &g, &L.s[k].x, &L.s[k].x2, L.s[k].b, L.s[k].d_u, L.s[k].d_v, L.s[k].inv,
+                                 mg->cfg.omega, 0, nullptr));
       }
     while (left > 0) {
       const int ns = left >= 3 ? 3 : left;
@@ -551,8 +560,8 @@ static int mg_smooth(nf_mg* mg, int l, int n) {
       }
       for (int k = 0; k < nl; ++k) {
         const nf_grid g = L.geom.grid(team->local[k]);
-        NF_TRY(nfi_rbsor_fused(ctx, &g, &L.s[k].x, &L.s[k].x2, L.s[k].b, L.s[k].d_u, L.s[k].d_v, L.s[k].inv,
-                               mg->cfg.omega, ns));
+        NF_TRY(nfi_rbsor_fused_x(ctx, &g, &L.s[k].x, &L.s[k].x2, L.s[k].b, L.s[k].d_u, L.s[k].d_v, L.s[k].inv,
+                                 mg->cfg.omega, ns, (extra && nl == 1 && left == ns) ? extra : nullptr));
       }
       if (timed) {
         cudaEventRecord(mg->ev[mg->ev_used + 1], ctx->stream);
@@ -618,18 +627,29 @@ static int mg_publish_rhs(nf_mg* mg, int l) {
 }
 
 // one V (kind 0) or W (kind 1) cycle on level l: multigrid.py:304-432 / :434-560
-static int mg_cycle(nf_mg* mg, int l, int kind) {
+// want_norm (level 0 of the 'v' / 'w' loop): ask the last post-smoothing launch for the residual norms
+// (-> mg->scal[0][0..1]); *norm_fused reports whether that happened
+static int mg_cycle(nf_mg* mg, int l, int kind, bool want_norm = false, bool* norm_fused = nullptr) {
   nf_ctx* ctx = mg->ctx;
   nf_team* team = mg->team;
   MgLevel& L = mg->lv[l];
   const int nl = nlocal(mg);
+  if (norm_fused) *norm_fused = false;
   if (L.geom.nx <= mg->cfg.coarsest || l + 1 == (int)mg->lv.size()) return mg_coarse_solve(mg, l);
   MgLevel& C = mg->lv[l + 1];
-  NF_TRY(mg_smooth(mg, l, mg->cfg.pre));
+  nf_smooth_extra pre;
+  if (nl == 1 && mg->cfg.smoother == 0 && mg->cfg.restriction == 0 && !L.geom.dist) {
+    pre.mode = 2;
+    pre.gc = restrict_target(C, team->local[0]);
+    pre.coarse_b = C.s[0].b;
+  }
+  NF_TRY(mg_smooth(mg, l, mg->cfg.pre, pre.mode ? &pre : nullptr));
   for (int k = 0; k < nl; ++k) {
     const int r = team->local[k];
     const nf_grid gf = L.geom.grid(r), gc = restrict_target(C, r);
-    if (mg->cfg.restriction == 0) {
+    if (pre.fused) {
+      // coarse right-hand side already written by the smoother
+    } else if (mg->cfg.restriction == 0) {
       NF_TRY(nfi_residual_restrict_fw(ctx, &gf, L.s[k].x, L.s[k].b, L.s[k].d_u, L.s[k].d_v, &gc, C.s[k].b));
     } else {
       NF_TRY(nfi_residual(ctx, &gf, L.s[k].x, L.s[k].b, L.s[k].d_u, L.s[k].d_v, L.s[k].r));
@@ -641,21 +661,27 @@ static int mg_cycle(nf_mg* mg, int l, int kind) {
   const int reps = (kind == 1) ? 2 : 1;
   for (int rep = 0; rep < reps; ++rep) NF_TRY(mg_cycle(mg, l + 1, kind));
   NF_TRY(mg_prolong(mg, l, mg->cfg.interpolation, 1));
-  NF_TRY(mg_smooth(mg, l, mg->cfg.post));
+  nf_smooth_extra post;
+  if (want_norm && nl == 1 && mg->cfg.smoother == 0 && !L.geom.dist) {
+    post.mode = 1;
+    post.out = mg->scal[0];
+  }
+  NF_TRY(mg_smooth(mg, l, mg->cfg.post, post.mode ? &post : nullptr));
+  if (norm_fused) *norm_fused = post.fused;
   return NF_OK;
 }
 
 // One cycle at level 0 through a CUDA graph when possible (see nf_mg::graph_exec).  The launch sequence of a
 // cycle is static: ~50 launches (10 levels) collapse into one graph launch, which removes the CPU launch cost and
 // most of the inter-kernel gaps on the small levels.
-static int mg_cycle_top(nf_mg* mg, int kind) {
+static int mg_cycle_top(nf_mg* mg, int kind, bool* norm_fused) {
   nf_ctx* ctx = mg->ctx;
   MgLevel& L = mg->lv[0];
   const char* env = getenv("NF_MG_GRAPH");
   const bool allowed = mg->use_graph && !(env && env[0] == '0') && nlocal(mg) == 1 && !L.geom.dist &&
                        mg->cfg.smoother == 0 && !mg->timing &&
                        ((mg->cfg.pre + 2) / 3 + (mg->cfg.post + 2) / 3) % 2 == 0;  // even number of x/x2 swaps
-  if (!allowed) return mg_cycle(mg, 0, kind);
+  if (!allowed) return mg_cycle(mg, 0, kind, true, norm_fused);
   MgSlab& S = L.s[0];
   const void* key[5] = {S.x, S.b, S.d_u, S.d_v, S.x2};
   bool same = mg->graph_exec && mg->graph_kind == kind;
@@ -663,11 +689,12 @@ static int mg_cycle_top(nf_mg* mg, int kind) {
   if (same) {
     NF_CHECK_CUDA(ctx, cudaGraphLaunch(mg->graph_exec, ctx->stream));
     ctx->launches += mg->graph_nodes;
+    *norm_fused = mg->graph_norm_fused;
     return NF_OK;
   }
   if (mg->warm_cycles < 1) {  // first cycle ever: plain launches (function attributes, tensor-map encoder, ...)
     mg->warm_cycles++;
-    return mg_cycle(mg, 0, kind);
+    return mg_cycle(mg, 0, kind, true, norm_fused);
   }
   if (mg->graph_exec) { cudaGraphExecDestroy(mg->graph_exec); mg->graph_exec = nullptr; }
   if (!mg->cap_stream) NF_CHECK_CUDA(ctx, cudaStreamCreateWithFlags(&mg->cap_stream, cudaStreamNonBlocking));
@@ -675,7 +702,8 @@ static int mg_cycle_top(nf_mg* mg, int kind) {
   const long long l0 = ctx->launches;
   NF_CHECK_CUDA(ctx, cudaStreamBeginCapture(mg->cap_stream, cudaStreamCaptureModeRelaxed));
   ctx->stream = mg->cap_stream;
-  int st = mg_cycle(mg, 0, kind);
+  bool nf = false;
+  int st = mg_cycle(mg, 0, kind, true, &nf);
   ctx->stream = orig;
   cudaGraph_t graph = nullptr;
   cudaError_t ce = cudaStreamEndCapture(mg->cap_stream, &graph);
@@ -685,9 +713,10 @@ static int mg_cycle_top(nf_mg* mg, int kind) {
     mg->use_graph = false;  // fall back to plain launches for good
     ctx->launches = l0;
     if (st != NF_OK) return st;
-    return mg_cycle(mg, 0, kind);
+    return mg_cycle(mg, 0, kind, true, norm_fused);
   }
   mg->graph_nodes = ctx->launches - l0;
+  mg->graph_norm_fused = nf;
   ctx->launches = l0;
   ce = cudaGraphInstantiate(&mg->graph_exec, graph, 0);
   cudaGraphDestroy(graph);
@@ -695,29 +724,35 @@ static int mg_cycle_top(nf_mg* mg, int kind) {
     cudaGetLastError();
     mg->graph_exec = nullptr;
     mg->use_graph = false;
-    return mg_cycle(mg, 0, kind);
+    return mg_cycle(mg, 0, kind, true, norm_fused);
   }
   for (int q = 0; q < 5; ++q) mg->graph_key[q] = key[q];
   mg->graph_kind = kind;
   NF_CHECK_CUDA(ctx, cudaGraphLaunch(mg->graph_exec, ctx->stream));
   ctx->launches += mg->graph_nodes;
+  *norm_fused = nf;
   return NF_OK;
 }
 
 // ||b - A x|| and ||b|| on level l over the whole grid (host values; multigrid.py:185-189, :652-676).
 // *b_norm < 0 on entry: ||b|| is not known yet and is computed in the same pass; otherwise it is kept.
 // sync == 0: leave sum r^2, sum b^2 in scal[k][0..1] (already reduced over the team) and do not synchronise.
-static int mg_rel_residual(nf_mg* mg, int l, double* r_norm, double* b_norm, int sync) {
+// have_norms: sum r^2, sum b^2 were already left in mg->scal[0][0..1] by the post-smoother (no kernel needed)
+static int mg_rel_residual(nf_mg* mg, int l, double* r_norm, double* b_norm, int sync, bool have_norms = false) {
   nf_ctx* ctx = mg->ctx;
   nf_team* team = mg->team;
   MgLevel& L = mg->lv[l];
   const int nl = nlocal(mg);
-  const int with_b = (*b_norm < 0.0) ? 1 : 0;
-  for (int k = 0; k < nl; ++k) {
-    const nf_grid g = L.geom.grid(team->local[k]);
-    NF_TRY(nfi_residual_norms(ctx, &g, L.s[k].x, L.s[k].b, L.s[k].d_u, L.s[k].d_v, L.s[k].r, with_b, mg->scal[k]));
+  int with_b = (*b_norm < 0.0) ? 1 : 0;
+  if (have_norms) {
+    with_b = 1;
+  } else {
+    for (int k = 0; k < nl; ++k) {
+      const nf_grid g = L.geom.grid(team->local[k]);
+      NF_TRY(nfi_residual_norms(ctx, &g, L.s[k].x, L.s[k].b, L.s[k].d_u, L.s[k].d_v, L.s[k].r, with_b, mg->scal[k]));
+    }
+    if (L.geom.dist) NF_TRY(nf_team_allreduce(team, mg->scal.data(), with_b ? 2 : 1));
   }
-  if (L.geom.dist) NF_TRY(nf_team_allreduce(team, mg->scal.data(), with_b ? 2 : 1));
   if (!sync) return NF_OK;
   NF_CHECK_CUDA(ctx, cudaMemcpyAsync(mg->scal_host, mg->scal[0], 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   NF_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -827,15 +862,23 @@ int nfi_mg_solve(nf_mg* mg, double* const* b, double* const* x, double* const* r
       }
       status = mg_rel_residual(mg, 0, &rn, &bn, sync);
     } else {
+      bool fused_any = false;
       for (int it = 0; it < mg->cfg.max_iterations; ++it) {
-        status = mg_cycle_top(mg, mg->cfg.cycle_type);
+        bool nfz = false;
+        status = mg_cycle_top(mg, mg->cfg.cycle_type, &nfz);
         if (status) break;
         ++cycles;
-        status = mg_rel_residual(mg, 0, &rn, &bn, 1);
+        status = mg_rel_residual(mg, 0, &rn, &bn, 1, nfz);
         if (status) break;
+        fused_any = fused_any || nfz;
         const double rel = bn > 0.0 ? rn / bn : rn;
         if (rel < mg->cfg.tolerance) break;
       }
+      if (!status && fused_any)  // the residual field itself (info['field']) once, at the end
+        for (int k = 0; k < nlocal(mg) && !status; ++k) {
+          const nf_grid g0 = L.geom.grid(mg->team->local[k]);
+          status = nfi_residual(ctx, &g0, L.s[k].x, L.s[k].b, L.s[k].d_u, L.s[k].d_v, L.s[k].r);
+        }
     }
   } while (0);
   int st2 = mg_unbind_level0(mg, x, k2, kr);

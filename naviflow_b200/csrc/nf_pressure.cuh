@@ -40,6 +40,17 @@ __device__ __forceinline__ double nf_Ap_cell(const nf_grid& g, const double* __r
                                              int i, int j) {
   const size_t k = nf_idx(g, i, j);
   const double pc = p[k];
+  if (i >= 1 && i < g.nx - 1 && j >= 1 && j < g.ny - 1) {
+    // interior cell: no folding, no masks (same expression order, so the same bits as the general path)
+    const double e = g.rho * d_u[k + g.ld] * g.dy, w = g.rho * d_u[k] * g.dy;
+    const double n = g.rho * d_v[k + 1] * g.dx, s = g.rho * d_v[k] * g.dx;
+    double out = (((e + w) + n) + s) * pc;
+    out -= e * p[k + g.ld];
+    out -= w * p[k - g.ld];
+    out -= n * p[k + 1];
+    out -= s * p[k - 1];
+    return out;
+  }
   if (i == 0 && j == 0) return pc;
   const PCoef c = nf_pcoef(g, d_u, d_v, i, j);
   double out = c.diag * pc;

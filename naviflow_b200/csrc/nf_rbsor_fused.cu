@@ -89,6 +89,26 @@ __device__ __forceinline__ CellCoef cell_coef(const nf_grid& g, int gi, int gj, 
 // The 2*NS colour passes.  S0 = parity of (global row + first column) of this thread's rows: it is the same for
 // all of a thread's row slots (rows differ by 16) and uniform in a warp, so the kernel branches once on it and
 // every "which cell of the pair is red" decision below folds at compile time.
+// aP of cell (gi,gj) as A*p uses it (matrix_free.py:63-84), from the raw d_u / d_v values
+__device__ __forceinline__ double cell_diag(const nf_grid& g, int gi, int gj, double du_c, double du_e, double dv_c,
+                                            double dv_n) {
+  double e = (gi < g.nx - 1) ? g.rho * du_e * g.dy : 0.0;
+  double w = (gi > 0) ? g.rho * du_c * g.dy : 0.0;
+  double n = (gj < g.ny - 1) ? g.rho * dv_n * g.dx : 0.0;
+  double s = (gj > 0) ? g.rho * dv_c * g.dx : 0.0;
+  double diag = 0.0;
+  if (gi == 0) diag += e;
+  if (gi == g.nx - 1) diag += w;
+  if (gj == 0) diag += n;
+  if (gj == g.ny - 1) diag += s;
+  if (gi == 0) e = 0.0;
+  if (gi == g.nx - 1) w = 0.0;
+  if (gj == 0) n = 0.0;
+  if (gj == g.ny - 1) s = 0.0;
+  diag += ((e + w) + n) + s;
+  return diag;
+}
+
 template <int NS, int S0>
 __device__ __forceinline__ void rbsor_passes(double (&sP)[2][RRW][33], int tx, int ty, double omega,
                                              double (&p0)[KS], double (&p1)[KS], const double (&b0)[KS],
@@ -285,18 +305,46 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
       "}\n" :: "r"(bar), "r"(parity) : "memory");
 }
 
-template <int NS, bool HAS_INV>
+// EXTRA work fused behind the last colour pass (the tile then keeps a slightly deeper halo):
+//   0  nothing
+//   1  residual norms: sum (b - A p)^2 and sum b^2 over the level (the multigrid convergence test after the
+//      post-smoothing, multigrid.py:185-240) -- saves a 40 B/cell pass
+//   2  residual + full-weighting restriction: coarse_b = FW(b - A p) (multigrid.py:362-372 after the
+//      pre-smoothing) -- saves a 34 B/cell pass
+struct TmaExtra {
+  nf_grid gc;               // coarse grid (mode 2)
+  double* coarse_b;         // mode 2
+  double* partials;         // mode 1: per-CTA partial sums, ticket, result (2 doubles)
+  unsigned int* ticket;
+  double* out;
+};
+
+template <int NS, int EXTRA>
+struct TileGeom {
+  static constexpr int HR = (EXTRA == 0) ? 2 * NS : 2 * NS + 1;   // rows of halo below the tile
+  static constexpr int HC = (EXTRA == 0) ? 2 * NS : 2 * NS + 2;   // columns of halo left of the tile (even)
+  static constexpr int TR = (EXTRA == 0) ? RRW - 4 * NS : (EXTRA == 1 ? RRW - 2 * HR : ((RRW - 2 - HR - 2 * NS) / 2) * 2);
+  static constexpr int TC = (EXTRA == 0) ? RCW - 4 * NS : (EXTRA == 1 ? RCW - 2 * HC : ((RCW - 2 - HC - 2 * NS) / 2) * 2);
+};
+
+constexpr int SM_SD = SM_BAR + 16;                      // sD[2][48][33]: aP of boundary tiles (EXTRA != 0)
+constexpr int SM_SR = SM_SD + 2 * RRW * 33 * 8;         // sR[48][65]: fine residual of the tile (EXTRA == 2)
+constexpr int SM_TOTAL_X1 = SM_SR;
+constexpr int SM_TOTAL_X2 = SM_SR + RRW * 65 * 8;
+
+template <int NS, bool HAS_INV, int EXTRA>
 __global__ void __launch_bounds__(32 * NYT, 1)
 k_rbsor_tma(nf_grid g, const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_b,
             const __grid_constant__ CUtensorMap map_du, const __grid_constant__ CUtensorMap map_dv,
             const __grid_constant__ CUtensorMap map_inv, double* __restrict__ pout, double omega, int tiles_x,
-            int n_tiles) {
+            int n_tiles, TmaExtra ex) {
   constexpr unsigned TX_BYTES = HAS_INV ? ST_END : ST_INV;
-  constexpr int H = 2 * NS;
-  constexpr int TR = RRW - 2 * H;
-  constexpr int TC = RCW - 2 * H;
+  using TG = TileGeom<NS, EXTRA>;
+  constexpr int HR = TG::HR, HC = TG::HC, TR = TG::TR, TC = TG::TC;
   extern __shared__ __align__(128) unsigned char smem[];
   double (&sP)[2][RRW][33] = *reinterpret_cast<double (*)[2][RRW][33]>(smem + SM_SP);
+  double (&sD)[2][RRW][33] = *reinterpret_cast<double (*)[2][RRW][33]>(smem + SM_SD);
+  double (&sR)[RRW][65] = *reinterpret_cast<double (*)[RRW][65]>(smem + SM_SR);
   const double* stP = reinterpret_cast<const double*>(smem + ST_P);
   const double* stB = reinterpret_cast<const double*>(smem + ST_B);
   const double* stDU = reinterpret_cast<const double*>(smem + ST_DU);
@@ -308,10 +356,11 @@ k_rbsor_tma(nf_grid g, const __grid_constant__ CUtensorMap map_p, const __grid_c
   const int tx = threadIdx.x, ty = threadIdx.y;
   const bool leader = (tx == 0 && ty == 0);
   const int c0 = 2 * tx;
+  double nrm[2] = {0.0, 0.0};  // EXTRA == 1: sum r^2, sum b^2 over this CTA's tiles
 
   auto issue = [&](int tile) {
     const int ti = tile / tiles_x, tj = tile - ti * tiles_x;
-    const int ri = g.gb + ti * TR - H, rj = tj * TC - H;
+    const int ri = g.gb + ti * TR - HR, rj = tj * TC - HC;
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(TX_BYTES) : "memory");
     tma_load_2d(st_base + ST_P, &map_p, rj, ri - g.row0, bar);
     tma_load_2d(st_base + ST_B, &map_b, rj, ri - g.row0, bar);
@@ -331,8 +380,8 @@ k_rbsor_tma(nf_grid g, const __grid_constant__ CUtensorMap map_p, const __grid_c
 
   for (; tile < n_tiles; tile += gridDim.x) {
     const int ti = tile / tiles_x, tj = tile - ti * tiles_x;
-    const int i0 = g.gb + ti * TR - H;
-    const int j0 = tj * TC - H;
+    const int i0 = g.gb + ti * TR - HR;
+    const int j0 = tj * TC - HC;
     const int gj0 = j0 + 2 * tx;
 
     double p0[KS], p1[KS], b0[KS], b1[KS], inv0[KS], inv1[KS];
@@ -367,35 +416,43 @@ k_rbsor_tma(nf_grid g, const __grid_constant__ CUtensorMap map_p, const __grid_c
       }
     } else {
 #pragma unroll
-    for (int k = 0; k < KS; ++k) {
-      const int r = ty + NYT * k;
-      const int gi = i0 + r;
-      const bool row_in = (gi >= 0 && gi < g.nx);
-      const bool in0 = row_in && gj0 >= 0 && gj0 < g.ny;
-      const bool in1 = row_in && gj0 + 1 >= 0 && gj0 + 1 < g.ny;
-      const double2 pp = *reinterpret_cast<const double2*>(stP + r * RCW + c0);
-      const double2 bb = *reinterpret_cast<const double2*>(stB + r * RCW + c0);
-      const double2 ua = *reinterpret_cast<const double2*>(stDU + r * RCW + c0);
-      const double2 ub = *reinterpret_cast<const double2*>(stDU + (r + 1) * RCW + c0);
-      const double2 vv = *reinterpret_cast<const double2*>(stDV + r * (RCW + 2) + c0);
-      const double w2 = stDV[r * (RCW + 2) + c0 + 2];
-      double2 iv = make_double2(1.0, 1.0);
-      if (HAS_INV) iv = *reinterpret_cast<const double2*>(stINV + r * RCW + c0);
-      const CellCoef ca = cell_coef<HAS_INV>(g, gi, gj0, in0, ua.x, ub.x, vv.x, vv.y, iv.x);
-      const CellCoef cb = cell_coef<HAS_INV>(g, gi, gj0 + 1, in1, ua.y, ub.y, vv.y, w2, iv.y);
-      aE0[k] = ca.e; aW0[k] = ca.w; aN0[k] = ca.n; aS0[k] = ca.s; inv0[k] = ca.inv;
-      aE1[k] = cb.e; aW1[k] = cb.w; aN1[k] = cb.n; aS1[k] = cb.s; inv1[k] = cb.inv;
-      double vp0 = pp.x;
-      if (gi == 0 && gj0 == 0) vp0 = 0.0;  // pinned cell
-      p0[k] = in0 ? vp0 : 0.0;
-      p1[k] = in1 ? pp.y : 0.0;
-      b0[k] = bb.x;
-      b1[k] = bb.y;
-      ok0[k] = in0 && !(gi == 0 && gj0 == 0) && r >= 1 && r <= RRW - 2 && c0 >= 1;
-      ok1[k] = in1 && r >= 1 && r <= RRW - 2 && (c0 + 1) <= RCW - 2;
-      sP[r & 1][r][tx] = p0[k];
-      sP[(r & 1) ^ 1][r][tx] = p1[k];
-    }
+      for (int k = 0; k < KS; ++k) {
+        const int r = ty + NYT * k;
+        const int gi = i0 + r;
+        const bool row_in = (gi >= 0 && gi < g.nx);
+        const bool in0 = row_in && gj0 >= 0 && gj0 < g.ny;
+        const bool in1 = row_in && gj0 + 1 >= 0 && gj0 + 1 < g.ny;
+        const double2 pp = *reinterpret_cast<const double2*>(stP + r * RCW + c0);
+        const double2 bb = *reinterpret_cast<const double2*>(stB + r * RCW + c0);
+        const double2 ua = *reinterpret_cast<const double2*>(stDU + r * RCW + c0);
+        const double2 ub = *reinterpret_cast<const double2*>(stDU + (r + 1) * RCW + c0);
+        const double2 vv = *reinterpret_cast<const double2*>(stDV + r * (RCW + 2) + c0);
+        const double w2 = stDV[r * (RCW + 2) + c0 + 2];
+        double2 iv = make_double2(1.0, 1.0);
+        if (HAS_INV) iv = *reinterpret_cast<const double2*>(stINV + r * RCW + c0);
+        CellCoef ca = cell_coef<HAS_INV>(g, gi, gj0, in0, ua.x, ub.x, vv.x, vv.y, iv.x);
+        const CellCoef cb = cell_coef<HAS_INV>(g, gi, gj0 + 1, in1, ua.y, ub.y, vv.y, w2, iv.y);
+        const bool pinned = (gi == 0 && gj0 == 0);
+        if (EXTRA != 0) {  // aP of boundary-tile cells for the residual (identity row at the pinned cell)
+          double d0 = in0 ? cell_diag(g, gi, gj0, ua.x, ub.x, vv.x, vv.y) : 1.0;
+          const double d1 = in1 ? cell_diag(g, gi, gj0 + 1, ua.y, ub.y, vv.y, w2) : 1.0;
+          if (pinned) { d0 = 1.0; ca.e = ca.w = ca.n = ca.s = 0.0; }
+          sD[r & 1][r][tx] = d0;
+          sD[(r & 1) ^ 1][r][tx] = d1;
+        }
+        aE0[k] = ca.e; aW0[k] = ca.w; aN0[k] = ca.n; aS0[k] = ca.s; inv0[k] = ca.inv;
+        aE1[k] = cb.e; aW1[k] = cb.w; aN1[k] = cb.n; aS1[k] = cb.s; inv1[k] = cb.inv;
+        double vp0 = pp.x;
+        if (pinned) vp0 = 0.0;
+        p0[k] = in0 ? vp0 : 0.0;
+        p1[k] = in1 ? pp.y : 0.0;
+        b0[k] = bb.x;
+        b1[k] = bb.y;
+        ok0[k] = in0 && !pinned && r >= 1 && r <= RRW - 2 && c0 >= 1;
+        ok1[k] = in1 && r >= 1 && r <= RRW - 2 && (c0 + 1) <= RCW - 2;
+        sP[r & 1][r][tx] = p0[k];
+        sP[(r & 1) ^ 1][r][tx] = p1[k];
+      }
     }
     __syncthreads();  // staging fully consumed, sP complete
     if (leader && tile + (int)gridDim.x < n_tiles) issue(tile + gridDim.x);
@@ -409,13 +466,76 @@ k_rbsor_tma(nf_grid g, const __grid_constant__ CUtensorMap map_p, const __grid_c
     for (int k = 0; k < KS; ++k) {
       const int r = ty + NYT * k;
       const int gi = i0 + r;
-      if (r < H || r >= H + TR || gi >= g.ge) continue;
-      if (c0 < H || c0 >= H + TC || gj0 >= g.ny) continue;
+      if (r < HR || r >= HR + TR || gi >= g.ge) continue;
+      if (c0 < HC || c0 >= HC + TC || gj0 >= g.ny) continue;
       const size_t kk = nf_idx(g, gi, gj0);
       if (gj0 + 1 < g.ny) *reinterpret_cast<double2*>(pout + kk) = make_double2(p0[k], p1[k]);
       else pout[kk] = p0[k];
     }
+
+    if (EXTRA != 0) {
+      // residual b - A p of this thread's cells from registers + the final sP (all neighbours of the cells used
+      // below are exact: they lie at least 2*NS cells inside the region)
+      const int par = ty & 1;
+      constexpr int RHI = (EXTRA == 2) ? 1 : 0;  // mode 2 also needs the ring row / column above the tile
+#pragma unroll
+      for (int k = 0; k < KS; ++k) {
+        const int r = ty + NYT * k;
+        const int gi = i0 + r;
+        const bool rin = r >= HR && r < HR + TR + RHI && gi < (EXTRA == 2 ? g.nx : g.ge);
+        double res0 = 0.0, res1 = 0.0;
+        if (rin) {
+          const int rmk = r - 1, rpk = r + 1;  // HR >= 1 and r <= RRW-2 here
+          {  // cell 0 (column 2tx): N neighbour is the partner, S neighbour belongs to pair tx-1
+            const int lp = par;
+            const double pc = p0[k];
+            const double d = interior ? ((aE0[k] + aW0[k]) + aN0[k]) + aS0[k] : sD[lp][r][tx];
+            double o = d * pc;
+            o -= aE0[k] * sP[lp ^ 1][rpk][tx];
+            o -= aW0[k] * sP[lp ^ 1][rmk][tx];
+            o -= aN0[k] * p1[k];
+            o -= aS0[k] * sP[lp ^ 1][r][tx > 0 ? tx - 1 : 0];
+            res0 = b0[k] - o;
+          }
+          {  // cell 1 (column 2tx+1)
+            const int lp = par ^ 1;
+            const double pc = p1[k];
+            const double d = interior ? ((aE1[k] + aW1[k]) + aN1[k]) + aS1[k] : sD[lp][r][tx];
+            double o = d * pc;
+            o -= aE1[k] * sP[lp ^ 1][rpk][tx];
+            o -= aW1[k] * sP[lp ^ 1][rmk][tx];
+            o -= aN1[k] * sP[lp ^ 1][r][tx + 1];
+            o -= aS1[k] * p0[k];
+            res1 = b1[k] - o;
+          }
+        }
+        const bool cin0 = c0 >= HC && c0 < HC + TC + RHI && gj0 < g.ny;
+        const bool cin1 = c0 + 1 >= HC && c0 + 1 < HC + TC + RHI && gj0 + 1 < g.ny;
+        if (EXTRA == 1) {
+          if (rin && cin0) { nrm[0] += res0 * res0; nrm[1] += b0[k] * b0[k]; }
+          if (rin && cin1) { nrm[0] += res1 * res1; nrm[1] += b1[k] * b1[k]; }
+        } else {
+          sR[r][c0] = (rin && cin0) ? res0 : 0.0;
+          sR[r][c0 + 1] = (rin && cin1) ? res1 : 0.0;
+        }
+      }
+      if (EXTRA == 2) {
+        __syncthreads();
+        const int it = g.gb + ti * TR, jt = tj * TC;  // tile origin (even)
+        for (int t = ty * 32 + tx; t < (TR / 2) * (TC / 2); t += 32 * NYT) {
+          const int ci = t / (TC / 2), cj = t - ci * (TC / 2);
+          const int I = it / 2 + ci, J = jt / 2 + cj;
+          if (I < ex.gc.gb || I >= ex.gc.ge || J >= ex.gc.ny) continue;
+          const int a = 2 * I - i0, q = 2 * J - j0;  // region coordinates of fine (2I, 2J)
+          const double cc = sR[a + 1][q + 1], n = sR[a + 1][q + 2], s = sR[a + 1][q], e = sR[a + 2][q + 1], w = sR[a][q + 1];
+          const double ne = sR[a + 2][q + 2], nw = sR[a][q + 2], se = sR[a + 2][q], sw = sR[a][q];
+          ex.coarse_b[nf_idx(ex.gc, I, J)] = (cc / 4.0 + (((n + s) + e) + w) / 8.0) + (((ne + nw) + se) + sw) / 16.0;
+        }
+        // the next tile's load phase writes sP / sD only; sR is rewritten after its passes (barriers in between)
+      }
+    }
   }
+  if (EXTRA == 1) nf_block_reduce_store<2>(nrm, ex.partials, ex.ticket, ex.out);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -450,15 +570,15 @@ bool make_map(CUtensorMap* map, const double* base, int rows, int cols, int ld, 
   return r == CUDA_SUCCESS;
 }
 
-template <int NS, bool HAS_INV>
+template <int NS, bool HAS_INV, int EXTRA>
 int launch_tma(nf_ctx* ctx, const nf_grid* g, const double* pin, double* pout, const double* b, const double* d_u,
-               const double* d_v, const double* inv, double omega, bool* used) {
-  constexpr int H = 2 * NS;
-  constexpr int TR = RRW - 2 * H, TC = RCW - 2 * H;
+               const double* d_v, const double* inv, double omega, const TmaExtra& ex, bool* used) {
+  using TG = TileGeom<NS, EXTRA>;
+  constexpr int TR = TG::TR, TC = TG::TC;
+  constexpr int SMEM = EXTRA == 0 ? SM_TOTAL : (EXTRA == 1 ? SM_TOTAL_X1 : SM_TOTAL_X2);
   *used = false;
   const int tiles_x = (g->ny + TC - 1) / TC, tiles_y = (g->ge - g->gb + TR - 1) / TR;
   const int n_tiles = tiles_x * tiles_y;
-  // stored rows of this (slab of the) grid: the maps cover rows [row0, ...) of the arrays as stored
   // rows the arrays hold (slab runs store [row0, row1); row1 == 0 means the whole grid)
   const int row_end = g->row1 > 0 ? g->row1 : g->nx + 1;
   const int stored_p = (row_end < g->nx ? row_end : g->nx) - g->row0;  // p-like arrays
@@ -469,15 +589,15 @@ int launch_tma(nf_ctx* ctx, const nf_grid* g, const double* pin, double* pout, c
       !make_map(&mv, d_v, stored_p, g->ny + 1, g->ld, RRW, RCW + 2) ||
       !make_map(&mi, HAS_INV ? inv : b, stored_p, g->ny, g->ld, RRW, RCW))
     return NF_OK;  // caller falls back to the plain fused kernel
-  static bool attr_set[4] = {false, false, false, false};
-  if (!attr_set[NS]) {
-    NF_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_rbsor_tma<NS, HAS_INV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            SM_TOTAL));
-    attr_set[NS] = true;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NF_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_rbsor_tma<NS, HAS_INV, EXTRA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            SMEM));
+    attr_set = true;
   }
   const int grid = n_tiles < NF_SM_COUNT ? n_tiles : NF_SM_COUNT;
-  k_rbsor_tma<NS, HAS_INV><<<grid, dim3(32, NYT, 1), SM_TOTAL, ctx->stream>>>(*g, mp, mb, mu, mv, mi, pout, omega,
-                                                                              tiles_x, n_tiles);
+  k_rbsor_tma<NS, HAS_INV, EXTRA><<<grid, dim3(32, NYT, 1), SMEM, ctx->stream>>>(*g, mp, mb, mu, mv, mi, pout, omega,
+                                                                                 tiles_x, n_tiles, ex);
   NF_LAUNCH_CHECK(ctx);
   *used = true;
   return NF_OK;
@@ -489,32 +609,61 @@ int launch_tma(nf_ctx* ctx, const nf_grid* g, const double* pin, double* pout, c
 // return *p points at the buffer holding the result (the two pointers are swapped once per launch).
 template <int NS>
 int launch_tma_any(nf_ctx* ctx, const nf_grid* g, const double* pin, double* pout, const double* b, const double* d_u,
-                   const double* d_v, const double* inv, double omega, bool* used) {
-  if (inv) return launch_tma<NS, true>(ctx, g, pin, pout, b, d_u, d_v, inv, omega, used);
-  return launch_tma<NS, false>(ctx, g, pin, pout, b, d_u, d_v, nullptr, omega, used);
+                   const double* d_v, const double* inv, double omega, int extra, const TmaExtra& ex, bool* used) {
+  if (inv && extra == 1) return launch_tma<NS, true, 1>(ctx, g, pin, pout, b, d_u, d_v, inv, omega, ex, used);
+  if (inv && extra == 2) return launch_tma<NS, true, 2>(ctx, g, pin, pout, b, d_u, d_v, inv, omega, ex, used);
+  if (inv) return launch_tma<NS, true, 0>(ctx, g, pin, pout, b, d_u, d_v, inv, omega, ex, used);
+  return launch_tma<NS, false, 0>(ctx, g, pin, pout, b, d_u, d_v, nullptr, omega, ex, used);
 }
 
+// Work fused behind the last launch of a smoothing call (persistent TMA kernel only; see TmaExtra):
+//   mode 1: sum (b - A p)^2 -> out[0], sum b^2 -> out[1];  mode 2: coarse_b = FW(b - A p) on the coarse grid gc.
+// *fused tells the caller whether the extra work was done (otherwise it runs the stand-alone kernels).
+struct nf_smooth_extra {
+  int mode = 0;
+  nf_grid gc;
+  double* coarse_b = nullptr;
+  double* out = nullptr;
+  bool fused = false;
+};
+
 // inv (optional): precomputed 1/aP of this level (nfi_inv_diag); NULL = divide inside the kernel
-int nfi_rbsor_fused(nf_ctx* ctx, const nf_grid* g, double** p, double** palt, const double* b, const double* d_u,
-                    const double* d_v, const double* inv, double omega, int n_sweeps) {
+int nfi_rbsor_fused_x(nf_ctx* ctx, const nf_grid* g, double** p, double** palt, const double* b, const double* d_u,
+                      const double* d_v, const double* inv, double omega, int n_sweeps, nf_smooth_extra* extra) {
+  if (extra) extra->fused = false;
   if (n_sweeps == 0) {  // the reference still pins p[0,0] = 0 (gauss_seidel.py:145)
     if (g->row0 == 0 && g->gb == 0) NF_CHECK_CUDA(ctx, cudaMemsetAsync(*p, 0, sizeof(double), ctx->stream));
     return NF_OK;
   }
-  // TMA path: single-GPU layout (row0 == 0), 16-byte aligned arrays, pitch a multiple of 2 doubles
+  // TMA path: 16-byte aligned arrays, pitch a multiple of 2 doubles, enough rows for a persistent pipeline
   const char* env = getenv("NF_RBSOR_TMA");
   const int tma_min_rows = env ? atoi(env) : 600;  // NF_RBSOR_TMA=0 forces TMA everywhere, a huge value disables it
   const bool use_tma = g->nx >= tma_min_rows && (g->ge - g->gb) >= 64;
+  const char* envx = getenv("NF_RBSOR_EXTRA");
+  const bool allow_extra = !(envx && envx[0] == '0');
   int left = n_sweeps;
   while (left > 0) {
     const int ns = left >= 3 ? 3 : left;
     int st = NF_OK;
     bool used = false;
+    TmaExtra ex;
+    ex.coarse_b = nullptr; ex.partials = ctx->partials; ex.ticket = ctx->ticket; ex.out = nullptr;
+    ex.gc = *g;
+    int mode = 0;
+    // extra work rides on the last launch; it needs the precomputed 1/aP, an unsplit grid and even tile origins
+    if (extra && extra->mode != 0 && allow_extra && left == ns && use_tma && inv && g->row0 == 0 && g->gb == 0 &&
+        g->ge == g->nx) {
+      mode = extra->mode;
+      ex.gc = extra->gc;
+      ex.coarse_b = extra->coarse_b;
+      ex.out = extra->out;
+    }
     if (use_tma) {  // persistent TMA pipeline: pays off once every SM gets several tiles
-      if (ns == 3) st = launch_tma_any<3>(ctx, g, *p, *palt, b, d_u, d_v, inv, omega, &used);
-      else if (ns == 2) st = launch_tma_any<2>(ctx, g, *p, *palt, b, d_u, d_v, inv, omega, &used);
-      else st = launch_tma_any<1>(ctx, g, *p, *palt, b, d_u, d_v, inv, omega, &used);
+      if (ns == 3) st = launch_tma_any<3>(ctx, g, *p, *palt, b, d_u, d_v, inv, omega, mode, ex, &used);
+      else if (ns == 2) st = launch_tma_any<2>(ctx, g, *p, *palt, b, d_u, d_v, inv, omega, mode, ex, &used);
+      else st = launch_tma_any<1>(ctx, g, *p, *palt, b, d_u, d_v, inv, omega, mode, ex, &used);
       if (st != NF_OK) return st;
+      if (used && mode != 0) extra->fused = true;
     }
     if (!used) {
       if (ns == 3) st = launch_fused<3>(ctx, g, *p, *palt, b, d_u, d_v, inv, omega);
@@ -526,6 +675,11 @@ int nfi_rbsor_fused(nf_ctx* ctx, const nf_grid* g, double** p, double** palt, co
     left -= ns;
   }
   return NF_OK;
+}
+
+int nfi_rbsor_fused(nf_ctx* ctx, const nf_grid* g, double** p, double** palt, const double* b, const double* d_u,
+                    const double* d_v, const double* inv, double omega, int n_sweeps) {
+  return nfi_rbsor_fused_x(ctx, g, p, palt, b, d_u, d_v, inv, omega, n_sweeps, nullptr);
 }
 
 // 1/aP of every cell (gauss_seidel.py:214-266: aP with the Neumann folding, < 1e-15 -> 1), once per level and

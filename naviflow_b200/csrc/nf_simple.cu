@@ -12,6 +12,7 @@
 // region that shrinks by one row, so after up to 6 sweeps the owned rows (+1) are exact.  Per outer iteration the
 // ranks exchange: the halo of b (once), the multigrid halos (nf_mg.cu), p, u, v (once each) and 6 scalars.
 #include <math.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -23,6 +24,8 @@ int nfi_momentum_links(nf_ctx*, const nf_grid*, int is_u, const double* u, const
                        double mu, double alpha, int sides, nf_links out, double* d);
 int nfi_momentum_sweep(nf_ctx*, const nf_grid*, int is_u, nf_links L, const double* src, double* dst);
 int nfi_momentum_residual_to(nf_ctx*, const nf_grid*, int is_u, nf_links L, const double* x, double* field, double* out);
+int nfi_momentum_sweeps_fused(nf_ctx*, const nf_grid*, int is_u, nf_links L, const double* xin, double* xout, int k,
+                              int with_res, int norm_b, int norm_e, double* field, double* out);
 int nfi_correct_velocity(nf_ctx*, const nf_grid*, const nf_bc_program*, const double* us, const double* vs,
                          const double* pp, const double* d_u, const double* d_v, double* u, double* v);
 int nfi_mg_create(nf_team* team, nf_mg** out, int nx, int ny, int ld, const nf_mg_config* cfg);
@@ -319,20 +322,43 @@ static int momentum_component(nf_simple* s, int is_u, int want_fields) {
       src[k] = a[k];
     }
   }
-  for (int sw = 0; sw < c.n_momentum_sweeps; ++sw) {
-    if (dist && margin <= 1) {  // out of halo: refresh it and start shrinking again
+  // Sweeps in chunks of up to 6 per tile load (nf_momentum_fused.cu); the last chunk also evaluates the residual
+  // norms.  On slabs each chunk consumes k (+1) rows of halo: the computed region shrinks instead of communicating.
+  const char* envf = getenv("NF_MOMENTUM_FUSED");
+  const bool fused = !(envf && envf[0] == '0');
+  bool res_done = false;
+  int left = c.n_momentum_sweeps;
+  while (left > 0) {
+    int k = fused ? (left > 6 ? 6 : left) : 1;
+    const bool last = (left == k);
+    const int need = k + ((fused && last) ? 1 : 0);  // halo rows this chunk consumes
+    if (dist && margin - need < 1) {  // out of halo: refresh it and start shrinking again
       std::vector<double*> f(nl);
-      for (int k = 0; k < nl; ++k) f[k] = const_cast<double*>(src[k]);
+      for (int kk = 0; kk < nl; ++kk) f[kk] = const_cast<double*>(src[kk]);
       NF_TRY(nf_team_exchange(team, s->geom, f.data(), NF_HALO));
       margin = NF_HALO;
+      if (margin - need < 1) k = 1;  // cannot happen with NF_HALO = 8 and k <= 6, kept for safety
     }
-    margin -= 1;
-    for (int k = 0; k < nl; ++k) {
-      const nf_grid g = s->geom.grid_ext(team->local[k], margin);
-      double* dst = (src[k] == a[k]) ? b[k] : a[k];
-      NF_TRY(nfi_momentum_sweep(ctx, &g, is_u, s->s[k].links, src[k], dst));
-      src[k] = dst;
+    const int out_margin = dist ? (last && fused ? 1 : margin - k) : 0;
+    for (int kk = 0; kk < nl; ++kk) {
+      SimpleSlab& S = s->s[kk];
+      const int r = team->local[kk];
+      const nf_grid g = s->geom.grid_ext(r, out_margin);
+      const nf_grid gown = s->geom.grid(r);
+      double* dst = (src[kk] == a[kk]) ? b[kk] : a[kk];
+      if (fused) {
+        const int nb = gown.gb, ne = (is_u && gown.ge == gown.nx) ? gown.nx + 1 : gown.ge;
+        NF_TRY(nfi_momentum_sweeps_fused(ctx, &g, is_u, S.links, src[kk], dst, k, last ? 1 : 0, nb, ne,
+                                         (last && want_fields) ? (is_u ? S.ures : S.vres) : nullptr,
+                                         S.scal + (is_u ? 2 : 4)));
+      } else {
+        NF_TRY(nfi_momentum_sweep(ctx, &g, is_u, S.links, src[kk], dst));
+      }
+      src[kk] = dst;
     }
+    margin = out_margin;
+    if (fused && last) res_done = true;
+    left -= k;
   }
   for (int k = 0; k < nl; ++k) {
     SimpleSlab& S = s->s[k];
@@ -343,12 +369,13 @@ static int momentum_component(nf_simple* s, int is_u, int want_fields) {
     for (int k = 0; k < nl; ++k) f[k] = const_cast<double*>(src[k]);
     NF_TRY(nf_team_exchange(team, s->geom, f.data(), 1));
   }
-  for (int k = 0; k < nl; ++k) {
-    SimpleSlab& S = s->s[k];
-    const nf_grid g = s->geom.grid(team->local[k]);
-    NF_TRY(nfi_momentum_residual_to(ctx, &g, is_u, S.links, src[k], want_fields ? (is_u ? S.ures : S.vres) : nullptr,
-                                    S.scal + (is_u ? 2 : 4)));
-  }
+  if (!res_done)
+    for (int k = 0; k < nl; ++k) {
+      SimpleSlab& S = s->s[k];
+      const nf_grid g = s->geom.grid(team->local[k]);
+      NF_TRY(nfi_momentum_residual_to(ctx, &g, is_u, S.links, src[k], want_fields ? (is_u ? S.ures : S.vres) : nullptr,
+                                      S.scal + (is_u ? 2 : 4)));
+    }
   return NF_OK;
 }
 

@@ -248,3 +248,33 @@ def test_fused_rbsor_tma_large_grid_matches_unfused():
         d.call("nf_rbsor_sweeps_fused", d.gref(), ptr(p), ptr(tmp), ptr(b), ptr(du), ptr(dv), ptr(inv), 1.5, sweeps)
         d.call("nf_rbsor_sweeps", d.gref(), ptr(p2), ptr(b), ptr(du), ptr(dv), 1.5, sweeps)
         np.testing.assert_array_equal(d.down(p), d.down(p2))
+
+
+@pytest.mark.parametrize("n", [9, 31, 40, 64, 65, 130, 257])
+def test_fused_momentum_sweeps_are_bit_identical(n):
+    """Temporally blocked Jacobi momentum sweeps + fused residual against the sweep-by-sweep kernels."""
+    from gpu_util import Dev, NfLinks, bc_program_struct, ptr
+    from naviflow_b200.host import practice_b_sides
+    s = synth(n, 3000 + n)
+    bc = cavity_bc()
+    d = Dev(n)
+    prog = bc_program_struct(bc, n, n)
+    u, v, p = d.up(s["u"]), d.up(s["v"]), d.up(s["p"])
+    d.call("nf_apply_velocity_bc", d.gref(), C.byref(prog), ptr(u), ptr(v))
+    for is_u, shape in ((1, (n + 1, n)), (0, (n, n + 1))):
+        arrs = [d.zeros() for _ in range(6)]
+        links = NfLinks(*[a.data_ptr() for a in arrs])
+        dd = d.zeros()
+        fn = "nf_momentum_links_u" if is_u else "nf_momentum_links_v"
+        d.call(fn, d.gref(), ptr(u), ptr(v), ptr(p), MU, 0.7, practice_b_sides(bc), links, ptr(dd))
+        x0 = s["u"] if is_u else s["v"]
+        for sweeps in (1, 2, 5, 6, 7, 13):
+            xa, ta, fa = d.up(x0), d.zeros(), d.zeros()
+            xb, tb, fb = d.up(x0), d.zeros(), d.zeros()
+            na, nbv = C.c_double(), C.c_double()
+            d.call("nf_momentum_jacobi", d.gref(), is_u, links, ptr(xa), ptr(ta), sweeps)
+            d.call("nf_momentum_residual", d.gref(), is_u, links, ptr(xa), ptr(fa), C.byref(na))
+            d.call("nf_momentum_jacobi_fused", d.gref(), is_u, links, ptr(xb), ptr(tb), sweeps, ptr(fb), C.byref(nbv))
+            np.testing.assert_array_equal(d.down(xb, *shape), d.down(xa, *shape), err_msg=f"n={n} u={is_u} k={sweeps}")
+            np.testing.assert_array_equal(d.down(fb, *shape), d.down(fa, *shape))
+            assert abs(na.value - nbv.value) <= 1e-12 * abs(na.value)

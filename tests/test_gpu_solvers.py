@@ -291,3 +291,32 @@ def test_slab_decomposition_tolerance_driven_cycles_match():
     assert out[0][2] == out[1][2]
     np.testing.assert_array_equal(out[0][0], out[1][0])
     np.testing.assert_array_equal(out[0][1], out[1][1])
+
+
+@pytest.mark.parametrize("n,pre,post", [(127, 3, 3), (200, 2, 3), (257, 3, 1), (130, 1, 2), (513, 3, 3)])
+def test_smoother_fused_residual_paths_match_standalone_kernels(n, pre, post, monkeypatch):
+    """The persistent TMA smoother can carry the residual+restriction (pre-smoothing) and the residual norms
+    (post-smoothing) behind its last colour pass.  Same iterates bit for bit as the stand-alone kernels, same cycle
+    count; checked against the oracle as well."""
+    import naviflow_b200 as nb
+    from oracle.make_golden import synth_pressure_inputs
+    s = synth_pressure_inputs(n, 4000 + n)
+    mesh, _ = cavity(n, 1000)
+    monkeypatch.setenv("NF_RBSOR_TMA", "0")        # force the TMA pipeline at every level with >= 64 rows
+    outs = []
+    for extra in ("1", "0"):
+        monkeypatch.setenv("NF_RBSOR_EXTRA", extra)
+        ps = nb.GpuMultiGridSolver(smoother=nb.GpuGaussSeidelSolver(omega=1.5), max_iterations=100, tolerance=1e-4,
+                                   pre_smoothing=pre, post_smoothing=post)
+        p, info = ps.solve(mesh, s["u_star"], s["v_star"], s["d_u"], s["d_v"], None)
+        outs.append((p, info, ps.last_info.cycles))
+    np.testing.assert_array_equal(outs[0][0], outs[1][0])
+    assert outs[0][2] == outs[1][2]
+    assert abs(outs[0][1]["rel_norm"] - outs[1][1]["rel_norm"]) <= 1e-10 * outs[1][1]["rel_norm"]
+    np.testing.assert_allclose(outs[0][1]["field"], outs[1][1]["field"], rtol=0, atol=1e-18 + 1e-12 * np.abs(outs[1][1]["field"]).max())
+    if n <= 200:
+        dx = dy = 1.0 / (n - 1)
+        cfg = O.MGConfig(omega=1.5, pre=pre, post=post, tolerance=1e-4, max_iterations=100)
+        x_ref, iref = O.mg_solve(cfg, n, n, dx, dy, s["u_star"], s["v_star"], s["d_u"], s["d_v"])
+        assert iref["cycles"] == outs[0][2]
+        assert rel(outs[0][0], x_ref) < 1e-11
