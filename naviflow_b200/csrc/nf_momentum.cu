@@ -85,9 +85,19 @@ __device__ __forceinline__ double nf_pow5(double x) {
   return h5 + l5;
 }
 
-__device__ __forceinline__ double nf_powerlaw(double F, double D) {
+// a / b for a divisor that is constant in the kernel, with rb = RN(1/b) computed once: q = RN(a*rb),
+// r = a - q*b (exact, FMA), result RN(q + r*rb).  By Markstein's theorem this is the correctly rounded quotient
+// (the same bits as a / b) for every a when rb is the correctly rounded reciprocal -- 3 fp64 operations instead
+// of the ~30-instruction division sequence.
+__device__ __forceinline__ double nf_div_const(double a, double b, double rb) {
+  const double q = a * rb;
+  const double r = __fma_rn(-q, b, a);
+  return __fma_rn(r, rb, q);
+}
+
+__device__ __forceinline__ double nf_powerlaw(double F, double D, double rD) {
   if (!(fabs(D) > 1e-10)) return 0.0;
-  const double pe = 0.1 * fabs(F / D);
+  const double pe = 0.1 * fabs(nf_div_const(F, D, rD));
   const double base = fmax(0.0, 1.0 - pe);
   const double r = nf_pow5(base);
   return isnan(r) ? 0.0 : r;
@@ -104,28 +114,29 @@ __device__ __forceinline__ LinkVals nf_links_u_cell(const nf_grid& g, const doub
   LinkVals L;
   const double dx = g.dx, dy = g.dy, rho = g.rho;
   const double De = mu * dy / dx, Dn = mu * dx / dy;
+  const double rDe = 1.0 / De, rDn = 1.0 / Dn;
   const size_t k = nf_idx(g, i, j);
   const size_t ld = g.ld;
   const double uc = u[k];
   const double Fe = 0.5 * rho * dy * (u[k + ld] + uc);
   const double Fw = 0.5 * rho * dy * (u[k - ld] + uc);
-  L.ae = De * nf_powerlaw(Fe, De) + fmax(-Fe, 0.0);
-  L.aw = De * nf_powerlaw(Fw, De) + fmax(Fw, 0.0);
+  L.ae = De * nf_powerlaw(Fe, De, rDe) + fmax(-Fe, 0.0);
+  L.aw = De * nf_powerlaw(Fw, De, rDe) + fmax(Fw, 0.0);
   if (j == 0) {  // bottom row (:112-125)
     const double Fn = 0.5 * rho * dx * (v[k + 1] + v[k - ld + 1]);
-    L.an = Dn * nf_powerlaw(Fn, Dn) + fmax(-Fn, 0.0);
+    L.an = Dn * nf_powerlaw(Fn, Dn, rDn) + fmax(-Fn, 0.0);
     L.as = 0.0;
     L.ap = (((L.ae + L.aw) + L.an) + (Fe - Fw)) + Fn;
   } else if (j == g.ny - 1) {  // top row (:127-140)
     const double Fs = 0.5 * rho * dx * (v[k] + v[k - ld]);
     L.an = 0.0;
-    L.as = Dn * nf_powerlaw(Fs, Dn) + fmax(Fs, 0.0);
+    L.as = Dn * nf_powerlaw(Fs, Dn, rDn) + fmax(Fs, 0.0);
     L.ap = (((L.ae + L.aw) + L.as) + (Fe - Fw)) - Fs;
   } else {  // interior (:89-110)
     const double Fn = 0.5 * rho * dx * (v[k + 1] + v[k - ld + 1]);
     const double Fs = 0.5 * rho * dx * (v[k] + v[k - ld]);
-    L.an = Dn * nf_powerlaw(Fn, Dn) + fmax(-Fn, 0.0);
-    L.as = Dn * nf_powerlaw(Fs, Dn) + fmax(Fs, 0.0);
+    L.an = Dn * nf_powerlaw(Fn, Dn, rDn) + fmax(-Fn, 0.0);
+    L.as = Dn * nf_powerlaw(Fs, Dn, rDn) + fmax(Fs, 0.0);
     L.ap = ((((L.ae + L.aw) + L.an) + L.as) + (Fe - Fw)) + (Fn - Fs);
   }
   L.src = (p[k - ld] - p[k]) * dy;
@@ -144,6 +155,7 @@ __device__ __forceinline__ LinkVals nf_links_v_cell(const nf_grid& g, const doub
   LinkVals L;
   const double dx = g.dx, dy = g.dy, rho = g.rho;
   const double De = mu * dy / dx, Dn = mu * dx / dy;
+  const double rDe = 1.0 / De, rDn = 1.0 / Dn;
   const size_t k = nf_idx(g, i, j);
   const size_t ld = g.ld;
   const double vc = v[k];
@@ -155,23 +167,23 @@ __device__ __forceinline__ LinkVals nf_links_v_cell(const nf_grid& g, const doub
     Fn = 0.5 * rho * dx * (vc + v[k + 1]);
     Fs = 0.5 * rho * dx * (v[k - 1] + vc);
   }
-  L.an = Dn * nf_powerlaw(Fn, Dn) + fmax(-Fn, 0.0);
-  L.as = Dn * nf_powerlaw(Fs, Dn) + fmax(Fs, 0.0);
+  L.an = Dn * nf_powerlaw(Fn, Dn, rDn) + fmax(-Fn, 0.0);
+  L.as = Dn * nf_powerlaw(Fs, Dn, rDn) + fmax(Fs, 0.0);
   if (i == 0) {
     const double Fe = 0.5 * rho * dy * (u[k + ld] + u[k + ld - 1]);
-    L.ae = De * nf_powerlaw(Fe, De) + fmax(-Fe, 0.0);
+    L.ae = De * nf_powerlaw(Fe, De, rDe) + fmax(-Fe, 0.0);
     L.aw = 0.0;
     L.ap = (((L.ae + L.an) + L.as) + Fe) + (Fn - Fs);
   } else if (i == g.nx - 1) {
     const double Fw = 0.5 * rho * dy * (u[k] + u[k - 1]);
     L.ae = 0.0;
-    L.aw = De * nf_powerlaw(Fw, De) + fmax(Fw, 0.0);
+    L.aw = De * nf_powerlaw(Fw, De, rDe) + fmax(Fw, 0.0);
     L.ap = (((L.aw + L.an) + L.as) - Fw) + (Fn - Fs);
   } else {
     const double Fe = 0.5 * rho * dy * (u[k + ld] + u[k + ld - 1]);
     const double Fw = 0.5 * rho * dy * (u[k] + u[k - 1]);
-    L.ae = De * nf_powerlaw(Fe, De) + fmax(-Fe, 0.0);
-    L.aw = De * nf_powerlaw(Fw, De) + fmax(Fw, 0.0);
+    L.ae = De * nf_powerlaw(Fe, De, rDe) + fmax(-Fe, 0.0);
+    L.aw = De * nf_powerlaw(Fw, De, rDe) + fmax(Fw, 0.0);
     L.ap = ((((L.ae + L.aw) + L.an) + L.as) + (Fe - Fw)) + (Fn - Fs);
   }
   L.src = (p[k - 1] - p[k]) * dx;
@@ -199,8 +211,9 @@ __global__ void k_momentum_links(nf_grid g, const double* __restrict__ u, const 
   const size_t k = nf_idx(g, i, j);
   const double phi = IS_U ? u[k] : v[k];
   // under-relaxation (jacobi_matrix_solver.py:186-187)
-  const double ap_rel = L.ap / alpha;
-  const double src_rel = L.src + (1.0 - alpha) * L.ap / alpha * phi;
+  const double ralpha = 1.0 / alpha;
+  const double ap_rel = nf_div_const(L.ap, alpha, ralpha);
+  const double src_rel = L.src + nf_div_const((1.0 - alpha) * L.ap, alpha, ralpha) * phi;
   out.a_e[k] = L.ae;
   out.a_w[k] = L.aw;
   out.a_n[k] = L.an;
