@@ -270,6 +270,13 @@ int nf_simple_download(nf_simple*, int which, double* host, int rows, int cols);
 int nf_simple_iterate(nf_simple*, int n_iterations, double tolerance, int want_fields, nf_simple_info* info_host,
                       int* n_done);
 
+/* BiCGSTAB with the multigrid preconditioner of matrix_free_BiCGSTAB.py:102-161: M z = mg_cycles cycles (mg_kind
+ * 0 'v', 1 'w', 2 'fmg') on A y = z from y = 0.  `mg` must have been set up (nf_mg_setup) with the same d_u, d_v;
+ * work: 7 same-shape scratch arrays. */
+int nf_bicgstab_solve_mg(nf_ctx*, const nf_grid*, const double* b, double* x, const double* d_u, const double* d_v,
+                         double atol, double rtol, int maxiter, int check_every, double* work, nf_mg* mg, int mg_cycles,
+                         int mg_kind, nf_krylov_info* info_host);
+
 #ifdef __cplusplus
 }
 #endif

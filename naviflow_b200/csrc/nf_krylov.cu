@@ -199,16 +199,16 @@ __global__ void k_bi_s(nf_grid g, double* __restrict__ r, const double* __restri
 }
 
 // t = A s; ts = t.s, tt = t.t ; epilogue omega = ts/tt
-__global__ void k_bi_t(nf_grid g, const double* __restrict__ s, double* __restrict__ t, const double* __restrict__ d_u,
-                       const double* __restrict__ d_v, KState* st, double* partials, unsigned int* ticket,
-                       double* out) {
+__global__ void k_bi_t(nf_grid g, const double* shat, const double* s, double* __restrict__ t,
+                       const double* __restrict__ d_u, const double* __restrict__ d_v, KState* st, double* partials,
+                       unsigned int* ticket, double* out) {
   if (st->done || st->half) return;
   double acc[2] = {0.0, 0.0};
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j < g.ny) {
     NF_ROWLOOP(g, i) {
       const size_t k = nf_idx(g, i, j);
-      const double tc = nf_Ap_cell(g, s, d_u, d_v, i, j);
+      const double tc = nf_Ap_cell(g, shat, d_u, d_v, i, j);
       t[k] = tc;
       acc[0] += tc * s[k];
       acc[1] += tc * tc;
@@ -219,9 +219,10 @@ __global__ void k_bi_t(nf_grid g, const double* __restrict__ s, double* __restri
 
 // x += alpha p; x += omega s; r = s - omega t; rr = r.r; rho' = rtilde.r ; epilogue: top-of-loop tests of the
 // next iteration (norm, rho breakdown, omega breakdown) and beta.  Half-step exit: x += alpha p only.
+// phat / shat: the preconditioned directions (== p / s without a preconditioner)
 __global__ void k_bi_x(nf_grid g, double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p,
-                       const double* __restrict__ t, const double* __restrict__ rt, KState* st, int it,
-                       double* partials, unsigned int* ticket, double* out) {
+                       const double* __restrict__ shat, const double* __restrict__ t, const double* __restrict__ rt,
+                       KState* st, int it, double* partials, unsigned int* ticket, double* out) {
   if (st->done) return;
   const double alpha = st->alpha, omega = st->omega;
   const int half = st->half;
@@ -234,7 +235,8 @@ __global__ void k_bi_x(nf_grid g, double* __restrict__ x, double* __restrict__ r
         x[k] = x[k] + alpha * p[k];
       } else {
         const double s = r[k];
-        x[k] = (x[k] + alpha * p[k]) + omega * s;
+        const double sh = shat ? shat[k] : s;  // shat == NULL: no preconditioner (shat = s, which lives in r)
+        x[k] = (x[k] + alpha * p[k]) + omega * sh;
         const double rn = s - omega * t[k];
         r[k] = rn;
         acc[0] += rn * rn;
@@ -323,15 +325,16 @@ extern "C" int nf_cg_solve(nf_ctx* ctx, const nf_grid* g, const double* b, doubl
   return NF_OK;
 }
 
-extern "C" int nf_bicgstab_solve(nf_ctx* ctx, const nf_grid* g, const double* b, double* x, const double* d_u,
-                                 const double* d_v, double atol, double rtol, int maxiter, int check_every,
-                                 double* work, nf_krylov_info* info) {
-  NF_GRID_OK(ctx, g);
-  NF_REQUIRE(ctx, b && x && d_u && d_v && work, "NULL argument");
-  NF_REQUIRE(ctx, maxiter >= 0, "maxiter < 0");
+int nfi_mg_apply(nf_mg* mg, const double* rhs, double* out, int cycles, int kind);
+
+static int bicgstab_impl(nf_ctx* ctx, const nf_grid* g, const double* b, double* x, const double* d_u, const double* d_v,
+                         double atol, double rtol, int maxiter, int check_every, double* work, nf_mg* mg, int mg_cycles,
+                         int mg_kind, nf_krylov_info* info) {
   if (check_every < 1) check_every = 1;
   const size_t n = (size_t)(g->nx + 1) * g->ld;
   double *r = work, *rt = work + n, *p = work + 2 * n, *v = work + 3 * n, *t = work + 4 * n;
+  double* phat = mg ? work + 5 * n : p;   // M p
+  double* shat = mg ? work + 6 * n : nullptr;   // M s (s itself lives in r)
   KState *st, *hst;
   krylov_state(ctx, &st, &hst);
   NfLaunch2D l = nf_launch_reduce(g->ge - g->gb, g->ny);
@@ -341,14 +344,18 @@ extern "C" int nf_bicgstab_solve(nf_ctx* ctx, const nf_grid* g, const double* b,
   for (int it = 0; it < maxiter; ++it) {
     k_bi_p<<<l.grid, l.block, 0, ctx->stream>>>(*g, r, p, v, st, it == 0);
     NF_LAUNCH_CHECK(ctx);
-    k_bi_v<<<l.grid, l.block, 0, ctx->stream>>>(*g, p, v, rt, d_u, d_v, st, it, ctx->partials, ctx->ticket,
+    if (mg) NF_TRY(nfi_mg_apply(mg, p, phat, mg_cycles, mg_kind));
+    k_bi_v<<<l.grid, l.block, 0, ctx->stream>>>(*g, phat, v, rt, d_u, d_v, st, it, ctx->partials, ctx->ticket,
                                                 ctx->scalars);
     NF_LAUNCH_CHECK(ctx);
     k_bi_s<<<l.grid, l.block, 0, ctx->stream>>>(*g, r, v, st, ctx->partials, ctx->ticket, ctx->scalars);
     NF_LAUNCH_CHECK(ctx);
-    k_bi_t<<<l.grid, l.block, 0, ctx->stream>>>(*g, r, t, d_u, d_v, st, ctx->partials, ctx->ticket, ctx->scalars);
+    if (mg) NF_TRY(nfi_mg_apply(mg, r, shat, mg_cycles, mg_kind));
+    k_bi_t<<<l.grid, l.block, 0, ctx->stream>>>(*g, shat ? shat : r, r, t, d_u, d_v, st, ctx->partials, ctx->ticket,
+                                                ctx->scalars);
     NF_LAUNCH_CHECK(ctx);
-    k_bi_x<<<l.grid, l.block, 0, ctx->stream>>>(*g, x, r, p, t, rt, st, it, ctx->partials, ctx->ticket, ctx->scalars);
+    k_bi_x<<<l.grid, l.block, 0, ctx->stream>>>(*g, x, r, phat, shat, t, rt, st, it, ctx->partials, ctx->ticket,
+                                                ctx->scalars);
     NF_LAUNCH_CHECK(ctx);
     if ((it + 1) % check_every == 0) {
       NF_TRY(krylov_poll(ctx, st, hst));
@@ -358,4 +365,25 @@ extern "C" int nf_bicgstab_solve(nf_ctx* ctx, const nf_grid* g, const double* b,
   NF_TRY(krylov_poll(ctx, st, hst));
   krylov_finish(hst, maxiter, info);
   return NF_OK;
+}
+
+extern "C" int nf_bicgstab_solve(nf_ctx* ctx, const nf_grid* g, const double* b, double* x, const double* d_u,
+                                 const double* d_v, double atol, double rtol, int maxiter, int check_every,
+                                 double* work, nf_krylov_info* info) {
+  NF_GRID_OK(ctx, g);
+  NF_REQUIRE(ctx, b && x && d_u && d_v && work, "NULL argument");
+  NF_REQUIRE(ctx, maxiter >= 0, "maxiter < 0");
+  return bicgstab_impl(ctx, g, b, x, d_u, d_v, atol, rtol, maxiter, check_every, work, nullptr, 0, 0, info);
+}
+
+// BiCGSTAB with the multigrid preconditioner of matrix_free_BiCGSTAB.py:102-161: M z = mg_cycles cycles
+// (mg_kind 0 'v', 1 'w', 2 'fmg') on A y = z from y = 0.  `mg` must have been set up (nf_mg_setup) with the same
+// d_u, d_v; work holds 7 same-shape arrays.
+extern "C" int nf_bicgstab_solve_mg(nf_ctx* ctx, const nf_grid* g, const double* b, double* x, const double* d_u,
+                                    const double* d_v, double atol, double rtol, int maxiter, int check_every,
+                                    double* work, nf_mg* mg, int mg_cycles, int mg_kind, nf_krylov_info* info) {
+  NF_GRID_OK(ctx, g);
+  NF_REQUIRE(ctx, b && x && d_u && d_v && work && mg, "NULL argument");
+  NF_REQUIRE(ctx, maxiter >= 0 && mg_cycles >= 1 && mg_kind >= 0 && mg_kind <= 2, "bad iteration arguments");
+  return bicgstab_impl(ctx, g, b, x, d_u, d_v, atol, rtol, maxiter, check_every, work, mg, mg_cycles, mg_kind, info);
 }

@@ -895,6 +895,25 @@ int nfi_mg_solve(nf_mg* mg, double* const* b, double* const* x, double* const* r
 
 double* nfi_mg_scalars(nf_mg* mg, int k) { return mg->scal[k]; }
 
+// Multigrid as a preconditioner (matrix_free_BiCGSTAB.py:102-161): out = `cycles` cycles (kind 0 'v', 1 'w',
+// 2 'fmg') applied to A out = rhs starting from out = 0.  Single slab.
+int nfi_mg_apply(nf_mg* mg, const double* rhs, double* out, int cycles, int kind) {
+  nf_ctx* ctx = mg->ctx;
+  NF_REQUIRE(ctx, mg->setup_done, "nf_mg_setup has not been called");
+  NF_REQUIRE(ctx, nlocal(mg) == 1, "the multigrid preconditioner is a single-slab entry point");
+  MgLevel& L = mg->lv[0];
+  std::vector<double*> k2, kr;
+  double* bb = const_cast<double*>(rhs);
+  NF_TRY(mg_bind_level0(mg, &bb, &out, nullptr, k2, kr));
+  int st = nfi_fill(ctx, L.s[0].x, L.geom.elems(mg->team->local[0]), 0.0);
+  for (int c = 0; c < cycles && st == NF_OK; ++c) {
+    if (kind == 2) st = mg_fmg(mg, 0);
+    else st = mg_cycle(mg, 0, kind);
+  }
+  int st2 = mg_unbind_level0(mg, &out, k2, kr);
+  return st ? st : st2;
+}
+
 // collect the finished event pairs (call after a stream synchronisation)
 static void mg_harvest_timing(nf_mg* mg) {
   for (size_t e = 0; e + 1 < mg->ev_used; e += 2) {

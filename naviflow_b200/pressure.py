@@ -284,25 +284,54 @@ class _KrylovBase(_GpuPressureBase):
     _fn = None
     _nwork = 0
 
-    def __init__(self, tolerance=1e-7, max_iterations=1000, use_preconditioner=False, check_every=10, device=None):
+    def __init__(self, tolerance=1e-7, max_iterations=1000, use_preconditioner=False, preconditioner="jacobi",
+                 mg_pre_smoothing=2, mg_post_smoothing=2, mg_cycles=1, mg_cycle_type="v", mg_cycle_type_buildup="v",
+                 mg_max_cycles_buildup=1, mg_coarsest_grid_size=7, mg_restriction_method="restrict_full_weighting",
+                 mg_interpolation_method="interpolate_linear", smoother_relaxation=0.8,
+                 smoother_method_type="red_black", check_every=10, device=None):
+        """Constructor of MatrixFreeBiCGSTABSolver (matrix_free_BiCGSTAB.py:20-100)."""
         super().__init__(tolerance, max_iterations, device)
-        if use_preconditioner:
-            raise NotImplementedError("preconditioned Krylov solvers are a 'next' row (SURVEY.md section 8f, rank 2)")
-        self.use_preconditioner = False
+        self.use_preconditioner = bool(use_preconditioner)
+        self.preconditioner = preconditioner
         self.check_every = check_every
+        self.mg_cycles = mg_cycles
+        self.mg_cycle_type = "fmg" if mg_cycle_type in ("f", "fmg") else mg_cycle_type
+        self.mg_precond = None
+        if self.use_preconditioner:
+            if preconditioner != "multigrid":
+                # the reference's 'jacobi' path calls an undefined method (matrix_free_BiCGSTAB.py:229)
+                raise NotImplementedError("only preconditioner='multigrid' exists (the reference's 'jacobi' path is broken)")
+            if self._fn != "nf_bicgstab_solve":
+                raise NotImplementedError("the multigrid preconditioner is implemented for BiCGSTAB")
+            smoother = GpuGaussSeidelSolver(omega=smoother_relaxation, method_type=smoother_method_type)
+            self.omega = smoother.omega
+            self.mg_precond = GpuMultiGridSolver(
+                smoother=smoother, tolerance=tolerance, max_iterations=1, pre_smoothing=mg_pre_smoothing,
+                post_smoothing=mg_post_smoothing, cycle_type=self.mg_cycle_type, cycle_type_buildup=mg_cycle_type_buildup,
+                max_cycles_buildup=mg_max_cycles_buildup, coarsest_grid_size=mg_coarsest_grid_size,
+                restriction_method=mg_restriction_method, interpolation_method=mg_interpolation_method, device=device)
 
     def solve(self, mesh, u_star, v_star, d_u, d_v, p_star=None, return_dict=True):
-        nx, ny, dx, dy, _, _ = mesh_scalars(mesh)
+        nx, ny, dx, dy, length, height = mesh_scalars(mesh)
         ctx = self.ctx
         torch = ctx.torch
         g, bd, du, dv = self._stage(nx, ny, dx, dy, 1.0, u_star, v_star, d_u, d_v)
         x = ctx.empty(nx, ny)
-        work = torch.zeros((self._nwork * (nx + 1), pad_ld(ny)), dtype=torch.float64, device=x.device)
+        nwork = 7 if self.mg_precond is not None else self._nwork
+        work = torch.zeros((nwork * (nx + 1), pad_ld(ny)), dtype=torch.float64, device=x.device)
         info = NfKrylovInfo()
-        fn = getattr(ctx.lib, self._fn)
         # scipy's default rtol = 1e-5 governs: the reference never passes rtol (matrix_free_BiCGSTAB.py:234-242)
-        ctx.check(fn(ctx.handle, C.byref(g), ptr(bd), ptr(x), ptr(du), ptr(dv), float(self.tolerance), 1e-5,
-                     int(self.max_iterations), int(self.check_every), ptr(work), C.byref(info)), self._fn)
+        if self.mg_precond is not None:
+            mg = self.mg_precond._hierarchy(nx, ny, length, height)
+            ctx.check(ctx.lib.nf_mg_setup(mg, ptr(du), ptr(dv)), "nf_mg_setup")
+            ctx.check(ctx.lib.nf_bicgstab_solve_mg(ctx.handle, C.byref(g), ptr(bd), ptr(x), ptr(du), ptr(dv),
+                                                   float(self.tolerance), 1e-5, int(self.max_iterations), 1, ptr(work), mg,
+                                                   int(self.mg_cycles), _CYCLE[self.mg_cycle_type], C.byref(info)),
+                      "nf_bicgstab_solve_mg")
+        else:
+            fn = getattr(ctx.lib, self._fn)
+            ctx.check(fn(ctx.handle, C.byref(g), ptr(bd), ptr(x), ptr(du), ptr(dv), float(self.tolerance), 1e-5,
+                         int(self.max_iterations), int(self.check_every), ptr(work), C.byref(info)), self._fn)
         self.last_info = info
         self.inner_iterations_history.append(info.iterations)
         self.total_inner_iterations += info.iterations

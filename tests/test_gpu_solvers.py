@@ -320,3 +320,36 @@ def test_smoother_fused_residual_paths_match_standalone_kernels(n, pre, post, mo
         x_ref, iref = O.mg_solve(cfg, n, n, dx, dy, s["u_star"], s["v_star"], s["d_u"], s["d_v"])
         assert iref["cycles"] == outs[0][2]
         assert rel(outs[0][0], x_ref) < 1e-11
+
+
+@pytest.mark.parametrize("n,kind,cycles", [(31, "v", 1), (64, "v", 2), (65, "w", 1), (63, "fmg", 1)])
+def test_mg_preconditioned_bicgstab_vs_oracle(n, kind, cycles):
+    """MatrixFreeBiCGSTABSolver(use_preconditioner=True, preconditioner='multigrid') twin against scipy's bicgstab
+    order with M = the oracle's multigrid cycles from zero (matrix_free_BiCGSTAB.py:102-161)."""
+    import naviflow_b200 as nb
+    from oracle.make_golden import synth_pressure_inputs
+    s = synth_pressure_inputs(n, 7000 + n)
+    mesh, _ = cavity(n, 1000)
+    dx = dy = 1.0 / (n - 1)
+    b = O.continuity_rhs(n, n, dx, dy, 1.0, s["u_star"], s["v_star"])
+    mv = lambda z: O.apply_A(z, dx, dy, 1.0, s["d_u"], s["d_v"])
+    cfg = O.MGConfig(smoother="red_black", omega=0.8, pre=2, post=2, coarsest=7, tolerance=1e-7, max_cycles_buildup=1)
+
+    def M(z):
+        x = np.zeros_like(z)
+        for _ in range(cycles):
+            x = O.mg_fmg(cfg, z, dx, dy, s["d_u"], s["d_v"]) if kind == "fmg" else O.mg_cycle(cfg, x, z, dx, dy, s["d_u"], s["d_v"], kind)
+        return x
+
+    x_ref, info_ref, it_ref = O.bicgstab(mv, b, atol=1e-7, maxiter=200, M=M)
+    sol = nb.GpuBiCGSTABSolver(tolerance=1e-7, max_iterations=200, use_preconditioner=True, preconditioner="multigrid",
+                               mg_cycles=cycles, mg_cycle_type=kind)
+    p, info = sol.solve(mesh, s["u_star"], s["v_star"], s["d_u"], s["d_v"], None)
+    assert info_ref == 0 and sol.last_info.info == 0
+    assert abs(sol.last_info.iterations - it_ref) <= 1
+    assert info["rel_norm"] < 2e-5
+    assert rel(p, x_ref) < 1e-4
+    # and far fewer iterations than the unpreconditioned solver
+    plain = nb.GpuBiCGSTABSolver(tolerance=1e-7, max_iterations=2000)
+    plain.solve(mesh, s["u_star"], s["v_star"], s["d_u"], s["d_v"], None)
+    assert sol.last_info.iterations < plain.last_info.iterations
