@@ -22,7 +22,8 @@
 #include "nf_slab.cuh"
 
 #define NF_MIN_SLAB_ROWS 64   // a level is cut only while every rank keeps at least this many rows
-#define NF_SMOOTH_HALO 6      // halo depth consumed by one fused smoother launch (2 * 3 sweeps)
+#define NF_SMOOTH_HALO NF_HALO  // halo rows kept valid around the iterate: 6 for a smoother launch (2 * 3 sweeps),
+                                // +1 / +2 when the residual norms / the restriction ride on it
 
 int nfi_residual_restrict_fw(nf_ctx*, const nf_grid* gf, const double* p, const double* b, const double* d_u,
                              const double* d_v, const nf_grid* gc, double* c);
@@ -485,6 +486,11 @@ int nfi_mg_setup(nf_mg* mg, double* const* d_u, double* const* d_v) {
     mg->lv[0].s[k].d_u = d_u[k];
     mg->lv[0].s[k].d_v = d_v[k];
   }
+  if (mg->lv[0].geom.dist) {  // the callers' coefficients are exact NF_HALO-1 rows out: complete the halo
+    std::vector<double*> du = field_of(mg->lv[0], &MgSlab::d_u), dv = field_of(mg->lv[0], &MgSlab::d_v);
+    NF_TRY(nf_team_exchange(team, mg->lv[0].geom, du.data(), NF_HALO));
+    NF_TRY(nf_team_exchange(team, mg->lv[0].geom, dv.data(), NF_HALO));
+  }
   for (size_t l = 0; l + 1 < mg->lv.size(); ++l) {
     MgLevel& L = mg->lv[l];
     MgLevel& C = mg->lv[l + 1];
@@ -507,7 +513,7 @@ int nfi_mg_setup(nf_mg* mg, double* const* d_u, double* const* d_v) {
   if (mg->cfg.smoother == 0)
     for (MgLevel& L : mg->lv)
       for (int k = 0; k < nl; ++k) {
-        const nf_grid g = L.geom.grid_ext(team->local[k], NF_SMOOTH_HALO);
+        const nf_grid g = L.geom.grid_ext(team->local[k], NF_HALO - 1);  // row i needs d_u[i+1]
         NF_TRY(nfi_inv_diag(ctx, &g, L.s[k].d_u, L.s[k].d_v, L.s[k].inv));
       }
   MgLevel& C = mg->lv.back();
@@ -534,7 +540,7 @@ extern "C" int nf_mg_setup(nf_mg* mg, const double* d_u, const double* d_v) {
 // =============================================================================================
 // n smoothing sweeps on level l; on a cut level the iterate's halo is valid on entry and on return
 // extra (single slab only): work fused behind the last smoother launch, see nf_smooth_extra
-static int mg_smooth(nf_mg* mg, int l, int n, nf_smooth_extra* extra = nullptr) {
+static int mg_smooth(nf_mg* mg, int l, int n, nf_smooth_extra* extra = nullptr /* one per local slab */) {
   nf_ctx* ctx = mg->ctx;
   nf_team* team = mg->team;
   MgLevel& L = mg->lv[l];
@@ -561,7 +567,7 @@ static int mg_smooth(nf_mg* mg, int l, int n, nf_smooth_extra* extra = nullptr) 
       for (int k = 0; k < nl; ++k) {
         const nf_grid g = L.geom.grid(team->local[k]);
         NF_TRY(nfi_rbsor_fused_x(ctx, &g, &L.s[k].x, &L.s[k].x2, L.s[k].b, L.s[k].d_u, L.s[k].d_v, L.s[k].inv,
-                                 mg->cfg.omega, ns, (extra && nl == 1 && left == ns) ? extra : nullptr));
+                                 mg->cfg.omega, ns, (extra && left == ns) ? &extra[k] : nullptr));
       }
       if (timed) {
         cudaEventRecord(mg->ev[mg->ev_used + 1], ctx->stream);
@@ -637,17 +643,19 @@ static int mg_cycle(nf_mg* mg, int l, int kind, bool want_norm = false, bool* no
   if (norm_fused) *norm_fused = false;
   if (L.geom.nx <= mg->cfg.coarsest || l + 1 == (int)mg->lv.size()) return mg_coarse_solve(mg, l);
   MgLevel& C = mg->lv[l + 1];
-  nf_smooth_extra pre;
-  if (nl == 1 && mg->cfg.smoother == 0 && mg->cfg.restriction == 0 && !L.geom.dist) {
-    pre.mode = 2;
-    pre.gc = restrict_target(C, team->local[0]);
-    pre.coarse_b = C.s[0].b;
-  }
-  NF_TRY(mg_smooth(mg, l, mg->cfg.pre, pre.mode ? &pre : nullptr));
+  std::vector<nf_smooth_extra> pre(nl);
+  const bool want_pre = mg->cfg.smoother == 0 && mg->cfg.restriction == 0;
+  if (want_pre)
+    for (int k = 0; k < nl; ++k) {
+      pre[k].mode = 2;
+      pre[k].gc = restrict_target(C, team->local[k]);
+      pre[k].coarse_b = C.s[k].b;
+    }
+  NF_TRY(mg_smooth(mg, l, mg->cfg.pre, want_pre ? pre.data() : nullptr));
   for (int k = 0; k < nl; ++k) {
     const int r = team->local[k];
     const nf_grid gf = L.geom.grid(r), gc = restrict_target(C, r);
-    if (pre.fused) {
+    if (pre[k].fused) {
       // coarse right-hand side already written by the smoother
     } else if (mg->cfg.restriction == 0) {
       NF_TRY(nfi_residual_restrict_fw(ctx, &gf, L.s[k].x, L.s[k].b, L.s[k].d_u, L.s[k].d_v, &gc, C.s[k].b));
@@ -661,13 +669,19 @@ static int mg_cycle(nf_mg* mg, int l, int kind, bool want_norm = false, bool* no
   const int reps = (kind == 1) ? 2 : 1;
   for (int rep = 0; rep < reps; ++rep) NF_TRY(mg_cycle(mg, l + 1, kind));
   NF_TRY(mg_prolong(mg, l, mg->cfg.interpolation, 1));
-  nf_smooth_extra post;
-  if (want_norm && nl == 1 && mg->cfg.smoother == 0 && !L.geom.dist) {
-    post.mode = 1;
-    post.out = mg->scal[0];
+  std::vector<nf_smooth_extra> post(nl);
+  const bool want_post = want_norm && mg->cfg.smoother == 0;
+  if (want_post)
+    for (int k = 0; k < nl; ++k) {
+      post[k].mode = 1;
+      post[k].out = mg->scal[k];
+    }
+  NF_TRY(mg_smooth(mg, l, mg->cfg.post, want_post ? post.data() : nullptr));
+  if (norm_fused) {
+    bool all = want_post;
+    for (int k = 0; k < nl; ++k) all = all && post[k].fused;
+    *norm_fused = all;  // same decision on every rank: it depends on the level geometry only
   }
-  NF_TRY(mg_smooth(mg, l, mg->cfg.post, post.mode ? &post : nullptr));
-  if (norm_fused) *norm_fused = post.fused;
   return NF_OK;
 }
 
@@ -746,6 +760,7 @@ static int mg_rel_residual(nf_mg* mg, int l, double* r_norm, double* b_norm, int
   int with_b = (*b_norm < 0.0) ? 1 : 0;
   if (have_norms) {
     with_b = 1;
+    if (L.geom.dist) NF_TRY(nf_team_allreduce(team, mg->scal.data(), 2));
   } else {
     for (int k = 0; k < nl; ++k) {
       const nf_grid g = L.geom.grid(team->local[k]);

@@ -651,8 +651,8 @@ int nfi_rbsor_fused_x(nf_ctx* ctx, const nf_grid* g, double** p, double** palt, 
     ex.gc = *g;
     int mode = 0;
     // extra work rides on the last launch; it needs the precomputed 1/aP, an unsplit grid and even tile origins
-    if (extra && extra->mode != 0 && allow_extra && left == ns && use_tma && inv && g->row0 == 0 && g->gb == 0 &&
-        g->ge == g->nx) {
+    if (extra && extra->mode != 0 && allow_extra && left == ns && use_tma && inv &&
+        (extra->mode == 1 || (g->gb % 2) == 0)) {
       mode = extra->mode;
       ex.gc = extra->gc;
       ex.coarse_b = extra->coarse_b;

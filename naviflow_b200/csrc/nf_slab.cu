@@ -4,6 +4,7 @@
 #include "nf_slab.cuh"
 
 #include <dlfcn.h>
+#include <stdlib.h>
 #include <string.h>
 
 // ---- minimal NCCL surface (types and enums as in nccl.h 2.x; the ABI of these entry points is stable) ----------
@@ -67,7 +68,8 @@ bool nf_split_rows(int nx, int world, int min_rows, std::vector<int>& gb, std::v
   if (world <= 1) return false;
   for (int r = 0; r < world; ++r) {
     long long b = ((long long)nx * r) / world;
-    b = (b / 2) * 2;  // even boundaries keep the red-black colouring and the 2I+1 parents aligned
+    b = (b / 16) * 16;  // boundaries on multiples of 16: even tile origins on the first four levels (fused
+                        // residual+restriction) and 2I+1 parents aligned with the owner of the fine rows
     gb[r] = (int)b;
   }
   for (int r = 0; r < world; ++r) ge[r] = (r + 1 < world) ? gb[r + 1] : nx;
@@ -98,6 +100,8 @@ void nf_coarsen_split(const std::vector<int>& gbf, const std::vector<int>& gef, 
 int nf_team_exchange(nf_team* team, const LevelGeom& geom, double* const* fields, int depth) {
   nf_ctx* ctx = team->ctx;
   if (!geom.dist || team->world <= 1 || depth <= 0) return NF_OK;
+  static const bool skip = getenv("NF_SKIP_EXCHANGE") != nullptr;  // timing experiments only: results are wrong
+  if (skip) return NF_OK;
   if (depth > geom.halo) depth = geom.halo;
   NcclApi* api = team->nccl ? nccl_api() : nullptr;
   if (api) NF_NCCL(ctx, api->GroupStart());

@@ -353,3 +353,31 @@ def test_mg_preconditioned_bicgstab_vs_oracle(n, kind, cycles):
     plain = nb.GpuBiCGSTABSolver(tolerance=1e-7, max_iterations=2000)
     plain.solve(mesh, s["u_star"], s["v_star"], s["d_u"], s["d_v"], None)
     assert sol.last_info.iterations < plain.last_info.iterations
+
+
+@pytest.mark.parametrize("n,ranks,k", [(257, 2, 5), (385, 3, 3), (513, 4, 6), (1025, 2, 5)])
+def test_slab_decomposition_with_tma_smoother_and_fused_residuals(n, ranks, k, monkeypatch):
+    """Same bit-identity with the persistent TMA smoother forced on every cut level, i.e. with the residual norms
+    and the residual+restriction riding on the smoother launches of every slab (halo depth 8)."""
+    monkeypatch.setenv("NF_RBSOR_TMA", "0")
+    ref, rres = _slab_run(n, 1000, k, 3, 1)
+    alg, res = _slab_run(n, 1000, k, 3, ranks)
+    for fld in ("u", "v", "p"):
+        np.testing.assert_array_equal(getattr(alg, fld), getattr(ref, fld), err_msg=fld)
+    np.testing.assert_allclose(res.get_history("p_rel_norm"), rres.get_history("p_rel_norm"), rtol=1e-10)
+    # tolerance-driven cycles
+    import naviflow_b200 as nb
+    out = []
+    for r in (1, ranks):
+        mesh, fluid = cavity(n, 1000)
+        ps = nb.GpuMultiGridSolver(smoother=nb.GpuGaussSeidelSolver(omega=1.5), max_iterations=100, tolerance=1e-3,
+                                   pre_smoothing=3, post_smoothing=3)
+        a = nb.GpuSimpleSolver(mesh, fluid, ps, nb.GpuJacobiMomentumSolver(n_jacobi_sweeps=k), virtual_ranks=r)
+        a.set_boundary_condition("top", "velocity", {"u": 1.0, "v": 0.0})
+        for b in ("bottom", "left", "right"):
+            a.set_boundary_condition(b, "wall")
+        a.solve(max_iterations=3, tolerance=0.0)
+        out.append((a.u.copy(), a.p.copy(), list(a.pressure_iterations_history)))
+    assert out[0][2] == out[1][2]
+    np.testing.assert_array_equal(out[0][0], out[1][0])
+    np.testing.assert_array_equal(out[0][1], out[1][1])
