@@ -246,6 +246,11 @@ int nf_nccl_unique_id(nf_ctx*, void* id_out_128_bytes);
 int nf_team_create_nccl(nf_ctx*, int world, int rank, const void* id_128_bytes, nf_team** out);
 int nf_team_create_virtual(nf_ctx*, int virtual_ranks, nf_team** out);
 int nf_team_free(nf_team*);
+/* host-only partition queries: cell rows [begin, end) of `rank` when nx rows are cut over `world` ranks (boundaries
+ * on multiples of 16; the grid is not cut when a slab would have fewer than 64 rows), and the rows of the
+ * next-coarser level a rank restricts into (coarse row I belongs to the owner of fine row 2I+1) */
+int nf_slab_rows(int nx, int world, int rank, int* row_begin, int* row_end);
+int nf_slab_coarse_rows(int fine_begin, int next_fine_begin, int is_last, int nxc, int* row_begin, int* row_end);
 /* SIMPLE state cut over the team (multigrid pressure solver, bilinear prolongation); the team outlives it */
 int nf_simple_create_team(nf_team*, nf_simple** out, const nf_simple_config* cfg);
 /* live CUDA-event timing of the finest-level fused smoother launches (3 sweeps each) inside nf_simple_iterate /

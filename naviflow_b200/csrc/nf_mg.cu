@@ -692,7 +692,11 @@ static int mg_cycle_top(nf_mg* mg, int kind, bool* norm_fused) {
   nf_ctx* ctx = mg->ctx;
   MgLevel& L = mg->lv[0];
   const char* env = getenv("NF_MG_GRAPH");
-  const bool allowed = mg->use_graph && !(env && env[0] == '0') && nlocal(mg) == 1 && !L.geom.dist &&
+  // slab runs under torchrun: the NCCL halo exchanges are captured into the graph as well (every rank replays the
+  // same sequence); opt out with NF_MG_GRAPH_DIST=0
+  const char* envd = getenv("NF_MG_GRAPH_DIST");
+  const bool dist_ok = !L.geom.dist || (mg->team->nccl != nullptr && !(envd && envd[0] == '0'));
+  const bool allowed = mg->use_graph && !(env && env[0] == '0') && nlocal(mg) == 1 && dist_ok &&
                        mg->cfg.smoother == 0 && !mg->timing &&
                        ((mg->cfg.pre + 2) / 3 + (mg->cfg.post + 2) / 3) % 2 == 0;  // even number of x/x2 swaps
   if (!allowed) return mg_cycle(mg, 0, kind, true, norm_fused);

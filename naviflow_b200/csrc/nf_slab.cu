@@ -245,3 +245,25 @@ int nf_team_destroy(nf_team* t) {
 }
 
 extern "C" int nf_team_free(nf_team* t) { return nf_team_destroy(t); }
+
+// Host-only queries of the partition rules (no device needed; used by the CPU tests and by callers that want to
+// know which rows a rank will own before creating any state).
+extern "C" int nf_slab_rows(int nx, int world, int rank, int* row_begin, int* row_end) {
+  if (nx < 3 || world < 1 || rank < 0 || rank >= world) return NF_ERR_ARG;
+  std::vector<int> gb, ge;
+  nf_split_rows(nx, world, 64, gb, ge);  // 64 = NF_MIN_SLAB_ROWS: thinner slabs -> the grid is not cut
+  if (row_begin) *row_begin = gb[rank];
+  if (row_end) *row_end = ge[rank];
+  return NF_OK;
+}
+
+// rows of the next-coarser level (nxc cells) a rank restricts into, given its fine rows [fb, fe) and those of the
+// rank above it: coarse row I belongs to the owner of fine row 2I+1
+extern "C" int nf_slab_coarse_rows(int fine_begin, int next_fine_begin, int is_last, int nxc, int* row_begin,
+                                   int* row_end) {
+  std::vector<int> gbf = {fine_begin, next_fine_begin}, gef = {next_fine_begin, 0}, gb, ge;
+  nf_coarsen_split(gbf, gef, nxc, gb, ge);
+  if (row_begin) *row_begin = gb[0];
+  if (row_end) *row_end = is_last ? nxc : ge[0];
+  return NF_OK;
+}

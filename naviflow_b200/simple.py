@@ -30,6 +30,31 @@ _FIELD = {"u": 0, "v": 1, "p": 2, "u_star": 3, "v_star": 4, "d_u": 5, "d_v": 6, 
           "p_res": 9, "u_res": 10, "v_res": 11}
 
 
+def slab_rows(nx, world, rank):
+    """Cell rows [begin, end) rank `rank` owns when nx rows are cut over `world` ranks (host-only query of the
+    library's partition rule; works without a GPU)."""
+    from . import _lib
+    b, e = C.c_int(), C.c_int()
+    st = _lib.lib().nf_slab_rows(int(nx), int(world), int(rank), C.byref(b), C.byref(e))
+    if st != 0:
+        raise ValueError(f"nf_slab_rows({nx}, {world}, {rank}) failed with status {st}")
+    return b.value, e.value
+
+
+def assemble_rows(arr, begin, end, device=None):
+    """Every rank holds valid rows [begin, end) of the same full-size array (the last rank up to the end): sum the
+    zero-padded pieces over the process group so that all ranks end with the complete array (in place)."""
+    import torch
+    import torch.distributed as dist
+    if device is None:
+        device = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.zeros(arr.shape, dtype=torch.float64, device=device)
+    t[begin:end].copy_(torch.from_numpy(np.ascontiguousarray(arr[begin:end])))
+    dist.all_reduce(t)
+    arr[...] = t.cpu().numpy()
+    return arr
+
+
 class GpuSimpleSolver:
     def __init__(self, mesh, fluid, pressure_solver=None, momentum_solver=None, velocity_updater=None,
                  boundary_conditions=None, alpha_p=0.3, alpha_u=0.7, fix_lid_corners=False, device=None,
@@ -263,11 +288,7 @@ class GpuSimpleSolver:
         b, e = self.local_rows()
         if rank == world - 1:
             e = arr.shape[0]
-        t = torch.zeros(arr.shape, dtype=torch.float64, device=f"cuda:{get_context(self._device).device}")
-        t[b:e].copy_(torch.from_numpy(np.ascontiguousarray(arr[b:e])))
-        dist.all_reduce(t)
-        arr[...] = t.cpu().numpy()
-        return arr
+        return assemble_rows(arr, b, e, device=f"cuda:{get_context(self._device).device}")
 
     # ---- SimpleSolver.solve -----------------------------------------------------------------------
     def solve(self, max_iterations=1000, tolerance=1e-6, save_profile=False, profile_dir="results/profiles",
