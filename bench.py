@@ -8,7 +8,7 @@ SIMPLE (alpha_p 0.3, alpha_u 0.7) with JacobiMatrixMomentumSolver-style fixed Ja
 geometric-multigrid pressure solve: V-cycles, red-black SOR smoother omega 1.5, 3 pre + 3 post sweeps, full
 weighting + bilinear prolongation, coarsest 7, cycles until ||r||/||b|| < 1e-3 (at most `--mg-cycles`).
 A step = one SIMPLE outer iteration.  value = cells * iterations / time (MLUPS), device resident.
-e2e = the same through GpuSimpleSolver.solve() with host arrays (H2D of u,v,p and D2H of u,v,p,residual
+e2e = the same through GpuSimpleSolver.solve() with host arrays (H2D of u,v,p and D2H of u,v,p
 inside the timed region, one outer iteration per call).
 --impl reference: the reference algorithm's CPU path (NumPy oracle port, oracle/np_oracle.py) on a bounded
 sample grid of the same workload.
@@ -319,7 +319,7 @@ def main():
         dt = float(tt.item())
         fb = 8.0 * n * (n + 1)
         e2e = {"value": cells * ksteps / dt / 1e6, "unit": "MLUPS", "steps": ksteps,
-               "h2d_bytes_per_step": int(2 * fb + 8.0 * n * n), "d2h_bytes_per_step": int(2 * fb + 2 * 8.0 * n * n),
+               "h2d_bytes_per_step": int(2 * fb + 8.0 * n * n), "d2h_bytes_per_step": int(2 * fb + 8.0 * n * n),
                "note": "whole-job bytes; with N ranks each rank moves its own row slab (+8 halo rows up)"}
 
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload ------------------------

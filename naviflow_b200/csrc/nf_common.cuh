@@ -24,7 +24,7 @@ struct nf_ctx {
   std::string err;
 };
 
-#define NF_MAX_PARTIALS 4096
+#define NF_MAX_PARTIALS 16384
 #define NF_MAX_RED 4
 #define NF_NUM_SCALARS 64
 
@@ -152,7 +152,7 @@ static inline NfLaunch2D nf_launch_reduce(int rows, int cols) {
   if (gy < 1) gy = 1;
   int max_gy = NF_MAX_PARTIALS / gx;
   if (max_gy < 1) max_gy = 1;
-  int target = (NF_SM_COUNT * 8 + gx - 1) / gx;  // ~8 blocks per SM
+  int target = (NF_SM_COUNT * 32 + gx - 1) / gx;  // ~32 blocks per SM: short per-thread row loops, 4 waves
   if (target < 1) target = 1;
   if (gy > target) gy = target;
   if (gy > max_gy) gy = max_gy;

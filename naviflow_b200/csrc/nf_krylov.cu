@@ -39,7 +39,7 @@ __device__ __forceinline__ double nf_Ap_cell_f(const nf_grid& g, const double* _
 }
 
 #define NF_ROWLOOP(g, i) \
-  for (int i = (g).gb + blockIdx.y * blockDim.y + threadIdx.y; i < (g).ge; i += gridDim.y * blockDim.y)
+  _Pragma("unroll 2") for (int i = (g).gb + blockIdx.y * blockDim.y + threadIdx.y; i < (g).ge; i += gridDim.y * blockDim.y)
 
 // ---------------------------------------------------------------------------------------------
 // shared: r = b, (rtilde = b), rr = rho = b.b, stopping tolerance

@@ -85,7 +85,8 @@ class GpuSimpleSolver:
         self._team = None
         self._virtual_ranks = int(virtual_ranks)
         self._distributed = distributed
-        self._final_u_residual_field = self._final_v_residual_field = self._final_p_residual_field = None
+        self._p_residual_cache = None
+        self._final_u_residual_field = self._final_v_residual_field = None
         self.initialize_fields()
 
     # ---- BaseAlgorithm interface ------------------------------------------------------------------
@@ -116,6 +117,19 @@ class GpuSimpleSolver:
         self.bc_manager.set_condition(boundary, condition_type, values)
         self.boundary_conditions = self.bc_manager.to_dict()
         self.apply_boundary_conditions()
+
+    @property
+    def _final_p_residual_field(self):
+        """Pressure residual field of the last iteration (simple.py:217-219), downloaded on first access."""
+        if self._p_residual_cache is None and self._state is not None:
+            ctx, st = self._ensure_state()
+            nx, ny = self.mesh.get_dimensions()
+            self._p_residual_cache = self._download(ctx, st, "p_res", nx, ny)
+        return self._p_residual_cache
+
+    @_final_p_residual_field.setter
+    def _final_p_residual_field(self, value):
+        self._p_residual_cache = value
 
     def get_max_divergence(self):
         dx, dy = self.mesh.get_cell_sizes()
@@ -331,7 +345,7 @@ class GpuSimpleSolver:
         except KeyboardInterrupt:
             print("Interrupted by user.")
         self.pull_fields(gather)
-        self._final_p_residual_field = self._download(ctx, st, "p_res", nx, ny, self._final_p_residual_field)
+        self._p_residual_cache = None  # the residual field stays on the device until somebody asks for it
         result = SimulationResult(self.u, self.v, self.p, self.mesh, iterations=iteration - 1,
                                   residuals=self.residual_history, reynolds=self.fluid.get_reynolds_number(),
                                   wall_time=time.perf_counter() - t0)
