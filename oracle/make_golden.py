@@ -194,6 +194,28 @@ def simple_runs(R):
     return out
 
 
+def piso_runs(R):
+    """PisoSolver with the deterministic momentum adapter."""
+    out = {}
+    for n, Re, k, N, nc, name in ((31, 100, 5, 15, 2, "v"), (31, 100, 5, 15, 3, "rbsor"), (63, 1000, 10, 8, 2, "v")):
+        GS = R.GaussSeidelSolver
+        ps = (R.MultiGridSolver(smoother=GS(omega=1.5, method_type="red_black"), max_iterations=100, tolerance=1e-3,
+                                pre_smoothing=3, post_smoothing=3) if name == "v"
+              else GS(tolerance=0.0, max_iterations=30, omega=1.5, method_type="red_black"))
+        mesh = R.StructuredMesh(n, n, 1.0, 1.0)
+        fluid = R.FluidProperties(density=1.0, reynolds_number=Re, characteristic_velocity=1.0)
+        alg = R.PisoSolver(mesh, fluid, ps, R.JacobiMatrixMomentumAdapter(n_jacobi_sweeps=k), R.StandardVelocityUpdater(),
+                           alpha_p=0.3, alpha_u=0.7, n_corrections=nc)
+        alg.set_boundary_condition("top", "velocity", {"u": 1.0, "v": 0.0})
+        for b in ("bottom", "left", "right"):
+            alg.set_boundary_condition(b, "wall")
+        _quiet(alg.solve, max_iterations=N, tolerance=0.0, save_profile=False, track_infinity_norm=False)
+        key = f"n{n}_Re{Re}_k{k}_N{N}_c{nc}_{name}"
+        out[key + "_u"], out[key + "_v"], out[key + "_p"] = alg.u, alg.v, alg.p
+        out[key + "_hist"] = np.array(alg.residual_history)
+    return out
+
+
 def main():
     warnings.filterwarnings("ignore")
     R = rl.ref()
@@ -203,6 +225,7 @@ def main():
     for n, seed in ((31, 231), (33, 233), (64, 264)):
         np.savez_compressed(os.path.join(GOLD, f"mg_n{n}.npz"), **mg_kats(R, n, seed))
     np.savez_compressed(os.path.join(GOLD, "simple_runs.npz"), **simple_runs(R))
+    np.savez_compressed(os.path.join(GOLD, "piso_runs.npz"), **piso_runs(R))
     cf = R.cavity_flow.BenchmarkData
     tables = {}
     for Re in (100, 400, 1000, 3200, 5000, 7500, 10000):

@@ -970,6 +970,45 @@ def simple_solve(nx, ny, reynolds, pressure_solver, n_sweeps=20, alpha_p=0.3, al
 
 
 # ----------------------------------------------------------------------------
+# "next" row: PISO outer loop (Algorithms/piso.py:41-175)
+# ----------------------------------------------------------------------------
+def piso_solve(nx, ny, reynolds, pressure_solver, n_sweeps=20, alpha_p=0.3, alpha_u=0.7, n_corrections=2,
+               max_iterations=100, tolerance=0.0, conditions=None, rho=1.0, U=1.0, L=1.0):
+    """PisoSolver.solve (piso.py:53-135) with the deterministic momentum oracle: predictor with alpha_u, then
+    n_corrections x (pressure solve, p update + Neumann copies, velocity correction); between corrections the momentum
+    equations are re-solved from the corrected (u, v, p) without relaxation (:92-104).  The norms reported are the
+    predictor's (:107-109)."""
+    conditions = bc_conditions() if conditions is None else conditions
+    dx, dy = mesh_spacing(nx, ny, L, L)
+    mu = rho * U * L / reynolds
+    st = SimpleState(nx, ny, conditions)
+    p_star = st.p.copy()
+    hist = {"u_rel_norm": [], "v_rel_norm": [], "p_rel_norm": [], "total_rel_norm": []}
+    it, total = 1, 1.0
+    while it <= max_iterations and total > tolerance:
+        us, du, un, _ = solve_u_momentum(nx, ny, dx, dy, rho, mu, st.u, st.v, p_star, alpha_u, conditions, n_sweeps)
+        vs, dv, vn, _ = solve_v_momentum(nx, ny, dx, dy, rho, mu, st.u, st.v, p_star, alpha_u, conditions, n_sweeps)
+        pinfo = None
+        for c in range(n_corrections):
+            pp, pinfo = pressure_solver(nx, ny, dx, dy, us, vs, du, dv)
+            st.p = update_pressure(p_star, pp, alpha_p, conditions)
+            p_star = st.p.copy()
+            st.u, st.v = correct_velocity(nx, ny, us, vs, pp, du, dv, conditions)
+            us, vs = st.u.copy(), st.v.copy()
+            if c < n_corrections - 1:
+                us, du, _, _ = solve_u_momentum(nx, ny, dx, dy, rho, mu, st.u, st.v, st.p, 1, conditions, n_sweeps)
+                vs, dv, _, _ = solve_v_momentum(nx, ny, dx, dy, rho, mu, st.u, st.v, st.p, 1, conditions, n_sweeps)
+        total = max(un, vn)
+        hist["u_rel_norm"].append(un)
+        hist["v_rel_norm"].append(vn)
+        hist["p_rel_norm"].append(pinfo["rel_norm"] if pinfo else 0.0)
+        hist["total_rel_norm"].append(total)
+        it += 1
+    hist["iterations"] = it - 1
+    return st, hist
+
+
+# ----------------------------------------------------------------------------
 # a17  Ghia centre-line errors (postprocessing/validation/cavity_flow.py:178-301)
 # ----------------------------------------------------------------------------
 def ghia_errors(u, v, nx, ny, table):

@@ -125,6 +125,7 @@ def ref():
     from naviflow_oo.solver.pressure_solver.matrix_free_BiCGSTAB import MatrixFreeBiCGSTABSolver
     from naviflow_oo.solver.velocity_solver.standard import StandardVelocityUpdater
     from naviflow_oo.solver.Algorithms.simple import SimpleSolver
+    from naviflow_oo.solver.Algorithms.piso import PisoSolver
     from naviflow_oo.postprocessing.validation import cavity_flow
     ns.__dict__.update(locals())
     del ns.__dict__["ns"]

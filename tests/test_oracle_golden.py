@@ -136,3 +136,18 @@ def test_simple_loop_golden(golden_dir, n, Re, k, N, name):
         tables = json.load(open(os.path.join(os.path.dirname(golden_dir), "..", "naviflow_b200", "ghia_tables.json")))
         inf, l2 = O.ghia_errors(st.u, st.v, n, n, tables[str(Re)])
         np.testing.assert_allclose([inf, l2], g[key + "_ghia"], rtol=1e-9)
+
+
+@pytest.mark.parametrize("n,Re,k,N,nc,name", [(31, 100, 5, 15, 2, "v"), (31, 100, 5, 15, 3, "rbsor"), (63, 1000, 10, 8, 2, "v")])
+def test_piso_loop_golden(golden_dir, n, Re, k, N, nc, name):
+    """PisoSolver.solve (Algorithms/piso.py:53-135) against the reference's own run."""
+    g = load(golden_dir, "piso_runs.npz")
+    key = f"n{n}_Re{Re}_k{k}_N{N}_c{nc}_{name}"
+    st, h = O.piso_solve(n, n, Re, _ps(name), n_sweeps=k, n_corrections=nc, max_iterations=N, tolerance=0.0)
+    tol = 0.0 if name == "rbsor" else 1e-12
+    for fld, arr in (("u", st.u), ("v", st.v), ("p", st.p)):
+        if tol == 0.0:
+            same(arr, g[f"{key}_{fld}"])
+        else:
+            close(arr, g[f"{key}_{fld}"], tol)
+    np.testing.assert_allclose(h["total_rel_norm"], g[key + "_hist"], rtol=1e-9)
