@@ -210,7 +210,7 @@ int nf_update_pressure(nf_ctx*, const nf_grid*, const double* p_star, const doub
                        double* p);
 int nf_max_abs_divergence(nf_ctx*, const nf_grid*, const double* u, const double* v, double* out_host);
 
-/* ---- device-resident SIMPLE outer loop: Algorithms/simple.py:78-269 ------------------------ */
+/* ---- device-resident SIMPLE / PISO outer loops: Algorithms/simple.py:78-269, piso.py:41-175 ---- */
 typedef struct nf_simple_config {
   int32_t nx, ny;
   int32_t n_momentum_sweeps;    /* JacobiMatrixMomentumSolver(n_jacobi_sweeps)                          */
@@ -218,7 +218,8 @@ typedef struct nf_simple_config {
   int32_t pressure_iterations;  /* fixed iteration count of the Jacobi / SOR pressure solvers          */
   int32_t sides;                /* boundaries with a registered condition: 1 left 2 right 4 bottom 8 top */
   int32_t krylov_maxiter;
-  int32_t pad;
+  int32_t piso_corrections;     /* 0: SIMPLE (simple.py:114-212); n >= 1: PISO with n pressure corrections per outer
+                                   iteration, momentum re-solved without relaxation in between (piso.py:73-104)     */
   double length, height, rho, mu;
   double alpha_p, alpha_u;      /* simple.py:23-76                                                      */
   double pressure_omega;        /* Jacobi / SOR relaxation                                              */

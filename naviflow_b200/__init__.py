@@ -9,9 +9,10 @@ from .host import (BoundaryConditionManager, FluidProperties, SimulationResult, 
 from .momentum import GpuJacobiMomentumSolver
 from .pressure import (GpuBiCGSTABSolver, GpuCGSolver, GpuGaussSeidelSolver, GpuJacobiSolver,
                        GpuMultiGridSolver)
-from .simple import GpuSimpleSolver
+from .simple import GpuPisoSolver, GpuSimpleSolver
 from .velocity import GpuVelocityUpdater
 
 __all__ = ["StructuredMesh", "FluidProperties", "BoundaryConditionManager", "SimulationResult", "ghia_errors",
            "ghia_table", "GpuJacobiMomentumSolver", "GpuJacobiSolver", "GpuGaussSeidelSolver",
-           "GpuMultiGridSolver", "GpuCGSolver", "GpuBiCGSTABSolver", "GpuVelocityUpdater", "GpuSimpleSolver"]
+           "GpuMultiGridSolver", "GpuCGSolver", "GpuBiCGSTABSolver", "GpuVelocityUpdater", "GpuSimpleSolver",
+           "GpuPisoSolver"]

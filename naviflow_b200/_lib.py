@@ -57,7 +57,7 @@ class NfLinks(C.Structure):
 class NfSimpleConfig(C.Structure):
     _fields_ = [("nx", C.c_int32), ("ny", C.c_int32), ("n_momentum_sweeps", C.c_int32),
                 ("pressure_solver", C.c_int32), ("pressure_iterations", C.c_int32),
-                ("sides", C.c_int32), ("krylov_maxiter", C.c_int32), ("pad", C.c_int32),
+                ("sides", C.c_int32), ("krylov_maxiter", C.c_int32), ("piso_corrections", C.c_int32),
                 ("length", C.c_double), ("height", C.c_double), ("rho", C.c_double), ("mu", C.c_double),
                 ("alpha_p", C.c_double), ("alpha_u", C.c_double), ("pressure_omega", C.c_double),
                 ("pressure_tolerance", C.c_double),

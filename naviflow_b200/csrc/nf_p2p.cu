@@ -1,0 +1,467 @@
+// nf_p2p.cu -- halo exchange, scalar all-reduce and row sharing of the slab decomposition done by the ranks' own
+// kernels over NVLink peer memory (one process per GPU; no counterpart in the reference, which is a single process).
+//
+// Why: a V-cycle on slabs performs ~18 halo exchanges of a few rows each.  As grouped ncclSend/ncclRecv every one
+// costs ~15-20 us of launch + protocol latency, which is what limits the 8-GPU scaling.  Here an
+// exchange is ONE kernel per rank:
+//   1. push: the rank stores its boundary rows straight into a staging slot in the neighbour's memory (NVLink stores,
+//      fire and forget), fences at system scope and the last block raises a sequence flag in the neighbour's memory;
+//   2. wait + unpack: the blocks spin on the flag the neighbour raises in OUR memory and copy the staged rows into the
+//      halo rows of the field.
+// Staging slots alternate (2 per direction), which makes the write-after-read hazard impossible without a second
+// handshake: a rank writes slot s again two exchanges later, after it has seen the neighbour's flag of the exchange in
+// between, which the neighbour raises only after its unpack of slot s has completed (stream order).
+// Sequence numbers live in DEVICE memory (ctrl->*_count) and are advanced by the kernels themselves, so the kernels
+// carry no per-call host state and can be captured into the CUDA graph of a multigrid cycle and replayed.
+//
+// Memory: every rank allocates its fields from an arena of cudaMalloc'ed chunks whose cudaIpc handles are exchanged
+// once per chunk (ncclAllGather on the team's communicator); all ranks allocate the same sizes in the same order
+// (callers pass the maximum over ranks), so a local pointer translates to the peer's address by chunk + offset.
+// If any step of the set-up fails on any rank the team falls back to the NCCL path on every rank.
+#include "nf_slab.cuh"
+
+#include <stdlib.h>
+#include <string.h>
+
+#define NF_P2P_MAX_WORLD 8
+#define NF_P2P_RED_MAX 8
+
+struct nf_p2p_ctrl {  // one per rank, lives in chunk 0 (peer-visible)
+  unsigned long long halo_flag[2];                    // [0] raised by the lower neighbour, [1] by the upper one
+  unsigned long long red_flag[NF_P2P_MAX_WORLD];      // raised by rank q
+  unsigned long long ack_flag[NF_P2P_MAX_WORLD];
+  unsigned long long done_flag[NF_P2P_MAX_WORLD];
+  unsigned long long halo_count, red_count, share_count;  // exchanges completed (local, advanced by the kernels)
+  unsigned int ticket[4];
+  int error;                                           // set when a wait timed out (peer ran a different program)
+  int pad;
+  double red_stage[2][NF_P2P_MAX_WORLD][NF_P2P_RED_MAX];
+};
+
+struct P2PChunk {
+  char* base = nullptr;
+  size_t size = 0, used = 0;
+  char* peer[NF_P2P_MAX_WORLD] = {nullptr};
+};
+
+struct nf_p2p {
+  bool active = false;
+  int rank = 0, world = 1;
+  std::vector<P2PChunk> chunks;
+  nf_p2p_ctrl* ctrl = nullptr;  // local control block
+  double* stage = nullptr;      // local staging: [from lower | from upper][slot 0 | 1][stage_elems]
+  size_t stage_elems = 0;
+  void* dbuf = nullptr;         // handle exchange scratch
+};
+
+// ---- device helpers ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_flag_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_flag_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long nf_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// spins until *flag >= seq; gives up after ~4 s (a peer that runs a different launch sequence must not hang the box)
+__device__ __forceinline__ bool wait_flag(const unsigned long long* flag, unsigned long long seq, int* error) {
+  if (ld_flag_sys(flag) >= seq) return true;
+  const unsigned long long t0 = nf_globaltimer();
+  for (;;) {
+    for (int k = 0; k < 64; ++k)
+      if (ld_flag_sys(flag) >= seq) return true;
+    if (nf_globaltimer() - t0 > 4000000000ull) { *error = 1; return false; }
+  }
+}
+
+struct HaloSide {
+  const double* src;            // my owned boundary rows
+  double* remote_stage;         // neighbour's staging area for data coming from me (slot 0)
+  const double* local_stage;    // my staging area for data coming from this neighbour (slot 0)
+  double* dst;                  // my halo rows
+  unsigned long long* remote_flag;
+  const unsigned long long* local_flag;
+  size_t count;                 // doubles (multiple of 2); 0 = no neighbour on this side
+};
+
+__global__ void __launch_bounds__(256) k_p2p_halo(HaloSide lo, HaloSide hi, nf_p2p_ctrl* ctrl, size_t stage_elems) {
+  __shared__ unsigned long long s_c;
+  __shared__ bool s_last;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_c = *(volatile unsigned long long*)&ctrl->halo_count;
+  __syncthreads();
+  const unsigned long long c = s_c, seq = c + 1;
+  const size_t slot = (size_t)(c & 1) * stage_elems;
+  const size_t g0 = (size_t)blockIdx.x * blockDim.x + tid, gs = (size_t)gridDim.x * blockDim.x;
+  // 1. push my boundary rows into the neighbours' staging slots
+  {
+    const double2* s = reinterpret_cast<const double2*>(lo.src);
+    double2* d = reinterpret_cast<double2*>(lo.remote_stage + slot);
+    for (size_t k = g0; k < lo.count / 2; k += gs) d[k] = s[k];
+    s = reinterpret_cast<const double2*>(hi.src);
+    d = reinterpret_cast<double2*>(hi.remote_stage + slot);
+    for (size_t k = g0; k < hi.count / 2; k += gs) d[k] = s[k];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned int t = atomicAdd(&ctrl->ticket[0], 1u);
+    s_last = (t == gridDim.x - 1);
+    if (s_last) {
+      __threadfence_system();
+      if (lo.count) st_flag_sys(lo.remote_flag, seq);
+      if (hi.count) st_flag_sys(hi.remote_flag, seq);
+    }
+    // 2. wait for the neighbours' rows
+    if (lo.count) wait_flag(lo.local_flag, seq, &ctrl->error);
+    if (hi.count) wait_flag(hi.local_flag, seq, &ctrl->error);
+  }
+  __syncthreads();
+  {
+    const double2* s = reinterpret_cast<const double2*>(lo.local_stage + slot);
+    double2* d = reinterpret_cast<double2*>(lo.dst);
+    for (size_t k = g0; k < lo.count / 2; k += gs) d[k] = __ldcg(s + k);
+    s = reinterpret_cast<const double2*>(hi.local_stage + slot);
+    d = reinterpret_cast<double2*>(hi.dst);
+    for (size_t k = g0; k < hi.count / 2; k += gs) d[k] = __ldcg(s + k);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    const unsigned int t = atomicAdd(&ctrl->ticket[1], 1u);
+    if (t == gridDim.x - 1) {  // everybody has read `c` and finished: advance the sequence, re-arm the tickets
+      ctrl->ticket[0] = 0u;
+      ctrl->ticket[1] = 0u;
+      *(volatile unsigned long long*)&ctrl->halo_count = c + 1;
+    }
+  }
+}
+
+struct RedPeers {
+  double* stage[NF_P2P_MAX_WORLD];              // rank q's red_stage (slot 0, row 0)
+  unsigned long long* flag[NF_P2P_MAX_WORLD];   // rank q's red_flag array
+};
+
+// sums `count` (<= 8) doubles over the ranks in rank order: identical bits on every rank
+__global__ void k_p2p_allreduce(double* buf, int count, nf_p2p_ctrl* ctrl, RedPeers peers, int rank, int world) {
+  __shared__ unsigned long long s_c;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_c = *(volatile unsigned long long*)&ctrl->red_count;
+  __syncthreads();
+  const unsigned long long c = s_c, seq = c + 1;
+  const int slot = (int)(c & 1);
+  if (tid < count) {
+    const double v = buf[tid];
+    for (int q = 0; q < world; ++q)
+      peers.stage[q][((size_t)slot * NF_P2P_MAX_WORLD + rank) * NF_P2P_RED_MAX + tid] = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid < world && tid != rank) {
+    st_flag_sys(peers.flag[tid] + rank, seq);
+    wait_flag(&ctrl->red_flag[tid], seq, &ctrl->error);
+  }
+  __syncthreads();
+  if (tid < count) {
+    double s = 0.0;
+    for (int q = 0; q < world; ++q) s += __ldcg(&ctrl->red_stage[slot][q][tid]);
+    buf[tid] = s;
+  }
+  __syncthreads();
+  if (tid == 0) *(volatile unsigned long long*)&ctrl->red_count = c + 1;
+}
+
+struct SharePeers {
+  double* array[NF_P2P_MAX_WORLD];               // rank q's copy of the replicated array
+  unsigned long long* ack[NF_P2P_MAX_WORLD];     // rank q's ack_flag array
+  unsigned long long* done[NF_P2P_MAX_WORLD];    // rank q's done_flag array
+};
+
+// replicated array: this rank computed elements [off, off+count); store them into every peer's copy.
+// Two handshakes: "entered" (the peers' earlier kernels, which may still read the array, are done) and "stored".
+__global__ void __launch_bounds__(256) k_p2p_share(const double* mine, size_t off, size_t count, nf_p2p_ctrl* ctrl,
+                                                   SharePeers peers, int rank, int world) {
+  __shared__ unsigned long long s_c;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_c = *(volatile unsigned long long*)&ctrl->share_count;
+  __syncthreads();
+  const unsigned long long c = s_c, seq = c + 1;
+  if (blockIdx.x == 0 && tid < world && tid != rank) st_flag_sys(peers.ack[tid] + rank, seq);
+  if (tid < world && tid != rank) wait_flag(&ctrl->ack_flag[tid], seq, &ctrl->error);
+  __syncthreads();
+  const size_t g0 = (size_t)blockIdx.x * blockDim.x + tid, gs = (size_t)gridDim.x * blockDim.x;
+  const double2* s = reinterpret_cast<const double2*>(mine + off);
+  for (int q = 0; q < world; ++q) {
+    if (q == rank) continue;
+    double2* d = reinterpret_cast<double2*>(peers.array[q] + off);
+    for (size_t k = g0; k < count / 2; k += gs) d[k] = s[k];
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool s_last;
+  if (tid == 0) {
+    const unsigned int t = atomicAdd(&ctrl->ticket[2], 1u);
+    s_last = (t == gridDim.x - 1);
+    if (s_last) __threadfence_system();
+  }
+  __syncthreads();
+  if (s_last && tid < world && tid != rank) st_flag_sys(peers.done[tid] + rank, seq);
+  if (tid < world && tid != rank) wait_flag(&ctrl->done_flag[tid], seq, &ctrl->error);
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    const unsigned int t = atomicAdd(&ctrl->ticket[3], 1u);
+    if (t == gridDim.x - 1) {
+      ctrl->ticket[2] = 0u;
+      ctrl->ticket[3] = 0u;
+      *(volatile unsigned long long*)&ctrl->share_count = c + 1;
+    }
+  }
+}
+
+// ---- arena ------------------------------------------------------------------------------------------------------
+int nf_nccl_allgather_bytes(nf_team* team, void* dev_buf, size_t bytes_per_rank);  // nf_slab.cu
+int nf_nccl_all_ok(nf_team* team, int ok, int* all_ok);
+
+static int p2p_new_chunk(nf_team* team, size_t bytes) {
+  nf_ctx* ctx = team->ctx;
+  nf_p2p* P = team->p2p;
+  P2PChunk ch;
+  ch.size = bytes;
+  NF_CHECK_CUDA(ctx, cudaMalloc((void**)&ch.base, bytes));
+  ch.peer[P->rank] = ch.base;
+  int ok = 1;
+  if (P->active) {
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, ch.base) != cudaSuccess) { cudaGetLastError(); ok = 0; memset(&h, 0, sizeof(h)); }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    std::vector<cudaIpcMemHandle_t> all(P->world);
+    if (!P->dbuf) NF_CHECK_CUDA(ctx, cudaMalloc(&P->dbuf, 64 * NF_P2P_MAX_WORLD));
+    NF_CHECK_CUDA(ctx, cudaMemcpyAsync((char*)P->dbuf + 64 * P->rank, &h, 64, cudaMemcpyHostToDevice, ctx->stream));
+    NF_TRY(nf_nccl_allgather_bytes(team, P->dbuf, 64));
+    NF_CHECK_CUDA(ctx, cudaMemcpyAsync(all.data(), P->dbuf, 64 * (size_t)P->world, cudaMemcpyDeviceToHost, ctx->stream));
+    NF_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int all_ok = 0;
+    NF_TRY(nf_nccl_all_ok(team, ok, &all_ok));  // nobody opens handles unless everybody could export one
+    if (all_ok) {
+      for (int q = 0; q < P->world && ok; ++q) {
+        if (q == P->rank) continue;
+        void* ptr = nullptr;
+        if (cudaIpcOpenMemHandle(&ptr, all[q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+        ch.peer[q] = (char*)ptr;
+      }
+      NF_TRY(nf_nccl_all_ok(team, ok, &all_ok));
+    }
+    if (!all_ok) {
+      for (int q = 0; q < P->world; ++q)
+        if (q != P->rank && ch.peer[q]) { cudaIpcCloseMemHandle(ch.peer[q]); ch.peer[q] = nullptr; }
+      P->active = false;  // every rank takes this branch together: NCCL exchanges from here on
+    }
+  }
+  P->chunks.push_back(ch);
+  return NF_OK;
+}
+
+static int p2p_alloc_bytes(nf_team* team, size_t bytes, void** out) {
+  nf_p2p* P = team->p2p;
+  bytes = (bytes + 255) / 256 * 256;
+  if (P->chunks.empty() || P->chunks.back().used + bytes > P->chunks.back().size) {
+    size_t want = bytes * 8;
+    if (want < ((size_t)64 << 20)) want = (size_t)64 << 20;
+    if (want > ((size_t)2 << 30)) want = (size_t)2 << 30;
+    if (want < bytes) want = bytes;
+    NF_TRY(p2p_new_chunk(team, want));
+  }
+  P2PChunk& ch = P->chunks.back();
+  *out = ch.base + ch.used;
+  ch.used += bytes;
+  return NF_OK;
+}
+
+// peer q's address of a pointer that lies in the local arena (nullptr when it does not)
+static char* p2p_translate(const nf_p2p* P, const void* ptr, int q) {
+  const char* c = (const char*)ptr;
+  for (const P2PChunk& ch : P->chunks)
+    if (c >= ch.base && c < ch.base + ch.size) return ch.peer[q] ? ch.peer[q] + (c - ch.base) : nullptr;
+  return nullptr;
+}
+
+bool nf_p2p_active(const nf_team* team) { return team->p2p && team->p2p->active; }
+
+bool nf_p2p_owns(const nf_team* team, const void* ptr) {
+  if (!team->p2p) return false;
+  const char* c = (const char*)ptr;
+  for (const P2PChunk& ch : team->p2p->chunks)
+    if (c >= ch.base && c < ch.base + ch.size) return true;
+  return false;
+}
+
+// collective over the team (called from nf_team_create_nccl): control block + staging area in chunk 0
+int nf_p2p_enable(nf_team* team, int rank, size_t max_halo_elems) {
+  nf_ctx* ctx = team->ctx;
+  if (team->world > NF_P2P_MAX_WORLD || team->world < 2 || !team->nccl) return NF_OK;
+  nf_p2p* P = new nf_p2p();
+  P->rank = rank;
+  P->world = team->world;
+  P->active = true;
+  P->stage_elems = max_halo_elems;
+  team->p2p = P;
+  void* p = nullptr;
+  const size_t ctrl_bytes = (sizeof(nf_p2p_ctrl) + 255) / 256 * 256;
+  const size_t stage_bytes = 4 * max_halo_elems * sizeof(double);
+  NF_TRY(p2p_new_chunk(team, ctrl_bytes + stage_bytes + ((size_t)32 << 20)));
+  NF_TRY(p2p_alloc_bytes(team, ctrl_bytes, &p));
+  P->ctrl = (nf_p2p_ctrl*)p;
+  NF_TRY(p2p_alloc_bytes(team, stage_bytes, &p));
+  P->stage = (double*)p;
+  NF_CHECK_CUDA(ctx, cudaMemsetAsync(P->ctrl, 0, ctrl_bytes, ctx->stream));
+  NF_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  int all_ok = 0;
+  NF_TRY(nf_nccl_all_ok(team, 1, &all_ok));  // barrier: every control block is zeroed before anybody raises a flag
+  return NF_OK;
+}
+
+void nf_p2p_destroy(nf_team* team) {
+  nf_p2p* P = team->p2p;
+  if (!P) return;
+  cudaStreamSynchronize(team->ctx->stream);
+  for (P2PChunk& ch : P->chunks) {
+    for (int q = 0; q < P->world; ++q)
+      if (q != P->rank && ch.peer[q]) cudaIpcCloseMemHandle(ch.peer[q]);
+    if (ch.base) cudaFree(ch.base);
+  }
+  if (P->dbuf) cudaFree(P->dbuf);
+  delete P;
+  team->p2p = nullptr;
+}
+
+// ---- allocation front end used by the drivers -----------------------------------------------------------------------
+// elems: what this rank needs; elems_max: maximum over the ranks (all ranks must allocate identical arena blocks)
+double* nf_team_alloc(nf_team* team, size_t elems, size_t elems_max) {
+  nf_ctx* ctx = team->ctx;
+  double* ptr = nullptr;
+  if (team->p2p) {
+    void* p = nullptr;
+    if (p2p_alloc_bytes(team, (elems_max > elems ? elems_max : elems) * sizeof(double), &p) != NF_OK) return nullptr;
+    ptr = (double*)p;
+    elems = elems_max > elems ? elems_max : elems;
+  } else if (cudaMalloc(&ptr, elems * sizeof(double)) != cudaSuccess) {
+    return nullptr;
+  }
+  cudaMemsetAsync(ptr, 0, elems * sizeof(double), ctx->stream);
+  return ptr;
+}
+
+void nf_team_release(nf_team* team, void* ptr) {
+  if (!ptr) return;
+  if (team && nf_p2p_owns(team, ptr)) return;  // arena memory goes away with the team
+  cudaFree(ptr);
+}
+
+// ---- the three collectives ------------------------------------------------------------------------------------------
+// returns NF_ERR_UNSUPPORTED when this call cannot take the peer path (caller falls back to NCCL)
+int nf_p2p_exchange(nf_team* team, const LevelGeom& geom, double* field, int depth) {
+  nf_ctx* ctx = team->ctx;
+  nf_p2p* P = team->p2p;
+  const int r = P->rank;
+  HaloSide side[2];
+  memset(side, 0, sizeof(side));
+  size_t total = 0;
+  for (int s = 0; s < 2; ++s) {  // s = 0: boundary with r-1, s = 1: boundary with r+1
+    const int q = s == 0 ? r - 1 : r + 1;
+    if (q < 0 || q >= team->world) continue;
+    const int lo = s == 0 ? q : r;  // the boundary lies between ranks lo and lo+1
+    const int B = geom.ge[lo];
+    int d = depth;
+    if (d > geom.ge[lo] - geom.gb[lo]) d = geom.ge[lo] - geom.gb[lo];
+    if (d > geom.ge[lo + 1] - geom.gb[lo + 1]) d = geom.ge[lo + 1] - geom.gb[lo + 1];
+    const size_t count = (size_t)d * geom.ld;
+    if (count == 0) continue;
+    if (count > P->stage_elems || (count & 1)) return NF_ERR_UNSUPPORTED;
+    HaloSide& H = side[s];
+    H.count = count;
+    // rows [B-d, B) are owned by lo, rows [B, B+d) by lo+1
+    if (s == 0) {  // I am lo+1: send my first d owned rows, receive rows [B-d, B)
+      H.src = field + (size_t)(B - geom.row0(r)) * geom.ld;
+      H.dst = field + (size_t)(B - d - geom.row0(r)) * geom.ld;
+    } else {       // I am lo: send my last d owned rows, receive rows [B, B+d)
+      H.src = field + (size_t)(B - d - geom.row0(r)) * geom.ld;
+      H.dst = field + (size_t)(B - geom.row0(r)) * geom.ld;
+    }
+    // the neighbour stages what comes from me in its "from upper" area when I am above it (s == 0), else "from lower"
+    char* rstage = p2p_translate(P, P->stage + (size_t)(s == 0 ? 1 : 0) * 2 * P->stage_elems, q);
+    char* rctrl = p2p_translate(P, P->ctrl, q);
+    if (!rstage || !rctrl) return NF_ERR_UNSUPPORTED;
+    H.remote_stage = (double*)rstage;
+    H.remote_flag = &((nf_p2p_ctrl*)rctrl)->halo_flag[s == 0 ? 1 : 0];
+    H.local_stage = P->stage + (size_t)s * 2 * P->stage_elems;
+    H.local_flag = &P->ctrl->halo_flag[s];
+    total += count;
+  }
+  if (total == 0) return NF_OK;
+  int blocks = (int)((total * sizeof(double) + 32767) / 32768);
+  if (blocks < 1) blocks = 1;
+  if (blocks > 32) blocks = 32;
+  k_p2p_halo<<<blocks, 256, 0, ctx->stream>>>(side[0], side[1], P->ctrl, P->stage_elems);
+  NF_LAUNCH_CHECK(ctx);
+  return NF_OK;
+}
+
+int nf_p2p_allreduce(nf_team* team, double* buf, size_t count) {
+  nf_ctx* ctx = team->ctx;
+  nf_p2p* P = team->p2p;
+  if (count > NF_P2P_RED_MAX) return NF_ERR_UNSUPPORTED;
+  RedPeers peers;
+  memset(&peers, 0, sizeof(peers));
+  for (int q = 0; q < P->world; ++q) {
+    char* rctrl = p2p_translate(P, P->ctrl, q);
+    if (!rctrl) return NF_ERR_UNSUPPORTED;
+    nf_p2p_ctrl* rc = (nf_p2p_ctrl*)rctrl;
+    peers.stage[q] = &rc->red_stage[0][0][0];
+    peers.flag[q] = rc->red_flag;
+  }
+  k_p2p_allreduce<<<1, 32, 0, ctx->stream>>>(buf, (int)count, P->ctrl, peers, P->rank, P->world);
+  NF_LAUNCH_CHECK(ctx);
+  return NF_OK;
+}
+
+int nf_p2p_share_rows(nf_team* team, int ld, int nx, const std::vector<int>& gb, const std::vector<int>& ge, double* array,
+                      int utype) {
+  nf_ctx* ctx = team->ctx;
+  nf_p2p* P = team->p2p;
+  SharePeers peers;
+  memset(&peers, 0, sizeof(peers));
+  for (int q = 0; q < P->world; ++q) {
+    char* ra = p2p_translate(P, array, q);
+    char* rctrl = p2p_translate(P, P->ctrl, q);
+    if (!ra || !rctrl) return NF_ERR_UNSUPPORTED;
+    nf_p2p_ctrl* rc = (nf_p2p_ctrl*)rctrl;
+    peers.array[q] = (double*)ra;
+    peers.ack[q] = rc->ack_flag;
+    peers.done[q] = rc->done_flag;
+  }
+  const int r = P->rank;
+  int b = gb[r], e = ge[r];
+  if (utype && r == team->world - 1) e = nx + 1;
+  const size_t off = (size_t)b * ld, count = e > b ? (size_t)(e - b) * ld : 0;
+  if ((off & 1) || (count & 1)) return NF_ERR_UNSUPPORTED;
+  int blocks = (int)((count * sizeof(double) * (P->world - 1) + 65535) / 65536);
+  if (blocks < 1) blocks = 1;
+  if (blocks > 32) blocks = 32;
+  k_p2p_share<<<blocks, 256, 0, ctx->stream>>>(array, off, count, P->ctrl, peers, r, P->world);
+  NF_LAUNCH_CHECK(ctx);
+  return NF_OK;
+}
+
+// 1 when a wait inside one of the kernels above timed out since the team was created (stream must be idle)
+int nf_p2p_error(nf_team* team) {
+  if (!team->p2p || !team->p2p->ctrl) return 0;
+  int e = 0;
+  cudaMemcpy(&e, &team->p2p->ctrl->error, sizeof(int), cudaMemcpyDeviceToHost);
+  return e;
+}

@@ -256,12 +256,16 @@ extern "C" int nf_simple_download(nf_simple* s, int which, double* host, int row
 
 // history record: [0] sum r_p^2 (or payload a), [1] sum b_p^2 (payload b), [2] sum r_u^2, [3] sum b_u^2,
 //                 [4] sum r_v^2, [5] sum b_v^2, [6] pressure iterations, [7] spare
-__global__ void k_store_hist(const double* __restrict__ scal, const double* __restrict__ pscal, double* __restrict__ rec,
-                             double pa, double pb, double iters, int p_from_scalars) {
+__global__ void k_store_hist_momentum(const double* __restrict__ scal, double* __restrict__ rec) {
+  const int t = threadIdx.x;
+  if (t >= 2 && t < 6) rec[t] = scal[t];
+}
+
+__global__ void k_store_hist_pressure(const double* __restrict__ pscal, double* __restrict__ rec, double pa, double pb,
+                                      double iters, int p_from_scalars) {
   const int t = threadIdx.x;
   if (t == 0) rec[0] = p_from_scalars ? pscal[0] : pa;
   if (t == 1) rec[1] = p_from_scalars ? pscal[1] : pb;
-  if (t >= 2 && t < 6) rec[t] = scal[t];
   if (t == 6) rec[6] = iters;
   if (t == 7) rec[7] = 0.0;
 }
@@ -292,7 +296,7 @@ static void decode_record(const nf_simple* s, const double* rec, nf_simple_info*
 }
 
 // momentum predictor of one component on every local slab (no communication, see the header comment)
-static int momentum_component(nf_simple* s, int is_u, int want_fields) {
+static int momentum_component(nf_simple* s, int is_u, double alpha, int want_fields) {
   nf_ctx* ctx = s->ctx;
   nf_team* team = s->team;
   const nf_simple_config& c = s->cfg;
@@ -304,7 +308,7 @@ static int momentum_component(nf_simple* s, int is_u, int want_fields) {
     const nf_grid g = s->geom.grid_ext(team->local[k], margin);
     const double* ubc = s->bc_clean ? S.u : S.ubc;
     const double* vbc = s->bc_clean ? S.v : S.vbc;
-    NF_TRY(nfi_momentum_links(ctx, &g, is_u, ubc, vbc, S.p, c.mu, c.alpha_u, c.sides, S.links, is_u ? S.d_u : S.d_v));
+    NF_TRY(nfi_momentum_links(ctx, &g, is_u, ubc, vbc, S.p, c.mu, alpha, c.sides, S.links, is_u ? S.d_u : S.d_v));
   }
   // sweeps: x0 = current velocity (valid NF_HALO rows out); sweep s is exact margin-1 rows out
   std::vector<const double*> src(nl);
@@ -379,26 +383,50 @@ static int momentum_component(nf_simple* s, int is_u, int want_fields) {
   return NF_OK;
 }
 
-// one outer iteration; leaves its history record in hist[slot]
-static int simple_step(nf_simple* s, int slot, int want_fields) {
+// velocities with BCs applied, used for the coefficients (jacobi_matrix_solver.py:170)
+static int refresh_bc_copies(nf_simple* s) {
+  nf_ctx* ctx = s->ctx;
+  nf_team* team = s->team;
+  if (s->bc_clean) return NF_OK;
+  for (int k = 0; k < nlocal(s); ++k) {
+    SimpleSlab& S = s->s[k];
+    const size_t bytes = s->geom.elems(team->local[k]) * sizeof(double);
+    NF_CHECK_CUDA(ctx, cudaMemcpyAsync(S.ubc, S.u, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    NF_CHECK_CUDA(ctx, cudaMemcpyAsync(S.vbc, S.v, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    const nf_grid g = s->geom.grid_ext(team->local[k], NF_HALO);
+    NF_TRY(nfi_apply_velocity_bc(ctx, &g, &s->cfg.bc, S.ubc, S.vbc));
+  }
+  return NF_OK;
+}
+
+// momentum predictor of both components from the same (u, v, p): simple.py:121-133, piso.py:58-71 / :92-104.
+// slot >= 0: the relaxed residual sums of this solve are the iteration's record (hist[slot][2..5])
+static int momentum_predictor(nf_simple* s, double alpha, int want_fields, int slot) {
+  nf_ctx* ctx = s->ctx;
+  NF_TRY(refresh_bc_copies(s));
+  NF_TRY(momentum_component(s, 1, alpha, want_fields));
+  NF_TRY(momentum_component(s, 0, alpha, want_fields));
+  if (slot < 0) return NF_OK;
+  const int nl = nlocal(s);
+  if (s->geom.dist) {  // momentum sums of all slabs (4 doubles at scal[2..5])
+    std::vector<double*> sc(nl);
+    for (int k = 0; k < nl; ++k) sc[k] = s->s[k].scal + 2;
+    NF_TRY(nf_team_allreduce(s->team, sc.data(), 4));
+  }
+  k_store_hist_momentum<<<1, 32, 0, ctx->stream>>>(s->s[0].scal, s->hist + (size_t)slot * 8);
+  NF_LAUNCH_CHECK(ctx);
+  return NF_OK;
+}
+
+// pressure correction from (u*, v*, d_u, d_v): continuity RHS, pressure solve, p = p* + alpha_p p' with zero-gradient
+// edges (p* <- p), velocity correction + BCs (simple.py:136-155, piso.py:73-90).  slot >= 0: the pressure part of the
+// iteration's record goes to hist[slot]
+static int pressure_correction(nf_simple* s, int slot) {
   nf_ctx* ctx = s->ctx;
   nf_team* team = s->team;
   const nf_simple_config& c = s->cfg;
   const int nl = nlocal(s);
   const bool dist = s->geom.dist;
-  // velocities with BCs applied, used for the coefficients (jacobi_matrix_solver.py:170)
-  if (!s->bc_clean) {
-    for (int k = 0; k < nl; ++k) {
-      SimpleSlab& S = s->s[k];
-      const size_t bytes = s->geom.elems(team->local[k]) * sizeof(double);
-      NF_CHECK_CUDA(ctx, cudaMemcpyAsync(S.ubc, S.u, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
-      NF_CHECK_CUDA(ctx, cudaMemcpyAsync(S.vbc, S.v, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
-      const nf_grid g = s->geom.grid_ext(team->local[k], NF_HALO);
-      NF_TRY(nfi_apply_velocity_bc(ctx, &g, &c.bc, S.ubc, S.vbc));
-    }
-  }
-  NF_TRY(momentum_component(s, 1, want_fields));
-  NF_TRY(momentum_component(s, 0, want_fields));  // same u, v, p*: simple.py:128-133
   // pressure correction
   std::vector<nf_grid> gp(nl);
   for (int k = 0; k < nl; ++k) {
@@ -460,13 +488,10 @@ static int simple_step(nf_simple* s, int slot, int want_fields) {
       break;
     }
   }
-  if (dist) {  // momentum sums of all slabs (4 doubles at scal[2..5])
-    std::vector<double*> sc(nl);
-    for (int k = 0; k < nl; ++k) sc[k] = s->s[k].scal + 2;
-    NF_TRY(nf_team_allreduce(team, sc.data(), 4));
+  if (slot >= 0) {
+    k_store_hist_pressure<<<1, 32, 0, ctx->stream>>>(pscal, s->hist + (size_t)slot * 8, pa, pb, iters, p_from_scalars);
+    NF_LAUNCH_CHECK(ctx);
   }
-  k_store_hist<<<1, 32, 0, ctx->stream>>>(s->s[0].scal, pscal, s->hist + (size_t)slot * 8, pa, pb, iters, p_from_scalars);
-  NF_LAUNCH_CHECK(ctx);
   // p = p* + alpha_p p' with zero-gradient edges; p* <- p.  velocity correction + BCs.
   for (int k = 0; k < nl; ++k) {
     SimpleSlab& S = s->s[k];
@@ -482,6 +507,22 @@ static int simple_step(nf_simple* s, int slot, int want_fields) {
     NF_TRY(nf_team_exchange(team, s->geom, v.data(), NF_HALO));
   }
   s->bc_clean = true;
+  return NF_OK;
+}
+
+
+// one outer iteration; leaves its history record in hist[slot].
+// SIMPLE (simple.py:114-212): predictor, one pressure correction.  PISO (piso.py:53-110, cfg.piso_corrections >= 1):
+// predictor with alpha_u, then n corrections; between corrections the momentum equations are solved again from the
+// corrected (u, v, p) without relaxation, their norms are discarded (:92-104).
+static int simple_step(nf_simple* s, int slot, int want_fields) {
+  const nf_simple_config& c = s->cfg;
+  NF_TRY(momentum_predictor(s, c.alpha_u, want_fields, slot));
+  const int nc = c.piso_corrections >= 1 ? c.piso_corrections : 1;
+  for (int k = 0; k < nc; ++k) {
+    NF_TRY(pressure_correction(s, k == nc - 1 ? slot : -1));
+    if (k < nc - 1) NF_TRY(momentum_predictor(s, 1.0, 0, -1));
+  }
   return NF_OK;
 }
 

@@ -56,6 +56,9 @@ def assemble_rows(arr, begin, end, device=None):
 
 
 class GpuSimpleSolver:
+    _piso_corrections = 0          # 0: SIMPLE; GpuPisoSolver sets n_corrections
+    _history_appends_per_iteration = 2  # the reference appends twice (simple.py:177, :196)
+
     def __init__(self, mesh, fluid, pressure_solver=None, momentum_solver=None, velocity_updater=None,
                  boundary_conditions=None, alpha_p=0.3, alpha_u=0.7, fix_lid_corners=False, device=None,
                  distributed=None, virtual_ranks=1):
@@ -147,6 +150,7 @@ class GpuSimpleSolver:
         c.n_momentum_sweeps = ms.n_jacobi_sweeps
         ps = self.pressure_solver
         c.krylov_maxiter = 0
+        c.piso_corrections = int(self._piso_corrections)
         c.pressure_iterations = 0
         c.pressure_omega = 1.0
         c.pressure_tolerance = 0.0
@@ -333,8 +337,7 @@ class GpuSimpleSolver:
                     self.y_momentum_rel_norms.append(r["v_rel_norm"])
                     self.pressure_rel_norms.append(r["p_rel_norm"])
                     self.pressure_iterations_history.append(r["pressure_iterations"])
-                    self.residual_history.append(total)
-                    self.residual_history.append(total)  # the reference appends twice (simple.py:177, :196)
+                    self.residual_history.extend([total] * self._history_appends_per_iteration)
                 iteration += len(recs)
                 if track_infinity_norm and (iteration - 1) % infinity_norm_interval == 0:
                     self.pull_fields()
@@ -356,3 +359,22 @@ class GpuSimpleSolver:
         if self.infinity_norm_history:
             result.add_history("infinity_norm_error", self.infinity_norm_history)
         return result
+
+
+class GpuPisoSolver(GpuSimpleSolver):
+    """Twin of ``PisoSolver(BaseAlgorithm)`` (solver/Algorithms/piso.py:9-175): predictor with alpha_u, then
+    ``n_corrections`` x (pressure solve, p = p* + alpha_p p' with zero-gradient edges, velocity correction); between
+    corrections both momentum equations are solved again from the corrected (u, v, p) with relaxation factor 1
+    (:92-104).  The recorded norms are the predictor's and the last correction's (:107-109); ``residual_history``
+    gets one entry per iteration (:119).  Same device loop as GpuSimpleSolver (``nf_simple_config.piso_corrections``)."""
+    _history_appends_per_iteration = 1
+
+    def __init__(self, mesh, fluid, pressure_solver=None, momentum_solver=None, velocity_updater=None,
+                 boundary_conditions=None, alpha_p=0.3, alpha_u=0.7, n_corrections=2, **kw):
+        if int(n_corrections) < 1:
+            # range(0) in piso.py:73 leaves p_res_info unbound -> UnboundLocalError at :108; refuse up front
+            raise ValueError("n_corrections must be >= 1")
+        self.n_corrections = int(n_corrections)
+        self._piso_corrections = self.n_corrections
+        super().__init__(mesh, fluid, pressure_solver, momentum_solver, velocity_updater, boundary_conditions,
+                         alpha_p=alpha_p, alpha_u=alpha_u, **kw)

@@ -381,3 +381,70 @@ def test_slab_decomposition_with_tma_smoother_and_fused_residuals(n, ranks, k, m
     assert out[0][2] == out[1][2]
     np.testing.assert_array_equal(out[0][0], out[1][0])
     np.testing.assert_array_equal(out[0][1], out[1][1])
+
+
+def run_gpu_piso(n, Re, name, k, N, nc, **kw):
+    import naviflow_b200 as nb
+    mesh, fluid = cavity(n, Re)
+    alg = nb.GpuPisoSolver(mesh, fluid, make_ps(name), nb.GpuJacobiMomentumSolver(n_jacobi_sweeps=k),
+                           nb.GpuVelocityUpdater(), alpha_p=0.3, alpha_u=0.7, n_corrections=nc, **kw)
+    alg.set_boundary_condition("top", "velocity", {"u": 1.0, "v": 0.0})
+    for b in ("bottom", "left", "right"):
+        alg.set_boundary_condition(b, "wall")
+    res = alg.solve(max_iterations=N, tolerance=0.0, save_profile=False, track_infinity_norm=False)
+    return alg, res
+
+
+@pytest.mark.parametrize("n,Re,k,N,nc,name", [(31, 100, 5, 15, 2, "v"), (31, 100, 5, 15, 3, "rbsor"), (63, 1000, 10, 8, 2, "v")])
+def test_piso_loop_vs_reference_golden(golden_dir, n, Re, k, N, nc, name):
+    """PISO outer loop (Algorithms/piso.py:53-135); u, v, p after N iterations equal the reference's
+    PisoSolver run to 1e-10 relative L2, one residual-history entry per iteration."""
+    g = load(golden_dir, "piso_runs.npz")
+    key = f"n{n}_Re{Re}_k{k}_N{N}_c{nc}_{name}"
+    alg, res = run_gpu_piso(n, Re, name, k, N, nc)
+    for fld in ("u", "v", "p"):
+        e = rel(getattr(alg, fld), g[f"{key}_{fld}"])
+        assert e < 1e-10, (fld, e)
+    hist = res.get_history("total_rel_norm")
+    assert len(hist) == N and res.iterations == N
+    np.testing.assert_allclose(hist, g[key + "_hist"], rtol=1e-8)
+
+
+def test_piso_loop_vs_oracle_fresh_config():
+    """Same loop against the NumPy oracle on a configuration that is not in the golden file (odd size, 4 corrections,
+    Jacobi pressure solver); PISO with one correction is SIMPLE."""
+    import naviflow_b200 as nb
+    n, Re, k, N, nc = 45, 400, 7, 6, 4
+    alg, res = run_gpu_piso(n, Re, "jacobi", k, N, nc)
+    st, h = O.piso_solve(n, n, Re, O.make_pressure_solver("jacobi", omega=0.8, n_iter=50), n_sweeps=k, n_corrections=nc,
+                         max_iterations=N, tolerance=0.0)
+    for fld in ("u", "v", "p"):
+        assert rel(getattr(alg, fld), getattr(st, fld)) < 1e-11, fld
+    np.testing.assert_allclose(res.get_history("total_rel_norm"), h["total_rel_norm"], rtol=1e-9)
+    np.testing.assert_allclose(res.get_history("p_rel_norm"), h["p_rel_norm"], rtol=1e-7)
+    one, _ = run_gpu_piso(63, 1000, "v", 5, 5, 1)
+    simple, _ = run_gpu_simple(63, 1000, "v", 5, 5)
+    for fld in ("u", "v", "p"):
+        np.testing.assert_array_equal(getattr(one, fld), getattr(simple, fld), err_msg=fld)
+    with pytest.raises(ValueError):
+        nb.GpuPisoSolver(*cavity(31, 100), make_ps("v"), n_corrections=0)
+
+
+def test_piso_slab_decomposition_is_bit_identical():
+    import naviflow_b200 as nb
+
+    def run(ranks):
+        mesh, fluid = cavity(385, 1000)
+        ps = nb.GpuMultiGridSolver(smoother=nb.GpuGaussSeidelSolver(omega=1.5), max_iterations=3, tolerance=1e-30,
+                                   pre_smoothing=3, post_smoothing=3)
+        alg = nb.GpuPisoSolver(mesh, fluid, ps, nb.GpuJacobiMomentumSolver(n_jacobi_sweeps=5), alpha_p=0.3, alpha_u=0.7,
+                               n_corrections=2, virtual_ranks=ranks)
+        alg.set_boundary_condition("top", "velocity", {"u": 1.0, "v": 0.0})
+        for b in ("bottom", "left", "right"):
+            alg.set_boundary_condition(b, "wall")
+        alg.solve(max_iterations=3, tolerance=0.0)
+        return alg
+
+    ref, alg = run(1), run(3)
+    for fld in ("u", "v", "p"):
+        np.testing.assert_array_equal(getattr(alg, fld), getattr(ref, fld), err_msg=fld)
