@@ -247,6 +247,13 @@ int nf_nccl_unique_id(nf_ctx*, void* id_out_128_bytes);
 int nf_team_create_nccl(nf_ctx*, int world, int rank, const void* id_128_bytes, nf_team** out);
 int nf_team_create_virtual(nf_ctx*, int virtual_ranks, nf_team** out);
 int nf_team_free(nf_team*);
+/* 1 when the team's halo exchanges / norm reductions run as the ranks' own kernels over NVLink peer memory (cudaIpc
+ * arena, default for nf_team_create_nccl with world <= 8; NF_P2P=0 or a failed cudaIpc set-up selects NCCL) */
+int nf_team_uses_p2p(nf_team*);
+/* collective micro-benchmark of the team's transport: mean time of `reps` halo exchanges of `depth` rows of an
+ * nx x ny level and of `reps` all-reduces of n_scalars doubles (CUDA events; tools/bench_exchange.py) */
+int nf_team_benchmark(nf_team*, int nx, int ny, int depth, int n_scalars, int reps, double* ms_exchange,
+                      double* ms_allreduce);
 /* host-only partition queries: cell rows [begin, end) of `rank` when nx rows are cut over `world` ranks (boundaries
  * on multiples of 16; the grid is not cut when a slab would have fewer than 64 rows), and the rows of the
  * next-coarser level a rank restricts into (coarse row I belongs to the owner of fine row 2I+1) */

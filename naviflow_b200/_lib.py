@@ -127,6 +127,8 @@ SIGNATURES = {
     "nf_team_create_nccl": (C.c_int, [CTX, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
     "nf_team_create_virtual": (C.c_int, [CTX, C.c_int, C.POINTER(C.c_void_p)]),
     "nf_team_free": (C.c_int, [C.c_void_p]),
+    "nf_team_uses_p2p": (C.c_int, [C.c_void_p]),
+    "nf_team_benchmark": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, DBL_OUT, DBL_OUT]),
     "nf_slab_rows": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "nf_slab_coarse_rows": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "nf_simple_create_team": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(NfSimpleConfig)]),

@@ -279,22 +279,23 @@ extern "C" int nf_mg_destroy(nf_mg* mg) {
   if (!mg) return NF_OK;
   cudaSetDevice(mg->ctx->device);
   cudaStreamSynchronize(mg->ctx->stream);
+  nf_team* tm = mg->team;
   for (MgLevel& L : mg->lv) {
     for (MgSlab& S : L.s) {
-      if (S.owns_x && S.x) cudaFree(S.x);
-      if (S.x2) cudaFree(S.x2);
-      if (S.owns_b && S.b) cudaFree(S.b);
-      if (S.r) cudaFree(S.r);
-      if (S.owns_d) { if (S.d_u) cudaFree(S.d_u); if (S.d_v) cudaFree(S.d_v); }
-      if (S.inv) cudaFree(S.inv);
+      if (S.owns_x) nf_team_release(tm, S.x);
+      nf_team_release(tm, S.x2);
+      if (S.owns_b) nf_team_release(tm, S.b);
+      nf_team_release(tm, S.r);
+      if (S.owns_d) { nf_team_release(tm, S.d_u); nf_team_release(tm, S.d_v); }
+      nf_team_release(tm, S.inv);
     }
     if (L.band) cudaFree(L.band);
     if (L.start) cudaFree(L.start);
     if (L.ptmp) cudaFree(L.ptmp);
   }
-  for (double* p : mg->coarse_A) if (p) cudaFree(p);
-  for (double* p : mg->coarse_inv) if (p) cudaFree(p);
-  for (double* p : mg->scal) if (p) cudaFree(p);
+  for (double* p : mg->coarse_A) nf_team_release(tm, p);
+  for (double* p : mg->coarse_inv) nf_team_release(tm, p);
+  for (double* p : mg->scal) nf_team_release(tm, p);
   if (mg->scal_host) cudaFreeHost(mg->scal_host);
   for (cudaEvent_t e : mg->ev) cudaEventDestroy(e);
   if (mg->graph_exec) cudaGraphExecDestroy(mg->graph_exec);
@@ -304,10 +305,9 @@ extern "C" int nf_mg_destroy(nf_mg* mg) {
   return NF_OK;
 }
 
-static bool dev_alloc(nf_ctx* ctx, double** p, size_t elems) {
-  if (cudaMalloc(p, elems * sizeof(double)) != cudaSuccess) return false;
-  cudaMemsetAsync(*p, 0, elems * sizeof(double), ctx->stream);
-  return true;
+static bool dev_alloc(nf_team* team, double** p, size_t elems, size_t elems_max) {
+  *p = nf_team_alloc(team, elems, elems_max);
+  return *p != nullptr;
 }
 
 // level-0 geometry of a team (shared with the SIMPLE driver)
@@ -376,19 +376,24 @@ int nfi_mg_create(nf_team* team, nf_mg** out, int nx, int ny, int ld, const nf_m
     nf_mg_destroy(mg);
     return NF_ERR_UNSUPPORTED;
   }
+  if (mg->lv[0].geom.dist) {  // peer-memory halo staging (no-op without p2p)
+    int st = nf_p2p_reserve_stage(team, (size_t)NF_HALO * mg->lv[0].geom.ld);
+    if (st != NF_OK) { nf_mg_destroy(mg); return st; }
+  }
   bool ok = true;
   for (size_t l = 0; l < mg->lv.size() && ok; ++l) {
     MgLevel& L = mg->lv[l];
     L.s.resize(nl);
     for (int k = 0; k < nl && ok; ++k) {
       MgSlab& S = L.s[k];
-      const size_t e = L.geom.elems(team->local[k]);
-      ok = ok && dev_alloc(ctx, &S.r, e) && dev_alloc(ctx, &S.x2, e);
+      const size_t e = L.geom.elems(team->local[k]), em = L.geom.max_elems();
+      ok = ok && dev_alloc(team, &S.r, e, em) && dev_alloc(team, &S.x2, e, em);
       if (l > 0) {
-        ok = ok && dev_alloc(ctx, &S.x, e) && dev_alloc(ctx, &S.b, e) && dev_alloc(ctx, &S.d_u, e) && dev_alloc(ctx, &S.d_v, e);
+        ok = ok && dev_alloc(team, &S.x, e, em) && dev_alloc(team, &S.b, e, em) && dev_alloc(team, &S.d_u, e, em) &&
+             dev_alloc(team, &S.d_v, e, em);
         S.owns_x = S.owns_b = S.owns_d = true;
       }
-      if (cfg->smoother == 0) ok = ok && dev_alloc(ctx, &S.inv, e);
+      if (cfg->smoother == 0) ok = ok && dev_alloc(team, &S.inv, e, em);
     }
     if (ok && need_cubic && l + 1 < mg->lv.size()) {
       const int mc = mg->lv[l + 1].geom.nx, m = L.geom.nx;
@@ -416,8 +421,9 @@ int nfi_mg_create(nf_team* team, nf_mg** out, int nx, int ny, int ld, const nf_m
   mg->coarse_inv.assign(nl, nullptr);
   mg->scal.assign(nl, nullptr);
   for (int k = 0; k < nl && ok; ++k)
-    ok = dev_alloc(ctx, &mg->coarse_A[k], (size_t)mg->coarse_N * mg->coarse_N) &&
-         dev_alloc(ctx, &mg->coarse_inv[k], (size_t)mg->coarse_N * mg->coarse_N) && dev_alloc(ctx, &mg->scal[k], 8);
+    ok = dev_alloc(team, &mg->coarse_A[k], (size_t)mg->coarse_N * mg->coarse_N, (size_t)mg->coarse_N * mg->coarse_N) &&
+         dev_alloc(team, &mg->coarse_inv[k], (size_t)mg->coarse_N * mg->coarse_N, (size_t)mg->coarse_N * mg->coarse_N) &&
+         dev_alloc(team, &mg->scal[k], 8, 8);
   ok = ok && cudaMallocHost(&mg->scal_host, 8 * sizeof(double)) == cudaSuccess;
   if (!ok) {
     ctx->err = std::string("multigrid allocation failed: ") + cudaGetErrorString(cudaGetLastError());

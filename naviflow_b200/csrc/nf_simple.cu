@@ -72,7 +72,7 @@ extern "C" int nf_simple_destroy(nf_simple* s) {
   cudaStreamSynchronize(s->ctx->stream);
   if (s->mg) nf_mg_destroy(s->mg);
   for (SimpleSlab& S : s->s)
-    for (double* ptr : S.owned) cudaFree(ptr);
+    for (double* ptr : S.owned) nf_team_release(s->team, ptr);
   if (s->hist) cudaFree(s->hist);
   if (s->hist_host) cudaFreeHost(s->hist_host);
   if (s->owns_team) nf_team_destroy(s->team);
@@ -80,11 +80,9 @@ extern "C" int nf_simple_destroy(nf_simple* s) {
   return NF_OK;
 }
 
-static double* alloc_elems(nf_simple* s, SimpleSlab& S, size_t elems) {
-  double* ptr = nullptr;
-  if (cudaMalloc(&ptr, elems * sizeof(double)) != cudaSuccess) return nullptr;
-  cudaMemsetAsync(ptr, 0, elems * sizeof(double), s->ctx->stream);
-  S.owned.push_back(ptr);
+static double* alloc_elems(nf_simple* s, SimpleSlab& S, size_t elems, size_t elems_max) {
+  double* ptr = nf_team_alloc(s->team, elems, elems_max);
+  if (ptr) S.owned.push_back(ptr);
   return ptr;
 }
 
@@ -115,6 +113,11 @@ int nfi_simple_create(nf_team* team, nf_simple** out, const nf_simple_config* cf
   }
   const int nl = (int)team->local.size();
   s->s.resize(nl);
+  if (s->geom.dist) {  // peer-memory halo staging for the deepest exchange of the finest level (no-op without p2p)
+    int st = nf_p2p_reserve_stage(team, (size_t)NF_HALO * s->geom.ld);
+    if (st != NF_OK) { delete s; return st; }
+  }
+  const size_t emax = s->geom.max_elems();
   bool ok = true;
   for (int k = 0; k < nl && ok; ++k) {
     SimpleSlab& S = s->s[k];
@@ -123,12 +126,12 @@ int nfi_simple_create(nf_team* team, nf_simple** out, const nf_simple_config* cf
                          &S.d_u, &S.d_v, &S.pp, &S.b, &S.pres, &S.ures, &S.vres, &S.tmp,
                          &S.links.a_e, &S.links.a_w, &S.links.a_n, &S.links.a_s, &S.links.a_p, &S.links.src};
     for (double** f : fields) {
-      *f = alloc_elems(s, S, e);
+      *f = alloc_elems(s, S, e, emax);
       if (!*f) { ok = false; break; }
     }
-    if (ok) { S.scal = alloc_elems(s, S, 8); ok = S.scal != nullptr; }
+    if (ok) { S.scal = alloc_elems(s, S, 8, 8); ok = S.scal != nullptr; }
     if (ok && cfg->pressure_solver >= 3) {
-      S.kwork = alloc_elems(s, S, e * (cfg->pressure_solver == 3 ? 4 : 5));
+      S.kwork = alloc_elems(s, S, e * (cfg->pressure_solver == 3 ? 4 : 5), emax * (cfg->pressure_solver == 3 ? 4 : 5));
       ok = S.kwork != nullptr;
     }
     S.u_star = S.ua;
@@ -561,5 +564,9 @@ extern "C" int nf_simple_iterate(nf_simple* s, int n_iterations, double toleranc
       for (int it = 0; it < done; ++it) decode_record(s, s->hist_host + (size_t)it * 8, &info_host[it]);
   }
   if (n_done) *n_done = done;
+  if (s->team->p2p && done > 0 && nf_p2p_error(s->team)) {
+    ctx->err = "peer-memory exchange timed out: the ranks of the team did not run the same sequence of exchanges";
+    return NF_ERR_CUDA;
+  }
   return NF_OK;
 }

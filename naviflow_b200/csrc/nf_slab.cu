@@ -11,7 +11,7 @@
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 typedef int ncclResult_t;
-enum { ncclFloat64_ = 8, ncclSum_ = 0 };
+enum { ncclUint8_ = 1, ncclInt32_ = 2, ncclFloat64_ = 8, ncclSum_ = 0, ncclMin_ = 3 };
 struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId*);
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
@@ -22,6 +22,7 @@ struct NcclApi {
   ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t);
   ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t);
   ncclResult_t (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t);
   const char* (*GetErrorString)(ncclResult_t);
   bool ok = false;
 };
@@ -43,6 +44,7 @@ static NcclApi* nccl_api() {
       *(void**)&api.Recv = dlsym(h, "ncclRecv");
       *(void**)&api.AllReduce = dlsym(h, "ncclAllReduce");
       *(void**)&api.Broadcast = dlsym(h, "ncclBroadcast");
+      *(void**)&api.AllGather = dlsym(h, "ncclAllGather");
       *(void**)&api.GetErrorString = dlsym(h, "ncclGetErrorString");
       api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.GroupStart && api.GroupEnd && api.Send &&
                api.Recv && api.AllReduce && api.Broadcast;
@@ -103,6 +105,10 @@ int nf_team_exchange(nf_team* team, const LevelGeom& geom, double* const* fields
   static const bool skip = getenv("NF_SKIP_EXCHANGE") != nullptr;  // timing experiments only: results are wrong
   if (skip) return NF_OK;
   if (depth > geom.halo) depth = geom.halo;
+  if (nf_p2p_active(team)) {  // one kernel per rank over NVLink peer memory (nf_p2p.cu)
+    const int st = nf_p2p_exchange(team, geom, fields[0], depth);
+    if (st != NF_ERR_UNSUPPORTED) return st;
+  }
   NcclApi* api = team->nccl ? nccl_api() : nullptr;
   if (api) NF_NCCL(ctx, api->GroupStart());
   for (int r = 0; r + 1 < team->world; ++r) {
@@ -148,6 +154,10 @@ __global__ void k_accumulate(double* __restrict__ dst, const double* __restrict_
 int nf_team_allreduce(nf_team* team, double* const* bufs, size_t count) {
   nf_ctx* ctx = team->ctx;
   if (team->world <= 1 || count == 0) return NF_OK;
+  if (nf_p2p_active(team)) {
+    const int st = nf_p2p_allreduce(team, bufs[0], count);
+    if (st != NF_ERR_UNSUPPORTED) return st;
+  }
   if (team->nccl) {
     NcclApi* api = nccl_api();
     NF_NCCL(ctx, api->AllReduce(bufs[0], bufs[0], count, ncclFloat64_, ncclSum_, (ncclComm_t)team->nccl, ctx->stream));
@@ -168,6 +178,10 @@ int nf_team_share_rows(nf_team* team, int ld, int nx, const std::vector<int>& gb
                        double* const* arrays, int utype) {
   nf_ctx* ctx = team->ctx;
   if (team->world <= 1) return NF_OK;
+  if (nf_p2p_active(team)) {
+    const int st = nf_p2p_share_rows(team, ld, nx, gb, ge, arrays[0], utype);
+    if (st != NF_ERR_UNSUPPORTED) return st;
+  }
   NcclApi* api = team->nccl ? nccl_api() : nullptr;
   if (api) NF_NCCL(ctx, api->GroupStart());
   for (int r = 0; r < team->world; ++r) {
@@ -187,6 +201,35 @@ int nf_team_share_rows(nf_team* team, int ld, int nx, const std::vector<int>& gb
     }
   }
   if (api) NF_NCCL(ctx, api->GroupEnd());
+  return NF_OK;
+}
+
+// ---- small NCCL collectives used while the peer-memory path is set up (nf_p2p.cu) ----------------------------------------
+// in-place all-gather: rank r's bytes_per_rank bytes sit at dev_buf + r * bytes_per_rank
+int nf_nccl_allgather_bytes(nf_team* team, void* dev_buf, size_t bytes_per_rank) {
+  nf_ctx* ctx = team->ctx;
+  NcclApi* api = nccl_api();
+  NF_REQUIRE(ctx, team->nccl && api->AllGather, "no NCCL communicator / ncclAllGather");
+  int rank = team->local[0];
+  NF_NCCL(ctx, api->AllGather((char*)dev_buf + (size_t)rank * bytes_per_rank, dev_buf, bytes_per_rank, ncclUint8_,
+                              (ncclComm_t)team->nccl, ctx->stream));
+  return NF_OK;
+}
+
+// *all_ok = 1 iff ok != 0 on every rank (also a barrier of the team's streams and hosts)
+int nf_nccl_all_ok(nf_team* team, int ok, int* all_ok) {
+  nf_ctx* ctx = team->ctx;
+  NcclApi* api = nccl_api();
+  NF_REQUIRE(ctx, team->nccl != nullptr, "no NCCL communicator");
+  int* d = nullptr;
+  NF_CHECK_CUDA(ctx, cudaMalloc(&d, sizeof(int)));
+  NF_CHECK_CUDA(ctx, cudaMemcpyAsync(d, &ok, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  NF_NCCL(ctx, api->AllReduce(d, d, 1, ncclInt32_, ncclMin_, (ncclComm_t)team->nccl, ctx->stream));
+  int v = 0;
+  NF_CHECK_CUDA(ctx, cudaMemcpyAsync(&v, d, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  NF_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaFree(d);
+  *all_ok = v;
   return NF_OK;
 }
 
@@ -225,10 +268,20 @@ extern "C" int nf_team_create_nccl(nf_ctx* ctx, int world, int rank, const void*
     ncclResult_t r = api->CommInitRank(&comm, world, id, rank);
     if (r != 0) { delete t; ctx->err = "ncclCommInitRank failed"; return NF_ERR_CUDA; }
     t->nccl = comm;
+    // exchanges by the ranks' own kernels over NVLink peer memory unless NF_P2P=0 (then, or when cudaIpc is not
+    // available, grouped ncclSend/ncclRecv)
+    const char* env = getenv("NF_P2P");
+    if (!(env && env[0] == '0') && api->AllGather) {
+      int st = nf_p2p_enable(t, rank);
+      if (st != NF_OK) { nf_team_destroy(t); return st; }
+    }
   }
   *out = t;
   return NF_OK;
 }
+
+// 1: halos / norms travel through peer memory (nf_p2p.cu), 0: through NCCL or in-process copies
+extern "C" int nf_team_uses_p2p(nf_team* t) { return t && nf_p2p_active(t) ? 1 : 0; }
 
 extern "C" int nf_team_create_virtual(nf_ctx* ctx, int virtual_ranks, nf_team** out) {
   return nf_team_create_local(ctx, virtual_ranks, out);
@@ -236,6 +289,7 @@ extern "C" int nf_team_create_virtual(nf_ctx* ctx, int virtual_ranks, nf_team** 
 
 int nf_team_destroy(nf_team* t) {
   if (!t) return NF_OK;
+  nf_p2p_destroy(t);
   if (t->nccl) {
     NcclApi* api = nccl_api();
     if (api->ok) api->CommDestroy((ncclComm_t)t->nccl);
@@ -265,5 +319,49 @@ extern "C" int nf_slab_coarse_rows(int fine_begin, int next_fine_begin, int is_l
   nf_coarsen_split(gbf, gef, nxc, gb, ge);
   if (row_begin) *row_begin = gb[0];
   if (row_end) *row_end = is_last ? nxc : ge[0];
+  return NF_OK;
+}
+
+// Times `reps` back-to-back halo exchanges of `depth` rows (and, if n_scalars > 0, all-reduces of n_scalars doubles) of
+// an nx x ny level cut over the team, with CUDA events on the context's stream; the transport is the team's
+// (peer-memory kernels or NCCL).  Collective.  Used by tools/bench_exchange.py.
+extern "C" int nf_team_benchmark(nf_team* team, int nx, int ny, int depth, int n_scalars, int reps, double* ms_exchange,
+                                 double* ms_allreduce) {
+  if (!team) return NF_ERR_ARG;
+  nf_ctx* ctx = team->ctx;
+  NF_REQUIRE(ctx, team->local.size() == 1 && team->world > 1, "needs a team of separate processes");
+  LevelGeom g;
+  g.nx = nx; g.ny = ny; g.ld = nf_pad_ld(ny);
+  g.dist = nf_split_rows(nx, team->world, 64, g.gb, g.ge);
+  g.halo = g.dist ? NF_HALO : 0;
+  NF_REQUIRE(ctx, g.dist, "grid too small to be cut");
+  NF_TRY(nf_p2p_reserve_stage(team, (size_t)NF_HALO * g.ld));
+  double* f = nf_team_alloc(team, g.elems(team->local[0]), g.max_elems());
+  double* sc = nf_team_alloc(team, 8, 8);
+  NF_REQUIRE(ctx, f && sc, "allocation failed");
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  float ms = 0.f;
+  for (int pass = 0; pass < 2; ++pass) {  // pass 0 warms up
+    NF_CHECK_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+    for (int k = 0; k < reps; ++k) NF_TRY(nf_team_exchange(team, g, &f, depth));
+    NF_CHECK_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+    NF_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ms, e0, e1);
+  }
+  if (ms_exchange) *ms_exchange = ms / reps;
+  ms = 0.f;
+  if (n_scalars > 0)
+    for (int pass = 0; pass < 2; ++pass) {
+      NF_CHECK_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+      for (int k = 0; k < reps; ++k) NF_TRY(nf_team_allreduce(team, &sc, (size_t)n_scalars));
+      NF_CHECK_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+      NF_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      cudaEventElapsedTime(&ms, e0, e1);
+    }
+  if (ms_allreduce) *ms_allreduce = ms / reps;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  nf_team_release(team, f);
+  nf_team_release(team, sc);
   return NF_OK;
 }

@@ -15,11 +15,14 @@
 
 #define NF_HALO 8  // rows of halo kept on each side of a distributed slab
 
+struct nf_p2p;  // peer-memory exchange state (nf_p2p.cu)
+
 struct nf_team {
   nf_ctx* ctx = nullptr;
   int world = 1;               // number of ranks the grid is cut into
   std::vector<int> local;      // global ids of the ranks living in this process (1 entry under torchrun)
   void* nccl = nullptr;        // ncclComm_t when world > 1 and the ranks are separate processes
+  nf_p2p* p2p = nullptr;       // NVLink peer-memory path of the exchanges (separate processes, world <= 8)
   bool is_local(int r) const { for (int q : local) if (q == r) return true; return false; }
   int slot_of(int r) const { for (size_t k = 0; k < local.size(); ++k) if (local[k] == r) return (int)k; return -1; }
 };
@@ -35,6 +38,11 @@ struct LevelGeom {
   int row0(int r) const { return dist ? (gb[r] - halo > 0 ? gb[r] - halo : 0) : 0; }
   int row1(int r) const { return dist ? (ge[r] + halo + 1 < nx + 1 ? ge[r] + halo + 1 : nx + 1) : nx + 1; }
   size_t elems(int r) const { return (size_t)(row1(r) - row0(r)) * ld; }
+  size_t max_elems() const {  // largest slab of the level (peer-memory arenas allocate the same size on every rank)
+    size_t m = 0;
+    for (size_t r = 0; r < gb.size(); ++r) m = elems((int)r) > m ? elems((int)r) : m;
+    return m ? m : (size_t)(nx + 1) * ld;
+  }
   nf_grid grid(int r) const {
     nf_grid g;
     g.nx = nx; g.ny = ny; g.ld = ld; g.row0 = row0(r); g.gb = gb[r]; g.ge = ge[r]; g.row1 = row1(r); g.pad = 0;
@@ -74,3 +82,20 @@ int nf_team_share_rows(nf_team* team, int ld, int nx, const std::vector<int>& gb
 // communicator plumbing (C-ABI wrappers in nf_slab.cu)
 int nf_team_create_local(nf_ctx* ctx, int virtual_ranks, nf_team** out);
 int nf_team_destroy(nf_team* team);
+
+// ---- device memory of a team ------------------------------------------------------------------------------------
+// Fields that take part in exchanges are allocated through the team: plain cudaMalloc normally, the peer-visible arena
+// (nf_p2p.cu) when the ranks are separate processes.  elems = what this rank needs, elems_max = the maximum over the
+// ranks (arena blocks must be identical on all ranks).  Zero-initialised (asynchronously on the context's stream).
+double* nf_team_alloc(nf_team* team, size_t elems, size_t elems_max);
+void nf_team_release(nf_team* team, void* ptr);
+// peer-memory path (all collective over the team)
+int nf_p2p_enable(nf_team* team, int rank);
+int nf_p2p_reserve_stage(nf_team* team, size_t halo_elems);  // staging for halo exchanges of up to halo_elems doubles
+void nf_p2p_destroy(nf_team* team);
+bool nf_p2p_active(const nf_team* team);
+int nf_p2p_exchange(nf_team* team, const LevelGeom& geom, double* field, int depth);
+int nf_p2p_allreduce(nf_team* team, double* buf, size_t count);
+int nf_p2p_share_rows(nf_team* team, int ld, int nx, const std::vector<int>& gb, const std::vector<int>& ge, double* array,
+                      int utype);
+int nf_p2p_error(nf_team* team);

@@ -232,6 +232,12 @@ class GpuSimpleSolver:
                 lib.nf_team_free(self._team)
             self._state, self._state_key, self._team = None, None, None
 
+    def uses_p2p(self):
+        """True when the slab exchanges of this solver run as peer-memory kernels over NVLink (nf_p2p.cu), False when
+        they go through NCCL or when the solver is not cut over processes."""
+        ctx, _ = self._ensure_state()
+        return self._team is not None and bool(ctx.lib.nf_team_uses_p2p(self._team))
+
     def local_rows(self):
         """Cell rows [begin, end) this process owns (the whole grid unless distributed over processes)."""
         ctx, st = self._ensure_state()

@@ -1,5 +1,7 @@
 #!/usr/bin/env python
-"""torchrun --nproc-per-node N tools/check_multi_gpu.py [n]: the NCCL slab run equals the single-GPU run bit for bit."""
+"""torchrun --nproc-per-node N tools/check_multi_gpu.py [n]: the slab run over N GPUs equals the single-GPU run bit for
+bit, with the exchanges as peer-memory kernels (default) and as NCCL send/recv (NF_P2P=0); SIMPLE and PISO; prints the
+time per outer iteration of both transports."""
 import os
 import sys
 
@@ -10,18 +12,30 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 
-def run(n, distributed, virtual_ranks=1, iters=3):
+def run(n, distributed, virtual_ranks=1, iters=3, piso=0, timed=0):
+    import time
     import naviflow_b200 as nb
     mesh = nb.StructuredMesh(n, n, 1.0, 1.0)
     fluid = nb.FluidProperties(density=1.0, reynolds_number=1000, characteristic_velocity=1.0)
     ps = nb.GpuMultiGridSolver(smoother=nb.GpuGaussSeidelSolver(omega=1.5), max_iterations=3, tolerance=1e-30,
                                pre_smoothing=3, post_smoothing=3)
-    alg = nb.GpuSimpleSolver(mesh, fluid, ps, nb.GpuJacobiMomentumSolver(n_jacobi_sweeps=5), distributed=distributed,
-                             virtual_ranks=virtual_ranks)
+    cls, kw = (nb.GpuPisoSolver, dict(n_corrections=piso)) if piso else (nb.GpuSimpleSolver, {})
+    alg = cls(mesh, fluid, ps, nb.GpuJacobiMomentumSolver(n_jacobi_sweeps=5), distributed=distributed,
+              virtual_ranks=virtual_ranks, **kw)
     alg.set_boundary_condition("top", "velocity", {"u": 1.0, "v": 0.0})
     for b in ("bottom", "left", "right"):
         alg.set_boundary_condition(b, "wall")
     res = alg.solve(max_iterations=iters, tolerance=0.0)
+    alg.ms_per_iteration = None
+    if timed:
+        alg.iterate_resident(2)
+        torch.cuda.synchronize()
+        if dist.is_initialized():
+            dist.barrier()
+        t0 = time.perf_counter()
+        alg.iterate_resident(timed)
+        torch.cuda.synchronize()
+        alg.ms_per_iteration = (time.perf_counter() - t0) * 1e3 / timed
     return alg, res
 
 
@@ -31,12 +45,21 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     rank, world = dist.get_rank(), dist.get_world_size()
-    alg, res = run(n, True)
-    rows = alg.local_rows()
     ref, rres = run(n, False)
-    ok = all(np.array_equal(getattr(alg, f), getattr(ref, f)) for f in ("u", "v", "p"))
-    hist_ok = np.allclose(res.get_history("total_rel_norm"), rres.get_history("total_rel_norm"), rtol=1e-12)
-    print(f"rank {rank}/{world} rows {rows} fields_bit_identical={ok} history_close={hist_ok}", flush=True)
+    ok_all = True
+    for label, env, piso in (("p2p", "1", 0), ("nccl", "0", 0), ("p2p-piso2", "1", 2)):
+        os.environ["NF_P2P"] = env
+        alg, res = run(n, True, piso=piso, timed=0 if piso else 10)
+        if piso:
+            ref, rres = run(n, False, piso=piso)
+        rows = alg.local_rows()
+        ok = all(np.array_equal(getattr(alg, f), getattr(ref, f)) for f in ("u", "v", "p"))
+        hist_ok = np.allclose(res.get_history("total_rel_norm"), rres.get_history("total_rel_norm"), rtol=1e-12)
+        ok_all = ok_all and ok and hist_ok and (alg.uses_p2p() == (env == "1"))
+        print(f"[{label}] rank {rank}/{world} rows {rows} uses_p2p={alg.uses_p2p()} fields_bit_identical={ok} "
+              f"history_close={hist_ok} ms_per_iteration={alg.ms_per_iteration}", flush=True)
+        del alg
+    ok = hist_ok = ok_all
     flag = torch.tensor([int(ok and hist_ok)], device=f"cuda:{local}")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
