@@ -345,8 +345,10 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": dict(workload_config(args, n),
                            parallelism="single GPU" if world == 1 else
-                           f"{world} row slabs, one rank per GPU; NCCL send/recv halos (8 rows), allreduce norms, "
-                           f"coarse multigrid levels replicated"),
+                           f"{world} row slabs, one rank per GPU; halos (8 rows) and norm reductions by "
+                           + ("the ranks' own kernels over NVLink peer memory (nf_p2p.cu)" if alg.uses_p2p() else
+                              "NCCL send/recv + allreduce")
+                           + ", coarse multigrid levels replicated"),
             "gpu_launches": int(launches), "mg_cycles_per_step": float(np.mean(cycles)) if cycles else None,
             "final_u_rel_norm": recs[-1]["u_rel_norm"] if recs else None,
             "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,

@@ -60,6 +60,14 @@ __device__ __forceinline__ size_t nf_idx(const nf_grid& g, int i, int j) {
   return (size_t)(i - g.row0) * (size_t)g.ld + (size_t)j;
 }
 
+// Rows a descriptor's arrays hold: [g.row0, nf_stored_end(g)) (row1 == 0 means the whole grid, nx+1 rows).  Tiled
+// kernels whose last tile overshoots the computed range must not load rows outside this window: on a slab the rows
+// beyond it are not allocated.
+__device__ __host__ __forceinline__ int nf_stored_end(const nf_grid& g) { return g.row1 > 0 ? g.row1 : g.nx + 1; }
+__device__ __host__ __forceinline__ bool nf_row_stored(const nf_grid& g, int i) {
+  return i >= g.row0 && i < nf_stored_end(g);
+}
+
 // 2-D launch geometry: x along j (contiguous), y along rows
 struct NfLaunch2D {
   dim3 grid, block;

@@ -58,7 +58,7 @@ k_momentum_fused(nf_grid g, nf_links L, const double* __restrict__ xin, double* 
     for (int k = 0; k < KS; ++k) {
       const int r = ty + NYT * k;
       const int gi = i0 + r;
-      const bool rin = gi >= 0 && gi < rows;
+      const bool rin = gi >= 0 && gi < rows && nf_row_stored(g, gi);  // rows outside the slab's storage: never needed
       in0[k] = rin && gj0 >= 0 && gj0 < cols;
       in1[k] = rin && gj0 + 1 >= 0 && gj0 + 1 < cols;
       ae0[k] = aw0[k] = an0[k] = as0[k] = di0[k] = b0[k] = 0.0;

@@ -198,7 +198,8 @@ k_rbsor_fused(nf_grid g, const double* __restrict__ pin, double* __restrict__ po
   for (int k = 0; k < KS; ++k) {
     const int r = ty + NYT * k;
     const int gi = i0 + r;
-    const bool row_in = (gi >= 0 && gi < g.nx);
+    // rows gi and gi+1 (d_u) must lie inside the slab's storage; the overshoot rows of the last tile are never needed
+    const bool row_in = (gi >= 0 && gi < g.nx) && nf_row_stored(g, gi) && nf_row_stored(g, gi + 1);
     const bool in0 = row_in && gj0 >= 0 && gj0 < g.ny;
     const bool in1 = row_in && gj0 + 1 >= 0 && gj0 + 1 < g.ny;
     double vp0 = 0.0, vp1 = 0.0, vb0 = 0.0, vb1 = 0.0;

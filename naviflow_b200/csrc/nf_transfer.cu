@@ -48,7 +48,10 @@ k_residual_restrict_fw(nf_grid gf, const double* __restrict__ p, const double* _
     for (int fc = tx; fc < 2 * RR_CC + 1; fc += 128) {
       const int j = fj0 + fc;
       double rv = 0.0;
-      if (i < gf.nx && j < gf.ny) rv = b[nf_idx(gf, i, j)] - nf_Ap_cell(gf, p, d_u, d_v, i, j);
+      // fine rows 2I..2I+2 of the coarse rows this launch writes; the last tile's overshoot is neither needed nor
+      // (on a slab) stored
+      if (i < gf.nx && j < gf.ny && i <= 2 * gc.ge && (i == 0 || nf_row_stored(gf, i - 1)) && nf_row_stored(gf, i + 1))
+        rv = b[nf_idx(gf, i, j)] - nf_Ap_cell(gf, p, d_u, d_v, i, j);
       sR[fr][fc] = rv;
     }
   }

@@ -448,3 +448,20 @@ def test_piso_slab_decomposition_is_bit_identical():
     ref, alg = run(1), run(3)
     for fld in ("u", "v", "p"):
         np.testing.assert_array_equal(getattr(alg, fld), getattr(ref, fld), err_msg=fld)
+
+
+def test_uneven_slabs_do_not_read_outside_their_storage():
+    """Regression: with slabs of unequal height (5793 rows over 8 ranks: 720 / 736 rows) the last tile of the fused
+    momentum / smoother / residual+restriction kernels overshoots the computed rows; it must not load rows outside the
+    slab's allocation (this configuration used to fail with an illegal memory access)."""
+    import naviflow_b200 as nb
+    mesh, fluid = cavity(5793, 1000)
+    ps = nb.GpuMultiGridSolver(smoother=nb.GpuGaussSeidelSolver(omega=1.5), max_iterations=100, tolerance=1e-3,
+                               pre_smoothing=3, post_smoothing=3)
+    alg = nb.GpuSimpleSolver(mesh, fluid, ps, nb.GpuJacobiMomentumSolver(n_jacobi_sweeps=5), virtual_ranks=8)
+    alg.set_boundary_condition("top", "velocity", {"u": 1.0, "v": 0.0})
+    for b in ("bottom", "left", "right"):
+        alg.set_boundary_condition(b, "wall")
+    alg.push_fields()
+    recs = alg.iterate_resident(2, 0.0)
+    assert len(recs) == 2 and np.isfinite(recs[-1]["u_rel_norm"]) and recs[-1]["pressure_iterations"] > 0
