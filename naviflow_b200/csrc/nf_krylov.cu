@@ -13,6 +13,7 @@
 #include <math.h>
 
 #include "nf_pressure.cuh"
+#include "nf_slab.cuh"
 
 struct KState {
   double rho, rho_prev, alpha, omega, beta;
@@ -38,6 +39,75 @@ __device__ __forceinline__ double nf_Ap_cell_f(const nf_grid& g, const double* _
   return out;
 }
 
+// ---- scalar epilogues of the reductions (one thread).  Single slab: run by the last block of the reducing kernel.
+// Slab-decomposed: the kernel leaves its partial sums in out[], the team all-reduces them and k_krylov_epilogue runs
+// the same code (every rank holds an identical copy of the state). -------------------------------------------------
+enum { EP_INIT = 0, EP_CG_PQ, EP_CG_UPDATE, EP_BI_V, EP_BI_S, EP_BI_T, EP_BI_X };
+
+__device__ __forceinline__ void ep_init(KState* st, const double* out, double atol, double rtol) {
+  const double bn = sqrt(out[0]);
+  st->bnorm = bn;
+  st->atol = fmax(atol, rtol * bn);
+  st->rr = out[0];
+  st->rho = out[0];
+  st->rho_prev = 0.0;
+  st->alpha = 0.0;
+  st->omega = 0.0;
+  st->beta = 0.0;
+  st->half = 0;
+  st->iters = 0;
+  st->info = 0;
+  // bnorm == 0: scipy returns x = b (= 0) immediately; ||r|| < atol at the top of iteration 0
+  st->done = (bn == 0.0 || bn < st->atol) ? 1 : 0;
+  if (!st->done && fabs(st->rho) < 4.930380657631324e-32) { st->done = 1; st->info = -10; }  // bicgstab rhotol = eps^2
+}
+__device__ __forceinline__ void ep_cg_pq(KState* st, const double* out) { st->alpha = st->rho / out[0]; }
+__device__ __forceinline__ void ep_cg_update(KState* st, const double* out, int it) {
+  const double rr = out[0];
+  st->rr = rr;
+  st->iters = it + 1;
+  st->rho_prev = st->rho;
+  st->rho = rr;
+  st->beta = rr / st->rho_prev;
+  if (sqrt(rr) < st->atol) { st->done = 1; st->info = 0; }
+}
+__device__ __forceinline__ void ep_bi_v(KState* st, const double* out, int it) {
+  const double rv = out[0];
+  if (rv == 0.0) { st->done = 1; st->info = -11; st->iters = it; }
+  else st->alpha = st->rho / rv;
+}
+__device__ __forceinline__ void ep_bi_s(KState* st, const double* out) {
+  st->rr = out[0];
+  st->half = (sqrt(out[0]) < st->atol) ? 1 : 0;
+}
+__device__ __forceinline__ void ep_bi_t(KState* st, const double* out) { st->omega = out[0] / out[1]; }
+__device__ __forceinline__ void ep_bi_x(KState* st, const double* out, int it) {
+  const double alpha = st->alpha, omega = st->omega;
+  st->iters = it + 1;
+  if (st->half) { st->done = 1; st->info = 0; return; }
+  st->rr = out[0];
+  st->rho_prev = st->rho;
+  st->rho = out[1];
+  const double eps2 = 4.930380657631324e-32;  // np.finfo(float64).eps ** 2
+  if (sqrt(out[0]) < st->atol) { st->done = 1; st->info = 0; }
+  else if (fabs(st->rho) < eps2) { st->done = 1; st->info = -10; }
+  else if (fabs(omega) < eps2) { st->done = 1; st->info = -11; }
+  else st->beta = (st->rho / st->rho_prev) * (alpha / omega);
+}
+
+__global__ void k_krylov_epilogue(int which, KState* st, const double* out, int it, double atol, double rtol) {
+  if (which == EP_INIT) { ep_init(st, out, atol, rtol); return; }
+  if (st->done) return;
+  switch (which) {
+    case EP_CG_PQ: ep_cg_pq(st, out); break;
+    case EP_CG_UPDATE: ep_cg_update(st, out, it); break;
+    case EP_BI_V: ep_bi_v(st, out, it); break;
+    case EP_BI_S: ep_bi_s(st, out); break;
+    case EP_BI_T: if (!st->half) ep_bi_t(st, out); break;
+    case EP_BI_X: ep_bi_x(st, out, it); break;
+  }
+}
+
 #define NF_ROWLOOP(g, i) \
   _Pragma("unroll 2") for (int i = (g).gb + blockIdx.y * blockDim.y + threadIdx.y; i < (g).ge; i += gridDim.y * blockDim.y)
 
@@ -46,7 +116,7 @@ __device__ __forceinline__ double nf_Ap_cell_f(const nf_grid& g, const double* _
 // ---------------------------------------------------------------------------------------------
 __global__ void k_krylov_init(nf_grid g, const double* __restrict__ b, double* __restrict__ r,
                               double* __restrict__ rt, double* __restrict__ x, KState* st, double atol, double rtol,
-                              double* partials, unsigned int* ticket, double* out) {
+                              int defer, double* partials, unsigned int* ticket, double* out) {
   double acc[1] = {0.0};
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j < g.ny) {
@@ -59,62 +129,53 @@ __global__ void k_krylov_init(nf_grid g, const double* __restrict__ b, double* _
       acc[0] += v * v;
     }
   }
-  if (nf_block_reduce_store<1>(acc, partials, ticket, out)) {
-    const double bn = sqrt(out[0]);
-    st->bnorm = bn;
-    st->atol = fmax(atol, rtol * bn);
-    st->rr = out[0];
-    st->rho = out[0];
-    st->rho_prev = 0.0;
-    st->alpha = 0.0;
-    st->omega = 0.0;
-    st->beta = 0.0;
-    st->half = 0;
-    st->iters = 0;
-    st->info = 0;
-    // bnorm == 0: scipy returns x = b (= 0) immediately; ||r|| < atol at the top of iteration 0
-    st->done = (bn == 0.0 || bn < st->atol) ? 1 : 0;
-    if (!st->done && fabs(st->rho) < 4.930380657631324e-32) { st->done = 1; st->info = -10; }  // bicgstab rhotol = eps^2
-  }
+  if (nf_block_reduce_store<1>(acc, partials, ticket, out) && !defer) ep_init(st, out, atol, rtol);
 }
 
 // ---------------------------------------------------------------------------------------------
 // CG.  scipy order: z = r; rho = r.z; p = z + beta p; q = A p; alpha = rho/(p.q); x += alpha p; r -= alpha q
 // ---------------------------------------------------------------------------------------------
 // kernel 1: p_new = r + beta*p_old (first iteration: p_new = r), q = A p_new, pq = p_new.q ; epilogue alpha
+// ext = 1 (slab-decomposed): p_new is also written on one row beyond the owned ones (r's halo is exchanged once per
+// iteration, p's halo maintains itself this way); q and the dot product cover the owned rows only
 __global__ void k_cg_pq(nf_grid g, const double* __restrict__ r, const double* __restrict__ p_old,
                         double* __restrict__ p_new, double* __restrict__ q, const double* __restrict__ d_u,
-                        const double* __restrict__ d_v, KState* st, int first, double* partials,
+                        const double* __restrict__ d_v, KState* st, int first, int ext, int defer, double* partials,
                         unsigned int* ticket, double* out) {
   if (st->done) return;
   const double beta = st->beta;
   double acc[1] = {0.0};
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j < g.ny) {
-    NF_ROWLOOP(g, i) {
+    const int lo = (ext && g.gb > 0) ? g.gb - 1 : g.gb, hi = (ext && g.ge < g.nx) ? g.ge + 1 : g.ge;
+#pragma unroll 2
+    for (int i = lo + blockIdx.y * blockDim.y + threadIdx.y; i < hi; i += gridDim.y * blockDim.y) {
       const size_t k = nf_idx(g, i, j);
-      double pc, qc;
+      const bool owned = i >= g.gb && i < g.ge;
+      double pc, qc = 0.0;
       if (first) {
         auto f = [&](size_t kk) { return r[kk]; };
         pc = f(k);
-        qc = nf_Ap_cell_f(g, d_u, d_v, i, j, f);
+        if (owned) qc = nf_Ap_cell_f(g, d_u, d_v, i, j, f);
       } else {
         auto f = [&](size_t kk) { return p_old[kk] * beta + r[kk]; };  // p *= beta; p += z
         pc = f(k);
-        qc = nf_Ap_cell_f(g, d_u, d_v, i, j, f);
+        if (owned) qc = nf_Ap_cell_f(g, d_u, d_v, i, j, f);
       }
       p_new[k] = pc;
-      q[k] = qc;
-      acc[0] += pc * qc;
+      if (owned) {
+        q[k] = qc;
+        acc[0] += pc * qc;
+      }
     }
   }
-  if (nf_block_reduce_store<1>(acc, partials, ticket, out)) st->alpha = st->rho / out[0];
+  if (nf_block_reduce_store<1>(acc, partials, ticket, out) && !defer) ep_cg_pq(st, out);
 }
 
 // kernel 2: x += alpha p; r -= alpha q; rr = r.r ; epilogue: stopping test, rho, beta
 __global__ void k_cg_update(nf_grid g, double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p,
-                            const double* __restrict__ q, KState* st, int it, double* partials, unsigned int* ticket,
-                            double* out) {
+                            const double* __restrict__ q, KState* st, int it, int defer, double* partials,
+                            unsigned int* ticket, double* out) {
   if (st->done) return;
   const double alpha = st->alpha;
   double acc[1] = {0.0};
@@ -128,15 +189,7 @@ __global__ void k_cg_update(nf_grid g, double* __restrict__ x, double* __restric
       acc[0] += rn * rn;
     }
   }
-  if (nf_block_reduce_store<1>(acc, partials, ticket, out)) {
-    const double rr = out[0];
-    st->rr = rr;
-    st->iters = it + 1;
-    st->rho_prev = st->rho;
-    st->rho = rr;
-    st->beta = rr / st->rho_prev;
-    if (sqrt(rr) < st->atol) { st->done = 1; st->info = 0; }
-  }
+  if (nf_block_reduce_store<1>(acc, partials, ticket, out) && !defer) ep_cg_update(st, out, it);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -157,7 +210,7 @@ __global__ void k_bi_p(nf_grid g, const double* __restrict__ r, double* __restri
 
 // v = A p; rv = rtilde.v ; epilogue alpha = rho/rv (rv == 0 -> breakdown -11)
 __global__ void k_bi_v(nf_grid g, const double* __restrict__ p, double* __restrict__ v, const double* __restrict__ rt,
-                       const double* __restrict__ d_u, const double* __restrict__ d_v, KState* st, int it,
+                       const double* __restrict__ d_u, const double* __restrict__ d_v, KState* st, int it, int defer,
                        double* partials, unsigned int* ticket, double* out) {
   if (st->done) return;
   double acc[1] = {0.0};
@@ -170,16 +223,12 @@ __global__ void k_bi_v(nf_grid g, const double* __restrict__ p, double* __restri
       acc[0] += rt[k] * vc;
     }
   }
-  if (nf_block_reduce_store<1>(acc, partials, ticket, out)) {
-    const double rv = out[0];
-    if (rv == 0.0) { st->done = 1; st->info = -11; st->iters = it; }
-    else st->alpha = st->rho / rv;
-  }
+  if (nf_block_reduce_store<1>(acc, partials, ticket, out) && !defer) ep_bi_v(st, out, it);
 }
 
 // s = r - alpha v (in place); ss = s.s ; epilogue: ||s|| < atol -> half-step exit
-__global__ void k_bi_s(nf_grid g, double* __restrict__ r, const double* __restrict__ v, KState* st, double* partials,
-                       unsigned int* ticket, double* out) {
+__global__ void k_bi_s(nf_grid g, double* __restrict__ r, const double* __restrict__ v, KState* st, int defer,
+                       double* partials, unsigned int* ticket, double* out) {
   if (st->done) return;
   const double alpha = st->alpha;
   double acc[1] = {0.0};
@@ -192,16 +241,13 @@ __global__ void k_bi_s(nf_grid g, double* __restrict__ r, const double* __restri
       acc[0] += s * s;
     }
   }
-  if (nf_block_reduce_store<1>(acc, partials, ticket, out)) {
-    st->rr = out[0];
-    st->half = (sqrt(out[0]) < st->atol) ? 1 : 0;
-  }
+  if (nf_block_reduce_store<1>(acc, partials, ticket, out) && !defer) ep_bi_s(st, out);
 }
 
 // t = A s; ts = t.s, tt = t.t ; epilogue omega = ts/tt
 __global__ void k_bi_t(nf_grid g, const double* shat, const double* s, double* __restrict__ t,
-                       const double* __restrict__ d_u, const double* __restrict__ d_v, KState* st, double* partials,
-                       unsigned int* ticket, double* out) {
+                       const double* __restrict__ d_u, const double* __restrict__ d_v, KState* st, int defer,
+                       double* partials, unsigned int* ticket, double* out) {
   if (st->done || st->half) return;
   double acc[2] = {0.0, 0.0};
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -214,7 +260,7 @@ __global__ void k_bi_t(nf_grid g, const double* shat, const double* s, double* _
       acc[1] += tc * tc;
     }
   }
-  if (nf_block_reduce_store<2>(acc, partials, ticket, out)) st->omega = out[0] / out[1];
+  if (nf_block_reduce_store<2>(acc, partials, ticket, out) && !defer) ep_bi_t(st, out);
 }
 
 // x += alpha p; x += omega s; r = s - omega t; rr = r.r; rho' = rtilde.r ; epilogue: top-of-loop tests of the
@@ -222,7 +268,7 @@ __global__ void k_bi_t(nf_grid g, const double* shat, const double* s, double* _
 // phat / shat: the preconditioned directions (== p / s without a preconditioner)
 __global__ void k_bi_x(nf_grid g, double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p,
                        const double* __restrict__ shat, const double* __restrict__ t, const double* __restrict__ rt,
-                       KState* st, int it, double* partials, unsigned int* ticket, double* out) {
+                       KState* st, int it, int defer, double* partials, unsigned int* ticket, double* out) {
   if (st->done) return;
   const double alpha = st->alpha, omega = st->omega;
   const int half = st->half;
@@ -244,18 +290,7 @@ __global__ void k_bi_x(nf_grid g, double* __restrict__ x, double* __restrict__ r
       }
     }
   }
-  if (nf_block_reduce_store<2>(acc, partials, ticket, out)) {
-    st->iters = it + 1;
-    if (half) { st->done = 1; st->info = 0; return; }
-    st->rr = out[0];
-    st->rho_prev = st->rho;
-    st->rho = out[1];
-    const double eps2 = 4.930380657631324e-32;  // np.finfo(float64).eps ** 2
-    if (sqrt(out[0]) < st->atol) { st->done = 1; st->info = 0; }
-    else if (fabs(st->rho) < eps2) { st->done = 1; st->info = -10; }
-    else if (fabs(omega) < eps2) { st->done = 1; st->info = -11; }
-    else st->beta = (st->rho / st->rho_prev) * (alpha / omega);
-  }
+  if (nf_block_reduce_store<2>(acc, partials, ticket, out) && !defer) ep_bi_x(st, out, it);
 }
 
 // =============================================================================================
@@ -302,17 +337,17 @@ extern "C" int nf_cg_solve(nf_ctx* ctx, const nf_grid* g, const double* b, doubl
   KState *st, *hst;
   krylov_state(ctx, &st, &hst);
   NfLaunch2D l = nf_launch_reduce(g->ge - g->gb, g->ny);
-  k_krylov_init<<<l.grid, l.block, 0, ctx->stream>>>(*g, b, r, nullptr, x, st, atol, rtol, ctx->partials, ctx->ticket,
-                                                     ctx->scalars);
+  k_krylov_init<<<l.grid, l.block, 0, ctx->stream>>>(*g, b, r, nullptr, x, st, atol, rtol, 0, ctx->partials,
+                                                     ctx->ticket, ctx->scalars);
   NF_LAUNCH_CHECK(ctx);
   int cur = 0;
   int it = 0;
   for (; it < maxiter; ++it) {
-    k_cg_pq<<<l.grid, l.block, 0, ctx->stream>>>(*g, r, pbuf[cur], pbuf[cur ^ 1], q, d_u, d_v, st, it == 0,
+    k_cg_pq<<<l.grid, l.block, 0, ctx->stream>>>(*g, r, pbuf[cur], pbuf[cur ^ 1], q, d_u, d_v, st, it == 0, 0, 0,
                                                  ctx->partials, ctx->ticket, ctx->scalars);
     NF_LAUNCH_CHECK(ctx);
     cur ^= 1;
-    k_cg_update<<<l.grid, l.block, 0, ctx->stream>>>(*g, x, r, pbuf[cur], q, st, it, ctx->partials, ctx->ticket,
+    k_cg_update<<<l.grid, l.block, 0, ctx->stream>>>(*g, x, r, pbuf[cur], q, st, it, 0, ctx->partials, ctx->ticket,
                                                      ctx->scalars);
     NF_LAUNCH_CHECK(ctx);
     if ((it + 1) % check_every == 0) {
@@ -338,23 +373,23 @@ static int bicgstab_impl(nf_ctx* ctx, const nf_grid* g, const double* b, double*
   KState *st, *hst;
   krylov_state(ctx, &st, &hst);
   NfLaunch2D l = nf_launch_reduce(g->ge - g->gb, g->ny);
-  k_krylov_init<<<l.grid, l.block, 0, ctx->stream>>>(*g, b, r, rt, x, st, atol, rtol, ctx->partials, ctx->ticket,
+  k_krylov_init<<<l.grid, l.block, 0, ctx->stream>>>(*g, b, r, rt, x, st, atol, rtol, 0, ctx->partials, ctx->ticket,
                                                      ctx->scalars);
   NF_LAUNCH_CHECK(ctx);
   for (int it = 0; it < maxiter; ++it) {
     k_bi_p<<<l.grid, l.block, 0, ctx->stream>>>(*g, r, p, v, st, it == 0);
     NF_LAUNCH_CHECK(ctx);
     if (mg) NF_TRY(nfi_mg_apply(mg, p, phat, mg_cycles, mg_kind));
-    k_bi_v<<<l.grid, l.block, 0, ctx->stream>>>(*g, phat, v, rt, d_u, d_v, st, it, ctx->partials, ctx->ticket,
+    k_bi_v<<<l.grid, l.block, 0, ctx->stream>>>(*g, phat, v, rt, d_u, d_v, st, it, 0, ctx->partials, ctx->ticket,
                                                 ctx->scalars);
     NF_LAUNCH_CHECK(ctx);
-    k_bi_s<<<l.grid, l.block, 0, ctx->stream>>>(*g, r, v, st, ctx->partials, ctx->ticket, ctx->scalars);
+    k_bi_s<<<l.grid, l.block, 0, ctx->stream>>>(*g, r, v, st, 0, ctx->partials, ctx->ticket, ctx->scalars);
     NF_LAUNCH_CHECK(ctx);
     if (mg) NF_TRY(nfi_mg_apply(mg, r, shat, mg_cycles, mg_kind));
-    k_bi_t<<<l.grid, l.block, 0, ctx->stream>>>(*g, shat ? shat : r, r, t, d_u, d_v, st, ctx->partials, ctx->ticket,
+    k_bi_t<<<l.grid, l.block, 0, ctx->stream>>>(*g, shat ? shat : r, r, t, d_u, d_v, st, 0, ctx->partials, ctx->ticket,
                                                 ctx->scalars);
     NF_LAUNCH_CHECK(ctx);
-    k_bi_x<<<l.grid, l.block, 0, ctx->stream>>>(*g, x, r, phat, shat, t, rt, st, it, ctx->partials, ctx->ticket,
+    k_bi_x<<<l.grid, l.block, 0, ctx->stream>>>(*g, x, r, phat, shat, t, rt, st, it, 0, ctx->partials, ctx->ticket,
                                                 ctx->scalars);
     NF_LAUNCH_CHECK(ctx);
     if ((it + 1) % check_every == 0) {
@@ -386,4 +421,121 @@ extern "C" int nf_bicgstab_solve_mg(nf_ctx* ctx, const nf_grid* g, const double*
   NF_REQUIRE(ctx, b && x && d_u && d_v && work && mg, "NULL argument");
   NF_REQUIRE(ctx, maxiter >= 0 && mg_cycles >= 1 && mg_kind >= 0 && mg_kind <= 2, "bad iteration arguments");
   return bicgstab_impl(ctx, g, b, x, d_u, d_v, atol, rtol, maxiter, check_every, work, mg, mg_cycles, mg_kind, info);
+}
+
+// =============================================================================================
+// Slab-decomposed CG / BiCGSTAB (kind 0 / 1): the same kernels per slab; every reduction leaves its partial sums in
+// the slab's scratch (state[k] + 32), the team all-reduces them (peer-memory kernel or NCCL: BASELINE north_star "dot
+// products use allreduce") and k_krylov_epilogue advances the slab's copy of the state.  One halo exchange of one row
+// per operator application.  The summation order of the dot products depends on the cut, so the iterates agree with
+// the single-slab run to rounding, not bit for bit.
+// state[k]: 64 device doubles per local slab; work[k]: 4 (CG) / 5 (BiCGSTAB) slab-sized arrays.
+// =============================================================================================
+int nfi_krylov_team(nf_team* team, const LevelGeom& geom, int kind, double* const* b, double* const* x, double* const* d_u,
+                    double* const* d_v, double atol, double rtol, int maxiter, int check_every, double* const* work,
+                    double* const* state, nf_krylov_info* info) {
+  nf_ctx* ctx = team->ctx;
+  const int nl = (int)team->local.size();
+  if (check_every < 1) check_every = 1;
+  std::vector<nf_grid> g(nl);
+  std::vector<NfLaunch2D> l(nl);
+  std::vector<KState*> st(nl);
+  std::vector<double*> out(nl), r(nl), a1(nl), a2(nl), a3(nl), a4(nl);
+  for (int k = 0; k < nl; ++k) {
+    const int rk = team->local[k];
+    g[k] = geom.grid(rk);
+    g[k].rho = 1.0;  // the pressure solvers hard-code rho = 1 (matrix_free_BiCGSTAB.py)
+    l[k] = nf_launch_reduce(g[k].ge - g[k].gb + 2, g[k].ny);
+    st[k] = reinterpret_cast<KState*>(state[k]);
+    out[k] = state[k] + 32;
+    const size_t n = geom.elems(rk);
+    r[k] = work[k]; a1[k] = work[k] + n; a2[k] = work[k] + 2 * n; a3[k] = work[k] + 3 * n;
+    a4[k] = kind == 1 ? work[k] + 4 * n : nullptr;
+  }
+  auto reduce_epilogue = [&](int which, int count, int it) -> int {
+    NF_TRY(nf_team_allreduce(team, out.data(), (size_t)count));
+    for (int k = 0; k < nl; ++k) {
+      k_krylov_epilogue<<<1, 1, 0, ctx->stream>>>(which, st[k], out[k], it, atol, rtol);
+      NF_LAUNCH_CHECK(ctx);
+    }
+    return NF_OK;
+  };
+  auto poll = [&](KState* host) -> int {
+    NF_CHECK_CUDA(ctx, cudaMemcpyAsync(host, st[0], sizeof(KState), cudaMemcpyDeviceToHost, ctx->stream));
+    NF_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return NF_OK;
+  };
+  KState* hst = reinterpret_cast<KState*>(ctx->scalars_host + 16);
+  for (int k = 0; k < nl; ++k) {
+    k_krylov_init<<<l[k].grid, l[k].block, 0, ctx->stream>>>(g[k], b[k], r[k], kind == 1 ? a1[k] : nullptr, x[k], st[k],
+                                                             atol, rtol, 1, ctx->partials, ctx->ticket, out[k]);
+    NF_LAUNCH_CHECK(ctx);
+  }
+  NF_TRY(reduce_epilogue(EP_INIT, 1, 0));
+  if (kind == 0) {
+    std::vector<double*> pb[2] = {a1, a2};
+    std::vector<double*>& q = a3;
+    NF_TRY(nf_team_exchange(team, geom, r.data(), 1));
+    int cur = 0;
+    for (int it = 0; it < maxiter; ++it) {
+      for (int k = 0; k < nl; ++k) {
+        k_cg_pq<<<l[k].grid, l[k].block, 0, ctx->stream>>>(g[k], r[k], pb[cur][k], pb[cur ^ 1][k], q[k], d_u[k], d_v[k],
+                                                           st[k], it == 0, 1, 1, ctx->partials, ctx->ticket, out[k]);
+        NF_LAUNCH_CHECK(ctx);
+      }
+      NF_TRY(reduce_epilogue(EP_CG_PQ, 1, it));
+      cur ^= 1;
+      for (int k = 0; k < nl; ++k) {
+        k_cg_update<<<l[k].grid, l[k].block, 0, ctx->stream>>>(g[k], x[k], r[k], pb[cur][k], q[k], st[k], it, 1,
+                                                               ctx->partials, ctx->ticket, out[k]);
+        NF_LAUNCH_CHECK(ctx);
+      }
+      NF_TRY(reduce_epilogue(EP_CG_UPDATE, 1, it));
+      NF_TRY(nf_team_exchange(team, geom, r.data(), 1));
+      if ((it + 1) % check_every == 0) {
+        NF_TRY(poll(hst));
+        if (hst->done) break;
+      }
+    }
+  } else {
+    std::vector<double*>&rt = a1, &p = a2, &v = a3, &t = a4;
+    for (int it = 0; it < maxiter; ++it) {
+      for (int k = 0; k < nl; ++k) {
+        k_bi_p<<<l[k].grid, l[k].block, 0, ctx->stream>>>(g[k], r[k], p[k], v[k], st[k], it == 0);
+        NF_LAUNCH_CHECK(ctx);
+      }
+      NF_TRY(nf_team_exchange(team, geom, p.data(), 1));
+      for (int k = 0; k < nl; ++k) {
+        k_bi_v<<<l[k].grid, l[k].block, 0, ctx->stream>>>(g[k], p[k], v[k], rt[k], d_u[k], d_v[k], st[k], it, 1,
+                                                          ctx->partials, ctx->ticket, out[k]);
+        NF_LAUNCH_CHECK(ctx);
+      }
+      NF_TRY(reduce_epilogue(EP_BI_V, 1, it));
+      for (int k = 0; k < nl; ++k) {
+        k_bi_s<<<l[k].grid, l[k].block, 0, ctx->stream>>>(g[k], r[k], v[k], st[k], 1, ctx->partials, ctx->ticket, out[k]);
+        NF_LAUNCH_CHECK(ctx);
+      }
+      NF_TRY(reduce_epilogue(EP_BI_S, 1, it));
+      NF_TRY(nf_team_exchange(team, geom, r.data(), 1));
+      for (int k = 0; k < nl; ++k) {
+        k_bi_t<<<l[k].grid, l[k].block, 0, ctx->stream>>>(g[k], r[k], r[k], t[k], d_u[k], d_v[k], st[k], 1, ctx->partials,
+                                                          ctx->ticket, out[k]);
+        NF_LAUNCH_CHECK(ctx);
+      }
+      NF_TRY(reduce_epilogue(EP_BI_T, 2, it));
+      for (int k = 0; k < nl; ++k) {
+        k_bi_x<<<l[k].grid, l[k].block, 0, ctx->stream>>>(g[k], x[k], r[k], p[k], nullptr, t[k], rt[k], st[k], it, 1,
+                                                          ctx->partials, ctx->ticket, out[k]);
+        NF_LAUNCH_CHECK(ctx);
+      }
+      NF_TRY(reduce_epilogue(EP_BI_X, 2, it));
+      if ((it + 1) % check_every == 0) {
+        NF_TRY(poll(hst));
+        if (hst->done) break;
+      }
+    }
+  }
+  NF_TRY(poll(hst));
+  krylov_finish(hst, maxiter, info);
+  return NF_OK;
 }

@@ -28,6 +28,11 @@ int nfi_momentum_sweeps_fused(nf_ctx*, const nf_grid*, int is_u, nf_links L, con
                               int with_res, int norm_b, int norm_e, double* field, double* out);
 int nfi_correct_velocity(nf_ctx*, const nf_grid*, const nf_bc_program*, const double* us, const double* vs,
                          const double* pp, const double* d_u, const double* d_v, double* u, double* v);
+int nfi_rbsor_fused_x(nf_ctx*, const nf_grid*, double** p, double** palt, const double* b, const double* d_u,
+                      const double* d_v, const double* inv, double omega, int n_sweeps, struct nf_smooth_extra* extra);
+int nfi_krylov_team(nf_team* team, const LevelGeom& geom, int kind, double* const* b, double* const* x, double* const* d_u,
+                    double* const* d_v, double atol, double rtol, int maxiter, int check_every, double* const* work,
+                    double* const* state, nf_krylov_info* info);
 int nfi_mg_create(nf_team* team, nf_mg** out, int nx, int ny, int ld, const nf_mg_config* cfg);
 int nfi_mg_setup(nf_mg* mg, double* const* d_u, double* const* d_v);
 int nfi_mg_solve(nf_mg* mg, double* const* b, double* const* x, double* const* r, nf_mg_info* info, int sync);
@@ -46,6 +51,7 @@ struct SimpleSlab {
   double *ures = nullptr, *vres = nullptr;
   double* tmp = nullptr;    // Jacobi pressure ping-pong
   double* kwork = nullptr;  // Krylov work arrays
+  double* kstate = nullptr; // slab-decomposed Krylov: this slab's copy of the scalar state + reduction scratch (64 doubles)
   double* scal = nullptr;   // 8 device doubles: [0..1] pressure norms, [2..5] momentum sums
   nf_links links;
 };
@@ -106,11 +112,6 @@ int nfi_simple_create(nf_team* team, nf_simple** out, const nf_simple_config* cf
   s->team = team;
   s->cfg = *cfg;
   s->geom = nf_level0_geom(team, cfg->nx, cfg->ny, nf_pad_ld(cfg->ny), cfg->length, cfg->height, cfg->rho);
-  if (s->geom.dist && cfg->pressure_solver != 0) {
-    ctx->err = "slab-decomposed runs support the multigrid pressure solver only";
-    delete s;
-    return NF_ERR_UNSUPPORTED;
-  }
   const int nl = (int)team->local.size();
   s->s.resize(nl);
   if (s->geom.dist) {  // peer-memory halo staging for the deepest exchange of the finest level (no-op without p2p)
@@ -133,6 +134,7 @@ int nfi_simple_create(nf_team* team, nf_simple** out, const nf_simple_config* cf
     if (ok && cfg->pressure_solver >= 3) {
       S.kwork = alloc_elems(s, S, e * (cfg->pressure_solver == 3 ? 4 : 5), emax * (cfg->pressure_solver == 3 ? 4 : 5));
       ok = S.kwork != nullptr;
+      if (ok) { S.kstate = alloc_elems(s, S, 64, 64); ok = S.kstate != nullptr; }
     }
     S.u_star = S.ua;
     S.v_star = S.va;
@@ -461,31 +463,81 @@ static int pressure_correction(nf_simple* s, int slot) {
     }
     case 1:
     case 2: {
-      SimpleSlab& S = s->s[0];
-      const nf_grid* g1 = &gp[0];
-      NF_TRY(nfi_fill(ctx, S.pp, (size_t)g1->nx * g1->ld, 0.0));
-      if (c.pressure_solver == 1)
-        NF_TRY(nfi_jacobi(ctx, g1, S.pp, S.tmp, S.b, S.d_u, S.d_v, c.pressure_omega, c.pressure_iterations));
-      else
-        NF_TRY(nfi_rbsor(ctx, g1, S.pp, S.b, S.d_u, S.d_v, c.pressure_omega, c.pressure_iterations));
-      NF_TRY(nfi_residual_norms(ctx, g1, S.pp, S.b, S.d_u, S.d_v, S.pres, 1, S.scal));
+      if (!dist) {
+        SimpleSlab& S = s->s[0];
+        const nf_grid* g1 = &gp[0];
+        NF_TRY(nfi_fill(ctx, S.pp, (size_t)g1->nx * g1->ld, 0.0));
+        if (c.pressure_solver == 1)
+          NF_TRY(nfi_jacobi(ctx, g1, S.pp, S.tmp, S.b, S.d_u, S.d_v, c.pressure_omega, c.pressure_iterations));
+        else
+          NF_TRY(nfi_rbsor(ctx, g1, S.pp, S.b, S.d_u, S.d_v, c.pressure_omega, c.pressure_iterations));
+        NF_TRY(nfi_residual_norms(ctx, g1, S.pp, S.b, S.d_u, S.d_v, S.pres, 1, S.scal));
+      } else {
+        // slabs: Jacobi exchanges one halo row per iteration; red-black SOR runs up to 3 sweeps per launch on a region
+        // that shrinks by two rows per sweep (nf_rbsor_fused.cu, bit-identical to the colour passes) and exchanges
+        // 2 x sweeps rows per launch
+        for (int k = 0; k < nl; ++k) NF_TRY(nfi_fill(ctx, s->s[k].pp, s->geom.elems(team->local[k]), 0.0));
+        int left = c.pressure_iterations;
+        while (left > 0) {
+          const int ns = c.pressure_solver == 1 ? 1 : (left >= 3 ? 3 : left);
+          for (int k = 0; k < nl; ++k) {
+            SimpleSlab& S = s->s[k];
+            if (c.pressure_solver == 1)
+              NF_TRY(nfi_jacobi(ctx, &gp[k], S.pp, S.tmp, S.b, S.d_u, S.d_v, c.pressure_omega, 1));
+            else
+              NF_TRY(nfi_rbsor_fused_x(ctx, &gp[k], &S.pp, &S.tmp, S.b, S.d_u, S.d_v, nullptr, c.pressure_omega, ns,
+                                       nullptr));
+          }
+          std::vector<double*> x = field_of(s, &SimpleSlab::pp);
+          NF_TRY(nf_team_exchange(team, s->geom, x.data(), c.pressure_solver == 1 ? 1 : 2 * ns));
+          left -= ns;
+        }
+        std::vector<double*> sc(nl);
+        for (int k = 0; k < nl; ++k) {
+          SimpleSlab& S = s->s[k];
+          NF_TRY(nfi_residual_norms(ctx, &gp[k], S.pp, S.b, S.d_u, S.d_v, S.pres, 1, S.scal));
+          sc[k] = S.scal;
+        }
+        NF_TRY(nf_team_allreduce(team, sc.data(), 2));
+      }
       p_from_scalars = 1;
       iters = c.pressure_iterations;
       break;
     }
     default: {
-      SimpleSlab& S = s->s[0];
-      const nf_grid* g1 = &gp[0];
       nf_krylov_info ki;
-      if (c.pressure_solver == 3)
-        NF_TRY(nf_cg_solve(ctx, g1, S.b, S.pp, S.d_u, S.d_v, c.pressure_tolerance, 1e-5, c.krylov_maxiter, 25, S.kwork, &ki));
-      else
-        NF_TRY(nf_bicgstab_solve(ctx, g1, S.b, S.pp, S.d_u, S.d_v, c.pressure_tolerance, 1e-5, c.krylov_maxiter, 10,
-                                 S.kwork, &ki));
-      // rel_norm = ||r_int|| / ||b_int|| of the true residual (matrix_free_BiCGSTAB.py:255-279)
-      NF_TRY(nfi_residual(ctx, g1, S.pp, S.b, S.d_u, S.d_v, S.pres));
-      NF_TRY(nfi_sumsq_to(ctx, g1, S.pres, 1, S.scal));
-      NF_TRY(nfi_sumsq_to(ctx, g1, S.b, 1, S.scal + 1));
+      if (!dist) {
+        SimpleSlab& S = s->s[0];
+        const nf_grid* g1 = &gp[0];
+        if (c.pressure_solver == 3)
+          NF_TRY(nf_cg_solve(ctx, g1, S.b, S.pp, S.d_u, S.d_v, c.pressure_tolerance, 1e-5, c.krylov_maxiter, 25, S.kwork, &ki));
+        else
+          NF_TRY(nf_bicgstab_solve(ctx, g1, S.b, S.pp, S.d_u, S.d_v, c.pressure_tolerance, 1e-5, c.krylov_maxiter, 10,
+                                   S.kwork, &ki));
+        // rel_norm = ||r_int|| / ||b_int|| of the true residual (matrix_free_BiCGSTAB.py:255-279)
+        NF_TRY(nfi_residual(ctx, g1, S.pp, S.b, S.d_u, S.d_v, S.pres));
+        NF_TRY(nfi_sumsq_to(ctx, g1, S.pres, 1, S.scal));
+        NF_TRY(nfi_sumsq_to(ctx, g1, S.b, 1, S.scal + 1));
+      } else {
+        std::vector<double*> du = field_of(s, &SimpleSlab::d_u), dv = field_of(s, &SimpleSlab::d_v);
+        std::vector<double*> b = field_of(s, &SimpleSlab::b), x = field_of(s, &SimpleSlab::pp);
+        std::vector<double*> w = field_of(s, &SimpleSlab::kwork), ks = field_of(s, &SimpleSlab::kstate);
+        NF_TRY(nf_team_exchange(team, s->geom, du.data(), 1));  // the operator reads d_u[i+1] and the neighbours' rows
+        NF_TRY(nf_team_exchange(team, s->geom, dv.data(), 1));
+        NF_TRY(nfi_krylov_team(team, s->geom, c.pressure_solver == 3 ? 0 : 1, b.data(), x.data(), du.data(), dv.data(),
+                               c.pressure_tolerance, 1e-5, c.krylov_maxiter, c.pressure_solver == 3 ? 25 : 10, w.data(),
+                               ks.data(), &ki));
+        NF_TRY(nf_team_exchange(team, s->geom, x.data(), 1));
+        std::vector<double*> sc(nl);
+        for (int k = 0; k < nl; ++k) {
+          SimpleSlab& S = s->s[k];
+          NF_TRY(nfi_residual(ctx, &gp[k], S.pp, S.b, S.d_u, S.d_v, S.pres));
+          NF_TRY(nfi_sumsq_to(ctx, &gp[k], S.pres, 1, S.scal));
+          NF_TRY(nfi_sumsq_to(ctx, &gp[k], S.b, 1, S.scal + 1));
+          sc[k] = S.scal;
+        }
+        NF_TRY(nf_team_allreduce(team, sc.data(), 2));
+      }
       p_from_scalars = 1;
       iters = ki.iterations;
       break;

@@ -465,3 +465,51 @@ def test_uneven_slabs_do_not_read_outside_their_storage():
     alg.push_fields()
     recs = alg.iterate_resident(2, 0.0)
     assert len(recs) == 2 and np.isfinite(recs[-1]["u_rel_norm"]) and recs[-1]["pressure_iterations"] > 0
+
+
+def _slab_run_ps(n, ps_factory, ranks, N=3, k=4):
+    import naviflow_b200 as nb
+    mesh, fluid = cavity(n, 1000)
+    alg = nb.GpuSimpleSolver(mesh, fluid, ps_factory(nb), nb.GpuJacobiMomentumSolver(n_jacobi_sweeps=k), alpha_p=0.3,
+                             alpha_u=0.7, virtual_ranks=ranks)
+    alg.set_boundary_condition("top", "velocity", {"u": 1.0, "v": 0.0})
+    for b in ("bottom", "left", "right"):
+        alg.set_boundary_condition(b, "wall")
+    res = alg.solve(max_iterations=N, tolerance=0.0)
+    return alg, res
+
+
+@pytest.mark.parametrize("name,n,ranks", [("jacobi", 257, 2), ("jacobi", 300, 3), ("rbsor", 257, 2), ("rbsor", 385, 4),
+                                          ("rbsor7", 300, 3)])
+def test_slab_jacobi_and_sor_pressure_solvers_bit_identical(name, n, ranks):
+    """Stationary pressure solvers on row slabs (one halo row per Jacobi iteration; up to 3 SOR sweeps per exchange on a
+    shrinking region) reproduce the single-slab fields bit for bit."""
+    fac = {"jacobi": lambda nb: nb.GpuJacobiSolver(tolerance=0.0, max_iterations=20, omega=0.8),
+           "rbsor": lambda nb: nb.GpuGaussSeidelSolver(tolerance=0.0, max_iterations=12, omega=1.5),
+           "rbsor7": lambda nb: nb.GpuGaussSeidelSolver(tolerance=0.0, max_iterations=7, omega=1.5)}[name]
+    ref, rres = _slab_run_ps(n, fac, 1)
+    alg, res = _slab_run_ps(n, fac, ranks)
+    for fld in ("u", "v", "p"):
+        np.testing.assert_array_equal(getattr(alg, fld), getattr(ref, fld), err_msg=fld)
+    np.testing.assert_allclose(res.get_history("p_rel_norm"), rres.get_history("p_rel_norm"), rtol=1e-10)
+
+
+@pytest.mark.parametrize("kind,n,ranks", [("cg", 257, 2), ("cg", 300, 3), ("bicgstab", 257, 2), ("bicgstab", 385, 4)])
+def test_slab_krylov_pressure_solvers_match_single_slab(kind, n, ranks):
+    """Slab-decomposed CG / BiCGSTAB (halo row per operator application, all-reduced dot products): with a fixed small
+    iteration count the fields equal the single-slab run to rounding (the dot products are summed in a different
+    order); run to scipy's tolerance they agree to that tolerance with the same iteration count +-10 %."""
+    import naviflow_b200 as nb
+    cls = nb.GpuCGSolver if kind == "cg" else nb.GpuBiCGSTABSolver
+    ref, _ = _slab_run_ps(n, lambda _: cls(tolerance=1e-30, max_iterations=8), 1, N=2)
+    alg, _ = _slab_run_ps(n, lambda _: cls(tolerance=1e-30, max_iterations=8), ranks, N=2)
+    for fld in ("u", "v", "p"):
+        assert rel(getattr(alg, fld), getattr(ref, fld)) < 1e-11, fld
+    if kind == "bicgstab":
+        ref, rres = _slab_run_ps(n, lambda _: cls(tolerance=1e-7, max_iterations=4000), 1, N=2)
+        alg, res = _slab_run_ps(n, lambda _: cls(tolerance=1e-7, max_iterations=4000), ranks, N=2)
+        for fld in ("u", "v", "p"):
+            assert rel(getattr(alg, fld), getattr(ref, fld)) < 1e-3, fld
+        a, b = np.array(alg.pressure_iterations_history, float), np.array(ref.pressure_iterations_history, float)
+        assert np.all(np.abs(a - b) <= 0.15 * b + 2), (a, b)
+        np.testing.assert_allclose(res.get_history("p_rel_norm"), rres.get_history("p_rel_norm"), rtol=0.5)
