@@ -216,6 +216,45 @@ def piso_runs(R):
     return out
 
 
+def mf_momentum_kats(R):
+    """MatrixFreeMomentumSolver (a7) on seeded fields + whole SimpleSolver runs with it (direct pressure solve)."""
+    out = {}
+    for n, Re, seed in ((15, 100, 715), (32, 1000, 732)):
+        rng = np.random.default_rng(seed)
+        mesh = R.StructuredMesh(n, n, 1.0, 1.0)
+        fluid = R.FluidProperties(density=1.0, reynolds_number=Re, characteristic_velocity=1.0)
+        bc = R.BoundaryConditionManager()
+        bc.set_condition("top", "velocity", {"u": 1.0, "v": 0.0})
+        for b in ("bottom", "left", "right"):
+            bc.set_condition(b, "wall")
+        u = 0.3 * rng.standard_normal((n + 1, n))
+        v = 0.3 * rng.standard_normal((n, n + 1))
+        p = rng.standard_normal((n, n))
+        ms = R.MatrixFreeMomentumSolver(tolerance=1e-8, max_iterations=200, solver_type="bicgstab")
+        us, du, iu = ms.solve_u_momentum(mesh, fluid, u.copy(), v.copy(), p.copy(), relaxation_factor=0.7,
+                                         boundary_conditions=bc)
+        vs, dv, iv = ms.solve_v_momentum(mesh, fluid, u.copy(), v.copy(), p.copy(), relaxation_factor=0.7,
+                                         boundary_conditions=bc)
+        k = f"kat_n{n}_Re{Re}"
+        out.update({k + "_u": u, k + "_v": v, k + "_p": p, k + "_us": us, k + "_du": du, k + "_vs": vs, k + "_dv": dv,
+                    k + "_unorm": iu["rel_norm"], k + "_vnorm": iv["rel_norm"], k + "_ufield": iu["field"],
+                    k + "_vfield": iv["field"], k + "_iters": np.array([iu["iterations"], iv["iterations"]])})
+    for n, Re, N in ((31, 100, 30), (63, 1000, 20)):
+        mesh = R.StructuredMesh(n, n, 1.0, 1.0)
+        fluid = R.FluidProperties(density=1.0, reynolds_number=Re, characteristic_velocity=1.0)
+        alg = R.SimpleSolver(mesh, fluid, R.DirectPressureSolver(),
+                             R.MatrixFreeMomentumSolver(tolerance=1e-8, max_iterations=200, solver_type="bicgstab"),
+                             R.StandardVelocityUpdater(), alpha_p=0.3, alpha_u=0.7)
+        alg.set_boundary_condition("top", "velocity", {"u": 1.0, "v": 0.0})
+        for b in ("bottom", "left", "right"):
+            alg.set_boundary_condition(b, "wall")
+        res = _quiet(alg.solve, max_iterations=N, tolerance=0.0, save_profile=False, track_infinity_norm=False)
+        k = f"run_n{n}_Re{Re}_N{N}"
+        out[k + "_u"], out[k + "_v"], out[k + "_p"] = alg.u, alg.v, alg.p
+        out[k + "_hist"] = np.array(res.get_history("total_rel_norm"))[::2]
+    return out
+
+
 def main():
     warnings.filterwarnings("ignore")
     R = rl.ref()
@@ -226,6 +265,7 @@ def main():
         np.savez_compressed(os.path.join(GOLD, f"mg_n{n}.npz"), **mg_kats(R, n, seed))
     np.savez_compressed(os.path.join(GOLD, "simple_runs.npz"), **simple_runs(R))
     np.savez_compressed(os.path.join(GOLD, "piso_runs.npz"), **piso_runs(R))
+    np.savez_compressed(os.path.join(GOLD, "mf_momentum.npz"), **mf_momentum_kats(R))
     cf = R.cavity_flow.BenchmarkData
     tables = {}
     for Re in (100, 400, 1000, 3200, 5000, 7500, 10000):

@@ -362,6 +362,81 @@ def solve_v_momentum(nx, ny, dx, dy, rho, mu, u, v, p, alpha, conditions, n_swee
 
 
 # ----------------------------------------------------------------------------
+# a7  MatrixFreeMomentumSolver (solver/momentum_solver/matrix_free_momentum.py:403-544): Krylov solve of the
+#     relaxed momentum system, interior rows 5-point, boundary rows identity
+# ----------------------------------------------------------------------------
+def mf_momentum_matvec(x, a_e, a_w, a_n, a_s, a_p):
+    """_matvec_u / _matvec_v (:49-79): same expression order."""
+    y = np.zeros_like(x)
+    y[1:-1, 1:-1] = (a_p[1:-1, 1:-1] * x[1:-1, 1:-1] - a_e[1:-1, 1:-1] * x[2:, 1:-1] - a_w[1:-1, 1:-1] * x[:-2, 1:-1]
+                     - a_n[1:-1, 1:-1] * x[1:-1, 2:] - a_s[1:-1, 1:-1] * x[1:-1, :-2])
+    y[[0, -1], :] = x[[0, -1], :]
+    y[:, [0, -1]] = x[:, [0, -1]]
+    return y
+
+
+def mf_momentum_ilu(a_e, a_w, a_n, a_s, a_p, drop_tol=1e-3, fill_factor=15):
+    """_build_sparse_approx + _create_ilu_preconditioner (:82-172).  As coded, the north/south diagonals fail the
+    length check (they hold rows*(cols-1) entries, not size-1) and are dropped: the ILU is built from the diagonal and
+    the east/west links only."""
+    from scipy.sparse import diags
+    from scipy.sparse.linalg import spilu
+    rows, cols = a_p.shape
+    size = rows * cols
+    data, offsets = [a_p.flatten()], [0]
+    for arr, off in ((-a_e[:-1, :].flatten(), cols), (-a_w[1:, :].flatten(), -cols),
+                     (-a_n[:, :-1].flatten(), 1), (-a_s[:, 1:].flatten(), -1)):
+        if arr.size == size - abs(off):
+            data.append(arr)
+            offsets.append(off)
+    A = diags(data, offsets, shape=(size, size), format="csr")
+    ilu = spilu(A, drop_tol=drop_tol, fill_factor=fill_factor)
+    return lambda z: ilu.solve(z.ravel()).reshape(z.shape)
+
+
+def solve_momentum_krylov(is_u, nx, ny, dx, dy, rho, mu, u, v, p, alpha, conditions, tol=1e-8, maxiter=200,
+                          precondition="ilu"):
+    """MatrixFreeMomentumSolver.solve_u_momentum / solve_v_momentum with solver_type='bicgstab' (:403-544).
+    precondition=None runs the same Krylov iteration without the ILU (what the device does; the answers agree to the
+    stopping tolerance max(tol, 1e-5 ||b||)).  Returns (star, d, abs_unrelaxed_norm, residual_field, iterations)."""
+    # the reference passes nx+1 as "nx" (:419, :491), which switches off the v[nx-1,:] reset
+    u_bc, v_bc = apply_velocity_bc(u.copy(), v.copy(), nx + 1, ny, conditions)
+    sides = tuple(s for s in ("left", "right", "bottom", "top") if conditions.get(s))
+    c = (u_coefficients if is_u else v_coefficients)(nx, ny, dx, dy, rho, mu, u_bc, v_bc, p, sides)
+    phi_bc = u_bc if is_u else v_bc
+    a_p_un, src_un = c["a_p"], c["source"]
+    a_p = np.where(np.abs(a_p_un) > 1e-12, a_p_un, 1e-12) / alpha
+    src = src_un + (1 - alpha) * a_p * phi_bc
+    links = (c["a_e"], c["a_w"], c["a_n"], c["a_s"])
+    M = mf_momentum_ilu(*links, a_p) if precondition == "ilu" else None
+    x0 = (u if is_u else v)
+    star, info, iters = bicgstab(lambda z: mf_momentum_matvec(z, *links, a_p), src, x0=x0, atol=tol, maxiter=maxiter,
+                                 M=M, order="C")
+    star = star.copy()
+    if is_u:
+        star, _ = apply_velocity_bc(star, v_bc, nx + 1, ny, conditions)
+    else:
+        _, star = apply_velocity_bc(u_bc, star, nx + 1, ny, conditions)
+    d = np.where(np.abs(a_p) > 1e-12, (dy if is_u else dx) / a_p, 0.0)
+    r = src_un - mf_momentum_matvec(star, *links, a_p_un)   # _calculate_unrelaxed_residual (:379-400)
+    r[0, :] = 0.0
+    r[-1, :] = 0.0
+    r[:, 0] = 0.0
+    r[:, -1] = 0.0
+    if is_u:
+        r[1, :] = 0.0
+        if nx > 1:
+            r[-2, :] = 0.0
+        interior = r[1:nx, 1:ny - 1]
+    else:
+        r[:, 1] = 0.0
+        if ny > 1:
+            r[:, -2] = 0.0
+        interior = r[1:nx - 1, 1:ny]
+    return star, d, float(np.linalg.norm(interior)), r, iters
+
+
+# ----------------------------------------------------------------------------
 # a8  continuity RHS (pressure_solver/helpers/rhs_construction.py:3-21)
 # ----------------------------------------------------------------------------
 def continuity_rhs(nx, ny, dx, dy, rho, u_star, v_star):
@@ -939,9 +1014,11 @@ def make_pressure_solver(kind, **kw):
 
 def simple_solve(nx, ny, reynolds, pressure_solver, n_sweeps=20, alpha_p=0.3, alpha_u=0.7,
                  max_iterations=100, tolerance=0.0, conditions=None, rho=1.0, U=1.0, L=1.0,
-                 state=None, callback=None):
+                 state=None, callback=None, momentum="jacobi", momentum_tol=1e-8, momentum_maxiter=200,
+                 momentum_precondition="ilu"):
     """SimpleSolver.solve (simple.py:114-212) with the deterministic momentum oracle
-    (JacobiMatrixMomentumSolver, n fixed sweeps).  Returns (state, history dict)."""
+    (JacobiMatrixMomentumSolver, n fixed sweeps) or, momentum='krylov', MatrixFreeMomentumSolver (a7; its rel_norm is
+    the absolute unrelaxed residual norm).  Returns (state, history dict)."""
     conditions = bc_conditions() if conditions is None else conditions
     dx, dy = mesh_spacing(nx, ny, L, L)
     mu = rho * U * L / reynolds  # fluid.py:41
@@ -951,8 +1028,15 @@ def simple_solve(nx, ny, reynolds, pressure_solver, n_sweeps=20, alpha_p=0.3, al
     it = 1
     total = 1.0
     while it <= max_iterations and total > tolerance:
-        us, du, un, _ = solve_u_momentum(nx, ny, dx, dy, rho, mu, st.u, st.v, p_star, alpha_u, conditions, n_sweeps)
-        vs, dv, vn, _ = solve_v_momentum(nx, ny, dx, dy, rho, mu, st.u, st.v, p_star, alpha_u, conditions, n_sweeps)
+        if momentum == "krylov":
+            us, du, un, _, ku = solve_momentum_krylov(True, nx, ny, dx, dy, rho, mu, st.u, st.v, p_star, alpha_u, conditions,
+                                                      momentum_tol, momentum_maxiter, momentum_precondition)
+            vs, dv, vn, _, kv = solve_momentum_krylov(False, nx, ny, dx, dy, rho, mu, st.u, st.v, p_star, alpha_u, conditions,
+                                                      momentum_tol, momentum_maxiter, momentum_precondition)
+            hist.setdefault("momentum_iterations", []).append((ku, kv))
+        else:
+            us, du, un, _ = solve_u_momentum(nx, ny, dx, dy, rho, mu, st.u, st.v, p_star, alpha_u, conditions, n_sweeps)
+            vs, dv, vn, _ = solve_v_momentum(nx, ny, dx, dy, rho, mu, st.u, st.v, p_star, alpha_u, conditions, n_sweeps)
         pp, pinfo = pressure_solver(nx, ny, dx, dy, us, vs, du, dv)
         st.p = update_pressure(p_star, pp, alpha_p, conditions)
         p_star = st.p.copy()
