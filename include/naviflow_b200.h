@@ -201,6 +201,23 @@ int nf_momentum_jacobi_fused(nf_ctx*, const nf_grid*, int is_u, nf_links L, doub
 int nf_momentum_residual(nf_ctx*, const nf_grid*, int is_u, nf_links L, const double* x, double* field_out,
                          double* rel_norm_host);
 
+/* ---- a7 MatrixFreeMomentumSolver (momentum_solver/matrix_free_momentum.py:403-544): Krylov momentum predictor ----
+ * Coefficients with that class's relaxation (a_P clamped to 1e-12 then /alpha, source relaxed with the relaxed a_P,
+ * d = 0 where a_P vanishes); u_bc/v_bc carry the BCs as that class applies them (caller's nx+1).  The unrelaxed a_P and
+ * source go to ap_unrelaxed / src_unrelaxed for nf_momentum_residual_unrelaxed. */
+int nf_momentum_links_mf(nf_ctx*, const nf_grid*, int is_u, const double* u_bc, const double* v_bc, const double* p,
+                         double mu, double alpha, int sides, nf_links out, double* d, double* ap_unrelaxed,
+                         double* src_unrelaxed);
+/* scipy bicgstab (operation order as nf_bicgstab_solve) on the relaxed system, interior rows 5-point / boundary rows
+ * identity (:49-79), x0 = x on entry, stop at ||r|| < max(atol, rtol ||b||); unpreconditioned (the reference's ILU only
+ * changes the iteration path).  work: 5 arrays of (nx+1)*ld doubles. */
+int nf_momentum_bicgstab(nf_ctx*, const nf_grid*, int is_u, nf_links L, double* x, double atol, double rtol, int maxiter,
+                         int check_every, double* work, nf_krylov_info* info);
+/* residual of the unrelaxed system (:379-400): L_unrelaxed = links with a_p, src = the unrelaxed arrays; boundary and
+ * boundary-adjacent lines zeroed; *norm_host = ||r|| (that class's "rel_norm") */
+int nf_momentum_residual_unrelaxed(nf_ctx*, const nf_grid*, int is_u, nf_links L_unrelaxed, const double* x,
+                                   double* field_out, double* norm_host);
+
 /* ---- K16/K17 corrections: velocity_solver/standard.py:10-69, Algorithms/simple.py:148-150,
  *      Algorithms/base_algorithm.py:161-197 ------------------------------------------------- */
 int nf_correct_velocity(nf_ctx*, const nf_grid*, const nf_bc_program*, const double* u_star,
@@ -226,10 +243,16 @@ typedef struct nf_simple_config {
   double pressure_tolerance;    /* Krylov atol (matrix_free_BiCGSTAB.py:234-242)                        */
   nf_bc_program bc;             /* velocity BC program evaluated with the true (nx, ny)                 */
   nf_mg_config mg;
+  int32_t momentum_solver;      /* 0: fixed Jacobi sweeps (JacobiMatrixMomentumSolver, a6); 1: BiCGSTAB on the relaxed
+                                   system (MatrixFreeMomentumSolver, a7; single slab only)                             */
+  int32_t momentum_maxiter;     /* a7: max_iterations (matrix_free_momentum.py:17)                                     */
+  double momentum_tolerance;    /* a7: atol of the Krylov solve (:16); stop at max(atol, 1e-5 ||b||)                   */
+  nf_bc_program bc_mf;          /* a7: BC program as that class applies it (caller's nx+1: :419, :491)                 */
 } nf_simple_config;
 
 typedef struct nf_simple_info {   /* one record per outer iteration */
-  double u_rel_norm, v_rel_norm;  /* momentum_solver rel_norm (jacobi_matrix_solver.py:246-250)          */
+  double u_rel_norm, v_rel_norm;  /* momentum solver's rel_norm: relaxed ||r||/||b|| (jacobi_matrix_solver.py:246-250)
+                                     or, momentum_solver 1, the absolute unrelaxed ||r|| (matrix_free_momentum.py:455) */
   double p_rel_norm;              /* pressure solver rel_norm (its own convention)           */
   double u_abs_res, v_abs_res;    /* sqrt(sum r^2) of the relaxed momentum residual over the interior   */
   int32_t pressure_iterations;    /* multigrid cycles / Krylov iterations used                          */

@@ -6,7 +6,7 @@ fallback: using a solver without the built library or without a CUDA device rais
 """
 from .host import (BoundaryConditionManager, FluidProperties, SimulationResult, StructuredMesh, ghia_errors,
                    ghia_table)
-from .momentum import GpuJacobiMomentumSolver
+from .momentum import GpuJacobiMomentumSolver, GpuMatrixFreeMomentumSolver
 from .pressure import (GpuBiCGSTABSolver, GpuCGSolver, GpuGaussSeidelSolver, GpuJacobiSolver,
                        GpuMultiGridSolver)
 from .simple import GpuPisoSolver, GpuSimpleSolver
@@ -15,4 +15,4 @@ from .velocity import GpuVelocityUpdater
 __all__ = ["StructuredMesh", "FluidProperties", "BoundaryConditionManager", "SimulationResult", "ghia_errors",
            "ghia_table", "GpuJacobiMomentumSolver", "GpuJacobiSolver", "GpuGaussSeidelSolver",
            "GpuMultiGridSolver", "GpuCGSolver", "GpuBiCGSTABSolver", "GpuVelocityUpdater", "GpuSimpleSolver",
-           "GpuPisoSolver"]
+           "GpuPisoSolver", "GpuMatrixFreeMomentumSolver"]

@@ -61,7 +61,9 @@ class NfSimpleConfig(C.Structure):
                 ("length", C.c_double), ("height", C.c_double), ("rho", C.c_double), ("mu", C.c_double),
                 ("alpha_p", C.c_double), ("alpha_u", C.c_double), ("pressure_omega", C.c_double),
                 ("pressure_tolerance", C.c_double),
-                ("bc", NfBcProgram), ("mg", NfMgConfig)]
+                ("bc", NfBcProgram), ("mg", NfMgConfig),
+                ("momentum_solver", C.c_int32), ("momentum_maxiter", C.c_int32), ("momentum_tolerance", C.c_double),
+                ("bc_mf", NfBcProgram)]
 
 
 class NfSimpleInfo(C.Structure):
@@ -118,6 +120,10 @@ SIGNATURES = {
     "nf_momentum_jacobi": (C.c_int, [CTX, GP, C.c_int, NfLinks, P, P, C.c_int]),
     "nf_momentum_jacobi_fused": (C.c_int, [CTX, GP, C.c_int, NfLinks, P, P, C.c_int, P, DBL_OUT]),
     "nf_momentum_residual": (C.c_int, [CTX, GP, C.c_int, NfLinks, P, P, DBL_OUT]),
+    "nf_momentum_links_mf": (C.c_int, [CTX, GP, C.c_int, P, P, P, C.c_double, C.c_double, C.c_int, NfLinks, P, P, P]),
+    "nf_momentum_bicgstab": (C.c_int, [CTX, GP, C.c_int, NfLinks, P, C.c_double, C.c_double, C.c_int, C.c_int, P,
+                                       C.POINTER(NfKrylovInfo)]),
+    "nf_momentum_residual_unrelaxed": (C.c_int, [CTX, GP, C.c_int, NfLinks, P, P, DBL_OUT]),
     "nf_correct_velocity": (C.c_int, [CTX, GP, C.POINTER(NfBcProgram), P, P, P, P, P, P, P]),
     "nf_update_pressure": (C.c_int, [CTX, GP, P, P, C.c_double, P]),
     "nf_max_abs_divergence": (C.c_int, [CTX, GP, P, P, DBL_OUT]),

@@ -424,6 +424,134 @@ extern "C" int nf_bicgstab_solve_mg(nf_ctx* ctx, const nf_grid* g, const double*
 }
 
 // =============================================================================================
+// a7  MatrixFreeMomentumSolver's Krylov solve (matrix_free_momentum.py:343-362, :434-441): scipy bicgstab on the relaxed
+// momentum system with x0 = the current velocity.  Operator: interior rows 5-point with the stored links, boundary rows
+// identity (:49-79).  The reference preconditions with an ILU of a matrix that (as coded) lacks the north/south links; the
+// device runs the same recurrence unpreconditioned -- the answers agree to the stopping tolerance max(atol, 1e-5 ||b||),
+// which is the parity this solver can be pinned to at all.
+// =============================================================================================
+__device__ __forceinline__ double nf_links_apply(const nf_grid& ga, const nf_links& L, const double* __restrict__ x, int i,
+                                                 int j) {
+  const size_t k = nf_idx(ga, i, j);
+  if (i == 0 || i == ga.nx - 1 || j == 0 || j == ga.ny - 1) return x[k];
+  double y = L.a_p[k] * x[k];
+  y -= L.a_e[k] * x[k + ga.ld];
+  y -= L.a_w[k] * x[k - ga.ld];
+  y -= L.a_n[k] * x[k + 1];
+  y -= L.a_s[k] * x[k - 1];
+  return y;
+}
+
+// r = b - A x0, rtilde = r; out[0] = b.b, out[1] = r.r ; epilogue: tolerance, rho, top-of-loop tests of iteration 0
+__global__ void k_links_init(nf_grid ga, nf_links L, const double* __restrict__ x, double* __restrict__ r,
+                             double* __restrict__ rt, KState* st, double atol, double rtol, double* partials,
+                             unsigned int* ticket, double* out) {
+  double acc[2] = {0.0, 0.0};
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < ga.ny) {
+    NF_ROWLOOP(ga, i) {
+      const size_t k = nf_idx(ga, i, j);
+      const double b = L.src[k];
+      const double rv = b - nf_links_apply(ga, L, x, i, j);
+      r[k] = rv;
+      rt[k] = rv;
+      acc[0] += b * b;
+      acc[1] += rv * rv;
+    }
+  }
+  if (nf_block_reduce_store<2>(acc, partials, ticket, out)) {
+    const double bb[1] = {out[0]};
+    ep_init(st, bb, atol, rtol);
+    st->rr = out[1];
+    st->rho = out[1];
+    st->done = (st->bnorm == 0.0 || sqrt(out[1]) < st->atol) ? 1 : 0;
+    if (!st->done && fabs(st->rho) < 4.930380657631324e-32) { st->done = 1; st->info = -10; }
+  }
+}
+
+__global__ void k_links_v(nf_grid ga, nf_links L, const double* __restrict__ p, double* __restrict__ v,
+                          const double* __restrict__ rt, KState* st, int it, double* partials, unsigned int* ticket,
+                          double* out) {
+  if (st->done) return;
+  double acc[1] = {0.0};
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < ga.ny) {
+    NF_ROWLOOP(ga, i) {
+      const size_t k = nf_idx(ga, i, j);
+      const double vc = nf_links_apply(ga, L, p, i, j);
+      v[k] = vc;
+      acc[0] += rt[k] * vc;
+    }
+  }
+  if (nf_block_reduce_store<1>(acc, partials, ticket, out)) ep_bi_v(st, out, it);
+}
+
+__global__ void k_links_t(nf_grid ga, nf_links L, const double* __restrict__ s, double* __restrict__ t, KState* st,
+                          double* partials, unsigned int* ticket, double* out) {
+  if (st->done || st->half) return;
+  double acc[2] = {0.0, 0.0};
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < ga.ny) {
+    NF_ROWLOOP(ga, i) {
+      const size_t k = nf_idx(ga, i, j);
+      const double tc = nf_links_apply(ga, L, s, i, j);
+      t[k] = tc;
+      acc[0] += tc * s[k];
+      acc[1] += tc * tc;
+    }
+  }
+  if (nf_block_reduce_store<2>(acc, partials, ticket, out)) ep_bi_t(st, out);
+}
+
+// x: in = x0, out = solution; work: 5 arrays of (nx+1)*ld doubles; L: RELAXED links (a_p, src relaxed)
+int nfi_momentum_bicgstab(nf_ctx* ctx, const nf_grid* g, int is_u, nf_links L, double* x, double atol, double rtol,
+                          int maxiter, int check_every, double* work, nf_krylov_info* info) {
+  if (check_every < 1) check_every = 1;
+  nf_grid ga = *g;  // the component's array seen as a plain rows x cols grid
+  ga.nx = g->nx + (is_u ? 1 : 0);
+  ga.ny = g->ny + (is_u ? 0 : 1);
+  ga.gb = 0;
+  ga.ge = ga.nx;
+  const size_t n = (size_t)(g->nx + 1) * g->ld;
+  double *r = work, *rt = work + n, *p = work + 2 * n, *v = work + 3 * n, *t = work + 4 * n;
+  KState *st, *hst;
+  krylov_state(ctx, &st, &hst);
+  NfLaunch2D l = nf_launch_reduce(ga.nx, ga.ny);
+  k_links_init<<<l.grid, l.block, 0, ctx->stream>>>(ga, L, x, r, rt, st, atol, rtol, ctx->partials, ctx->ticket,
+                                                    ctx->scalars);
+  NF_LAUNCH_CHECK(ctx);
+  for (int it = 0; it < maxiter; ++it) {
+    k_bi_p<<<l.grid, l.block, 0, ctx->stream>>>(ga, r, p, v, st, it == 0);
+    NF_LAUNCH_CHECK(ctx);
+    k_links_v<<<l.grid, l.block, 0, ctx->stream>>>(ga, L, p, v, rt, st, it, ctx->partials, ctx->ticket, ctx->scalars);
+    NF_LAUNCH_CHECK(ctx);
+    k_bi_s<<<l.grid, l.block, 0, ctx->stream>>>(ga, r, v, st, 0, ctx->partials, ctx->ticket, ctx->scalars);
+    NF_LAUNCH_CHECK(ctx);
+    k_links_t<<<l.grid, l.block, 0, ctx->stream>>>(ga, L, r, t, st, ctx->partials, ctx->ticket, ctx->scalars);
+    NF_LAUNCH_CHECK(ctx);
+    k_bi_x<<<l.grid, l.block, 0, ctx->stream>>>(ga, x, r, p, nullptr, t, rt, st, it, 0, ctx->partials, ctx->ticket,
+                                                ctx->scalars);
+    NF_LAUNCH_CHECK(ctx);
+    if ((it + 1) % check_every == 0) {
+      NF_TRY(krylov_poll(ctx, st, hst));
+      if (hst->done) break;
+    }
+  }
+  NF_TRY(krylov_poll(ctx, st, hst));
+  krylov_finish(hst, maxiter, info);
+  return NF_OK;
+}
+
+extern "C" int nf_momentum_bicgstab(nf_ctx* ctx, const nf_grid* g, int is_u, nf_links L, double* x, double atol,
+                                    double rtol, int maxiter, int check_every, double* work, nf_krylov_info* info) {
+  NF_GRID_OK(ctx, g);
+  NF_REQUIRE(ctx, L.a_e && L.a_w && L.a_n && L.a_s && L.a_p && L.src && x && work, "NULL argument");
+  NF_REQUIRE(ctx, maxiter >= 0, "maxiter < 0");
+  NF_REQUIRE(ctx, g->row0 == 0 && g->gb == 0 && g->ge == g->nx, "single-slab grids only");
+  return nfi_momentum_bicgstab(ctx, g, is_u, L, x, atol, rtol, maxiter, check_every, work, info);
+}
+
+// =============================================================================================
 // Slab-decomposed CG / BiCGSTAB (kind 0 / 1): the same kernels per slab; every reduction leaves its partial sums in
 // the slab's scratch (state[k] + 32), the team all-reduces them (peer-memory kernel or NCCL: BASELINE north_star "dot
 // products use allreduce") and k_krylov_epilogue advances the slab's copy of the state.  One halo exchange of one row

@@ -194,10 +194,13 @@ __device__ __forceinline__ LinkVals nf_links_v_cell(const nf_grid& g, const doub
   return L;
 }
 
-template <int IS_U>
+// MF = 0: relaxation of JacobiMatrixMomentumSolver (a6).  MF = 1: MatrixFreeMomentumSolver (a7,
+// matrix_free_momentum.py:429-430, :448-449): a_P clamped to 1e-12 before the division, source relaxed with the relaxed
+// a_P, d = 0 where a_P vanishes; the unrelaxed a_P and source are kept for its residual (:379-400).
+template <int IS_U, int MF>
 __global__ void k_momentum_links(nf_grid g, const double* __restrict__ u, const double* __restrict__ v,
                                  const double* __restrict__ p, double mu, double alpha, int sides, nf_links out,
-                                 double* __restrict__ d) {
+                                 double* __restrict__ d, double* __restrict__ ap_un, double* __restrict__ src_un) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const int i = g.gb + blockIdx.y * blockDim.y + threadIdx.y;
   if (j >= nf_cols(g, IS_U) || i >= nf_row_end(g, IS_U)) return;
@@ -212,8 +215,17 @@ __global__ void k_momentum_links(nf_grid g, const double* __restrict__ u, const 
   const double phi = IS_U ? u[k] : v[k];
   // under-relaxation (jacobi_matrix_solver.py:186-187)
   const double ralpha = 1.0 / alpha;
-  const double ap_rel = nf_div_const(L.ap, alpha, ralpha);
-  const double src_rel = L.src + nf_div_const((1.0 - alpha) * L.ap, alpha, ralpha) * phi;
+  double ap_rel, src_rel;
+  if (MF) {
+    const double apc = (fabs(L.ap) > 1e-12) ? L.ap : 1e-12;
+    ap_rel = nf_div_const(apc, alpha, ralpha);
+    src_rel = L.src + ((1.0 - alpha) * ap_rel) * phi;
+    ap_un[k] = L.ap;
+    src_un[k] = L.src;
+  } else {
+    ap_rel = nf_div_const(L.ap, alpha, ralpha);
+    src_rel = L.src + nf_div_const((1.0 - alpha) * L.ap, alpha, ralpha) * phi;
+  }
   out.a_e[k] = L.ae;
   out.a_w[k] = L.aw;
   out.a_n[k] = L.an;
@@ -221,7 +233,38 @@ __global__ void k_momentum_links(nf_grid g, const double* __restrict__ u, const 
   out.a_p[k] = ap_rel;
   out.src[k] = src_rel;
   // d = dy/a_p (u) or dx/a_p (v); NaN where |a_p| <= 1e-12 (:213-219)
-  d[k] = (fabs(ap_rel) > 1e-12) ? ((IS_U ? g.dy : g.dx) / ap_rel) : nan("");
+  d[k] = (fabs(ap_rel) > 1e-12) ? ((IS_U ? g.dy : g.dx) / ap_rel) : (MF ? 0.0 : nan(""));
+}
+
+// a7 residual of the UNRELAXED system at the solution (matrix_free_momentum.py:379-400): r = S - A x with identity
+// boundary rows, boundary and boundary-adjacent lines (in the component's normal direction) zeroed; sum r^2 -> out[0]
+template <int IS_U>
+__global__ void k_momentum_residual_unrelaxed(nf_grid g, nf_links L, const double* __restrict__ x,
+                                              double* __restrict__ field, double* partials, unsigned int* ticket,
+                                              double* out) {
+  double acc[1] = {0.0};
+  const int rows = nf_rows(g, IS_U), cols = nf_cols(g, IS_U);
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < cols) {
+    for (int i = blockIdx.y * blockDim.y + threadIdx.y; i < rows; i += gridDim.y * blockDim.y) {
+      const size_t k = nf_idx(g, i, j);
+      bool zero = (i == 0 || i == rows - 1 || j == 0 || j == cols - 1);
+      if (IS_U) zero = zero || i == 1 || i == rows - 2;
+      else zero = zero || j == 1 || j == cols - 2;
+      double r = 0.0;
+      if (!zero) {
+        double ax = L.a_p[k] * x[k];
+        ax -= L.a_e[k] * x[k + g.ld];
+        ax -= L.a_w[k] * x[k - g.ld];
+        ax -= L.a_n[k] * x[k + 1];
+        ax -= L.a_s[k] * x[k - 1];
+        r = L.src[k] - ax;
+      }
+      acc[0] += r * r;
+      if (field) field[k] = r;
+    }
+  }
+  nf_block_reduce_store<1>(acc, partials, ticket, out);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -324,9 +367,53 @@ extern "C" int nf_apply_velocity_bc(nf_ctx* ctx, const nf_grid* g, const nf_bc_p
 int nfi_momentum_links(nf_ctx* ctx, const nf_grid* g, int is_u, const double* u, const double* v, const double* p,
                        double mu, double alpha, int sides, nf_links out, double* d) {
   NfLaunch2D l = nf_launch2d(nf_row_end(*g, is_u) - g->gb, nf_cols(*g, is_u));
-  if (is_u) k_momentum_links<1><<<l.grid, l.block, 0, ctx->stream>>>(*g, u, v, p, mu, alpha, sides, out, d);
-  else k_momentum_links<0><<<l.grid, l.block, 0, ctx->stream>>>(*g, u, v, p, mu, alpha, sides, out, d);
+  if (is_u) k_momentum_links<1, 0><<<l.grid, l.block, 0, ctx->stream>>>(*g, u, v, p, mu, alpha, sides, out, d, nullptr, nullptr);
+  else k_momentum_links<0, 0><<<l.grid, l.block, 0, ctx->stream>>>(*g, u, v, p, mu, alpha, sides, out, d, nullptr, nullptr);
   NF_LAUNCH_CHECK(ctx);
+  return NF_OK;
+}
+
+// a7 variant of the coefficients (see k_momentum_links<.., 1>)
+int nfi_momentum_links_mf(nf_ctx* ctx, const nf_grid* g, int is_u, const double* u, const double* v, const double* p,
+                          double mu, double alpha, int sides, nf_links out, double* d, double* ap_un, double* src_un) {
+  NfLaunch2D l = nf_launch2d(nf_row_end(*g, is_u) - g->gb, nf_cols(*g, is_u));
+  if (is_u) k_momentum_links<1, 1><<<l.grid, l.block, 0, ctx->stream>>>(*g, u, v, p, mu, alpha, sides, out, d, ap_un, src_un);
+  else k_momentum_links<0, 1><<<l.grid, l.block, 0, ctx->stream>>>(*g, u, v, p, mu, alpha, sides, out, d, ap_un, src_un);
+  NF_LAUNCH_CHECK(ctx);
+  return NF_OK;
+}
+
+extern "C" int nf_momentum_links_mf(nf_ctx* ctx, const nf_grid* g, int is_u, const double* u_bc, const double* v_bc,
+                                    const double* p, double mu, double alpha, int sides, nf_links out, double* d,
+                                    double* ap_unrelaxed, double* src_unrelaxed) {
+  NF_GRID_OK(ctx, g);
+  NF_REQUIRE(ctx, out.a_e && out.a_w && out.a_n && out.a_s && out.a_p && out.src && d && ap_unrelaxed && src_unrelaxed,
+             "NULL array");
+  NF_REQUIRE(ctx, alpha > 0.0, "relaxation factor must be > 0");
+  NF_REQUIRE(ctx, g->row0 == 0 && g->gb == 0 && g->ge == g->nx, "single-slab grids only");
+  return nfi_momentum_links_mf(ctx, g, is_u, u_bc, v_bc, p, mu, alpha, sides, out, d, ap_unrelaxed, src_unrelaxed);
+}
+
+// sum r^2 of the unrelaxed residual -> out[0] (device); L.a_p / L.src hold the UNRELAXED a_P and source
+int nfi_momentum_residual_unrelaxed(nf_ctx* ctx, const nf_grid* g, int is_u, nf_links L, const double* x, double* field,
+                                    double* out) {
+  NfLaunch2D l = nf_launch_reduce(nf_rows(*g, is_u), nf_cols(*g, is_u));
+  if (is_u) k_momentum_residual_unrelaxed<1><<<l.grid, l.block, 0, ctx->stream>>>(*g, L, x, field, ctx->partials, ctx->ticket, out);
+  else k_momentum_residual_unrelaxed<0><<<l.grid, l.block, 0, ctx->stream>>>(*g, L, x, field, ctx->partials, ctx->ticket, out);
+  NF_LAUNCH_CHECK(ctx);
+  return NF_OK;
+}
+
+extern "C" int nf_momentum_residual_unrelaxed(nf_ctx* ctx, const nf_grid* g, int is_u, nf_links L_unrelaxed, const double* x,
+                                              double* field_out, double* norm_host) {
+  NF_GRID_OK(ctx, g);
+  NF_REQUIRE(ctx, L_unrelaxed.a_e && L_unrelaxed.a_w && L_unrelaxed.a_n && L_unrelaxed.a_s && L_unrelaxed.a_p &&
+                      L_unrelaxed.src && x, "NULL array");
+  NF_REQUIRE(ctx, g->row0 == 0 && g->gb == 0 && g->ge == g->nx, "single-slab grids only");
+  NF_TRY(nfi_momentum_residual_unrelaxed(ctx, g, is_u, L_unrelaxed, x, field_out, ctx->scalars));
+  double s[1];
+  NF_TRY(nf_read_scalars(ctx, 0, 1, s));
+  if (norm_host) *norm_host = sqrt(s[0]);
   return NF_OK;
 }
 

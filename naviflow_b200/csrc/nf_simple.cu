@@ -26,6 +26,12 @@ int nfi_momentum_sweep(nf_ctx*, const nf_grid*, int is_u, nf_links L, const doub
 int nfi_momentum_residual_to(nf_ctx*, const nf_grid*, int is_u, nf_links L, const double* x, double* field, double* out);
 int nfi_momentum_sweeps_fused(nf_ctx*, const nf_grid*, int is_u, nf_links L, const double* xin, double* xout, int k,
                               int with_res, int norm_b, int norm_e, double* field, double* out);
+int nfi_momentum_links_mf(nf_ctx*, const nf_grid*, int is_u, const double* u, const double* v, const double* p, double mu,
+                          double alpha, int sides, nf_links out, double* d, double* ap_un, double* src_un);
+int nfi_momentum_bicgstab(nf_ctx*, const nf_grid*, int is_u, nf_links L, double* x, double atol, double rtol, int maxiter,
+                          int check_every, double* work, nf_krylov_info* info);
+int nfi_momentum_residual_unrelaxed(nf_ctx*, const nf_grid*, int is_u, nf_links L, const double* x, double* field,
+                                    double* out);
 int nfi_correct_velocity(nf_ctx*, const nf_grid*, const nf_bc_program*, const double* us, const double* vs,
                          const double* pp, const double* d_u, const double* d_v, double* u, double* v);
 int nfi_rbsor_fused_x(nf_ctx*, const nf_grid*, double** p, double** palt, const double* b, const double* d_u,
@@ -51,6 +57,7 @@ struct SimpleSlab {
   double *ures = nullptr, *vres = nullptr;
   double* tmp = nullptr;    // Jacobi pressure ping-pong
   double* kwork = nullptr;  // Krylov work arrays
+  double *ap_un = nullptr, *src_un = nullptr, *mwork = nullptr;  // Krylov momentum predictor (a7)
   double* kstate = nullptr; // slab-decomposed Krylov: this slab's copy of the scalar state + reduction scratch (64 doubles)
   double* scal = nullptr;   // 8 device doubles: [0..1] pressure norms, [2..5] momentum sums
   nf_links links;
@@ -107,11 +114,18 @@ int nfi_simple_create(nf_team* team, nf_simple** out, const nf_simple_config* cf
   NF_REQUIRE(ctx, cfg->pressure_solver >= 0 && cfg->pressure_solver <= 4, "unknown pressure solver");
   NF_REQUIRE(ctx, cfg->alpha_u > 0.0, "alpha_u must be > 0");
   NF_REQUIRE(ctx, cfg->n_momentum_sweeps >= 0, "n_momentum_sweeps < 0");
+  NF_REQUIRE(ctx, cfg->momentum_solver == 0 || cfg->momentum_solver == 1, "unknown momentum solver");
+  NF_REQUIRE(ctx, cfg->momentum_solver == 0 || cfg->momentum_maxiter >= 0, "momentum_maxiter < 0");
   nf_simple* s = new nf_simple();
   s->ctx = ctx;
   s->team = team;
   s->cfg = *cfg;
   s->geom = nf_level0_geom(team, cfg->nx, cfg->ny, nf_pad_ld(cfg->ny), cfg->length, cfg->height, cfg->rho);
+  if (s->geom.dist && cfg->momentum_solver != 0) {
+    ctx->err = "slab-decomposed runs support the Jacobi-sweep momentum predictor only";
+    delete s;
+    return NF_ERR_UNSUPPORTED;
+  }
   const int nl = (int)team->local.size();
   s->s.resize(nl);
   if (s->geom.dist) {  // peer-memory halo staging for the deepest exchange of the finest level (no-op without p2p)
@@ -131,6 +145,12 @@ int nfi_simple_create(nf_team* team, nf_simple** out, const nf_simple_config* cf
       if (!*f) { ok = false; break; }
     }
     if (ok) { S.scal = alloc_elems(s, S, 8, 8); ok = S.scal != nullptr; }
+    if (ok && cfg->momentum_solver == 1) {
+      S.ap_un = alloc_elems(s, S, e, emax);
+      S.src_un = alloc_elems(s, S, e, emax);
+      S.mwork = alloc_elems(s, S, e * 5, emax * 5);
+      ok = S.ap_un && S.src_un && S.mwork;
+    }
     if (ok && cfg->pressure_solver >= 3) {
       S.kwork = alloc_elems(s, S, e * (cfg->pressure_solver == 3 ? 4 : 5), emax * (cfg->pressure_solver == 3 ? 4 : 5));
       ok = S.kwork != nullptr;
@@ -290,14 +310,45 @@ static int ensure_hist(nf_simple* s, int n) {
 static void decode_record(const nf_simple* s, const double* rec, nf_simple_info* out) {
   out->u_abs_res = sqrt(rec[2]);
   out->v_abs_res = sqrt(rec[4]);
-  out->u_rel_norm = sqrt(rec[2]) / (sqrt(rec[3]) + 1e-15);  // jacobi_matrix_solver.py:246-250
-  out->v_rel_norm = sqrt(rec[4]) / (sqrt(rec[5]) + 1e-15);
+  if (s->cfg.momentum_solver == 1) {  // absolute unrelaxed residual norm (matrix_free_momentum.py:455, :527)
+    out->u_rel_norm = sqrt(rec[2]);
+    out->v_rel_norm = sqrt(rec[4]);
+  } else {
+    out->u_rel_norm = sqrt(rec[2]) / (sqrt(rec[3]) + 1e-15);  // jacobi_matrix_solver.py:246-250
+    out->v_rel_norm = sqrt(rec[4]) / (sqrt(rec[5]) + 1e-15);
+  }
   switch (s->cfg.pressure_solver) {
     case 0: case 1: case 2: out->p_rel_norm = sqrt(rec[0]); break;  // absolute ||b - A p'|| (multigrid.py:257)
     default: out->p_rel_norm = rec[1] > 0.0 ? sqrt(rec[0]) / sqrt(rec[1]) : sqrt(rec[0]); break;  // ||r_int||/||b_int||
   }
   out->pressure_iterations = (int)rec[6];
   out->pad = 0;
+}
+
+// a7: MatrixFreeMomentumSolver.solve_u/v_momentum (matrix_free_momentum.py:403-544), single slab.  ubc / vbc hold the
+// velocities with the BCs applied the way that class does it (caller's nx+1).
+static int momentum_component_krylov(nf_simple* s, int is_u, double alpha, int want_fields) {
+  nf_ctx* ctx = s->ctx;
+  const nf_simple_config& c = s->cfg;
+  SimpleSlab& S = s->s[0];
+  const nf_grid g = s->geom.grid(s->team->local[0]);
+  double* d = is_u ? S.d_u : S.d_v;
+  NF_TRY(nfi_momentum_links_mf(ctx, &g, is_u, S.ubc, S.vbc, S.p, c.mu, alpha, c.sides, S.links, d, S.ap_un, S.src_un));
+  double* x = is_u ? S.ua : S.va;
+  NF_CHECK_CUDA(ctx, cudaMemcpyAsync(x, is_u ? S.u : S.v, s->geom.elems(s->team->local[0]) * sizeof(double),
+                                     cudaMemcpyDeviceToDevice, ctx->stream));  // x0 = the raw velocity (:436, :508)
+  nf_krylov_info ki;
+  NF_TRY(nfi_momentum_bicgstab(ctx, &g, is_u, S.links, x, c.momentum_tolerance, 1e-5, c.momentum_maxiter, 10, S.mwork, &ki));
+  // BCs on the solution; the partner argument is the BC'd copy (idempotent) (:438, :510)
+  if (is_u) NF_TRY(nfi_apply_velocity_bc(ctx, &g, &c.bc_mf, x, S.vbc));
+  else NF_TRY(nfi_apply_velocity_bc(ctx, &g, &c.bc_mf, S.ubc, x));
+  if (is_u) S.u_star = x; else S.v_star = x;
+  nf_links Lun = S.links;
+  Lun.a_p = S.ap_un;
+  Lun.src = S.src_un;
+  NF_TRY(nfi_momentum_residual_unrelaxed(ctx, &g, is_u, Lun, x, want_fields ? (is_u ? S.ures : S.vres) : nullptr,
+                                         S.scal + (is_u ? 2 : 4)));
+  return NF_OK;
 }
 
 // momentum predictor of one component on every local slab (no communication, see the header comment)
@@ -408,9 +459,20 @@ static int refresh_bc_copies(nf_simple* s) {
 // slot >= 0: the relaxed residual sums of this solve are the iteration's record (hist[slot][2..5])
 static int momentum_predictor(nf_simple* s, double alpha, int want_fields, int slot) {
   nf_ctx* ctx = s->ctx;
-  NF_TRY(refresh_bc_copies(s));
-  NF_TRY(momentum_component(s, 1, alpha, want_fields));
-  NF_TRY(momentum_component(s, 0, alpha, want_fields));
+  if (s->cfg.momentum_solver == 1) {
+    SimpleSlab& S = s->s[0];
+    const size_t bytes = s->geom.elems(s->team->local[0]) * sizeof(double);
+    const nf_grid g = s->geom.grid(s->team->local[0]);
+    NF_CHECK_CUDA(ctx, cudaMemcpyAsync(S.ubc, S.u, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    NF_CHECK_CUDA(ctx, cudaMemcpyAsync(S.vbc, S.v, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    NF_TRY(nfi_apply_velocity_bc(ctx, &g, &s->cfg.bc_mf, S.ubc, S.vbc));
+    NF_TRY(momentum_component_krylov(s, 1, alpha, want_fields));
+    NF_TRY(momentum_component_krylov(s, 0, alpha, want_fields));
+  } else {
+    NF_TRY(refresh_bc_copies(s));
+    NF_TRY(momentum_component(s, 1, alpha, want_fields));
+    NF_TRY(momentum_component(s, 0, alpha, want_fields));
+  }
   if (slot < 0) return NF_OK;
   const int nl = nlocal(s);
   if (s->geom.dist) {  // momentum sums of all slabs (4 doubles at scal[2..5])

@@ -71,3 +71,90 @@ class GpuJacobiMomentumSolver:
         if return_dict:
             return vs, dv, {"rel_norm": norm, "field": field}
         return vs, dv, norm, field
+
+
+class GpuMatrixFreeMomentumSolver:
+    """Twin of ``MatrixFreeMomentumSolver`` (solver/momentum_solver/matrix_free_momentum.py:11-544) with
+    ``solver_type='bicgstab'``: power-law links, a_P clamped to 1e-12 and divided by the relaxation factor, source relaxed
+    with the relaxed a_P, scipy's BiCGSTAB recurrence on the relaxed system (interior rows 5-point, boundary rows
+    identity) started from the current velocity and stopped at ``||r|| < max(tolerance, 1e-5 ||b||)``, BCs re-applied to
+    the solution (with the reference's ``nx+1`` call), ``d = dy/a_P`` (0 where a_P vanishes) and ``rel_norm`` = the absolute
+    norm of the *unrelaxed* residual over the interior.
+
+    The reference preconditions the iteration with an ILU (``ilu_drop_tol``, ``ilu_fill_factor``) of a matrix that, as
+    coded, lacks the north/south links; the device iteration is unpreconditioned, so the two agree to the stopping
+    tolerance, not bit for bit (this solver cannot be pinned below ~1e-6 against itself either).  The ILU
+    arguments are accepted and ignored; ``gmres`` / ``idrs`` are not implemented."""
+
+    def __init__(self, discretization_scheme="power_law", tolerance=1e-8, max_iterations=200, solver_type="bicgstab",
+                 ilu_drop_tol=1e-3, ilu_fill_factor=15, idrs_s=4, device=None):
+        solver_type = str(solver_type).lower()
+        if solver_type not in {"gmres", "bicgstab", "idrs"}:  # matrix_free_momentum.py:31-33
+            raise ValueError("solver_type must be 'gmres', 'bicgstab', or 'idrs'")
+        if solver_type != "bicgstab":
+            raise NotImplementedError("the device momentum solver implements solver_type='bicgstab'")
+        if discretization_scheme != "power_law":
+            if discretization_scheme in ("quick", "second_order_upwind"):
+                raise NotImplementedError("only the power-law scheme is implemented on the device")
+            raise ValueError(f"Unsupported discretization scheme: {discretization_scheme}")
+        self.tol = float(tolerance)
+        self.maxiter = int(max_iterations)
+        self.solver_type = solver_type
+        self.ilu_drop_tol, self.ilu_fill_factor, self.idrs_s = float(ilu_drop_tol), int(ilu_fill_factor), int(idrs_s)
+        self._device = device
+        self._ctx = None
+
+    @property
+    def ctx(self):
+        if self._ctx is None:
+            self._ctx = get_context(self._device)
+        return self._ctx
+
+    def _solve(self, is_u, mesh, fluid, u, v, p, alpha, bc):
+        from ._lib import NfKrylovInfo
+        ctx = self.ctx
+        nx, ny = mesh.get_dimensions()
+        dx, dy = mesh.get_cell_sizes()
+        g = ctx.grid(nx, ny, dx, dy, fluid.get_density())
+        ud, vd, pd = ctx.upload(u, nx, ny), ctx.upload(v, nx, ny), ctx.upload(p, nx, ny)
+        ubc, vbc = ud.clone(), vd.clone()
+        prog = bc_program_struct(bc, nx, ny, nx + 1)   # the reference passes nx+1 (matrix_free_momentum.py:419, :491)
+        apply_bc = lambda a, b: ctx.check(ctx.lib.nf_apply_velocity_bc(ctx.handle, C.byref(g), C.byref(prog), ptr(a), ptr(b)),
+                                          "nf_apply_velocity_bc")
+        apply_bc(ubc, vbc)
+        arrays = [ctx.empty(nx, ny) for _ in range(6)]
+        links = NfLinks(*[a.data_ptr() for a in arrays])
+        d, ap_un, src_un = ctx.empty(nx, ny), ctx.empty(nx, ny), ctx.empty(nx, ny)
+        ctx.check(ctx.lib.nf_momentum_links_mf(ctx.handle, C.byref(g), int(is_u), ptr(ubc), ptr(vbc), ptr(pd),
+                                               float(fluid.get_viscosity()), float(alpha), practice_b_sides(bc), links,
+                                               ptr(d), ptr(ap_un), ptr(src_un)), "nf_momentum_links_mf")
+        x = ud if is_u else vd   # x0 = the current velocity (:436, :508)
+        work = ctx.torch.zeros((5 * (nx + 1), x.shape[1]), dtype=ctx.torch.float64, device=x.device)
+        info = NfKrylovInfo()
+        ctx.check(ctx.lib.nf_momentum_bicgstab(ctx.handle, C.byref(g), int(is_u), links, ptr(x), self.tol, 1e-5,
+                                               self.maxiter, 10, ptr(work), C.byref(info)), "nf_momentum_bicgstab")
+        if is_u:
+            apply_bc(x, vbc)
+        else:
+            apply_bc(ubc, x)
+        unrelaxed = NfLinks(arrays[0].data_ptr(), arrays[1].data_ptr(), arrays[2].data_ptr(), arrays[3].data_ptr(),
+                            ap_un.data_ptr(), src_un.data_ptr())
+        field = ctx.empty(nx, ny)
+        norm = C.c_double()
+        ctx.check(ctx.lib.nf_momentum_residual_unrelaxed(ctx.handle, C.byref(g), int(is_u), unrelaxed, ptr(x), ptr(field),
+                                                         C.byref(norm)), "nf_momentum_residual_unrelaxed")
+        rows, cols = (nx + 1, ny) if is_u else (nx, ny + 1)
+        self.last_info = info
+        res = {"rel_norm": norm.value, "field": ctx.download(field, rows, cols), "iterations": int(info.iterations),
+               "solver_type": self.solver_type}
+        return ctx.download(x, rows, cols), ctx.download(d, rows, cols), res
+
+    def solve_u_momentum(self, mesh, fluid, u, v, p, relaxation_factor=0.7, boundary_conditions=None,
+                         return_dict=True):
+        us, du, res = self._solve(True, mesh, fluid, u, v, p, relaxation_factor, boundary_conditions)
+        return (us, du, res) if return_dict else (us, du, res["rel_norm"])
+
+    def solve_v_momentum(self, mesh, fluid, u, v, p, relaxation_factor=0.7, boundary_conditions=None,
+                         return_dict=True):
+        vs, dv, res = self._solve(False, mesh, fluid, u, v, p, relaxation_factor, boundary_conditions)
+        return (vs, dv, res) if return_dict else (vs, dv, res["rel_norm"])

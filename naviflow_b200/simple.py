@@ -21,7 +21,7 @@ import numpy as np
 from ._lib import NfSimpleConfig, NfSimpleInfo
 from .device import bc_program_struct, get_context, mesh_scalars
 from .host import BoundaryConditionManager, SimulationResult, ghia_errors, practice_b_sides
-from .momentum import GpuJacobiMomentumSolver
+from .momentum import GpuJacobiMomentumSolver, GpuMatrixFreeMomentumSolver
 from .pressure import (GpuBiCGSTABSolver, GpuCGSolver, GpuGaussSeidelSolver, GpuJacobiSolver,
                        GpuMultiGridSolver)
 from .velocity import GpuVelocityUpdater
@@ -145,9 +145,13 @@ class GpuSimpleSolver:
         c = NfSimpleConfig()
         c.nx, c.ny = nx, ny
         ms = self.momentum_solver
-        if not isinstance(ms, GpuJacobiMomentumSolver):
-            raise TypeError("GpuSimpleSolver needs a GpuJacobiMomentumSolver (fixed Jacobi sweeps on the device)")
-        c.n_momentum_sweeps = ms.n_jacobi_sweeps
+        c.momentum_solver, c.momentum_maxiter, c.momentum_tolerance, c.n_momentum_sweeps = 0, 0, 0.0, 0
+        if isinstance(ms, GpuJacobiMomentumSolver):
+            c.n_momentum_sweeps = ms.n_jacobi_sweeps
+        elif isinstance(ms, GpuMatrixFreeMomentumSolver):
+            c.momentum_solver, c.momentum_maxiter, c.momentum_tolerance = 1, ms.maxiter, ms.tol
+        else:
+            raise TypeError("GpuSimpleSolver needs a GpuJacobiMomentumSolver or a GpuMatrixFreeMomentumSolver")
         ps = self.pressure_solver
         c.krylov_maxiter = 0
         c.piso_corrections = int(self._piso_corrections)
@@ -175,6 +179,7 @@ class GpuSimpleSolver:
         c.rho, c.mu = float(self.fluid.get_density()), float(self.fluid.get_viscosity())
         c.alpha_p, c.alpha_u = float(self.alpha_p), float(self.alpha_u)
         c.bc = bc_program_struct(self.bc_manager, nx, ny)
+        c.bc_mf = bc_program_struct(self.bc_manager, nx, ny, nx + 1)
         return c
 
     def _world(self):
