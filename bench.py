@@ -224,6 +224,11 @@ def main():
     recs = alg.iterate_resident(args.steps, 0.0)
     e1.record()
     barrier()
+    # phases of the step on the following `steps` iterations (4 CUDA events per iteration between the phases' launches;
+    # the V-cycle graph is still replayed): momentum predictor / pressure solve incl. RHS + hierarchy / corrections
+    alg.phase_timing(True)
+    precs = alg.iterate_resident(args.steps, 0.0)
+    phases = alg.phase_timing(False)
     live_ms, live_launches = 0.0, 0
     if world == 1:
         # the dominant kernel inside the real step: two more outer iterations with CUDA-event pairs around every
@@ -337,6 +342,21 @@ def main():
                "sample": f"{ns}x{ns} grid of the same workload, {k} outer iterations after 1 warm-up, NumPy oracle port "
                          f"(single threaded; host has {os.cpu_count()} cores)"}
 
+    pressure = None
+    if phases["iterations"] > 0:
+        pc = float(np.mean([r["pressure_iterations"] for r in precs]))
+        p_ms = phases["pressure_ms"] / phases["iterations"]
+        # V(3,3) cycle = [(3+3)*40 + 40 + 10 + 18] * 4/3 = 411 B/fine cell; per solve the coefficient
+        # hierarchy (27 B/cell) and the continuity RHS (24 B/cell) once
+        p_bytes = (411.0 * pc + 27.0 + 24.0) * cells
+        pressure = {"ms_per_step": p_ms, "cycles_per_step": pc, "ms_per_cycle": p_ms / max(pc, 1e-9),
+                    "algorithmic_bytes_per_step": p_bytes, "achieved_gbs": p_bytes / (p_ms * 1e-3) / 1e9 if p_ms > 0 else None,
+                    "frac_of_measured_hbm_peak": (p_bytes / (p_ms * 1e-3) / 1e9 / (peak * world)) if p_ms > 0 else None,
+                    "momentum_ms_per_step": phases["momentum_ms"] / phases["iterations"],
+                    "corrections_ms_per_step": phases["correct_ms"] / phases["iterations"],
+                    "how": f"CUDA events between the phases of {phases['iterations']} further outer iterations of the same "
+                           f"run (rank 0's clock); algorithmic bytes per SURVEY.md 8d: 411 B/cell per V(3,3) cycle + 51 B/cell "
+                           f"per solve; peak = measured HBM copy bandwidth x {world} GPU(s)"}
     if rank == 0:
         cycles = [r["pressure_iterations"] for r in recs]
         line = {
@@ -351,7 +371,7 @@ def main():
                            + ", coarse multigrid levels replicated"),
             "gpu_launches": int(launches), "mg_cycles_per_step": float(np.mean(cycles)) if cycles else None,
             "final_u_rel_norm": recs[-1]["u_rel_norm"] if recs else None,
-            "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
+            "clocks": clocks, "roofline": roofline, "pressure_solve": pressure, "e2e": e2e, "cpu_baseline": cpu,
         }
         print(json.dumps(line))
     if world > 1:

@@ -288,6 +288,10 @@ int nf_simple_create_team(nf_team*, nf_simple** out, const nf_simple_config* cfg
  * nf_mg_solve: switches the instrumentation on / off and returns + resets the accumulated time and launch count */
 int nf_mg_smoother_timing(nf_mg*, int on, double* total_ms, long long* launches);
 int nf_simple_smoother_timing(nf_simple*, int on, double* total_ms, long long* launches);
+/* CUDA-event timing of the phases of the outer iteration (momentum predictor / pressure solve incl. its RHS / p and
+ * velocity corrections): switches it on / off, returns + resets the accumulated ms and the iterations they cover */
+int nf_simple_phase_timing(nf_simple*, int on, double* ms_momentum, double* ms_pressure, double* ms_correct,
+                           long long* iterations);
 /* cell rows [*row_begin, *row_end) owned by local slab k of this process (k = 0 under torchrun) */
 int nf_simple_local_rows(nf_simple*, int k, int* row_begin, int* row_end);
 int nf_simple_destroy(nf_simple*);

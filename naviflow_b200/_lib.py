@@ -140,6 +140,7 @@ SIGNATURES = {
     "nf_simple_create_team": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(NfSimpleConfig)]),
     "nf_mg_smoother_timing": (C.c_int, [C.c_void_p, C.c_int, DBL_OUT, C.POINTER(C.c_longlong)]),
     "nf_simple_smoother_timing": (C.c_int, [C.c_void_p, C.c_int, DBL_OUT, C.POINTER(C.c_longlong)]),
+    "nf_simple_phase_timing": (C.c_int, [C.c_void_p, C.c_int, DBL_OUT, DBL_OUT, DBL_OUT, C.POINTER(C.c_longlong)]),
     "nf_simple_local_rows": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "nf_simple_ld": (C.c_int, [C.c_void_p]),
     "nf_simple_field": (C.c_void_p, [C.c_void_p, C.c_int]),

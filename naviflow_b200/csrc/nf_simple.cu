@@ -75,7 +75,23 @@ struct nf_simple {
   double* hist_host = nullptr;  // pinned
   int hist_cap = 0;
   bool bc_clean = false;
+  // optional phase timing (nf_simple_phase_timing): 4 events per outer iteration on the context's stream
+  bool phase_timing = false;
+  std::vector<cudaEvent_t> pev;
+  size_t pev_used = 0;
+  double phase_ms[3] = {0.0, 0.0, 0.0};  // momentum predictor(s), pressure solve(s) incl. RHS, corrections
+  long long phase_iters = 0;
 };
+
+static void phase_mark(nf_simple* s) {
+  if (!s->phase_timing) return;
+  if (s->pev_used == s->pev.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    s->pev.push_back(e);
+  }
+  cudaEventRecord(s->pev[s->pev_used++], s->ctx->stream);
+}
 
 static int nlocal(const nf_simple* s) { return (int)s->team->local.size(); }
 
@@ -88,6 +104,7 @@ extern "C" int nf_simple_destroy(nf_simple* s) {
     for (double* ptr : S.owned) nf_team_release(s->team, ptr);
   if (s->hist) cudaFree(s->hist);
   if (s->hist_host) cudaFreeHost(s->hist_host);
+  for (cudaEvent_t e : s->pev) cudaEventDestroy(e);
   if (s->owns_team) nf_team_destroy(s->team);
   delete s;
   return NF_OK;
@@ -605,6 +622,7 @@ static int pressure_correction(nf_simple* s, int slot) {
       break;
     }
   }
+  phase_mark(s);  // end of the pressure solve
   if (slot >= 0) {
     k_store_hist_pressure<<<1, 32, 0, ctx->stream>>>(pscal, s->hist + (size_t)slot * 8, pa, pb, iters, p_from_scalars);
     NF_LAUNCH_CHECK(ctx);
@@ -634,12 +652,48 @@ static int pressure_correction(nf_simple* s, int slot) {
 // corrected (u, v, p) without relaxation, their norms are discarded (:92-104).
 static int simple_step(nf_simple* s, int slot, int want_fields) {
   const nf_simple_config& c = s->cfg;
+  // phase marks per (predictor, correction) pair: start, end of predictor, end of pressure solve, end of corrections
+  phase_mark(s);
   NF_TRY(momentum_predictor(s, c.alpha_u, want_fields, slot));
+  phase_mark(s);
   const int nc = c.piso_corrections >= 1 ? c.piso_corrections : 1;
   for (int k = 0; k < nc; ++k) {
     NF_TRY(pressure_correction(s, k == nc - 1 ? slot : -1));
-    if (k < nc - 1) NF_TRY(momentum_predictor(s, 1.0, 0, -1));
+    phase_mark(s);
+    if (k < nc - 1) {
+      phase_mark(s);
+      NF_TRY(momentum_predictor(s, 1.0, 0, -1));
+      phase_mark(s);
+    }
   }
+  if (s->phase_timing) s->phase_iters++;
+  return NF_OK;
+}
+
+// CUDA-event timing of the three phases of the outer iteration (momentum predictor / pressure solve incl. its RHS /
+// p and velocity corrections) inside nf_simple_iterate: switches the instrumentation on or off and returns + resets the
+// accumulated milliseconds and the number of outer iterations they cover.  The events sit between the phases' launches
+// on the context's stream (the V-cycle graph is launched between two of them), so they do not perturb the kernels.
+extern "C" int nf_simple_phase_timing(nf_simple* s, int on, double* ms_momentum, double* ms_pressure, double* ms_correct,
+                                      long long* iterations) {
+  if (!s) return NF_ERR_ARG;
+  nf_ctx* ctx = s->ctx;
+  NF_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (size_t k = 0; k + 3 < s->pev_used; k += 4) {  // groups of 4 marks: start, predictor, solve, corrections
+    float a = 0.f, b = 0.f, c = 0.f;
+    cudaEventElapsedTime(&a, s->pev[k], s->pev[k + 1]);
+    cudaEventElapsedTime(&b, s->pev[k + 1], s->pev[k + 2]);
+    cudaEventElapsedTime(&c, s->pev[k + 2], s->pev[k + 3]);
+    s->phase_ms[0] += a; s->phase_ms[1] += b; s->phase_ms[2] += c;
+  }
+  s->pev_used = 0;
+  if (ms_momentum) *ms_momentum = s->phase_ms[0];
+  if (ms_pressure) *ms_pressure = s->phase_ms[1];
+  if (ms_correct) *ms_correct = s->phase_ms[2];
+  if (iterations) *iterations = s->phase_iters;
+  s->phase_ms[0] = s->phase_ms[1] = s->phase_ms[2] = 0.0;
+  s->phase_iters = 0;
+  s->phase_timing = on != 0;
   return NF_OK;
 }
 

@@ -296,6 +296,15 @@ class GpuSimpleSolver:
                   "nf_simple_smoother_timing")
         return ms.value, cnt.value
 
+    def phase_timing(self, on):
+        """Switches the CUDA-event timing of the iteration's phases on/off; returns the accumulated
+        ``{'momentum_ms', 'pressure_ms', 'correct_ms', 'iterations'}`` since the last call."""
+        ctx, st = self._ensure_state()
+        a, b, c, n = C.c_double(), C.c_double(), C.c_double(), C.c_longlong()
+        ctx.check(ctx.lib.nf_simple_phase_timing(st, 1 if on else 0, C.byref(a), C.byref(b), C.byref(c), C.byref(n)),
+                  "nf_simple_phase_timing")
+        return {"momentum_ms": a.value, "pressure_ms": b.value, "correct_ms": c.value, "iterations": n.value}
+
     def push_fields(self):
         ctx, st = self._ensure_state()
         for name in ("u", "v", "p"):
