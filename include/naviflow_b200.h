@@ -99,6 +99,11 @@ int nf_jacobi_diag(nf_ctx*, const nf_grid*, const double* d_u, const double* d_v
 /* ---- K8  red-black SOR: pressure_solver/gauss_seidel.py:214-305 ----------------------- */
 int nf_rbsor_sweeps(nf_ctx*, const nf_grid*, double* p, const double* b, const double* d_u,
                     const double* d_v, double omega, int n_sweeps);
+/* GaussSeidelSolver method_type 'standard' / 'symmetric' (gauss_seidel.py:307-367): sequential SOR sweeps `for j: for i:`
+ * (symmetric: followed by the reverse sweep), evaluated as a two-level anti-diagonal wavefront (32 x 32 blocks, one launch
+ * per block diagonal) -- same bits as the loop.  Single-slab grids. */
+int nf_gs_lex_sweeps(nf_ctx*, const nf_grid*, double* p, const double* b, const double* d_u, const double* d_v,
+                     double omega, int n_sweeps, int symmetric);
 
 /* Same sweeps, temporally blocked: up to 3 full sweeps (6 colour passes) per tile load, bit-identical result.
  * tmp is a same-shape scratch array (p is double buffered between launches); arrays 16-byte aligned, ld even. */
@@ -231,7 +236,8 @@ int nf_max_abs_divergence(nf_ctx*, const nf_grid*, const double* u, const double
 typedef struct nf_simple_config {
   int32_t nx, ny;
   int32_t n_momentum_sweeps;    /* JacobiMatrixMomentumSolver(n_jacobi_sweeps)                          */
-  int32_t pressure_solver;      /* 0 multigrid, 1 Jacobi, 2 red-black SOR, 3 CG, 4 BiCGSTAB             */
+  int32_t pressure_solver;      /* 0 multigrid, 1 Jacobi, 2 red-black SOR, 3 CG, 4 BiCGSTAB,
+                                   5 lexicographic SOR, 6 symmetric SOR (5, 6: single slab)              */
   int32_t pressure_iterations;  /* fixed iteration count of the Jacobi / SOR pressure solvers          */
   int32_t sides;                /* boundaries with a registered condition: 1 left 2 right 4 bottom 8 top */
   int32_t krylov_maxiter;

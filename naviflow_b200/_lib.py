@@ -92,6 +92,7 @@ SIGNATURES = {
     "nf_jacobi_iterate": (C.c_int, [CTX, GP, P, P, P, P, P, C.c_double, C.c_int]),
     "nf_jacobi_diag": (C.c_int, [CTX, GP, P, P, P]),
     "nf_rbsor_sweeps": (C.c_int, [CTX, GP, P, P, P, P, C.c_double, C.c_int]),
+    "nf_gs_lex_sweeps": (C.c_int, [CTX, GP, P, P, P, P, C.c_double, C.c_int, C.c_int]),
     "nf_rbsor_sweeps_fused": (C.c_int, [CTX, GP, P, P, P, P, P, P, C.c_double, C.c_int]),
     "nf_pressure_inv_diag": (C.c_int, [CTX, GP, P, P, P]),
     "nf_restrict_fw": (C.c_int, [CTX, GP, P, GP, P]),

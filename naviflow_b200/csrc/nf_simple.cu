@@ -36,6 +36,8 @@ int nfi_correct_velocity(nf_ctx*, const nf_grid*, const nf_bc_program*, const do
                          const double* pp, const double* d_u, const double* d_v, double* u, double* v);
 int nfi_rbsor_fused_x(nf_ctx*, const nf_grid*, double** p, double** palt, const double* b, const double* d_u,
                       const double* d_v, const double* inv, double omega, int n_sweeps, struct nf_smooth_extra* extra);
+int nfi_gs_lex(nf_ctx*, const nf_grid*, double* p, const double* b, const double* d_u, const double* d_v, double omega,
+               int n_sweeps, int symmetric);
 int nfi_krylov_team(nf_team* team, const LevelGeom& geom, int kind, double* const* b, double* const* x, double* const* d_u,
                     double* const* d_v, double atol, double rtol, int maxiter, int check_every, double* const* work,
                     double* const* state, nf_krylov_info* info);
@@ -128,7 +130,7 @@ int nfi_simple_create(nf_team* team, nf_simple** out, const nf_simple_config* cf
   NF_REQUIRE(ctx, out && cfg, "NULL argument");
   *out = nullptr;
   NF_REQUIRE(ctx, cfg->nx >= 3 && cfg->ny >= 3, "nx, ny must be >= 3");
-  NF_REQUIRE(ctx, cfg->pressure_solver >= 0 && cfg->pressure_solver <= 4, "unknown pressure solver");
+  NF_REQUIRE(ctx, cfg->pressure_solver >= 0 && cfg->pressure_solver <= 6, "unknown pressure solver");
   NF_REQUIRE(ctx, cfg->alpha_u > 0.0, "alpha_u must be > 0");
   NF_REQUIRE(ctx, cfg->n_momentum_sweeps >= 0, "n_momentum_sweeps < 0");
   NF_REQUIRE(ctx, cfg->momentum_solver == 0 || cfg->momentum_solver == 1, "unknown momentum solver");
@@ -138,6 +140,11 @@ int nfi_simple_create(nf_team* team, nf_simple** out, const nf_simple_config* cf
   s->team = team;
   s->cfg = *cfg;
   s->geom = nf_level0_geom(team, cfg->nx, cfg->ny, nf_pad_ld(cfg->ny), cfg->length, cfg->height, cfg->rho);
+  if (s->geom.dist && cfg->pressure_solver >= 5) {
+    ctx->err = "the sequential Gauss-Seidel sweeps run on a single slab only";
+    delete s;
+    return NF_ERR_UNSUPPORTED;
+  }
   if (s->geom.dist && cfg->momentum_solver != 0) {
     ctx->err = "slab-decomposed runs support the Jacobi-sweep momentum predictor only";
     delete s;
@@ -168,7 +175,7 @@ int nfi_simple_create(nf_team* team, nf_simple** out, const nf_simple_config* cf
       S.mwork = alloc_elems(s, S, e * 5, emax * 5);
       ok = S.ap_un && S.src_un && S.mwork;
     }
-    if (ok && cfg->pressure_solver >= 3) {
+    if (ok && (cfg->pressure_solver == 3 || cfg->pressure_solver == 4)) {
       S.kwork = alloc_elems(s, S, e * (cfg->pressure_solver == 3 ? 4 : 5), emax * (cfg->pressure_solver == 3 ? 4 : 5));
       ok = S.kwork != nullptr;
       if (ok) { S.kstate = alloc_elems(s, S, 64, 64); ok = S.kstate != nullptr; }
@@ -335,7 +342,8 @@ static void decode_record(const nf_simple* s, const double* rec, nf_simple_info*
     out->v_rel_norm = sqrt(rec[4]) / (sqrt(rec[5]) + 1e-15);
   }
   switch (s->cfg.pressure_solver) {
-    case 0: case 1: case 2: out->p_rel_norm = sqrt(rec[0]); break;  // absolute ||b - A p'|| (multigrid.py:257)
+    case 0: case 1: case 2: case 5: case 6:
+      out->p_rel_norm = sqrt(rec[0]); break;  // absolute ||b - A p'|| (multigrid.py:257)
     default: out->p_rel_norm = rec[1] > 0.0 ? sqrt(rec[0]) / sqrt(rec[1]) : sqrt(rec[0]); break;  // ||r_int||/||b_int||
   }
   out->pressure_iterations = (int)rec[6];
@@ -579,6 +587,17 @@ static int pressure_correction(nf_simple* s, int slot) {
         }
         NF_TRY(nf_team_allreduce(team, sc.data(), 2));
       }
+      p_from_scalars = 1;
+      iters = c.pressure_iterations;
+      break;
+    }
+    case 5:
+    case 6: {  // sequential SOR sweeps (single slab)
+      SimpleSlab& S = s->s[0];
+      const nf_grid* g1 = &gp[0];
+      NF_TRY(nfi_fill(ctx, S.pp, (size_t)g1->nx * g1->ld, 0.0));
+      NF_TRY(nfi_gs_lex(ctx, g1, S.pp, S.b, S.d_u, S.d_v, c.pressure_omega, c.pressure_iterations, c.pressure_solver == 6));
+      NF_TRY(nfi_residual_norms(ctx, g1, S.pp, S.b, S.d_u, S.d_v, S.pres, 1, S.scal));
       p_from_scalars = 1;
       iters = c.pressure_iterations;
       break;

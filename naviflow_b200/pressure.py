@@ -154,20 +154,22 @@ class GpuJacobiSolver(_StationaryBase):
 
 
 class GpuGaussSeidelSolver(_StationaryBase):
-    """Red-black SOR (gauss_seidel.py:268-305).  The lexicographic / symmetric variants are sequential
-    sweeps and are not offered on the GPU."""
+    """GaussSeidelSolver twin: red-black SOR (gauss_seidel.py:268-305) and the sequential 'standard' (lexicographic) /
+    'symmetric' sweeps (:307-367), which run as anti-diagonal wavefronts with the loop's exact bits (nf_gs_lex.cu)."""
 
     def __init__(self, tolerance=1e-6, max_iterations=1000, omega=1.0, method_type="red_black", device=None):
         super().__init__(tolerance, max_iterations, device)
         if method_type not in ("red_black", "standard", "symmetric"):
             raise ValueError("method_type must be one of 'red_black', 'standard', or 'symmetric'")
-        if method_type != "red_black":
-            raise NotImplementedError("only method_type='red_black' runs on the GPU (sequential sweeps are out of scope)")
         self.omega = omega
         self.method_type = method_type
 
     def _iterate(self, g, p, b, du, dv, n):
         ctx = self.ctx
+        if self.method_type != "red_black":
+            ctx.check(ctx.lib.nf_gs_lex_sweeps(ctx.handle, C.byref(g), ptr(p), ptr(b), ptr(du), ptr(dv), float(self.omega),
+                                               int(n), int(self.method_type == "symmetric")), "nf_gs_lex_sweeps")
+            return
         ctx.check(ctx.lib.nf_rbsor_sweeps(ctx.handle, C.byref(g), ptr(p), ptr(b), ptr(du), ptr(dv), float(self.omega),
                                           int(n)), "nf_rbsor_sweeps")
 

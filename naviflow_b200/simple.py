@@ -165,7 +165,8 @@ class GpuSimpleSolver:
             if ps.tolerance > 0:
                 raise NotImplementedError(
                     "device-resident Jacobi / SOR pressure solves run a fixed number of iterations: pass tolerance=0")
-            c.pressure_solver = 1 if isinstance(ps, GpuJacobiSolver) else 2
+            c.pressure_solver = 1 if isinstance(ps, GpuJacobiSolver) else \
+                {"red_black": 2, "standard": 5, "symmetric": 6}[ps.method_type]
             c.pressure_iterations = int(ps.max_iterations)
             c.pressure_omega = float(ps.omega)
         elif isinstance(ps, (GpuCGSolver, GpuBiCGSTABSolver)):

@@ -255,6 +255,26 @@ def mf_momentum_kats(R):
     return out
 
 
+def gs_lex_kats(R):
+    """GaussSeidelSolver(method_type='standard' | 'symmetric'): 3 sweeps on seeded systems."""
+    out = {}
+    for n, seed in ((15, 915), (33, 933), (40, 940)):
+        rng = np.random.default_rng(seed)
+        mesh = R.StructuredMesh(n, n, 1.0, 1.0)
+        dx, dy = mesh.get_cell_sizes()
+        d_u = (0.7 * dy / 4e-3) * (1 + 0.1 * rng.random((n + 1, n)))
+        d_v = (0.7 * dx / 4e-3) * (1 + 0.1 * rng.random((n, n + 1)))
+        b = 1e-2 * rng.standard_normal((n, n))
+        b[0, 0] = 0.0
+        p0 = 1e-3 * rng.standard_normal((n, n))
+        out[f"n{n}_du"], out[f"n{n}_dv"], out[f"n{n}_b"], out[f"n{n}_p0"] = d_u, d_v, b, p0
+        for mt in ("standard", "symmetric"):
+            gs = R.GaussSeidelSolver(omega=1.5, method_type=mt)
+            out[f"n{n}_{mt}"] = gs.solve(mesh=mesh, p=p0.copy(), b=b.copy(), d_u=d_u, d_v=d_v, rho=1.0, num_iterations=3,
+                                         track_residuals=False, return_dict=False)
+    return out
+
+
 def main():
     warnings.filterwarnings("ignore")
     R = rl.ref()
@@ -266,6 +286,7 @@ def main():
     np.savez_compressed(os.path.join(GOLD, "simple_runs.npz"), **simple_runs(R))
     np.savez_compressed(os.path.join(GOLD, "piso_runs.npz"), **piso_runs(R))
     np.savez_compressed(os.path.join(GOLD, "mf_momentum.npz"), **mf_momentum_kats(R))
+    np.savez_compressed(os.path.join(GOLD, "gs_lex.npz"), **gs_lex_kats(R))
     cf = R.cavity_flow.BenchmarkData
     tables = {}
     for Re in (100, 400, 1000, 3200, 5000, 7500, 10000):

@@ -591,6 +591,47 @@ def rb_sor(p, b, dx, dy, rho, d_u, d_v, omega, n_sweeps):
 
 
 # ----------------------------------------------------------------------------
+# 8f rank 3: lexicographic / symmetric Gauss-Seidel (pressure_solver/gauss_seidel.py:307-367)
+# ----------------------------------------------------------------------------
+def gs_lex(p, b, dx, dy, rho, d_u, d_v, omega, n_sweeps, symmetric=False):
+    """GaussSeidelSolver(method_type='standard' | 'symmetric').solve(p=p, b=b, num_iterations=n_sweeps): sequential SOR
+    sweeps `for j: for i:` (the symmetric variant adds the reverse sweep), pinned cell (0,0) skipped and reset to 0.
+    Evaluated here by anti-diagonals i+j = const (vectorised): every update reads the new west/south and the old east/north
+    values exactly as the loop order does, so the bits are the loop's."""
+    nx, ny = b.shape
+    aE, aW, aN, aS, aP = sor_coefficients(nx, ny, dx, dy, rho, d_u, d_v)
+    inv = 1.0 / aP
+    p = p.copy()
+    p[0, 0] = 0.0
+    P = np.zeros((nx + 2, ny + 2))   # padded copy: out-of-domain neighbours contribute exactly 0
+    diags = []
+    for d in range(nx + ny - 1):
+        i = np.arange(max(0, d - ny + 1), min(nx - 1, d) + 1)
+        j = d - i
+        keep = ~((i == 0) & (j == 0))
+        diags.append((i[keep], j[keep]))
+
+    def one_pass(order):
+        for i, j in order:
+            if i.size == 0:
+                continue
+            P[1:-1, 1:-1] = p
+            east = np.where(i < nx - 1, aE[i, j] * P[i + 2, j + 1], 0.0)
+            west = np.where(i > 0, aW[i, j] * P[i, j + 1], 0.0)
+            north = np.where(j < ny - 1, aN[i, j] * P[i + 1, j + 2], 0.0)
+            south = np.where(j > 0, aS[i, j] * P[i + 1, j], 0.0)
+            p_new = ((((b[i, j] + east) + west) + north) + south) * inv[i, j]
+            p[i, j] = p[i, j] + omega * (p_new - p[i, j])
+
+    for _ in range(n_sweeps):
+        one_pass(diags)
+        if symmetric:
+            one_pass(diags[::-1])
+        p[0, 0] = 0.0
+    return p
+
+
+# ----------------------------------------------------------------------------
 # a12  multigrid transfer operators (helpers/multigrid_helpers.py)
 # ----------------------------------------------------------------------------
 def restrict_inject(f):

@@ -599,3 +599,58 @@ def test_simple_loop_with_krylov_momentum_vs_oracle():
     import naviflow_b200 as nb
     with pytest.raises(NotImplementedError):
         nb.GpuMatrixFreeMomentumSolver(solver_type="gmres")
+
+
+@pytest.mark.parametrize("n", [15, 33, 40])
+@pytest.mark.parametrize("mt", ["standard", "symmetric"])
+def test_lexicographic_gauss_seidel_vs_reference_golden(golden_dir, n, mt):
+    """8f rank 3: GaussSeidelSolver(method_type='standard' | 'symmetric') (gauss_seidel.py:307-367) as a block wavefront:
+    bit-identical to the reference's sequential loops."""
+    import naviflow_b200 as nb
+    g = load(golden_dir, "gs_lex.npz")
+    mesh, _ = cavity(n, 100)
+    gs = nb.GpuGaussSeidelSolver(omega=1.5, method_type=mt)
+    p = gs.solve(mesh=mesh, p=g[f"n{n}_p0"].copy(), b=g[f"n{n}_b"].copy(), d_u=g[f"n{n}_du"], d_v=g[f"n{n}_dv"], rho=1.0,
+                 num_iterations=3, track_residuals=False, return_dict=False)
+    np.testing.assert_array_equal(p, g[f"n{n}_{mt}"])
+
+
+@pytest.mark.parametrize("n,mt,sweeps", [(64, "standard", 2), (65, "symmetric", 2), (97, "standard", 1), (130, "symmetric", 1),
+                                         (7, "standard", 4)])
+def test_lexicographic_gauss_seidel_vs_oracle(n, mt, sweeps):
+    """Sizes around the 32-cell block edge (full blocks, one extra row, ragged edges, a single partial block)."""
+    import naviflow_b200 as nb
+    rng = np.random.default_rng(1000 + n)
+    dx, dy = O.mesh_spacing(n, n)
+    d_u = (0.7 * dy / 4e-3) * (1 + 0.1 * rng.random((n + 1, n)))
+    d_v = (0.7 * dx / 4e-3) * (1 + 0.1 * rng.random((n, n + 1)))
+    b = 1e-2 * rng.standard_normal((n, n))
+    b[0, 0] = 0.0
+    p0 = 1e-3 * rng.standard_normal((n, n))
+    mesh, _ = cavity(n, 100)
+    gs = nb.GpuGaussSeidelSolver(omega=1.3, method_type=mt)
+    p = gs.solve(mesh=mesh, p=p0.copy(), b=b.copy(), d_u=d_u, d_v=d_v, rho=1.0, num_iterations=sweeps, track_residuals=False)
+    np.testing.assert_array_equal(p, O.gs_lex(p0, b, dx, dy, 1.0, d_u, d_v, 1.3, sweeps, symmetric=(mt == "symmetric")))
+
+
+def test_simple_loop_with_lexicographic_gauss_seidel_vs_oracle():
+    """The sequential sweeps as the pressure solver of the device SIMPLE loop (fixed iteration count)."""
+    import naviflow_b200 as nb
+    n, Re, k, N = 40, 100, 5, 6
+    for mt in ("standard", "symmetric"):
+        mesh, fluid = cavity(n, Re)
+        alg = nb.GpuSimpleSolver(mesh, fluid, nb.GpuGaussSeidelSolver(tolerance=0.0, max_iterations=10, omega=1.5, method_type=mt),
+                                 nb.GpuJacobiMomentumSolver(n_jacobi_sweeps=k), alpha_p=0.3, alpha_u=0.7)
+        alg.set_boundary_condition("top", "velocity", {"u": 1.0, "v": 0.0})
+        for b in ("bottom", "left", "right"):
+            alg.set_boundary_condition(b, "wall")
+        alg.solve(max_iterations=N, tolerance=0.0)
+
+        def ps(nx, ny, dx, dy, us, vs, du, dv, mt=mt):
+            b = O.continuity_rhs(nx, ny, dx, dy, 1.0, us, vs)
+            x = O.gs_lex(np.zeros((nx, ny)), b, dx, dy, 1.0, du, dv, 1.5, 10, symmetric=(mt == "symmetric"))
+            r = b - O.apply_A(x, dx, dy, 1.0, du, dv)
+            return x, {"rel_norm": float(np.linalg.norm(r)), "field": r}
+        st, _ = O.simple_solve(n, n, Re, ps, n_sweeps=k, max_iterations=N, tolerance=0.0)
+        for fld in ("u", "v", "p"):
+            assert rel(getattr(alg, fld), getattr(st, fld)) < 1e-12, (mt, fld)

@@ -185,3 +185,13 @@ def test_simple_loop_with_krylov_momentum_golden(golden_dir, n, Re, N):
             err = np.linalg.norm(arr - g[f"{k}_{fld}"]) / np.linalg.norm(g[f"{k}_{fld}"])
             assert err < tol, (pre, fld, err)
         np.testing.assert_allclose(h["total_rel_norm"], g[k + "_hist"], rtol=10 * tol)
+
+
+@pytest.mark.parametrize("n", [15, 33, 40])
+@pytest.mark.parametrize("mt", ["standard", "symmetric"])
+def test_lexicographic_gauss_seidel_golden(golden_dir, n, mt):
+    """8f rank 3: sequential SOR sweeps (gauss_seidel.py:307-367), evaluated by anti-diagonals: bit-exact."""
+    g = load(golden_dir, "gs_lex.npz")
+    dx, dy = O.mesh_spacing(n, n)
+    p = O.gs_lex(g[f"n{n}_p0"], g[f"n{n}_b"], dx, dy, 1.0, g[f"n{n}_du"], g[f"n{n}_dv"], 1.5, 3, symmetric=(mt == "symmetric"))
+    same(p, g[f"n{n}_{mt}"])
