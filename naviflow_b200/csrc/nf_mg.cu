@@ -22,6 +22,10 @@
 #include "nf_slab.cuh"
 
 #define NF_MIN_SLAB_ROWS 64   // a level is cut only while every rank keeps at least this many rows
+// ... and only while it is large enough for the cut to pay: a level of <= NF_REPLICATE_BELOW rows per side is launch-latency
+// bound (its kernels take the same few microseconds on the whole level as on a slab), so three halo exchanges of ~7.5 us per
+// cycle cost more than the redundant arithmetic (env NF_REPLICATE_BELOW overrides; coarser levels of the finest one only)
+#define NF_REPLICATE_BELOW 768
 #define NF_SMOOTH_HALO NF_HALO  // halo rows kept valid around the iterate: 6 for a smoother launch (2 * 3 sweeps),
                                 // +1 / +2 when the residual norms / the restriction ride on it
 
@@ -358,6 +362,10 @@ int nfi_mg_create(nf_team* team, nf_mg** out, int nx, int ny, int ld, const nf_m
       if (cut)
         for (int r = 0; r < team->world; ++r)
           if (L.rge[r] - L.rgb[r] < NF_MIN_SLAB_ROWS) cut = false;
+      {
+        static const int below = getenv("NF_REPLICATE_BELOW") ? atoi(getenv("NF_REPLICATE_BELOW")) : NF_REPLICATE_BELOW;
+        if (n <= below) cut = false;
+      }
       g.dist = cut;
       g.halo = cut ? NF_HALO : 0;
       if (cut) { g.gb = L.rgb; g.ge = L.rge; }
