@@ -224,6 +224,7 @@ def main():
     recs = alg.iterate_resident(args.steps, 0.0)
     e1.record()
     barrier()
+    launches = ctx.launches() - l0        # kernels launched (graph nodes included) inside the timed region
     # phases of the step on the following `steps` iterations (4 CUDA events per iteration between the phases' launches;
     # the V-cycle graph is still replayed): momentum predictor / pressure solve incl. RHS + hierarchy / corrections
     alg.phase_timing(True)
@@ -238,7 +239,6 @@ def main():
         alg.iterate_resident(2, 0.0)
         live_ms, live_launches = alg.smoother_timing(False)
     ms = e0.elapsed_time(e1)
-    launches = ctx.launches() - l0
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local}")
     if world > 1:

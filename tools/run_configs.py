@@ -156,6 +156,14 @@ def c4(n):
         x.zero_()
         ms = timed(lambda: ctx.check(call(300)))
         rec["solvers"][name] = {"ms_per_iteration": ms / 300, "MLUPS": cells * 300 / ms / 1e3, "rel_residual_after_300": relres()}
+    # sequential Gauss-Seidel of the reference's `04 gauss_seidel` script (lexicographic, omega 1.8) and the symmetric variant:
+    # block wavefronts (nf_gs_lex.cu), 20 sweeps
+    for name, sym in (("gs_lexicographic_w1.8", 0), ("gs_symmetric_w1.8", 1)):
+        x.zero_()
+        ctx.check(lib.nf_gs_lex_sweeps(H, G, ptr(x), ptr(b), ptr(du), ptr(dv), 1.8, 1, sym))
+        x.zero_()
+        ms = timed(lambda: ctx.check(lib.nf_gs_lex_sweeps(H, G, ptr(x), ptr(b), ptr(du), ptr(dv), 1.8, 20, sym)))
+        rec["solvers"][name] = {"ms_per_iteration": ms / 20, "MLUPS": cells * 20 / ms / 1e3, "rel_residual_after_20": relres()}
     # Krylov
     work = torch.zeros((5 * (n + 1), pad_ld(n)), dtype=torch.float64, device=x.device)
     for name, fn in (("bicgstab", lib.nf_bicgstab_solve), ("cg", lib.nf_cg_solve)):
@@ -184,6 +192,11 @@ def c4(n):
     t0 = time.perf_counter(); O.jacobi_iterate(np.zeros_like(bh), bh, dx, dy, 1.0, d_u, d_v, 0.8, 1); cpu["jacobi_iteration_ms"] = (time.perf_counter() - t0) * 1e3
     t0 = time.perf_counter(); O.rb_sor(np.zeros_like(bh), bh, dx, dy, 1.0, d_u, d_v, 1.5, 1); cpu["rbsor_sweep_ms"] = (time.perf_counter() - t0) * 1e3
     if n <= 2049:
+        ns = 257   # the sequential sweep is a Python-level loop in the reference: timed on a 257^2 sample, scaled per cell
+        rs = np.random.default_rng(5)
+        dus, dvs = (0.7 * dy / 4e-3) * (1 + 0.1 * rs.random((ns + 1, ns))), (0.7 * dx / 4e-3) * (1 + 0.1 * rs.random((ns, ns + 1)))
+        t0 = time.perf_counter(); O.gs_lex(np.zeros((ns, ns)), 1e-2 * rs.standard_normal((ns, ns)), dx, dy, 1.0, dus, dvs, 1.8, 1)
+        cpu["gs_lexicographic_sweep_ms_scaled_from_257"] = (time.perf_counter() - t0) * 1e3 * (n * n) / (ns * ns)
         mcfg = O.MGConfig(omega=1.5, pre=3, post=3)
         t0 = time.perf_counter(); O.mg_cycle(mcfg, np.zeros_like(bh), bh, dx, dy, d_u, d_v); cpu["mg_v33_cycle_ms"] = (time.perf_counter() - t0) * 1e3
     rec["cpu_oracle_port_single_thread"] = cpu
