@@ -37,6 +37,8 @@ struct nf_smooth_extra {  // see nf_rbsor_fused.cu
   double* coarse_b = nullptr;
   double* out = nullptr;
   bool fused = false;
+  double* in_norm_out = nullptr;
+  bool in_norm_fused = false;
 };
 int nfi_rbsor_fused_x(nf_ctx*, const nf_grid*, double** p, double** palt, const double* b, const double* d_u,
                       const double* d_v, const double* inv, double omega, int n_sweeps, nf_smooth_extra* extra);
@@ -78,6 +80,9 @@ struct nf_mg {
   cudaStream_t cap_stream = nullptr;
   const void* graph_key[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // x, b, d_u, d_v, x2 of level 0
   int graph_kind = -1;
+  int graph_part = 0;
+  bool graph_want_norm = true;
+  bool graph_swapped = false;  // the captured launches leave level 0's x / x2 exchanged (odd number of smoother launches)
   bool graph_norm_fused = false;
   long long graph_nodes = 0;
   int warm_cycles = 0;
@@ -649,37 +654,51 @@ static int mg_publish_rhs(nf_mg* mg, int l) {
 // one V (kind 0) or W (kind 1) cycle on level l: multigrid.py:304-432 / :434-560
 // want_norm (level 0 of the 'v' / 'w' loop): ask the last post-smoothing launch for the residual norms
 // (-> mg->scal[0][0..1]); *norm_fused reports whether that happened
-static int mg_cycle(nf_mg* mg, int l, int kind, bool want_norm = false, bool* norm_fused = nullptr) {
+// part: 0 = the whole cycle; 1 = head only (pre-smoothing, residual, restriction, coarse x = 0, RHS published);
+//       2 = the rest (coarse levels, prolongation, post-smoothing).  in_norm (head of level 0): ask the pre-smoothing
+//       launch for the residual norms of its INPUT iterate (-> mg->scal[k][0..1]); *in_norm_fused reports whether it did.
+static int mg_cycle(nf_mg* mg, int l, int kind, bool want_norm = false, bool* norm_fused = nullptr, int part = 0,
+                    bool in_norm = false, bool* in_norm_fused = nullptr) {
   nf_ctx* ctx = mg->ctx;
   nf_team* team = mg->team;
   MgLevel& L = mg->lv[l];
   const int nl = nlocal(mg);
   if (norm_fused) *norm_fused = false;
-  if (L.geom.nx <= mg->cfg.coarsest || l + 1 == (int)mg->lv.size()) return mg_coarse_solve(mg, l);
+  if (in_norm_fused) *in_norm_fused = false;
+  if (L.geom.nx <= mg->cfg.coarsest || l + 1 == (int)mg->lv.size()) return part == 1 ? NF_OK : mg_coarse_solve(mg, l);
   MgLevel& C = mg->lv[l + 1];
-  std::vector<nf_smooth_extra> pre(nl);
-  const bool want_pre = mg->cfg.smoother == 0 && mg->cfg.restriction == 0;
-  if (want_pre)
+  if (part != 2) {
+    std::vector<nf_smooth_extra> pre(nl);
+    const bool want_pre = mg->cfg.smoother == 0 && mg->cfg.restriction == 0;
+    if (want_pre)
+      for (int k = 0; k < nl; ++k) {
+        pre[k].mode = 2;
+        pre[k].gc = restrict_target(C, team->local[k]);
+        pre[k].coarse_b = C.s[k].b;
+        if (in_norm) pre[k].in_norm_out = mg->scal[k];
+      }
+    NF_TRY(mg_smooth(mg, l, mg->cfg.pre, want_pre ? pre.data() : nullptr));
+    if (in_norm_fused) {
+      bool all = want_pre && in_norm;
+      for (int k = 0; k < nl; ++k) all = all && pre[k].in_norm_fused;
+      *in_norm_fused = all;  // same decision on every rank: it depends on the level geometry only
+    }
     for (int k = 0; k < nl; ++k) {
-      pre[k].mode = 2;
-      pre[k].gc = restrict_target(C, team->local[k]);
-      pre[k].coarse_b = C.s[k].b;
+      const int r = team->local[k];
+      const nf_grid gf = L.geom.grid(r), gc = restrict_target(C, r);
+      if (pre[k].fused) {
+        // coarse right-hand side already written by the smoother
+      } else if (mg->cfg.restriction == 0) {
+        NF_TRY(nfi_residual_restrict_fw(ctx, &gf, L.s[k].x, L.s[k].b, L.s[k].d_u, L.s[k].d_v, &gc, C.s[k].b));
+      } else {
+        NF_TRY(nfi_residual(ctx, &gf, L.s[k].x, L.s[k].b, L.s[k].d_u, L.s[k].d_v, L.s[k].r));
+        NF_TRY(nfi_restrict_inject(ctx, &gf, L.s[k].r, &gc, C.s[k].b));
+      }
+      NF_TRY(nfi_fill(ctx, C.s[k].x, C.geom.elems(r), 0.0));
     }
-  NF_TRY(mg_smooth(mg, l, mg->cfg.pre, want_pre ? pre.data() : nullptr));
-  for (int k = 0; k < nl; ++k) {
-    const int r = team->local[k];
-    const nf_grid gf = L.geom.grid(r), gc = restrict_target(C, r);
-    if (pre[k].fused) {
-      // coarse right-hand side already written by the smoother
-    } else if (mg->cfg.restriction == 0) {
-      NF_TRY(nfi_residual_restrict_fw(ctx, &gf, L.s[k].x, L.s[k].b, L.s[k].d_u, L.s[k].d_v, &gc, C.s[k].b));
-    } else {
-      NF_TRY(nfi_residual(ctx, &gf, L.s[k].x, L.s[k].b, L.s[k].d_u, L.s[k].d_v, L.s[k].r));
-      NF_TRY(nfi_restrict_inject(ctx, &gf, L.s[k].r, &gc, C.s[k].b));
-    }
-    NF_TRY(nfi_fill(ctx, C.s[k].x, C.geom.elems(r), 0.0));
+    NF_TRY(mg_publish_rhs(mg, l));
+    if (part == 1) return NF_OK;
   }
-  NF_TRY(mg_publish_rhs(mg, l));
   const int reps = (kind == 1) ? 2 : 1;
   for (int rep = 0; rep < reps; ++rep) NF_TRY(mg_cycle(mg, l + 1, kind));
   NF_TRY(mg_prolong(mg, l, mg->cfg.interpolation, 1));
@@ -702,7 +721,8 @@ static int mg_cycle(nf_mg* mg, int l, int kind, bool want_norm = false, bool* no
 // One cycle at level 0 through a CUDA graph when possible (see nf_mg::graph_exec).  The launch sequence of a
 // cycle is static: ~50 launches (10 levels) collapse into one graph launch, which removes the CPU launch cost and
 // most of the inter-kernel gaps on the small levels.
-static int mg_cycle_top(nf_mg* mg, int kind, bool* norm_fused) {
+// part / want_norm as in mg_cycle (part 2 with want_norm = false is the body of a "lookahead norm" cycle)
+static int mg_cycle_top(nf_mg* mg, int kind, bool* norm_fused, int part = 0, bool want_norm = true) {
   nf_ctx* ctx = mg->ctx;
   MgLevel& L = mg->lv[0];
   const char* env = getenv("NF_MG_GRAPH");
@@ -713,20 +733,21 @@ static int mg_cycle_top(nf_mg* mg, int kind, bool* norm_fused) {
   const bool allowed = mg->use_graph && !(env && env[0] == '0') && nlocal(mg) == 1 && dist_ok &&
                        mg->cfg.smoother == 0 && !mg->timing &&
                        ((mg->cfg.pre + 2) / 3 + (mg->cfg.post + 2) / 3) % 2 == 0;  // even number of x/x2 swaps
-  if (!allowed) return mg_cycle(mg, 0, kind, true, norm_fused);
+  if (!allowed) return mg_cycle(mg, 0, kind, want_norm, norm_fused, part);
   MgSlab& S = L.s[0];
   const void* key[5] = {S.x, S.b, S.d_u, S.d_v, S.x2};
-  bool same = mg->graph_exec && mg->graph_kind == kind;
+  bool same = mg->graph_exec && mg->graph_kind == kind && mg->graph_part == part && mg->graph_want_norm == want_norm;
   for (int q = 0; q < 5 && same; ++q) same = (key[q] == mg->graph_key[q]);
   if (same) {
     NF_CHECK_CUDA(ctx, cudaGraphLaunch(mg->graph_exec, ctx->stream));
     ctx->launches += mg->graph_nodes;
     *norm_fused = mg->graph_norm_fused;
+    if (mg->graph_swapped) { double* t = S.x; S.x = S.x2; S.x2 = t; }  // what the launches did to the host's pointers
     return NF_OK;
   }
   if (mg->warm_cycles < 1) {  // first cycle ever: plain launches (function attributes, tensor-map encoder, ...)
     mg->warm_cycles++;
-    return mg_cycle(mg, 0, kind, true, norm_fused);
+    return mg_cycle(mg, 0, kind, want_norm, norm_fused, part);
   }
   if (mg->graph_exec) { cudaGraphExecDestroy(mg->graph_exec); mg->graph_exec = nullptr; }
   if (!mg->cap_stream) NF_CHECK_CUDA(ctx, cudaStreamCreateWithFlags(&mg->cap_stream, cudaStreamNonBlocking));
@@ -735,7 +756,7 @@ static int mg_cycle_top(nf_mg* mg, int kind, bool* norm_fused) {
   NF_CHECK_CUDA(ctx, cudaStreamBeginCapture(mg->cap_stream, cudaStreamCaptureModeRelaxed));
   ctx->stream = mg->cap_stream;
   bool nf = false;
-  int st = mg_cycle(mg, 0, kind, true, &nf);
+  int st = mg_cycle(mg, 0, kind, want_norm, &nf, part);
   ctx->stream = orig;
   cudaGraph_t graph = nullptr;
   cudaError_t ce = cudaStreamEndCapture(mg->cap_stream, &graph);
@@ -745,10 +766,11 @@ static int mg_cycle_top(nf_mg* mg, int kind, bool* norm_fused) {
     mg->use_graph = false;  // fall back to plain launches for good
     ctx->launches = l0;
     if (st != NF_OK) return st;
-    return mg_cycle(mg, 0, kind, true, norm_fused);
+    return mg_cycle(mg, 0, kind, want_norm, norm_fused, part);
   }
   mg->graph_nodes = ctx->launches - l0;
   mg->graph_norm_fused = nf;
+  mg->graph_swapped = (S.x != key[0]);
   ctx->launches = l0;
   ce = cudaGraphInstantiate(&mg->graph_exec, graph, 0);
   cudaGraphDestroy(graph);
@@ -756,10 +778,12 @@ static int mg_cycle_top(nf_mg* mg, int kind, bool* norm_fused) {
     cudaGetLastError();
     mg->graph_exec = nullptr;
     mg->use_graph = false;
-    return mg_cycle(mg, 0, kind, true, norm_fused);
+    return mg_cycle(mg, 0, kind, want_norm, norm_fused, part);
   }
   for (int q = 0; q < 5; ++q) mg->graph_key[q] = key[q];
   mg->graph_kind = kind;
+  mg->graph_part = part;
+  mg->graph_want_norm = want_norm;
   NF_CHECK_CUDA(ctx, cudaGraphLaunch(mg->graph_exec, ctx->stream));
   ctx->launches += mg->graph_nodes;
   *norm_fused = nf;
@@ -896,7 +920,57 @@ int nfi_mg_solve(nf_mg* mg, double* const* b, double* const* x, double* const* r
       status = mg_rel_residual(mg, 0, &rn, &bn, sync);
     } else {
       bool fused_any = false;
+      // "Lookahead norm": the pre-smoothing launch of cycle k+1 evaluates ||b - A x_k|| of its input while it sets up
+      // its tiles (no deeper halo, unlike a norm fused behind the post-smoother), the host reads it and either lets the
+      // rest of cycle k+1 run or -- converged after k cycles, multigrid.py:185-240 -- drops the launch's output (x_k is
+      // still intact in the other buffer).  One wasted pre-smoothing launch per solve buys a plain post-smoother in
+      // every cycle.  Needs the fused path of the level-0 pre-smoother (one launch: 1..3 sweeps, TMA variant).
+      const char* envl = getenv("NF_MG_LOOKAHEAD");
+      bool lookahead = !(envl && envl[0] == '0') && mg->cfg.smoother == 0 && mg->cfg.restriction == 0 &&
+                       mg->cfg.pre >= 1 && mg->cfg.pre <= 3 && mg->lv.size() > 1 && L.geom.nx > mg->cfg.coarsest;
+      bool have_final_norm = false;
       for (int it = 0; it < mg->cfg.max_iterations; ++it) {
+        if (lookahead) {
+          std::vector<double*> x_before(nlocal(mg)), x2_before(nlocal(mg));
+          for (int k = 0; k < nlocal(mg); ++k) { x_before[k] = L.s[k].x; x2_before[k] = L.s[k].x2; }
+          bool inz = false;
+          status = mg_cycle(mg, 0, mg->cfg.cycle_type, false, nullptr, 1, true, &inz);
+          if (status) break;
+          if (inz) {
+            fused_any = true;
+            double rin = 0.0, bin = bn;
+            status = mg_rel_residual(mg, 0, &rin, &bin, 1, true);  // all-reduce (slabs) + 16-byte D2H + sync
+            if (status) break;
+            bn = bin;
+            if (it > 0) {
+              rn = rin;
+              const double rel = bn > 0.0 ? rn / bn : rn;
+              if (rel < mg->cfg.tolerance) {  // converged after `it` cycles: forget the speculative pre-smoothing
+                for (int k = 0; k < nlocal(mg); ++k) { L.s[k].x = x_before[k]; L.s[k].x2 = x2_before[k]; }
+                have_final_norm = true;
+                break;
+              }
+            }
+            bool nfz = false;
+            status = mg_cycle_top(mg, mg->cfg.cycle_type, &nfz, 2, false);
+            if (status) break;
+            ++cycles;
+            continue;
+          }
+          // the level is too small for the fused path: the head ran as a plain pre-smoothing; finish this cycle the
+          // classic way and stay there
+          lookahead = false;
+          bool nfz = false;
+          status = mg_cycle(mg, 0, mg->cfg.cycle_type, true, &nfz, 2);
+          if (status) break;
+          ++cycles;
+          status = mg_rel_residual(mg, 0, &rn, &bn, 1, nfz);
+          if (status) break;
+          fused_any = fused_any || nfz;
+          const double rel = bn > 0.0 ? rn / bn : rn;
+          if (rel < mg->cfg.tolerance) { have_final_norm = true; break; }
+          continue;
+        }
         bool nfz = false;
         status = mg_cycle_top(mg, mg->cfg.cycle_type, &nfz);
         if (status) break;
@@ -904,9 +978,12 @@ int nfi_mg_solve(nf_mg* mg, double* const* b, double* const* x, double* const* r
         status = mg_rel_residual(mg, 0, &rn, &bn, 1, nfz);
         if (status) break;
         fused_any = fused_any || nfz;
+        have_final_norm = true;
         const double rel = bn > 0.0 ? rn / bn : rn;
         if (rel < mg->cfg.tolerance) break;
       }
+      if (!status && lookahead && !have_final_norm && cycles > 0)  // ran out of cycles: the norm after the last one
+        status = mg_rel_residual(mg, 0, &rn, &bn, 1);
       if (!status && fused_any)  // the residual field itself (info['field']) once, at the end
         for (int k = 0; k < nlocal(mg) && !status; ++k) {
           const nf_grid g0 = L.geom.grid(mg->team->local[k]);

@@ -311,13 +311,17 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
 //   1  residual norms: sum (b - A p)^2 and sum b^2 over the level (the multigrid convergence test after the
 //      post-smoothing, multigrid.py:185-240) -- saves a 40 B/cell pass
 //   2  residual + full-weighting restriction: coarse_b = FW(b - A p) (multigrid.py:362-372 after the
-//      pre-smoothing) -- saves a 34 B/cell pass
+//      pre-smoothing) -- saves a 34 B/cell pass.  With ex.in_norm the launch also evaluates the residual norms of its
+//      INPUT iterate while the tile is being set up (neighbours are in the halo anyway, no deeper halo needed): the
+//      pre-smoother of cycle k+1 thereby delivers the convergence test of cycle k, and the post-smoother runs without
+//      extra work (nf_mg.cu, "lookahead norm")
 struct TmaExtra {
   nf_grid gc;               // coarse grid (mode 2)
   double* coarse_b;         // mode 2
-  double* partials;         // mode 1: per-CTA partial sums, ticket, result (2 doubles)
+  double* partials;         // mode 1 (and mode 2 with in_norm): per-CTA partial sums, ticket, result (2 doubles)
   unsigned int* ticket;
   double* out;
+  int in_norm;              // mode 2: also sum (b - A p_in)^2 and sum b^2 of the INPUT iterate -> out[0..1]
 };
 
 template <int NS, int EXTRA>
@@ -331,7 +335,8 @@ struct TileGeom {
 constexpr int SM_SD = SM_BAR + 16;                      // sD[2][48][33]: aP of boundary tiles (EXTRA != 0)
 constexpr int SM_SR = SM_SD + 2 * RRW * 33 * 8;         // sR[48][65]: fine residual of the tile (EXTRA == 2)
 constexpr int SM_TOTAL_X1 = SM_SR;
-constexpr int SM_TOTAL_X2 = SM_SR + RRW * 65 * 8;
+constexpr int SM_SN = SM_SR + RRW * 65 * 8;             // sN[512][2]: per-thread sums of the input-residual norms (EXTRA == 2)
+constexpr int SM_TOTAL_X2 = SM_SN + 32 * NYT * 2 * 8;
 
 template <int NS, bool HAS_INV, int EXTRA>
 __global__ void __launch_bounds__(32 * NYT, 1)
@@ -346,6 +351,7 @@ k_rbsor_tma(nf_grid g, const __grid_constant__ CUtensorMap map_p, const __grid_c
   double (&sP)[2][RRW][33] = *reinterpret_cast<double (*)[2][RRW][33]>(smem + SM_SP);
   double (&sD)[2][RRW][33] = *reinterpret_cast<double (*)[2][RRW][33]>(smem + SM_SD);
   double (&sR)[RRW][65] = *reinterpret_cast<double (*)[RRW][65]>(smem + SM_SR);
+  double* sN = reinterpret_cast<double*>(smem + SM_SN);
   const double* stP = reinterpret_cast<const double*>(smem + ST_P);
   const double* stB = reinterpret_cast<const double*>(smem + ST_B);
   const double* stDU = reinterpret_cast<const double*>(smem + ST_DU);
@@ -370,6 +376,10 @@ k_rbsor_tma(nf_grid g, const __grid_constant__ CUtensorMap map_p, const __grid_c
     if (HAS_INV) tma_load_2d(st_base + ST_INV, &map_inv, rj, ri - g.row0, bar);
   };
 
+  if (EXTRA == 2) {
+    sN[2 * (ty * 32 + tx)] = 0.0;
+    sN[2 * (ty * 32 + tx) + 1] = 0.0;
+  }
   if (leader) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -458,6 +468,52 @@ k_rbsor_tma(nf_grid g, const __grid_constant__ CUtensorMap map_p, const __grid_c
     __syncthreads();  // staging fully consumed, sP complete
     if (leader && tile + (int)gridDim.x < n_tiles) issue(tile + gridDim.x);
 
+    if (EXTRA == 2) {
+      if (ex.in_norm) {
+        // residual of the INPUT iterate on this tile's cells, from the registers and the initial sP (same expression
+        // order as the stand-alone residual: nf_Ap_cell)
+        const int par = ty & 1;
+        double s_r = 0.0, s_b = 0.0;
+#pragma unroll
+        for (int k = 0; k < KS; ++k) {
+          const int r = ty + NYT * k;
+          const int gi = i0 + r;
+          const bool rin = r >= HR && r < HR + TR && gi < g.ge;
+          const bool cin0 = c0 >= HC && c0 < HC + TC && gj0 < g.ny;
+          const bool cin1 = c0 >= HC && c0 < HC + TC && gj0 + 1 < g.ny;
+          if (rin && cin0) {
+            const int rmk = r - 1, rpk = r + 1;
+            {
+              const int lp = par;
+              const double d = interior ? ((aE0[k] + aW0[k]) + aN0[k]) + aS0[k] : sD[lp][r][tx];
+              double o = d * p0[k];
+              o -= aE0[k] * sP[lp ^ 1][rpk][tx];
+              o -= aW0[k] * sP[lp ^ 1][rmk][tx];
+              o -= aN0[k] * p1[k];
+              o -= aS0[k] * sP[lp ^ 1][r][tx > 0 ? tx - 1 : 0];
+              const double res = b0[k] - o;
+              s_r += res * res;
+              s_b += b0[k] * b0[k];
+            }
+            if (cin1) {
+              const int lp = par ^ 1;
+              const double d = interior ? ((aE1[k] + aW1[k]) + aN1[k]) + aS1[k] : sD[lp][r][tx];
+              double o = d * p1[k];
+              o -= aE1[k] * sP[lp ^ 1][rpk][tx];
+              o -= aW1[k] * sP[lp ^ 1][rmk][tx];
+              o -= aN1[k] * sP[lp ^ 1][r][tx + 1];
+              o -= aS1[k] * p0[k];
+              const double res = b1[k] - o;
+              s_r += res * res;
+              s_b += b1[k] * b1[k];
+            }
+          }
+        }
+        sN[2 * (ty * 32 + tx)] += s_r;       // own slot, fixed tile order: deterministic
+        sN[2 * (ty * 32 + tx) + 1] += s_b;
+      }
+    }
+
     if ((i0 + ty + j0) & 1)
       rbsor_passes<NS, 1>(sP, tx, ty, omega, p0, p1, b0, b1, inv0, inv1, aE0, aW0, aN0, aS0, aE1, aW1, aN1, aS1, ok0, ok1);
     else
@@ -537,6 +593,13 @@ k_rbsor_tma(nf_grid g, const __grid_constant__ CUtensorMap map_p, const __grid_c
     }
   }
   if (EXTRA == 1) nf_block_reduce_store<2>(nrm, ex.partials, ex.ticket, ex.out);
+  if (EXTRA == 2) {
+    if (ex.in_norm) {
+      nrm[0] = sN[2 * (ty * 32 + tx)];
+      nrm[1] = sN[2 * (ty * 32 + tx) + 1];
+      nf_block_reduce_store<2>(nrm, ex.partials, ex.ticket, ex.out);
+    }
+  }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -626,12 +689,14 @@ struct nf_smooth_extra {
   double* coarse_b = nullptr;
   double* out = nullptr;
   bool fused = false;
+  double* in_norm_out = nullptr;  // mode 2: also the residual norms of the input iterate -> in_norm_out[0..1]
+  bool in_norm_fused = false;
 };
 
 // inv (optional): precomputed 1/aP of this level (nfi_inv_diag); NULL = divide inside the kernel
 int nfi_rbsor_fused_x(nf_ctx* ctx, const nf_grid* g, double** p, double** palt, const double* b, const double* d_u,
                       const double* d_v, const double* inv, double omega, int n_sweeps, nf_smooth_extra* extra) {
-  if (extra) extra->fused = false;
+  if (extra) { extra->fused = false; extra->in_norm_fused = false; }
   if (n_sweeps == 0) {  // the reference still pins p[0,0] = 0 (gauss_seidel.py:145)
     if (g->row0 == 0 && g->gb == 0) NF_CHECK_CUDA(ctx, cudaMemsetAsync(*p, 0, sizeof(double), ctx->stream));
     return NF_OK;
@@ -649,6 +714,7 @@ int nfi_rbsor_fused_x(nf_ctx* ctx, const nf_grid* g, double** p, double** palt, 
     bool used = false;
     TmaExtra ex;
     ex.coarse_b = nullptr; ex.partials = ctx->partials; ex.ticket = ctx->ticket; ex.out = nullptr;
+    ex.in_norm = 0;
     ex.gc = *g;
     int mode = 0;
     // extra work rides on the last launch; it needs the precomputed 1/aP, an unsplit grid and even tile origins
@@ -658,6 +724,10 @@ int nfi_rbsor_fused_x(nf_ctx* ctx, const nf_grid* g, double** p, double** palt, 
       ex.gc = extra->gc;
       ex.coarse_b = extra->coarse_b;
       ex.out = extra->out;
+      if (mode == 2 && extra->in_norm_out && left == n_sweeps) {  // the launch that sees the call's input iterate
+        ex.in_norm = 1;
+        ex.out = extra->in_norm_out;
+      }
     }
     if (use_tma) {  // persistent TMA pipeline: pays off once every SM gets several tiles
       if (ns == 3) st = launch_tma_any<3>(ctx, g, *p, *palt, b, d_u, d_v, inv, omega, mode, ex, &used);
@@ -665,6 +735,7 @@ int nfi_rbsor_fused_x(nf_ctx* ctx, const nf_grid* g, double** p, double** palt, 
       else st = launch_tma_any<1>(ctx, g, *p, *palt, b, d_u, d_v, inv, omega, mode, ex, &used);
       if (st != NF_OK) return st;
       if (used && mode != 0) extra->fused = true;
+      if (used && mode == 2 && ex.in_norm) extra->in_norm_fused = true;
     }
     if (!used) {
       if (ns == 3) st = launch_fused<3>(ctx, g, *p, *palt, b, d_u, d_v, inv, omega);

@@ -654,3 +654,51 @@ def test_simple_loop_with_lexicographic_gauss_seidel_vs_oracle():
         st, _ = O.simple_solve(n, n, Re, ps, n_sweeps=k, max_iterations=N, tolerance=0.0)
         for fld in ("u", "v", "p"):
             assert rel(getattr(alg, fld), getattr(st, fld)) < 1e-12, (mt, fld)
+
+
+@pytest.mark.parametrize("n,kw", [(257, dict(tolerance=1e-4)), (513, dict(tolerance=1e-6, pre_smoothing=2, post_smoothing=1)),
+                                  (300, dict(tolerance=1e-30, max_iterations=4)), (385, dict(tolerance=1e-5, cycle_type="w")),
+                                  (200, dict(tolerance=1e-4, pre_smoothing=5))])
+def test_multigrid_lookahead_norm_equals_classic_convergence_test(n, kw, monkeypatch):
+    """The convergence test of cycle k evaluated by the pre-smoothing launch of cycle k+1 ("lookahead norm", nf_mg.cu)
+    stops after the same cycle with the same iterate (bit for bit) and reports the same residual norm / field as the test
+    fused behind the post-smoother (NF_MG_LOOKAHEAD=0); pre_smoothing > 3 (two launches) takes the classic path."""
+    import naviflow_b200 as nb
+    from oracle.make_golden import synth_pressure_inputs
+    s = synth_pressure_inputs(n, 7000 + n)
+    mesh, _ = cavity(n, 1000)
+    monkeypatch.setenv("NF_RBSOR_TMA", "0")        # TMA pipeline (and with it the fused extras) at every level >= 64 rows
+    outs = []
+    for look in ("1", "0"):
+        monkeypatch.setenv("NF_MG_LOOKAHEAD", look)
+        args = dict(max_iterations=100, tolerance=1e-4, pre_smoothing=3, post_smoothing=3)
+        args.update(kw)
+        ps = nb.GpuMultiGridSolver(smoother=nb.GpuGaussSeidelSolver(omega=1.5), **args)
+        for rep in range(2):   # the second solve replays the captured graph of the cycle body
+            p, info = ps.solve(mesh, s["u_star"], s["v_star"], s["d_u"], s["d_v"], None)
+        outs.append((p, info, ps.last_info.cycles))
+    assert outs[0][2] == outs[1][2]
+    np.testing.assert_array_equal(outs[0][0], outs[1][0])
+    assert abs(outs[0][1]["rel_norm"] - outs[1][1]["rel_norm"]) <= 1e-10 * outs[1][1]["rel_norm"]
+    np.testing.assert_allclose(outs[0][1]["field"], outs[1][1]["field"], rtol=0, atol=1e-18 + 1e-12 * np.abs(outs[1][1]["field"]).max())
+
+
+def test_multigrid_lookahead_norm_on_slabs(monkeypatch):
+    """Same on row slabs (the input norms of the slabs are all-reduced): identical fields and cycle counts."""
+    runs = []
+    for look in ("1", "0"):
+        monkeypatch.setenv("NF_MG_LOOKAHEAD", look)
+        import naviflow_b200 as nb
+        mesh, fluid = cavity(1281, 1000)
+        ps = nb.GpuMultiGridSolver(smoother=nb.GpuGaussSeidelSolver(omega=1.5), max_iterations=100, tolerance=1e-3,
+                                   pre_smoothing=3, post_smoothing=3)
+        alg = nb.GpuSimpleSolver(mesh, fluid, ps, nb.GpuJacobiMomentumSolver(n_jacobi_sweeps=3), alpha_p=0.3, alpha_u=0.7,
+                                 virtual_ranks=2)
+        alg.set_boundary_condition("top", "velocity", {"u": 1.0, "v": 0.0})
+        for b in ("bottom", "left", "right"):
+            alg.set_boundary_condition(b, "wall")
+        alg.solve(max_iterations=3, tolerance=0.0)
+        runs.append((alg.u.copy(), alg.v.copy(), alg.p.copy(), list(alg.pressure_iterations_history)))
+    assert runs[0][3] == runs[1][3]
+    for a, b in zip(runs[0][:3], runs[1][:3]):
+        np.testing.assert_array_equal(a, b)
