@@ -290,13 +290,14 @@ def main():
     if live_launches > 0 and n_alg == n:   # the number the roofline is quoted on: launches inside the real steps
         ms_launch = live_ms / live_launches
         if os.environ.get("NF_RBSOR_EXTRA", "1") != "0":
-            # inside the V-cycle every finest-level launch also carries the residual work of its cycle half:
-            # pre-smoothing + residual + full-weighting restriction (120 + 34 B/cell) and post-smoothing + residual
-            # norms (120 + 40 B/cell), alternating: 157 B/cell on average (SURVEY 8d figures)
+            # inside the V-cycle the finest-level pre-smoothing launch also carries the residual work of the cycle:
+            # residual + full-weighting restriction (34 B/cell) and the residual norms of its input = the convergence
+            # test of the previous cycle (40 B/cell) on top of 3 sweeps (120 B/cell); the post-smoothing launch is plain
+            # (120 B/cell): (194 + 120) / 2 = 157 B/cell per launch on average (SURVEY 8d figures)
             alg_bytes = 157.0 * n * n
         achieved = alg_bytes / (ms_launch * 1e-3) / 1e9
-    roofline = {"kernel": "k_rbsor_tma<3> (finest level: 3 red-black SOR sweeps = 6 colour passes per launch, with the "
-                          "residual+restriction / residual-norm pass of the V-cycle fused behind the last colour pass)",
+    roofline = {"kernel": "k_rbsor_tma<3> (finest level: 3 red-black SOR sweeps = 6 colour passes per launch; the pre-smoothing "
+                          "launch also carries the V-cycle's residual + restriction and the convergence-test norms)",
                 "bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                 "frac": achieved / peak, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms_launch,
                 "launches_timed": int(live_launches) if (live_launches > 0 and n_alg == n) else reps,
