@@ -201,3 +201,21 @@ int nfi_restrict_inject(nf_ctx*, const nf_grid* fine, const double* f, const nf_
 int nfi_restrict_coeffs(nf_ctx*, const nf_grid* fine, const double* d_u, const double* d_v, const nf_grid* coarse,
                         double* d_u_c, double* d_v_c);
 int nfi_prolong_linear(nf_ctx*, const nf_grid* coarse, const double* c, const nf_grid* fine, double* f, int add);
+
+// Work fused behind the last launch of a smoothing call (persistent TMA kernel only; nf_rbsor_fused.cu):
+//   mode 1: sum (b - A p)^2 -> out[0], sum b^2 -> out[1];  mode 2: coarse_b = FW(b - A p) on the coarse grid gc and,
+//   with in_norm_out, the residual norms of the launch's INPUT iterate -> in_norm_out[0..1] (lookahead convergence test).
+// *fused / *in_norm_fused tell the caller whether the work was done (otherwise it runs the stand-alone kernels).
+struct nf_smooth_extra {
+  int mode = 0;
+  nf_grid gc;
+  double* coarse_b = nullptr;
+  double* out = nullptr;
+  bool fused = false;
+  double* in_norm_out = nullptr;
+  bool in_norm_fused = false;
+};
+// n_sweeps red-black SOR sweeps, double buffered (*p input / result, *palt scratch; swapped once per launch);
+// inv (optional): precomputed 1/aP of the level
+int nfi_rbsor_fused_x(nf_ctx*, const nf_grid*, double** p, double** palt, const double* b, const double* d_u,
+                      const double* d_v, const double* inv, double omega, int n_sweeps, nf_smooth_extra* extra);

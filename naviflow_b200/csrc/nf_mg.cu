@@ -31,17 +31,6 @@
 
 int nfi_residual_restrict_fw(nf_ctx*, const nf_grid* gf, const double* p, const double* b, const double* d_u,
                              const double* d_v, const nf_grid* gc, double* c);
-struct nf_smooth_extra {  // see nf_rbsor_fused.cu
-  int mode = 0;
-  nf_grid gc;
-  double* coarse_b = nullptr;
-  double* out = nullptr;
-  bool fused = false;
-  double* in_norm_out = nullptr;
-  bool in_norm_fused = false;
-};
-int nfi_rbsor_fused_x(nf_ctx*, const nf_grid*, double** p, double** palt, const double* b, const double* d_u,
-                      const double* d_v, const double* inv, double omega, int n_sweeps, nf_smooth_extra* extra);
 int nfi_inv_diag(nf_ctx*, const nf_grid*, const double* d_u, const double* d_v, double* inv);
 int nfi_prolong_banded(nf_ctx*, const nf_grid* gc, const double* c, const nf_grid* gf, double* f, double* tmp,
                        int ldt, const double* band, const int* start, int W, int add);

@@ -680,19 +680,6 @@ int launch_tma_any(nf_ctx* ctx, const nf_grid* g, const double* pin, double* pou
   return launch_tma<NS, false, 0>(ctx, g, pin, pout, b, d_u, d_v, nullptr, omega, ex, used);
 }
 
-// Work fused behind the last launch of a smoothing call (persistent TMA kernel only; see TmaExtra):
-//   mode 1: sum (b - A p)^2 -> out[0], sum b^2 -> out[1];  mode 2: coarse_b = FW(b - A p) on the coarse grid gc.
-// *fused tells the caller whether the extra work was done (otherwise it runs the stand-alone kernels).
-struct nf_smooth_extra {
-  int mode = 0;
-  nf_grid gc;
-  double* coarse_b = nullptr;
-  double* out = nullptr;
-  bool fused = false;
-  double* in_norm_out = nullptr;  // mode 2: also the residual norms of the input iterate -> in_norm_out[0..1]
-  bool in_norm_fused = false;
-};
-
 // inv (optional): precomputed 1/aP of this level (nfi_inv_diag); NULL = divide inside the kernel
 int nfi_rbsor_fused_x(nf_ctx* ctx, const nf_grid* g, double** p, double** palt, const double* b, const double* d_u,
                       const double* d_v, const double* inv, double omega, int n_sweeps, nf_smooth_extra* extra) {

@@ -34,8 +34,6 @@ int nfi_momentum_residual_unrelaxed(nf_ctx*, const nf_grid*, int is_u, nf_links 
                                     double* out);
 int nfi_correct_velocity(nf_ctx*, const nf_grid*, const nf_bc_program*, const double* us, const double* vs,
                          const double* pp, const double* d_u, const double* d_v, double* u, double* v);
-int nfi_rbsor_fused_x(nf_ctx*, const nf_grid*, double** p, double** palt, const double* b, const double* d_u,
-                      const double* d_v, const double* inv, double omega, int n_sweeps, struct nf_smooth_extra* extra);
 int nfi_gs_lex(nf_ctx*, const nf_grid*, double* p, const double* b, const double* d_u, const double* d_v, double omega,
                int n_sweeps, int symmetric);
 int nfi_krylov_team(nf_team* team, const LevelGeom& geom, int kind, double* const* b, double* const* x, double* const* d_u,

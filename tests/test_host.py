@@ -150,3 +150,51 @@ def test_ghia_errors_match_reference_golden(golden_dir):
     mesh = nb.StructuredMesh(63, 63)
     inf, l2 = nb.ghia_errors(g[key + "_u"], g[key + "_v"], mesh, 1000)
     np.testing.assert_allclose([inf, l2], g[key + "_ghia"], rtol=1e-12)
+
+
+def test_constructor_argument_errors_match_the_reference_classes():
+    """Argument validation happens on the host before any device work (gauss_seidel.py:38-39, matrix_free_momentum.py:31-33,
+    piso.py:73 -- n_corrections = 0 would leave p_res_info unbound there)."""
+    import naviflow_b200 as nb
+    with pytest.raises(ValueError):
+        nb.GpuGaussSeidelSolver(method_type="zebra")
+    for mt in ("red_black", "standard", "symmetric"):
+        assert nb.GpuGaussSeidelSolver(method_type=mt).method_type == mt
+    with pytest.raises(ValueError):
+        nb.GpuMatrixFreeMomentumSolver(solver_type="cholesky")
+    with pytest.raises(NotImplementedError):
+        nb.GpuMatrixFreeMomentumSolver(solver_type="idrs")
+    with pytest.raises(ValueError):
+        nb.GpuMatrixFreeMomentumSolver(discretization_scheme="central")
+    mesh = nb.StructuredMesh(17, 17, 1.0, 1.0)
+    fluid = nb.FluidProperties(density=1.0, reynolds_number=100, characteristic_velocity=1.0)
+    with pytest.raises(ValueError):
+        nb.GpuPisoSolver(mesh, fluid, nb.GpuJacobiSolver(), n_corrections=0)
+    piso = nb.GpuPisoSolver(mesh, fluid, nb.GpuJacobiSolver(tolerance=0.0, max_iterations=5), n_corrections=3)
+    assert piso.n_corrections == 3 and piso.u.shape == (18, 17) and piso.v.shape == (17, 18)
+
+
+def test_simple_config_struct_carries_the_plugin_settings():
+    """GpuSimpleSolver._config(): the nf_simple_config the C-ABI receives (no device needed)."""
+    import naviflow_b200 as nb
+    mesh = nb.StructuredMesh(33, 33, 1.0, 1.0)
+    fluid = nb.FluidProperties(density=1.0, reynolds_number=400, characteristic_velocity=1.0)
+    alg = nb.GpuPisoSolver(mesh, fluid, nb.GpuGaussSeidelSolver(tolerance=0.0, max_iterations=7, omega=1.8, method_type="symmetric"),
+                           nb.GpuMatrixFreeMomentumSolver(tolerance=1e-9, max_iterations=77), n_corrections=2, alpha_p=0.2,
+                           alpha_u=0.6)
+    alg.set_boundary_condition("top", "velocity", {"u": 1.0, "v": 0.0})
+    for b in ("bottom", "left", "right"):
+        alg.set_boundary_condition(b, "wall")
+    c = alg._config()
+    assert (c.nx, c.ny, c.pressure_solver, c.pressure_iterations, c.piso_corrections) == (33, 33, 6, 7, 2)
+    assert (c.momentum_solver, c.momentum_maxiter) == (1, 77) and c.momentum_tolerance == 1e-9
+    assert c.pressure_omega == 1.8 and c.alpha_p == 0.2 and c.alpha_u == 0.6 and c.sides == 15
+    assert abs(c.mu - 1.0 / 400) < 1e-18
+    # the Krylov momentum twin applies the BCs with the reference's nx+1 call: the v "right" edge is then skipped
+    assert c.bc.v_right_row == 32 and c.bc_mf.v_right_row == -1
+    simple = nb.GpuSimpleSolver(mesh, fluid, nb.GpuJacobiSolver(tolerance=0.0, max_iterations=3),
+                                nb.GpuJacobiMomentumSolver(n_jacobi_sweeps=4))
+    c = simple._config()
+    assert (c.pressure_solver, c.piso_corrections, c.momentum_solver, c.n_momentum_sweeps) == (1, 0, 0, 4)
+    with pytest.raises(NotImplementedError):
+        nb.GpuSimpleSolver(mesh, fluid, nb.GpuJacobiSolver(tolerance=1e-3))._config()
