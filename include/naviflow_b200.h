@@ -232,7 +232,8 @@ int nf_update_pressure(nf_ctx*, const nf_grid*, const double* p_star, const doub
                        double* p);
 int nf_max_abs_divergence(nf_ctx*, const nf_grid*, const double* u, const double* v, double* out_host);
 
-/* ---- device-resident SIMPLE / PISO outer loops: Algorithms/simple.py:78-269, piso.py:41-175 ---- */
+/* ---- device-resident SIMPLE / PISO / SIMPLER outer loops: Algorithms/simple.py:78-269, piso.py:41-175,
+ *      simpler.py:78-262 ---- */
 typedef struct nf_simple_config {
   int32_t nx, ny;
   int32_t n_momentum_sweeps;    /* JacobiMatrixMomentumSolver(n_jacobi_sweeps)                          */
@@ -242,7 +243,9 @@ typedef struct nf_simple_config {
   int32_t sides;                /* boundaries with a registered condition: 1 left 2 right 4 bottom 8 top */
   int32_t krylov_maxiter;
   int32_t piso_corrections;     /* 0: SIMPLE (simple.py:114-212); n >= 1: PISO with n pressure corrections per outer
-                                   iteration, momentum re-solved without relaxation in between (piso.py:73-104)     */
+                                   iteration, momentum re-solved without relaxation in between (piso.py:73-104);
+                                   -1: SIMPLER as coded in simpler.py:99-167 (p += p-bar unrelaxed, momentum again,
+                                   p += alpha_p p', velocity correction; p_rel_norm = ||p - p_old|| / sqrt(nx ny))   */
   double length, height, rho, mu;
   double alpha_p, alpha_u;      /* simple.py:23-76                                                      */
   double pressure_omega;        /* Jacobi / SOR relaxation                                              */

@@ -9,10 +9,10 @@ from .host import (BoundaryConditionManager, FluidProperties, SimulationResult, 
 from .momentum import GpuJacobiMomentumSolver, GpuMatrixFreeMomentumSolver
 from .pressure import (GpuBiCGSTABSolver, GpuCGSolver, GpuGaussSeidelSolver, GpuJacobiSolver,
                        GpuMultiGridSolver)
-from .simple import GpuPisoSolver, GpuSimpleSolver
+from .simple import GpuPisoSolver, GpuSimpleSolver, GpuSimplerSolver
 from .velocity import GpuVelocityUpdater
 
 __all__ = ["StructuredMesh", "FluidProperties", "BoundaryConditionManager", "SimulationResult", "ghia_errors",
            "ghia_table", "GpuJacobiMomentumSolver", "GpuJacobiSolver", "GpuGaussSeidelSolver",
            "GpuMultiGridSolver", "GpuCGSolver", "GpuBiCGSTABSolver", "GpuVelocityUpdater", "GpuSimpleSolver",
-           "GpuPisoSolver", "GpuMatrixFreeMomentumSolver"]
+           "GpuPisoSolver", "GpuSimplerSolver", "GpuMatrixFreeMomentumSolver"]

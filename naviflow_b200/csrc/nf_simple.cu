@@ -58,6 +58,7 @@ struct SimpleSlab {
   double* tmp = nullptr;    // Jacobi pressure ping-pong
   double* kwork = nullptr;  // Krylov work arrays
   double *ap_un = nullptr, *src_un = nullptr, *mwork = nullptr;  // Krylov momentum predictor (a7)
+  double* p_old = nullptr;  // SIMPLER: p at the start of the iteration (p_rel_norm)
   double* kstate = nullptr; // slab-decomposed Krylov: this slab's copy of the scalar state + reduction scratch (64 doubles)
   double* scal = nullptr;   // 8 device doubles: [0..1] pressure norms, [2..5] momentum sums
   nf_links links;
@@ -167,6 +168,7 @@ int nfi_simple_create(nf_team* team, nf_simple** out, const nf_simple_config* cf
       if (!*f) { ok = false; break; }
     }
     if (ok) { S.scal = alloc_elems(s, S, 8, 8); ok = S.scal != nullptr; }
+    if (ok && cfg->piso_corrections == -1) { S.p_old = alloc_elems(s, S, e, emax); ok = S.p_old != nullptr; }
     if (ok && cfg->momentum_solver == 1) {
       S.ap_un = alloc_elems(s, S, e, emax);
       S.src_un = alloc_elems(s, S, e, emax);
@@ -317,6 +319,20 @@ __global__ void k_store_hist_pressure(const double* __restrict__ pscal, double* 
   if (t == 7) rec[7] = 0.0;
 }
 
+// sum (a - b)^2 over the cells of g -> out[0]
+__global__ void k_diff_sumsq(nf_grid g, const double* __restrict__ a, const double* __restrict__ b, double* partials,
+                             unsigned int* ticket, double* out) {
+  double acc[1] = {0.0};
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < g.ny)
+    for (int i = g.gb + blockIdx.y * blockDim.y + threadIdx.y; i < g.ge; i += gridDim.y * blockDim.y) {
+      const size_t k = nf_idx(g, i, j);
+      const double d = a[k] - b[k];
+      acc[0] += d * d;
+    }
+  nf_block_reduce_store<1>(acc, partials, ticket, out);
+}
+
 static int ensure_hist(nf_simple* s, int n) {
   nf_ctx* ctx = s->ctx;
   if (n <= s->hist_cap) return NF_OK;
@@ -339,7 +355,9 @@ static void decode_record(const nf_simple* s, const double* rec, nf_simple_info*
     out->u_rel_norm = sqrt(rec[2]) / (sqrt(rec[3]) + 1e-15);  // jacobi_matrix_solver.py:246-250
     out->v_rel_norm = sqrt(rec[4]) / (sqrt(rec[5]) + 1e-15);
   }
-  switch (s->cfg.pressure_solver) {
+  if (s->cfg.piso_corrections == -1) {  // SIMPLER: ||p - p_old|| / (sqrt(nx ny) + SMALL) (simpler.py:19, :172)
+    out->p_rel_norm = sqrt(rec[0]) / (sqrt((double)s->cfg.nx * (double)s->cfg.ny) + 1.0e-30);
+  } else switch (s->cfg.pressure_solver) {
     case 0: case 1: case 2: case 5: case 6:
       out->p_rel_norm = sqrt(rec[0]); break;  // absolute ||b - A p'|| (multigrid.py:257)
     default: out->p_rel_norm = rec[1] > 0.0 ? sqrt(rec[0]) / sqrt(rec[1]) : sqrt(rec[0]); break;  // ||r_int||/||b_int||
@@ -511,7 +529,9 @@ static int momentum_predictor(nf_simple* s, double alpha, int want_fields, int s
 // pressure correction from (u*, v*, d_u, d_v): continuity RHS, pressure solve, p = p* + alpha_p p' with zero-gradient
 // edges (p* <- p), velocity correction + BCs (simple.py:136-155, piso.py:73-90).  slot >= 0: the pressure part of the
 // iteration's record goes to hist[slot]
-static int pressure_correction(nf_simple* s, int slot) {
+// alpha: relaxation of the pressure update; correct: also correct the velocities; diff_record (SIMPLER): the record's
+// pressure entry is sum (p - p_old)^2 instead of the pressure solver's residual
+static int pressure_correction(nf_simple* s, int slot, double alpha, bool correct = true, bool diff_record = false) {
   nf_ctx* ctx = s->ctx;
   nf_team* team = s->team;
   const nf_simple_config& c = s->cfg;
@@ -640,25 +660,42 @@ static int pressure_correction(nf_simple* s, int slot) {
     }
   }
   phase_mark(s);  // end of the pressure solve
-  if (slot >= 0) {
+  if (slot >= 0 && !diff_record) {
     k_store_hist_pressure<<<1, 32, 0, ctx->stream>>>(pscal, s->hist + (size_t)slot * 8, pa, pb, iters, p_from_scalars);
     NF_LAUNCH_CHECK(ctx);
   }
-  // p = p* + alpha_p p' with zero-gradient edges; p* <- p.  velocity correction + BCs.
+  // p = p* + alpha p' with zero-gradient edges; p* <- p.  velocity correction + BCs.
   for (int k = 0; k < nl; ++k) {
     SimpleSlab& S = s->s[k];
     const nf_grid g = s->geom.grid(team->local[k]);
-    NF_TRY(nf_update_pressure(ctx, &g, S.p, S.pp, c.alpha_p, S.p_alt));
+    NF_TRY(nf_update_pressure(ctx, &g, S.p, S.pp, alpha, S.p_alt));
     { double* t = S.p; S.p = S.p_alt; S.p_alt = t; }
-    NF_TRY(nfi_correct_velocity(ctx, &g, &c.bc, S.u_star, S.v_star, S.pp, S.d_u, S.d_v, S.u, S.v));
+    if (correct) NF_TRY(nfi_correct_velocity(ctx, &g, &c.bc, S.u_star, S.v_star, S.pp, S.d_u, S.d_v, S.u, S.v));
+  }
+  if (slot >= 0 && diff_record) {  // SIMPLER: p_rel_norm = ||p - p_old|| / sqrt(nx ny) (simpler.py:172)
+    std::vector<double*> sc(nl);
+    for (int k = 0; k < nl; ++k) {
+      SimpleSlab& S = s->s[k];
+      const nf_grid g = s->geom.grid(team->local[k]);
+      NfLaunch2D l = nf_launch_reduce(g.ge - g.gb, g.ny);
+      k_diff_sumsq<<<l.grid, l.block, 0, ctx->stream>>>(g, S.p, S.p_old, ctx->partials, ctx->ticket, S.scal);
+      NF_LAUNCH_CHECK(ctx);
+      sc[k] = S.scal;
+    }
+    if (dist) NF_TRY(nf_team_allreduce(team, sc.data(), 1));
+    k_store_hist_pressure<<<1, 32, 0, ctx->stream>>>(s->s[0].scal, s->hist + (size_t)slot * 8, 0.0, 0.0, iters, 1);
+    NF_LAUNCH_CHECK(ctx);
   }
   if (dist) {
-    std::vector<double*> p = field_of(s, &SimpleSlab::p), u = field_of(s, &SimpleSlab::u), v = field_of(s, &SimpleSlab::v);
+    std::vector<double*> p = field_of(s, &SimpleSlab::p);
     NF_TRY(nf_team_exchange(team, s->geom, p.data(), NF_HALO));
-    NF_TRY(nf_team_exchange(team, s->geom, u.data(), NF_HALO));
-    NF_TRY(nf_team_exchange(team, s->geom, v.data(), NF_HALO));
+    if (correct) {
+      std::vector<double*> u = field_of(s, &SimpleSlab::u), v = field_of(s, &SimpleSlab::v);
+      NF_TRY(nf_team_exchange(team, s->geom, u.data(), NF_HALO));
+      NF_TRY(nf_team_exchange(team, s->geom, v.data(), NF_HALO));
+    }
   }
-  s->bc_clean = true;
+  if (correct) s->bc_clean = true;
   return NF_OK;
 }
 
@@ -671,11 +708,30 @@ static int simple_step(nf_simple* s, int slot, int want_fields) {
   const nf_simple_config& c = s->cfg;
   // phase marks per (predictor, correction) pair: start, end of predictor, end of pressure solve, end of corrections
   phase_mark(s);
+  if (c.piso_corrections == -1) {
+    // SIMPLER as the reference codes it (simpler.py:99-167): predictor; p += p-bar (the pressure solver's answer from u*, v*,
+    // unrelaxed); momentum again from the same (u, v) with the new p; p' ; p += alpha_p p'; velocity correction with p'
+    nf_ctx* ctx = s->ctx;
+    for (int k = 0; k < nlocal(s); ++k)
+      NF_CHECK_CUDA(ctx, cudaMemcpyAsync(s->s[k].p_old, s->s[k].p, s->geom.elems(s->team->local[k]) * sizeof(double),
+                                         cudaMemcpyDeviceToDevice, ctx->stream));
+    NF_TRY(momentum_predictor(s, c.alpha_u, want_fields, slot));
+    phase_mark(s);
+    NF_TRY(pressure_correction(s, -1, 1.0, false));
+    phase_mark(s);
+    phase_mark(s);
+    NF_TRY(momentum_predictor(s, c.alpha_u, 0, -1));
+    phase_mark(s);
+    NF_TRY(pressure_correction(s, slot, c.alpha_p, true, true));
+    phase_mark(s);
+    if (s->phase_timing) s->phase_iters++;
+    return NF_OK;
+  }
   NF_TRY(momentum_predictor(s, c.alpha_u, want_fields, slot));
   phase_mark(s);
   const int nc = c.piso_corrections >= 1 ? c.piso_corrections : 1;
   for (int k = 0; k < nc; ++k) {
-    NF_TRY(pressure_correction(s, k == nc - 1 ? slot : -1));
+    NF_TRY(pressure_correction(s, k == nc - 1 ? slot : -1, c.alpha_p));
     phase_mark(s);
     if (k < nc - 1) {
       phase_mark(s);

@@ -399,3 +399,19 @@ class GpuPisoSolver(GpuSimpleSolver):
         self._piso_corrections = self.n_corrections
         super().__init__(mesh, fluid, pressure_solver, momentum_solver, velocity_updater, boundary_conditions,
                          alpha_p=alpha_p, alpha_u=alpha_u, **kw)
+
+
+class GpuSimplerSolver(GpuSimpleSolver):
+    """Twin of ``SimplerSolver(BaseAlgorithm)`` (solver/Algorithms/simpler.py:22-262) as the reference codes it: momentum
+    predictor from (u, v, p); the pressure solver's answer from (u*, v*, d) is added to p unrelaxed ("p-bar", :124-128);
+    both momentum equations are solved again from the same (u, v) with the new p (:131-154); pressure correction p',
+    ``p += alpha_p p'`` (:162-163) and the velocity correction with p' (:165-167).  The recorded momentum norms are the first
+    predictor's, ``p_rel_norm = ||p - p_old|| / sqrt(nx ny)`` (:172); ``residual_history`` gets one entry per iteration.
+    ``alpha_p`` / ``alpha_u`` are keyword-only like the reference's.  Same device loop (``piso_corrections = -1``)."""
+    _history_appends_per_iteration = 1
+    _piso_corrections = -1
+
+    def __init__(self, mesh, fluid, pressure_solver=None, momentum_solver=None, velocity_updater=None,
+                 boundary_conditions=None, *, alpha_p=0.3, alpha_u=0.7, **kw):
+        super().__init__(mesh, fluid, pressure_solver, momentum_solver, velocity_updater, boundary_conditions,
+                         alpha_p=alpha_p, alpha_u=alpha_u, **kw)

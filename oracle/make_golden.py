@@ -216,6 +216,29 @@ def piso_runs(R):
     return out
 
 
+def simpler_runs(R):
+    """SimplerSolver with the deterministic momentum adapter."""
+    out = {}
+    for n, Re, k, N, name in ((31, 100, 5, 12, "v"), (31, 100, 5, 12, "rbsor"), (63, 1000, 10, 6, "v")):
+        GS = R.GaussSeidelSolver
+        ps = (R.MultiGridSolver(smoother=GS(omega=1.5, method_type="red_black"), max_iterations=100, tolerance=1e-3,
+                                pre_smoothing=3, post_smoothing=3) if name == "v"
+              else GS(tolerance=0.0, max_iterations=30, omega=1.5, method_type="red_black"))
+        mesh = R.StructuredMesh(n, n, 1.0, 1.0)
+        fluid = R.FluidProperties(density=1.0, reynolds_number=Re, characteristic_velocity=1.0)
+        alg = R.SimplerSolver(mesh, fluid, ps, R.JacobiMatrixMomentumAdapter(n_jacobi_sweeps=k), R.StandardVelocityUpdater(),
+                              alpha_p=0.3, alpha_u=0.7)
+        alg.set_boundary_condition("top", "velocity", {"u": 1.0, "v": 0.0})
+        for b in ("bottom", "left", "right"):
+            alg.set_boundary_condition(b, "wall")
+        res = _quiet(alg.solve, max_iterations=N, tolerance=0.0, save_profile=False, track_infinity_norm=False)
+        key = f"n{n}_Re{Re}_k{k}_N{N}_{name}"
+        out[key + "_u"], out[key + "_v"], out[key + "_p"] = alg.u, alg.v, alg.p
+        out[key + "_hist"] = np.array(res.get_history("total_rel_norm"))
+        out[key + "_phist"] = np.array(res.get_history("p_rel_norm"))
+    return out
+
+
 def mf_momentum_kats(R):
     """MatrixFreeMomentumSolver (a7) on seeded fields + whole SimpleSolver runs with it (direct pressure solve)."""
     out = {}
@@ -285,6 +308,7 @@ def main():
         np.savez_compressed(os.path.join(GOLD, f"mg_n{n}.npz"), **mg_kats(R, n, seed))
     np.savez_compressed(os.path.join(GOLD, "simple_runs.npz"), **simple_runs(R))
     np.savez_compressed(os.path.join(GOLD, "piso_runs.npz"), **piso_runs(R))
+    np.savez_compressed(os.path.join(GOLD, "simpler_runs.npz"), **simpler_runs(R))
     np.savez_compressed(os.path.join(GOLD, "mf_momentum.npz"), **mf_momentum_kats(R))
     np.savez_compressed(os.path.join(GOLD, "gs_lex.npz"), **gs_lex_kats(R))
     cf = R.cavity_flow.BenchmarkData

@@ -1133,6 +1133,39 @@ def piso_solve(nx, ny, reynolds, pressure_solver, n_sweeps=20, alpha_p=0.3, alph
     return st, hist
 
 
+def simpler_solve(nx, ny, reynolds, pressure_solver, n_sweeps=20, alpha_p=0.3, alpha_u=0.7, max_iterations=100,
+                  tolerance=0.0, conditions=None, rho=1.0, U=1.0, L=1.0):
+    """SimplerSolver.solve (Algorithms/simpler.py:78-190) with the deterministic momentum oracle: predictor; the pressure
+    solver's answer from (u*, v*, d) added to p UNRELAXED (p-bar, :124-128); momentum solved again from the same (u, v)
+    with the new p (:131-154); pressure correction p', p += alpha_p p' (:162-163), velocity correction with p' (:165-167).
+    Norms: the first predictor's; p_rel_norm = ||p - p_old|| / sqrt(nx ny) (:172)."""
+    conditions = bc_conditions() if conditions is None else conditions
+    dx, dy = mesh_spacing(nx, ny, L, L)
+    mu = rho * U * L / reynolds
+    st = SimpleState(nx, ny, conditions)
+    hist = {"u_rel_norm": [], "v_rel_norm": [], "p_rel_norm": [], "total_rel_norm": []}
+    it, total = 1, 1.0
+    while it <= max_iterations and total > tolerance:
+        p_old = st.p.copy()
+        us, du, un, _ = solve_u_momentum(nx, ny, dx, dy, rho, mu, st.u, st.v, st.p, alpha_u, conditions, n_sweeps)
+        vs, dv, vn, _ = solve_v_momentum(nx, ny, dx, dy, rho, mu, st.u, st.v, st.p, alpha_u, conditions, n_sweeps)
+        p_bar, _ = pressure_solver(nx, ny, dx, dy, us, vs, du, dv)
+        st.p = update_pressure(st.p, p_bar, 1.0, conditions)
+        us, du, _, _ = solve_u_momentum(nx, ny, dx, dy, rho, mu, st.u, st.v, st.p, alpha_u, conditions, n_sweeps)
+        vs, dv, _, _ = solve_v_momentum(nx, ny, dx, dy, rho, mu, st.u, st.v, st.p, alpha_u, conditions, n_sweeps)
+        pp, _ = pressure_solver(nx, ny, dx, dy, us, vs, du, dv)
+        st.p = update_pressure(st.p, pp, alpha_p, conditions)
+        st.u, st.v = correct_velocity(nx, ny, us, vs, pp, du, dv, conditions)
+        total = max(un, vn)
+        hist["u_rel_norm"].append(un)
+        hist["v_rel_norm"].append(vn)
+        hist["p_rel_norm"].append(float(np.linalg.norm(st.p - p_old) / (np.sqrt(nx * ny) + 1.0e-30)))
+        hist["total_rel_norm"].append(total)
+        it += 1
+    hist["iterations"] = it - 1
+    return st, hist
+
+
 # ----------------------------------------------------------------------------
 # a17  Ghia centre-line errors (postprocessing/validation/cavity_flow.py:178-301)
 # ----------------------------------------------------------------------------

@@ -126,6 +126,7 @@ def ref():
     from naviflow_oo.solver.velocity_solver.standard import StandardVelocityUpdater
     from naviflow_oo.solver.Algorithms.simple import SimpleSolver
     from naviflow_oo.solver.Algorithms.piso import PisoSolver
+    from naviflow_oo.solver.Algorithms.simpler import SimplerSolver
     from naviflow_oo.postprocessing.validation import cavity_flow
     ns.__dict__.update(locals())
     del ns.__dict__["ns"]

@@ -702,3 +702,47 @@ def test_multigrid_lookahead_norm_on_slabs(monkeypatch):
     assert runs[0][3] == runs[1][3]
     for a, b in zip(runs[0][:3], runs[1][:3]):
         np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.parametrize("n,Re,k,N,name", [(31, 100, 5, 12, "v"), (31, 100, 5, 12, "rbsor"), (63, 1000, 10, 6, "v")])
+def test_simpler_loop_vs_reference_golden(golden_dir, n, Re, k, N, name):
+    """SIMPLER outer loop (Algorithms/simpler.py:78-190); u, v, p after N iterations equal the reference's
+    SimplerSolver run to 1e-10 relative L2; momentum and pressure histories."""
+    import naviflow_b200 as nb
+    g = load(golden_dir, "simpler_runs.npz")
+    key = f"n{n}_Re{Re}_k{k}_N{N}_{name}"
+    mesh, fluid = cavity(n, Re)
+    alg = nb.GpuSimplerSolver(mesh, fluid, make_ps(name), nb.GpuJacobiMomentumSolver(n_jacobi_sweeps=k),
+                              nb.GpuVelocityUpdater(), alpha_p=0.3, alpha_u=0.7)
+    alg.set_boundary_condition("top", "velocity", {"u": 1.0, "v": 0.0})
+    for b in ("bottom", "left", "right"):
+        alg.set_boundary_condition(b, "wall")
+    res = alg.solve(max_iterations=N, tolerance=0.0)
+    for fld in ("u", "v", "p"):
+        e = rel(getattr(alg, fld), g[f"{key}_{fld}"])
+        assert e < 1e-10, (fld, e)
+    hist = res.get_history("total_rel_norm")
+    assert len(hist) == N and res.iterations == N
+    np.testing.assert_allclose(hist, g[key + "_hist"], rtol=1e-8)
+    np.testing.assert_allclose(res.get_history("p_rel_norm"), g[key + "_phist"], rtol=1e-8)
+
+
+def test_simpler_slab_decomposition_is_bit_identical():
+    import naviflow_b200 as nb
+
+    def run(ranks):
+        mesh, fluid = cavity(385, 1000)
+        ps = nb.GpuMultiGridSolver(smoother=nb.GpuGaussSeidelSolver(omega=1.5), max_iterations=3, tolerance=1e-30,
+                                   pre_smoothing=3, post_smoothing=3)
+        alg = nb.GpuSimplerSolver(mesh, fluid, ps, nb.GpuJacobiMomentumSolver(n_jacobi_sweeps=5), alpha_p=0.3, alpha_u=0.7,
+                                  virtual_ranks=ranks)
+        alg.set_boundary_condition("top", "velocity", {"u": 1.0, "v": 0.0})
+        for b in ("bottom", "left", "right"):
+            alg.set_boundary_condition(b, "wall")
+        res = alg.solve(max_iterations=3, tolerance=0.0)
+        return alg, res
+
+    (ref, rres), (alg, res) = run(1), run(3)
+    for fld in ("u", "v", "p"):
+        np.testing.assert_array_equal(getattr(alg, fld), getattr(ref, fld), err_msg=fld)
+    np.testing.assert_allclose(res.get_history("p_rel_norm"), rres.get_history("p_rel_norm"), rtol=1e-12)

@@ -195,3 +195,18 @@ def test_lexicographic_gauss_seidel_golden(golden_dir, n, mt):
     dx, dy = O.mesh_spacing(n, n)
     p = O.gs_lex(g[f"n{n}_p0"], g[f"n{n}_b"], dx, dy, 1.0, g[f"n{n}_du"], g[f"n{n}_dv"], 1.5, 3, symmetric=(mt == "symmetric"))
     same(p, g[f"n{n}_{mt}"])
+
+
+@pytest.mark.parametrize("n,Re,k,N,name", [(31, 100, 5, 12, "v"), (31, 100, 5, 12, "rbsor"), (63, 1000, 10, 6, "v")])
+def test_simpler_loop_golden(golden_dir, n, Re, k, N, name):
+    """SimplerSolver.solve (Algorithms/simpler.py:78-190) against the reference's own run."""
+    g = load(golden_dir, "simpler_runs.npz")
+    key = f"n{n}_Re{Re}_k{k}_N{N}_{name}"
+    st, h = O.simpler_solve(n, n, Re, _ps(name), n_sweeps=k, max_iterations=N, tolerance=0.0)
+    for fld, arr in (("u", st.u), ("v", st.v), ("p", st.p)):
+        if name == "rbsor":
+            same(arr, g[f"{key}_{fld}"])
+        else:
+            close(arr, g[f"{key}_{fld}"], 1e-12)
+    np.testing.assert_allclose(h["total_rel_norm"], g[key + "_hist"], rtol=1e-9)
+    np.testing.assert_allclose(h["p_rel_norm"], g[key + "_phist"], rtol=1e-9)
