@@ -133,7 +133,8 @@ int nf_dot(nf_ctx*, const nf_grid*, const double* x, const double* y, double* ou
 
 /* ---- K13 + multigrid driver: pressure_solver/multigrid.py:121-688 ---------------------- */
 typedef struct nf_mg_config {
-  int32_t smoother;        /* 0 = red-black SOR (gauss_seidel.py), 1 = weighted Jacobi (jacobi.py) */
+  int32_t smoother;        /* 0 = red-black SOR (gauss_seidel.py), 1 = weighted Jacobi (jacobi.py),
+                              2 / 3 = lexicographic / symmetric SOR (gauss_seidel.py:307-367; single slab) */
   int32_t pre, post;       /* pre_smoothing, post_smoothing                                       */
   int32_t cycle_type;      /* 0 'v', 1 'w', 2 'fmg'                                               */
   int32_t cycle_buildup;   /* 0 'v', 1 'w'                                                        */

@@ -32,6 +32,8 @@
 int nfi_residual_restrict_fw(nf_ctx*, const nf_grid* gf, const double* p, const double* b, const double* d_u,
                              const double* d_v, const nf_grid* gc, double* c);
 int nfi_inv_diag(nf_ctx*, const nf_grid*, const double* d_u, const double* d_v, double* inv);
+int nfi_gs_lex(nf_ctx*, const nf_grid*, double* p, const double* b, const double* d_u, const double* d_v, double omega,
+               int n_sweeps, int symmetric);
 int nfi_prolong_banded(nf_ctx*, const nf_grid* gc, const double* c, const nf_grid* gf, double* f, double* tmp,
                        int ldt, const double* band, const int* start, int W, int add);
 
@@ -327,7 +329,8 @@ int nfi_mg_create(nf_team* team, nf_mg** out, int nx, int ny, int ld, const nf_m
   NF_REQUIRE(ctx, nx == ny, "multigrid needs a square grid (the reference's transfer operators assume it)");
   NF_REQUIRE(ctx, nx >= 3 && ld >= ny + 1 && (ld % 2) == 0, "bad grid (ld must be even and >= ny+1)");
   NF_REQUIRE(ctx, cfg->coarsest >= 3 && (cfg->coarsest % 2) == 1, "coarsest_grid_size must be odd and >= 3");  // multigrid.py:82-85
-  NF_REQUIRE(ctx, cfg->smoother == 0 || cfg->smoother == 1, "smoother must be 0 (red-black SOR) or 1 (Jacobi)");
+  NF_REQUIRE(ctx, cfg->smoother >= 0 && cfg->smoother <= 3,
+             "smoother must be 0 (red-black SOR), 1 (Jacobi), 2 (lexicographic SOR) or 3 (symmetric SOR)");
   NF_REQUIRE(ctx, cfg->restriction == 0 || cfg->restriction == 1, "bad restriction");
   NF_REQUIRE(ctx, cfg->interpolation == 0 || cfg->interpolation == 1, "bad interpolation");
   NF_REQUIRE(ctx, cfg->cycle_type >= 0 && cfg->cycle_type <= 2, "bad cycle_type");
@@ -375,6 +378,11 @@ int nfi_mg_create(nf_team* team, nf_mg** out, int nx, int ny, int ld, const nf_m
   const bool need_cubic = (cfg->interpolation == 1) || (cfg->cycle_type == 2);  // FMG hard-codes cubic (:631)
   if (need_cubic && mg->lv[0].geom.dist) {
     ctx->err = "cubic prolongation (interpolate_cubic / FMG) is a whole-grid spline: not available on a slab-decomposed grid";
+    nf_mg_destroy(mg);
+    return NF_ERR_UNSUPPORTED;
+  }
+  if (cfg->smoother >= 2 && (mg->lv[0].geom.dist || nl != 1)) {
+    ctx->err = "the sequential Gauss-Seidel smoothers run on a single slab only";
     nf_mg_destroy(mg);
     return NF_ERR_UNSUPPORTED;
   }
@@ -553,6 +561,10 @@ static int mg_smooth(nf_mg* mg, int l, int n, nf_smooth_extra* extra = nullptr /
   nf_team* team = mg->team;
   MgLevel& L = mg->lv[l];
   const int nl = nlocal(mg);
+  if (mg->cfg.smoother >= 2) {  // sequential SOR sweeps (gauss_seidel.py:307-367) as block wavefronts; single slab
+    const nf_grid g = L.geom.grid(team->local[0]);
+    return nfi_gs_lex(ctx, &g, L.s[0].x, L.s[0].b, L.s[0].d_u, L.s[0].d_v, mg->cfg.omega, n, mg->cfg.smoother == 3);
+  }
   if (mg->cfg.smoother == 0) {
     int left = n;
     if (left == 0)

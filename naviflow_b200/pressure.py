@@ -207,9 +207,10 @@ class GpuMultiGridSolver(_GpuPressureBase):
         if "jacobi" in name:
             self._smoother_id = 1
         elif "gauss" in name or "seidel" in name:
-            if getattr(smoother, "method_type", "red_black") != "red_black":
-                raise NotImplementedError("only the red-black Gauss-Seidel smoother runs on the GPU")
-            self._smoother_id = 0
+            mt = getattr(smoother, "method_type", "red_black")
+            if mt not in ("red_black", "standard", "symmetric"):
+                raise ValueError("method_type must be one of 'red_black', 'standard', or 'symmetric'")
+            self._smoother_id = {"red_black": 0, "standard": 2, "symmetric": 3}[mt]
         else:
             raise ValueError(f"unsupported smoother {type(smoother).__name__}")
         self.smoother = smoother

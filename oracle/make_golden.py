@@ -278,6 +278,24 @@ def mf_momentum_kats(R):
     return out
 
 
+def mg_lex_kats(R):
+    """MultiGridSolver with the sequential Gauss-Seidel smoothers (the configuration of the reference's README table)."""
+    out = {}
+    for n, seed in ((31, 1131), (40, 1140)):
+        inp = synth_pressure_inputs(n, seed)
+        d_u, d_v, us, vs = inp["d_u"], inp["d_v"], inp["u_star"], inp["v_star"]
+        mesh = R.StructuredMesh(n, n, 1.0, 1.0)
+        out.update({f"n{n}_d_u": d_u, f"n{n}_d_v": d_v, f"n{n}_u_star": us, f"n{n}_v_star": vs})
+        for mt, kw in (("standard", dict(pre_smoothing=2, post_smoothing=2, max_iterations=2, tolerance=1e-14)),
+                       ("symmetric", dict(pre_smoothing=1, post_smoothing=1, max_iterations=100, tolerance=1e-4))):
+            ps = R.MultiGridSolver(smoother=R.GaussSeidelSolver(omega=1.2, method_type=mt), **kw)
+            p1, i1 = _quiet(ps.solve, mesh, us, vs, d_u, d_v, None)
+            out[f"n{n}_{mt}_p"] = p1
+            out[f"n{n}_{mt}_relnorm"] = np.float64(i1["rel_norm"])
+            out[f"n{n}_{mt}_ncycles"] = np.int64(len(ps.residual_history))
+    return out
+
+
 def gs_lex_kats(R):
     """GaussSeidelSolver(method_type='standard' | 'symmetric'): 3 sweeps on seeded systems."""
     out = {}
@@ -311,6 +329,7 @@ def main():
     np.savez_compressed(os.path.join(GOLD, "simpler_runs.npz"), **simpler_runs(R))
     np.savez_compressed(os.path.join(GOLD, "mf_momentum.npz"), **mf_momentum_kats(R))
     np.savez_compressed(os.path.join(GOLD, "gs_lex.npz"), **gs_lex_kats(R))
+    np.savez_compressed(os.path.join(GOLD, "mg_lex.npz"), **mg_lex_kats(R))
     cf = R.cavity_flow.BenchmarkData
     tables = {}
     for Re in (100, 400, 1000, 3200, 5000, 7500, 10000):

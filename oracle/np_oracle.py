@@ -770,6 +770,8 @@ def _smooth(cfg, p, b, dx, dy, d_u, d_v, n):
         return rb_sor(p, b, dx, dy, cfg.rho, d_u, d_v, cfg.omega, n)
     if cfg.smoother == "jacobi":
         return jacobi_iterate(p, b, dx, dy, cfg.rho, d_u, d_v, cfg.omega, n)
+    if cfg.smoother in ("standard", "symmetric"):   # sequential Gauss-Seidel smoothers (gauss_seidel.py:307-367)
+        return gs_lex(p, b, dx, dy, cfg.rho, d_u, d_v, cfg.omega, n, symmetric=(cfg.smoother == "symmetric"))
     raise ValueError(cfg.smoother)
 
 

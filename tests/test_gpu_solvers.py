@@ -746,3 +746,20 @@ def test_simpler_slab_decomposition_is_bit_identical():
     for fld in ("u", "v", "p"):
         np.testing.assert_array_equal(getattr(alg, fld), getattr(ref, fld), err_msg=fld)
     np.testing.assert_allclose(res.get_history("p_rel_norm"), rres.get_history("p_rel_norm"), rtol=1e-12)
+
+
+@pytest.mark.parametrize("n", [31, 40])
+def test_multigrid_with_sequential_gauss_seidel_smoother_vs_reference_golden(golden_dir, n):
+    """Multigrid V-cycles smoothed by the lexicographic / symmetric Gauss-Seidel wavefront kernel (nf_mg_config.smoother
+    2 / 3) against the reference's MultiGridSolver(smoother=GaussSeidelSolver(method_type=...)): iterate 1e-11, same
+    cycle count for the tolerance-driven run."""
+    import naviflow_b200 as nb
+    g = load(golden_dir, "mg_lex.npz")
+    mesh, _ = cavity(n, 1000)
+    for mt, kw in (("standard", dict(pre_smoothing=2, post_smoothing=2, max_iterations=2, tolerance=1e-14)),
+                   ("symmetric", dict(pre_smoothing=1, post_smoothing=1, max_iterations=100, tolerance=1e-4))):
+        ps = nb.GpuMultiGridSolver(smoother=nb.GpuGaussSeidelSolver(omega=1.2, method_type=mt), **kw)
+        p, info = ps.solve(mesh, g[f"n{n}_u_star"], g[f"n{n}_v_star"], g[f"n{n}_d_u"], g[f"n{n}_d_v"], None)
+        assert rel(p, g[f"n{n}_{mt}_p"]) < 1e-11, mt
+        assert ps.last_info.cycles == int(g[f"n{n}_{mt}_ncycles"])
+        assert abs(info["rel_norm"] - g[f"n{n}_{mt}_relnorm"]) <= 1e-8 * g[f"n{n}_{mt}_relnorm"]

@@ -210,3 +210,18 @@ def test_simpler_loop_golden(golden_dir, n, Re, k, N, name):
             close(arr, g[f"{key}_{fld}"], 1e-12)
     np.testing.assert_allclose(h["total_rel_norm"], g[key + "_hist"], rtol=1e-9)
     np.testing.assert_allclose(h["p_rel_norm"], g[key + "_phist"], rtol=1e-9)
+
+
+@pytest.mark.parametrize("n", [31, 40])
+def test_multigrid_with_sequential_gauss_seidel_smoother_golden(golden_dir, n):
+    """MultiGridSolver(smoother=GaussSeidelSolver(method_type='standard' | 'symmetric')) -- the reference README's
+    "Standard Gauss-Seidel" multigrid row."""
+    g = load(golden_dir, "mg_lex.npz")
+    dx, dy = O.mesh_spacing(n, n)
+    for mt, kw in (("standard", dict(pre=2, post=2, max_iterations=2, tolerance=1e-14)),
+                   ("symmetric", dict(pre=1, post=1, max_iterations=100, tolerance=1e-4))):
+        cfg = O.MGConfig(smoother=mt, omega=1.2, **kw)
+        p, info = O.mg_solve(cfg, n, n, dx, dy, g[f"n{n}_u_star"], g[f"n{n}_v_star"], g[f"n{n}_d_u"], g[f"n{n}_d_v"])
+        close(p, g[f"n{n}_{mt}_p"], 1e-13)
+        assert info["cycles"] == int(g[f"n{n}_{mt}_ncycles"])
+        assert abs(info["rel_norm"] - g[f"n{n}_{mt}_relnorm"]) <= 1e-9 * g[f"n{n}_{mt}_relnorm"]
