@@ -133,6 +133,43 @@ def cpu_oracle_step_fn(n, args):
     return step
 
 
+# ---- cpu_baseline leg: every use of oracle/ outside tests/ and __graft_entry__.smoke() lives in the functions of this
+# section (cpu_oracle_step_fn above, run_reference below, and the two helpers the config runner tools/run_configs.py calls)
+def cpu_baseline_simple_run(n, reynolds, n_sweeps, iterations, mg_kwargs):
+    """Seconds per outer iteration of the oracle port's SIMPLE loop with the given multigrid settings (bounded run)."""
+    from oracle import np_oracle as O
+    cfg = O.MGConfig(**mg_kwargs)
+    t0 = time.perf_counter()
+    O.simple_solve(n, n, reynolds, O.make_pressure_solver("mg", cfg=cfg), n_sweeps=n_sweeps, max_iterations=iterations,
+                   tolerance=0.0)
+    return (time.perf_counter() - t0) / iterations
+
+
+def cpu_baseline_pressure_kernels(n, dx, dy, d_u, d_v, us, vs, with_mg=True):
+    """Milliseconds of one application / iteration / sweep / cycle of the oracle port's pressure kernels on the given
+    system (single thread), plus one sequential Gauss-Seidel sweep timed on a 257^2 sample and scaled per cell."""
+    from oracle import np_oracle as O
+    bh = O.continuity_rhs(n, n, dx, dy, 1.0, us, vs)
+    cpu = {}
+    t0 = time.perf_counter(); O.apply_A(bh, dx, dy, 1.0, d_u, d_v); cpu["A_p_ms"] = (time.perf_counter() - t0) * 1e3
+    t0 = time.perf_counter(); O.jacobi_iterate(np.zeros_like(bh), bh, dx, dy, 1.0, d_u, d_v, 0.8, 1)
+    cpu["jacobi_iteration_ms"] = (time.perf_counter() - t0) * 1e3
+    t0 = time.perf_counter(); O.rb_sor(np.zeros_like(bh), bh, dx, dy, 1.0, d_u, d_v, 1.5, 1)
+    cpu["rbsor_sweep_ms"] = (time.perf_counter() - t0) * 1e3
+    if with_mg:
+        ns = 257
+        rs = np.random.default_rng(5)
+        dus = (0.7 * dy / 4e-3) * (1 + 0.1 * rs.random((ns + 1, ns)))
+        dvs = (0.7 * dx / 4e-3) * (1 + 0.1 * rs.random((ns, ns + 1)))
+        t0 = time.perf_counter()
+        O.gs_lex(np.zeros((ns, ns)), 1e-2 * rs.standard_normal((ns, ns)), dx, dy, 1.0, dus, dvs, 1.8, 1)
+        cpu["gs_lexicographic_sweep_ms_scaled_from_257"] = (time.perf_counter() - t0) * 1e3 * (n * n) / (ns * ns)
+        mcfg = O.MGConfig(omega=1.5, pre=3, post=3)
+        t0 = time.perf_counter(); O.mg_cycle(mcfg, np.zeros_like(bh), bh, dx, dy, d_u, d_v)
+        cpu["mg_v33_cycle_ms"] = (time.perf_counter() - t0) * 1e3
+    return cpu
+
+
 def cpu_threads():
     try:
         from threadpoolctl import threadpool_info

@@ -32,7 +32,7 @@ def c1():
     1500 fixed outer iterations; golden norms measured with the real reference in the survey."""
     import torch
     import naviflow_b200 as nb
-    from oracle import np_oracle as O
+    import bench  # the CPU-baseline leg (the only place outside tests/ that runs oracle/)
     n, Re, k, N = 63, 100, 20, 1500
     mesh, fluid = cavity(nb, n, Re)
     ps = nb.GpuMultiGridSolver(smoother=nb.GpuGaussSeidelSolver(omega=1.5, method_type="red_black"), max_iterations=100,
@@ -50,11 +50,8 @@ def c1():
     t_gpu = time.perf_counter() - t0
     inf, l2 = nb.ghia_errors(alg.u, alg.v, mesh, Re)
     # CPU oracle port, bounded sample: 100 iterations
-    cfg = O.MGConfig(omega=1.5, pre=3, post=3, cycle_type="fmg", cycle_type_final="v", interpolation="interpolate_cubic",
-                     tolerance=1e-3)
-    t0 = time.perf_counter()
-    st, _ = O.simple_solve(n, n, Re, O.make_pressure_solver("mg", cfg=cfg), n_sweeps=k, max_iterations=100, tolerance=0.0)
-    t_cpu = (time.perf_counter() - t0) / 100
+    t_cpu = bench.cpu_baseline_simple_run(n, Re, k, 100, dict(omega=1.5, pre=3, post=3, cycle_type="fmg", cycle_type_final="v",
+                                                               interpolation="interpolate_cubic", tolerance=1e-3))
     golden = {"u": 14.5192971946493, "v": 9.52637420908884, "p": 33.7706672709561, "ghia_inf": 0.05498, "ghia_l2": 0.01865}
     rec = {"config": "c1: 63^2 Re=100 SIMPLE, FMG(1)+V(3,3) RB-SOR 1.5 cubic, 20 Jacobi momentum sweeps, 1500 iterations",
            "gpu_s_per_iter": t_gpu / N, "gpu_iter_per_s": N / t_gpu, "cpu_port_s_per_iter": t_cpu,
@@ -118,7 +115,7 @@ def c4(n):
     import naviflow_b200 as nb
     from naviflow_b200._lib import NfKrylovInfo, NfMgInfo
     from naviflow_b200.device import get_context, pad_ld, ptr
-    from oracle import np_oracle as O
+    import bench  # the CPU-baseline leg (the only place outside tests/ that runs oracle/)
     mu = 1e-3
     rng = np.random.default_rng(0)
     dx = dy = 1.0 / (n - 1)
@@ -186,19 +183,7 @@ def c4(n):
                                        "rel_residual": mi.r_norm / mi.b_norm, "MLUPS_cycles": cells * mi.cycles / ms / 1e3}
     lib.nf_mg_destroy(mg)
     # CPU oracle port: one iteration / sweep / cycle each (bounded)
-    bh = O.continuity_rhs(n, n, dx, dy, 1.0, us, vs)
-    cpu = {}
-    t0 = time.perf_counter(); O.apply_A(bh, dx, dy, 1.0, d_u, d_v); cpu["A_p_ms"] = (time.perf_counter() - t0) * 1e3
-    t0 = time.perf_counter(); O.jacobi_iterate(np.zeros_like(bh), bh, dx, dy, 1.0, d_u, d_v, 0.8, 1); cpu["jacobi_iteration_ms"] = (time.perf_counter() - t0) * 1e3
-    t0 = time.perf_counter(); O.rb_sor(np.zeros_like(bh), bh, dx, dy, 1.0, d_u, d_v, 1.5, 1); cpu["rbsor_sweep_ms"] = (time.perf_counter() - t0) * 1e3
-    if n <= 2049:
-        ns = 257   # the sequential sweep is a Python-level loop in the reference: timed on a 257^2 sample, scaled per cell
-        rs = np.random.default_rng(5)
-        dus, dvs = (0.7 * dy / 4e-3) * (1 + 0.1 * rs.random((ns + 1, ns))), (0.7 * dx / 4e-3) * (1 + 0.1 * rs.random((ns, ns + 1)))
-        t0 = time.perf_counter(); O.gs_lex(np.zeros((ns, ns)), 1e-2 * rs.standard_normal((ns, ns)), dx, dy, 1.0, dus, dvs, 1.8, 1)
-        cpu["gs_lexicographic_sweep_ms_scaled_from_257"] = (time.perf_counter() - t0) * 1e3 * (n * n) / (ns * ns)
-        mcfg = O.MGConfig(omega=1.5, pre=3, post=3)
-        t0 = time.perf_counter(); O.mg_cycle(mcfg, np.zeros_like(bh), bh, dx, dy, d_u, d_v); cpu["mg_v33_cycle_ms"] = (time.perf_counter() - t0) * 1e3
+    cpu = bench.cpu_baseline_pressure_kernels(n, dx, dy, d_u, d_v, us, vs, with_mg=(n <= 2049))
     rec["cpu_oracle_port_single_thread"] = cpu
     print(json.dumps(rec))
 
