@@ -109,6 +109,10 @@ __device__ __forceinline__ double cell_diag(const nf_grid& g, int gi, int gj, do
   return diag;
 }
 
+// region row of slot k of the threads with threadIdx.y == ty: three CONSECUTIVE rows per thread, so that the vertical
+// neighbours of a thread's middle row (and one of each outer row) are the thread's own registers
+__device__ __forceinline__ int slot_row(int ty, int k) { return KS * ty + k; }
+
 template <int NS, int S0>
 __device__ __forceinline__ void rbsor_passes(double (&sP)[2][RRW][33], int tx, int ty, double omega,
                                              double (&p0)[KS], double (&p1)[KS], const double (&b0)[KS],
@@ -119,26 +123,24 @@ __device__ __forceinline__ void rbsor_passes(double (&sP)[2][RRW][33], int tx, i
                                              const bool (&ok1)[KS]) {
   // All three row slots are updated in every pass without a branch (the commit is predicated on `ok`), so the
   // compiler can interleave the three independent fp64 dependency chains.  Rows outside the shrinking trapezoid
-  // are updated too; their values are never read by cells that matter.  Neighbour rows are clamped for the two
-  // region-edge rows, whose result is discarded anyway.
-  int rm[KS], rp[KS];
-#pragma unroll
-  for (int k = 0; k < KS; ++k) {
-    const int r = ty + NYT * k;
-    rm[k] = r > 0 ? r - 1 : 0;
-    rp[k] = r < RRW - 1 ? r + 1 : RRW - 1;
-  }
+  // are updated too; their values are never read by cells that matter.  A thread owns rows 3ty, 3ty+1, 3ty+2: of the
+  // six vertical neighbours of a pass only two (row 3ty-1 and row 3ty+3) come from shared memory, the others are the
+  // thread's own registers -- the cell with the same index one row up / down has the opposite colour and is not
+  // updated in this pass.  S0: which cell of the pair is red ((i+j) even) in slot 0's row; it alternates with the slot.
+  const int r0 = slot_row(ty, 0);
+  const int rup = r0 > 0 ? r0 - 1 : 0;                    // clamped at the region edge (that row's result is discarded)
+  const int rdn = r0 + KS < RRW ? r0 + KS : RRW - 1;
   const int txm = tx > 0 ? tx - 1 : 0;
-  const int par = ty & 1;  // r & 1 for every slot (rows differ by 16)
+  const int par = ty & 1;  // parity of slot 0's row
 #pragma unroll
   for (int t = 0; t < 2 * NS; ++t) {
     const int col = t & 1;            // 0: (i+j) even ("red"), 1: odd ("black")
-    const int s = S0 ^ col;           // which cell of the pair has colour `col`: 0 -> cell 0, 1 -> cell 1
-    const int lp = par ^ s;           // local parity of the updated cell
+    const int lp = par ^ S0 ^ col;    // shared-memory plane of the cells updated in this pass (the same for all slots)
     double pnew[KS];
 #pragma unroll
     for (int k = 0; k < KS; ++k) {
-      const int r = ty + NYT * k;
+      const int r = r0 + k;
+      const int s = S0 ^ col ^ (k & 1);  // which cell of the pair has colour `col` in this row: 0 -> cell 0, 1 -> cell 1
       const double pc = s ? p1[k] : p0[k];
       const double bc = s ? b1[k] : b0[k];
       const double ic = s ? inv1[k] : inv0[k];
@@ -146,10 +148,11 @@ __device__ __forceinline__ void rbsor_passes(double (&sP)[2][RRW][33], int tx, i
       const double aW = s ? aW1[k] : aW0[k];
       const double aN = s ? aN1[k] : aN0[k];
       const double aS = s ? aS1[k] : aS0[k];
-      // opposite-colour neighbours: rows r+-1 from shared memory; in the row, one is the thread's own partner
-      // cell (register) and the other belongs to the neighbouring pair
-      const double pE = sP[lp ^ 1][rp[k]][tx];
-      const double pW = sP[lp ^ 1][rm[k]][tx];
+      // opposite-colour neighbours.  Rows r+-1: the same cell index of the neighbouring slot (register) or, at the
+      // ends of the thread's row triple, of the neighbouring warp's row (shared memory).  In the row: one is the
+      // thread's own partner cell (register), the other belongs to the neighbouring pair (shared memory).
+      const double pE = (k < KS - 1) ? (s ? p1[k < KS - 1 ? k + 1 : k] : p0[k < KS - 1 ? k + 1 : k]) : sP[lp ^ 1][rdn][tx];
+      const double pW = (k > 0) ? (s ? p1[k > 0 ? k - 1 : k] : p0[k > 0 ? k - 1 : k]) : sP[lp ^ 1][rup][tx];
       const double pN = s ? sP[lp ^ 1][r][tx + 1] : p1[k];
       const double pS = s ? p0[k] : sP[lp ^ 1][r][txm];
       double acc = bc;       // ((((b + E) + W) + N) + S) * (1/aP): gauss_seidel.py:285-299
@@ -162,7 +165,8 @@ __device__ __forceinline__ void rbsor_passes(double (&sP)[2][RRW][33], int tx, i
     }
 #pragma unroll
     for (int k = 0; k < KS; ++k) {
-      const int r = ty + NYT * k;
+      const int r = r0 + k;
+      const int s = S0 ^ col ^ (k & 1);
       const bool ok = s ? ok1[k] : ok0[k];
       if (ok) {
         if (s) p1[k] = pnew[k]; else p0[k] = pnew[k];
@@ -196,7 +200,7 @@ k_rbsor_fused(nf_grid g, const double* __restrict__ pin, double* __restrict__ po
 
 #pragma unroll
   for (int k = 0; k < KS; ++k) {
-    const int r = ty + NYT * k;
+    const int r = slot_row(ty, k);
     const int gi = i0 + r;
     // rows gi and gi+1 (d_u) must lie inside the slab's storage; the overshoot rows of the last tile are never needed
     const bool row_in = (gi >= 0 && gi < g.nx) && nf_row_stored(g, gi) && nf_row_stored(g, gi + 1);
@@ -246,7 +250,7 @@ k_rbsor_fused(nf_grid g, const double* __restrict__ pin, double* __restrict__ po
   // write the tile (cells of the region interior that belong to this CTA)
 #pragma unroll
   for (int k = 0; k < KS; ++k) {
-    const int r = ty + NYT * k;
+    const int r = slot_row(ty, k);
     const int gi = i0 + r;
     if (r < H || r >= H + TR || gi >= g.ge) continue;
     if (c0 < H || c0 >= H + TC || gj0 >= g.ny) continue;
@@ -406,7 +410,7 @@ k_rbsor_tma(nf_grid g, const __grid_constant__ CUtensorMap map_p, const __grid_c
     if (interior) {
 #pragma unroll
       for (int k = 0; k < KS; ++k) {
-        const int r = ty + NYT * k;
+        const int r = slot_row(ty, k);
         const double2 pp = *reinterpret_cast<const double2*>(stP + r * RCW + c0);
         const double2 bb = *reinterpret_cast<const double2*>(stB + r * RCW + c0);
         const double2 ua = *reinterpret_cast<const double2*>(stDU + r * RCW + c0);
@@ -428,7 +432,7 @@ k_rbsor_tma(nf_grid g, const __grid_constant__ CUtensorMap map_p, const __grid_c
     } else {
 #pragma unroll
       for (int k = 0; k < KS; ++k) {
-        const int r = ty + NYT * k;
+        const int r = slot_row(ty, k);
         const int gi = i0 + r;
         const bool row_in = (gi >= 0 && gi < g.nx);
         const bool in0 = row_in && gj0 >= 0 && gj0 < g.ny;
@@ -472,11 +476,11 @@ k_rbsor_tma(nf_grid g, const __grid_constant__ CUtensorMap map_p, const __grid_c
       if (ex.in_norm) {
         // residual of the INPUT iterate on this tile's cells, from the registers and the initial sP (same expression
         // order as the stand-alone residual: nf_Ap_cell)
-        const int par = ty & 1;
         double s_r = 0.0, s_b = 0.0;
 #pragma unroll
         for (int k = 0; k < KS; ++k) {
-          const int r = ty + NYT * k;
+          const int r = slot_row(ty, k);
+          const int par = r & 1;
           const int gi = i0 + r;
           const bool rin = r >= HR && r < HR + TR && gi < g.ge;
           const bool cin0 = c0 >= HC && c0 < HC + TC && gj0 < g.ny;
@@ -511,6 +515,7 @@ k_rbsor_tma(nf_grid g, const __grid_constant__ CUtensorMap map_p, const __grid_c
         }
         sN[2 * (ty * 32 + tx)] += s_r;       // own slot, fixed tile order: deterministic
         sN[2 * (ty * 32 + tx) + 1] += s_b;
+        __syncthreads();  // the first colour pass overwrites sP rows that neighbouring warps have just read
       }
     }
 
@@ -521,7 +526,7 @@ k_rbsor_tma(nf_grid g, const __grid_constant__ CUtensorMap map_p, const __grid_c
 
 #pragma unroll
     for (int k = 0; k < KS; ++k) {
-      const int r = ty + NYT * k;
+      const int r = slot_row(ty, k);
       const int gi = i0 + r;
       if (r < HR || r >= HR + TR || gi >= g.ge) continue;
       if (c0 < HC || c0 >= HC + TC || gj0 >= g.ny) continue;
@@ -533,11 +538,11 @@ k_rbsor_tma(nf_grid g, const __grid_constant__ CUtensorMap map_p, const __grid_c
     if (EXTRA != 0) {
       // residual b - A p of this thread's cells from registers + the final sP (all neighbours of the cells used
       // below are exact: they lie at least 2*NS cells inside the region)
-      const int par = ty & 1;
       constexpr int RHI = (EXTRA == 2) ? 1 : 0;  // mode 2 also needs the ring row / column above the tile
 #pragma unroll
       for (int k = 0; k < KS; ++k) {
-        const int r = ty + NYT * k;
+        const int r = slot_row(ty, k);
+        const int par = r & 1;
         const int gi = i0 + r;
         const bool rin = r >= HR && r < HR + TR + RHI && gi < (EXTRA == 2 ? g.nx : g.ge);
         double res0 = 0.0, res1 = 0.0;
@@ -576,6 +581,7 @@ k_rbsor_tma(nf_grid g, const __grid_constant__ CUtensorMap map_p, const __grid_c
           sR[r][c0 + 1] = (rin && cin1) ? res1 : 0.0;
         }
       }
+      if (EXTRA == 1) __syncthreads();  // the next tile's set-up overwrites sP rows the neighbouring warps have just read
       if (EXTRA == 2) {
         __syncthreads();
         const int it = g.gb + ti * TR, jt = tj * TC;  // tile origin (even)
