@@ -7,10 +7,11 @@
 //   * One CTA (32 x 16 threads) owns an output tile of TR x TC cells and loads the region grown by the halo
 //     H = 2*NS on every side (48 rows x 64 columns).  After colour pass t the cells at distance > t from the
 //     region edge are exact, so after 2*NS passes the tile is exact.
-//   * Thread (tx, ty) owns the column pair (2tx, 2tx+1) of region rows ty, ty+16, ty+32: one red and one
-//     black cell per row.  Their constants (b, 1/aP, aE, aW, aN, aS) live in REGISTERS for all passes; only p
-//     goes through shared memory, stored split by colour so that every access is lane-contiguous
-//     (conflict-free): sP[parity][row][pair].
+//   * Thread (tx, ty) owns the column pair (2tx, 2tx+1) of the three consecutive region rows 3ty, 3ty+1, 3ty+2:
+//     one red and one black cell per row.  Their constants (b, 1/aP, aE, aW, aN, aS) live in REGISTERS for all
+//     passes; p is mirrored in shared memory for the neighbouring threads, stored split by colour so that every
+//     access is lane-contiguous (conflict-free): sP[parity][row][pair].  Vertical neighbours inside the row triple
+//     are read from the thread's own registers (see rbsor_passes).
 //   * HBM traffic per launch: read p, b, d_u, d_v (32 B/cell x region/tile overhead, largely absorbed by L2
 //     between neighbouring tiles) + write p (8 B/cell) -- versus 2*NS passes x ~40 B/cell unfused.
 //   * p is double buffered in global memory (p_in -> p_out): neighbouring tiles read each other's halo.
