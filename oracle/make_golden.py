@@ -296,6 +296,21 @@ def mg_lex_kats(R):
     return out
 
 
+def bicgstab_mg_kats(R):
+    """MatrixFreeBiCGSTABSolver with the multigrid preconditioner."""
+    out = {}
+    for n, kind, cycles in ((31, "v", 1), (64, "v", 2), (65, "w", 1), (63, "fmg", 1)):
+        s = synth_pressure_inputs(n, 6000 + n)
+        mesh = R.StructuredMesh(n, n, 1.0, 1.0)
+        bs = R.MatrixFreeBiCGSTABSolver(tolerance=1e-7, max_iterations=200, use_preconditioner=True,
+                                        preconditioner="multigrid", mg_cycles=cycles, mg_cycle_type=kind)
+        p, info = _quiet(bs.solve, mesh, s["u_star"], s["v_star"], s["d_u"], s["d_v"], None)
+        k = f"n{n}_{kind}{cycles}"
+        out.update({k + "_d_u": s["d_u"], k + "_d_v": s["d_v"], k + "_u_star": s["u_star"], k + "_v_star": s["v_star"],
+                    k + "_p": p, k + "_relnorm": np.float64(info["rel_norm"])})
+    return out
+
+
 def gs_lex_kats(R):
     """GaussSeidelSolver(method_type='standard' | 'symmetric'): 3 sweeps on seeded systems."""
     out = {}
@@ -330,6 +345,7 @@ def main():
     np.savez_compressed(os.path.join(GOLD, "mf_momentum.npz"), **mf_momentum_kats(R))
     np.savez_compressed(os.path.join(GOLD, "gs_lex.npz"), **gs_lex_kats(R))
     np.savez_compressed(os.path.join(GOLD, "mg_lex.npz"), **mg_lex_kats(R))
+    np.savez_compressed(os.path.join(GOLD, "bicgstab_mg.npz"), **bicgstab_mg_kats(R))
     cf = R.cavity_flow.BenchmarkData
     tables = {}
     for Re in (100, 400, 1000, 3200, 5000, 7500, 10000):

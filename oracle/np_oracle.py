@@ -977,6 +977,38 @@ def krylov_pressure_solve(kind, nx, ny, dx, dy, u_star, v_star, d_u, d_v, tol=1e
                "iterations": iters, "info": info}
 
 
+def mg_preconditioner(dx, dy, d_u, d_v, kind="v", cycles=1, omega=0.8, pre=2, post=2, coarsest=7, tolerance=1e-7,
+                      cycle_type_buildup="v", max_cycles_buildup=1, restriction="restrict_full_weighting",
+                      interpolation="interpolate_linear"):
+    """M of MatrixFreeBiCGSTABSolver(use_preconditioner=True, preconditioner='multigrid') (matrix_free_BiCGSTAB.py:102-161):
+    `cycles` multigrid cycles of the given kind on A y = z from y = 0 (red-black smoother with omega =
+    smoother_relaxation)."""
+    cfg = MGConfig(smoother="red_black", omega=omega, pre=pre, post=post, coarsest=coarsest, tolerance=tolerance,
+                   cycle_type_buildup=cycle_type_buildup, max_cycles_buildup=max_cycles_buildup, restriction=restriction,
+                   interpolation=interpolation)
+
+    def M(z):
+        x = np.zeros_like(z)
+        for _ in range(cycles):
+            x = mg_fmg(cfg, z, dx, dy, d_u, d_v) if kind == "fmg" else mg_cycle(cfg, x, z, dx, dy, d_u, d_v, kind)
+        return x
+    return M
+
+
+def bicgstab_mg_pressure_solve(nx, ny, dx, dy, u_star, v_star, d_u, d_v, tol=1e-7, maxiter=1000, kind="v", cycles=1, **mg):
+    """MatrixFreeBiCGSTABSolver.solve with the multigrid preconditioner (:163-287).  Returns (p', info dict with rel_norm =
+    ||r_interior|| / ||b_interior|| as krylov_pressure_solve computes it (:255-279), iterations)."""
+    b = continuity_rhs(nx, ny, dx, dy, 1.0, u_star, v_star)
+    mv = lambda z: apply_A(z, dx, dy, 1.0, d_u, d_v)
+    x, info, iters = bicgstab(mv, b, atol=tol, maxiter=maxiter, M=mg_preconditioner(dx, dy, d_u, d_v, kind, cycles, **mg))
+    bi = b.copy()
+    Ax = mv(x)
+    for a in (bi, Ax):
+        a[0, :] = 0; a[:, 0] = 0; a[-1, :] = 0; a[:, -1] = 0
+    r = bi - Ax
+    return x, {"rel_norm": np.linalg.norm(r) / np.linalg.norm(bi), "field": r, "iterations": iters, "info": info}
+
+
 # ----------------------------------------------------------------------------
 # a14  velocity correction (velocity_solver/standard.py:10-69)
 # ----------------------------------------------------------------------------

@@ -763,3 +763,19 @@ def test_multigrid_with_sequential_gauss_seidel_smoother_vs_reference_golden(gol
         assert rel(p, g[f"n{n}_{mt}_p"]) < 1e-11, mt
         assert ps.last_info.cycles == int(g[f"n{n}_{mt}_ncycles"])
         assert abs(info["rel_norm"] - g[f"n{n}_{mt}_relnorm"]) <= 1e-8 * g[f"n{n}_{mt}_relnorm"]
+
+
+@pytest.mark.parametrize("n,kind,cycles", [(31, "v", 1), (64, "v", 2), (65, "w", 1), (63, "fmg", 1)])
+def test_mg_preconditioned_bicgstab_vs_reference_golden(golden_dir, n, kind, cycles):
+    """The multigrid-preconditioned BiCGSTAB against the REFERENCE's MatrixFreeBiCGSTABSolver(use_preconditioner=True,
+    preconditioner='multigrid') output: a converged Krylov answer, so the bar is the stopping tolerance (rtol 1e-5)."""
+    import naviflow_b200 as nb
+    g = load(golden_dir, "bicgstab_mg.npz")
+    k = f"n{n}_{kind}{cycles}"
+    mesh, _ = cavity(n, 1000)
+    sol = nb.GpuBiCGSTABSolver(tolerance=1e-7, max_iterations=200, use_preconditioner=True, preconditioner="multigrid",
+                               mg_cycles=cycles, mg_cycle_type=kind)
+    p, info = sol.solve(mesh, g[k + "_u_star"], g[k + "_v_star"], g[k + "_d_u"], g[k + "_d_v"], None)
+    assert sol.last_info.info == 0
+    assert rel(p, g[k + "_p"]) < 1e-4
+    assert info["rel_norm"] < 2e-5

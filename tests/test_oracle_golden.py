@@ -225,3 +225,16 @@ def test_multigrid_with_sequential_gauss_seidel_smoother_golden(golden_dir, n):
         close(p, g[f"n{n}_{mt}_p"], 1e-13)
         assert info["cycles"] == int(g[f"n{n}_{mt}_ncycles"])
         assert abs(info["rel_norm"] - g[f"n{n}_{mt}_relnorm"]) <= 1e-9 * g[f"n{n}_{mt}_relnorm"]
+
+
+@pytest.mark.parametrize("n,kind,cycles", [(31, "v", 1), (64, "v", 2), (65, "w", 1), (63, "fmg", 1)])
+def test_mg_preconditioned_bicgstab_golden(golden_dir, n, kind, cycles):
+    """8f rank 2: MatrixFreeBiCGSTABSolver(use_preconditioner=True, preconditioner='multigrid')
+    (matrix_free_BiCGSTAB.py:102-287): scipy's bicgstab order with M = multigrid cycles from zero."""
+    g = load(golden_dir, "bicgstab_mg.npz")
+    k = f"n{n}_{kind}{cycles}"
+    dx, dy = O.mesh_spacing(n, n)
+    p, info = O.bicgstab_mg_pressure_solve(n, n, dx, dy, g[k + "_u_star"], g[k + "_v_star"], g[k + "_d_u"], g[k + "_d_v"],
+                                           tol=1e-7, maxiter=200, kind=kind, cycles=cycles)
+    close(p, g[k + "_p"], 1e-12)
+    assert abs(info["rel_norm"] - g[k + "_relnorm"]) <= 1e-9 * g[k + "_relnorm"]
