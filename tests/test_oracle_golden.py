@@ -238,3 +238,33 @@ def test_mg_preconditioned_bicgstab_golden(golden_dir, n, kind, cycles):
                                            tol=1e-7, maxiter=200, kind=kind, cycles=cycles)
     close(p, g[k + "_p"], 1e-12)
     assert abs(info["rel_norm"] - g[k + "_relnorm"]) <= 1e-9 * g[k + "_relnorm"]
+
+
+@pytest.mark.parametrize("n", [17, 40])
+def test_krylov_restatements_equal_the_installed_scipy(n):
+    """The Krylov arithmetic of the path lives in scipy (the reference pins no version).  The oracle's cg / bicgstab
+    restate scipy.sparse.linalg's operation order: same iterates as the installed scipy on the pressure operator, with and
+    without a (diagonal) preconditioner, started from zero and from a given x0, stopped by tolerance and by maxiter."""
+    from scipy.sparse.linalg import LinearOperator, bicgstab, cg
+    from oracle.make_golden import synth_pressure_inputs
+    s = synth_pressure_inputs(n, 8800 + n)
+    dx, dy = O.mesh_spacing(n, n)
+    b2 = O.continuity_rhs(n, n, dx, dy, 1.0, s["u_star"], s["v_star"])
+    mv2 = lambda z: O.apply_A(z, dx, dy, 1.0, s["d_u"], s["d_v"])
+    N = n * n
+    A = LinearOperator((N, N), matvec=lambda v: mv2(v.reshape((n, n), order="F")).flatten("F"), dtype=np.float64)
+    diag = O.pressure_coefficients(n, n, dx, dy, 1.0, s["d_u"], s["d_v"])[4].copy()
+    diag[0, 0] = 1.0
+    Mop = LinearOperator((N, N), matvec=lambda v: v / diag.flatten("F"), dtype=np.float64)
+    M2 = lambda z: z / diag
+    x0 = 1e-3 * np.random.default_rng(n).standard_normal((n, n))
+    for kw_s, kw_o in ((dict(), dict()), (dict(M=Mop), dict(M=M2)), (dict(x0=x0.flatten("F")), dict(x0=x0)),
+                       (dict(maxiter=7), dict(maxiter=7))):
+        xs, info_s = bicgstab(A, b2.flatten("F"), atol=1e-9, **kw_s)
+        xo, info_o, _ = O.bicgstab(mv2, b2, atol=1e-9, **kw_o)
+        assert info_s == info_o
+        np.testing.assert_allclose(xo.flatten("F"), xs, rtol=0, atol=1e-13 * np.abs(xs).max())
+        xs, info_s = cg(A, b2.flatten("F"), atol=1e-9, maxiter=kw_s.get("maxiter", 60), **{k: v for k, v in kw_s.items() if k != "maxiter"})
+        xo, info_o, _ = O.cg(mv2, b2, atol=1e-9, maxiter=kw_o.get("maxiter", 60), **{k: v for k, v in kw_o.items() if k != "maxiter"})
+        assert info_s == info_o
+        np.testing.assert_allclose(xo.flatten("F"), xs, rtol=0, atol=1e-12 * np.abs(xs).max())
