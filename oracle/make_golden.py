@@ -296,6 +296,29 @@ def mg_lex_kats(R):
     return out
 
 
+RECT_CASES = ((40, 24, 100, 5, 10, "rbsor"), (24, 40, 400, 3, 8, "jacobi"), (33, 70, 100, 4, 6, "rbsor"))
+
+
+def rect_runs(R):
+    """SimpleSolver on rectangular cell grids (nx != ny, unit square: dx != dy) with the stationary pressure solvers."""
+    out = {}
+    for nx, ny, Re, k, N, name in RECT_CASES:
+        ps = (R.GaussSeidelSolver(tolerance=0.0, max_iterations=30, omega=1.5, method_type="red_black") if name == "rbsor"
+              else R.JacobiSolver(tolerance=0.0, max_iterations=50, omega=0.8))
+        mesh = R.StructuredMesh(nx, ny, 1.0, 1.0)
+        fluid = R.FluidProperties(density=1.0, reynolds_number=Re, characteristic_velocity=1.0)
+        alg = R.SimpleSolver(mesh, fluid, ps, R.JacobiMatrixMomentumAdapter(n_jacobi_sweeps=k), R.StandardVelocityUpdater(),
+                             alpha_p=0.3, alpha_u=0.7)
+        alg.set_boundary_condition("top", "velocity", {"u": 1.0, "v": 0.0})
+        for b in ("bottom", "left", "right"):
+            alg.set_boundary_condition(b, "wall")
+        res = _quiet(alg.solve, max_iterations=N, tolerance=0.0, save_profile=False, track_infinity_norm=False)
+        key = f"nx{nx}_ny{ny}_Re{Re}_k{k}_N{N}_{name}"
+        out[key + "_u"], out[key + "_v"], out[key + "_p"] = alg.u, alg.v, alg.p
+        out[key + "_hist"] = np.array(res.get_history("total_rel_norm"))[::2]
+    return out
+
+
 def bicgstab_mg_kats(R):
     """MatrixFreeBiCGSTABSolver with the multigrid preconditioner."""
     out = {}
@@ -346,6 +369,7 @@ def main():
     np.savez_compressed(os.path.join(GOLD, "gs_lex.npz"), **gs_lex_kats(R))
     np.savez_compressed(os.path.join(GOLD, "mg_lex.npz"), **mg_lex_kats(R))
     np.savez_compressed(os.path.join(GOLD, "bicgstab_mg.npz"), **bicgstab_mg_kats(R))
+    np.savez_compressed(os.path.join(GOLD, "rect_runs.npz"), **rect_runs(R))
     cf = R.cavity_flow.BenchmarkData
     tables = {}
     for Re in (100, 400, 1000, 3200, 5000, 7500, 10000):

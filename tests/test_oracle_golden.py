@@ -268,3 +268,14 @@ def test_krylov_restatements_equal_the_installed_scipy(n):
         xo, info_o, _ = O.cg(mv2, b2, atol=1e-9, maxiter=kw_o.get("maxiter", 60), **{k: v for k, v in kw_o.items() if k != "maxiter"})
         assert info_s == info_o
         np.testing.assert_allclose(xo.flatten("F"), xs, rtol=0, atol=1e-12 * np.abs(xs).max())
+
+
+@pytest.mark.parametrize("nx,ny,Re,k,N,name", [(40, 24, 100, 5, 10, "rbsor"), (24, 40, 400, 3, 8, "jacobi"), (33, 70, 100, 4, 6, "rbsor")])
+def test_simple_loop_on_rectangular_grids_golden(golden_dir, nx, ny, Re, k, N, name):
+    """nx != ny (dx != dy): every kernel of the loop except the multigrid transfers (which assume square grids); bit-exact."""
+    g = load(golden_dir, "rect_runs.npz")
+    key = f"nx{nx}_ny{ny}_Re{Re}_k{k}_N{N}_{name}"
+    st, h = O.simple_solve(nx, ny, Re, _ps(name), n_sweeps=k, max_iterations=N, tolerance=0.0)
+    for fld, arr in (("u", st.u), ("v", st.v), ("p", st.p)):
+        same(arr, g[f"{key}_{fld}"])
+    np.testing.assert_allclose(h["total_rel_norm"], g[key + "_hist"], rtol=1e-12)
