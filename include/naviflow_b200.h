@@ -279,6 +279,8 @@ int nf_simple_create(nf_ctx*, nf_simple** out, const nf_simple_config* cfg);
 int nf_nccl_unique_id(nf_ctx*, void* id_out_128_bytes);
 int nf_team_create_nccl(nf_ctx*, int world, int rank, const void* id_128_bytes, nf_team** out);
 int nf_team_create_virtual(nf_ctx*, int virtual_ranks, nf_team** out);
+/* COLLECTIVE for teams created by nf_team_create_nccl: every rank must call it (peer mappings are closed and all ranks
+ * meet before any rank frees the memory its peers had mapped) */
 int nf_team_free(nf_team*);
 /* 1 when the team's halo exchanges / norm reductions run as the ranks' own kernels over NVLink peer memory (cudaIpc
  * arena, default for nf_team_create_nccl with world <= 8; NF_P2P=0 or a failed cudaIpc set-up selects NCCL) */

@@ -222,21 +222,31 @@ static int p2p_new_chunk(nf_team* team, size_t bytes) {
   nf_p2p* P = team->p2p;
   P2PChunk ch;
   ch.size = bytes;
-  NF_CHECK_CUDA(ctx, cudaMalloc((void**)&ch.base, bytes));
-  ch.peer[P->rank] = ch.base;
+  if (!P->active) {  // NCCL transport: a private allocation, nothing collective
+    NF_CHECK_CUDA(ctx, cudaMalloc((void**)&ch.base, bytes));
+    ch.peer[P->rank] = ch.base;
+    P->chunks.push_back(ch);
+    return NF_OK;
+  }
+  // Collective part.  A failure that only this rank sees (allocation, export) must not make it leave while the others
+  // wait in the next collective: local errors are folded into `ok`, which all ranks agree on before anybody returns.
   int ok = 1;
-  if (P->active) {
+  if (cudaMalloc((void**)&ch.base, bytes) != cudaSuccess) { cudaGetLastError(); ch.base = nullptr; ok = 0; }
+  ch.peer[P->rank] = ch.base;
+  bool alloc_failed = !ch.base;
+  {
     cudaIpcMemHandle_t h;
-    if (cudaIpcGetMemHandle(&h, ch.base) != cudaSuccess) { cudaGetLastError(); ok = 0; memset(&h, 0, sizeof(h)); }
+    memset(&h, 0, sizeof(h));
+    if (ok && cudaIpcGetMemHandle(&h, ch.base) != cudaSuccess) { cudaGetLastError(); ok = 0; memset(&h, 0, sizeof(h)); }
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
     std::vector<cudaIpcMemHandle_t> all(P->world);
-    if (!P->dbuf) NF_CHECK_CUDA(ctx, cudaMalloc(&P->dbuf, 64 * NF_P2P_MAX_WORLD));
+    if (!P->dbuf) NF_CHECK_CUDA(ctx, cudaMalloc(&P->dbuf, 64 * NF_P2P_MAX_WORLD));  // 512 bytes, first chunk only
     NF_CHECK_CUDA(ctx, cudaMemcpyAsync((char*)P->dbuf + 64 * P->rank, &h, 64, cudaMemcpyHostToDevice, ctx->stream));
     NF_TRY(nf_nccl_allgather_bytes(team, P->dbuf, 64));
     NF_CHECK_CUDA(ctx, cudaMemcpyAsync(all.data(), P->dbuf, 64 * (size_t)P->world, cudaMemcpyDeviceToHost, ctx->stream));
     NF_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     int all_ok = 0;
-    NF_TRY(nf_nccl_all_ok(team, ok, &all_ok));  // nobody opens handles unless everybody could export one
+    NF_TRY(nf_nccl_all_ok(team, ok, &all_ok));  // nobody opens handles unless everybody could allocate and export
     if (all_ok) {
       for (int q = 0; q < P->world && ok; ++q) {
         if (q == P->rank) continue;
@@ -251,6 +261,10 @@ static int p2p_new_chunk(nf_team* team, size_t bytes) {
         if (q != P->rank && ch.peer[q]) { cudaIpcCloseMemHandle(ch.peer[q]); ch.peer[q] = nullptr; }
       P->active = false;  // every rank takes this branch together: NCCL exchanges from here on
     }
+  }
+  if (alloc_failed) {  // agreed on above: the other ranks fell back to NCCL, this one reports its allocation failure
+    ctx->err = "peer-memory arena: cudaMalloc failed";
+    return NF_ERR_ALLOC;
   }
   P->chunks.push_back(ch);
   return NF_OK;
@@ -329,15 +343,22 @@ int nf_p2p_reserve_stage(nf_team* team, size_t halo_elems) {
   return NF_OK;
 }
 
+// COLLECTIVE over the team (nf_team_free is therefore collective as well): cudaFree on an exported allocation is
+// undefined while a peer still maps it, so every rank first drains its stream and closes its imported mappings, then
+// all ranks meet (the NCCL communicator is still alive here), and only then the local chunks are released.
 void nf_p2p_destroy(nf_team* team) {
   nf_p2p* P = team->p2p;
   if (!P) return;
   cudaStreamSynchronize(team->ctx->stream);
-  for (P2PChunk& ch : P->chunks) {
+  for (P2PChunk& ch : P->chunks)
     for (int q = 0; q < P->world; ++q)
-      if (q != P->rank && ch.peer[q]) cudaIpcCloseMemHandle(ch.peer[q]);
-    if (ch.base) cudaFree(ch.base);
+      if (q != P->rank && ch.peer[q]) { cudaIpcCloseMemHandle(ch.peer[q]); ch.peer[q] = nullptr; }
+  if (team->nccl && P->world > 1) {
+    int all_ok = 0;
+    nf_nccl_all_ok(team, 1, &all_ok);  // barrier: nobody maps (or spins on) this rank's memory any more
   }
+  for (P2PChunk& ch : P->chunks)
+    if (ch.base) cudaFree(ch.base);
   if (P->dbuf) cudaFree(P->dbuf);
   delete P;
   team->p2p = nullptr;

@@ -723,7 +723,12 @@ int nfi_rbsor_fused_x(nf_ctx* ctx, const nf_grid* g, double** p, double** palt, 
         ex.out = extra->in_norm_out;
       }
     }
-    if (use_tma) {  // persistent TMA pipeline: pays off once every SM gets several tiles
+    // streaming (wavefront) kernel: plain launches (no fused residual work yet) on levels of >= NF_RBSOR_STREAM rows
+    const int stream_min_rows = getenv("NF_RBSOR_STREAM") ? atoi(getenv("NF_RBSOR_STREAM")) : 1 << 30;
+    if (mode == 0 && inv && g->nx >= stream_min_rows && (g->ge - g->gb) >= 16) {
+      NF_TRY(nfi_rbsor_stream(ctx, g, *p, *palt, b, d_u, d_v, inv, omega, ns, &used));
+    }
+    if (use_tma && !used) {  // persistent TMA pipeline: pays off once every SM gets several tiles
       if (ns == 3) st = launch_tma_any<3>(ctx, g, *p, *palt, b, d_u, d_v, inv, omega, mode, ex, &used);
       else if (ns == 2) st = launch_tma_any<2>(ctx, g, *p, *palt, b, d_u, d_v, inv, omega, mode, ex, &used);
       else st = launch_tma_any<1>(ctx, g, *p, *palt, b, d_u, d_v, inv, omega, mode, ex, &used);
