@@ -36,10 +36,14 @@
 namespace {
 
 constexpr int SW = 64;    // strip width in cells
-constexpr int NSTG = 4;   // rows in flight per warp
-constexpr int SG_P = 0, SG_DU = 512, SG_B = 1024, SG_INV = 1536, SG_DV = 2048;  // stage layout (bytes)
-constexpr int SG_BYTES = 2048 + 640;                                            // d_v row: 66 doubles, padded
-constexpr unsigned SG_TX = 4 * 512 + 66 * 8;
+// Ring of TMA boxes per warp: NSTG stages of RB rows each (RB * NSTG == 8: the stage of a step is a compile-time function of
+// its phase).  One box per array and stage: the TMA unit retires roughly one op per 46 cycles per SM whatever its size, so
+// single-row boxes (5 ops per step and warp) made the unit the bottleneck.
+constexpr int RB = 4, NSTG = 2;
+static_assert(RB * NSTG == 8, "ring length must equal the phase count");
+constexpr int SG_P = 0, SG_DU = RB * 512, SG_B = 2 * RB * 512, SG_INV = 3 * RB * 512, SG_DV = 4 * RB * 512;  // stage layout
+constexpr int SG_BYTES = ((4 * RB * 512 + RB * 66 * 8 + 127) / 128) * 128;
+constexpr unsigned SG_TX = RB * (4 * 512 + 66 * 8);
 
 __device__ __forceinline__ unsigned s_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -74,95 +78,197 @@ struct Job {
   int j0;          // global column of lane 0's first cell (even, may be negative)
 };
 
-// One step of the wavefront.  PH = (s - r0) & 7 (compile time), NP = number of colour passes.
-template <int PH, int NP, bool BND>
-__device__ __forceinline__ void stream_step(Win& W, const nf_grid& g, const Job& jb, int s, int lane, double omega,
-                                            const unsigned char* stage, double* __restrict__ pout) {
-  constexpr int SN = PH;              // slot of row s
-  constexpr int SC = (PH + 7) & 7;    // slot of row s-1 (its coefficients arrive now)
-  const int gjA = jb.j0 + 2 * lane;
-  // ---- the new row: p[s], d_u[s] and the coefficients of row s-1 ----
-  {
-    const double2 pp = *reinterpret_cast<const double2*>(stage + SG_P + 16 * lane);
-    const double2 uu = *reinterpret_cast<const double2*>(stage + SG_DU + 16 * lane);
-    const double2 bb = *reinterpret_cast<const double2*>(stage + SG_B + 16 * lane);
-    const double2 iv = *reinterpret_cast<const double2*>(stage + SG_INV + 16 * lane);
-    const double2 vv = *reinterpret_cast<const double2*>(stage + SG_DV + 16 * lane);
-    const double v2 = *reinterpret_cast<const double*>(stage + SG_DV + 16 * lane + 16);
-    W.pA[SN] = pp.x; W.pB[SN] = pp.y;
-    if (BND) {
-      if (s == 0 && gjA == 0) W.pA[SN] = 0.0;  // pinned cell (gauss_seidel.py:145, :305)
-      // cells outside the domain hold p = 0 (zero-filled by the TMA unit) and are never updated
+// Domain edges.  The reference zeroes the links of a boundary cell across its edge direction but keeps the reverse links
+// (matrix_free.py:63-84), which breaks the face sharing at exactly four places: row 0's aE, row nx-1's aW, column 0's aN,
+// column ny-1's aS.  Everything else is settled when a row is loaded: the faces that only boundary or virtual cells use
+// (d_u rows 0 and nx, d_v columns 0 and ny -- NaN in real runs: the momentum solver divides by a zero aP there) are replaced
+// by 0, and cells outside the domain then keep p = 0 on their own (all their operands are zero-filled by the TMA unit), so no
+// update needs a validity predicate except the pinned cell (0,0).  ROWB / COLB: the variant handles row / column edges;
+// only the 8-step groups that touch rows 0 / nx-1 run ROWB, only the first and last strip run COLB.
+struct ColFlags {
+  bool A_bnd, B_bnd;   // the lane's cell is in column 0 or ny-1
+  bool z0, z1, z2;     // face j = jA, jA+1, jA+2 is column 0 or ny: zero at load
+  bool pin;            // the lane owns column 0 (cell A)
+};
+
+// Loads row s of p and d_u (-> slot SN) and the coefficient rows of row s-1 (-> slot SN-1) from row RW of a stage.
+// p of the second cell goes to *pB_out (the double step commits it late, see below).
+template <int SN, int RW, bool ROWB, bool COLB>
+__device__ __forceinline__ void stream_load(Win& W, const nf_grid& g, int s, int lane, const unsigned char* stage,
+                                            const ColFlags& cf, double* pB_out) {
+  constexpr int SC = (SN + 7) & 7;
+  const double2 pp = *reinterpret_cast<const double2*>(stage + SG_P + RW * 512 + 16 * lane);
+  const double2 uu = *reinterpret_cast<const double2*>(stage + SG_DU + RW * 512 + 16 * lane);
+  const double2 bb = *reinterpret_cast<const double2*>(stage + SG_B + RW * 512 + 16 * lane);
+  const double2 iv = *reinterpret_cast<const double2*>(stage + SG_INV + RW * 512 + 16 * lane);
+  const double2 vv = *reinterpret_cast<const double2*>(stage + SG_DV + RW * 528 + 16 * lane);
+  const double v2 = *reinterpret_cast<const double*>(stage + SG_DV + RW * 528 + 16 * lane + 16);
+  W.pA[SN] = pp.x;
+  *pB_out = pp.y;
+  if (ROWB && COLB) {
+    if (s == 0 && cf.pin) W.pA[SN] = 0.0;  // pinned cell (gauss_seidel.py:145, :305)
+  }
+  double fa = g.rho * uu.x * g.dy, fb = g.rho * uu.y * g.dy;
+  if (ROWB) {
+    if (s == 0 || s == g.nx) { fa = 0.0; fb = 0.0; }
+  }
+  W.fA[SN] = fa;
+  W.fB[SN] = fb;
+  double g0 = g.rho * vv.x * g.dx, g1 = g.rho * vv.y * g.dx, g2 = g.rho * v2 * g.dx;
+  if (COLB) {
+    if (cf.z0) g0 = 0.0;
+    if (cf.z1) g1 = 0.0;
+    if (cf.z2) g2 = 0.0;
+    if (cf.A_bnd) g0 = 0.0;  // aS of a boundary column (g0 is used by this lane's cell A only)
+    if (cf.B_bnd) g2 = 0.0;  // aN of a boundary column (g2 is used by this lane's cell B only)
+  }
+  W.g0[SC] = g0;
+  W.g1[SC] = g1;
+  W.g2[SC] = g2;
+  W.bA[SC] = bb.x; W.bB[SC] = bb.y;
+  W.iA[SC] = iv.x; W.iB[SC] = iv.y;
+}
+
+// One SOR update of the cell UPD_A ? A : B of the row in slot a (global row r); nbv = the neighbour across the pair boundary.
+template <bool UPD_A, int a, bool ROWB, bool COLB>
+__device__ __forceinline__ void stream_update(Win& W, const nf_grid& g, int r, double omega, double nbv, const ColFlags& cf) {
+  constexpr int se = (a + 1) & 7, sw = (a + 7) & 7;  // rows r+1, r-1
+  double aE, aW, aN, aS, pc, pE, pW, pN, pS, bc, ic;
+  if (UPD_A) {
+    aE = W.fA[se]; aW = W.fA[a]; aN = W.g1[a]; aS = W.g0[a];
+    pc = W.pA[a]; pE = W.pA[se]; pW = W.pA[sw]; pN = W.pB[a]; pS = nbv;
+    bc = W.bA[a]; ic = W.iA[a];
+  } else {
+    aE = W.fB[se]; aW = W.fB[a]; aN = W.g2[a]; aS = W.g1[a];
+    pc = W.pB[a]; pE = W.pB[se]; pW = W.pB[sw]; pN = nbv; pS = W.pA[a];
+    bc = W.bB[a]; ic = W.iB[a];
+  }
+  if (ROWB) {  // row 0 keeps no E link, row nx-1 no W link (their other vertical face is zero since the load)
+    if (r == 0) aE = 0.0;
+    if (r == g.nx - 1) aW = 0.0;
+  }
+  if (COLB) {  // the face between the lane's two cells serves both: zero it for the one in a boundary column
+    if (UPD_A) { if (cf.A_bnd) aN = 0.0; } else { if (cf.B_bnd) aS = 0.0; }
+  }
+  double acc = bc;  // ((((b + E) + W) + N) + S) * (1/aP): gauss_seidel.py:285-299
+  acc += aE * pE;
+  acc += aW * pW;
+  acc += aN * pN;
+  acc += aS * pS;
+  const double pn = acc * ic;
+  const double pu = pc + omega * (pn - pc);
+  if (UPD_A) {
+    if (ROWB && COLB) { if (!(r == 0 && cf.pin)) W.pA[a] = pu; }
+    else W.pA[a] = pu;
+  } else {
+    W.pB[a] = pu;
+  }
+}
+
+// Iteration T of the interleaved chains of a double step (see stream_step2): X_T, then the shuffle Y_(T+1) will need, then
+// Y_(T-1).
+template <int PH, int T, int NP, bool ROWB, bool COLB>
+__device__ __forceinline__ void stream_pair(Win& W, const nf_grid& g, int s, double omega, const ColFlags& cf,
+                                            const double (&nbX)[NP], double (&nbY)[NP]) {
+  if constexpr (T < NP) {
+    constexpr int ax = (PH + 15 - T) & 7;  // row s-1-T
+    stream_update<false, ax, ROWB, COLB>(W, g, s - 1 - T, omega, nbX[T], cf);
+    if constexpr (T + 1 < NP) nbY[T + 1] = __shfl_up_sync(0xffffffffu, W.pB[ax], 1);
+  }
+  if constexpr (T >= 1) {
+    constexpr int ay = (PH + 17 - T) & 7;  // row s-(T-1)
+    stream_update<true, ay, ROWB, COLB>(W, g, s - (T - 1), omega, nbY[T - 1], cf);
+  }
+  if constexpr (T < NP) stream_pair<PH, T + 1, NP, ROWB, COLB>(W, g, s, omega, cf, nbX, nbY);
+}
+
+// Two steps of the wavefront at once: step s (even phase PH: the B cells, chain X) and step s+1 (the A cells, chain Y).
+// X_t = pass t on row s-1-t, Y_t = pass t on row s-t.  Y_t needs X_(t-1) (its in-row neighbours) and Y_(t-1); X_t needs only
+// X_(t-1) and values of the previous double step -- so the statements are emitted as X_0, {X_1, Y_0}, {X_2, Y_1}, ... , Y_last
+// and each brace holds two independent dependency chains for the scheduler to interleave (a single step is one serial chain
+// of 2NS x 9 fp64 operations; with two warps per scheduler that left the issue slots 60 % empty).
+template <int PH, int NP, bool ROWB, bool COLB>
+__device__ __forceinline__ void stream_step2(Win& W, const nf_grid& g, const Job& jb, int s, int lane, double omega,
+                                             const unsigned char* stage, const ColFlags& cf, double* __restrict__ pout) {
+  static_assert((PH & 1) == 0, "double steps start on even phases");
+  constexpr int S0 = PH, S1 = (PH + 1) & 7;  // slots of rows s, s+1
+  double pB_s1;
+  stream_load<S0, PH % RB, ROWB, COLB>(W, g, s, lane, stage, cf, &W.pB[S0]);  // slot of row s-8: free
+  // pB of row s+1 shares its slot with row s-7, which chain X still reads (W neighbour of its last update): committed below
+  stream_load<S1, (PH + 1) % RB, ROWB, COLB>(W, g, s + 1, lane, stage, cf, &pB_s1);
+  double nbX[NP], nbY[NP];
+#pragma unroll
+  for (int t = 0; t < NP; ++t) nbX[t] = __shfl_down_sync(0xffffffffu, W.pA[(PH + 15 - t) & 7], 1);  // rows s-1-t
+  nbY[0] = __shfl_up_sync(0xffffffffu, W.pB[S0], 1);                                                // row s
+  stream_pair<PH, 0, NP, ROWB, COLB>(W, g, s, omega, cf, nbX, nbY);
+  W.pB[S1] = pB_s1;
+  // ---- rows s-NP and s+1-NP are final ----
+  const int c = 2 * lane;
+  const int gjA = jb.j0 + c;
+  if (c >= NP && c < SW - NP && gjA < g.ny) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int rf = s + q - NP;
+      const int sf = (PH + q + 16 - NP) & 7;
+      if (rf >= jb.ia && rf < jb.ib) {
+        const size_t kk = nf_idx(g, rf, gjA);
+        if (!COLB || gjA + 1 < g.ny) *reinterpret_cast<double2*>(pout + kk) = make_double2(W.pA[sf], W.pB[sf]);
+        else pout[kk] = W.pA[sf];
+      }
     }
-    W.fA[SN] = g.rho * uu.x * g.dy;
-    W.fB[SN] = g.rho * uu.y * g.dy;
-    W.g0[SC] = g.rho * vv.x * g.dx;
-    W.g1[SC] = g.rho * vv.y * g.dx;
-    W.g2[SC] = g.rho * v2 * g.dx;
-    W.bA[SC] = bb.x; W.bB[SC] = bb.y;
-    W.iA[SC] = iv.x; W.iB[SC] = iv.y;
   }
-  // ---- the colour passes of this step: all on the same cell of the pair ----
-  constexpr bool UPD_A = (PH & 1) != 0;  // s odd (r0 even) -> even columns
-  double nb[NP];  // the neighbour across the pair boundary, state after the previous step
+}
+
+// The march of one job.  COLB (first / last strip) is a property of the job; the row variant is chosen per group of 8 steps.
+template <int NP, bool COLB, class Issue>
+__device__ __forceinline__ void stream_job(const nf_grid& g, const Job& jb, int lane, double omega, const unsigned char* ring,
+                                           unsigned bar0, Issue& issue, double* __restrict__ pout) {
+  Win W;
 #pragma unroll
-  for (int t = 0; t < NP; ++t) {
-    const int a = (PH + 7 - t) & 7;
-    nb[t] = UPD_A ? __shfl_up_sync(0xffffffffu, W.pB[a], 1) : __shfl_down_sync(0xffffffffu, W.pA[a], 1);
+  for (int q = 0; q < 8; ++q) {
+    W.pA[q] = W.pB[q] = 0.0;
+    W.fA[q] = W.fB[q] = 0.0;
+    W.g0[q] = W.g1[q] = W.g2[q] = 0.0;
+    W.bA[q] = W.bB[q] = 0.0;
+    W.iA[q] = W.iB[q] = 0.0;
   }
-  bool colA_in = true, colB_in = true, colA_bnd = false, colB_bnd = false;
-  if (BND) {
-    colA_in = gjA >= 0 && gjA < g.ny;
-    colB_in = gjA + 1 >= 0 && gjA + 1 < g.ny;
-    colA_bnd = gjA == 0 || gjA == g.ny - 1;
-    colB_bnd = gjA + 1 == 0 || gjA + 1 == g.ny - 1;
+  ColFlags cf = {false, false, false, false, false, false};
+  if (COLB) {
+    const int gjA = jb.j0 + 2 * lane;
+    cf.A_bnd = gjA == 0 || gjA == g.ny - 1;
+    cf.B_bnd = gjA + 1 == 0 || gjA + 1 == g.ny - 1;
+    cf.z0 = gjA == 0 || gjA == g.ny;
+    cf.z1 = gjA + 1 == 0 || gjA + 1 == g.ny;
+    cf.z2 = gjA + 2 == 0 || gjA + 2 == g.ny;
+    cf.pin = gjA == 0;
   }
-#pragma unroll
-  for (int t = 0; t < NP; ++t) {
-    const int a = (PH + 7 - t) & 7;    // row r = s-1-t
-    const int se = (PH + 8 - t) & 7;   // row r+1
-    const int sw = (PH + 6 - t) & 7;   // row r-1
-    const int r = s - 1 - t;
-    double aE, aW, aN, aS, pc, pE, pW, pN, pS, bc, ic;
-    if (UPD_A) {
-      aE = W.fA[se]; aW = W.fA[a]; aN = W.g1[a]; aS = W.g0[a];
-      pc = W.pA[a]; pE = W.pA[se]; pW = W.pA[sw]; pN = W.pB[a]; pS = nb[t];
-      bc = W.bA[a]; ic = W.iA[a];
+
+#define NF_STREAM_STEP2(PH, ROWB)                                                                   \
+  {                                                                                                 \
+    const int s = s8 + PH;                                                                          \
+    if (s > jb.s_last) break;                                                                       \
+    if ((PH % RB) == 0) {                                                                           \
+      const unsigned bar = bar0 + 8 * (PH / RB);                                                    \
+      while (!mbar_try(bar, ring_phase)) {}                                                         \
+    }                                                                                               \
+    const unsigned char* stage = ring + (PH / RB) * SG_BYTES;                                       \
+    stream_step2<PH, NP, ROWB, COLB>(W, g, jb, s, lane, omega, stage, cf, pout);                   \
+    if (((PH + 1) % RB) == RB - 1) { /* the stage is consumed: refill it for the steps 8 ahead */    \
+      __syncwarp();                                                                                 \
+      if (lane == 0 && s + 8 - (RB - 2) <= jb.s_last) issue(s + 8 - (RB - 2));                      \
+    }                                                                                               \
+  }
+
+  unsigned ring_phase = 0;
+  for (int s8 = jb.r0;; s8 += 8, ring_phase ^= 1) {
+    // rows these 8 steps load or update: s8-NP .. s8+7
+    if (s8 - NP <= 0 || s8 + 7 >= g.nx - 1) {
+      NF_STREAM_STEP2(0, true) NF_STREAM_STEP2(2, true) NF_STREAM_STEP2(4, true) NF_STREAM_STEP2(6, true)
     } else {
-      aE = W.fB[se]; aW = W.fB[a]; aN = W.g2[a]; aS = W.g1[a];
-      pc = W.pB[a]; pE = W.pB[se]; pW = W.pB[sw]; pN = nb[t]; pS = W.pA[a];
-      bc = W.bB[a]; ic = W.iB[a];
-    }
-    bool ok = true;
-    if (BND) {
-      const bool row_in = r >= 0 && r < g.nx;
-      const bool row_bnd = r == 0 || r == g.nx - 1;
-      const bool col_bnd = UPD_A ? colA_bnd : colB_bnd;
-      if (row_bnd) { aE = 0.0; aW = 0.0; }   // matrix_free.py:63-84: boundary cells keep no link across the edge direction
-      if (col_bnd) { aN = 0.0; aS = 0.0; }
-      ok = row_in && (UPD_A ? colA_in : colB_in) && !(UPD_A && r == 0 && gjA == 0);
-      if (!ok) { aE = aW = aN = aS = 0.0; }  // keeps NaN coefficients of the array borders out of the arithmetic
-    }
-    double acc = bc;  // ((((b + E) + W) + N) + S) * (1/aP): gauss_seidel.py:285-299
-    acc += aE * pE;
-    acc += aW * pW;
-    acc += aN * pN;
-    acc += aS * pS;
-    const double pn = acc * ic;
-    const double pu = pc + omega * (pn - pc);
-    if (UPD_A) { if (ok) W.pA[a] = pu; } else { if (ok) W.pB[a] = pu; }
-  }
-  // ---- row s-NP is final ----
-  {
-    constexpr int SF = (PH + 8 - NP) & 7;
-    const int rf = s - NP;
-    const int c = 2 * lane;
-    if (rf >= jb.ia && rf < jb.ib && c >= NP && c < SW - NP && gjA < g.ny) {
-      const size_t kk = nf_idx(g, rf, gjA);
-      if (!BND || gjA + 1 < g.ny) *reinterpret_cast<double2*>(pout + kk) = make_double2(W.pA[SF], W.pB[SF]);
-      else pout[kk] = W.pA[SF];
+      NF_STREAM_STEP2(0, false) NF_STREAM_STEP2(2, false) NF_STREAM_STEP2(4, false) NF_STREAM_STEP2(6, false)
     }
   }
+#undef NF_STREAM_STEP2
 }
 
 struct StreamMaps {
@@ -172,30 +278,53 @@ struct StreamMaps {
 // registers per thread the launch bounds leave (64 K registers per SM, allocated per warp in units of 8 per thread)
 constexpr int stream_maxreg(int wpc) { return ((65536 / (32 * wpc)) / 8) * 8 > 255 ? 255 : ((65536 / (32 * wpc)) / 8) * 8; }
 
+// How the (strip, row chunk) jobs are numbered.  The strips that touch column 0 / ny-1 run the COLB variant, which costs a
+// few selects more per update; they get shorter chunks so that all warps of the single wave finish together (the kernel's
+// duration is the duration of its slowest warp).
+struct JobPlan {
+  int n_inner, first_right;   // inner strips are 1 .. first_right-1; edge strips: 0 and first_right .. nstrips-1
+  int n_edge;
+  int len_inner, len_edge;    // rows per chunk (even)
+  int jobs_inner, njobs;      // jobs_inner = n_inner * chunks of an inner strip
+};
+
 template <int NS, int WPC>
 __global__ void __launch_bounds__(32 * WPC, 1) __maxnreg__(stream_maxreg(WPC))
-k_rbsor_stream(nf_grid g, const __grid_constant__ StreamMaps maps, double* __restrict__ pout, double omega, int nstrips,
-               int njobs, int chunk_len) {
+k_rbsor_stream(nf_grid g, const __grid_constant__ StreamMaps maps, double* __restrict__ pout, double omega, JobPlan plan) {
   constexpr int NP = 2 * NS;
   constexpr int SCOLS = SW - 2 * NP;  // columns a strip finalises
   extern __shared__ __align__(128) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int job = blockIdx.x * WPC + warp;
-  if (job >= njobs) return;
+  if (job >= plan.njobs) return;
   unsigned char* ring = smem + (size_t)warp * (NSTG * SG_BYTES);
   const unsigned bar0 = s_u32(smem + (size_t)WPC * NSTG * SG_BYTES + warp * NSTG * 8);
   const unsigned ring_u = s_u32(ring);
 
   Job jb;
+  bool colb;
   {
-    const int chunk = job / nstrips, strip = job - chunk * nstrips;
-    jb.ia = g.gb + chunk * chunk_len;
-    jb.ib = jb.ia + chunk_len < g.ge ? jb.ia + chunk_len : g.ge;
+    int chunk, strip, len;
+    if (job < plan.jobs_inner) {
+      chunk = job / plan.n_inner;
+      strip = 1 + (job - chunk * plan.n_inner);
+      len = plan.len_inner;
+      colb = false;
+    } else {
+      const int q = job - plan.jobs_inner;
+      chunk = q / plan.n_edge;
+      const int e = q - chunk * plan.n_edge;
+      strip = e == 0 ? 0 : plan.first_right + e - 1;
+      len = plan.len_edge;
+      colb = true;
+    }
+    jb.ia = g.gb + chunk * len;
+    jb.ib = jb.ia + len < g.ge ? jb.ia + len : g.ge;
     jb.r0 = (jb.ia - NP) & ~1;
     jb.s_last = jb.ib - 1 + NP;
+    if (((jb.s_last - jb.r0) & 1) == 0) jb.s_last += 1;  // steps come in pairs
     jb.j0 = strip * SCOLS - NP;
   }
-  const bool bnd = jb.r0 <= 0 || jb.s_last >= g.nx - 1 || jb.j0 <= 0 || jb.j0 + SW >= g.ny - 1;
 
   if (lane == 0) {
 #pragma unroll
@@ -204,8 +333,8 @@ k_rbsor_stream(nf_grid g, const __grid_constant__ StreamMaps maps, double* __res
   }
   __syncwarp();
 
-  auto issue = [&](int s) {  // stage of step s: p[s], d_u[s]; d_v, b, 1/aP of row s-1
-    const int q = (s - jb.r0) & (NSTG - 1);
+  auto issue = [&](int s) {  // stage of steps s .. s+RB-1: rows s.. of p, d_u; rows s-1.. of d_v, b, 1/aP
+    const int q = ((s - jb.r0) / RB) & (NSTG - 1);
     const unsigned bar = bar0 + 8 * q, dst = ring_u + q * SG_BYTES;
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(SG_TX) : "memory");
     tma_row(dst + SG_P, &maps.p, jb.j0, s - g.row0, bar);
@@ -217,37 +346,11 @@ k_rbsor_stream(nf_grid g, const __grid_constant__ StreamMaps maps, double* __res
   if (lane == 0) {
 #pragma unroll
     for (int q = 0; q < NSTG; ++q)
-      if (jb.r0 + q <= jb.s_last) issue(jb.r0 + q);
+      if (jb.r0 + q * RB <= jb.s_last) issue(jb.r0 + q * RB);
   }
 
-  Win W;
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    W.pA[q] = W.pB[q] = 0.0;
-    W.fA[q] = W.fB[q] = 0.0;
-    W.g0[q] = W.g1[q] = W.g2[q] = 0.0;
-    W.bA[q] = W.bB[q] = 0.0;
-    W.iA[q] = W.iB[q] = 1.0;
-  }
-
-#define NF_STREAM_STEP(PH)                                                                          \
-  {                                                                                                 \
-    const int s = s8 + PH;                                                                          \
-    if (s > jb.s_last) break;                                                                       \
-    const unsigned bar = bar0 + 8 * (PH & (NSTG - 1));                                              \
-    while (!mbar_try(bar, (PH >> 2) & 1)) {}                                                        \
-    const unsigned char* stage = ring + (PH & (NSTG - 1)) * SG_BYTES;                               \
-    if (bnd) stream_step<PH, NP, true>(W, g, jb, s, lane, omega, stage, pout);                     \
-    else stream_step<PH, NP, false>(W, g, jb, s, lane, omega, stage, pout);                        \
-    __syncwarp();                                                                                   \
-    if (lane == 0 && s + NSTG <= jb.s_last) issue(s + NSTG);                                        \
-  }
-
-  for (int s8 = jb.r0;; s8 += 8) {
-    NF_STREAM_STEP(0) NF_STREAM_STEP(1) NF_STREAM_STEP(2) NF_STREAM_STEP(3)
-    NF_STREAM_STEP(4) NF_STREAM_STEP(5) NF_STREAM_STEP(6) NF_STREAM_STEP(7)
-  }
-#undef NF_STREAM_STEP
+  if (colb) stream_job<NP, true>(g, jb, lane, omega, ring, bar0, issue, pout);
+  else stream_job<NP, false>(g, jb, lane, omega, ring, bar0, issue, pout);
 }
 
 // ---- tensor maps, cached per (array, shape): re-encoding costs a driver call per array and launch ----
@@ -298,7 +401,7 @@ bool row_map(CUtensorMap* out, const double* base, int rows, int cols, int ld, i
   if (!enc) return false;
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(double)};
-  cuuint32_t box[2] = {(cuuint32_t)box_cols, 1u};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)RB};
   cuuint32_t estr[2] = {1, 1};
   CUtensorMap m;
   if (enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), gdim, gstride, box, estr,
@@ -311,23 +414,45 @@ bool row_map(CUtensorMap* out, const double* base, int rows, int cols, int ld, i
   return true;
 }
 
+// strips / chunks of a level: one job per warp slot of a single wave (148 SMs x WPC warps)
+template <int NS>
+JobPlan make_plan(const nf_grid* g, int slots) {
+  constexpr int NP = 2 * NS, SCOLS = SW - 2 * NP;
+  const int rows = g->ge - g->gb;
+  const int nstrips = (g->ny + SCOLS - 1) / SCOLS;
+  // strip k is an edge strip when its 64 columns (plus the d_v column to their right) reach column 0 or ny-1
+  int first_right = (g->ny - 1 - SW + NP + SCOLS - 1) / SCOLS;  // smallest k with k*SCOLS - NP + SW >= ny-1
+  if (first_right < 1) first_right = 1;
+  if (first_right > nstrips) first_right = nstrips;
+  JobPlan P;
+  P.first_right = first_right;
+  P.n_inner = first_right - 1;
+  P.n_edge = nstrips - P.n_inner;
+  const double edge_cost = 1.12;  // relative cost of a COLB step
+  // the smallest chunk length (of the inner strips) whose jobs fit into one wave
+  int best_li = -1, best_le = -1;
+  for (int li = 8; li <= ((rows + 1) & ~1) + 2; li += 2) {
+    int le = (int)((li + 2 * NP) / edge_cost) - 2 * NP;
+    le &= ~1;
+    if (le < 8) le = 8;
+    const int ci = (rows + li - 1) / li, ce = (rows + le - 1) / le;
+    if ((long long)P.n_inner * ci + (long long)P.n_edge * ce <= slots) { best_li = li; best_le = le; break; }
+  }
+  if (best_li < 0) { best_li = (rows + 1) & ~1; best_le = best_li; }  // more strips than slots: several waves
+  P.len_inner = best_li;
+  P.len_edge = best_le;
+  P.jobs_inner = P.n_inner * ((rows + best_li - 1) / best_li);
+  P.njobs = P.jobs_inner + P.n_edge * ((rows + best_le - 1) / best_le);
+  return P;
+}
+
 template <int NS, int WPC>
 int launch_stream(nf_ctx* ctx, const nf_grid* g, const double* pin, double* pout, const double* b, const double* d_u,
                   const double* d_v, const double* inv, double omega, bool* used) {
-  constexpr int NP = 2 * NS, SCOLS = SW - 2 * NP;
   constexpr int SMEM = WPC * NSTG * SG_BYTES + WPC * NSTG * 8;
   *used = false;
-  const int rows = g->ge - g->gb;
-  const int nstrips = (g->ny + SCOLS - 1) / SCOLS;
-  const int slots = NF_SM_COUNT * WPC;
-  int nchunks = slots / nstrips;
-  if (nchunks < 1) nchunks = 1;
-  int chunk_len = (rows + nchunks - 1) / nchunks;
-  if (chunk_len < 8) chunk_len = 8;
-  chunk_len = (chunk_len + 1) & ~1;  // even chunk starts keep the row parity of the phases
-  if ((g->gb & 1) != 0) return NF_OK;  // odd origin: the caller falls back
-  nchunks = (rows + chunk_len - 1) / chunk_len;
-  const int njobs = nstrips * nchunks;
+  if ((g->gb & 1) != 0) return NF_OK;  // odd origin (the phases assume even chunk starts): the caller falls back
+  const JobPlan plan = make_plan<NS>(g, NF_SM_COUNT * WPC);
   const int row_end = g->row1 > 0 ? g->row1 : g->nx + 1;
   const int stored_p = (row_end < g->nx ? row_end : g->nx) - g->row0;
   const int stored_u = row_end - g->row0;
@@ -341,8 +466,8 @@ int launch_stream(nf_ctx* ctx, const nf_grid* g, const double* pin, double* pout
     NF_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_rbsor_stream<NS, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_set = true;
   }
-  const int grid = (njobs + WPC - 1) / WPC;
-  k_rbsor_stream<NS, WPC><<<grid, 32 * WPC, SMEM, ctx->stream>>>(*g, m, pout, omega, nstrips, njobs, chunk_len);
+  const int grid = (plan.njobs + WPC - 1) / WPC;
+  k_rbsor_stream<NS, WPC><<<grid, 32 * WPC, SMEM, ctx->stream>>>(*g, m, pout, omega, plan);
   NF_LAUNCH_CHECK(ctx);
   *used = true;
   return NF_OK;
@@ -354,15 +479,8 @@ int nfi_rbsor_stream(nf_ctx* ctx, const nf_grid* g, const double* pin, double* p
                      const double* d_v, const double* inv, double omega, int ns, bool* used) {
   *used = false;
   if (!inv) return NF_OK;
-  const int wpc = getenv("NF_STREAM_WPC") ? atoi(getenv("NF_STREAM_WPC")) : 12;
-  if (ns == 3) {
-    if (wpc == 8) return launch_stream<3, 8>(ctx, g, pin, pout, b, d_u, d_v, inv, omega, used);
-    if (wpc == 9) return launch_stream<3, 9>(ctx, g, pin, pout, b, d_u, d_v, inv, omega, used);
-    if (wpc == 11) return launch_stream<3, 11>(ctx, g, pin, pout, b, d_u, d_v, inv, omega, used);
-    if (wpc == 10) return launch_stream<3, 10>(ctx, g, pin, pout, b, d_u, d_v, inv, omega, used);
-    return launch_stream<3, 12>(ctx, g, pin, pout, b, d_u, d_v, inv, omega, used);
-  }
-  if (ns == 2) return launch_stream<2, 12>(ctx, g, pin, pout, b, d_u, d_v, inv, omega, used);
-  if (ns == 1) return launch_stream<1, 12>(ctx, g, pin, pout, b, d_u, d_v, inv, omega, used);
+  if (ns == 3) return launch_stream<3, 8>(ctx, g, pin, pout, b, d_u, d_v, inv, omega, used);
+  if (ns == 2) return launch_stream<2, 8>(ctx, g, pin, pout, b, d_u, d_v, inv, omega, used);
+  if (ns == 1) return launch_stream<1, 8>(ctx, g, pin, pout, b, d_u, d_v, inv, omega, used);
   return NF_OK;
 }

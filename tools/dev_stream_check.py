@@ -43,7 +43,7 @@ def run(n, sweeps_list=(1, 2, 3, 4, 7), time_it=False):
     if time_it:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         p, tmp = x.clone(), torch.zeros_like(x)
-        for mode, wpc in (("tma", 0), ("stream", 8), ("stream", 12)):
+        for mode, wpc in (("tma", 0), ("stream", 8)):
             os.environ["NF_RBSOR_STREAM"] = "0" if mode == "stream" else "1000000000"
             os.environ["NF_STREAM_WPC"] = str(wpc)
             fn = lambda: ctx.check(lib.nf_rbsor_sweeps_fused(H, G, ptr(p), ptr(tmp), ptr(b), ptr(du), ptr(dv), ptr(inv), 1.5, 12))
