@@ -221,6 +221,9 @@ int nfi_rbsor_fused_x(nf_ctx*, const nf_grid*, double** p, double** palt, const 
                       const double* d_v, const double* inv, double omega, int n_sweeps, nf_smooth_extra* extra);
 
 // streaming (wavefront) variant of the temporally blocked smoother (nf_rbsor_stream.cu): ns in 1..3 sweeps from pin into
-// pout; needs the precomputed 1/aP and an even first row.  *used = false: nothing was launched, take another path.
+// pout; needs the precomputed 1/aP and an even first row.  mode / extra as nf_smooth_extra (fused work on 3-sweep launches
+// only, no in_norm).  *used = false: nothing was launched, take another path.
 int nfi_rbsor_stream(nf_ctx*, const nf_grid*, const double* pin, double* pout, const double* b, const double* d_u,
-                     const double* d_v, const double* inv, double omega, int ns, bool* used);
+                     const double* d_v, const double* inv, double omega, int ns, int mode, const nf_smooth_extra* extra,
+                     bool* used);
+bool nfi_rbsor_stream_enabled(const nf_grid* g);

@@ -18,6 +18,7 @@
 
 #include <vector>
 
+#include "nf_mg_tail.cuh"
 #include "nf_pressure.cuh"
 #include "nf_slab.cuh"
 
@@ -64,6 +65,7 @@ struct nf_mg {
   std::vector<double*> scal;                  // per local rank: 8 device doubles for the norms
   double* scal_host = nullptr;                // pinned
   int coarse_N = 0;
+  int tail_level = -1;  // first level (>= 1) of the single-kernel coarse end of a V-cycle (nf_mg_tail.cu), -1: none
   bool setup_done = false;
   // CUDA graph of one whole cycle at level 0 (single slab): captured after a warm-up cycle, replayed afterwards.
   // Valid while the level-0 arrays stay the same and every level swaps x/x2 an even number of times per cycle.
@@ -440,6 +442,25 @@ int nfi_mg_create(nf_team* team, nf_mg** out, int nx, int ny, int ld, const nf_m
     nf_mg_destroy(mg);
     return NF_ERR_ALLOC;
   }
+  // Coarse end of the V-cycle in one kernel: the levels of <= NF_TAIL_MAX_N cells per side, when they are whole
+  // (replicated) grids smoothed by red-black SOR with full weighting / bilinear transfer and the chain ends in the dense solve
+  {
+    const char* env = getenv("NF_MG_TAIL");
+    const bool want = !(env && env[0] == '0') && cfg->smoother == 0 && cfg->restriction == 0 && cfg->interpolation == 0 &&
+                      C.geom.nx <= cfg->coarsest;
+    if (want) {
+      int first = -1;
+      for (size_t l = 1; l < mg->lv.size(); ++l)
+        if (mg->lv[l].geom.nx <= NF_TAIL_MAX_N && !mg->lv[l].geom.dist) { first = (int)l; break; }
+      if (first >= 0 && (int)mg->lv.size() - first >= 2 && (int)mg->lv.size() - first <= NF_TAIL_MAX_LEVELS) {
+        size_t bytes = 0;
+        for (size_t l = first; l < mg->lv.size(); ++l)
+          bytes += sizeof(double) * ((size_t)(mg->lv[l].geom.nx + 2) * (mg->lv[l].geom.ny + 2) +
+                                     7 * (size_t)mg->lv[l].geom.nx * mg->lv[l].geom.ny);
+        if (bytes + 2048 <= NF_TAIL_MAX_SMEM) mg->tail_level = first;
+      }
+    }
+  }
   *out = mg;
   return NF_OK;
 }
@@ -652,6 +673,31 @@ static int mg_publish_rhs(nf_mg* mg, int l) {
   return nf_team_share_rows(mg->team, C.geom.ld, C.geom.nx, C.rgb, C.rge, b.data(), 0);
 }
 
+// levels tail_level .. coarsest of a V-cycle in one kernel per local slab (the level's right-hand side is in place, its
+// solution is written; same bits as the launch-by-launch recursion)
+static int mg_tail(nf_mg* mg) {
+  nf_ctx* ctx = mg->ctx;
+  for (int k = 0; k < nlocal(mg); ++k) {
+    nf_tail_args a;
+    a.nlev = (int)mg->lv.size() - mg->tail_level;
+    for (int q = 0; q < a.nlev; ++q) {
+      MgLevel& L = mg->lv[mg->tail_level + q];
+      MgSlab& S = L.s[k];
+      nf_tail_level& T = a.lv[q];
+      T.x = S.x; T.b = S.b; T.d_u = S.d_u; T.d_v = S.d_v; T.inv = S.inv;
+      T.nx = L.geom.nx; T.ny = L.geom.ny; T.ld = L.geom.ld; T.dx = L.geom.dx; T.dy = L.geom.dy;
+    }
+    a.N = mg->coarse_N;
+    a.coarse_inv = mg->coarse_inv[k];
+    a.rho = mg->cfg.rho;
+    a.omega = mg->cfg.omega;
+    a.pre = mg->cfg.pre;
+    a.post = mg->cfg.post;
+    NF_TRY(nfi_mg_tail(ctx, &a));
+  }
+  return NF_OK;
+}
+
 // one V (kind 0) or W (kind 1) cycle on level l: multigrid.py:304-432 / :434-560
 // want_norm (level 0 of the 'v' / 'w' loop): ask the last post-smoothing launch for the residual norms
 // (-> mg->scal[0][0..1]); *norm_fused reports whether that happened
@@ -666,6 +712,7 @@ static int mg_cycle(nf_mg* mg, int l, int kind, bool want_norm = false, bool* no
   const int nl = nlocal(mg);
   if (norm_fused) *norm_fused = false;
   if (in_norm_fused) *in_norm_fused = false;
+  if (l == mg->tail_level && kind == 0 && part == 0 && !want_norm && !in_norm) return mg_tail(mg);
   if (L.geom.nx <= mg->cfg.coarsest || l + 1 == (int)mg->lv.size()) return part == 1 ? NF_OK : mg_coarse_solve(mg, l);
   MgLevel& C = mg->lv[l + 1];
   if (part != 2) {
@@ -695,7 +742,8 @@ static int mg_cycle(nf_mg* mg, int l, int kind, bool want_norm = false, bool* no
         NF_TRY(nfi_residual(ctx, &gf, L.s[k].x, L.s[k].b, L.s[k].d_u, L.s[k].d_v, L.s[k].r));
         NF_TRY(nfi_restrict_inject(ctx, &gf, L.s[k].r, &gc, C.s[k].b));
       }
-      NF_TRY(nfi_fill(ctx, C.s[k].x, C.geom.elems(r), 0.0));
+      if (!(l + 1 == mg->tail_level && kind == 0))  // the tail kernel starts from zero by itself
+        NF_TRY(nfi_fill(ctx, C.s[k].x, C.geom.elems(r), 0.0));
     }
     NF_TRY(mg_publish_rhs(mg, l));
     if (part == 1) return NF_OK;
@@ -929,6 +977,12 @@ int nfi_mg_solve(nf_mg* mg, double* const* b, double* const* x, double* const* r
       const char* envl = getenv("NF_MG_LOOKAHEAD");
       bool lookahead = !(envl && envl[0] == '0') && mg->cfg.smoother == 0 && mg->cfg.restriction == 0 &&
                        mg->cfg.pre >= 1 && mg->cfg.pre <= 3 && mg->lv.size() > 1 && L.geom.nx > mg->cfg.coarsest;
+      {
+        // the streaming smoother evaluates the residual norms of its OUTPUT at no extra halo cost (no speculative launch
+        // needed): classic test behind the post-smoother on the levels it serves
+        const nf_grid g0 = L.geom.grid(mg->team->local[0]);
+        if (nfi_rbsor_stream_enabled(&g0)) lookahead = false;
+      }
       bool have_final_norm = false;
       for (int it = 0; it < mg->cfg.max_iterations; ++it) {
         if (lookahead) {

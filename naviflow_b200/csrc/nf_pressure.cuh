@@ -78,3 +78,29 @@ __device__ __forceinline__ double nf_jacobi_diag_cell(const nf_grid& g, const do
   return d;
 }
 
+
+// Value of interpolate_linear (multigrid_helpers.py:116-186) at fine cell (i,j) of an mx x my grid from the coarse array c:
+// coarse k -> fine 2k+1, even points averaged, the outer ring copied from ring 1 (clamped indices); grids of <= 3 cells only
+// get the coincident points (:127-128).
+__device__ __forceinline__ double nf_prolong_linear_value(const nf_grid& gc, const double* __restrict__ c,
+                                                          int mx, int my, int i, int j) {
+  const int mcx = gc.nx, mcy = gc.ny;
+  if (mx <= 3 || my <= 3) {
+    if ((i & 1) && (j & 1) && (i - 1) / 2 < mcx && (j - 1) / 2 < mcy) return c[nf_idx(gc, (i - 1) / 2, (j - 1) / 2)];
+    return 0.0;
+  }
+  i = min(max(i, 1), mx - 2);
+  j = min(max(j, 1), my - 2);
+  const bool io = i & 1, jo = j & 1;
+  const int I = io ? (i - 1) / 2 : (i - 2) / 2;
+  const int J = jo ? (j - 1) / 2 : (j - 2) / 2;
+  const bool iok = io ? (I < mcx) : (I <= mcx - 2);
+  const bool jok = jo ? (J < mcy) : (J <= mcy - 2);
+  if (!iok || !jok) return 0.0;
+  const size_t k = nf_idx(gc, I, J);
+  if (io && jo) return c[k];
+  if (io && !jo) return 0.5 * (c[k] + c[k + 1]);
+  if (!io && jo) return 0.5 * (c[k] + c[k + gc.ld]);
+  return 0.25 * (((c[k] + c[k + gc.ld]) + c[k + 1]) + c[k + gc.ld + 1]);
+}
+

@@ -687,6 +687,14 @@ int launch_tma_any(nf_ctx* ctx, const nf_grid* g, const double* pin, double* pou
   return launch_tma<NS, false, 0>(ctx, g, pin, pout, b, d_u, d_v, nullptr, omega, ex, used);
 }
 
+// The streaming kernel serves levels of >= NF_RBSOR_STREAM rows per side (default 1500: below that a strip's row chunks get
+// so short that the 12 halo rows per chunk outweigh the lower column redundancy) whose slab starts on an even row.
+bool nfi_rbsor_stream_enabled(const nf_grid* g) {
+  const char* env = getenv("NF_RBSOR_STREAM");
+  const int min_rows = env ? atoi(env) : 1500;
+  return g->nx >= min_rows && (g->ge - g->gb) >= 16 && (g->gb % 2) == 0 && (g->ld % 2) == 0;
+}
+
 // inv (optional): precomputed 1/aP of this level (nfi_inv_diag); NULL = divide inside the kernel
 int nfi_rbsor_fused_x(nf_ctx* ctx, const nf_grid* g, double** p, double** palt, const double* b, const double* d_u,
                       const double* d_v, const double* inv, double omega, int n_sweeps, nf_smooth_extra* extra) {
@@ -723,10 +731,14 @@ int nfi_rbsor_fused_x(nf_ctx* ctx, const nf_grid* g, double** p, double** palt, 
         ex.out = extra->in_norm_out;
       }
     }
-    // streaming (wavefront) kernel: plain launches (no fused residual work yet) on levels of >= NF_RBSOR_STREAM rows
-    const int stream_min_rows = getenv("NF_RBSOR_STREAM") ? atoi(getenv("NF_RBSOR_STREAM")) : 1 << 30;
-    if (mode == 0 && inv && g->nx >= stream_min_rows && (g->ge - g->gb) >= 16) {
-      NF_TRY(nfi_rbsor_stream(ctx, g, *p, *palt, b, d_u, d_v, inv, omega, ns, &used));
+    // streaming (wavefront) kernel (nf_rbsor_stream.cu) on large levels; its fused modes ride on 3-sweep launches and do not
+    // deliver the input norms (the multigrid driver then runs the classic convergence test behind the post-smoother)
+    if (nfi_rbsor_stream_enabled(g) && inv) {
+      int smode = 0;
+      if (extra && extra->mode != 0 && allow_extra && left == ns && ns == 3 && (g->gb % 2) == 0) smode = extra->mode;
+      NF_TRY(nfi_rbsor_stream(ctx, g, *p, *palt, b, d_u, d_v, inv, omega, ns, smode, extra, &used));
+      if (used && smode != 0) extra->fused = true;
+      if (used) mode = 0;
     }
     if (use_tma && !used) {  // persistent TMA pipeline: pays off once every SM gets several tiles
       if (ns == 3) st = launch_tma_any<3>(ctx, g, *p, *palt, b, d_u, d_v, inv, omega, mode, ex, &used);

@@ -86,9 +86,8 @@ struct Job {
 // update needs a validity predicate except the pinned cell (0,0).  ROWB / COLB: the variant handles row / column edges;
 // only the 8-step groups that touch rows 0 / nx-1 run ROWB, only the first and last strip run COLB.
 struct ColFlags {
-  bool A_bnd, B_bnd;   // the lane's cell is in column 0 or ny-1
-  bool z0, z1, z2;     // face j = jA, jA+1, jA+2 is column 0 or ny: zero at load
-  bool pin;            // the lane owns column 0 (cell A)
+  bool A_first, A_last, B_last;  // the lane's cell A is column 0 / ny-1, its cell B is column ny-1 (column 0 is always an A)
+  bool z0, z1, z2;               // face j = jA, jA+1, jA+2 is column 0 or ny: zero at load
 };
 
 // Loads row s of p and d_u (-> slot SN) and the coefficient rows of row s-1 (-> slot SN-1) from row RW of a stage.
@@ -106,7 +105,7 @@ __device__ __forceinline__ void stream_load(Win& W, const nf_grid& g, int s, int
   W.pA[SN] = pp.x;
   *pB_out = pp.y;
   if (ROWB && COLB) {
-    if (s == 0 && cf.pin) W.pA[SN] = 0.0;  // pinned cell (gauss_seidel.py:145, :305)
+    if (s == 0 && cf.A_first) W.pA[SN] = 0.0;  // pinned cell (gauss_seidel.py:145, :305)
   }
   double fa = g.rho * uu.x * g.dy, fb = g.rho * uu.y * g.dy;
   if (ROWB) {
@@ -119,8 +118,6 @@ __device__ __forceinline__ void stream_load(Win& W, const nf_grid& g, int s, int
     if (cf.z0) g0 = 0.0;
     if (cf.z1) g1 = 0.0;
     if (cf.z2) g2 = 0.0;
-    if (cf.A_bnd) g0 = 0.0;  // aS of a boundary column (g0 is used by this lane's cell A only)
-    if (cf.B_bnd) g2 = 0.0;  // aN of a boundary column (g2 is used by this lane's cell B only)
   }
   W.g0[SC] = g0;
   W.g1[SC] = g1;
@@ -147,8 +144,8 @@ __device__ __forceinline__ void stream_update(Win& W, const nf_grid& g, int r, d
     if (r == 0) aE = 0.0;
     if (r == g.nx - 1) aW = 0.0;
   }
-  if (COLB) {  // the face between the lane's two cells serves both: zero it for the one in a boundary column
-    if (UPD_A) { if (cf.A_bnd) aN = 0.0; } else { if (cf.B_bnd) aS = 0.0; }
+  if (COLB) {  // column 0 keeps no N link, column ny-1 no S link (their outer faces are zero since the load)
+    if (UPD_A) { if (cf.A_first) aN = 0.0; if (cf.A_last) aS = 0.0; } else { if (cf.B_last) aS = 0.0; }
   }
   double acc = bc;  // ((((b + E) + W) + N) + S) * (1/aP): gauss_seidel.py:285-299
   acc += aE * pE;
@@ -158,10 +155,54 @@ __device__ __forceinline__ void stream_update(Win& W, const nf_grid& g, int r, d
   const double pn = acc * ic;
   const double pu = pc + omega * (pn - pc);
   if (UPD_A) {
-    if (ROWB && COLB) { if (!(r == 0 && cf.pin)) W.pA[a] = pu; }
+    if (ROWB && COLB) { if (!(r == 0 && cf.A_first)) W.pA[a] = pu; }
     else W.pA[a] = pu;
   } else {
     W.pB[a] = pu;
+  }
+}
+
+// b - A p of the lane's two cells of a FINAL row r (nf_Ap_cell's expression order: diag*p - E - W - N - S with the reference's
+// diagonal folding at the edges, matrix_free.py:63-121).  Faces are the raw ones (the faces outside the domain are zero
+// since the load); nS / nN = the in-row neighbours across the pair boundary.
+struct StreamExtra {
+  nf_grid gc;          // EXTRA 2: coarse grid and its right-hand side
+  double* coarse_b;
+  double* partials;    // EXTRA 1: per-job partial sums, ticket, result (sum r^2, sum b^2)
+  unsigned int* ticket;
+  double* out;
+};
+
+template <bool ROWB, bool COLB>
+__device__ __forceinline__ void stream_residual(const nf_grid& g, int r, const ColFlags& cf, double pWA, double pWB,
+                                                double pcA, double pcB, double pEA, double pEB, double fWA, double fWB,
+                                                double fEA, double fEB, double g0, double g1, double g2, double bA,
+                                                double bB, double nS, double nN, double* rA, double* rB) {
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    double e = q ? fEB : fEA, w = q ? fWB : fWA, n = q ? g2 : g1, s = q ? g1 : g0;
+    const double pc = q ? pcB : pcA, pE = q ? pEB : pEA, pW = q ? pWB : pWA;
+    const double pN = q ? nN : pcB, pS = q ? pcA : nS, b = q ? bB : bA;
+    double diag;
+    if (ROWB || COLB) {
+      diag = 0.0;
+      const bool first = COLB && q == 0 && cf.A_first, last = COLB && (q ? cf.B_last : cf.A_last);
+      if (ROWB) { if (r == 0) diag += e; if (r == g.nx - 1) diag += w; }
+      if (COLB) { if (first) diag += n; if (last) diag += s; }
+      if (ROWB) { if (r == 0) e = 0.0; if (r == g.nx - 1) w = 0.0; }
+      if (COLB) { if (first) n = 0.0; if (last) s = 0.0; }
+      diag += ((e + w) + n) + s;
+    } else {
+      diag = ((e + w) + n) + s;
+    }
+    double o = diag * pc;
+    o -= e * pE;
+    o -= w * pW;
+    o -= n * pN;
+    o -= s * pS;
+    double res = b - o;
+    if (ROWB && COLB) { if (q == 0 && r == 0 && cf.A_first) res = b - pc; }  // identity row of the pinned cell
+    if (q) *rB = res; else *rA = res;
   }
 }
 
@@ -187,12 +228,22 @@ __device__ __forceinline__ void stream_pair(Win& W, const nf_grid& g, int s, dou
 // X_(t-1) and values of the previous double step -- so the statements are emitted as X_0, {X_1, Y_0}, {X_2, Y_1}, ... , Y_last
 // and each brace holds two independent dependency chains for the scheduler to interleave (a single step is one serial chain
 // of 2NS x 9 fp64 operations; with two warps per scheduler that left the issue slots 60 % empty).
-template <int PH, int NP, bool ROWB, bool COLB>
+// EXTRA work on the rows that have become final (both need NP == 6; the halo is two columns / rows deeper):
+//   1  sum (b - A p)^2, sum b^2 over the level (the multigrid convergence test, multigrid.py:185-240) -> acc[0..1]
+//   2  coarse_b = FW(b - A p) (multigrid.py:362-372 after the pre-smoothing); acc[0..1] carries the residual of the
+//      previous even row.  A double step finalises rows s-6 and s-5, so the residual rows s-7 and s-6 are complete.
+template <int PH, int NP, bool ROWB, bool COLB, int EXTRA>
 __device__ __forceinline__ void stream_step2(Win& W, const nf_grid& g, const Job& jb, int s, int lane, double omega,
-                                             const unsigned char* stage, const ColFlags& cf, double* __restrict__ pout) {
+                                             const unsigned char* stage, const ColFlags& cf, double* __restrict__ pout,
+                                             double (&acc)[2], const StreamExtra& ex) {
   static_assert((PH & 1) == 0, "double steps start on even phases");
+  static_assert(EXTRA == 0 || NP == 6, "the fused residual work rides on 3-sweep launches");
   constexpr int S0 = PH, S1 = (PH + 1) & 7;  // slots of rows s, s+1
+  constexpr int HL = EXTRA ? NP + 2 : NP;     // halo columns on each side of the strip
   double pB_s1;
+  // rows s-8 (p) and s-7 (p of cell A, faces) leave the window with the loads below; the residual of row s-7 needs them
+  double o8A = 0.0, o8B = 0.0, o7A = 0.0, o7fA = 0.0, o7fB = 0.0;
+  if (EXTRA != 0) { o8A = W.pA[S0]; o8B = W.pB[S0]; o7A = W.pA[S1]; o7fA = W.fA[S1]; o7fB = W.fB[S1]; }
   stream_load<S0, PH % RB, ROWB, COLB>(W, g, s, lane, stage, cf, &W.pB[S0]);  // slot of row s-8: free
   // pB of row s+1 shares its slot with row s-7, which chain X still reads (W neighbour of its last update): committed below
   stream_load<S1, (PH + 1) % RB, ROWB, COLB>(W, g, s + 1, lane, stage, cf, &pB_s1);
@@ -201,11 +252,47 @@ __device__ __forceinline__ void stream_step2(Win& W, const nf_grid& g, const Job
   for (int t = 0; t < NP; ++t) nbX[t] = __shfl_down_sync(0xffffffffu, W.pA[(PH + 15 - t) & 7], 1);  // rows s-1-t
   nbY[0] = __shfl_up_sync(0xffffffffu, W.pB[S0], 1);                                                // row s
   stream_pair<PH, 0, NP, ROWB, COLB>(W, g, s, omega, cf, nbX, nbY);
-  W.pB[S1] = pB_s1;
-  // ---- rows s-NP and s+1-NP are final ----
   const int c = 2 * lane;
   const int gjA = jb.j0 + c;
-  if (c >= NP && c < SW - NP && gjA < g.ny) {
+  if (EXTRA != 0) {
+    constexpr int S2 = (PH + 2) & 7, S3 = (PH + 3) & 7;  // rows s-6, s-5
+    double r7A, r7B, r6A, r6B;
+    {
+      const double nS = __shfl_up_sync(0xffffffffu, W.pB[S1], 1), nN = __shfl_down_sync(0xffffffffu, o7A, 1);
+      stream_residual<ROWB, COLB>(g, s - 7, cf, o8A, o8B, o7A, W.pB[S1], W.pA[S2], W.pB[S2], o7fA, o7fB, W.fA[S2], W.fB[S2],
+                                  W.g0[S1], W.g1[S1], W.g2[S1], W.bA[S1], W.bB[S1], nS, nN, &r7A, &r7B);
+    }
+    {
+      const double nS = __shfl_up_sync(0xffffffffu, W.pB[S2], 1), nN = __shfl_down_sync(0xffffffffu, W.pA[S2], 1);
+      stream_residual<ROWB, COLB>(g, s - 6, cf, o7A, W.pB[S1], W.pA[S2], W.pB[S2], W.pA[S3], W.pB[S3], W.fA[S2], W.fB[S2],
+                                  W.fA[S3], W.fB[S3], W.g0[S2], W.g1[S2], W.g2[S2], W.bA[S2], W.bB[S2], nS, nN, &r6A, &r6B);
+    }
+    const bool colA = c >= HL && c < SW - HL && gjA < g.ny, colB = colA && gjA + 1 < g.ny;
+    if (EXTRA == 1) {
+      if (s - 7 >= jb.ia && s - 7 < jb.ib) {
+        if (colA) { acc[0] += r7A * r7A; acc[1] += W.bA[S1] * W.bA[S1]; }
+        if (colB) { acc[0] += r7B * r7B; acc[1] += W.bB[S1] * W.bB[S1]; }
+      }
+      if (s - 6 >= jb.ia && s - 6 < jb.ib) {
+        if (colA) { acc[0] += r6A * r6A; acc[1] += W.bA[S2] * W.bA[S2]; }
+        if (colB) { acc[0] += r6B * r6B; acc[1] += W.bB[S2] * W.bB[S2]; }
+      }
+    } else {
+      // coarse row I = (s-8)/2: fine rows s-8 (carried), s-7, s-6; coarse column J = gjA/2: fine columns gjA .. gjA+2
+      const double n7 = __shfl_down_sync(0xffffffffu, r7A, 1), n6 = __shfl_down_sync(0xffffffffu, r6A, 1);
+      const double n8 = __shfl_down_sync(0xffffffffu, acc[0], 1);
+      const int I = (s - 8) >> 1, J = gjA >> 1;
+      if (s - 7 >= jb.ia && s - 7 < jb.ib && I >= ex.gc.gb && I < ex.gc.ge && colA && J < ex.gc.ny) {
+        const double cc = r7B, n = n7, sd = r7A, e = r6B, w = acc[1], ne = n6, nw = n8, se = r6A, sw = acc[0];
+        ex.coarse_b[nf_idx(ex.gc, I, J)] = (cc / 4.0 + (((n + sd) + e) + w) / 8.0) + (((ne + nw) + se) + sw) / 16.0;
+      }
+      acc[0] = r6A;
+      acc[1] = r6B;
+    }
+  }
+  W.pB[S1] = pB_s1;
+  // ---- rows s-NP and s+1-NP are final ----
+  if (c >= HL && c < SW - HL && gjA < g.ny) {
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
       const int rf = s + q - NP;
@@ -220,9 +307,10 @@ __device__ __forceinline__ void stream_step2(Win& W, const nf_grid& g, const Job
 }
 
 // The march of one job.  COLB (first / last strip) is a property of the job; the row variant is chosen per group of 8 steps.
-template <int NP, bool COLB, class Issue>
+template <int NP, bool COLB, int EXTRA, class Issue>
 __device__ __forceinline__ void stream_job(const nf_grid& g, const Job& jb, int lane, double omega, const unsigned char* ring,
-                                           unsigned bar0, Issue& issue, double* __restrict__ pout) {
+                                           unsigned bar0, Issue& issue, double* __restrict__ pout, double (&acc)[2],
+                                           const StreamExtra& ex) {
   Win W;
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
@@ -235,12 +323,12 @@ __device__ __forceinline__ void stream_job(const nf_grid& g, const Job& jb, int 
   ColFlags cf = {false, false, false, false, false, false};
   if (COLB) {
     const int gjA = jb.j0 + 2 * lane;
-    cf.A_bnd = gjA == 0 || gjA == g.ny - 1;
-    cf.B_bnd = gjA + 1 == 0 || gjA + 1 == g.ny - 1;
+    cf.A_first = gjA == 0;
+    cf.A_last = gjA == g.ny - 1;
+    cf.B_last = gjA + 1 == g.ny - 1;
     cf.z0 = gjA == 0 || gjA == g.ny;
     cf.z1 = gjA + 1 == 0 || gjA + 1 == g.ny;
     cf.z2 = gjA + 2 == 0 || gjA + 2 == g.ny;
-    cf.pin = gjA == 0;
   }
 
 #define NF_STREAM_STEP2(PH, ROWB)                                                                   \
@@ -252,7 +340,7 @@ __device__ __forceinline__ void stream_job(const nf_grid& g, const Job& jb, int 
       while (!mbar_try(bar, ring_phase)) {}                                                         \
     }                                                                                               \
     const unsigned char* stage = ring + (PH / RB) * SG_BYTES;                                       \
-    stream_step2<PH, NP, ROWB, COLB>(W, g, jb, s, lane, omega, stage, cf, pout);                   \
+    stream_step2<PH, NP, ROWB, COLB, EXTRA>(W, g, jb, s, lane, omega, stage, cf, pout, acc, ex);   \
     if (((PH + 1) % RB) == RB - 1) { /* the stage is consumed: refill it for the steps 8 ahead */    \
       __syncwarp();                                                                                 \
       if (lane == 0 && s + 8 - (RB - 2) <= jb.s_last) issue(s + 8 - (RB - 2));                      \
@@ -288,11 +376,13 @@ struct JobPlan {
   int jobs_inner, njobs;      // jobs_inner = n_inner * chunks of an inner strip
 };
 
-template <int NS, int WPC>
+template <int NS, int WPC, int EXTRA>
 __global__ void __launch_bounds__(32 * WPC, 1) __maxnreg__(stream_maxreg(WPC))
-k_rbsor_stream(nf_grid g, const __grid_constant__ StreamMaps maps, double* __restrict__ pout, double omega, JobPlan plan) {
+k_rbsor_stream(nf_grid g, const __grid_constant__ StreamMaps maps, double* __restrict__ pout, double omega, JobPlan plan,
+               StreamExtra ex) {
   constexpr int NP = 2 * NS;
-  constexpr int SCOLS = SW - 2 * NP;  // columns a strip finalises
+  constexpr int HL = EXTRA ? NP + 2 : NP;
+  constexpr int SCOLS = SW - 2 * HL;  // columns a strip finalises
   extern __shared__ __align__(128) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int job = blockIdx.x * WPC + warp;
@@ -320,10 +410,10 @@ k_rbsor_stream(nf_grid g, const __grid_constant__ StreamMaps maps, double* __res
     }
     jb.ia = g.gb + chunk * len;
     jb.ib = jb.ia + len < g.ge ? jb.ia + len : g.ge;
-    jb.r0 = (jb.ia - NP) & ~1;
-    jb.s_last = jb.ib - 1 + NP;
+    jb.r0 = (jb.ia - HL) & ~1;
+    jb.s_last = jb.ib - 1 + NP + EXTRA;  // EXTRA 1 needs the residual of row ib-1 (p final up to ib), EXTRA 2 that of row ib
     if (((jb.s_last - jb.r0) & 1) == 0) jb.s_last += 1;  // steps come in pairs
-    jb.j0 = strip * SCOLS - NP;
+    jb.j0 = strip * SCOLS - HL;
   }
 
   if (lane == 0) {
@@ -349,8 +439,39 @@ k_rbsor_stream(nf_grid g, const __grid_constant__ StreamMaps maps, double* __res
       if (jb.r0 + q * RB <= jb.s_last) issue(jb.r0 + q * RB);
   }
 
-  if (colb) stream_job<NP, true>(g, jb, lane, omega, ring, bar0, issue, pout);
-  else stream_job<NP, false>(g, jb, lane, omega, ring, bar0, issue, pout);
+  double acc[2] = {0.0, 0.0};
+  if (colb) stream_job<NP, true, EXTRA>(g, jb, lane, omega, ring, bar0, issue, pout, acc, ex);
+  else stream_job<NP, false, EXTRA>(g, jb, lane, omega, ring, bar0, issue, pout, acc, ex);
+  if (EXTRA == 1) {
+    // deterministic reduction: fixed tree inside the warp, one partial per job, the last job to arrive adds the partials in
+    // job order
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) acc[k] += __shfl_down_sync(0xffffffffu, acc[k], off);
+    unsigned int t = 0;
+    if (lane == 0) {
+      ex.partials[job] = acc[0];
+      ex.partials[NF_MAX_PARTIALS + job] = acc[1];
+      __threadfence();
+      t = atomicAdd(ex.ticket, 1u);
+    }
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t == (unsigned int)(plan.njobs - 1)) {
+      __threadfence();
+      double v0 = 0.0, v1 = 0.0;
+      for (int q = lane; q < plan.njobs; q += 32) {
+        v0 += ((volatile double*)ex.partials)[q];
+        v1 += ((volatile double*)ex.partials)[NF_MAX_PARTIALS + q];
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        v0 += __shfl_down_sync(0xffffffffu, v0, off);
+        v1 += __shfl_down_sync(0xffffffffu, v1, off);
+      }
+      if (lane == 0) { ex.out[0] = v0; ex.out[1] = v1; *ex.ticket = 0u; }
+    }
+  }
 }
 
 // ---- tensor maps, cached per (array, shape): re-encoding costs a driver call per array and launch ----
@@ -415,13 +536,13 @@ bool row_map(CUtensorMap* out, const double* base, int rows, int cols, int ld, i
 }
 
 // strips / chunks of a level: one job per warp slot of a single wave (148 SMs x WPC warps)
-template <int NS>
+template <int NS, int EXTRA>
 JobPlan make_plan(const nf_grid* g, int slots) {
-  constexpr int NP = 2 * NS, SCOLS = SW - 2 * NP;
+  constexpr int NP = 2 * NS, HL = EXTRA ? NP + 2 : NP, SCOLS = SW - 2 * HL;
   const int rows = g->ge - g->gb;
   const int nstrips = (g->ny + SCOLS - 1) / SCOLS;
   // strip k is an edge strip when its 64 columns (plus the d_v column to their right) reach column 0 or ny-1
-  int first_right = (g->ny - 1 - SW + NP + SCOLS - 1) / SCOLS;  // smallest k with k*SCOLS - NP + SW >= ny-1
+  int first_right = (g->ny - 1 - SW + HL + SCOLS - 1) / SCOLS;  // smallest k with k*SCOLS - HL + SW >= ny-1
   if (first_right < 1) first_right = 1;
   if (first_right > nstrips) first_right = nstrips;
   JobPlan P;
@@ -432,7 +553,7 @@ JobPlan make_plan(const nf_grid* g, int slots) {
   // the smallest chunk length (of the inner strips) whose jobs fit into one wave
   int best_li = -1, best_le = -1;
   for (int li = 8; li <= ((rows + 1) & ~1) + 2; li += 2) {
-    int le = (int)((li + 2 * NP) / edge_cost) - 2 * NP;
+    int le = (int)((li + 2 * HL) / edge_cost) - 2 * HL;
     le &= ~1;
     if (le < 8) le = 8;
     const int ci = (rows + li - 1) / li, ce = (rows + le - 1) / le;
@@ -446,13 +567,14 @@ JobPlan make_plan(const nf_grid* g, int slots) {
   return P;
 }
 
-template <int NS, int WPC>
+template <int NS, int WPC, int EXTRA>
 int launch_stream(nf_ctx* ctx, const nf_grid* g, const double* pin, double* pout, const double* b, const double* d_u,
-                  const double* d_v, const double* inv, double omega, bool* used) {
+                  const double* d_v, const double* inv, double omega, const StreamExtra& ex, bool* used) {
   constexpr int SMEM = WPC * NSTG * SG_BYTES + WPC * NSTG * 8;
   *used = false;
   if ((g->gb & 1) != 0) return NF_OK;  // odd origin (the phases assume even chunk starts): the caller falls back
-  const JobPlan plan = make_plan<NS>(g, NF_SM_COUNT * WPC);
+  const JobPlan plan = make_plan<NS, EXTRA>(g, NF_SM_COUNT * WPC);
+  if (plan.njobs > NF_MAX_PARTIALS) return NF_OK;
   const int row_end = g->row1 > 0 ? g->row1 : g->nx + 1;
   const int stored_p = (row_end < g->nx ? row_end : g->nx) - g->row0;
   const int stored_u = row_end - g->row0;
@@ -463,11 +585,12 @@ int launch_stream(nf_ctx* ctx, const nf_grid* g, const double* pin, double* pout
     return NF_OK;
   static bool attr_set = false;
   if (!attr_set) {
-    NF_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_rbsor_stream<NS, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    NF_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_rbsor_stream<NS, WPC, EXTRA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            SMEM));
     attr_set = true;
   }
   const int grid = (plan.njobs + WPC - 1) / WPC;
-  k_rbsor_stream<NS, WPC><<<grid, 32 * WPC, SMEM, ctx->stream>>>(*g, m, pout, omega, plan);
+  k_rbsor_stream<NS, WPC, EXTRA><<<grid, 32 * WPC, SMEM, ctx->stream>>>(*g, m, pout, omega, plan, ex);
   NF_LAUNCH_CHECK(ctx);
   *used = true;
   return NF_OK;
@@ -475,12 +598,24 @@ int launch_stream(nf_ctx* ctx, const nf_grid* g, const double* pin, double* pout
 
 }  // namespace
 
+// mode 0: plain; 1: + residual norms -> extra->out[0..1]; 2: + coarse_b = FW(b - A p) on extra->gc.  The fused modes exist
+// for 3-sweep launches; *used = false means nothing was launched (the caller takes another path).
 int nfi_rbsor_stream(nf_ctx* ctx, const nf_grid* g, const double* pin, double* pout, const double* b, const double* d_u,
-                     const double* d_v, const double* inv, double omega, int ns, bool* used) {
+                     const double* d_v, const double* inv, double omega, int ns, int mode, const nf_smooth_extra* extra,
+                     bool* used) {
   *used = false;
   if (!inv) return NF_OK;
-  if (ns == 3) return launch_stream<3, 8>(ctx, g, pin, pout, b, d_u, d_v, inv, omega, used);
-  if (ns == 2) return launch_stream<2, 8>(ctx, g, pin, pout, b, d_u, d_v, inv, omega, used);
-  if (ns == 1) return launch_stream<1, 8>(ctx, g, pin, pout, b, d_u, d_v, inv, omega, used);
+  StreamExtra ex;
+  ex.gc = *g; ex.coarse_b = nullptr; ex.partials = ctx->partials; ex.ticket = ctx->ticket; ex.out = nullptr;
+  if (mode != 0) {
+    if (ns != 3 || !extra) return NF_OK;
+    ex.gc = extra->gc; ex.coarse_b = extra->coarse_b; ex.out = extra->out;
+    if (mode == 1) return launch_stream<3, 8, 1>(ctx, g, pin, pout, b, d_u, d_v, inv, omega, ex, used);
+    if (mode == 2) return launch_stream<3, 8, 2>(ctx, g, pin, pout, b, d_u, d_v, inv, omega, ex, used);
+    return NF_OK;
+  }
+  if (ns == 3) return launch_stream<3, 8, 0>(ctx, g, pin, pout, b, d_u, d_v, inv, omega, ex, used);
+  if (ns == 2) return launch_stream<2, 8, 0>(ctx, g, pin, pout, b, d_u, d_v, inv, omega, ex, used);
+  if (ns == 1) return launch_stream<1, 8, 0>(ctx, g, pin, pout, b, d_u, d_v, inv, omega, ex, used);
   return NF_OK;
 }

@@ -119,27 +119,7 @@ __global__ void k_restrict_coeffs(nf_grid gf, const double* __restrict__ d_u, co
 //     Ring cells copy ring 1: f[i,j] = V(clamp(i,1,m-2), clamp(j,1,m-2))  (:170-186).
 //     m <= 3: only the coincident points, no ring copy (:127-128).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double nf_prolong_linear_value(const nf_grid& gc, const double* __restrict__ c,
-                                                          int mx, int my, int i, int j) {
-  const int mcx = gc.nx, mcy = gc.ny;
-  if (mx <= 3 || my <= 3) {
-    if ((i & 1) && (j & 1) && (i - 1) / 2 < mcx && (j - 1) / 2 < mcy) return c[nf_idx(gc, (i - 1) / 2, (j - 1) / 2)];
-    return 0.0;
-  }
-  i = min(max(i, 1), mx - 2);
-  j = min(max(j, 1), my - 2);
-  const bool io = i & 1, jo = j & 1;
-  const int I = io ? (i - 1) / 2 : (i - 2) / 2;
-  const int J = jo ? (j - 1) / 2 : (j - 2) / 2;
-  const bool iok = io ? (I < mcx) : (I <= mcx - 2);
-  const bool jok = jo ? (J < mcy) : (J <= mcy - 2);
-  if (!iok || !jok) return 0.0;
-  const size_t k = nf_idx(gc, I, J);
-  if (io && jo) return c[k];
-  if (io && !jo) return 0.5 * (c[k] + c[k + 1]);
-  if (!io && jo) return 0.5 * (c[k] + c[k + gc.ld]);
-  return 0.25 * (((c[k] + c[k + gc.ld]) + c[k + 1]) + c[k + gc.ld + 1]);
-}
+// nf_prolong_linear_value: nf_pressure.cuh (shared with the multigrid tail kernel)
 
 // Bulk of the fine grid: one thread per coarse cell (I,J) writes the 2x2 fine block (2I+1..2I+2, 2J+1..2J+2) from
 // c[I..I+1][J..J+1] (each coarse value loaded once per thread, no per-cell index logic).  The thin strips the
