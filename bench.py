@@ -41,8 +41,10 @@ def parse():
                     "4097*sqrt(N) on N GPUs (weak scaling: 16.8 M cells per GPU)")
     ap.add_argument("--momentum-sweeps", type=int, default=5)
     ap.add_argument("--mg-cycles", type=int, default=100, help="max V-cycles per pressure solve")
-    ap.add_argument("--cpu-sample-n", type=int, default=513, help="grid of the bounded CPU sample")
+    ap.add_argument("--cpu-sample-n", type=int, default=0, help="grid of the bounded CPU sample (0: 513 inside the "
+                    "GPU arm's cpu_baseline, 1025 or 513 for --impl reference depending on --steps)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-kernels", action="store_true", help="skip the port's 4097^2 kernel timings (~20 s)")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
@@ -145,7 +147,7 @@ def cpu_baseline_simple_run(n, reynolds, n_sweeps, iterations, mg_kwargs):
     return (time.perf_counter() - t0) / iterations
 
 
-def cpu_baseline_pressure_kernels(n, dx, dy, d_u, d_v, us, vs, with_mg=True):
+def cpu_baseline_pressure_kernels(n, dx, dy, d_u, d_v, us, vs, with_mg=True, with_lex=True):
     """Milliseconds of one application / iteration / sweep / cycle of the oracle port's pressure kernels on the given
     system (single thread), plus one sequential Gauss-Seidel sweep timed on a 257^2 sample and scaled per cell."""
     from oracle import np_oracle as O
@@ -156,7 +158,7 @@ def cpu_baseline_pressure_kernels(n, dx, dy, d_u, d_v, us, vs, with_mg=True):
     cpu["jacobi_iteration_ms"] = (time.perf_counter() - t0) * 1e3
     t0 = time.perf_counter(); O.rb_sor(np.zeros_like(bh), bh, dx, dy, 1.0, d_u, d_v, 1.5, 1)
     cpu["rbsor_sweep_ms"] = (time.perf_counter() - t0) * 1e3
-    if with_mg:
+    if with_mg and with_lex:
         ns = 257
         rs = np.random.default_rng(5)
         dus = (0.7 * dy / 4e-3) * (1 + 0.1 * rs.random((ns + 1, ns)))
@@ -164,6 +166,7 @@ def cpu_baseline_pressure_kernels(n, dx, dy, d_u, d_v, us, vs, with_mg=True):
         t0 = time.perf_counter()
         O.gs_lex(np.zeros((ns, ns)), 1e-2 * rs.standard_normal((ns, ns)), dx, dy, 1.0, dus, dvs, 1.8, 1)
         cpu["gs_lexicographic_sweep_ms_scaled_from_257"] = (time.perf_counter() - t0) * 1e3 * (n * n) / (ns * ns)
+    if with_mg:
         mcfg = O.MGConfig(omega=1.5, pre=3, post=3)
         t0 = time.perf_counter(); O.mg_cycle(mcfg, np.zeros_like(bh), bh, dx, dy, d_u, d_v)
         cpu["mg_v33_cycle_ms"] = (time.perf_counter() - t0) * 1e3
@@ -179,11 +182,22 @@ def cpu_threads():
         return 1
 
 
-def run_reference(args, rank):
-    """Reference arm: the reference's CPU algorithm (oracle port) on the host cores; rank 0 only."""
+def reference_sample_n(args):
+    """Grid of the bounded CPU sample: 1025^2 (about 8 s per outer iteration of the NumPy port) when the whole
+    --steps/--warmup run then stays within a few minutes, else 513^2 (about 2 s)."""
+    if args.cpu_sample_n > 0:
+        return args.cpu_sample_n
+    return 1025 if (args.steps + args.warmup) <= 12 else 513
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the reference algorithm's CPU path (oracle port: /root/reference is pure Python and not
+    present on the GPU box) on the host cores; rank 0 only.  `config` is this repo's arm's config (the workload
+    both arms are quoted on); each timed step is one outer iteration of that workload on the bounded sample grid
+    named in `sample` / `cpu_baseline.sample` -- MLUPS is per cell, so the grid size cancels to first order."""
     if rank != 0:
         return
-    n = args.cpu_sample_n
+    n = reference_sample_n(args)
     step = cpu_oracle_step_fn(n, args)
     for _ in range(args.warmup):
         step()
@@ -192,27 +206,31 @@ def run_reference(args, rank):
         step()
     dt = time.perf_counter() - t0
     mlups = n * n * args.steps / dt / 1e6
+    sample = (f"{n}x{n} grid of the same workload (same Re, relaxation, momentum sweeps, V(3,3) settings and stopping "
+              f"tolerance), {args.steps} outer iterations after {args.warmup} warm-up; NumPy/SciPy oracle port, single "
+              f"threaded (host has {os.cpu_count()} cores, BLAS threads {cpu_threads()})")
     line = {
         "impl": "reference", "metric": "simple_outer_mlups", "value": mlups, "unit": "MLUPS",
         "iter_per_s": args.steps / dt, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, args.n),
-        "cpu_baseline": {"value": mlups, "unit": "MLUPS", "cores": 1, "kind": "port",
-                         "sample": f"{n}x{n} grid of the same workload, {args.steps} outer iterations after "
-                                   f"{args.warmup} warm-up (NumPy is single threaded; host has {os.cpu_count()} cores, "
-                                   f"BLAS threads {cpu_threads()})"},
+        "config": workload_config(args, args.n, world),
+        "sample": {"n": n, "cells": n * n, "note": "bounded sample of config.workload: ms_per_step and iter_per_s are "
+                                                   "per outer iteration of THIS grid, value (MLUPS) is per cell"},
+        "cpu_baseline": {"value": mlups, "unit": "MLUPS", "cores": 1, "kind": "port", "sample": sample},
         "e2e": {"value": mlups, "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
 
 
-def workload_config(args, n):
+def workload_config(args, n, world=1):
+    """The workload both arms are quoted on (identical dict in both lines)."""
     return {"workload": f"lid-driven cavity {n}x{n} Re=1000 SIMPLE from rest, {args.momentum_sweeps} Jacobi momentum "
                         f"sweeps/component, multigrid V(3,3) RB-SOR omega 1.5 FW+bilinear coarsest 7, cycles to "
                         f"||r||/||b||<1e-3 (max {args.mg_cycles})",
             "n": n, "reynolds": RE, "alpha_p": 0.3, "alpha_u": 0.7,
-            "l2_policy": "fields (134 MB each at 4097^2, ~25 live arrays) exceed the 126 MB L2; no explicit flush"}
+            "l2_policy": "fields (134 MB each at 4097^2, ~25 live arrays) exceed the 126 MB L2; no explicit flush",
+            "parallelism": "single GPU" if world == 1 else f"{world} row slabs, one rank per GPU"}
 
 
 WEAK_N = {1: 4097, 2: 5793, 4: 8193, 8: 11585}
@@ -226,7 +244,7 @@ def main():
     if args.n <= 0:
         args.n = WEAK_N.get(world, int(round(4097 * world ** 0.5)))
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, world)
         return
     import torch
     import torch.distributed as dist
@@ -284,10 +302,10 @@ def main():
     cells = float(n) * n                  # one grid, cut into row slabs over the ranks
     mlups = cells * args.steps / (ms * 1e-3) / 1e6
 
-    # ---- roofline of the dominant kernel (red-black SOR colour pass on the finest level) ------------
+    # ---- roofline of the dominant kernel (the finest-level smoother launch) ---------------------------
     peak, peak_src = measured_peaks()
     lib = ctx.lib
-    nr = min(n, 4097)                      # the dominant kernel is timed alone on a 4097^2 level (> L2)
+    nr = min(n, 4097)                      # the dominant kernel is also timed alone on a 4097^2 level (> L2)
     g = ctx.grid(nr, nr, 1.0 / (nr - 1), 1.0 / (nr - 1), 1.0)
     rng = np.random.default_rng(0)
     mk = lambda scale: ctx.upload(scale * (1 + 0.1 * rng.random((nr + 1, nr + 1))), nr, nr)
@@ -302,7 +320,7 @@ def main():
     ctx.check(lib.nf_rbsor_sweeps_fused(*args_f, 6))
     torch.cuda.synchronize()
     e0.record()
-    ctx.check(lib.nf_rbsor_sweeps_fused(*args_f, 3 * reps))       # `reps` launches of k_rbsor_fused<3>
+    ctx.check(lib.nf_rbsor_sweeps_fused(*args_f, 3 * reps))       # `reps` plain 3-sweep launches
     e1.record()
     torch.cuda.synchronize()
     ms_launch = e0.elapsed_time(e1) / reps
@@ -314,33 +332,45 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms_color = e0.elapsed_time(e1) / (2 * reps)
-    traffic = None
+    # DRAM bytes per launch of each variant from this round's ncu capture (dram__bytes_read.sum + dram__bytes_write.sum)
+    prof = {}
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_dominant_kernel.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_dominant_kernel.json")) as f:
             prof = json.load(f)
-        if prof.get("n") == n:
-            traffic = prof["dram_bytes_per_launch"]
     except Exception:
         pass
-    isolated = {"ms_per_launch": ms_launch, "achieved": achieved, "frac": achieved / peak,
+    variants = prof.get("variants", {}) if prof.get("n") == n else {}
+    plain_traffic = variants.get("plain", {}).get("dram_bytes_per_launch")
+    isolated = {"variant": "plain (3 sweeps)", "ms_per_launch": ms_launch, "achieved": achieved, "frac": achieved / peak,
+                "traffic": plain_traffic,
+                "dram_frac": (plain_traffic / (ms_launch * 1e-3) / 1e9 / peak) if plain_traffic else None,
                 "how": f"{reps} back-to-back launches on a synthetic {n}^2 level, CUDA events"}
-    if live_launches > 0 and n_alg == n:   # the number the roofline is quoted on: launches inside the real steps
+    traffic = plain_traffic
+    live = live_launches > 0 and n_alg == n
+    if live:   # the number the roofline is quoted on: launches inside the real steps
         ms_launch = live_ms / live_launches
         if os.environ.get("NF_RBSOR_EXTRA", "1") != "0":
-            # inside the V-cycle the finest-level pre-smoothing launch also carries the residual work of the cycle:
-            # residual + full-weighting restriction (34 B/cell) and the residual norms of its input = the convergence
-            # test of the previous cycle (40 B/cell) on top of 3 sweeps (120 B/cell); the post-smoothing launch is plain
-            # (120 B/cell): (194 + 120) / 2 = 157 B/cell per launch on average (SURVEY 8d figures)
+            # inside the V-cycle the finest-level pre-smoothing launch also carries the residual + full-weighting
+            # restriction (34 B/cell) and the post-smoothing launch the residual norms of the convergence test (40 B/cell)
+            # on top of 3 sweeps (120 B/cell) each: (154 + 160) / 2 = 157 B/cell per launch on average (SURVEY 8d figures)
             alg_bytes = 157.0 * n * n
+            tr = [variants.get(k, {}).get("dram_bytes_per_launch") for k in ("pre_restrict", "post_norms")]
+            traffic = (tr[0] + tr[1]) / 2.0 if all(tr) else None
         achieved = alg_bytes / (ms_launch * 1e-3) / 1e9
-    roofline = {"kernel": "k_rbsor_tma<3> (finest level: 3 red-black SOR sweeps = 6 colour passes per launch; the pre-smoothing "
-                          "launch also carries the V-cycle's residual + restriction and the convergence-test norms)",
+    roofline = {"kernel": "k_rbsor_stream<3> (finest level: 3 red-black SOR sweeps = 6 colour passes per launch, streaming "
+                          "wavefront form; the pre-smoothing launch also carries the V-cycle's residual + restriction, the "
+                          "post-smoothing launch the convergence-test norms)",
                 "bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                 "frac": achieved / peak, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms_launch,
-                "launches_timed": int(live_launches) if (live_launches > 0 and n_alg == n) else reps,
+                "launches_timed": int(live_launches) if live else reps,
                 "timing": "CUDA events around every finest-level launch of 2 further outer iterations of the same run"
-                          if (live_launches > 0 and n_alg == n) else isolated["how"],
-                "traffic": traffic, "isolated": isolated,
+                          if live else isolated["how"],
+                "traffic": traffic,
+                "dram_frac": (traffic / (ms_launch * 1e-3) / 1e9 / peak) if traffic else None,
+                "traffic_source": prof.get("source"),
+                "note": "frac counts SURVEY 8d's algorithmic bytes (3 temporally blocked sweeps count 3 x 40 B/cell, so it "
+                        "can exceed 1); dram_frac = ncu-measured DRAM bytes / live time / peak is the physical utilisation",
+                "isolated": isolated,
                 "unfused_color_pass": {"ms_per_launch": ms_color, "achieved": 20.0 * n * n / (ms_color * 1e-3) / 1e9}}
 
     n = n_alg
@@ -368,7 +398,7 @@ def main():
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload ------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        ns = args.cpu_sample_n
+        ns = args.cpu_sample_n if args.cpu_sample_n > 0 else 513
         step = cpu_oracle_step_fn(ns, args)
         step()
         t0 = time.perf_counter()
@@ -379,6 +409,20 @@ def main():
         cpu = {"value": ns * ns * k / dt / 1e6, "unit": "MLUPS", "cores": 1, "kind": "port",
                "sample": f"{ns}x{ns} grid of the same workload, {k} outer iterations after 1 warm-up, NumPy oracle port "
                          f"(single threaded; host has {os.cpu_count()} cores)"}
+        if n >= 4097 and not args.no_cpu_kernels:
+            # the port's pressure kernels at the config's own size (one application each, single thread)
+            nk = 4097
+            rk = np.random.default_rng(1)
+            dxk = 1.0 / (nk - 1)
+            duk = (0.7 * dxk / 4e-3) * (1 + 0.1 * rk.random((nk + 1, nk)))
+            dvk = (0.7 * dxk / 4e-3) * (1 + 0.1 * rk.random((nk, nk + 1)))
+            usk = 1e-2 * rk.standard_normal((nk + 1, nk)); usk[0, :] = usk[nk, :] = 0.0
+            vsk = 1e-2 * rk.standard_normal((nk, nk + 1)); vsk[:, 0] = vsk[:, nk] = 0.0
+            kt = cpu_baseline_pressure_kernels(nk, dxk, dxk, duk, dvk, usk, vsk, with_mg=True, with_lex=False)
+            cpu["kernels_4097"] = {key: round(val, 1) for key, val in kt.items()}
+            cpu["kernels_4097"]["note"] = ("oracle port, one call each on a seeded 4097^2 system: A*p, one Jacobi iteration, "
+                                           "one red-black SOR sweep, one V(3,3) cycle; milliseconds, single thread")
+            del duk, dvk, usk, vsk
 
     pressure = None
     if phases["iterations"] > 0:
@@ -401,12 +445,11 @@ def main():
             "metric": "simple_outer_mlups", "value": mlups, "unit": "MLUPS", "iter_per_s": args.steps / (ms * 1e-3),
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": dict(workload_config(args, n),
-                           parallelism="single GPU" if world == 1 else
-                           f"{world} row slabs, one rank per GPU; halos (8 rows) and norm reductions by "
-                           + ("the ranks' own kernels over NVLink peer memory (nf_p2p.cu)" if alg.uses_p2p() else
-                              "NCCL send/recv + allreduce")
-                           + ", coarse multigrid levels replicated"),
+            "config": workload_config(args, n, world),
+            "transport": None if world == 1 else
+                         ("halos (8 rows) and norm reductions by the ranks' own kernels over NVLink peer memory (nf_p2p.cu)"
+                          if alg.uses_p2p() else "halos and norm reductions by NCCL send/recv + allreduce")
+                         + ", coarse multigrid levels replicated",
             "gpu_launches": int(launches), "mg_cycles_per_step": float(np.mean(cycles)) if cycles else None,
             "final_u_rel_norm": recs[-1]["u_rel_norm"] if recs else None,
             "clocks": clocks, "roofline": roofline, "pressure_solve": pressure, "e2e": e2e, "cpu_baseline": cpu,

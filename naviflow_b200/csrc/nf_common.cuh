@@ -210,6 +210,8 @@ struct nf_smooth_extra {
   int mode = 0;
   nf_grid gc;
   double* coarse_b = nullptr;
+  double* coarse_x_zero = nullptr;  // mode 2, optional: coarse iterate to be zeroed cell by cell along with the restriction
+                                    // (the cycle recurses from a zero guess: saves the fill launch on unsplit levels)
   double* out = nullptr;
   bool fused = false;
   double* in_norm_out = nullptr;

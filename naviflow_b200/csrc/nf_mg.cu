@@ -31,7 +31,7 @@
                                 // +1 / +2 when the residual norms / the restriction ride on it
 
 int nfi_residual_restrict_fw(nf_ctx*, const nf_grid* gf, const double* p, const double* b, const double* d_u,
-                             const double* d_v, const nf_grid* gc, double* c);
+                             const double* d_v, const nf_grid* gc, double* c, double* x0);
 int nfi_inv_diag(nf_ctx*, const nf_grid*, const double* d_u, const double* d_v, double* inv);
 int nfi_gs_lex(nf_ctx*, const nf_grid*, double* p, const double* b, const double* d_u, const double* d_v, double omega,
                int n_sweeps, int symmetric);
@@ -704,25 +704,32 @@ static int mg_tail(nf_mg* mg) {
 // part: 0 = the whole cycle; 1 = head only (pre-smoothing, residual, restriction, coarse x = 0, RHS published);
 //       2 = the rest (coarse levels, prolongation, post-smoothing).  in_norm (head of level 0): ask the pre-smoothing
 //       launch for the residual norms of its INPUT iterate (-> mg->scal[k][0..1]); *in_norm_fused reports whether it did.
+// from_zero: the level's iterate is known to be zero on entry (the recursion of a cycle; not the cycles FMG runs on a
+// prolonged iterate) -- the precondition of the single-kernel coarse end
 static int mg_cycle(nf_mg* mg, int l, int kind, bool want_norm = false, bool* norm_fused = nullptr, int part = 0,
-                    bool in_norm = false, bool* in_norm_fused = nullptr) {
+                    bool in_norm = false, bool* in_norm_fused = nullptr, bool from_zero = false) {
   nf_ctx* ctx = mg->ctx;
   nf_team* team = mg->team;
   MgLevel& L = mg->lv[l];
   const int nl = nlocal(mg);
   if (norm_fused) *norm_fused = false;
   if (in_norm_fused) *in_norm_fused = false;
-  if (l == mg->tail_level && kind == 0 && part == 0 && !want_norm && !in_norm) return mg_tail(mg);
+  if (l == mg->tail_level && kind == 0 && part == 0 && !want_norm && !in_norm && from_zero) return mg_tail(mg);
   if (L.geom.nx <= mg->cfg.coarsest || l + 1 == (int)mg->lv.size()) return part == 1 ? NF_OK : mg_coarse_solve(mg, l);
   MgLevel& C = mg->lv[l + 1];
   if (part != 2) {
     std::vector<nf_smooth_extra> pre(nl);
     const bool want_pre = mg->cfg.smoother == 0 && mg->cfg.restriction == 0;
+    // The coarse level starts from a zero guess (multigrid.py:374).  On an unsplit level the kernel that writes the restricted
+    // right-hand side zeroes the coarse iterate cell by cell as well; on slabs the whole array (halo rows included) is filled.
+    const bool tail_next = (l + 1 == mg->tail_level && kind == 0);  // the tail kernel starts from zero by itself
+    const bool zero_by_restriction = !tail_next && !L.geom.dist && mg->cfg.restriction == 0;
     if (want_pre)
       for (int k = 0; k < nl; ++k) {
         pre[k].mode = 2;
         pre[k].gc = restrict_target(C, team->local[k]);
         pre[k].coarse_b = C.s[k].b;
+        if (zero_by_restriction) pre[k].coarse_x_zero = C.s[k].x;
         if (in_norm) pre[k].in_norm_out = mg->scal[k];
       }
     NF_TRY(mg_smooth(mg, l, mg->cfg.pre, want_pre ? pre.data() : nullptr));
@@ -737,19 +744,20 @@ static int mg_cycle(nf_mg* mg, int l, int kind, bool want_norm = false, bool* no
       if (pre[k].fused) {
         // coarse right-hand side already written by the smoother
       } else if (mg->cfg.restriction == 0) {
-        NF_TRY(nfi_residual_restrict_fw(ctx, &gf, L.s[k].x, L.s[k].b, L.s[k].d_u, L.s[k].d_v, &gc, C.s[k].b));
+        NF_TRY(nfi_residual_restrict_fw(ctx, &gf, L.s[k].x, L.s[k].b, L.s[k].d_u, L.s[k].d_v, &gc, C.s[k].b,
+                                        zero_by_restriction ? C.s[k].x : nullptr));
       } else {
         NF_TRY(nfi_residual(ctx, &gf, L.s[k].x, L.s[k].b, L.s[k].d_u, L.s[k].d_v, L.s[k].r));
         NF_TRY(nfi_restrict_inject(ctx, &gf, L.s[k].r, &gc, C.s[k].b));
       }
-      if (!(l + 1 == mg->tail_level && kind == 0))  // the tail kernel starts from zero by itself
-        NF_TRY(nfi_fill(ctx, C.s[k].x, C.geom.elems(r), 0.0));
+      if (!tail_next && !zero_by_restriction) NF_TRY(nfi_fill(ctx, C.s[k].x, C.geom.elems(r), 0.0));
     }
     NF_TRY(mg_publish_rhs(mg, l));
     if (part == 1) return NF_OK;
   }
   const int reps = (kind == 1) ? 2 : 1;
-  for (int rep = 0; rep < reps; ++rep) NF_TRY(mg_cycle(mg, l + 1, kind));
+  for (int rep = 0; rep < reps; ++rep)
+    NF_TRY(mg_cycle(mg, l + 1, kind, false, nullptr, 0, false, nullptr, /*from_zero=*/rep == 0));
   NF_TRY(mg_prolong(mg, l, mg->cfg.interpolation, 1));
   std::vector<nf_smooth_extra> post(nl);
   const bool want_post = want_norm && mg->cfg.smoother == 0;

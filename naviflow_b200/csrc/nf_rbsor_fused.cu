@@ -323,6 +323,7 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
 struct TmaExtra {
   nf_grid gc;               // coarse grid (mode 2)
   double* coarse_b;         // mode 2
+  double* coarse_x0;        // mode 2, optional: coarse iterate, zeroed along with the restriction
   double* partials;         // mode 1 (and mode 2 with in_norm): per-CTA partial sums, ticket, result (2 doubles)
   unsigned int* ticket;
   double* out;
@@ -594,6 +595,7 @@ k_rbsor_tma(nf_grid g, const __grid_constant__ CUtensorMap map_p, const __grid_c
           const double cc = sR[a + 1][q + 1], n = sR[a + 1][q + 2], s = sR[a + 1][q], e = sR[a + 2][q + 1], w = sR[a][q + 1];
           const double ne = sR[a + 2][q + 2], nw = sR[a][q + 2], se = sR[a + 2][q], sw = sR[a][q];
           ex.coarse_b[nf_idx(ex.gc, I, J)] = (cc / 4.0 + (((n + s) + e) + w) / 8.0) + (((ne + nw) + se) + sw) / 16.0;
+          if (ex.coarse_x0) ex.coarse_x0[nf_idx(ex.gc, I, J)] = 0.0;
         }
         // the next tile's load phase writes sP / sD only; sR is rewritten after its passes (barriers in between)
       }
@@ -715,7 +717,7 @@ int nfi_rbsor_fused_x(nf_ctx* ctx, const nf_grid* g, double** p, double** palt, 
     int st = NF_OK;
     bool used = false;
     TmaExtra ex;
-    ex.coarse_b = nullptr; ex.partials = ctx->partials; ex.ticket = ctx->ticket; ex.out = nullptr;
+    ex.coarse_b = nullptr; ex.coarse_x0 = nullptr; ex.partials = ctx->partials; ex.ticket = ctx->ticket; ex.out = nullptr;
     ex.in_norm = 0;
     ex.gc = *g;
     int mode = 0;
@@ -725,6 +727,7 @@ int nfi_rbsor_fused_x(nf_ctx* ctx, const nf_grid* g, double** p, double** palt, 
       mode = extra->mode;
       ex.gc = extra->gc;
       ex.coarse_b = extra->coarse_b;
+      ex.coarse_x0 = extra->coarse_x_zero;
       ex.out = extra->out;
       if (mode == 2 && extra->in_norm_out && left == n_sweeps) {  // the launch that sees the call's input iterate
         ex.in_norm = 1;

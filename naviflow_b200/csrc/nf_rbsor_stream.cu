@@ -168,6 +168,7 @@ __device__ __forceinline__ void stream_update(Win& W, const nf_grid& g, int r, d
 struct StreamExtra {
   nf_grid gc;          // EXTRA 2: coarse grid and its right-hand side
   double* coarse_b;
+  double* coarse_x0;   // EXTRA 2, optional: coarse iterate, zeroed along with the restriction
   double* partials;    // EXTRA 1: per-job partial sums, ticket, result (sum r^2, sum b^2)
   unsigned int* ticket;
   double* out;
@@ -285,6 +286,7 @@ __device__ __forceinline__ void stream_step2(Win& W, const nf_grid& g, const Job
       if (s - 7 >= jb.ia && s - 7 < jb.ib && I >= ex.gc.gb && I < ex.gc.ge && colA && J < ex.gc.ny) {
         const double cc = r7B, n = n7, sd = r7A, e = r6B, w = acc[1], ne = n6, nw = n8, se = r6A, sw = acc[0];
         ex.coarse_b[nf_idx(ex.gc, I, J)] = (cc / 4.0 + (((n + sd) + e) + w) / 8.0) + (((ne + nw) + se) + sw) / 16.0;
+        if (ex.coarse_x0) ex.coarse_x0[nf_idx(ex.gc, I, J)] = 0.0;
       }
       acc[0] = r6A;
       acc[1] = r6B;
@@ -606,10 +608,11 @@ int nfi_rbsor_stream(nf_ctx* ctx, const nf_grid* g, const double* pin, double* p
   *used = false;
   if (!inv) return NF_OK;
   StreamExtra ex;
-  ex.gc = *g; ex.coarse_b = nullptr; ex.partials = ctx->partials; ex.ticket = ctx->ticket; ex.out = nullptr;
+  ex.gc = *g; ex.coarse_b = nullptr; ex.coarse_x0 = nullptr; ex.partials = ctx->partials; ex.ticket = ctx->ticket;
+  ex.out = nullptr;
   if (mode != 0) {
     if (ns != 3 || !extra) return NF_OK;
-    ex.gc = extra->gc; ex.coarse_b = extra->coarse_b; ex.out = extra->out;
+    ex.gc = extra->gc; ex.coarse_b = extra->coarse_b; ex.coarse_x0 = extra->coarse_x_zero; ex.out = extra->out;
     if (mode == 1) return launch_stream<3, 8, 1>(ctx, g, pin, pout, b, d_u, d_v, inv, omega, ex, used);
     if (mode == 2) return launch_stream<3, 8, 2>(ctx, g, pin, pout, b, d_u, d_v, inv, omega, ex, used);
     return NF_OK;

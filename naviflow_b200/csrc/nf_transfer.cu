@@ -38,7 +38,7 @@ constexpr int RR_CR = 8, RR_CC = 64;
 __global__ void __launch_bounds__(256)
 k_residual_restrict_fw(nf_grid gf, const double* __restrict__ p, const double* __restrict__ b,
                        const double* __restrict__ d_u, const double* __restrict__ d_v, nf_grid gc,
-                       double* __restrict__ c) {
+                       double* __restrict__ c, double* __restrict__ x0) {
   __shared__ double sR[2 * RR_CR + 1][2 * RR_CC + 2];
   const int tx = threadIdx.x, ty = threadIdx.y;  // 128 x 2
   const int I0 = gc.gb + blockIdx.y * RR_CR, J0 = blockIdx.x * RR_CC;
@@ -64,6 +64,7 @@ k_residual_restrict_fw(nf_grid gf, const double* __restrict__ p, const double* _
     const double cc = sR[a + 1][q + 1], n = sR[a + 1][q + 2], s = sR[a + 1][q], e = sR[a + 2][q + 1], w = sR[a][q + 1];
     const double ne = sR[a + 2][q + 2], nw = sR[a][q + 2], se = sR[a + 2][q], sw = sR[a][q];
     c[nf_idx(gc, I, J)] = (cc / 4.0 + (((n + s) + e) + w) / 8.0) + (((ne + nw) + se) + sw) / 16.0;
+    if (x0) x0[nf_idx(gc, I, J)] = 0.0;  // the coarse iterate starts from zero (saves the fill launch)
   }
 }
 
@@ -222,9 +223,9 @@ int nfi_restrict_fw(nf_ctx* ctx, const nf_grid* gf, const double* f, const nf_gr
 }
 
 int nfi_residual_restrict_fw(nf_ctx* ctx, const nf_grid* gf, const double* p, const double* b, const double* d_u,
-                             const double* d_v, const nf_grid* gc, double* c) {
+                             const double* d_v, const nf_grid* gc, double* c, double* x0) {
   dim3 grid((gc->ny + RR_CC - 1) / RR_CC, (gc->ge - gc->gb + RR_CR - 1) / RR_CR, 1);
-  k_residual_restrict_fw<<<grid, dim3(128, 2, 1), 0, ctx->stream>>>(*gf, p, b, d_u, d_v, *gc, c);
+  k_residual_restrict_fw<<<grid, dim3(128, 2, 1), 0, ctx->stream>>>(*gf, p, b, d_u, d_v, *gc, c, x0);
   NF_LAUNCH_CHECK(ctx);
   return NF_OK;
 }

@@ -93,17 +93,77 @@ class GpuSimpleSolver:
         self.initialize_fields()
 
     # ---- BaseAlgorithm interface ------------------------------------------------------------------
+    _PIN_WHOLE_LIMIT = 1 << 30   # bytes: larger host fields are not page-locked as a whole (see _pin_local_rows)
+
     @staticmethod
     def _host_zeros(shape):
-        """Host field; page-locked when a CUDA device is present so that solve()'s H2D/D2H run at PCIe speed."""
+        """Host field; page-locked when a CUDA device is present so that solve()'s H2D/D2H run at PCIe speed.  Fields
+        above 1 GiB are allocated pageable here and only the rows this process transfers are registered later
+        (_pin_local_rows): on N ranks every rank moves 1/N of the rows."""
         try:
             import torch
-            if torch.cuda.is_available() and int(np.prod(shape)) * 8 <= (1 << 30):
+            if torch.cuda.is_available() and int(np.prod(shape)) * 8 <= GpuSimpleSolver._PIN_WHOLE_LIMIT:
                 t = torch.zeros(shape, dtype=torch.float64).pin_memory()
                 return t.numpy()  # the array keeps the pinned tensor alive through its base
         except Exception:
             pass
         return np.zeros(shape)
+
+    def _pin_local_rows(self):
+        """cudaHostRegister of the rows [row0, row1) of u, v, p that nf_simple_upload / nf_simple_download touch for this
+        process's slab (whole arrays on a single rank), for host fields that are not page-locked yet.  Registered
+        ranges are remembered per array and released in _free()."""
+        if self._state is None:
+            return
+        try:
+            import torch
+            rt = torch.cuda.cudart()
+        except Exception:
+            return
+        if not hasattr(self, "_registered"):
+            self._registered = {}
+        b, e = self.local_rows()
+        halo = 8
+        for name in ("u", "v", "p"):
+            arr = getattr(self, name)
+            if arr.nbytes <= self._PIN_WHOLE_LIMIT and getattr(arr, "base", None) is not None:
+                continue  # page-locked as a whole by _host_zeros (a view of the pinned tensor)
+            if not (arr.flags.c_contiguous and arr.dtype == np.float64):
+                continue
+            lo = max(b - halo, 0)
+            hi = min(e + halo + 1, arr.shape[0])
+            row_bytes = arr.strides[0]
+            start = arr.ctypes.data + lo * row_bytes
+            end = arr.ctypes.data + hi * row_bytes
+            start_al = start & ~4095
+            end_al = (end + 4095) & ~4095
+            key = (arr.ctypes.data, arr.nbytes)
+            if self._registered.get(name, (None,))[0] == key:
+                continue
+            self._unregister(name)
+            try:
+                err = rt.cudaHostRegister(start_al, end_al - start_al, 0)
+                if int(err) == 0:
+                    self._registered[name] = (key, start_al)
+            except Exception:
+                pass
+
+    def _unregister(self, name=None):
+        reg = getattr(self, "_registered", None)
+        if not reg:
+            return
+        try:
+            import torch
+            rt = torch.cuda.cudart()
+        except Exception:
+            return
+        for nm in ([name] if name else list(reg)):
+            ent = reg.pop(nm, None)
+            if ent:
+                try:
+                    rt.cudaHostUnregister(ent[1])
+                except Exception:
+                    pass
 
     def initialize_fields(self):
         nx, ny = self.mesh.get_dimensions()
@@ -230,7 +290,13 @@ class GpuSimpleSolver:
             self._state, self._state_key = h, key
         return ctx, self._state
 
+    def close(self):
+        """Releases the device state.  COLLECTIVE on a distributed solver (the peer-memory arena is torn down by all
+        ranks together, nf_team_free): every rank must call it (or drop the solver) at the same point."""
+        self._free()
+
     def _free(self):
+        self._unregister()
         if self._state is not None:
             lib = get_context(self._device).lib
             lib.nf_simple_destroy(self._state)
@@ -308,6 +374,7 @@ class GpuSimpleSolver:
 
     def push_fields(self):
         ctx, st = self._ensure_state()
+        self._pin_local_rows()
         for name in ("u", "v", "p"):
             self._upload(ctx, st, name, getattr(self, name))
 
