@@ -379,11 +379,11 @@ def main():
     e2e = None
     if not args.no_e2e:
         ksteps = max(1, min(args.steps, 5))
-        alg.solve(max_iterations=1, tolerance=0.0, gather=False)  # warm the path (pinned buffers, first-touch)
+        alg.solve(max_iterations=1, tolerance=0.0, save_profile=False, gather=False)  # warm the path (pinned buffers, first-touch)
         barrier()
         t0 = time.perf_counter()
         for _ in range(ksteps):
-            alg.solve(max_iterations=1, tolerance=0.0, gather=False)
+            alg.solve(max_iterations=1, tolerance=0.0, save_profile=False, gather=False)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt], dtype=torch.float64, device=f"cuda:{local}")

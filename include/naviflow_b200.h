@@ -239,14 +239,19 @@ typedef struct nf_simple_config {
   int32_t nx, ny;
   int32_t n_momentum_sweeps;    /* JacobiMatrixMomentumSolver(n_jacobi_sweeps)                          */
   int32_t pressure_solver;      /* 0 multigrid, 1 Jacobi, 2 red-black SOR, 3 CG, 4 BiCGSTAB,
-                                   5 lexicographic SOR, 6 symmetric SOR (5, 6: single slab)              */
+                                   5 lexicographic SOR, 6 symmetric SOR, 7 BiCGSTAB with the multigrid
+                                   preconditioner (5, 6, 7: single slab)                                 */
   int32_t pressure_iterations;  /* fixed iteration count of the Jacobi / SOR pressure solvers          */
   int32_t sides;                /* boundaries with a registered condition: 1 left 2 right 4 bottom 8 top */
   int32_t krylov_maxiter;
   int32_t piso_corrections;     /* 0: SIMPLE (simple.py:114-212); n >= 1: PISO with n pressure corrections per outer
                                    iteration, momentum re-solved without relaxation in between (piso.py:73-104);
                                    -1: SIMPLER as coded in simpler.py:99-167 (p += p-bar unrelaxed, momentum again,
-                                   p += alpha_p p', velocity correction; p_rel_norm = ||p - p_old|| / sqrt(nx ny))   */
+                                   p += alpha_p p', velocity correction; p_rel_norm = ||p - p_old|| / sqrt(nx ny));
+                                   -2: SIMPLEC as coded in simplec.py:99-171 (d / simplec_divisor, 5-point smoothing of
+                                   p', p += alpha_p p' without edge copies; the record holds infinity norms: u_rel_norm =
+                                   v_rel_norm = max|u - u_old|, |v - v_old|; u_abs_res = max|u* - u|, |v* - v|;
+                                   p_rel_norm = max|p - p_old|; single slab)                                        */
   double length, height, rho, mu;
   double alpha_p, alpha_u;      /* simple.py:23-76                                                      */
   double pressure_omega;        /* Jacobi / SOR relaxation                                              */
@@ -258,6 +263,14 @@ typedef struct nf_simple_config {
   int32_t momentum_maxiter;     /* a7: max_iterations (matrix_free_momentum.py:17)                                     */
   double momentum_tolerance;    /* a7: atol of the Krylov solve (:16); stop at max(atol, 1e-5 ||b||)                   */
   nf_bc_program bc_mf;          /* a7: BC program as that class applies it (caller's nx+1: :419, :491)                 */
+  double simplec_divisor;       /* SIMPLEC (piso_corrections == -2): d_u, d_v are divided by 1 - (1 - alpha_u), evaluated by
+                                   the caller exactly as simplec.py:126-127 does                                       */
+  int32_t krylov_check_every;   /* CG / BiCGSTAB pressure solves: the host polls the device-side stopping flag every n
+                                   iterations (0: 25 for CG, 10 for BiCGSTAB); the answer does not depend on it        */
+  int32_t krylov_mg_cycles;     /* pressure_solver 7: multigrid cycles per preconditioner application                  */
+  int32_t krylov_mg_kind;       /* pressure_solver 7: 0 'v', 1 'w', 2 'fmg' (matrix_free_BiCGSTAB.py:102-161); the
+                                   preconditioner's hierarchy is described by `mg`                                     */
+  int32_t pad2;
 } nf_simple_config;
 
 typedef struct nf_simple_info {   /* one record per outer iteration */

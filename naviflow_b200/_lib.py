@@ -63,7 +63,9 @@ class NfSimpleConfig(C.Structure):
                 ("pressure_tolerance", C.c_double),
                 ("bc", NfBcProgram), ("mg", NfMgConfig),
                 ("momentum_solver", C.c_int32), ("momentum_maxiter", C.c_int32), ("momentum_tolerance", C.c_double),
-                ("bc_mf", NfBcProgram)]
+                ("bc_mf", NfBcProgram),
+                ("simplec_divisor", C.c_double), ("krylov_check_every", C.c_int32), ("krylov_mg_cycles", C.c_int32),
+                ("krylov_mg_kind", C.c_int32), ("pad2", C.c_int32)]
 
 
 class NfSimpleInfo(C.Structure):

@@ -58,7 +58,9 @@ struct SimpleSlab {
   double* tmp = nullptr;    // Jacobi pressure ping-pong
   double* kwork = nullptr;  // Krylov work arrays
   double *ap_un = nullptr, *src_un = nullptr, *mwork = nullptr;  // Krylov momentum predictor (a7)
-  double* p_old = nullptr;  // SIMPLER: p at the start of the iteration (p_rel_norm)
+  double* p_old = nullptr;  // SIMPLER / SIMPLEC: p at the start of the iteration (p_rel_norm)
+  double *u_old = nullptr, *v_old = nullptr;  // SIMPLEC: velocities at the start of the iteration (total residual)
+  double* cscal = nullptr;  // SIMPLEC: 8 device doubles, infinity norms [0] |u*-u| [1] |v*-v| [2] |p-p_old| [3] |u-u_old| [4] |v-v_old|
   double* kstate = nullptr; // slab-decomposed Krylov: this slab's copy of the scalar state + reduction scratch (64 doubles)
   double* scal = nullptr;   // 8 device doubles: [0..1] pressure norms, [2..5] momentum sums
   nf_links links;
@@ -129,7 +131,11 @@ int nfi_simple_create(nf_team* team, nf_simple** out, const nf_simple_config* cf
   NF_REQUIRE(ctx, out && cfg, "NULL argument");
   *out = nullptr;
   NF_REQUIRE(ctx, cfg->nx >= 3 && cfg->ny >= 3, "nx, ny must be >= 3");
-  NF_REQUIRE(ctx, cfg->pressure_solver >= 0 && cfg->pressure_solver <= 6, "unknown pressure solver");
+  NF_REQUIRE(ctx, cfg->pressure_solver >= 0 && cfg->pressure_solver <= 7, "unknown pressure solver");
+  NF_REQUIRE(ctx, cfg->piso_corrections >= -2, "unknown algorithm (piso_corrections < -2)");
+  NF_REQUIRE(ctx, cfg->piso_corrections != -2 || cfg->simplec_divisor != 0.0, "SIMPLEC needs simplec_divisor");
+  NF_REQUIRE(ctx, cfg->pressure_solver != 7 || (cfg->krylov_mg_cycles >= 1 && cfg->krylov_mg_kind >= 0 &&
+                                                cfg->krylov_mg_kind <= 2), "bad multigrid preconditioner arguments");
   NF_REQUIRE(ctx, cfg->alpha_u > 0.0, "alpha_u must be > 0");
   NF_REQUIRE(ctx, cfg->n_momentum_sweeps >= 0, "n_momentum_sweeps < 0");
   NF_REQUIRE(ctx, cfg->momentum_solver == 0 || cfg->momentum_solver == 1, "unknown momentum solver");
@@ -140,7 +146,12 @@ int nfi_simple_create(nf_team* team, nf_simple** out, const nf_simple_config* cf
   s->cfg = *cfg;
   s->geom = nf_level0_geom(team, cfg->nx, cfg->ny, nf_pad_ld(cfg->ny), cfg->length, cfg->height, cfg->rho);
   if (s->geom.dist && cfg->pressure_solver >= 5) {
-    ctx->err = "the sequential Gauss-Seidel sweeps run on a single slab only";
+    ctx->err = "the sequential Gauss-Seidel sweeps and the multigrid-preconditioned BiCGSTAB run on a single slab only";
+    delete s;
+    return NF_ERR_UNSUPPORTED;
+  }
+  if ((s->geom.dist || team->local.size() != 1) && cfg->piso_corrections == -2) {
+    ctx->err = "the SIMPLEC loop runs on a single slab only";
     delete s;
     return NF_ERR_UNSUPPORTED;
   }
@@ -168,15 +179,22 @@ int nfi_simple_create(nf_team* team, nf_simple** out, const nf_simple_config* cf
       if (!*f) { ok = false; break; }
     }
     if (ok) { S.scal = alloc_elems(s, S, 8, 8); ok = S.scal != nullptr; }
-    if (ok && cfg->piso_corrections == -1) { S.p_old = alloc_elems(s, S, e, emax); ok = S.p_old != nullptr; }
+    if (ok && cfg->piso_corrections <= -1) { S.p_old = alloc_elems(s, S, e, emax); ok = S.p_old != nullptr; }
+    if (ok && cfg->piso_corrections == -2) {
+      S.u_old = alloc_elems(s, S, e, emax);
+      S.v_old = alloc_elems(s, S, e, emax);
+      S.cscal = alloc_elems(s, S, 8, 8);
+      ok = S.u_old && S.v_old && S.cscal;
+    }
     if (ok && cfg->momentum_solver == 1) {
       S.ap_un = alloc_elems(s, S, e, emax);
       S.src_un = alloc_elems(s, S, e, emax);
       S.mwork = alloc_elems(s, S, e * 5, emax * 5);
       ok = S.ap_un && S.src_un && S.mwork;
     }
-    if (ok && (cfg->pressure_solver == 3 || cfg->pressure_solver == 4)) {
-      S.kwork = alloc_elems(s, S, e * (cfg->pressure_solver == 3 ? 4 : 5), emax * (cfg->pressure_solver == 3 ? 4 : 5));
+    if (ok && (cfg->pressure_solver == 3 || cfg->pressure_solver == 4 || cfg->pressure_solver == 7)) {
+      const size_t nw = cfg->pressure_solver == 3 ? 4 : (cfg->pressure_solver == 4 ? 5 : 7);
+      S.kwork = alloc_elems(s, S, e * nw, emax * nw);
       ok = S.kwork != nullptr;
       if (ok) { S.kstate = alloc_elems(s, S, 64, 64); ok = S.kstate != nullptr; }
     }
@@ -188,7 +206,7 @@ int nfi_simple_create(nf_team* team, nf_simple** out, const nf_simple_config* cf
     nf_simple_destroy(s);
     return NF_ERR_ALLOC;
   }
-  if (cfg->pressure_solver == 0) {
+  if (cfg->pressure_solver == 0 || cfg->pressure_solver == 7) {  // the solver itself / BiCGSTAB's preconditioner
     nf_mg_config mc = cfg->mg;
     mc.length = cfg->length; mc.height = cfg->height; mc.rho = 1.0;  // callers hard-code rho = 1 (multigrid.py:151)
     int st = nfi_mg_create(team, &s->mg, s->geom.nx, s->geom.ny, s->geom.ld, &mc);
@@ -333,6 +351,70 @@ __global__ void k_diff_sumsq(nf_grid g, const double* __restrict__ a, const doub
   nf_block_reduce_store<1>(acc, partials, ticket, out);
 }
 
+// ---- SIMPLEC helpers (Algorithms/simplec.py) ----
+// d <- d / c over `rows` x `cols` (:126-127; NaN entries of the array borders stay NaN)
+__global__ void k_scale_div(int rows, int cols, int ld, double* __restrict__ d, double c) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i < rows && j < cols) d[(size_t)i * ld + j] = d[(size_t)i * ld + j] / c;
+}
+
+// *out = max(*out, max |a - b|) over rows x cols (np.max(np.abs(a - b)), :119-122, :157, :169-171).  |x| >= 0, so the
+// ordering of the bit patterns is the ordering of the values: one atomicMax per block, order independent.
+__global__ void k_maxabs_diff(int rows, int cols, int ld, const double* __restrict__ a, const double* __restrict__ b,
+                              double* out) {
+  double m = 0.0;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < cols)
+    for (int i = blockIdx.y * blockDim.y + threadIdx.y; i < rows; i += gridDim.y * blockDim.y)
+      m = fmax(m, fabs(a[(size_t)i * ld + j] - b[(size_t)i * ld + j]));
+  for (int off = 16; off > 0; off >>= 1) m = fmax(m, __shfl_down_sync(0xffffffffu, m, off));
+  if (((threadIdx.y * blockDim.x + threadIdx.x) & 31) == 0)
+    atomicMax(reinterpret_cast<unsigned long long*>(out), (unsigned long long)__double_as_longlong(m));
+}
+
+// p'_smooth: 0.6 p' + 0.1 (((E + W) + N) + S) in the interior, 0 on the boundary ring (:141-147)
+__global__ void k_smooth_pprime(nf_grid g, const double* __restrict__ pp, double* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = g.gb + blockIdx.y * blockDim.y + threadIdx.y;
+  if (j >= g.ny || i >= g.ge) return;
+  const size_t k = nf_idx(g, i, j);
+  double v = 0.0;
+  if (i >= 1 && i <= g.nx - 2 && j >= 1 && j <= g.ny - 2)
+    v = 0.6 * pp[k] + 0.1 * (((pp[k + g.ld] + pp[k - g.ld]) + pp[k + 1]) + pp[k - 1]);
+  out[k] = v;
+}
+
+// p = p* + alpha p' without the zero-gradient edge copies (:154)
+__global__ void k_axpy_pressure(nf_grid g, const double* __restrict__ ps, const double* __restrict__ pp, double alpha,
+                                double* __restrict__ p) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = g.gb + blockIdx.y * blockDim.y + threadIdx.y;
+  if (j >= g.ny || i >= g.ge) return;
+  const size_t k = nf_idx(g, i, j);
+  p[k] = ps[k] + alpha * pp[k];
+}
+
+// SIMPLEC record: [0] max|p - p_old|, [1] momentum residual, [6] pressure iterations, [7] total residual
+__global__ void k_store_hist_simplec(const double* __restrict__ cs, double* __restrict__ rec, double iters) {
+  if (threadIdx.x == 0) {
+    rec[0] = cs[2];
+    rec[1] = fmax(cs[0], cs[1]);
+    rec[6] = iters;
+    rec[7] = fmax(cs[3], cs[4]);
+  }
+}
+
+static int maxabs_diff(nf_ctx* ctx, int rows, int cols, int ld, const double* a, const double* b, double* out) {
+  dim3 block(128, 2, 1);
+  int gy = (rows + 1) / 2;
+  if (gy > 296) gy = 296;
+  dim3 grid((cols + 127) / 128, gy < 1 ? 1 : gy, 1);
+  k_maxabs_diff<<<grid, block, 0, ctx->stream>>>(rows, cols, ld, a, b, out);
+  NF_LAUNCH_CHECK(ctx);
+  return NF_OK;
+}
+
 static int ensure_hist(nf_simple* s, int n) {
   nf_ctx* ctx = s->ctx;
   if (n <= s->hist_cap) return NF_OK;
@@ -346,6 +428,14 @@ static int ensure_hist(nf_simple* s, int n) {
 }
 
 static void decode_record(const nf_simple* s, const double* rec, nf_simple_info* out) {
+  if (s->cfg.piso_corrections == -2) {  // SIMPLEC: infinity norms (simplec.py:119-122, :157, :169-171)
+    out->u_rel_norm = out->v_rel_norm = rec[7];
+    out->u_abs_res = out->v_abs_res = rec[1];
+    out->p_rel_norm = rec[0];
+    out->pressure_iterations = (int)rec[6];
+    out->pad = 0;
+    return;
+  }
   out->u_abs_res = sqrt(rec[2]);
   out->v_abs_res = sqrt(rec[4]);
   if (s->cfg.momentum_solver == 1) {  // absolute unrelaxed residual norm (matrix_free_momentum.py:455, :527)
@@ -531,7 +621,9 @@ static int momentum_predictor(nf_simple* s, double alpha, int want_fields, int s
 // iteration's record goes to hist[slot]
 // alpha: relaxation of the pressure update; correct: also correct the velocities; diff_record (SIMPLER): the record's
 // pressure entry is sum (p - p_old)^2 instead of the pressure solver's residual
-static int pressure_correction(nf_simple* s, int slot, double alpha, bool correct = true, bool diff_record = false) {
+// simplec: the update part follows simplec.py:141-171 instead (smoothed p', plain p update, infinity-norm record)
+static int pressure_correction(nf_simple* s, int slot, double alpha, bool correct = true, bool diff_record = false,
+                               bool simplec = false) {
   nf_ctx* ctx = s->ctx;
   nf_team* team = s->team;
   const nf_simple_config& c = s->cfg;
@@ -622,14 +714,22 @@ static int pressure_correction(nf_simple* s, int slot, double alpha, bool correc
     }
     default: {
       nf_krylov_info ki;
+      const int poll = c.krylov_check_every > 0 ? c.krylov_check_every : (c.pressure_solver == 3 ? 25 : 10);
       if (!dist) {
         SimpleSlab& S = s->s[0];
         const nf_grid* g1 = &gp[0];
-        if (c.pressure_solver == 3)
-          NF_TRY(nf_cg_solve(ctx, g1, S.b, S.pp, S.d_u, S.d_v, c.pressure_tolerance, 1e-5, c.krylov_maxiter, 25, S.kwork, &ki));
-        else
-          NF_TRY(nf_bicgstab_solve(ctx, g1, S.b, S.pp, S.d_u, S.d_v, c.pressure_tolerance, 1e-5, c.krylov_maxiter, 10,
+        if (c.pressure_solver == 3) {
+          NF_TRY(nf_cg_solve(ctx, g1, S.b, S.pp, S.d_u, S.d_v, c.pressure_tolerance, 1e-5, c.krylov_maxiter, poll, S.kwork,
+                             &ki));
+        } else if (c.pressure_solver == 7) {  // M = multigrid cycles on the same coefficients (matrix_free_BiCGSTAB.py:102-161)
+          std::vector<double*> du = field_of(s, &SimpleSlab::d_u), dv = field_of(s, &SimpleSlab::d_v);
+          NF_TRY(nfi_mg_setup(s->mg, du.data(), dv.data()));
+          NF_TRY(nf_bicgstab_solve_mg(ctx, g1, S.b, S.pp, S.d_u, S.d_v, c.pressure_tolerance, 1e-5, c.krylov_maxiter, poll,
+                                      S.kwork, s->mg, c.krylov_mg_cycles, c.krylov_mg_kind, &ki));
+        } else {
+          NF_TRY(nf_bicgstab_solve(ctx, g1, S.b, S.pp, S.d_u, S.d_v, c.pressure_tolerance, 1e-5, c.krylov_maxiter, poll,
                                    S.kwork, &ki));
+        }
         // rel_norm = ||r_int|| / ||b_int|| of the true residual (matrix_free_BiCGSTAB.py:255-279)
         NF_TRY(nfi_residual(ctx, g1, S.pp, S.b, S.d_u, S.d_v, S.pres));
         NF_TRY(nfi_sumsq_to(ctx, g1, S.pres, 1, S.scal));
@@ -641,7 +741,7 @@ static int pressure_correction(nf_simple* s, int slot, double alpha, bool correc
         NF_TRY(nf_team_exchange(team, s->geom, du.data(), 1));  // the operator reads d_u[i+1] and the neighbours' rows
         NF_TRY(nf_team_exchange(team, s->geom, dv.data(), 1));
         NF_TRY(nfi_krylov_team(team, s->geom, c.pressure_solver == 3 ? 0 : 1, b.data(), x.data(), du.data(), dv.data(),
-                               c.pressure_tolerance, 1e-5, c.krylov_maxiter, c.pressure_solver == 3 ? 25 : 10, w.data(),
+                               c.pressure_tolerance, 1e-5, c.krylov_maxiter, poll, w.data(),
                                ks.data(), &ki));
         NF_TRY(nf_team_exchange(team, s->geom, x.data(), 1));
         std::vector<double*> sc(nl);
@@ -660,6 +760,27 @@ static int pressure_correction(nf_simple* s, int slot, double alpha, bool correc
     }
   }
   phase_mark(s);  // end of the pressure solve
+  if (simplec) {
+    SimpleSlab& S = s->s[0];
+    const nf_grid g = s->geom.grid(team->local[0]);
+    NfLaunch2D l = nf_launch2d(g.ge - g.gb, g.ny);
+    k_smooth_pprime<<<l.grid, l.block, 0, ctx->stream>>>(g, S.pp, S.tmp);
+    NF_LAUNCH_CHECK(ctx);
+    { double* t = S.pp; S.pp = S.tmp; S.tmp = t; }
+    k_axpy_pressure<<<l.grid, l.block, 0, ctx->stream>>>(g, S.p, S.pp, alpha, S.p_alt);
+    NF_LAUNCH_CHECK(ctx);
+    { double* t = S.p; S.p = S.p_alt; S.p_alt = t; }
+    NF_TRY(maxabs_diff(ctx, g.nx, g.ny, g.ld, S.p, S.p_old, S.cscal + 2));
+    NF_TRY(nfi_correct_velocity(ctx, &g, &c.bc, S.u_star, S.v_star, S.pp, S.d_u, S.d_v, S.u, S.v));
+    NF_TRY(maxabs_diff(ctx, g.nx + 1, g.ny, g.ld, S.u, S.u_old, S.cscal + 3));
+    NF_TRY(maxabs_diff(ctx, g.nx, g.ny + 1, g.ld, S.v, S.v_old, S.cscal + 4));
+    if (slot >= 0) {
+      k_store_hist_simplec<<<1, 32, 0, ctx->stream>>>(S.cscal, s->hist + (size_t)slot * 8, iters);
+      NF_LAUNCH_CHECK(ctx);
+    }
+    s->bc_clean = true;
+    return NF_OK;
+  }
   if (slot >= 0 && !diff_record) {
     k_store_hist_pressure<<<1, 32, 0, ctx->stream>>>(pscal, s->hist + (size_t)slot * 8, pa, pb, iters, p_from_scalars);
     NF_LAUNCH_CHECK(ctx);
@@ -723,6 +844,32 @@ static int simple_step(nf_simple* s, int slot, int want_fields) {
     NF_TRY(momentum_predictor(s, c.alpha_u, 0, -1));
     phase_mark(s);
     NF_TRY(pressure_correction(s, slot, c.alpha_p, true, true));
+    phase_mark(s);
+    if (s->phase_timing) s->phase_iters++;
+    return NF_OK;
+  }
+  if (c.piso_corrections == -2) {
+    // SIMPLEC as the reference codes it (simplec.py:99-171), single slab
+    nf_ctx* ctx = s->ctx;
+    SimpleSlab& S = s->s[0];
+    const nf_grid g = s->geom.grid(s->team->local[0]);
+    const size_t bytes = s->geom.elems(s->team->local[0]) * sizeof(double);
+    NF_CHECK_CUDA(ctx, cudaMemcpyAsync(S.u_old, S.u, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    NF_CHECK_CUDA(ctx, cudaMemcpyAsync(S.v_old, S.v, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    NF_CHECK_CUDA(ctx, cudaMemcpyAsync(S.p_old, S.p, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    NF_CHECK_CUDA(ctx, cudaMemsetAsync(S.cscal, 0, 8 * sizeof(double), ctx->stream));
+    NF_TRY(momentum_predictor(s, c.alpha_u, want_fields, slot));
+    NF_TRY(maxabs_diff(ctx, g.nx + 1, g.ny, g.ld, S.u_star, S.u, S.cscal + 0));
+    NF_TRY(maxabs_diff(ctx, g.nx, g.ny + 1, g.ld, S.v_star, S.v, S.cscal + 1));
+    {
+      dim3 block(128, 2, 1), grid((g.ny + 1 + 127) / 128, (g.nx + 1 + 1) / 2, 1);
+      k_scale_div<<<grid, block, 0, ctx->stream>>>(g.nx + 1, g.ny, g.ld, S.d_u, c.simplec_divisor);
+      NF_LAUNCH_CHECK(ctx);
+      k_scale_div<<<grid, block, 0, ctx->stream>>>(g.nx, g.ny + 1, g.ld, S.d_v, c.simplec_divisor);
+      NF_LAUNCH_CHECK(ctx);
+    }
+    phase_mark(s);
+    NF_TRY(pressure_correction(s, slot, c.alpha_p, true, false, true));
     phase_mark(s);
     if (s->phase_timing) s->phase_iters++;
     return NF_OK;

@@ -164,6 +164,14 @@ class GpuGaussSeidelSolver(_StationaryBase):
         self.omega = omega
         self.method_type = method_type
 
+
+    def solve(self, mesh=None, u_star=None, v_star=None, d_u=None, d_v=None, p_star=None, p=None, b=None,
+              nx=None, ny=None, dx=None, dy=None, rho=1.0, num_iterations=None, track_residuals=True,
+              return_dict=True):
+        """Signature of ``GaussSeidelSolver.solve`` (gauss_seidel.py:55-57): unlike JacobiSolver it returns
+        ``(p, info)`` by default; as a multigrid smoother it is called with ``return_dict=False`` (multigrid.py:352-354)."""
+        return super().solve(mesh, u_star, v_star, d_u, d_v, p_star, p, b, nx, ny, dx, dy, rho, num_iterations,
+                             track_residuals, return_dict)
     def _iterate(self, g, p, b, du, dv, n):
         ctx = self.ctx
         if self.method_type != "red_black":
@@ -263,7 +271,7 @@ class GpuMultiGridSolver(_GpuPressureBase):
         except Exception:
             pass
 
-    def solve(self, mesh, u_star, v_star, d_u, d_v, p_star=None, return_dict=True):
+    def solve(self, mesh, u_star, v_star, d_u, d_v, p_star, return_dict=True):
         nx, ny, dx, dy, length, height = mesh_scalars(mesh)
         ctx = self.ctx
         g, bd, du, dv = self._stage(nx, ny, dx, dy, self.rho, u_star, v_star, d_u, d_v)
@@ -314,7 +322,7 @@ class _KrylovBase(_GpuPressureBase):
                 max_cycles_buildup=mg_max_cycles_buildup, coarsest_grid_size=mg_coarsest_grid_size,
                 restriction_method=mg_restriction_method, interpolation_method=mg_interpolation_method, device=device)
 
-    def solve(self, mesh, u_star, v_star, d_u, d_v, p_star=None, return_dict=True):
+    def solve(self, mesh, u_star, v_star, d_u, d_v, p_star, return_dict=True):
         nx, ny, dx, dy, length, height = mesh_scalars(mesh)
         ctx = self.ctx
         torch = ctx.torch

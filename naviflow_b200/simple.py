@@ -24,6 +24,7 @@ from .host import BoundaryConditionManager, SimulationResult, ghia_errors, pract
 from .momentum import GpuJacobiMomentumSolver, GpuMatrixFreeMomentumSolver
 from .pressure import (GpuBiCGSTABSolver, GpuCGSolver, GpuGaussSeidelSolver, GpuJacobiSolver,
                        GpuMultiGridSolver)
+from .profiler import Profiler
 from .velocity import GpuVelocityUpdater
 
 _FIELD = {"u": 0, "v": 1, "p": 2, "u_star": 3, "v_star": 4, "d_u": 5, "d_v": 6, "p_prime": 7, "b": 8,
@@ -58,6 +59,7 @@ def assemble_rows(arr, begin, end, device=None):
 class GpuSimpleSolver:
     _piso_corrections = 0          # 0: SIMPLE; GpuPisoSolver sets n_corrections
     _history_appends_per_iteration = 2  # the reference appends twice (simple.py:177, :196)
+    _profile_prefix = "SIMPLE"     # file name of the saved run record (simple.py:265)
 
     def __init__(self, mesh, fluid, pressure_solver=None, momentum_solver=None, velocity_updater=None,
                  boundary_conditions=None, alpha_p=0.3, alpha_u=0.7, fix_lid_corners=False, device=None,
@@ -80,7 +82,7 @@ class GpuSimpleSolver:
                     for typ, vals in conds.items():
                         self.bc_manager.set_condition(loc, typ, vals)
         self.boundary_conditions = self.bc_manager.to_dict()
-        self.profiler = None
+        self.profiler = Profiler(self.__class__.__name__, mesh, fluid, algorithm=self)  # base_algorithm.py:60
         self.residual_history = []
         self._device = device
         self._state = None
@@ -215,6 +217,7 @@ class GpuSimpleSolver:
         ps = self.pressure_solver
         c.krylov_maxiter = 0
         c.piso_corrections = int(self._piso_corrections)
+        c.simplec_divisor = 0.0
         c.pressure_iterations = 0
         c.pressure_omega = 1.0
         c.pressure_tolerance = 0.0
@@ -233,6 +236,16 @@ class GpuSimpleSolver:
             c.pressure_solver = 3 if isinstance(ps, GpuCGSolver) else 4
             c.krylov_maxiter = int(ps.max_iterations)
             c.pressure_tolerance = float(ps.tolerance)
+            c.krylov_check_every = int(ps.check_every)
+            if getattr(ps, "mg_precond", None) is not None:
+                # MatrixFreeBiCGSTABSolver(use_preconditioner=True, preconditioner='multigrid'): same recurrence with
+                # M = mg_cycles multigrid cycles (matrix_free_BiCGSTAB.py:102-161); the host polls every iteration
+                from .pressure import _CYCLE
+                c.pressure_solver = 7
+                c.mg = ps.mg_precond.config_struct(length, height)
+                c.krylov_mg_cycles = int(ps.mg_cycles)
+                c.krylov_mg_kind = _CYCLE[ps.mg_cycle_type]
+                c.krylov_check_every = 1
         else:
             raise TypeError("pressure_solver must be one of the naviflow_b200 Gpu*Solver classes")
         c.sides = practice_b_sides(self.bc_manager)
@@ -397,12 +410,18 @@ class GpuSimpleSolver:
         return assemble_rows(arr, b, e, device=f"cuda:{get_context(self._device).device}")
 
     # ---- SimpleSolver.solve -----------------------------------------------------------------------
-    def solve(self, max_iterations=1000, tolerance=1e-6, save_profile=False, profile_dir="results/profiles",
+    def save_profiling_data(self, filename=None, profile_dir="results/profiles"):
+        """base_algorithm.py:200-216"""
+        return self.profiler.save(filename, profile_dir)
+
+    def solve(self, max_iterations=1000, tolerance=1e-6, save_profile=True, profile_dir="results/profiles",
               track_infinity_norm=False, infinity_norm_interval=10, use_l2_norm=False, chunk=None, gather=True):
-        """``gather=False`` (distributed runs): every rank keeps only its own rows in ``self.u/v/p`` instead of
-        assembling the full fields on all ranks at the end."""
-        if save_profile:
-            raise NotImplementedError("HDF5 profile output is out of scope (SURVEY.md section 2, row 12)")
+        """Signature and defaults of ``SimpleSolver.solve`` (simple.py:78-79), including ``save_profile=True``: the run
+        record (naviflow_b200/profiler.py, the reference's HDF5 layout) goes to ``profile_dir``.  Extra keywords:
+        ``chunk`` = outer iterations per device call, ``gather=False`` (distributed runs): every rank keeps only its own
+        rows in ``self.u/v/p`` instead of assembling the full fields on all ranks at the end."""
+        self.profiler.initialize()
+        self.profiler.start()
         t0 = time.perf_counter()
         ctx, st = self._ensure_state()
         nx, ny = self.mesh.get_dimensions()
@@ -411,6 +430,7 @@ class GpuSimpleSolver:
         self.x_momentum_rel_norms, self.y_momentum_rel_norms, self.pressure_rel_norms = [], [], []
         self.infinity_norm_history = []
         self.pressure_iterations_history = []
+        self._u_abs_res_history = []
         iteration = 1
         total = 1.0
         if chunk is None:
@@ -418,13 +438,20 @@ class GpuSimpleSolver:
         try:
             while iteration <= max_iterations and total > tolerance:
                 n = min(chunk, max_iterations - iteration + 1)
+                t_chunk = time.perf_counter() - t0
                 recs = self.iterate_resident(n, tolerance, want_fields=False)
+                if recs:
+                    self.profiler.add_residual_block(
+                        iteration, [max(r["u_rel_norm"], r["v_rel_norm"]) for r in recs],
+                        [max(r["u_rel_norm"], r["v_rel_norm"]) if self._piso_corrections != -2 else r["u_abs_res"]
+                         for r in recs], [r["p_rel_norm"] for r in recs], t_chunk, time.perf_counter() - t0)
                 for r in recs:
                     total = max(r["u_rel_norm"], r["v_rel_norm"])
                     self.x_momentum_rel_norms.append(r["u_rel_norm"])
                     self.y_momentum_rel_norms.append(r["v_rel_norm"])
                     self.pressure_rel_norms.append(r["p_rel_norm"])
                     self.pressure_iterations_history.append(r["pressure_iterations"])
+                    self._u_abs_res_history.append(r["u_abs_res"])
                     self.residual_history.extend([total] * self._history_appends_per_iteration)
                 iteration += len(recs)
                 if track_infinity_norm and (iteration - 1) % infinity_norm_interval == 0:
@@ -437,6 +464,13 @@ class GpuSimpleSolver:
             print("Interrupted by user.")
         self.pull_fields(gather)
         self._p_residual_cache = None  # the residual field stays on the device until somebody asks for it
+        final_residual = total
+        self.profiler.set_iterations(iteration - 1)
+        self.profiler.set_convergence_info(tolerance=tolerance, final_residual=final_residual,
+                                           residual_history=self.residual_history, converged=(final_residual < tolerance))
+        self.profiler.set_pressure_solver_info(  # simple.py:233-240; the device loop counts the inner iterations itself
+            solver_name=type(self.pressure_solver).__name__, inner_iterations=self.pressure_iterations_history)
+        self.profiler.end()
         result = SimulationResult(self.u, self.v, self.p, self.mesh, iterations=iteration - 1,
                                   residuals=self.residual_history, reynolds=self.fluid.get_reynolds_number(),
                                   wall_time=time.perf_counter() - t0)
@@ -446,6 +480,12 @@ class GpuSimpleSolver:
         result.add_history("total_rel_norm", self.residual_history)
         if self.infinity_norm_history:
             result.add_history("infinity_norm_error", self.infinity_norm_history)
+        import os
+        if save_profile and self._world()[1] == 0 and os.environ.get("NAVIFLOW_B200_NO_PROFILE_FILES") != "1":
+            os.makedirs(profile_dir, exist_ok=True)
+            filename = os.path.join(profile_dir, f"{self._profile_prefix}_Re{int(self.fluid.get_reynolds_number())}"
+                                                 f"_mesh{nx}x{ny}_profile.h5")
+            print(f"Saved profile to {self.save_profiling_data(filename)}")
         return result
 
 
@@ -456,16 +496,17 @@ class GpuPisoSolver(GpuSimpleSolver):
     (:92-104).  The recorded norms are the predictor's and the last correction's (:107-109); ``residual_history``
     gets one entry per iteration (:119).  Same device loop as GpuSimpleSolver (``nf_simple_config.piso_corrections``)."""
     _history_appends_per_iteration = 1
+    _profile_prefix = "PISO"
 
     def __init__(self, mesh, fluid, pressure_solver=None, momentum_solver=None, velocity_updater=None,
-                 boundary_conditions=None, alpha_p=0.3, alpha_u=0.7, n_corrections=2, **kw):
+                 boundary_conditions=None, alpha_p=0.3, alpha_u=0.7, fix_lid_corners=False, n_corrections=2, **kw):
         if int(n_corrections) < 1:
             # range(0) in piso.py:73 leaves p_res_info unbound -> UnboundLocalError at :108; refuse up front
             raise ValueError("n_corrections must be >= 1")
         self.n_corrections = int(n_corrections)
         self._piso_corrections = self.n_corrections
         super().__init__(mesh, fluid, pressure_solver, momentum_solver, velocity_updater, boundary_conditions,
-                         alpha_p=alpha_p, alpha_u=alpha_u, **kw)
+                         alpha_p=alpha_p, alpha_u=alpha_u, fix_lid_corners=fix_lid_corners, **kw)
 
 
 class GpuSimplerSolver(GpuSimpleSolver):
@@ -477,8 +518,51 @@ class GpuSimplerSolver(GpuSimpleSolver):
     ``alpha_p`` / ``alpha_u`` are keyword-only like the reference's.  Same device loop (``piso_corrections = -1``)."""
     _history_appends_per_iteration = 1
     _piso_corrections = -1
+    _profile_prefix = "SIMPLER"
 
     def __init__(self, mesh, fluid, pressure_solver=None, momentum_solver=None, velocity_updater=None,
                  boundary_conditions=None, *, alpha_p=0.3, alpha_u=0.7, **kw):
         super().__init__(mesh, fluid, pressure_solver, momentum_solver, velocity_updater, boundary_conditions,
                          alpha_p=alpha_p, alpha_u=alpha_u, **kw)
+
+    def solve(self, *, max_iterations=1000, tolerance=1e-6, save_profile=True, profile_dir="results/profiles",
+              track_infinity_norm=False, infinity_norm_interval=10, use_l2_norm=False, chunk=None, gather=True):
+        """Keyword-only like ``SimplerSolver.solve`` (simpler.py:78-88)."""
+        return super().solve(max_iterations, tolerance, save_profile, profile_dir, track_infinity_norm,
+                             infinity_norm_interval, use_l2_norm, chunk, gather)
+
+
+class GpuSimplecSolver(GpuSimpleSolver):
+    """Twin of ``SimplecSolver(BaseAlgorithm)`` (solver/Algorithms/simplec.py:11-283) AS THE REFERENCE CODES IT: momentum
+    predictor with alpha_u; ``d_u, d_v`` divided by ``1 - (1 - alpha_u)`` (:126-127); pressure correction with the scaled
+    ``d``; 5-point smoothing of ``p'`` with a zero boundary ring (:141-147); ``p = p* + alpha_p p'`` without zero-gradient edge
+    copies (:154); velocity correction with the smoothed ``p'`` (:162-166).  Residuals are infinity norms: ``residual_history``
+    = max|u - u_old|, |v - v_old| (the stopping test), ``momentum_residual_history`` = max|u* - u|, |v* - v|,
+    ``pressure_residual_history`` = max|p - p_old|.  The reference's adaptive ``alpha_p *= 0.95`` (:150-153) compares the
+    previous total residual with itself and never fires; it is reproduced by leaving ``alpha_p`` alone.  (The reference's
+    loop no longer runs against its own solvers -- it unpacks 2-tuples, :107-117 -- the golden runs use two adapters that only
+    reshape return values, oracle/make_golden.py:simplec_runs.)  Same device loop (``piso_corrections = -2``), single slab."""
+    _history_appends_per_iteration = 1
+    _piso_corrections = -2
+    _profile_prefix = "SIMPLEC"
+
+    def __init__(self, mesh, fluid, pressure_solver=None, momentum_solver=None, velocity_updater=None,
+                 boundary_conditions=None, alpha_p=0.2, alpha_u=0.7, **kw):
+        super().__init__(mesh, fluid, pressure_solver, momentum_solver, velocity_updater, boundary_conditions,
+                         alpha_p=alpha_p, alpha_u=alpha_u, **kw)
+
+    def _config(self):
+        c = super()._config()
+        c.simplec_divisor = 1 - (1 - self.alpha_u)  # the reference's expression, evaluated in the same order
+        return c
+
+    def solve(self, max_iterations=1000, tolerance=1e-6, save_profile=True, profile_dir="results/profiles",
+              track_infinity_norm=False, infinity_norm_interval=10, use_l2_norm=False, chunk=None, gather=True):
+        result = super().solve(max_iterations, tolerance, save_profile, profile_dir, track_infinity_norm,
+                               infinity_norm_interval, use_l2_norm, chunk, gather)
+        # the device record carries the three infinity norms (include/naviflow_b200.h: piso_corrections == -2)
+        self.momentum_residual_history = list(self._u_abs_res_history)
+        self.pressure_residual_history = list(self.pressure_rel_norms)
+        result.momentum_residuals = self.momentum_residual_history
+        result.pressure_residuals = self.pressure_residual_history
+        return result

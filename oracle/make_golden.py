@@ -9,6 +9,7 @@ import contextlib
 import io
 import json
 import os
+import sys
 import warnings
 
 import numpy as np
@@ -239,6 +240,51 @@ def simpler_runs(R):
     return out
 
 
+def simplec_runs(R):
+    """SimplecSolver.  Its loop is stale against the reference's own solvers: it unpacks 2-tuples from
+    the momentum solver (simplec.py:107-117) and indexes the pressure solver's answer as an array (:141-147).  Two adapters
+    that only reshape return values make it run; every number is the reference's."""
+    from naviflow_oo.solver.Algorithms.simplec import SimplecSolver
+
+    class Momentum2(R.JacobiMatrixMomentumSolver):
+        def solve_u_momentum(self, mesh, fluid, u, v, p, relaxation_factor=0.7, boundary_conditions=None):
+            return super().solve_u_momentum(mesh, fluid, u, v, p, relaxation_factor, boundary_conditions)[:2]
+
+        def solve_v_momentum(self, mesh, fluid, u, v, p, relaxation_factor=0.7, boundary_conditions=None):
+            return super().solve_v_momentum(mesh, fluid, u, v, p, relaxation_factor, boundary_conditions)[:2]
+
+    def array_only(cls):
+        class ArrayOnly(cls):
+            def solve(self, mesh, u_star, v_star, d_u, d_v, p_star):
+                out = super().solve(mesh, u_star, v_star, d_u, d_v, p_star)
+                return out[0] if isinstance(out, tuple) else out
+        return ArrayOnly
+
+    out = {}
+    for n, Re, k, N, name in ((31, 100, 5, 12, "v"), (31, 100, 5, 12, "rbsor"), (63, 1000, 10, 8, "v")):
+        GS = R.GaussSeidelSolver
+        if name == "v":
+            ps = array_only(R.MultiGridSolver)(smoother=GS(omega=1.5, method_type="red_black"), max_iterations=100,
+                                               tolerance=1e-3, pre_smoothing=3, post_smoothing=3)
+        else:
+            ps = array_only(GS)(tolerance=0.0, max_iterations=30, omega=1.5, method_type="red_black")
+        mesh = R.StructuredMesh(n, n, 1.0, 1.0)
+        fluid = R.FluidProperties(density=1.0, reynolds_number=Re, characteristic_velocity=1.0)
+        alg = SimplecSolver(mesh, fluid, ps, Momentum2(n_jacobi_sweeps=k), R.StandardVelocityUpdater(),
+                            alpha_p=0.2, alpha_u=0.7)
+        alg.set_boundary_condition("top", "velocity", {"u": 1.0, "v": 0.0})
+        for b in ("bottom", "left", "right"):
+            alg.set_boundary_condition(b, "wall")
+        _quiet(alg.solve, max_iterations=N, tolerance=0.0, save_profile=False, track_infinity_norm=False)
+        key = f"n{n}_Re{Re}_k{k}_N{N}_{name}"
+        out[key + "_u"], out[key + "_v"], out[key + "_p"] = alg.u, alg.v, alg.p
+        out[key + "_total"] = np.array(alg.residual_history)
+        out[key + "_momentum"] = np.array(alg.momentum_residual_history)
+        out[key + "_pressure"] = np.array(alg.pressure_residual_history)
+        out[key + "_alpha_p"] = np.array([alg.alpha_p])
+    return out
+
+
 def mf_momentum_kats(R):
     """MatrixFreeMomentumSolver (a7) on seeded fields + whole SimpleSolver runs with it (direct pressure solve)."""
     out = {}
@@ -358,6 +404,11 @@ def main():
     warnings.filterwarnings("ignore")
     R = rl.ref()
     os.makedirs(GOLD, exist_ok=True)
+    if len(sys.argv) > 1:  # regenerate single fixtures: make_golden.py simplec_runs ...
+        for name in sys.argv[1:]:
+            np.savez_compressed(os.path.join(GOLD, name + ".npz"), **globals()[name](R))
+            print("written", name)
+        return
     for n, seed in ((8, 108), (15, 115), (31, 131), (32, 132)):
         np.savez_compressed(os.path.join(GOLD, f"kernels_n{n}.npz"), **kernel_kats(R, n, seed))
     for n, seed in ((31, 231), (33, 233), (64, 264)):
@@ -365,6 +416,7 @@ def main():
     np.savez_compressed(os.path.join(GOLD, "simple_runs.npz"), **simple_runs(R))
     np.savez_compressed(os.path.join(GOLD, "piso_runs.npz"), **piso_runs(R))
     np.savez_compressed(os.path.join(GOLD, "simpler_runs.npz"), **simpler_runs(R))
+    np.savez_compressed(os.path.join(GOLD, "simplec_runs.npz"), **simplec_runs(R))
     np.savez_compressed(os.path.join(GOLD, "mf_momentum.npz"), **mf_momentum_kats(R))
     np.savez_compressed(os.path.join(GOLD, "gs_lex.npz"), **gs_lex_kats(R))
     np.savez_compressed(os.path.join(GOLD, "mg_lex.npz"), **mg_lex_kats(R))

@@ -1200,6 +1200,47 @@ def simpler_solve(nx, ny, reynolds, pressure_solver, n_sweeps=20, alpha_p=0.3, a
     return st, hist
 
 
+def simplec_solve(nx, ny, reynolds, pressure_solver, n_sweeps=20, alpha_p=0.2, alpha_u=0.7, max_iterations=100,
+                  tolerance=0.0, conditions=None, rho=1.0, U=1.0, L=1.0):
+    """SimplecSolver.solve (Algorithms/simplec.py:47-283) AS CODED, with the deterministic momentum oracle:
+    momentum predictor; d_u, d_v divided by 1 - (1 - alpha_u) (:126-127); pressure solve with the scaled d (:130-137);
+    5-point smoothing of p' with a zero boundary ring (:141-147); p = p* + alpha_p p' WITHOUT the zero-gradient edge copies
+    (:154; the call at :139 acts on the array that :154 replaces); velocity correction with the smoothed p' and the scaled d
+    (:162-166).  Residuals are infinity norms: momentum max|u* - u|, pressure max|p - p_old|, total max|u - u_old| (:119-122,
+    :157, :169-171); the loop runs while total > tolerance.  The adaptive alpha_p (:150-153) compares the previous total
+    residual with itself (max_res IS residual_history[-1] at that point) and therefore never fires."""
+    conditions = bc_conditions() if conditions is None else conditions
+    dx, dy = mesh_spacing(nx, ny, L, L)
+    mu = rho * U * L / reynolds
+    st = SimpleState(nx, ny, conditions)
+    p_star = st.p.copy()
+    hist = {"total": [], "momentum": [], "pressure": []}
+    it, max_res = 1, 1000.0
+    div = 1 - (1 - alpha_u)
+    while it <= max_iterations and max_res > tolerance:
+        u_old, v_old, p_old = st.u.copy(), st.v.copy(), st.p.copy()
+        us, du, _, _ = solve_u_momentum(nx, ny, dx, dy, rho, mu, st.u, st.v, p_star, alpha_u, conditions, n_sweeps)
+        vs, dv, _, _ = solve_v_momentum(nx, ny, dx, dy, rho, mu, st.u, st.v, p_star, alpha_u, conditions, n_sweeps)
+        momentum_res = max(np.max(np.abs(us - st.u)), np.max(np.abs(vs - st.v)))
+        with np.errstate(invalid="ignore", divide="ignore"):
+            du_c, dv_c = du / div, dv / div
+        pp, _ = pressure_solver(nx, ny, dx, dy, us, vs, du_c, dv_c)
+        sm = np.zeros_like(pp)
+        sm[1:-1, 1:-1] = 0.6 * pp[1:-1, 1:-1] + 0.1 * (pp[2:, 1:-1] + pp[:-2, 1:-1] + pp[1:-1, 2:] + pp[1:-1, :-2])
+        pp = sm
+        st.p = p_star + alpha_p * pp
+        pressure_res = np.max(np.abs(st.p - p_old))
+        p_star = st.p.copy()
+        st.u, st.v = correct_velocity(nx, ny, us, vs, pp, du_c, dv_c, conditions)
+        max_res = max(np.max(np.abs(st.u - u_old)), np.max(np.abs(st.v - v_old)))
+        hist["total"].append(float(max_res))
+        hist["momentum"].append(float(momentum_res))
+        hist["pressure"].append(float(pressure_res))
+        it += 1
+    hist["iterations"] = it - 1
+    return st, hist
+
+
 # ----------------------------------------------------------------------------
 # a17  Ghia centre-line errors (postprocessing/validation/cavity_flow.py:178-301)
 # ----------------------------------------------------------------------------

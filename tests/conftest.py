@@ -8,6 +8,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+# solve() saves a run record by default like the reference (save_profile=True); the tests that check the record ask for it
+os.environ.setdefault("NAVIFLOW_B200_NO_PROFILE_FILES", "1")
 
 
 def pytest_configure(config):

@@ -205,13 +205,15 @@ def test_argument_errors_are_reported():
         d.call("nf_pressure_apply", d.gref(), ptr(x), ptr(x), ptr(x), ptr(x))
 
 
-@pytest.mark.parametrize("tma", [False, True])
+@pytest.mark.parametrize("path", ["tiled", "tma", "stream"])
 @pytest.mark.parametrize("n", [7, 8, 31, 40, 53, 64, 65, 127, 130, 257])
-def test_fused_rbsor_is_bit_identical(n, tma, monkeypatch):
+def test_fused_rbsor_is_bit_identical(n, path, monkeypatch):
     """Temporally blocked red-black SOR (1..7 sweeps, tile/halo edges at every size class) against the oracle
-    and against the unfused colour kernels; tma=True forces the persistent TMA pipeline at every size."""
+    and against the unfused colour kernels; "tma" forces the persistent TMA pipeline and "stream" the streaming
+    (wavefront) kernel at every size they accept."""
     from gpu_util import Dev, ptr
-    monkeypatch.setenv("NF_RBSOR_TMA", "0" if tma else "1000000")
+    monkeypatch.setenv("NF_RBSOR_TMA", "0" if path == "tma" else "1000000")
+    monkeypatch.setenv("NF_RBSOR_STREAM", "0" if path == "stream" else "1000000000")
     s = synth(n, 2000 + n)
     dx = dy = 1.0 / (n - 1)
     d = Dev(n)
@@ -232,10 +234,13 @@ def test_fused_rbsor_is_bit_identical(n, tma, monkeypatch):
         np.testing.assert_array_equal(d.down(p2), want)
 
 
-def test_fused_rbsor_tma_large_grid_matches_unfused():
-    """1025^2 (the TMA pipeline's production regime: several tiles per SM) against the colour-pass kernels."""
+@pytest.mark.parametrize("n,path", [(1025, "tma"), (1025, "stream"), (2049, "stream"), (2048, "stream")])
+def test_fused_rbsor_large_grid_matches_unfused(n, path, monkeypatch):
+    """Production regimes (several tiles per SM for the TMA pipeline; one job per warp of a single wave with row chunks,
+    edge strips and an even-sized level for the streaming kernel) against the colour-pass kernels."""
     from gpu_util import Dev, ptr
-    n = 1025
+    monkeypatch.setenv("NF_RBSOR_TMA", "0" if path == "tma" else "1000000")
+    monkeypatch.setenv("NF_RBSOR_STREAM", "0" if path == "stream" else "1000000000")
     s = synth(n, 77)
     d = Dev(n)
     du, dv, us, vs = (d.up(s[k]) for k in ("d_u", "d_v", "u_star", "v_star"))

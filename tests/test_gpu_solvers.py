@@ -322,6 +322,39 @@ def test_smoother_fused_residual_paths_match_standalone_kernels(n, pre, post, mo
         assert rel(outs[0][0], x_ref) < 1e-11
 
 
+@pytest.mark.parametrize("n,pre,post", [(127, 3, 3), (200, 3, 3), (257, 3, 1), (130, 1, 3), (513, 3, 3), (640, 2, 2)])
+def test_streaming_smoother_and_single_kernel_coarse_end_match_the_round1_kernels(n, pre, post, monkeypatch):
+    """Round-2 cycle (streaming wavefront smoother with the fused residual + restriction / residual norms on every level of
+    >= 16 rows, coarse end of the V-cycle in one shared-memory kernel, coarse iterate zeroed by the restriction) against the
+    round-1 kernels (tiled smoother, one launch per operation): same iterates bit for bit, same cycle count, same norm to
+    rounding; small sizes also against the oracle."""
+    import naviflow_b200 as nb
+    from oracle.make_golden import synth_pressure_inputs
+    s = synth_pressure_inputs(n, 4100 + n)
+    # the array borders the momentum solver leaves NaN (a_P = 0 there): the kernels must never read them
+    s["d_u"][0, :] = np.nan; s["d_u"][n, :] = np.nan; s["d_v"][:, 0] = np.nan; s["d_v"][:, n] = np.nan
+    mesh, _ = cavity(n, 1000)
+    outs = []
+    for new in (True, False):
+        monkeypatch.setenv("NF_RBSOR_STREAM", "0" if new else "1000000000")
+        monkeypatch.setenv("NF_MG_TAIL", "1" if new else "0")
+        ps = nb.GpuMultiGridSolver(smoother=nb.GpuGaussSeidelSolver(omega=1.5), max_iterations=100, tolerance=1e-4,
+                                   pre_smoothing=pre, post_smoothing=post)
+        for rep in range(2):   # the second solve replays the captured graph of the cycle
+            p, info = ps.solve(mesh, s["u_star"], s["v_star"], s["d_u"], s["d_v"], None)
+        outs.append((p, info, ps.last_info.cycles))
+    np.testing.assert_array_equal(outs[0][0], outs[1][0])
+    assert outs[0][2] == outs[1][2]
+    assert abs(outs[0][1]["rel_norm"] - outs[1][1]["rel_norm"]) <= 1e-10 * outs[1][1]["rel_norm"]
+    if n <= 200:
+        dx = dy = 1.0 / (n - 1)
+        du, dv = np.nan_to_num(s["d_u"]), np.nan_to_num(s["d_v"])
+        cfg = O.MGConfig(omega=1.5, pre=pre, post=post, tolerance=1e-4, max_iterations=100)
+        x_ref, iref = O.mg_solve(cfg, n, n, dx, dy, s["u_star"], s["v_star"], du, dv)
+        assert iref["cycles"] == outs[0][2]
+        assert rel(outs[0][0], x_ref) < 1e-11
+
+
 @pytest.mark.parametrize("n,kind,cycles", [(31, "v", 1), (64, "v", 2), (65, "w", 1), (63, "fmg", 1)])
 def test_mg_preconditioned_bicgstab_vs_oracle(n, kind, cycles):
     """MatrixFreeBiCGSTABSolver(use_preconditioner=True, preconditioner='multigrid') twin against scipy's bicgstab
@@ -629,7 +662,7 @@ def test_lexicographic_gauss_seidel_vs_oracle(n, mt, sweeps):
     p0 = 1e-3 * rng.standard_normal((n, n))
     mesh, _ = cavity(n, 100)
     gs = nb.GpuGaussSeidelSolver(omega=1.3, method_type=mt)
-    p = gs.solve(mesh=mesh, p=p0.copy(), b=b.copy(), d_u=d_u, d_v=d_v, rho=1.0, num_iterations=sweeps, track_residuals=False)
+    p = gs.solve(mesh=mesh, p=p0.copy(), b=b.copy(), d_u=d_u, d_v=d_v, rho=1.0, num_iterations=sweeps, track_residuals=False, return_dict=False)
     np.testing.assert_array_equal(p, O.gs_lex(p0, b, dx, dy, 1.0, d_u, d_v, 1.3, sweeps, symmetric=(mt == "symmetric")))
 
 
@@ -800,3 +833,150 @@ def test_simple_loop_on_rectangular_grids_vs_reference_golden(golden_dir, nx, ny
         e = rel(getattr(alg, fld), g[f"{key}_{fld}"])
         assert e < 1e-10, (fld, e)
     np.testing.assert_allclose(res.get_history("total_rel_norm")[::2], g[key + "_hist"], rtol=1e-8)
+
+
+@pytest.mark.parametrize("n,Re,k,N,name", [(31, 100, 5, 12, "v"), (31, 100, 5, 12, "rbsor"), (63, 1000, 10, 8, "v")])
+def test_simplec_loop_vs_reference_golden(golden_dir, n, Re, k, N, name):
+    """SIMPLEC outer loop as the reference codes it (Algorithms/simplec.py:99-171): u, v, p after N
+    iterations equal the reference's SimplecSolver run to 1e-10 relative L2; the three infinity-norm histories."""
+    import naviflow_b200 as nb
+    g = load(golden_dir, "simplec_runs.npz")
+    key = f"n{n}_Re{Re}_k{k}_N{N}_{name}"
+    mesh, fluid = cavity(n, Re)
+    alg = nb.GpuSimplecSolver(mesh, fluid, make_ps(name), nb.GpuJacobiMomentumSolver(n_jacobi_sweeps=k),
+                              nb.GpuVelocityUpdater(), alpha_p=0.2, alpha_u=0.7)
+    alg.set_boundary_condition("top", "velocity", {"u": 1.0, "v": 0.0})
+    for b in ("bottom", "left", "right"):
+        alg.set_boundary_condition(b, "wall")
+    res = alg.solve(max_iterations=N, tolerance=0.0)
+    for fld in ("u", "v", "p"):
+        e = rel(getattr(alg, fld), g[f"{key}_{fld}"])
+        assert e < 1e-10, (fld, e)
+    assert res.iterations == N and alg.alpha_p == 0.2
+    np.testing.assert_allclose(alg.residual_history, g[key + "_total"], rtol=1e-8, atol=1e-14)
+    np.testing.assert_allclose(alg.momentum_residual_history, g[key + "_momentum"], rtol=1e-8, atol=1e-14)
+    np.testing.assert_allclose(alg.pressure_residual_history, g[key + "_pressure"], rtol=1e-8, atol=1e-14)
+    # the stopping test is on the total residual (simplec.py:99)
+    alg2 = nb.GpuSimplecSolver(mesh, fluid, make_ps(name), nb.GpuJacobiMomentumSolver(n_jacobi_sweeps=k), alpha_p=0.2,
+                               alpha_u=0.7)
+    alg2.set_boundary_condition("top", "velocity", {"u": 1.0, "v": 0.0})
+    for b in ("bottom", "left", "right"):
+        alg2.set_boundary_condition(b, "wall")
+    tol = float(g[key + "_total"][3]) * 1.0000001
+    want = 1 + int(np.argmax(g[key + "_total"] <= tol))
+    res2 = alg2.solve(max_iterations=N, tolerance=tol)
+    assert res2.iterations == want
+
+
+def test_device_loop_runs_the_multigrid_preconditioner_of_bicgstab():
+    """GpuSimpleSolver with GpuBiCGSTABSolver(use_preconditioner=True, preconditioner='multigrid') must run the
+    preconditioned recurrence (nf_simple_config.pressure_solver 7), not silently the plain one: same p' and the same
+    iteration counts as the plugin called step by step."""
+    import naviflow_b200 as nb
+    n, Re = 63, 100
+    mesh, fluid = cavity(n, Re)
+
+    def mk():
+        return nb.GpuBiCGSTABSolver(tolerance=1e-8, max_iterations=200, use_preconditioner=True, preconditioner="multigrid",
+                                    mg_cycles=1, mg_cycle_type="v")
+    alg = nb.GpuSimpleSolver(mesh, fluid, mk(), nb.GpuJacobiMomentumSolver(n_jacobi_sweeps=5), alpha_p=0.3, alpha_u=0.7)
+    alg.set_boundary_condition("top", "velocity", {"u": 1.0, "v": 0.0})
+    for b in ("bottom", "left", "right"):
+        alg.set_boundary_condition(b, "wall")
+    alg.solve(max_iterations=3, tolerance=0.0)
+    its_pre = list(alg.pressure_iterations_history)
+    plain = nb.GpuSimpleSolver(mesh, fluid, nb.GpuBiCGSTABSolver(tolerance=1e-8, max_iterations=200),
+                               nb.GpuJacobiMomentumSolver(n_jacobi_sweeps=5), alpha_p=0.3, alpha_u=0.7)
+    plain.set_boundary_condition("top", "velocity", {"u": 1.0, "v": 0.0})
+    for b in ("bottom", "left", "right"):
+        plain.set_boundary_condition(b, "wall")
+    plain.solve(max_iterations=3, tolerance=0.0)
+    its_plain = list(plain.pressure_iterations_history)
+    assert max(its_pre) < min(its_plain) / 2, (its_pre, its_plain)  # the preconditioner is really applied
+    # step-by-step with the plugin objects on the host fields of iteration 1 (from rest)
+    bc = alg.bc_manager
+    u0, v0, p0 = np.zeros((n + 1, n)), np.zeros((n, n + 1)), np.zeros((n, n))
+    u0, v0 = bc.apply_velocity_boundary_conditions(u0, v0, n, n)
+    ms = nb.GpuJacobiMomentumSolver(n_jacobi_sweeps=5)
+    us, du, _ = ms.solve_u_momentum(mesh, fluid, u0, v0, p0, relaxation_factor=0.7, boundary_conditions=bc)
+    vs, dv, _ = ms.solve_v_momentum(mesh, fluid, u0, v0, p0, relaxation_factor=0.7, boundary_conditions=bc)
+    sol = mk()
+    sol.solve(mesh, us, vs, du, dv, p0)
+    assert sol.last_info.iterations == its_pre[0]
+
+
+def test_solve_writes_the_reference_run_record(tmp_path, monkeypatch):
+    """solve(save_profile=True) (the reference's default) leaves <ALG>_Re<Re>_mesh<nx>x<ny>_profile.{h5,npz} with the
+    reference Profiler's groups (utils/profiler.py:317-443)."""
+    import naviflow_b200 as nb
+    monkeypatch.delenv("NAVIFLOW_B200_NO_PROFILE_FILES", raising=False)
+    mesh, fluid = cavity(33, 100)
+    alg = nb.GpuSimpleSolver(mesh, fluid, make_ps("v"), nb.GpuJacobiMomentumSolver(n_jacobi_sweeps=5), alpha_p=0.3, alpha_u=0.7)
+    alg.set_boundary_condition("top", "velocity", {"u": 1.0, "v": 0.0})
+    for b in ("bottom", "left", "right"):
+        alg.set_boundary_condition(b, "wall")
+    res = alg.solve(max_iterations=4, tolerance=0.0, profile_dir=str(tmp_path))
+    files = [f for f in os.listdir(tmp_path) if f.startswith("SIMPLE_Re100_mesh33x33_profile.")]
+    assert len(files) == 1
+    tree = nb.load_profile(os.path.join(str(tmp_path), files[0]))
+    assert int(tree["performance"]["iterations"]) == 4 and str(tree["pressure_solver"]["type"]) == "GpuMultiGridSolver"
+    np.testing.assert_allclose(tree["residual_history"]["total_residual"], res.get_history("total_rel_norm")[::2])
+    assert alg.profiler.profiling_data["pressure_solver_info"]["total_inner_iterations"] == sum(alg.pressure_iterations_history)
+
+
+@pytest.mark.parametrize("n", [1025, 2049])
+def test_multigrid_cycle_at_baseline_sizes_vs_oracle(n):
+    """BASELINE.json sizes (level chains with the even 512 / 1024 level, streaming smoother on the top levels, single-kernel
+    coarse end): two V(3,3) cycles against the NumPy oracle port, <= 1e-11 relative L2."""
+    import naviflow_b200 as nb
+    rng = np.random.default_rng(n)
+    dx, dy = O.mesh_spacing(n, n)
+    d_u = (0.7 * dy / 4e-3) * (1 + 0.1 * rng.random((n + 1, n)))
+    d_v = (0.7 * dx / 4e-3) * (1 + 0.1 * rng.random((n, n + 1)))
+    us = 1e-2 * rng.standard_normal((n + 1, n)); us[0, :] = us[n, :] = 0.0
+    vs = 1e-2 * rng.standard_normal((n, n + 1)); vs[:, 0] = vs[:, n] = 0.0
+    mesh, _ = cavity(n, 1000)
+    ps = nb.GpuMultiGridSolver(smoother=nb.GpuGaussSeidelSolver(omega=1.5), max_iterations=2, tolerance=1e-30,
+                               pre_smoothing=3, post_smoothing=3)
+    p, info = ps.solve(mesh, us, vs, d_u, d_v, None)
+    cfg = O.MGConfig(omega=1.5, pre=3, post=3, max_iterations=2, tolerance=1e-30)
+    p_ref, info_ref = O.mg_solve(cfg, n, n, dx, dy, us, vs, d_u, d_v)
+    assert rel(p, p_ref) < 1e-11
+    assert abs(info["rel_norm"] - info_ref["rel_norm"]) < 1e-9 * info_ref["rel_norm"]
+
+
+def test_outer_iteration_at_1025_vs_oracle():
+    """One full SIMPLE outer iteration at 1025^2 (BASELINE configs[1] size) against the oracle port: u, v, p <= 1e-10."""
+    import naviflow_b200 as nb
+    n, Re, k = 1025, 1000, 5
+    mesh, fluid = cavity(n, Re)
+    ps = nb.GpuMultiGridSolver(smoother=nb.GpuGaussSeidelSolver(omega=1.5), max_iterations=3, tolerance=1e-30,
+                               pre_smoothing=3, post_smoothing=3)
+    alg = nb.GpuSimpleSolver(mesh, fluid, ps, nb.GpuJacobiMomentumSolver(n_jacobi_sweeps=k), alpha_p=0.3, alpha_u=0.7)
+    alg.set_boundary_condition("top", "velocity", {"u": 1.0, "v": 0.0})
+    for b in ("bottom", "left", "right"):
+        alg.set_boundary_condition(b, "wall")
+    alg.solve(max_iterations=2, tolerance=0.0)
+    cfg = O.MGConfig(omega=1.5, pre=3, post=3, max_iterations=3, tolerance=1e-30)
+    st, _ = O.simple_solve(n, n, Re, O.make_pressure_solver("mg", cfg=cfg), n_sweeps=k, max_iterations=2, tolerance=0.0)
+    for fld in ("u", "v", "p"):
+        e = rel(getattr(alg, fld), getattr(st, fld))
+        assert e < 1e-10, (fld, e)
+
+
+def test_config1_fmg_1500_iterations_reproduces_the_survey_norms():
+    """SURVEY 8c golden values of BASELINE configs[0]: 63^2 Re=100, FMG(1)+V(3,3) cubic, 20 Jacobi momentum sweeps, 1500
+    outer iterations -> ||u||, ||v||, ||p|| generated with the reference during the survey."""
+    import naviflow_b200 as nb
+    mesh, fluid = cavity(63, 100)
+    alg = nb.GpuSimpleSolver(mesh, fluid, make_ps("fmg"), nb.GpuJacobiMomentumSolver(n_jacobi_sweeps=20), alpha_p=0.3,
+                             alpha_u=0.7)
+    alg.set_boundary_condition("top", "velocity", {"u": 1.0, "v": 0.0})
+    for b in ("bottom", "left", "right"):
+        alg.set_boundary_condition(b, "wall")
+    alg.solve(max_iterations=1500, tolerance=0.0)
+    assert abs(np.linalg.norm(alg.u) - 14.5192971946493) < 1e-9
+    assert abs(np.linalg.norm(alg.v) - 9.52637420908884) < 1e-9
+    assert abs(np.linalg.norm(alg.p) - 33.7706672709561) < 1e-8
+    inf, l2 = nb.ghia_errors(alg.u, alg.v, mesh, 100)
+    assert abs(inf - 0.05498) < 5e-5 and abs(l2 - 0.01865) < 5e-5

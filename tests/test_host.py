@@ -198,3 +198,46 @@ def test_simple_config_struct_carries_the_plugin_settings():
     assert (c.pressure_solver, c.piso_corrections, c.momentum_solver, c.n_momentum_sweeps) == (1, 0, 0, 4)
     with pytest.raises(NotImplementedError):
         nb.GpuSimpleSolver(mesh, fluid, nb.GpuJacobiSolver(tolerance=1e-3))._config()
+
+
+def test_profiler_record_layout_round_trip(tmp_path):
+    """naviflow_b200.Profiler keeps the reference's on-disk tree (utils/profiler.py:317-443): groups simulation/mesh_size,
+    performance, convergence, system, algorithm, pressure_solver/{smoother,multigrid}, momentum_solver as attributes and
+    residual_history/<column> datasets; without h5py the same tree goes to an .npz that load_profile reads back."""
+    import naviflow_b200 as nb
+
+    class PS:
+        tolerance, max_iterations, cycle_type, pre_smoothing, post_smoothing, smoother_omega = 1e-3, 100, "v", 3, 3, 1.5
+        smoother = object()
+
+    class Alg:
+        alpha_p, alpha_u = 0.3, 0.7
+        pressure_solver = PS()
+        momentum_solver = object()
+
+    mesh = nb.StructuredMesh(17, 17, 1.0, 1.0)
+    fluid = nb.FluidProperties(density=1.0, reynolds_number=100, characteristic_velocity=1.0)
+    prof = nb.Profiler("SimpleSolver", mesh, fluid, algorithm=Alg())
+    prof.start()
+    for it in range(1, 4):
+        prof.add_residual_data(it, 1.0 / it, 2.0 / it, 3.0 / it, None if it < 3 else 0.05)
+    prof.set_iterations(3)
+    prof.set_convergence_info(1e-6, 1.0 / 3, [1.0, 0.5, 1.0 / 3])
+    prof.set_pressure_solver_info("GpuMultiGridSolver", inner_iterations=[5, 6, 7])
+    prof.end()
+    path = prof.save(str(tmp_path / "SIMPLE_Re100_mesh17x17_profile.h5"))
+    tree = nb.load_profile(path)
+    assert set(tree) >= {"simulation", "performance", "convergence", "system", "algorithm", "pressure_solver",
+                         "momentum_solver", "residual_history"}
+    assert int(tree["simulation"]["mesh_size"]["x"]) == 17 and float(tree["simulation"]["reynolds_number"]) == 100.0
+    assert int(tree["performance"]["iterations"]) == 3 and not bool(tree["convergence"]["converged"])
+    assert float(tree["algorithm"]["alpha_p"]) == 0.3
+    assert str(tree["pressure_solver"]["type"]) == "PS" and int(tree["pressure_solver"]["multigrid"]["pre_smoothing"]) == 3
+    assert float(tree["pressure_solver"]["smoother"]["omega"]) == 1.5
+    rh = tree["residual_history"]
+    assert set(rh) == {"iteration", "wall_time", "cpu_time", "total_residual", "momentum_residual", "pressure_residual",
+                       "infinity_norm_error"}
+    np.testing.assert_allclose(rh["total_residual"], [1.0, 0.5, 1.0 / 3])
+    assert np.isnan(rh["infinity_norm_error"][0]) and rh["infinity_norm_error"][2] == 0.05
+    info = prof.profiling_data["pressure_solver_info"]
+    assert info["total_inner_iterations"] == 18 and info["max_inner_iterations"] == 7 and info["min_inner_iterations"] == 5

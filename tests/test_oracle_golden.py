@@ -279,3 +279,21 @@ def test_simple_loop_on_rectangular_grids_golden(golden_dir, nx, ny, Re, k, N, n
     for fld, arr in (("u", st.u), ("v", st.v), ("p", st.p)):
         same(arr, g[f"{key}_{fld}"])
     np.testing.assert_allclose(h["total_rel_norm"], g[key + "_hist"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("n,Re,k,N,name", [(31, 100, 5, 12, "v"), (31, 100, 5, 12, "rbsor"), (63, 1000, 10, 8, "v")])
+def test_simplec_loop_golden(golden_dir, n, Re, k, N, name):
+    """SimplecSolver.solve (Algorithms/simplec.py:47-283) as coded, against the reference's own run (through
+    two adapters that only reshape return values, oracle/make_golden.py:simplec_runs): fields, the three infinity-norm
+    histories, and alpha_p left untouched by the never-firing adaptive rule."""
+    g = load(golden_dir, "simplec_runs.npz")
+    key = f"n{n}_Re{Re}_k{k}_N{N}_{name}"
+    st, h = O.simplec_solve(n, n, Re, _ps(name), n_sweeps=k, alpha_p=0.2, alpha_u=0.7, max_iterations=N, tolerance=0.0)
+    for fld, arr in (("u", st.u), ("v", st.v), ("p", st.p)):
+        if name == "rbsor":
+            same(arr, g[f"{key}_{fld}"])
+        else:
+            close(arr, g[f"{key}_{fld}"], 1e-12)
+    for hk in ("total", "momentum", "pressure"):
+        np.testing.assert_allclose(h[hk], g[f"{key}_{hk}"], rtol=1e-9, atol=1e-15)
+    assert float(g[key + "_alpha_p"][0]) == 0.2

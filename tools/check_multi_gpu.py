@@ -33,7 +33,7 @@ def run(n, distributed, virtual_ranks=1, iters=3, piso=0, timed=0, solver="mg"):
     alg.set_boundary_condition("top", "velocity", {"u": 1.0, "v": 0.0})
     for b in ("bottom", "left", "right"):
         alg.set_boundary_condition(b, "wall")
-    res = alg.solve(max_iterations=iters, tolerance=0.0)
+    res = alg.solve(max_iterations=iters, tolerance=0.0, save_profile=False)
     alg.ms_per_iteration = None
     if timed:
         alg.iterate_resident(2)

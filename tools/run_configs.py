@@ -42,11 +42,11 @@ def c1():
                                coarsest_grid_size=7)
     alg = nb.GpuSimpleSolver(mesh, fluid, ps, nb.GpuJacobiMomentumSolver(n_jacobi_sweeps=k), alpha_p=0.3, alpha_u=0.7)
     set_bcs(alg)
-    alg.solve(max_iterations=5, tolerance=0.0)  # warm up
+    alg.solve(max_iterations=5, tolerance=0.0, save_profile=False)  # warm up
     alg.initialize_fields()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    alg.solve(max_iterations=N, tolerance=0.0)
+    alg.solve(max_iterations=N, tolerance=0.0, save_profile=False)
     t_gpu = time.perf_counter() - t0
     inf, l2 = nb.ghia_errors(alg.u, alg.v, mesh, Re)
     # CPU oracle port, bounded sample: 100 iterations
@@ -76,10 +76,10 @@ def c2(iters):
                      ("bicgstab", nb.GpuBiCGSTABSolver(tolerance=1e-7, max_iterations=3000))):
         alg = nb.GpuSimpleSolver(mesh, fluid, ps, nb.GpuJacobiMomentumSolver(n_jacobi_sweeps=5), alpha_p=0.3, alpha_u=0.7)
         set_bcs(alg)
-        alg.solve(max_iterations=2, tolerance=0.0)
+        alg.solve(max_iterations=2, tolerance=0.0, save_profile=False)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        res = alg.solve(max_iterations=10, tolerance=0.0)
+        res = alg.solve(max_iterations=10, tolerance=0.0, save_profile=False)
         dt = time.perf_counter() - t0
         its = alg.pressure_iterations_history
         out[name] = {"s_per_outer_iter": dt / 10, "krylov_iters_per_solve": float(np.mean(its)),
@@ -232,7 +232,7 @@ def c3(n, k, max_iters):
     set_bcs(alg)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    res = alg.solve(max_iterations=max_iters, tolerance=1e-6)
+    res = alg.solve(max_iterations=max_iters, tolerance=1e-6, save_profile=False)
     dt = time.perf_counter() - t0
     h = res.get_history("total_rel_norm")[::2]
     inf, l2 = nb.ghia_errors(alg.u, alg.v, mesh, Re)
