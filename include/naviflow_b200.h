@@ -270,7 +270,10 @@ typedef struct nf_simple_config {
   int32_t krylov_mg_cycles;     /* pressure_solver 7: multigrid cycles per preconditioner application                  */
   int32_t krylov_mg_kind;       /* pressure_solver 7: 0 'v', 1 'w', 2 'fmg' (matrix_free_BiCGSTAB.py:102-161); the
                                    preconditioner's hierarchy is described by `mg`                                     */
-  int32_t pad2;
+  int32_t track_unrelaxed_residual; /* 1: every record also carries the absolute UNRELAXED momentum residual norms of the
+                                   predicted velocities (matrix_free_momentum.py:380-400 masks) -- one extra pass over the
+                                   links per component; the convergence measure of the outer loop for the Jacobi-sweep
+                                   predictor, whose own rel_norm is the relaxed inner residual           */
 } nf_simple_config;
 
 typedef struct nf_simple_info {   /* one record per outer iteration */
@@ -280,6 +283,7 @@ typedef struct nf_simple_info {   /* one record per outer iteration */
   double u_abs_res, v_abs_res;    /* sqrt(sum r^2) of the relaxed momentum residual over the interior   */
   int32_t pressure_iterations;    /* multigrid cycles / Krylov iterations used                          */
   int32_t pad;
+  double u_unrelaxed_res, v_unrelaxed_res; /* cfg.track_unrelaxed_residual: ||S_un - A_un u*|| over the interior, else 0 */
 } nf_simple_info;
 
 int nf_simple_create(nf_ctx*, nf_simple** out, const nf_simple_config* cfg);

@@ -65,13 +65,14 @@ class NfSimpleConfig(C.Structure):
                 ("momentum_solver", C.c_int32), ("momentum_maxiter", C.c_int32), ("momentum_tolerance", C.c_double),
                 ("bc_mf", NfBcProgram),
                 ("simplec_divisor", C.c_double), ("krylov_check_every", C.c_int32), ("krylov_mg_cycles", C.c_int32),
-                ("krylov_mg_kind", C.c_int32), ("pad2", C.c_int32)]
+                ("krylov_mg_kind", C.c_int32), ("track_unrelaxed_residual", C.c_int32)]
 
 
 class NfSimpleInfo(C.Structure):
     _fields_ = [("u_rel_norm", C.c_double), ("v_rel_norm", C.c_double), ("p_rel_norm", C.c_double),
                 ("u_abs_res", C.c_double), ("v_abs_res", C.c_double),
-                ("pressure_iterations", C.c_int32), ("pad", C.c_int32)]
+                ("pressure_iterations", C.c_int32), ("pad", C.c_int32),
+                ("u_unrelaxed_res", C.c_double), ("v_unrelaxed_res", C.c_double)]
 
 
 P = C.c_void_p          # device pointer

@@ -394,6 +394,47 @@ extern "C" int nf_momentum_links_mf(nf_ctx* ctx, const nf_grid* g, int is_u, con
   return nfi_momentum_links_mf(ctx, g, is_u, u_bc, v_bc, p, mu, alpha, sides, out, d, ap_unrelaxed, src_unrelaxed);
 }
 
+// The same unrelaxed residual from the RELAXED links of the Jacobi-sweep predictor (jacobi_matrix_solver.py:186-187, :213-219:
+// a_P <- a_P / alpha, S <- S + (1 - alpha) (a_P / alpha) phi_old): a_P,un = alpha a_P,rel and S,un = S,rel - (1 - alpha) a_P,rel
+// phi_old, masks as matrix_free_momentum.py:380-400.  A convergence diagnostic of the OUTER loop (the relaxed inner
+// residual the stopping test uses says nothing about it); rows [g.gb, row_end) of a slab.
+template <int IS_U>
+__global__ void k_momentum_unrelaxed_from_relaxed(nf_grid g, nf_links L, const double* __restrict__ x,
+                                                  const double* __restrict__ phi_old, double alpha, double* partials,
+                                                  unsigned int* ticket, double* out) {
+  double acc[1] = {0.0};
+  const int rows = nf_rows(g, IS_U), cols = nf_cols(g, IS_U);
+  const int i_end = nf_row_end(g, IS_U);
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < cols) {
+    for (int i = g.gb + blockIdx.y * blockDim.y + threadIdx.y; i < i_end; i += gridDim.y * blockDim.y) {
+      bool zero = (i == 0 || i == rows - 1 || j == 0 || j == cols - 1);
+      if (IS_U) zero = zero || i == 1 || i == rows - 2;
+      else zero = zero || j == 1 || j == cols - 2;
+      if (zero) continue;
+      const size_t k = nf_idx(g, i, j);
+      const double ap_rel = L.a_p[k];
+      double ax = (alpha * ap_rel) * x[k];
+      ax -= L.a_e[k] * x[k + g.ld];
+      ax -= L.a_w[k] * x[k - g.ld];
+      ax -= L.a_n[k] * x[k + 1];
+      ax -= L.a_s[k] * x[k - 1];
+      const double r = (L.src[k] - (1.0 - alpha) * ap_rel * phi_old[k]) - ax;
+      acc[0] += r * r;
+    }
+  }
+  nf_block_reduce_store<1>(acc, partials, ticket, out);
+}
+
+int nfi_momentum_unrelaxed_from_relaxed(nf_ctx* ctx, const nf_grid* g, int is_u, nf_links L, const double* x,
+                                        const double* phi_old, double alpha, double* out) {
+  NfLaunch2D l = nf_launch_reduce(nf_row_end(*g, is_u) - g->gb, nf_cols(*g, is_u));
+  if (is_u) k_momentum_unrelaxed_from_relaxed<1><<<l.grid, l.block, 0, ctx->stream>>>(*g, L, x, phi_old, alpha, ctx->partials, ctx->ticket, out);
+  else k_momentum_unrelaxed_from_relaxed<0><<<l.grid, l.block, 0, ctx->stream>>>(*g, L, x, phi_old, alpha, ctx->partials, ctx->ticket, out);
+  NF_LAUNCH_CHECK(ctx);
+  return NF_OK;
+}
+
 // sum r^2 of the unrelaxed residual -> out[0] (device); L.a_p / L.src hold the UNRELAXED a_P and source
 int nfi_momentum_residual_unrelaxed(nf_ctx* ctx, const nf_grid* g, int is_u, nf_links L, const double* x, double* field,
                                     double* out) {

@@ -32,6 +32,9 @@ int nfi_momentum_bicgstab(nf_ctx*, const nf_grid*, int is_u, nf_links L, double*
                           int check_every, double* work, nf_krylov_info* info);
 int nfi_momentum_residual_unrelaxed(nf_ctx*, const nf_grid*, int is_u, nf_links L, const double* x, double* field,
                                     double* out);
+int nfi_momentum_unrelaxed_from_relaxed(nf_ctx*, const nf_grid*, int is_u, nf_links L, const double* x,
+                                        const double* phi_old, double alpha, double* out);
+#define NF_HIST 10  // doubles per history record
 int nfi_correct_velocity(nf_ctx*, const nf_grid*, const nf_bc_program*, const double* us, const double* vs,
                          const double* pp, const double* d_u, const double* d_v, double* u, double* v);
 int nfi_gs_lex(nf_ctx*, const nf_grid*, double* p, const double* b, const double* d_u, const double* d_v, double omega,
@@ -322,10 +325,12 @@ extern "C" int nf_simple_download(nf_simple* s, int which, double* host, int row
 }
 
 // history record: [0] sum r_p^2 (or payload a), [1] sum b_p^2 (payload b), [2] sum r_u^2, [3] sum b_u^2,
-//                 [4] sum r_v^2, [5] sum b_v^2, [6] pressure iterations, [7] spare
-__global__ void k_store_hist_momentum(const double* __restrict__ scal, double* __restrict__ rec) {
+//                 [4] sum r_v^2, [5] sum b_v^2, [6] pressure iterations, [7] spare (SIMPLEC: total residual),
+//                 [8], [9] sum of squares of the UNRELAXED u / v momentum residual (cfg.track_unrelaxed_residual)
+__global__ void k_store_hist_momentum(const double* __restrict__ scal, double* __restrict__ rec, int with_unrelaxed) {
   const int t = threadIdx.x;
   if (t >= 2 && t < 6) rec[t] = scal[t];
+  if (t == 8 || t == 9) rec[t] = with_unrelaxed ? scal[t - 2] : 0.0;  // scal[6], scal[7]
 }
 
 __global__ void k_store_hist_pressure(const double* __restrict__ pscal, double* __restrict__ rec, double pa, double pb,
@@ -421,8 +426,8 @@ static int ensure_hist(nf_simple* s, int n) {
   if (s->hist) cudaFree(s->hist);
   if (s->hist_host) cudaFreeHost(s->hist_host);
   s->hist = nullptr; s->hist_host = nullptr; s->hist_cap = 0;
-  NF_CHECK_CUDA(ctx, cudaMalloc(&s->hist, (size_t)n * 8 * sizeof(double)));
-  NF_CHECK_CUDA(ctx, cudaMallocHost(&s->hist_host, (size_t)n * 8 * sizeof(double)));
+  NF_CHECK_CUDA(ctx, cudaMalloc(&s->hist, (size_t)n * NF_HIST * sizeof(double)));
+  NF_CHECK_CUDA(ctx, cudaMallocHost(&s->hist_host, (size_t)n * NF_HIST * sizeof(double)));
   s->hist_cap = n;
   return NF_OK;
 }
@@ -434,6 +439,8 @@ static void decode_record(const nf_simple* s, const double* rec, nf_simple_info*
     out->p_rel_norm = rec[0];
     out->pressure_iterations = (int)rec[6];
     out->pad = 0;
+    out->u_unrelaxed_res = sqrt(rec[8]);
+    out->v_unrelaxed_res = sqrt(rec[9]);
     return;
   }
   out->u_abs_res = sqrt(rec[2]);
@@ -454,6 +461,8 @@ static void decode_record(const nf_simple* s, const double* rec, nf_simple_info*
   }
   out->pressure_iterations = (int)rec[6];
   out->pad = 0;
+  out->u_unrelaxed_res = sqrt(rec[8]);
+  out->v_unrelaxed_res = sqrt(rec[9]);
 }
 
 // a7: MatrixFreeMomentumSolver.solve_u/v_momentum (matrix_free_momentum.py:403-544), single slab.  ubc / vbc hold the
@@ -483,7 +492,8 @@ static int momentum_component_krylov(nf_simple* s, int is_u, double alpha, int w
 }
 
 // momentum predictor of one component on every local slab (no communication, see the header comment)
-static int momentum_component(nf_simple* s, int is_u, double alpha, int want_fields) {
+// track: also leave the sum of squares of the UNRELAXED residual of the predicted component in scal[6] (u) / scal[7] (v)
+static int momentum_component(nf_simple* s, int is_u, double alpha, int want_fields, int track = 0) {
   nf_ctx* ctx = s->ctx;
   nf_team* team = s->team;
   const nf_simple_config& c = s->cfg;
@@ -567,6 +577,13 @@ static int momentum_component(nf_simple* s, int is_u, double alpha, int want_fie
       NF_TRY(nfi_momentum_residual_to(ctx, &g, is_u, S.links, src[k], want_fields ? (is_u ? S.ures : S.vres) : nullptr,
                                       S.scal + (is_u ? 2 : 4)));
     }
+  if (track)  // the component's links are still in place (the other component overwrites them next)
+    for (int k = 0; k < nl; ++k) {
+      SimpleSlab& S = s->s[k];
+      const nf_grid g = s->geom.grid(team->local[k]);
+      const double* phi_old = is_u ? (s->bc_clean ? S.u : S.ubc) : (s->bc_clean ? S.v : S.vbc);
+      NF_TRY(nfi_momentum_unrelaxed_from_relaxed(ctx, &g, is_u, S.links, src[k], phi_old, alpha, S.scal + (is_u ? 6 : 7)));
+    }
   return NF_OK;
 }
 
@@ -600,18 +617,20 @@ static int momentum_predictor(nf_simple* s, double alpha, int want_fields, int s
     NF_TRY(momentum_component_krylov(s, 1, alpha, want_fields));
     NF_TRY(momentum_component_krylov(s, 0, alpha, want_fields));
   } else {
+    const int trk = (slot >= 0 && s->cfg.track_unrelaxed_residual != 0) ? 1 : 0;
     NF_TRY(refresh_bc_copies(s));
-    NF_TRY(momentum_component(s, 1, alpha, want_fields));
-    NF_TRY(momentum_component(s, 0, alpha, want_fields));
+    NF_TRY(momentum_component(s, 1, alpha, want_fields, trk));
+    NF_TRY(momentum_component(s, 0, alpha, want_fields, trk));
   }
   if (slot < 0) return NF_OK;
   const int nl = nlocal(s);
-  if (s->geom.dist) {  // momentum sums of all slabs (4 doubles at scal[2..5])
+  const int track = (s->cfg.track_unrelaxed_residual != 0 && s->cfg.momentum_solver == 0) ? 1 : 0;
+  if (s->geom.dist) {  // momentum sums of all slabs (scal[2..5], with the unrelaxed sums scal[6..7])
     std::vector<double*> sc(nl);
     for (int k = 0; k < nl; ++k) sc[k] = s->s[k].scal + 2;
-    NF_TRY(nf_team_allreduce(s->team, sc.data(), 4));
+    NF_TRY(nf_team_allreduce(s->team, sc.data(), track ? 6 : 4));
   }
-  k_store_hist_momentum<<<1, 32, 0, ctx->stream>>>(s->s[0].scal, s->hist + (size_t)slot * 8);
+  k_store_hist_momentum<<<1, 32, 0, ctx->stream>>>(s->s[0].scal, s->hist + (size_t)slot * NF_HIST, track);
   NF_LAUNCH_CHECK(ctx);
   return NF_OK;
 }
@@ -775,14 +794,14 @@ static int pressure_correction(nf_simple* s, int slot, double alpha, bool correc
     NF_TRY(maxabs_diff(ctx, g.nx + 1, g.ny, g.ld, S.u, S.u_old, S.cscal + 3));
     NF_TRY(maxabs_diff(ctx, g.nx, g.ny + 1, g.ld, S.v, S.v_old, S.cscal + 4));
     if (slot >= 0) {
-      k_store_hist_simplec<<<1, 32, 0, ctx->stream>>>(S.cscal, s->hist + (size_t)slot * 8, iters);
+      k_store_hist_simplec<<<1, 32, 0, ctx->stream>>>(S.cscal, s->hist + (size_t)slot * NF_HIST, iters);
       NF_LAUNCH_CHECK(ctx);
     }
     s->bc_clean = true;
     return NF_OK;
   }
   if (slot >= 0 && !diff_record) {
-    k_store_hist_pressure<<<1, 32, 0, ctx->stream>>>(pscal, s->hist + (size_t)slot * 8, pa, pb, iters, p_from_scalars);
+    k_store_hist_pressure<<<1, 32, 0, ctx->stream>>>(pscal, s->hist + (size_t)slot * NF_HIST, pa, pb, iters, p_from_scalars);
     NF_LAUNCH_CHECK(ctx);
   }
   // p = p* + alpha p' with zero-gradient edges; p* <- p.  velocity correction + BCs.
@@ -804,7 +823,7 @@ static int pressure_correction(nf_simple* s, int slot, double alpha, bool correc
       sc[k] = S.scal;
     }
     if (dist) NF_TRY(nf_team_allreduce(team, sc.data(), 1));
-    k_store_hist_pressure<<<1, 32, 0, ctx->stream>>>(s->s[0].scal, s->hist + (size_t)slot * 8, 0.0, 0.0, iters, 1);
+    k_store_hist_pressure<<<1, 32, 0, ctx->stream>>>(s->s[0].scal, s->hist + (size_t)slot * NF_HIST, 0.0, 0.0, iters, 1);
     NF_LAUNCH_CHECK(ctx);
   }
   if (dist) {
@@ -934,22 +953,22 @@ extern "C" int nf_simple_iterate(nf_simple* s, int n_iterations, double toleranc
     NF_TRY(simple_step(s, it, want_fields));
     ++done;
     if (tolerance > 0.0) {  // stopping test of simple.py:114 needs this iteration's norms
-      NF_CHECK_CUDA(ctx, cudaMemcpyAsync(s->hist_host + (size_t)it * 8, s->hist + (size_t)it * 8, 8 * sizeof(double),
+      NF_CHECK_CUDA(ctx, cudaMemcpyAsync(s->hist_host + (size_t)it * NF_HIST, s->hist + (size_t)it * NF_HIST, NF_HIST * sizeof(double),
                                          cudaMemcpyDeviceToHost, ctx->stream));
       NF_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
       nf_simple_info rec;
-      decode_record(s, s->hist_host + (size_t)it * 8, &rec);
+      decode_record(s, s->hist_host + (size_t)it * NF_HIST, &rec);
       if (info_host) info_host[it] = rec;
       const double total = fmax(rec.u_rel_norm, rec.v_rel_norm);
       if (!(total > tolerance)) break;
     }
   }
   if (!(tolerance > 0.0) && done > 0) {
-    NF_CHECK_CUDA(ctx, cudaMemcpyAsync(s->hist_host, s->hist, (size_t)done * 8 * sizeof(double), cudaMemcpyDeviceToHost,
+    NF_CHECK_CUDA(ctx, cudaMemcpyAsync(s->hist_host, s->hist, (size_t)done * NF_HIST * sizeof(double), cudaMemcpyDeviceToHost,
                                        ctx->stream));
     NF_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (info_host)
-      for (int it = 0; it < done; ++it) decode_record(s, s->hist_host + (size_t)it * 8, &info_host[it]);
+      for (int it = 0; it < done; ++it) decode_record(s, s->hist_host + (size_t)it * NF_HIST, &info_host[it]);
   }
   if (n_done) *n_done = done;
   if (s->team->p2p && done > 0 && nf_p2p_error(s->team)) {

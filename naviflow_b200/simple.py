@@ -63,7 +63,7 @@ class GpuSimpleSolver:
 
     def __init__(self, mesh, fluid, pressure_solver=None, momentum_solver=None, velocity_updater=None,
                  boundary_conditions=None, alpha_p=0.3, alpha_u=0.7, fix_lid_corners=False, device=None,
-                 distributed=None, virtual_ranks=1):
+                 distributed=None, virtual_ranks=1, track_unrelaxed_residual=False):
         """``distributed``: cut the grid into row slabs over the ranks of the initialised torch.distributed
         (NCCL) process group (default: automatically when its world size is > 1).  ``virtual_ranks`` > 1 cuts
         the grid into that many slabs inside this process on this device (same code path; used by the tests)."""
@@ -89,6 +89,10 @@ class GpuSimpleSolver:
         self._state_key = None
         self._team = None
         self._virtual_ranks = int(virtual_ranks)
+        # every iteration record then carries ||S_un - A_un u*||, ||S_un - A_un v*|| (``unrelaxed_residual_history``): the
+        # outer loop's convergence measure when the momentum predictor is the fixed-sweep Jacobi solver
+        self.track_unrelaxed_residual = bool(track_unrelaxed_residual)
+        self.unrelaxed_residual_history = []
         self._distributed = distributed
         self._p_residual_cache = None
         self._final_u_residual_field = self._final_v_residual_field = None
@@ -218,6 +222,7 @@ class GpuSimpleSolver:
         c.krylov_maxiter = 0
         c.piso_corrections = int(self._piso_corrections)
         c.simplec_divisor = 0.0
+        c.track_unrelaxed_residual = 1 if self.track_unrelaxed_residual else 0
         c.pressure_iterations = 0
         c.pressure_omega = 1.0
         c.pressure_tolerance = 0.0
@@ -364,7 +369,8 @@ class GpuSimpleSolver:
         ctx.check(ctx.lib.nf_simple_iterate(st, int(n_iterations), float(tolerance), 1 if want_fields else 0, infos,
                                             C.byref(done)), "nf_simple_iterate")
         return [dict(u_rel_norm=r.u_rel_norm, v_rel_norm=r.v_rel_norm, p_rel_norm=r.p_rel_norm,
-                     u_abs_res=r.u_abs_res, v_abs_res=r.v_abs_res, pressure_iterations=r.pressure_iterations)
+                     u_abs_res=r.u_abs_res, v_abs_res=r.v_abs_res, pressure_iterations=r.pressure_iterations,
+                     u_unrelaxed_res=r.u_unrelaxed_res, v_unrelaxed_res=r.v_unrelaxed_res)
                 for r in infos[: done.value]]
 
     def smoother_timing(self, on):
@@ -431,6 +437,7 @@ class GpuSimpleSolver:
         self.infinity_norm_history = []
         self.pressure_iterations_history = []
         self._u_abs_res_history = []
+        self.unrelaxed_residual_history = []
         iteration = 1
         total = 1.0
         if chunk is None:
@@ -452,6 +459,7 @@ class GpuSimpleSolver:
                     self.pressure_rel_norms.append(r["p_rel_norm"])
                     self.pressure_iterations_history.append(r["pressure_iterations"])
                     self._u_abs_res_history.append(r["u_abs_res"])
+                    self.unrelaxed_residual_history.append(max(r["u_unrelaxed_res"], r["v_unrelaxed_res"]))
                     self.residual_history.extend([total] * self._history_appends_per_iteration)
                 iteration += len(recs)
                 if track_infinity_norm and (iteration - 1) % infinity_norm_interval == 0:

@@ -361,6 +361,22 @@ def solve_v_momentum(nx, ny, dx, dy, rho, mu, u, v, p, alpha, conditions, n_swee
     return v_star, d_v, norm, field
 
 
+def momentum_unrelaxed_residual_norm(is_u, nx, ny, dx, dy, rho, mu, u, v, p, star, conditions):
+    """||S_un - A_un star|| over the interior with the masks of MatrixFreeMomentumSolver._calculate_unrelaxed_residual
+    (matrix_free_momentum.py:380-400), for a predicted field `star` of the power-law system assembled from (u, v, p): the
+    convergence measure of the outer loop that does not depend on the momentum solver."""
+    u_bc, v_bc = apply_velocity_bc(u.copy(), v.copy(), nx, ny, conditions)
+    sides = tuple(s for s in ("left", "right", "bottom", "top") if conditions.get(s))
+    c = (u_coefficients if is_u else v_coefficients)(nx, ny, dx, dy, rho, mu, u_bc, v_bc, p, sides)
+    r = momentum_residual(c["a_e"], c["a_w"], c["a_n"], c["a_s"], c["a_p"], c["source"], star)
+    r[0, :] = 0.0; r[-1, :] = 0.0; r[:, 0] = 0.0; r[:, -1] = 0.0
+    if is_u:
+        r[1, :] = 0.0; r[-2, :] = 0.0
+    else:
+        r[:, 1] = 0.0; r[:, -2] = 0.0
+    return float(np.linalg.norm(r))
+
+
 # ----------------------------------------------------------------------------
 # a7  MatrixFreeMomentumSolver (solver/momentum_solver/matrix_free_momentum.py:403-544): Krylov solve of the
 #     relaxed momentum system, interior rows 5-point, boundary rows identity

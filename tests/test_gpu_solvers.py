@@ -980,3 +980,49 @@ def test_config1_fmg_1500_iterations_reproduces_the_survey_norms():
     assert abs(np.linalg.norm(alg.p) - 33.7706672709561) < 1e-8
     inf, l2 = nb.ghia_errors(alg.u, alg.v, mesh, 100)
     assert abs(inf - 0.05498) < 5e-5 and abs(l2 - 0.01865) < 5e-5
+
+
+def test_unrelaxed_momentum_residual_column_vs_oracle():
+    """nf_simple_config.track_unrelaxed_residual: every record carries ||S_un - A_un u*||, ||S_un - A_un v*|| (masks of
+    matrix_free_momentum.py:380-400) evaluated from the relaxed links; against the oracle's unrelaxed assembly, single slab
+    and 3 slabs; the iterates themselves do not change."""
+    import naviflow_b200 as nb
+    n, Re, k, N = 97, 1000, 5, 4
+    cond = O.bc_conditions()
+    dx, dy = O.mesh_spacing(n, n)
+    want = []
+    cfg = O.MGConfig(omega=1.5, pre=3, post=3, max_iterations=100, tolerance=1e-3)
+
+    def cb(it, st, us, vs, du, dv, pp):
+        want.append((us.copy(), vs.copy()))
+    states = []
+    st = O.SimpleState(n, n, cond)
+    p_star = st.p.copy()
+    for it in range(N):   # one oracle iteration at a time so that (u, v, p) before the iteration are at hand
+        before = (st.u.copy(), st.v.copy(), st.p.copy())
+        st, _ = O.simple_solve(n, n, Re, O.make_pressure_solver("mg", cfg=cfg), n_sweeps=k, max_iterations=1, tolerance=0.0,
+                               state=st, callback=cb)
+        states.append(before)
+    ref = []
+    for (u0, v0, p0), (us, vs) in zip(states, want):
+        ru = O.momentum_unrelaxed_residual_norm(True, n, n, dx, dy, 1.0, 1.0 / Re, u0, v0, p0, us, cond)
+        rv = O.momentum_unrelaxed_residual_norm(False, n, n, dx, dy, 1.0, 1.0 / Re, u0, v0, p0, vs, cond)
+        ref.append((ru, rv))
+    runs = []
+    for ranks, track in ((1, True), (3, True), (1, False)):
+        mesh, fluid = cavity(n, Re)
+        alg = nb.GpuSimpleSolver(mesh, fluid, make_ps("v"), nb.GpuJacobiMomentumSolver(n_jacobi_sweeps=k), alpha_p=0.3,
+                                 alpha_u=0.7, virtual_ranks=ranks, track_unrelaxed_residual=track)
+        alg.set_boundary_condition("top", "velocity", {"u": 1.0, "v": 0.0})
+        for b in ("bottom", "left", "right"):
+            alg.set_boundary_condition(b, "wall")
+        alg.push_fields()
+        recs = alg.iterate_resident(N, 0.0)
+        alg.pull_fields()
+        runs.append((alg.u.copy(), recs))
+    for recs in (runs[0][1], runs[1][1]):
+        got = [(r["u_unrelaxed_res"], r["v_unrelaxed_res"]) for r in recs]
+        np.testing.assert_allclose(got, ref, rtol=1e-9)
+    assert all(r["u_unrelaxed_res"] == 0.0 for r in runs[2][1])
+    np.testing.assert_array_equal(runs[0][0], runs[2][0])
+    np.testing.assert_array_equal(runs[0][0], runs[1][0])
