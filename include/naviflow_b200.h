@@ -346,6 +346,11 @@ int nf_bicgstab_solve_mg(nf_ctx*, const nf_grid*, const double* b, double* x, co
                          double atol, double rtol, int maxiter, int check_every, double* work, nf_mg* mg, int mg_cycles,
                          int mg_kind, nf_krylov_info* info_host);
 
+/* CG with the multigrid preconditioner of GeoMultigridPrecondCGSolver (pressure_solver/geo_multigrid_cg.py:125-191): scipy's
+ * cg with M = mg_cycles cycles from zero.  `mg` must have been set up with the same d_u, d_v; work: 5 same-shape arrays. */
+int nf_cg_solve_mg(nf_ctx*, const nf_grid*, const double* b, double* x, const double* d_u, const double* d_v, double atol,
+                   double rtol, int maxiter, double* work, nf_mg* mg, int mg_cycles, int mg_kind, nf_krylov_info* info_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,15 +7,15 @@ fallback: using a solver without the built library or without a CUDA device rais
 from .host import (BoundaryConditionManager, FluidProperties, SimulationResult, StructuredMesh, ghia_errors,
                    ghia_table)
 from .momentum import GpuJacobiMomentumSolver, GpuMatrixFreeMomentumSolver
-from .pressure import (GpuBiCGSTABSolver, GpuCGSolver, GpuGaussSeidelSolver, GpuJacobiSolver,
-                       GpuMultiGridSolver)
+from .pressure import (GpuBiCGSTABSolver, GpuCGSolver, GpuGaussSeidelSolver, GpuGeoMultigridPrecondCGSolver,
+                       GpuJacobiSolver, GpuMultiGridSolver)
 from .profiler import Profiler, load_profile
 from .simple import GpuPisoSolver, GpuSimplecSolver, GpuSimpleSolver, GpuSimplerSolver
 from .velocity import GpuVelocityUpdater
 
 __all__ = ["StructuredMesh", "FluidProperties", "BoundaryConditionManager", "SimulationResult", "ghia_errors",
            "ghia_table", "GpuJacobiMomentumSolver", "GpuJacobiSolver", "GpuGaussSeidelSolver",
-           "GpuMultiGridSolver", "GpuCGSolver", "GpuBiCGSTABSolver", "GpuVelocityUpdater", "GpuSimpleSolver",
+           "GpuMultiGridSolver", "GpuGeoMultigridPrecondCGSolver", "GpuCGSolver", "GpuBiCGSTABSolver", "GpuVelocityUpdater", "GpuSimpleSolver",
            "GpuPisoSolver", "GpuSimplerSolver", "GpuSimplecSolver", "GpuMatrixFreeMomentumSolver", "Profiler",
            "load_profile"]
 
@@ -33,7 +33,7 @@ def register_with_reference():
     except Exception:
         return []
     pairs = [(c, PressureSolver) for c in (GpuJacobiSolver, GpuGaussSeidelSolver, GpuMultiGridSolver, GpuCGSolver,
-                                           GpuBiCGSTABSolver)]
+                                           GpuBiCGSTABSolver, GpuGeoMultigridPrecondCGSolver)]
     pairs += [(c, MomentumSolver) for c in (GpuJacobiMomentumSolver, GpuMatrixFreeMomentumSolver)]
     pairs += [(GpuVelocityUpdater, VelocityUpdater)]
     pairs += [(c, BaseAlgorithm) for c in (GpuSimpleSolver, GpuPisoSolver, GpuSimplerSolver, GpuSimplecSolver)]

@@ -119,6 +119,8 @@ SIGNATURES = {
                                     C.POINTER(NfKrylovInfo)]),
     "nf_bicgstab_solve_mg": (C.c_int, [CTX, GP, P, P, P, P, C.c_double, C.c_double, C.c_int, C.c_int, P, C.c_void_p,
                                        C.c_int, C.c_int, C.POINTER(NfKrylovInfo)]),
+    "nf_cg_solve_mg": (C.c_int, [CTX, GP, P, P, P, P, C.c_double, C.c_double, C.c_int, P, C.c_void_p, C.c_int, C.c_int,
+                                 C.POINTER(NfKrylovInfo)]),
     "nf_momentum_links_u": (C.c_int, [CTX, GP, P, P, P, C.c_double, C.c_double, C.c_int, NfLinks, P]),
     "nf_momentum_links_v": (C.c_int, [CTX, GP, P, P, P, C.c_double, C.c_double, C.c_int, NfLinks, P]),
     "nf_momentum_jacobi": (C.c_int, [CTX, GP, C.c_int, NfLinks, P, P, C.c_int]),

@@ -71,6 +71,17 @@ __device__ __forceinline__ void ep_cg_update(KState* st, const double* out, int 
   st->beta = rr / st->rho_prev;
   if (sqrt(rr) < st->atol) { st->done = 1; st->info = 0; }
 }
+// preconditioned CG (scipy cg with M): the update only tests ||r||; rho = r.z and beta come from the reduction behind M
+__device__ __forceinline__ void ep_pcg_update(KState* st, const double* out, int it) {
+  st->rr = out[0];
+  st->iters = it + 1;
+  if (sqrt(out[0]) < st->atol) { st->done = 1; st->info = 0; }
+}
+__device__ __forceinline__ void ep_pcg_rz(KState* st, const double* out, int first) {
+  st->rho_prev = st->rho;
+  st->rho = out[0];
+  st->beta = first ? 0.0 : st->rho / st->rho_prev;
+}
 __device__ __forceinline__ void ep_bi_v(KState* st, const double* out, int it) {
   const double rv = out[0];
   if (rv == 0.0) { st->done = 1; st->info = -11; st->iters = it; }
@@ -189,7 +200,24 @@ __global__ void k_cg_update(nf_grid g, double* __restrict__ x, double* __restric
       acc[0] += rn * rn;
     }
   }
-  if (nf_block_reduce_store<1>(acc, partials, ticket, out) && !defer) ep_cg_update(st, out, it);
+  if (nf_block_reduce_store<1>(acc, partials, ticket, out) && defer != 1) {  // defer -1: preconditioned recurrence
+    if (defer == -1) ep_pcg_update(st, out, it); else ep_cg_update(st, out, it);
+  }
+}
+
+// rho = r.z behind the preconditioner application (preconditioned CG); epilogue beta = rho / rho_prev
+__global__ void k_pcg_rz(nf_grid g, const double* __restrict__ r, const double* __restrict__ z, KState* st, int first,
+                         double* partials, unsigned int* ticket, double* out) {
+  if (st->done) return;
+  double acc[1] = {0.0};
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < g.ny) {
+    NF_ROWLOOP(g, i) {
+      const size_t k = nf_idx(g, i, j);
+      acc[0] += r[k] * z[k];
+    }
+  }
+  if (nf_block_reduce_store<1>(acc, partials, ticket, out)) ep_pcg_rz(st, out, first);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -361,6 +389,50 @@ extern "C" int nf_cg_solve(nf_ctx* ctx, const nf_grid* g, const double* b, doubl
 }
 
 int nfi_mg_apply(nf_mg* mg, const double* rhs, double* out, int cycles, int kind);
+
+// CG with the multigrid preconditioner of GeoMultigridPrecondCGSolver (pressure_solver/geo_multigrid_cg.py:125-191):
+// scipy's cg(A, b, x0 = 0, M, atol) statement by statement -- ||r|| < atol test, z = M r (mg_cycles cycles on A y = r from
+// y = 0), rho = r.z, p = z + (rho / rho_prev) p, q = A p, alpha = rho / p.q, x += alpha p, r -= alpha q.  The reference
+// multiplies with the assembled matrix (coeff_matrix.py), which equals the matrix-free operator to rounding (SURVEY 5a = 5b).
+// The host polls the device-side stopping flag once per iteration (the preconditioner is a sequence of launches that must
+// not be issued for nothing).  work: 5 same-shape arrays.
+extern "C" int nf_cg_solve_mg(nf_ctx* ctx, const nf_grid* g, const double* b, double* x, const double* d_u,
+                              const double* d_v, double atol, double rtol, int maxiter, double* work, nf_mg* mg,
+                              int mg_cycles, int mg_kind, nf_krylov_info* info) {
+  NF_GRID_OK(ctx, g);
+  NF_REQUIRE(ctx, b && x && d_u && d_v && work && mg, "NULL argument");
+  NF_REQUIRE(ctx, maxiter >= 0 && mg_cycles >= 1 && mg_kind >= 0 && mg_kind <= 2, "bad iteration arguments");
+  const size_t n = (size_t)(g->nx + 1) * g->ld;
+  double* r = work;
+  double* pbuf[2] = {work + n, work + 2 * n};
+  double* q = work + 3 * n;
+  double* z = work + 4 * n;
+  KState *st, *hst;
+  krylov_state(ctx, &st, &hst);
+  NfLaunch2D l = nf_launch_reduce(g->ge - g->gb, g->ny);
+  k_krylov_init<<<l.grid, l.block, 0, ctx->stream>>>(*g, b, r, nullptr, x, st, atol, rtol, 0, ctx->partials,
+                                                     ctx->ticket, ctx->scalars);
+  NF_LAUNCH_CHECK(ctx);
+  NF_TRY(krylov_poll(ctx, st, hst));
+  int cur = 0;
+  for (int it = 0; it < maxiter && !hst->done; ++it) {
+    NF_TRY(nfi_mg_apply(mg, r, z, mg_cycles, mg_kind));
+    k_pcg_rz<<<l.grid, l.block, 0, ctx->stream>>>(*g, r, z, st, it == 0, ctx->partials, ctx->ticket, ctx->scalars);
+    NF_LAUNCH_CHECK(ctx);
+    // p = z + beta p (k_cg_pq takes z in the place of r), q = A p, alpha = rho / p.q
+    k_cg_pq<<<l.grid, l.block, 0, ctx->stream>>>(*g, z, pbuf[cur], pbuf[cur ^ 1], q, d_u, d_v, st, it == 0, 0, 0,
+                                                 ctx->partials, ctx->ticket, ctx->scalars);
+    NF_LAUNCH_CHECK(ctx);
+    cur ^= 1;
+    k_cg_update<<<l.grid, l.block, 0, ctx->stream>>>(*g, x, r, pbuf[cur], q, st, it, -1, ctx->partials, ctx->ticket,
+                                                     ctx->scalars);
+    NF_LAUNCH_CHECK(ctx);
+    NF_TRY(krylov_poll(ctx, st, hst));
+  }
+  krylov_finish(hst, maxiter, info);
+  return NF_OK;
+}
+
 
 static int bicgstab_impl(nf_ctx* ctx, const nf_grid* g, const double* b, double* x, const double* d_u, const double* d_v,
                          double atol, double rtol, int maxiter, int check_every, double* work, nf_mg* mg, int mg_cycles,

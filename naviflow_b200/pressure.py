@@ -371,3 +371,54 @@ class GpuBiCGSTABSolver(_KrylovBase):
     """MatrixFreeBiCGSTABSolver twin (scipy ``bicgstab`` operation order)."""
     _fn = "nf_bicgstab_solve"
     _nwork = 5
+
+
+class GpuGeoMultigridPrecondCGSolver(_GpuPressureBase):
+    """Twin of ``GeoMultigridPrecondCGSolver`` (pressure_solver/geo_multigrid_cg.py:16-258): scipy's ``cg`` with M =
+    ``mg_cycles`` multigrid cycles from zero, ``atol = tolerance`` (scipy's default ``rtol = 1e-5`` governs as well).  Same
+    constructor and, like the reference, ``solve`` returns the bare ``p'`` array (it does not plug into the outer loops,
+    which expect ``(p', info)``).  The reference's default ``mg_cycle_type='f'`` is not a cycle type its MultiGridSolver
+    knows (multigrid.py:96-99): the ValueError is raised here at the same place; a V-cycle needs a ``smoother`` object."""
+
+    def __init__(self, tolerance=1e-5, max_iterations=500, mg_pre_smoothing=3, mg_post_smoothing=2, mg_cycles=1,
+                 mg_cycle_type="f", mg_cycle_type_buildup="w", mg_max_cycles_buildup=1, mg_coarsest_grid_size=7,
+                 mg_restriction_method="restrict_inject", mg_interpolation_method="interpolate_cubic", smoother=None,
+                 device=None):
+        super().__init__(tolerance, max_iterations, device)
+        self.inner_iterations = []
+        self.mg_cycles = mg_cycles
+        self.mg_precond = GpuMultiGridSolver(
+            smoother=smoother, tolerance=tolerance * 0.1, max_iterations=1, pre_smoothing=mg_pre_smoothing,
+            post_smoothing=mg_post_smoothing, cycle_type=mg_cycle_type, cycle_type_buildup=mg_cycle_type_buildup,
+            max_cycles_buildup=mg_max_cycles_buildup, coarsest_grid_size=mg_coarsest_grid_size,
+            restriction_method=mg_restriction_method, interpolation_method=mg_interpolation_method, device=device)
+        self.omega = getattr(smoother, "omega", 1.0) if smoother else 1.0
+
+    def solve(self, mesh, u_star, v_star, d_u, d_v, p_star):
+        nx, ny, dx, dy, length, height = mesh_scalars(mesh)
+        ctx = self.ctx
+        torch = ctx.torch
+        g, bd, du, dv = self._stage(nx, ny, dx, dy, 1.0, u_star, v_star, d_u, d_v)
+        x = ctx.empty(nx, ny)
+        work = torch.zeros((5 * (nx + 1), pad_ld(ny)), dtype=torch.float64, device=x.device)
+        info = NfKrylovInfo()
+        mg = self.mg_precond._hierarchy(nx, ny, length, height)
+        ctx.check(ctx.lib.nf_mg_setup(mg, ptr(du), ptr(dv)), "nf_mg_setup")
+        ctx.check(ctx.lib.nf_cg_solve_mg(ctx.handle, C.byref(g), ptr(bd), ptr(x), ptr(du), ptr(dv), float(self.tolerance), 1e-5,
+                                         int(self.max_iterations), ptr(work), mg, int(self.mg_cycles),
+                                         _CYCLE[self.mg_precond.cycle_type], C.byref(info)), "nf_cg_solve_mg")
+        self.last_info = info
+        self.inner_iterations.append(info.iterations)
+        self.inner_iterations_history.append(info.iterations)
+        self.total_inner_iterations += info.iterations
+        if info.info != 0:
+            print(f"Warning: Geo-Multigrid Preconditioned CG did not converge, info={info.info}")
+        return ctx.download(x, nx, ny)
+
+    def get_solver_info(self):
+        return {"name": "GeoMultigridPrecondCGSolver", "inner_iterations_history": self.inner_iterations,
+                "total_inner_iterations": sum(self.inner_iterations), "convergence_rate": None,
+                "solver_specific": {"method": "conjugate_gradient", "preconditioner": "geometric_multigrid",
+                                    "pre_smoothing": self.mg_precond.pre_smoothing,
+                                    "post_smoothing": self.mg_precond.post_smoothing,
+                                    "cycle_type": self.mg_precond.cycle_type}}

@@ -345,6 +345,28 @@ def mg_lex_kats(R):
 RECT_CASES = ((40, 24, 100, 5, 10, "rbsor"), (24, 40, 400, 3, 8, "jacobi"), (33, 70, 100, 4, 6, "rbsor"))
 
 
+def cg_mg_kats(R):
+    """GeoMultigridPrecondCGSolver (geo_multigrid_cg.py) on seeded systems.  Its defaults do not construct
+    (mg_cycle_type='f' is rejected by MultiGridSolver, and the V-cycle needs a smoother object), so the runs name a cycle
+    type and pass the red-black smoother."""
+    from naviflow_oo.solver.pressure_solver.geo_multigrid_cg import GeoMultigridPrecondCGSolver
+    out = {}
+    for n, kind, cycles, seed in ((31, "v", 1, 931), (64, "v", 2, 964), (65, "w", 1, 965)):
+        s = synth_pressure_inputs(n, seed)
+        mesh = R.StructuredMesh(n, n, 1.0, 1.0)
+        sol = GeoMultigridPrecondCGSolver(tolerance=1e-7, max_iterations=200, mg_pre_smoothing=2, mg_post_smoothing=2,
+                                          mg_cycles=cycles, mg_cycle_type=kind, mg_restriction_method="restrict_full_weighting",
+                                          mg_interpolation_method="interpolate_linear",
+                                          smoother=R.GaussSeidelSolver(omega=0.8, method_type="red_black"))
+        p = _quiet(sol.solve, mesh, s["u_star"], s["v_star"], s["d_u"], s["d_v"], None)
+        key = f"n{n}_{kind}{cycles}"
+        for f in ("u_star", "v_star", "d_u", "d_v"):
+            out[f"{key}_{f}"] = s[f]
+        out[key + "_p"] = p
+        out[key + "_iterations"] = np.array([sol.inner_iterations[-1]])
+    return out
+
+
 def rect_runs(R):
     """SimpleSolver on rectangular cell grids (nx != ny, unit square: dx != dy) with the stationary pressure solvers."""
     out = {}
@@ -422,6 +444,7 @@ def main():
     np.savez_compressed(os.path.join(GOLD, "mg_lex.npz"), **mg_lex_kats(R))
     np.savez_compressed(os.path.join(GOLD, "bicgstab_mg.npz"), **bicgstab_mg_kats(R))
     np.savez_compressed(os.path.join(GOLD, "rect_runs.npz"), **rect_runs(R))
+    np.savez_compressed(os.path.join(GOLD, "cg_mg_kats.npz"), **cg_mg_kats(R))
     cf = R.cavity_flow.BenchmarkData
     tables = {}
     for Re in (100, 400, 1000, 3200, 5000, 7500, 10000):

@@ -1028,6 +1028,18 @@ def bicgstab_mg_pressure_solve(nx, ny, dx, dy, u_star, v_star, d_u, d_v, tol=1e-
 # ----------------------------------------------------------------------------
 # a14  velocity correction (velocity_solver/standard.py:10-69)
 # ----------------------------------------------------------------------------
+def cg_mg_pressure_solve(nx, ny, dx, dy, u_star, v_star, d_u, d_v, tol=1e-5, maxiter=500, kind="v", cycles=1, **mg):
+    """GeoMultigridPrecondCGSolver.solve (pressure_solver/geo_multigrid_cg.py:73-197): scipy cg on the pressure matrix with
+    M = `cycles` multigrid cycles from zero, x0 = 0, atol = tolerance (scipy's default rtol = 1e-5 governs as well).  The
+    reference multiplies with the assembled matrix whose first row is replaced by the identity (:116-123); the matrix-free
+    operator is the same matrix (SURVEY 5a = 5b).  Returns (p', iterations, info): the reference returns the bare array."""
+    b = continuity_rhs(nx, ny, dx, dy, 1.0, u_star, v_star)
+    mv = lambda z: apply_A(z, dx, dy, 1.0, d_u, d_v)
+    M = mg_preconditioner(dx, dy, d_u, d_v, kind=kind, cycles=cycles, **mg)
+    x, info, iters = cg(mv, b, atol=tol, maxiter=maxiter, M=M)
+    return x, iters, info
+
+
 def correct_velocity(nx, ny, u_star, v_star, p_prime, d_u, d_v, conditions):
     u = u_star.copy()
     v = v_star.copy()

@@ -1026,3 +1026,35 @@ def test_unrelaxed_momentum_residual_column_vs_oracle():
     assert all(r["u_unrelaxed_res"] == 0.0 for r in runs[2][1])
     np.testing.assert_array_equal(runs[0][0], runs[2][0])
     np.testing.assert_array_equal(runs[0][0], runs[1][0])
+
+
+@pytest.mark.parametrize("n,kind,cycles", [(31, "v", 1), (64, "v", 2), (65, "w", 1)])
+def test_multigrid_preconditioned_cg_vs_reference_golden(golden_dir, n, kind, cycles):
+    """GpuGeoMultigridPrecondCGSolver against the reference's GeoMultigridPrecondCGSolver run: the answers
+    agree to the stopping tolerance max(atol, 1e-5 ||b||) of the recurrence (the dot products are summed in another order),
+    the iteration counts within one; the first iterate of the recurrence against the oracle to rounding."""
+    import naviflow_b200 as nb
+    g = load(golden_dir, "cg_mg_kats.npz")
+    key = f"n{n}_{kind}{cycles}"
+    mesh, _ = cavity(n, 1000)
+    mk = lambda it: nb.GpuGeoMultigridPrecondCGSolver(
+        tolerance=1e-7, max_iterations=it, mg_pre_smoothing=2, mg_post_smoothing=2, mg_cycles=cycles, mg_cycle_type=kind,
+        mg_restriction_method="restrict_full_weighting", mg_interpolation_method="interpolate_linear",
+        smoother=nb.GpuGaussSeidelSolver(omega=0.8, method_type="red_black"))
+    sol = mk(200)
+    p = sol.solve(mesh, g[key + "_u_star"], g[key + "_v_star"], g[key + "_d_u"], g[key + "_d_v"], None)
+    assert isinstance(p, np.ndarray) and p.shape == (n, n)   # bare array like the reference
+    assert sol.last_info.info == 0 and abs(sol.last_info.iterations - int(g[key + "_iterations"][0])) <= 1
+    dx, dy = O.mesh_spacing(n, n)
+    b = O.continuity_rhs(n, n, dx, dy, 1.0, g[key + "_u_star"], g[key + "_v_star"])
+    tol = max(1e-7, 1e-5 * np.linalg.norm(b))
+    r = b - O.apply_A(p, dx, dy, 1.0, g[key + "_d_u"], g[key + "_d_v"])
+    assert np.linalg.norm(r) < 2 * tol
+    assert rel(p, g[key + "_p"]) < 1e-3
+    one = mk(2)
+    p2 = one.solve(mesh, g[key + "_u_star"], g[key + "_v_star"], g[key + "_d_u"], g[key + "_d_v"], None)
+    x2, _, _ = O.cg_mg_pressure_solve(n, n, dx, dy, g[key + "_u_star"], g[key + "_v_star"], g[key + "_d_u"], g[key + "_d_v"],
+                                      tol=1e-7, maxiter=2, kind=kind, cycles=cycles, omega=0.8, pre=2, post=2)
+    assert rel(p2, x2) < 1e-10
+    with pytest.raises(ValueError):
+        nb.GpuGeoMultigridPrecondCGSolver()   # the reference's defaults do not construct either (cycle type 'f')

@@ -297,3 +297,16 @@ def test_simplec_loop_golden(golden_dir, n, Re, k, N, name):
     for hk in ("total", "momentum", "pressure"):
         np.testing.assert_allclose(h[hk], g[f"{key}_{hk}"], rtol=1e-9, atol=1e-15)
     assert float(g[key + "_alpha_p"][0]) == 0.2
+
+
+@pytest.mark.parametrize("n,kind,cycles", [(31, "v", 1), (64, "v", 2), (65, "w", 1)])
+def test_multigrid_preconditioned_cg_golden(golden_dir, n, kind, cycles):
+    """GeoMultigridPrecondCGSolver (geo_multigrid_cg.py:73-197) -- scipy cg with M = multigrid cycles --
+    against the reference's own output: same iteration count, p' to rounding."""
+    g = load(golden_dir, "cg_mg_kats.npz")
+    key = f"n{n}_{kind}{cycles}"
+    dx, dy = O.mesh_spacing(n, n)
+    x, its, info = O.cg_mg_pressure_solve(n, n, dx, dy, g[key + "_u_star"], g[key + "_v_star"], g[key + "_d_u"], g[key + "_d_v"],
+                                          tol=1e-7, maxiter=200, kind=kind, cycles=cycles, omega=0.8, pre=2, post=2)
+    assert info == 0 and its == int(g[key + "_iterations"][0])
+    close(x, g[key + "_p"], 1e-12)

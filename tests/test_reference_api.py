@@ -44,6 +44,10 @@ def _pairs():
         (nb.GpuGaussSeidelSolver, R.GaussSeidelSolver, ["__init__", "solve", "get_solver_info"]),
         (nb.GpuJacobiSolver, R.JacobiSolver, ["__init__", "solve", "get_solver_info"]),
         (nb.GpuBiCGSTABSolver, R.MatrixFreeBiCGSTABSolver, ["__init__", "solve", "get_solver_info"]),
+        (nb.GpuGeoMultigridPrecondCGSolver,
+         __import__("naviflow_oo.solver.pressure_solver.geo_multigrid_cg",
+                    fromlist=["GeoMultigridPrecondCGSolver"]).GeoMultigridPrecondCGSolver,
+         ["__init__", "solve", "get_solver_info"]),
         (nb.GpuJacobiMomentumSolver, R.JacobiMatrixMomentumSolver, ["__init__", "solve_u_momentum", "solve_v_momentum"]),
         (nb.GpuMatrixFreeMomentumSolver, R.MatrixFreeMomentumSolver, ["__init__", "solve_u_momentum", "solve_v_momentum"]),
         (nb.GpuVelocityUpdater, R.StandardVelocityUpdater, ["__init__", "update_velocity"]),
@@ -87,7 +91,7 @@ def test_virtual_subclass_registration():
     import naviflow_b200 as nb
     RL.load()
     pairs = nb.register_with_reference()
-    assert len(pairs) == 12
+    assert len(pairs) == 13
     from naviflow_oo.solver.pressure_solver.base_pressure_solver import PressureSolver
     from naviflow_oo.solver.Algorithms.base_algorithm import BaseAlgorithm
     assert issubclass(nb.GpuMultiGridSolver, PressureSolver) and issubclass(nb.GpuSimpleSolver, BaseAlgorithm)
