@@ -213,6 +213,9 @@ struct nf_smooth_extra {
   double* coarse_x_zero = nullptr;  // mode 2, optional: coarse iterate to be zeroed cell by cell along with the restriction
                                     // (the cycle recurses from a zero guess: saves the fill launch on unsplit levels)
   double* out = nullptr;
+  const double* prolong_c = nullptr;  // modes 0 / 1, optional (streaming kernel only): the launch smooths p + P(prolong_c),
+  nf_grid prolong_gc;                 // the bilinear prolongation of the coarse iterate on prolong_gc (saves the prolongation pass)
+  bool prolong_fused = false;
   bool fused = false;
   double* in_norm_out = nullptr;
   bool in_norm_fused = false;
@@ -229,3 +232,5 @@ int nfi_rbsor_stream(nf_ctx*, const nf_grid*, const double* pin, double* pout, c
                      const double* d_v, const double* inv, double omega, int ns, int mode, const nf_smooth_extra* extra,
                      bool* used);
 bool nfi_rbsor_stream_enabled(const nf_grid* g);
+bool nfi_rbsor_can_fuse_prolong(const nf_grid* g, int n_sweeps, bool has_inv);
+void nfi_prolong_block_extent(const nf_grid* gc, const nf_grid* gf, int* nI, int* nJ);

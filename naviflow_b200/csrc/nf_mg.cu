@@ -607,8 +607,20 @@ static int mg_smooth(nf_mg* mg, int l, int n, nf_smooth_extra* extra = nullptr /
       }
       for (int k = 0; k < nl; ++k) {
         const nf_grid g = L.geom.grid(team->local[k]);
+        // the fused prolongation rides on the FIRST launch of the call, the residual work on the LAST one
+        const bool first = (left == n), last = (left == ns);
+        nf_smooth_extra ex1;
+        nf_smooth_extra* pe = nullptr;
+        if (extra && (last || (first && extra[k].prolong_c))) {
+          ex1 = extra[k];
+          if (!first) ex1.prolong_c = nullptr;
+          if (!last) { ex1.mode = 0; ex1.in_norm_out = nullptr; }
+          pe = &ex1;
+        }
         NF_TRY(nfi_rbsor_fused_x(ctx, &g, &L.s[k].x, &L.s[k].x2, L.s[k].b, L.s[k].d_u, L.s[k].d_v, L.s[k].inv,
-                                 mg->cfg.omega, ns, (extra && left == ns) ? &extra[k] : nullptr));
+                                 mg->cfg.omega, ns, pe));
+        if (pe && last) { extra[k].fused = ex1.fused; extra[k].in_norm_fused = ex1.in_norm_fused; }
+        if (pe && first) extra[k].prolong_fused = ex1.prolong_fused;
       }
       if (timed) {
         cudaEventRecord(mg->ev[mg->ev_used + 1], ctx->stream);
@@ -758,15 +770,28 @@ static int mg_cycle(nf_mg* mg, int l, int kind, bool want_norm = false, bool* no
   const int reps = (kind == 1) ? 2 : 1;
   for (int rep = 0; rep < reps; ++rep)
     NF_TRY(mg_cycle(mg, l + 1, kind, false, nullptr, 0, false, nullptr, /*from_zero=*/rep == 0));
-  NF_TRY(mg_prolong(mg, l, mg->cfg.interpolation, 1));
   std::vector<nf_smooth_extra> post(nl);
   const bool want_post = want_norm && mg->cfg.smoother == 0;
-  if (want_post)
+  // x += P x_coarse (multigrid.py:405-415): a pass of its own, or -- bilinear prolongation, streaming smoother -- added
+  // to the iterate on the way into the first post-smoothing launch
+  bool fuse_prolong = mg->cfg.smoother == 0 && mg->cfg.interpolation == 0;
+  for (int k = 0; k < nl && fuse_prolong; ++k) {
+    const nf_grid g = L.geom.grid(team->local[k]);
+    fuse_prolong = nfi_rbsor_can_fuse_prolong(&g, mg->cfg.post, L.s[k].inv != nullptr);
+  }
+  NF_TRY(mg_prolong(mg, l, mg->cfg.interpolation, fuse_prolong ? 2 : 1));  // 2: only the strips outside the block rule
+  if (want_post || fuse_prolong)
     for (int k = 0; k < nl; ++k) {
-      post[k].mode = 1;
-      post[k].out = mg->scal[k];
+      if (want_post) {
+        post[k].mode = 1;
+        post[k].out = mg->scal[k];
+      }
+      if (fuse_prolong) {
+        post[k].prolong_c = C.s[k].x;
+        post[k].prolong_gc = C.geom.grid(team->local[k]);
+      }
     }
-  NF_TRY(mg_smooth(mg, l, mg->cfg.post, want_post ? post.data() : nullptr));
+  NF_TRY(mg_smooth(mg, l, mg->cfg.post, (want_post || fuse_prolong) ? post.data() : nullptr));
   if (norm_fused) {
     bool all = want_post;
     for (int k = 0; k < nl; ++k) all = all && post[k].fused;

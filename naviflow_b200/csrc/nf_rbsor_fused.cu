@@ -697,6 +697,14 @@ bool nfi_rbsor_stream_enabled(const nf_grid* g) {
   return g->nx >= min_rows && (g->ge - g->gb) >= 16 && (g->gb % 2) == 0 && (g->ld % 2) == 0;
 }
 
+// Can a smoothing call of n_sweeps on this level take the prolongation of the coarse correction into its first launch?
+// (streaming kernel, a 3-sweep first launch; NF_MG_PROLONG_FUSED=0 switches it off)
+bool nfi_rbsor_can_fuse_prolong(const nf_grid* g, int n_sweeps, bool has_inv) {
+  const char* env = getenv("NF_MG_PROLONG_FUSED");
+  if (env && env[0] == '0') return false;
+  return has_inv && n_sweeps >= 3 && nfi_rbsor_stream_enabled(g);
+}
+
 // inv (optional): precomputed 1/aP of this level (nfi_inv_diag); NULL = divide inside the kernel
 int nfi_rbsor_fused_x(nf_ctx* ctx, const nf_grid* g, double** p, double** palt, const double* b, const double* d_u,
                       const double* d_v, const double* inv, double omega, int n_sweeps, nf_smooth_extra* extra) {
@@ -736,12 +744,21 @@ int nfi_rbsor_fused_x(nf_ctx* ctx, const nf_grid* g, double** p, double** palt, 
     }
     // streaming (wavefront) kernel (nf_rbsor_stream.cu) on large levels; its fused modes ride on 3-sweep launches and do not
     // deliver the input norms (the multigrid driver then runs the classic convergence test behind the post-smoother)
+    const bool want_prl = extra && extra->prolong_c != nullptr && left == n_sweeps;  // rides on the FIRST launch
     if (nfi_rbsor_stream_enabled(g) && inv) {
       int smode = 0;
       if (extra && extra->mode != 0 && allow_extra && left == ns && ns == 3 && (g->gb % 2) == 0) smode = extra->mode;
-      NF_TRY(nfi_rbsor_stream(ctx, g, *p, *palt, b, d_u, d_v, inv, omega, ns, smode, extra, &used));
+      nf_smooth_extra sx;
+      if (extra) sx = *extra;
+      if (!want_prl) sx.prolong_c = nullptr;
+      NF_TRY(nfi_rbsor_stream(ctx, g, *p, *palt, b, d_u, d_v, inv, omega, ns, smode, extra ? &sx : nullptr, &used));
       if (used && smode != 0) extra->fused = true;
+      if (used && want_prl) extra->prolong_fused = true;
       if (used) mode = 0;
+    }
+    if (want_prl && !used) {
+      ctx->err = "fused prolongation was requested for a launch the streaming smoother does not serve";
+      return NF_ERR_UNSUPPORTED;
     }
     if (use_tma && !used) {  // persistent TMA pipeline: pays off once every SM gets several tiles
       if (ns == 3) st = launch_tma_any<3>(ctx, g, *p, *palt, b, d_u, d_v, inv, omega, mode, ex, &used);

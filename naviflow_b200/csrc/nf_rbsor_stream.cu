@@ -42,8 +42,14 @@ constexpr int SW = 64;    // strip width in cells
 constexpr int RB = 4, NSTG = 2;
 static_assert(RB * NSTG == 8, "ring length must equal the phase count");
 constexpr int SG_P = 0, SG_DU = RB * 512, SG_B = 2 * RB * 512, SG_INV = 3 * RB * 512, SG_DV = 4 * RB * 512;  // stage layout
-constexpr int SG_BYTES = ((4 * RB * 512 + RB * 66 * 8 + 127) / 128) * 128;
+constexpr int SG_CX = ((4 * RB * 512 + RB * 66 * 8 + 127) / 128) * 128;  // coarse iterate (fused prolongation): 3 rows x 34
+// coarse rows / columns of a stage's box: 34 columns are needed; the box starts on an EVEN column (measured on B200: a
+// fp64 box whose inner start coordinate is odd -- a byte offset that is not a multiple of 16 -- raises "illegal instruction",
+// tools/dev/tma_box_test2.cu), hence 36
+constexpr int CXR = RB / 2 + 1, CXC = SW / 2 + 4;
+constexpr int SG_BYTES = ((SG_CX + CXR * CXC * 8 + 127) / 128) * 128;
 constexpr unsigned SG_TX = RB * (4 * 512 + 66 * 8);
+constexpr unsigned SG_TX_CX = CXR * CXC * 8;
 
 __device__ __forceinline__ unsigned s_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -78,6 +84,20 @@ struct Job {
   int j0;          // global column of lane 0's first cell (even, may be negative)
 };
 
+// Work fused into a launch (see stream_step2 / stream_load)
+struct StreamExtra {
+  nf_grid gc;          // EXTRA 2: coarse grid and its right-hand side
+  double* coarse_b;
+  double* coarse_x0;   // EXTRA 2, optional: coarse iterate, zeroed along with the restriction
+  nf_grid pgc;         // PRL: grid and array of the coarse iterate whose bilinear prolongation is added to p on the way in
+  const double* pcx;
+  int prl_nI, prl_nJ;  // PRL: the block rule covers fine rows 1 .. 2 nI, columns 1 .. 2 nJ; the other cells (ring, trailing
+                       // cells of even-sized grids) were prolonged by the strips launch of k_prolong_linear
+  double* partials;    // EXTRA 1: per-job partial sums, ticket, result (sum r^2, sum b^2)
+  unsigned int* ticket;
+  double* out;
+};
+
 // Domain edges.  The reference zeroes the links of a boundary cell across its edge direction but keeps the reverse links
 // (matrix_free.py:63-84), which breaks the face sharing at exactly four places: row 0's aE, row nx-1's aW, column 0's aN,
 // column ny-1's aS.  Everything else is settled when a row is loaded: the faces that only boundary or virtual cells use
@@ -92,11 +112,37 @@ struct ColFlags {
 
 // Loads row s of p and d_u (-> slot SN) and the coefficient rows of row s-1 (-> slot SN-1) from row RW of a stage.
 // p of the second cell goes to *pB_out (the double step commits it late, see below).
-template <int SN, int RW, bool ROWB, bool COLB>
+// PRL: p_in = x + P x_coarse (interpolate_linear, multigrid_helpers.py:116-186; the prolongation + correction of the V-cycle,
+// multigrid.py:405-415, fused into the post-smoother's load -- saves an 18 B/cell pass): the block rule of
+// k_prolong_linear evaluated from the coarse rows the stage carries.  The cells the block rule does not cover (ring copy,
+// trailing cells of even-sized grids) are prolonged beforehand by the strips launch of k_prolong_linear (add = 2).
+template <int SN, int RW, bool ROWB, bool COLB, bool PRL>
 __device__ __forceinline__ void stream_load(Win& W, const nf_grid& g, int s, int lane, const unsigned char* stage,
-                                            const ColFlags& cf, double* pB_out) {
+                                            const ColFlags& cf, double* pB_out, const StreamExtra& ex, int gjA) {
   constexpr int SC = (SN + 7) & 7;
-  const double2 pp = *reinterpret_cast<const double2*>(stage + SG_P + RW * 512 + 16 * lane);
+  double2 pp = *reinterpret_cast<const double2*>(stage + SG_P + RW * 512 + 16 * lane);
+  if (PRL) {
+    double vA, vB;
+    // the box starts at the even column <= j0/2 - 1; lane l needs coarse columns j0/2 - 1 + l and + l + 1
+    const double* cx = reinterpret_cast<const double*>(stage + SG_CX) + (((gjA >> 1) - lane - 1) & 1);
+    if ((RW & 1) == 0) {  // even fine row 2I+2: between coarse rows I = RW/2 and I+1 of the stage's box
+      const double c00 = cx[(RW / 2) * CXC + lane], c01 = cx[(RW / 2) * CXC + lane + 1];
+      const double c10 = cx[(RW / 2 + 1) * CXC + lane], c11 = cx[(RW / 2 + 1) * CXC + lane + 1];
+      vA = 0.25 * (((c00 + c10) + c01) + c11);
+      vB = 0.5 * (c01 + c11);
+    } else {              // odd fine row 2I+1: coarse row I = (RW+1)/2
+      const double c00 = cx[((RW + 1) / 2) * CXC + lane], c01 = cx[((RW + 1) / 2) * CXC + lane + 1];
+      vA = 0.5 * (c00 + c01);
+      vB = c01;
+    }
+    if (ROWB || COLB) {  // cells outside the block rule (and outside the domain) get nothing here
+      const bool rin = s >= 1 && s <= 2 * ex.prl_nI;
+      if (!(rin && gjA >= 1 && gjA <= 2 * ex.prl_nJ)) vA = 0.0;
+      if (!(rin && gjA + 1 >= 1 && gjA + 1 <= 2 * ex.prl_nJ)) vB = 0.0;
+    }
+    pp.x = pp.x + vA;
+    pp.y = pp.y + vB;
+  }
   const double2 uu = *reinterpret_cast<const double2*>(stage + SG_DU + RW * 512 + 16 * lane);
   const double2 bb = *reinterpret_cast<const double2*>(stage + SG_B + RW * 512 + 16 * lane);
   const double2 iv = *reinterpret_cast<const double2*>(stage + SG_INV + RW * 512 + 16 * lane);
@@ -165,14 +211,6 @@ __device__ __forceinline__ void stream_update(Win& W, const nf_grid& g, int r, d
 // b - A p of the lane's two cells of a FINAL row r (nf_Ap_cell's expression order: diag*p - E - W - N - S with the reference's
 // diagonal folding at the edges, matrix_free.py:63-121).  Faces are the raw ones (the faces outside the domain are zero
 // since the load); nS / nN = the in-row neighbours across the pair boundary.
-struct StreamExtra {
-  nf_grid gc;          // EXTRA 2: coarse grid and its right-hand side
-  double* coarse_b;
-  double* coarse_x0;   // EXTRA 2, optional: coarse iterate, zeroed along with the restriction
-  double* partials;    // EXTRA 1: per-job partial sums, ticket, result (sum r^2, sum b^2)
-  unsigned int* ticket;
-  double* out;
-};
 
 template <bool ROWB, bool COLB>
 __device__ __forceinline__ void stream_residual(const nf_grid& g, int r, const ColFlags& cf, double pWA, double pWB,
@@ -233,7 +271,7 @@ __device__ __forceinline__ void stream_pair(Win& W, const nf_grid& g, int s, dou
 //   1  sum (b - A p)^2, sum b^2 over the level (the multigrid convergence test, multigrid.py:185-240) -> acc[0..1]
 //   2  coarse_b = FW(b - A p) (multigrid.py:362-372 after the pre-smoothing); acc[0..1] carries the residual of the
 //      previous even row.  A double step finalises rows s-6 and s-5, so the residual rows s-7 and s-6 are complete.
-template <int PH, int NP, bool ROWB, bool COLB, int EXTRA>
+template <int PH, int NP, bool ROWB, bool COLB, int EXTRA, bool PRL>
 __device__ __forceinline__ void stream_step2(Win& W, const nf_grid& g, const Job& jb, int s, int lane, double omega,
                                              const unsigned char* stage, const ColFlags& cf, double* __restrict__ pout,
                                              double (&acc)[2], const StreamExtra& ex) {
@@ -245,16 +283,16 @@ __device__ __forceinline__ void stream_step2(Win& W, const nf_grid& g, const Job
   // rows s-8 (p) and s-7 (p of cell A, faces) leave the window with the loads below; the residual of row s-7 needs them
   double o8A = 0.0, o8B = 0.0, o7A = 0.0, o7fA = 0.0, o7fB = 0.0;
   if (EXTRA != 0) { o8A = W.pA[S0]; o8B = W.pB[S0]; o7A = W.pA[S1]; o7fA = W.fA[S1]; o7fB = W.fB[S1]; }
-  stream_load<S0, PH % RB, ROWB, COLB>(W, g, s, lane, stage, cf, &W.pB[S0]);  // slot of row s-8: free
+  const int c = 2 * lane;
+  const int gjA = jb.j0 + c;
+  stream_load<S0, PH % RB, ROWB, COLB, PRL>(W, g, s, lane, stage, cf, &W.pB[S0], ex, gjA);  // slot of row s-8: free
   // pB of row s+1 shares its slot with row s-7, which chain X still reads (W neighbour of its last update): committed below
-  stream_load<S1, (PH + 1) % RB, ROWB, COLB>(W, g, s + 1, lane, stage, cf, &pB_s1);
+  stream_load<S1, (PH + 1) % RB, ROWB, COLB, PRL>(W, g, s + 1, lane, stage, cf, &pB_s1, ex, gjA);
   double nbX[NP], nbY[NP];
 #pragma unroll
   for (int t = 0; t < NP; ++t) nbX[t] = __shfl_down_sync(0xffffffffu, W.pA[(PH + 15 - t) & 7], 1);  // rows s-1-t
   nbY[0] = __shfl_up_sync(0xffffffffu, W.pB[S0], 1);                                                // row s
   stream_pair<PH, 0, NP, ROWB, COLB>(W, g, s, omega, cf, nbX, nbY);
-  const int c = 2 * lane;
-  const int gjA = jb.j0 + c;
   if (EXTRA != 0) {
     constexpr int S2 = (PH + 2) & 7, S3 = (PH + 3) & 7;  // rows s-6, s-5
     double r7A, r7B, r6A, r6B;
@@ -309,7 +347,7 @@ __device__ __forceinline__ void stream_step2(Win& W, const nf_grid& g, const Job
 }
 
 // The march of one job.  COLB (first / last strip) is a property of the job; the row variant is chosen per group of 8 steps.
-template <int NP, bool COLB, int EXTRA, class Issue>
+template <int NP, bool COLB, int EXTRA, bool PRL, class Issue>
 __device__ __forceinline__ void stream_job(const nf_grid& g, const Job& jb, int lane, double omega, const unsigned char* ring,
                                            unsigned bar0, Issue& issue, double* __restrict__ pout, double (&acc)[2],
                                            const StreamExtra& ex) {
@@ -342,7 +380,7 @@ __device__ __forceinline__ void stream_job(const nf_grid& g, const Job& jb, int 
       while (!mbar_try(bar, ring_phase)) {}                                                         \
     }                                                                                               \
     const unsigned char* stage = ring + (PH / RB) * SG_BYTES;                                       \
-    stream_step2<PH, NP, ROWB, COLB, EXTRA>(W, g, jb, s, lane, omega, stage, cf, pout, acc, ex);   \
+    stream_step2<PH, NP, ROWB, COLB, EXTRA, PRL>(W, g, jb, s, lane, omega, stage, cf, pout, acc, ex); \
     if (((PH + 1) % RB) == RB - 1) { /* the stage is consumed: refill it for the steps 8 ahead */    \
       __syncwarp();                                                                                 \
       if (lane == 0 && s + 8 - (RB - 2) <= jb.s_last) issue(s + 8 - (RB - 2));                      \
@@ -351,8 +389,8 @@ __device__ __forceinline__ void stream_job(const nf_grid& g, const Job& jb, int 
 
   unsigned ring_phase = 0;
   for (int s8 = jb.r0;; s8 += 8, ring_phase ^= 1) {
-    // rows these 8 steps load or update: s8-NP .. s8+7
-    if (s8 - NP <= 0 || s8 + 7 >= g.nx - 1) {
+    // rows these 8 steps load or update: s8-NP .. s8+7 (PRL: the last two rows of an even-sized grid follow edge rules)
+    if (s8 - NP <= 0 || s8 + 7 >= g.nx - 1 - (PRL ? 2 : 0)) {
       NF_STREAM_STEP2(0, true) NF_STREAM_STEP2(2, true) NF_STREAM_STEP2(4, true) NF_STREAM_STEP2(6, true)
     } else {
       NF_STREAM_STEP2(0, false) NF_STREAM_STEP2(2, false) NF_STREAM_STEP2(4, false) NF_STREAM_STEP2(6, false)
@@ -363,6 +401,7 @@ __device__ __forceinline__ void stream_job(const nf_grid& g, const Job& jb, int 
 
 struct StreamMaps {
   CUtensorMap p, b, du, dv, inv;
+  CUtensorMap cx;  // PRL: coarse iterate, box CXR x CXC
 };
 
 // registers per thread the launch bounds leave (64 K registers per SM, allocated per warp in units of 8 per thread)
@@ -378,7 +417,7 @@ struct JobPlan {
   int jobs_inner, njobs;      // jobs_inner = n_inner * chunks of an inner strip
 };
 
-template <int NS, int WPC, int EXTRA>
+template <int NS, int WPC, int EXTRA, bool PRL>
 __global__ void __launch_bounds__(32 * WPC, 1) __maxnreg__(stream_maxreg(WPC))
 k_rbsor_stream(nf_grid g, const __grid_constant__ StreamMaps maps, double* __restrict__ pout, double omega, JobPlan plan,
                StreamExtra ex) {
@@ -428,7 +467,10 @@ k_rbsor_stream(nf_grid g, const __grid_constant__ StreamMaps maps, double* __res
   auto issue = [&](int s) {  // stage of steps s .. s+RB-1: rows s.. of p, d_u; rows s-1.. of d_v, b, 1/aP
     const int q = ((s - jb.r0) / RB) & (NSTG - 1);
     const unsigned bar = bar0 + 8 * q, dst = ring_u + q * SG_BYTES;
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(SG_TX) : "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(SG_TX + (PRL ? SG_TX_CX : 0u))
+                 : "memory");
+    if (PRL)  // coarse rows (s-2)/2 .. (s-2)/2 + RB/2 and columns j0/2 - 1 .. j0/2 + 32 (s, j0 even), from an even column
+      tma_row(dst + SG_CX, &maps.cx, ((jb.j0 >> 1) - 1) & ~1, ((s - 2) >> 1) - ex.pgc.row0, bar);
     tma_row(dst + SG_P, &maps.p, jb.j0, s - g.row0, bar);
     tma_row(dst + SG_DU, &maps.du, jb.j0, s - g.row0, bar);
     tma_row(dst + SG_B, &maps.b, jb.j0, s - 1 - g.row0, bar);
@@ -442,8 +484,8 @@ k_rbsor_stream(nf_grid g, const __grid_constant__ StreamMaps maps, double* __res
   }
 
   double acc[2] = {0.0, 0.0};
-  if (colb) stream_job<NP, true, EXTRA>(g, jb, lane, omega, ring, bar0, issue, pout, acc, ex);
-  else stream_job<NP, false, EXTRA>(g, jb, lane, omega, ring, bar0, issue, pout, acc, ex);
+  if (colb) stream_job<NP, true, EXTRA, PRL>(g, jb, lane, omega, ring, bar0, issue, pout, acc, ex);
+  else stream_job<NP, false, EXTRA, PRL>(g, jb, lane, omega, ring, bar0, issue, pout, acc, ex);
   if (EXTRA == 1) {
     // deterministic reduction: fixed tree inside the warp, one partial per job, the last job to arrive adds the partials in
     // job order
@@ -497,9 +539,10 @@ EncodeTiledFn stream_encoder() {
 
 struct MapKey {
   const void* base;
-  int rows, cols, ld, box_cols;
+  int rows, cols, ld, box_cols, box_rows;
   bool operator==(const MapKey& o) const {
-    return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_cols == o.box_cols;
+    return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_cols == o.box_cols &&
+           box_rows == o.box_rows;
   }
 };
 struct MapKeyHash {
@@ -509,22 +552,23 @@ struct MapKeyHash {
     h = h * 1000003u ^ (size_t)k.cols;
     h = h * 1000003u ^ (size_t)k.ld;
     h = h * 1000003u ^ (size_t)k.box_cols;
+    h = h * 1000003u ^ (size_t)k.box_rows;
     return h;
   }
 };
 
-bool row_map(CUtensorMap* out, const double* base, int rows, int cols, int ld, int box_cols) {
+bool row_map(CUtensorMap* out, const double* base, int rows, int cols, int ld, int box_cols, int box_rows = RB) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
   std::lock_guard<std::mutex> lock(mu);
-  const MapKey key{base, rows, cols, ld, box_cols};
+  const MapKey key{base, rows, cols, ld, box_cols, box_rows};
   auto it = cache.find(key);
   if (it != cache.end()) { *out = it->second; return true; }
   EncodeTiledFn enc = stream_encoder();
   if (!enc) return false;
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(double)};
-  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)RB};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUtensorMap m;
   if (enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), gdim, gstride, box, estr,
@@ -538,20 +582,21 @@ bool row_map(CUtensorMap* out, const double* base, int rows, int cols, int ld, i
 }
 
 // strips / chunks of a level: one job per warp slot of a single wave (148 SMs x WPC warps)
-template <int NS, int EXTRA>
+template <int NS, int EXTRA, bool PRL>
 JobPlan make_plan(const nf_grid* g, int slots) {
   constexpr int NP = 2 * NS, HL = EXTRA ? NP + 2 : NP, SCOLS = SW - 2 * HL;
   const int rows = g->ge - g->gb;
   const int nstrips = (g->ny + SCOLS - 1) / SCOLS;
   // strip k is an edge strip when its 64 columns (plus the d_v column to their right) reach column 0 or ny-1
-  int first_right = (g->ny - 1 - SW + HL + SCOLS - 1) / SCOLS;  // smallest k with k*SCOLS - HL + SW >= ny-1
+  // (PRL: the last two columns of an even-sized grid follow edge rules of the prolongation as well)
+  int first_right = (g->ny - 1 - (PRL ? 2 : 0) - SW + HL + SCOLS - 1) / SCOLS;  // smallest k with k*SCOLS - HL + SW >= ny-1
   if (first_right < 1) first_right = 1;
   if (first_right > nstrips) first_right = nstrips;
   JobPlan P;
   P.first_right = first_right;
   P.n_inner = first_right - 1;
   P.n_edge = nstrips - P.n_inner;
-  const double edge_cost = 1.12;  // relative cost of a COLB step
+  const double edge_cost = PRL ? 1.15 : 1.12;  // relative cost of a COLB step
   // the smallest chunk length (of the inner strips) whose jobs fit into one wave
   int best_li = -1, best_le = -1;
   for (int li = 8; li <= ((rows + 1) & ~1) + 2; li += 2) {
@@ -569,13 +614,13 @@ JobPlan make_plan(const nf_grid* g, int slots) {
   return P;
 }
 
-template <int NS, int WPC, int EXTRA>
+template <int NS, int WPC, int EXTRA, bool PRL>
 int launch_stream(nf_ctx* ctx, const nf_grid* g, const double* pin, double* pout, const double* b, const double* d_u,
                   const double* d_v, const double* inv, double omega, const StreamExtra& ex, bool* used) {
   constexpr int SMEM = WPC * NSTG * SG_BYTES + WPC * NSTG * 8;
   *used = false;
   if ((g->gb & 1) != 0) return NF_OK;  // odd origin (the phases assume even chunk starts): the caller falls back
-  const JobPlan plan = make_plan<NS, EXTRA>(g, NF_SM_COUNT * WPC);
+  const JobPlan plan = make_plan<NS, EXTRA, PRL>(g, NF_SM_COUNT * WPC);
   if (plan.njobs > NF_MAX_PARTIALS) return NF_OK;
   const int row_end = g->row1 > 0 ? g->row1 : g->nx + 1;
   const int stored_p = (row_end < g->nx ? row_end : g->nx) - g->row0;
@@ -585,14 +630,21 @@ int launch_stream(nf_ctx* ctx, const nf_grid* g, const double* pin, double* pout
       !row_map(&m.du, d_u, stored_u, g->ny, g->ld, SW) || !row_map(&m.dv, d_v, stored_p, g->ny + 1, g->ld, SW + 2) ||
       !row_map(&m.inv, inv, stored_p, g->ny, g->ld, SW))
     return NF_OK;
+  m.cx = m.p;
+  if (PRL) {
+    const nf_grid& c = ex.pgc;
+    const int c_end = c.row1 > 0 ? c.row1 : c.nx + 1;
+    const int c_rows = (c_end < c.nx ? c_end : c.nx) - c.row0;
+    if (!row_map(&m.cx, ex.pcx, c_rows, c.ny, c.ld, CXC, CXR)) return NF_OK;
+  }
   static bool attr_set = false;
   if (!attr_set) {
-    NF_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_rbsor_stream<NS, WPC, EXTRA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    NF_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_rbsor_stream<NS, WPC, EXTRA, PRL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             SMEM));
     attr_set = true;
   }
   const int grid = (plan.njobs + WPC - 1) / WPC;
-  k_rbsor_stream<NS, WPC, EXTRA><<<grid, 32 * WPC, SMEM, ctx->stream>>>(*g, m, pout, omega, plan, ex);
+  k_rbsor_stream<NS, WPC, EXTRA, PRL><<<grid, 32 * WPC, SMEM, ctx->stream>>>(*g, m, pout, omega, plan, ex);
   NF_LAUNCH_CHECK(ctx);
   *used = true;
   return NF_OK;
@@ -600,8 +652,9 @@ int launch_stream(nf_ctx* ctx, const nf_grid* g, const double* pin, double* pout
 
 }  // namespace
 
-// mode 0: plain; 1: + residual norms -> extra->out[0..1]; 2: + coarse_b = FW(b - A p) on extra->gc.  The fused modes exist
-// for 3-sweep launches; *used = false means nothing was launched (the caller takes another path).
+// mode 0: plain; 1: + residual norms -> extra->out[0..1]; 2: + coarse_b = FW(b - A p) on extra->gc.  extra->prolong_c: the
+// launch takes p + P(prolong_c) as its input (modes 0 and 1).  The fused work exists for 3-sweep launches; *used = false
+// means nothing was launched (the caller takes another path).
 int nfi_rbsor_stream(nf_ctx* ctx, const nf_grid* g, const double* pin, double* pout, const double* b, const double* d_u,
                      const double* d_v, const double* inv, double omega, int ns, int mode, const nf_smooth_extra* extra,
                      bool* used) {
@@ -610,15 +663,26 @@ int nfi_rbsor_stream(nf_ctx* ctx, const nf_grid* g, const double* pin, double* p
   StreamExtra ex;
   ex.gc = *g; ex.coarse_b = nullptr; ex.coarse_x0 = nullptr; ex.partials = ctx->partials; ex.ticket = ctx->ticket;
   ex.out = nullptr;
+  ex.pgc = *g; ex.pcx = nullptr;
+  ex.prl_nI = ex.prl_nJ = 0;
+  const bool prl = extra && extra->prolong_c != nullptr;
+  if (prl) {
+    if (ns != 3 || mode == 2) return NF_OK;
+    ex.pgc = extra->prolong_gc;
+    ex.pcx = extra->prolong_c;
+    nfi_prolong_block_extent(&ex.pgc, g, &ex.prl_nI, &ex.prl_nJ);
+  }
   if (mode != 0) {
     if (ns != 3 || !extra) return NF_OK;
     ex.gc = extra->gc; ex.coarse_b = extra->coarse_b; ex.coarse_x0 = extra->coarse_x_zero; ex.out = extra->out;
-    if (mode == 1) return launch_stream<3, 8, 1>(ctx, g, pin, pout, b, d_u, d_v, inv, omega, ex, used);
-    if (mode == 2) return launch_stream<3, 8, 2>(ctx, g, pin, pout, b, d_u, d_v, inv, omega, ex, used);
+    if (mode == 1 && prl) return launch_stream<3, 8, 1, true>(ctx, g, pin, pout, b, d_u, d_v, inv, omega, ex, used);
+    if (mode == 1) return launch_stream<3, 8, 1, false>(ctx, g, pin, pout, b, d_u, d_v, inv, omega, ex, used);
+    if (mode == 2) return launch_stream<3, 8, 2, false>(ctx, g, pin, pout, b, d_u, d_v, inv, omega, ex, used);
     return NF_OK;
   }
-  if (ns == 3) return launch_stream<3, 8, 0>(ctx, g, pin, pout, b, d_u, d_v, inv, omega, ex, used);
-  if (ns == 2) return launch_stream<2, 8, 0>(ctx, g, pin, pout, b, d_u, d_v, inv, omega, ex, used);
-  if (ns == 1) return launch_stream<1, 8, 0>(ctx, g, pin, pout, b, d_u, d_v, inv, omega, ex, used);
+  if (prl) return launch_stream<3, 8, 0, true>(ctx, g, pin, pout, b, d_u, d_v, inv, omega, ex, used);
+  if (ns == 3) return launch_stream<3, 8, 0, false>(ctx, g, pin, pout, b, d_u, d_v, inv, omega, ex, used);
+  if (ns == 2) return launch_stream<2, 8, 0, false>(ctx, g, pin, pout, b, d_u, d_v, inv, omega, ex, used);
+  if (ns == 1) return launch_stream<1, 8, 0, false>(ctx, g, pin, pout, b, d_u, d_v, inv, omega, ex, used);
   return NF_OK;
 }

@@ -245,7 +245,24 @@ int nfi_restrict_coeffs(nf_ctx* ctx, const nf_grid* gf, const double* d_u, const
   return NF_OK;
 }
 
+// Rows / columns the block rule of the bilinear prolongation covers on a fine grid: fine rows 1 .. 2 nI, columns 1 .. 2 nJ
+void nfi_prolong_block_extent(const nf_grid* gc, const nf_grid* gf, int* nI_out, int* nJ_out) {
+  int nI = 0, nJ = 0;
+  if (gf->nx > 3 && gf->ny > 3) {
+    nI = gc->nx - 1 < (gf->nx - 2) / 2 ? gc->nx - 1 : (gf->nx - 2) / 2;
+    nJ = gc->ny - 1 < (gf->ny - 2) / 2 ? gc->ny - 1 : (gf->ny - 2) / 2;
+    if (nI < 0) nI = 0;
+    if (nJ < 0) nJ = 0;
+    if (nI == 0 || nJ == 0) nI = nJ = 0;
+  }
+  *nI_out = nI;
+  *nJ_out = nJ;
+}
+
+// add = 2: only the thin strips outside the block rule (ring rows / columns, trailing cells of even-sized grids) are
+// prolonged and added -- the streaming smoother adds the block part on the way in (nf_rbsor_stream.cu, PRL)
 int nfi_prolong_linear(nf_ctx* ctx, const nf_grid* gc, const double* c, const nf_grid* gf, double* f, int add) {
+  const bool strips_only = (add == 2);
   // block rule valid for coarse I in [0, nI): needs c[I+1] and fine row 2I+2 <= m-2
   int nI = 0, nJ = 0;
   if (gf->nx > 3 && gf->ny > 3) {
@@ -260,7 +277,7 @@ int nfi_prolong_linear(nf_ctx* ctx, const nf_grid* gc, const double* c, const nf
   int I_hi = gf->ge / 2 < nI ? gf->ge / 2 : nI;
   if (I_lo > I_hi) I_lo = I_hi;
   const int gx = nJ > 0 ? (nJ + 31) / 32 : 1;
-  const int nby_fast = (nI > 0 && I_hi > I_lo) ? (I_hi - I_lo + 7) / 8 : 0;
+  const int nby_fast = (!strips_only && nI > 0 && I_hi > I_lo) ? (I_hi - I_lo + 7) / 8 : 0;
   const long long strip = (long long)(1 + gf->nx - (2 * nI + 1)) * gf->ny + (long long)(1 + gf->ny - (2 * nJ + 1)) * (2 * nI);
   const int nby_strip = (int)((strip + (long long)gx * 256 - 1) / ((long long)gx * 256));
   dim3 grid(gx, nby_fast + nby_strip, 1), block(32, 8, 1);
