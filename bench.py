@@ -352,14 +352,17 @@ def main():
         if os.environ.get("NF_RBSOR_EXTRA", "1") != "0":
             # inside the V-cycle the finest-level pre-smoothing launch also carries the residual + full-weighting
             # restriction (34 B/cell) and the post-smoothing launch the residual norms of the convergence test (40 B/cell)
-            # on top of 3 sweeps (120 B/cell) each: (154 + 160) / 2 = 157 B/cell per launch on average (SURVEY 8d figures)
-            alg_bytes = 157.0 * n * n
+            # on top of 3 sweeps (120 B/cell) each: (154 + 160) / 2 = 157 B/cell per launch on average
+            # -- and, with the streaming smoother, the bilinear prolongation + correction of the cycle (18 B/cell, fused
+            # into the post-smoother's load): (154 + 178) / 2 = 166 B/cell per launch on average (SURVEY 8d figures)
+            fused_prolong = os.environ.get("NF_MG_PROLONG_FUSED", "1") != "0" and os.environ.get("NF_RBSOR_STREAM") is None
+            alg_bytes = (166.0 if fused_prolong else 157.0) * n * n
             tr = [variants.get(k, {}).get("dram_bytes_per_launch") for k in ("pre_restrict", "post_norms")]
             traffic = (tr[0] + tr[1]) / 2.0 if all(tr) else None
         achieved = alg_bytes / (ms_launch * 1e-3) / 1e9
     roofline = {"kernel": "k_rbsor_stream<3> (finest level: 3 red-black SOR sweeps = 6 colour passes per launch, streaming "
                           "wavefront form; the pre-smoothing launch also carries the V-cycle's residual + restriction, the "
-                          "post-smoothing launch the convergence-test norms)",
+                          "post-smoothing launch the convergence-test norms and the prolongation + correction)",
                 "bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                 "frac": achieved / peak, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms_launch,
                 "launches_timed": int(live_launches) if live else reps,
