@@ -26,6 +26,7 @@
 #ifndef NAVIFLOW_B200_H
 #define NAVIFLOW_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -122,9 +123,14 @@ int nf_restrict_coeffs(nf_ctx*, const nf_grid* fine, const double* d_u, const do
 int nf_prolong_linear(nf_ctx*, const nf_grid* coarse, const double* c, const nf_grid* fine, double* f,
                       int add);                                                                          /* :73-192 */
 /* interpolate_cubic (:333-391): separable not-a-knot spline on linspace(0,1,.) coordinates, square grids.
- * Builds the banded 1-D operator on the host on every call (setup cost); the multigrid driver caches it. */
+ * Builds the banded 1-D operator on the host on every call (setup cost; the multigrid driver caches it) and keeps it, with
+ * the row-interpolated intermediate array, in the caller's device workspace: 256-byte aligned, at least
+ * nf_workspace_bytes(NF_WS_PROLONG_CUBIC, fine nx, fine ny, coarse nx, coarse ld) bytes.  No allocation, no synchronisation. */
 int nf_prolong_cubic(nf_ctx*, const nf_grid* coarse, const double* c, const nf_grid* fine, double* f,
-                     int add);
+                     int add, void* workspace, size_t workspace_bytes);
+/* device scratch a stand-alone entry point needs (the *_create objects own theirs) */
+enum nf_workspace_kind { NF_WS_PROLONG_CUBIC = 1 };
+size_t nf_workspace_bytes(int which, int nx, int ny, int nxc, int ldc);
 
 /* ---- reductions (K18) ------------------------------------------------------------------ */
 /* sqrt(sum x^2) over the nx*ny cells (rows [gb,ge)); interior_only!=0 masks the boundary ring */

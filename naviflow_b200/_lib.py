@@ -102,7 +102,8 @@ SIGNATURES = {
     "nf_restrict_inject": (C.c_int, [CTX, GP, P, GP, P]),
     "nf_restrict_coeffs": (C.c_int, [CTX, GP, P, P, GP, P, P]),
     "nf_prolong_linear": (C.c_int, [CTX, GP, P, GP, P, C.c_int]),
-    "nf_prolong_cubic": (C.c_int, [CTX, GP, P, GP, P, C.c_int]),
+    "nf_prolong_cubic": (C.c_int, [CTX, GP, P, GP, P, C.c_int, C.c_void_p, C.c_size_t]),
+    "nf_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "nf_norm2": (C.c_int, [CTX, GP, P, C.c_int, DBL_OUT]),
     "nf_dot": (C.c_int, [CTX, GP, P, P, DBL_OUT]),
     "nf_mg_create": (C.c_int, [CTX, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.POINTER(NfMgConfig)]),

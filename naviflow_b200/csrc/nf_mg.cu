@@ -15,6 +15,7 @@
 // and the coarse part of the cycle runs redundantly, so the way back up needs no communication.
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <vector>
 
@@ -1145,25 +1146,46 @@ extern "C" int nf_mg_solve(nf_mg* mg, const double* b, double* x, double* r, nf_
   return nfi_mg_solve(mg, &bb, &x, &r, info, 1);
 }
 
-// standalone interpolate_cubic (tests, Python-level callers): builds the band on every call
+// Device workspace of the stand-alone entry points that need scratch memory (the header's rule: no allocation inside hot
+// calls; the multigrid / Krylov / SIMPLE objects own theirs).  which = NF_WS_PROLONG_CUBIC: nf_prolong_cubic from an
+// nxc-cell coarse grid onto an nx-cell fine grid (band of the 1-D interpolation matrix, its start indices, the row-interpolated
+// intermediate array).
+static size_t cubic_ws_layout(int nc, int nf_, int ldc, size_t* off_start, size_t* off_tmp) {
+  const int W = (nc < 48) ? nc : 48;
+  size_t band = (size_t)nf_ * W * sizeof(double);
+  band = (band + 255) / 256 * 256;
+  size_t start = ((size_t)nf_ * sizeof(int) + 255) / 256 * 256;
+  if (off_start) *off_start = band;
+  if (off_tmp) *off_tmp = band + start;
+  return band + start + (size_t)nf_ * ldc * sizeof(double);
+}
+
+extern "C" size_t nf_workspace_bytes(int which, int nx, int ny, int nxc, int ldc) {
+  (void)ny;
+  if (which == NF_WS_PROLONG_CUBIC) return cubic_ws_layout(nxc, nx, ldc, nullptr, nullptr);
+  return 0;
+}
+
+// standalone interpolate_cubic (tests, Python-level callers): the band is built on the host and copied into the caller's
+// workspace on every call; no device allocation, no stream synchronisation
 extern "C" int nf_prolong_cubic(nf_ctx* ctx, const nf_grid* gc, const double* c, const nf_grid* gf, double* f,
-                                int add) {
+                                int add, void* workspace, size_t workspace_bytes) {
   NF_REQUIRE(ctx, gc && gf && c && f, "NULL argument");
   NF_REQUIRE(ctx, gc->nx == gc->ny && gf->nx == gf->ny, "square grids only");
   NF_REQUIRE(ctx, gc->nx >= 2 && gf->nx >= 2, "grid too small");
+  size_t off_start = 0, off_tmp = 0;
+  const size_t need = cubic_ws_layout(gc->nx, gf->nx, gc->ld, &off_start, &off_tmp);
+  NF_REQUIRE(ctx, workspace && workspace_bytes >= need, "workspace too small (nf_workspace_bytes(NF_WS_PROLONG_CUBIC, ...))");
+  NF_REQUIRE(ctx, ((uintptr_t)workspace % 256) == 0, "workspace must be 256-byte aligned");
   std::vector<double> band;
   std::vector<int> start;
   int W = 0;
   build_interp_band(gc->nx, gf->nx, 24, band, start, W);
-  double *dband = nullptr, *tmp = nullptr;
-  int* dstart = nullptr;
-  NF_CHECK_CUDA(ctx, cudaMalloc(&dband, band.size() * sizeof(double)));
-  NF_CHECK_CUDA(ctx, cudaMalloc(&dstart, start.size() * sizeof(int)));
-  NF_CHECK_CUDA(ctx, cudaMalloc(&tmp, (size_t)gf->nx * gc->ld * sizeof(double)));
-  NF_CHECK_CUDA(ctx, cudaMemcpyAsync(dband, band.data(), band.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  NF_CHECK_CUDA(ctx, cudaMemcpyAsync(dstart, start.data(), start.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-  int st = nfi_prolong_banded(ctx, gc, c, gf, f, tmp, gc->ld, dband, dstart, W, add);
-  cudaStreamSynchronize(ctx->stream);
-  cudaFree(dband); cudaFree(dstart); cudaFree(tmp);
-  return st;
+  // pageable host memory: cudaMemcpyAsync stages it before it returns, so the vectors may go out of scope afterwards
+  char* ws = (char*)workspace;
+  NF_CHECK_CUDA(ctx, cudaMemcpyAsync(ws, band.data(), band.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  NF_CHECK_CUDA(ctx, cudaMemcpyAsync(ws + off_start, start.data(), start.size() * sizeof(int), cudaMemcpyHostToDevice,
+                                     ctx->stream));
+  return nfi_prolong_banded(ctx, gc, c, gf, f, (double*)(ws + off_tmp), gc->ld, (const double*)ws, (const int*)(ws + off_start),
+                            W, add);
 }

@@ -21,6 +21,8 @@
 
 #include "nf_pressure.cuh"
 
+bool nfi_tensor_map_2d(CUtensorMap* out, const double* base, int rows, int cols, int ld, int box_cols, int box_rows);
+
 namespace {
 
 constexpr int RCW = 64;        // region width in cells (32 column pairs = one warp per row)
@@ -611,36 +613,11 @@ k_rbsor_tma(nf_grid g, const __grid_constant__ CUtensorMap map_p, const __grid_c
   }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encoder() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)ptr;
-  }
-  return fn;
-}
-
-// 2-D fp64 tensor map over `rows` x `cols` valid elements with row pitch ld; box = box_rows x box_cols
+// 2-D fp64 tensor map over `rows` x `cols` valid elements with row pitch ld; box = box_rows x box_cols.  Cached per
+// (array, shape) in nf_rbsor_stream.cu: encoding is a driver call per array, and a smoothing call used to pay five of them
+// per launch.
 bool make_map(CUtensorMap* map, const double* base, int rows, int cols, int ld, int box_rows, int box_cols) {
-  EncodeTiledFn enc = get_encoder();
-  if (!enc) return false;
-  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(double)};
-  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS;
+  return nfi_tensor_map_2d(map, base, rows, cols, ld, box_cols, box_rows);
 }
 
 template <int NS, bool HAS_INV, int EXTRA>

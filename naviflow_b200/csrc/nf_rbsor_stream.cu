@@ -652,6 +652,11 @@ int launch_stream(nf_ctx* ctx, const nf_grid* g, const double* pin, double* pout
 
 }  // namespace
 
+// cached 2-D fp64 tensor map (box_rows x box_cols over rows x cols valid elements, pitch ld): shared with the tiled kernels
+bool nfi_tensor_map_2d(CUtensorMap* out, const double* base, int rows, int cols, int ld, int box_cols, int box_rows) {
+  return row_map(out, base, rows, cols, ld, box_cols, box_rows);
+}
+
 // mode 0: plain; 1: + residual norms -> extra->out[0..1]; 2: + coarse_b = FW(b - A p) on extra->gc.  extra->prolong_c: the
 // launch takes p + P(prolong_c) as its input (modes 0 and 1).  The fused work exists for 3-sweep launches; *used = false
 // means nothing was launched (the caller takes another path).

@@ -143,7 +143,10 @@ class GpuJacobiSolver(_StationaryBase):
 
     def _iterate(self, g, p, b, du, dv, n):
         ctx = self.ctx
-        tmp = ctx.empty(g.nx, g.ny)
+        key = (g.nx, g.ny)
+        if getattr(self, "_tmp_key", None) != key:   # ping-pong scratch, kept across calls (no allocation per iteration)
+            self._tmp, self._tmp_key = ctx.empty(g.nx, g.ny), key
+        tmp = self._tmp
         ctx.check(ctx.lib.nf_jacobi_iterate(ctx.handle, C.byref(g), ptr(p), ptr(tmp), ptr(b), ptr(du), ptr(dv),
                                             float(self.omega), int(n)), "nf_jacobi_iterate")
 

@@ -29,6 +29,14 @@ def cavity_bc():
     return bc
 
 
+def cubic_workspace(d, gc):
+    """caller-provided device scratch of nf_prolong_cubic (include/naviflow_b200.h: nf_workspace_bytes)"""
+    import torch
+    nbytes = d.lib.nf_workspace_bytes(1, d.nx, d.ny, gc.nx, gc.ld)
+    assert nbytes > 0
+    return torch.zeros((nbytes + 7) // 8, dtype=torch.float64, device="cuda")
+
+
 def synth(n, seed):
     from oracle.make_golden import synth_pressure_inputs
     return synth_pressure_inputs(n, seed)
@@ -87,7 +95,8 @@ def test_transfer_kernels_vs_reference_golden(golden_dir, n):
         gc = grid_for(ctx, nc)
         cd = ctx.upload(g["fw"], nc, nc)
         f = d.zeros()
-        d.call("nf_prolong_cubic", C.byref(gc), ptr(cd), d.gref(), ptr(f), 0)
+        ws = cubic_workspace(d, gc)
+        d.call("nf_prolong_cubic", C.byref(gc), ptr(cd), d.gref(), ptr(f), 0, ptr(ws), ws.numel() * 8)
         assert rel(d.down(f), g["cub_from_fw"]) < 1e-13
 
 
@@ -173,7 +182,8 @@ def test_kernels_vs_oracle_seeded(n):
         d.call("nf_prolong_linear", C.byref(gc), ptr(c), d.gref(), ptr(f), 0)
         np.testing.assert_array_equal(d.down(f), O.prolong_linear(fw, n))
         if nc >= 4:
-            d.call("nf_prolong_cubic", C.byref(gc), ptr(c), d.gref(), ptr(f), 0)
+            ws = cubic_workspace(d, gc)
+            d.call("nf_prolong_cubic", C.byref(gc), ptr(c), d.gref(), ptr(f), 0, ptr(ws), ws.numel() * 8)
             assert rel(d.down(f), O.prolong_cubic(fw, n)) < 1e-12
     # norms / dot
     val = C.c_double()
