@@ -79,6 +79,13 @@ struct nf_mg {
   bool graph_swapped = false;  // the captured launches leave level 0's x / x2 exchanged (odd number of smoother launches)
   bool graph_norm_fused = false;
   long long graph_nodes = 0;
+  // device-side convergence loop: one graph whose WHILE node replays {cycle, norms, test} until ||r||/||b|| < tol
+  cudaGraphExec_t loop_exec = nullptr;
+  const void* loop_key[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  int loop_kind = -1;
+  bool loop_norm_fused = false;
+  long long loop_nodes = 0;
+  bool use_loop = true;
   int warm_cycles = 0;
   bool use_graph = true;
   // optional live timing of the finest-level smoother launches (bench.py roofline): event pairs, read at the
@@ -302,6 +309,7 @@ extern "C" int nf_mg_destroy(nf_mg* mg) {
   if (mg->scal_host) cudaFreeHost(mg->scal_host);
   for (cudaEvent_t e : mg->ev) cudaEventDestroy(e);
   if (mg->graph_exec) cudaGraphExecDestroy(mg->graph_exec);
+  if (mg->loop_exec) cudaGraphExecDestroy(mg->loop_exec);
   if (mg->cap_stream) cudaStreamDestroy(mg->cap_stream);
   if (mg->owns_team) nf_team_destroy(mg->team);
   delete mg;
@@ -902,6 +910,115 @@ static int mg_rel_residual(nf_mg* mg, int l, double* r_norm, double* b_norm, int
   return NF_OK;
 }
 
+// ---- device-side convergence loop -----------------------------------------------------------------------------------
+// MultiGridSolver.solve's `for cycle in range(max_iterations): ...; if rel < tol: break` (multigrid.py:185-240) as a
+// CUDA-graph conditional WHILE node: the body is one cycle at level 0 + the residual norms of its result (fused into
+// the post-smoother where the level-0 kernel can, one reduction kernel otherwise; all-reduced over the slabs) + a
+// one-thread kernel that counts the cycle, evaluates the reference's test in the reference's arithmetic
+// (sqrt(sum r^2) / sqrt(sum b^2) < tol) and arms or disarms the node.  The host launches the graph once per solve and
+// reads {sum r^2, sum b^2, cycles} once: no per-cycle D2H + synchronisation, no per-cycle graph launch.
+// scal[0][4] is the cycle counter (a double so that one 40-byte copy brings everything back).
+__global__ void k_mg_loop_check(cudaGraphConditionalHandle handle, double* scal, double tol, int max_it) {
+  const double c = scal[4] + 1.0;
+  scal[4] = c;
+  const double rn = sqrt(scal[0]), bn = sqrt(scal[1]);
+  const double rel = bn > 0.0 ? rn / bn : rn;
+  cudaGraphSetConditional(handle, (!(rel < tol) && c < (double)max_it) ? 1u : 0u);
+}
+
+// *used = false: not available here (the caller runs the host loop).  On success the iterate is in L.s[0].x, the
+// cycle count in *cycles and the norms of the last iterate in *rn / *bn.
+static int mg_device_loop(nf_mg* mg, int* cycles, double* rn, double* bn, bool* norm_fused, bool* used) {
+  nf_ctx* ctx = mg->ctx;
+  nf_team* team = mg->team;
+  MgLevel& L = mg->lv[0];
+  *used = false;
+  const char* env = getenv("NF_MG_DEVICE_LOOP");
+  const char* envg = getenv("NF_MG_GRAPH");
+  const char* envd = getenv("NF_MG_GRAPH_DIST");
+  const bool force = env && env[0] == '2';
+  // slabs: the peer-memory transport keeps its sequence numbers on the device (replayable, every rank takes the same
+  // decision because the all-reduced norms are bit-identical); NCCL inside a WHILE body only on request (=2)
+  const bool dist_ok = !L.geom.dist || (!(envd && envd[0] == '0') && team->nccl != nullptr && (nf_p2p_active(team) || force));
+  const bool allowed = mg->use_loop && mg->use_graph && !(env && env[0] == '0') && !(envg && envg[0] == '0') &&
+                       nlocal(mg) == 1 && dist_ok && mg->cfg.smoother == 0 && !mg->timing && mg->cfg.max_iterations >= 1 &&
+                       mg->warm_cycles >= 1 && (mg->cfg.cycle_type == 0 || mg->cfg.cycle_type == 1) &&
+                       ((mg->cfg.pre + 2) / 3 + (mg->cfg.post + 2) / 3) % 2 == 0;
+  if (!allowed) return NF_OK;
+  MgSlab& S = L.s[0];
+  const int kind = mg->cfg.cycle_type;
+  const void* key[5] = {S.x, S.b, S.d_u, S.d_v, S.x2};
+  bool same = mg->loop_exec && mg->loop_kind == kind;
+  for (int q = 0; q < 5 && same; ++q) same = (key[q] == mg->loop_key[q]);
+  if (!same) {
+    if (mg->loop_exec) { cudaGraphExecDestroy(mg->loop_exec); mg->loop_exec = nullptr; }
+    if (!mg->cap_stream) NF_CHECK_CUDA(ctx, cudaStreamCreateWithFlags(&mg->cap_stream, cudaStreamNonBlocking));
+    cudaGraph_t graph = nullptr;
+    cudaGraphConditionalHandle handle;
+    cudaGraphNode_t node;
+    cudaGraphNodeParams np = {};
+    bool ok = cudaGraphCreate(&graph, 0) == cudaSuccess &&
+              cudaGraphConditionalHandleCreate(&handle, graph, 1, cudaGraphCondAssignDefault) == cudaSuccess;
+    if (ok) {
+      np.type = cudaGraphNodeTypeConditional;
+      np.conditional.handle = handle;
+      np.conditional.type = cudaGraphCondTypeWhile;
+      np.conditional.size = 1;
+      ok = cudaGraphAddNode(&node, graph, nullptr, 0, &np) == cudaSuccess;
+    }
+    int st = NF_OK;
+    bool nf = false;
+    const long long l0 = ctx->launches;
+    if (ok) {
+      cudaGraph_t body = np.conditional.phGraph_out[0];
+      ok = cudaStreamBeginCaptureToGraph(mg->cap_stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+      if (ok) {
+        cudaStream_t orig = ctx->stream;
+        ctx->stream = mg->cap_stream;
+        st = mg_cycle(mg, 0, kind, true, &nf);
+        if (st == NF_OK && !nf) {
+          const nf_grid g = L.geom.grid(team->local[0]);
+          st = nfi_residual_norms(ctx, &g, S.x, S.b, S.d_u, S.d_v, S.r, 1, mg->scal[0]);
+        }
+        if (st == NF_OK && L.geom.dist) st = nf_team_allreduce(team, mg->scal.data(), 2);
+        if (st == NF_OK) {
+          k_mg_loop_check<<<1, 1, 0, mg->cap_stream>>>(handle, mg->scal[0], mg->cfg.tolerance, mg->cfg.max_iterations);
+          ctx->launches++;
+        }
+        ctx->stream = orig;
+        cudaGraph_t out = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(mg->cap_stream, &out);
+        ok = (st == NF_OK) && ce == cudaSuccess && S.x == key[0];
+        if (S.x != key[0]) { S.x = (double*)key[0]; S.x2 = (double*)key[4]; }
+      }
+    }
+    mg->loop_nodes = ctx->launches - l0;
+    ctx->launches = l0;
+    if (ok) ok = cudaGraphInstantiate(&mg->loop_exec, graph, 0) == cudaSuccess;
+    if (graph) cudaGraphDestroy(graph);
+    if (!ok) {
+      cudaGetLastError();
+      mg->loop_exec = nullptr;
+      mg->use_loop = false;  // host loop from now on
+      return st;
+    }
+    for (int q = 0; q < 5; ++q) mg->loop_key[q] = key[q];
+    mg->loop_kind = kind;
+    mg->loop_norm_fused = nf;
+  }
+  NF_CHECK_CUDA(ctx, cudaMemsetAsync(mg->scal[0] + 4, 0, sizeof(double), ctx->stream));
+  NF_CHECK_CUDA(ctx, cudaGraphLaunch(mg->loop_exec, ctx->stream));
+  NF_CHECK_CUDA(ctx, cudaMemcpyAsync(mg->scal_host, mg->scal[0], 5 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  NF_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *cycles = (int)mg->scal_host[4];
+  ctx->launches += 1 + mg->loop_nodes * (long long)*cycles;
+  *rn = sqrt(mg->scal_host[0]);
+  *bn = sqrt(mg->scal_host[1]);
+  *norm_fused = mg->loop_norm_fused;
+  *used = true;
+  return NF_OK;
+}
+
 // recursive FMG (multigrid.py:562-688): RHS restricted down, exact coarsest solve, cubic prolongation
 // (hard-coded :631), max_cycles_buildup cycles per level with early exit on ||r||/||b|| < tol.
 static int mg_fmg(nf_mg* mg, int l) {
@@ -1018,7 +1135,11 @@ int nfi_mg_solve(nf_mg* mg, double* const* b, double* const* x, double* const* r
         if (nfi_rbsor_stream_enabled(&g0)) lookahead = false;
       }
       bool have_final_norm = false;
-      for (int it = 0; it < mg->cfg.max_iterations; ++it) {
+      bool on_device = false;
+      status = mg_device_loop(mg, &cycles, &rn, &bn, &fused_any, &on_device);
+      if (status) break;
+      if (on_device) have_final_norm = true;
+      for (int it = 0; it < mg->cfg.max_iterations && !on_device; ++it) {
         if (lookahead) {
           std::vector<double*> x_before(nlocal(mg)), x2_before(nlocal(mg));
           for (int k = 0; k < nlocal(mg); ++k) { x_before[k] = L.s[k].x; x2_before[k] = L.s[k].x2; }

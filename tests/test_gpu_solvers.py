@@ -716,6 +716,32 @@ def test_multigrid_lookahead_norm_equals_classic_convergence_test(n, kw, monkeyp
     np.testing.assert_allclose(outs[0][1]["field"], outs[1][1]["field"], rtol=0, atol=1e-18 + 1e-12 * np.abs(outs[1][1]["field"]).max())
 
 
+@pytest.mark.parametrize("n,kw", [(257, dict(tolerance=1e-4)), (300, dict(tolerance=1e-30, max_iterations=4)),
+                                  (385, dict(tolerance=1e-5, cycle_type="w")), (2049, dict(tolerance=1e-3, max_iterations=12)),
+                                  (129, dict(tolerance=1e-30, max_iterations=1))])
+def test_multigrid_device_side_convergence_loop_equals_host_loop(n, kw, monkeypatch):
+    """The `for cycle ...: if rel < tol: break` loop of MultiGridSolver.solve (multigrid.py:185-240) replayed by a CUDA-graph
+    WHILE node (nf_mg.cu: mg_device_loop) stops after the same cycle with the same iterate, bit for bit, and reports the same
+    norms as the host-driven loop (NF_MG_DEVICE_LOOP=0); the third solve replays the instantiated loop graph."""
+    import naviflow_b200 as nb
+    from oracle.make_golden import synth_pressure_inputs
+    s = synth_pressure_inputs(n, 9100 + n)
+    mesh, _ = cavity(n, 1000)
+    outs = []
+    for dev in ("1", "0"):
+        monkeypatch.setenv("NF_MG_DEVICE_LOOP", dev)
+        args = dict(max_iterations=100, tolerance=1e-4, pre_smoothing=3, post_smoothing=3)
+        args.update(kw)
+        ps = nb.GpuMultiGridSolver(smoother=nb.GpuGaussSeidelSolver(omega=1.5), **args)
+        for rep in range(3):
+            p, info = ps.solve(mesh, s["u_star"], s["v_star"], s["d_u"], s["d_v"], None)
+        outs.append((p, info, ps.last_info.cycles))
+    assert outs[0][2] == outs[1][2] and outs[0][2] >= 1
+    np.testing.assert_array_equal(outs[0][0], outs[1][0])
+    assert outs[0][1]["rel_norm"] == outs[1][1]["rel_norm"]
+    np.testing.assert_array_equal(outs[0][1]["field"], outs[1][1]["field"])
+
+
 def test_multigrid_lookahead_norm_on_slabs(monkeypatch):
     """Same on row slabs (the input norms of the slabs are all-reduced): identical fields and cycle counts."""
     runs = []
