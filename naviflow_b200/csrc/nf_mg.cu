@@ -86,11 +86,23 @@ struct nf_mg {
   bool loop_norm_fused = false;
   long long loop_nodes = 0;
   bool use_loop = true;
+  // slabs over peer memory: the scalar all-reduce of the residual norms rode on the last halo exchange of the cycle
+  bool norm_reduced = false;
+  bool graph_norm_reduced = false;
   int warm_cycles = 0;
   bool use_graph = true;
   // optional live timing of the finest-level smoother launches (bench.py roofline): event pairs, read at the
   // synchronisation points the cycle loop already has
   bool timing = false;
+  // NF_MG_PROFILE=1: event pairs around every phase of the cycles (plain launches, no graphs), summed per (level, phase)
+  // and printed to stderr when the hierarchy is destroyed -- a development aid for the slab runs, where ncu cannot go
+  bool prof = false;
+  std::vector<cudaEvent_t> pev;
+  std::vector<int> ptag;  // per pair: level * 16 + phase
+  size_t pev_used = 0;
+  double pms[32][16] = {};
+  long long pcnt[32][16] = {};
+  long long psolves = 0, pcycles = 0;
   std::vector<cudaEvent_t> ev;
   size_t ev_used = 0;
   double smooth_ms = 0.0;
@@ -285,6 +297,60 @@ static void build_interp_band(int mc, int m, int K, std::vector<double>& band, s
 static int nlocal(const nf_mg* mg) { return (int)mg->team->local.size(); }
 static void mg_harvest_timing(nf_mg* mg);
 
+enum { PH_SMOOTH = 0, PH_EXCH_X, PH_RESTRICT, PH_FILL, PH_EXCH_B, PH_PROLONG, PH_TAIL, PH_COARSE, PH_NORM, PH_ALLREDUCE, PH_N };
+static const char* const kPhaseName[PH_N] = {"smooth", "exch_x", "restrict", "fill", "exch_b", "prolong", "tail", "coarse",
+                                             "norm", "allreduce"};
+struct MgProf {  // scope guard: records an event pair on the context's stream when profiling is on
+  nf_mg* mg;
+  bool on;
+  MgProf(nf_mg* m, int level, int phase) : mg(m), on(m->prof) {
+    if (!on) return;
+    if (mg->pev_used + 2 > mg->pev.size()) {
+      cudaEvent_t a, b;
+      cudaEventCreate(&a); cudaEventCreate(&b);
+      mg->pev.push_back(a); mg->pev.push_back(b);
+    }
+    if (mg->ptag.size() < mg->pev.size() / 2) mg->ptag.resize(mg->pev.size() / 2);
+    mg->ptag[mg->pev_used / 2] = level * 16 + phase;
+    cudaEventRecord(mg->pev[mg->pev_used], mg->ctx->stream);
+  }
+  ~MgProf() {
+    if (!on) return;
+    cudaEventRecord(mg->pev[mg->pev_used + 1], mg->ctx->stream);
+    mg->pev_used += 2;
+  }
+};
+static void mg_prof_harvest(nf_mg* mg) {  // after a stream synchronisation
+  for (size_t e = 0; e + 1 < mg->pev_used; e += 2) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, mg->pev[e], mg->pev[e + 1]) != cudaSuccess) continue;
+    const int t = mg->ptag[e / 2];
+    mg->pms[(t / 16) & 31][t % 16] += ms;
+    mg->pcnt[(t / 16) & 31][t % 16]++;
+  }
+  mg->pev_used = 0;
+}
+static void mg_prof_print(nf_mg* mg) {
+  if (!mg->prof || mg->pcycles == 0) return;
+  fprintf(stderr, "[NF_MG_PROFILE] rank %d: %lld solves, %lld cycles; microseconds per cycle (launches per cycle)\n",
+          mg->team->local.empty() ? 0 : mg->team->local[0], mg->psolves, mg->pcycles);
+  double total = 0.0;
+  for (size_t l = 0; l < mg->lv.size() && l < 32; ++l) {
+    bool any = false;
+    for (int ph = 0; ph < PH_N; ++ph) any = any || mg->pcnt[l][ph] > 0;
+    if (!any) continue;
+    fprintf(stderr, "  level %2zu (%5d rows%s):", l, mg->lv[l].geom.nx, mg->lv[l].geom.dist ? ", cut" : "");
+    for (int ph = 0; ph < PH_N; ++ph)
+      if (mg->pcnt[l][ph] > 0) {
+        fprintf(stderr, " %s %.1f (%.1f)", kPhaseName[ph], 1e3 * mg->pms[l][ph] / mg->pcycles,
+                (double)mg->pcnt[l][ph] / mg->pcycles);
+        total += mg->pms[l][ph];
+      }
+    fprintf(stderr, "\n");
+  }
+  fprintf(stderr, "  sum of phases: %.1f us per cycle\n", 1e3 * total / mg->pcycles);
+}
+
 extern "C" int nf_mg_destroy(nf_mg* mg) {
   if (!mg) return NF_OK;
   cudaSetDevice(mg->ctx->device);
@@ -310,6 +376,8 @@ extern "C" int nf_mg_destroy(nf_mg* mg) {
   for (cudaEvent_t e : mg->ev) cudaEventDestroy(e);
   if (mg->graph_exec) cudaGraphExecDestroy(mg->graph_exec);
   if (mg->loop_exec) cudaGraphExecDestroy(mg->loop_exec);
+  mg_prof_print(mg);
+  for (cudaEvent_t e : mg->pev) cudaEventDestroy(e);
   if (mg->cap_stream) cudaStreamDestroy(mg->cap_stream);
   if (mg->owns_team) nf_team_destroy(mg->team);
   delete mg;
@@ -347,6 +415,7 @@ int nfi_mg_create(nf_team* team, nf_mg** out, int nx, int ny, int ld, const nf_m
   NF_REQUIRE(ctx, cfg->cycle_type >= 0 && cfg->cycle_type <= 2, "bad cycle_type");
   NF_REQUIRE(ctx, cfg->pre >= 0 && cfg->post >= 0, "negative smoothing count");
   nf_mg* mg = new nf_mg();
+  { const char* ep = getenv("NF_MG_PROFILE"); mg->prof = ep && ep[0] == '1'; }
   mg->ctx = ctx;
   mg->team = team;
   mg->cfg = *cfg;
@@ -398,7 +467,8 @@ int nfi_mg_create(nf_team* team, nf_mg** out, int nx, int ny, int ld, const nf_m
     return NF_ERR_UNSUPPORTED;
   }
   if (mg->lv[0].geom.dist) {  // peer-memory halo staging (no-op without p2p)
-    int st = nf_p2p_reserve_stage(team, (size_t)NF_HALO * mg->lv[0].geom.ld);
+    // one exchange may carry a level's iterate and the next level's right-hand side (mg_publish_rhs)
+    int st = nf_p2p_reserve_stage(team, (size_t)NF_HALO * (mg->lv[0].geom.ld + (mg->lv.size() > 1 ? mg->lv[1].geom.ld : 0)));
     if (st != NF_OK) { nf_mg_destroy(mg); return st; }
   }
   bool ok = true;
@@ -586,7 +656,10 @@ extern "C" int nf_mg_setup(nf_mg* mg, const double* d_u, const double* d_v) {
 // =============================================================================================
 // n smoothing sweeps on level l; on a cut level the iterate's halo is valid on entry and on return
 // extra (single slab only): work fused behind the last smoother launch, see nf_smooth_extra
-static int mg_smooth(nf_mg* mg, int l, int n, nf_smooth_extra* extra = nullptr /* one per local slab */) {
+// defer_exchange: the caller exchanges the iterate's halo after the LAST launch itself (merged with another field)
+// red: sum these 2 scalars over the ranks in the last launch's halo exchange when the transport can (-> mg->norm_reduced)
+static int mg_smooth(nf_mg* mg, int l, int n, nf_smooth_extra* extra = nullptr /* one per local slab */,
+                     bool defer_exchange = false, double* red = nullptr) {
   nf_ctx* ctx = mg->ctx;
   nf_team* team = mg->team;
   MgLevel& L = mg->lv[l];
@@ -615,6 +688,7 @@ static int mg_smooth(nf_mg* mg, int l, int n, nf_smooth_extra* extra = nullptr /
         cudaEventRecord(mg->ev[mg->ev_used], ctx->stream);
       }
       for (int k = 0; k < nl; ++k) {
+        MgProf prof_(mg, l, PH_SMOOTH);
         const nf_grid g = L.geom.grid(team->local[k]);
         // the fused prolongation rides on the FIRST launch of the call, the residual work on the LAST one
         const bool first = (left == n), last = (left == ns);
@@ -635,9 +709,18 @@ static int mg_smooth(nf_mg* mg, int l, int n, nf_smooth_extra* extra = nullptr /
         cudaEventRecord(mg->ev[mg->ev_used + 1], ctx->stream);
         mg->ev_used += 2;
       }
-      if (L.geom.dist) {
+      if (L.geom.dist && !(defer_exchange && left == ns)) {
+        MgProf prof_(mg, l, PH_EXCH_X);
         std::vector<double*> x = field_of(L, &MgSlab::x);
-        NF_TRY(nf_team_exchange(team, L.geom, x.data(), NF_SMOOTH_HALO));
+        int st = NF_ERR_UNSUPPORTED;
+        if (red && left == ns && nl == 1 && extra && extra[0].fused && nf_p2p_active(team)) {
+          const LevelGeom* gp = &L.geom;
+          const int depth = NF_SMOOTH_HALO;
+          st = nf_p2p_exchange_multi(team, 1, &gp, x.data(), &depth, nullptr, nullptr, red, 2);
+          if (st == NF_OK) mg->norm_reduced = true;
+        }
+        if (st == NF_ERR_UNSUPPORTED) st = nf_team_exchange(team, L.geom, x.data(), NF_SMOOTH_HALO);
+        NF_TRY(st);
       }
       left -= ns;
     }
@@ -662,6 +745,7 @@ static int mg_coarse_solve(nf_mg* mg, int l) {
   MgLevel& L = mg->lv[l];
   const int N = mg->coarse_N;
   const int threads = 128, blocks = (N * 32 + threads - 1) / threads;
+  MgProf prof_(mg, l, PH_COARSE);
   for (int k = 0; k < nlocal(mg); ++k) {
     k_coarse_apply<<<blocks, threads, 0, ctx->stream>>>(L.geom.grid(mg->team->local[k]), mg->coarse_inv[k], L.s[k].b,
                                                         L.s[k].x, N);
@@ -675,6 +759,7 @@ static int mg_prolong(nf_mg* mg, int l, int cubic, int add) {
   nf_team* team = mg->team;
   MgLevel& L = mg->lv[l];
   MgLevel& C = mg->lv[l + 1];
+  MgProf prof_(mg, l, PH_PROLONG);
   for (int k = 0; k < nlocal(mg); ++k) {
     const int r = team->local[k];
     const nf_grid gc = C.geom.grid(r), gf = L.geom.grid_ext(r, NF_SMOOTH_HALO);
@@ -685,10 +770,28 @@ static int mg_prolong(nf_mg* mg, int l, int cubic, int add) {
 }
 
 // after a restriction into level l+1: make the new right-hand side visible where the coarse level needs it
-static int mg_publish_rhs(nf_mg* mg, int l) {
+// with_x: level l's iterate is waiting for its halo exchange as well (mg_smooth's defer_exchange) -- one launch for both over
+// peer memory; zero_x: that launch also clears the halo rows of level l+1's iterate (its own rows were cleared by the
+// restriction kernel)
+static int mg_publish_rhs(nf_mg* mg, int l, bool with_x = false, bool zero_x = false) {
   MgLevel& L = mg->lv[l];
   MgLevel& C = mg->lv[l + 1];
   if (!L.geom.dist) return NF_OK;
+  if (with_x || zero_x) {  // single local slab, cut coarse level (see mg_cycle)
+    MgProf prof_(mg, l, PH_EXCH_X);
+    const LevelGeom* gp[2] = {&C.geom, &L.geom};
+    double* f[2] = {C.s[0].b, L.s[0].x};
+    const int depth[2] = {NF_SMOOTH_HALO, NF_SMOOTH_HALO};
+    int st = nf_p2p_exchange_multi(mg->team, with_x ? 2 : 1, gp, f, depth, zero_x ? &C.geom : nullptr,
+                                   zero_x ? C.s[0].x : nullptr, nullptr, 0);
+    if (st != NF_ERR_UNSUPPORTED) return st;
+    if (with_x) {
+      std::vector<double*> x = field_of(L, &MgSlab::x);
+      NF_TRY(nf_team_exchange(mg->team, L.geom, x.data(), NF_SMOOTH_HALO));
+    }
+    if (zero_x) NF_TRY(nfi_fill(mg->ctx, C.s[0].x, C.geom.elems(mg->team->local[0]), 0.0));
+  }
+  MgProf prof_(mg, l + 1, PH_EXCH_B);
   std::vector<double*> b = field_of(C, &MgSlab::b);
   if (C.geom.dist) return nf_team_exchange(mg->team, C.geom, b.data(), NF_SMOOTH_HALO);
   return nf_team_share_rows(mg->team, C.geom.ld, C.geom.nx, C.rgb, C.rge, b.data(), 0);
@@ -698,6 +801,7 @@ static int mg_publish_rhs(nf_mg* mg, int l) {
 // solution is written; same bits as the launch-by-launch recursion)
 static int mg_tail(nf_mg* mg) {
   nf_ctx* ctx = mg->ctx;
+  MgProf prof_(mg, mg->tail_level, PH_TAIL);
   for (int k = 0; k < nlocal(mg); ++k) {
     nf_tail_args a;
     a.nlev = (int)mg->lv.size() - mg->tail_level;
@@ -735,6 +839,7 @@ static int mg_cycle(nf_mg* mg, int l, int kind, bool want_norm = false, bool* no
   const int nl = nlocal(mg);
   if (norm_fused) *norm_fused = false;
   if (in_norm_fused) *in_norm_fused = false;
+  if (l == 0) mg->norm_reduced = false;
   if (l == mg->tail_level && kind == 0 && part == 0 && !want_norm && !in_norm && from_zero) return mg_tail(mg);
   if (L.geom.nx <= mg->cfg.coarsest || l + 1 == (int)mg->lv.size()) return part == 1 ? NF_OK : mg_coarse_solve(mg, l);
   MgLevel& C = mg->lv[l + 1];
@@ -744,7 +849,12 @@ static int mg_cycle(nf_mg* mg, int l, int kind, bool want_norm = false, bool* no
     // The coarse level starts from a zero guess (multigrid.py:374).  On an unsplit level the kernel that writes the restricted
     // right-hand side zeroes the coarse iterate cell by cell as well; on slabs the whole array (halo rows included) is filled.
     const bool tail_next = (l + 1 == mg->tail_level && kind == 0);  // the tail kernel starts from zero by itself
-    const bool zero_by_restriction = !tail_next && !L.geom.dist && mg->cfg.restriction == 0;
+    // cut level over peer memory: the halo exchange of the pre-smoothed iterate and the one that publishes the coarse
+    // right-hand side are one launch, which clears the halo rows of the coarse iterate on the way
+    const char* envm = getenv("NF_MG_MERGED_EXCHANGE");
+    const bool merged = L.geom.dist && C.geom.dist && nl == 1 && mg->cfg.smoother == 0 && mg->cfg.pre > 0 && part == 0 &&
+                        nf_p2p_active(team) && !(envm && envm[0] == '0');
+    const bool zero_by_restriction = !tail_next && (!L.geom.dist || merged) && mg->cfg.restriction == 0;
     if (want_pre)
       for (int k = 0; k < nl; ++k) {
         pre[k].mode = 2;
@@ -753,7 +863,15 @@ static int mg_cycle(nf_mg* mg, int l, int kind, bool want_norm = false, bool* no
         if (zero_by_restriction) pre[k].coarse_x_zero = C.s[k].x;
         if (in_norm) pre[k].in_norm_out = mg->scal[k];
       }
-    NF_TRY(mg_smooth(mg, l, mg->cfg.pre, want_pre ? pre.data() : nullptr));
+    NF_TRY(mg_smooth(mg, l, mg->cfg.pre, want_pre ? pre.data() : nullptr, merged));
+    bool x_pending = merged;
+    if (merged && !(want_pre && pre[0].fused)) {
+      // the restriction is a kernel of its own here and reads the pre-smoothed iterate's halo rows: exchange them now
+      MgProf prof_(mg, l, PH_EXCH_X);
+      std::vector<double*> x = field_of(L, &MgSlab::x);
+      NF_TRY(nf_team_exchange(team, L.geom, x.data(), NF_SMOOTH_HALO));
+      x_pending = false;
+    }
     if (in_norm_fused) {
       bool all = want_pre && in_norm;
       for (int k = 0; k < nl; ++k) all = all && pre[k].in_norm_fused;
@@ -765,15 +883,19 @@ static int mg_cycle(nf_mg* mg, int l, int kind, bool want_norm = false, bool* no
       if (pre[k].fused) {
         // coarse right-hand side already written by the smoother
       } else if (mg->cfg.restriction == 0) {
+        MgProf prof_(mg, l, PH_RESTRICT);
         NF_TRY(nfi_residual_restrict_fw(ctx, &gf, L.s[k].x, L.s[k].b, L.s[k].d_u, L.s[k].d_v, &gc, C.s[k].b,
                                         zero_by_restriction ? C.s[k].x : nullptr));
       } else {
         NF_TRY(nfi_residual(ctx, &gf, L.s[k].x, L.s[k].b, L.s[k].d_u, L.s[k].d_v, L.s[k].r));
         NF_TRY(nfi_restrict_inject(ctx, &gf, L.s[k].r, &gc, C.s[k].b));
       }
-      if (!tail_next && !zero_by_restriction) NF_TRY(nfi_fill(ctx, C.s[k].x, C.geom.elems(r), 0.0));
+      if (!tail_next && !zero_by_restriction) {
+        MgProf prof_(mg, l + 1, PH_FILL);
+        NF_TRY(nfi_fill(ctx, C.s[k].x, C.geom.elems(r), 0.0));
+      }
     }
-    NF_TRY(mg_publish_rhs(mg, l));
+    NF_TRY(mg_publish_rhs(mg, l, x_pending, merged && zero_by_restriction));
     if (part == 1) return NF_OK;
   }
   const int reps = (kind == 1) ? 2 : 1;
@@ -800,7 +922,10 @@ static int mg_cycle(nf_mg* mg, int l, int kind, bool want_norm = false, bool* no
         post[k].prolong_gc = C.geom.grid(team->local[k]);
       }
     }
-  NF_TRY(mg_smooth(mg, l, mg->cfg.post, (want_post || fuse_prolong) ? post.data() : nullptr));
+  const char* envr = getenv("NF_MG_MERGED_ALLREDUCE");
+  const bool red = want_post && l == 0 && L.geom.dist && nl == 1 && mg->cfg.post > 0 && mg->cfg.post <= 3 &&
+                   !(envr && envr[0] == '0');
+  NF_TRY(mg_smooth(mg, l, mg->cfg.post, (want_post || fuse_prolong) ? post.data() : nullptr, false, red ? mg->scal[0] : nullptr));
   if (norm_fused) {
     bool all = want_post;
     for (int k = 0; k < nl; ++k) all = all && post[k].fused;
@@ -822,7 +947,7 @@ static int mg_cycle_top(nf_mg* mg, int kind, bool* norm_fused, int part = 0, boo
   const char* envd = getenv("NF_MG_GRAPH_DIST");
   const bool dist_ok = !L.geom.dist || (mg->team->nccl != nullptr && !(envd && envd[0] == '0'));
   const bool allowed = mg->use_graph && !(env && env[0] == '0') && nlocal(mg) == 1 && dist_ok &&
-                       mg->cfg.smoother == 0 && !mg->timing &&
+                       mg->cfg.smoother == 0 && !mg->timing && !mg->prof &&
                        ((mg->cfg.pre + 2) / 3 + (mg->cfg.post + 2) / 3) % 2 == 0;  // even number of x/x2 swaps
   if (!allowed) return mg_cycle(mg, 0, kind, want_norm, norm_fused, part);
   MgSlab& S = L.s[0];
@@ -833,6 +958,7 @@ static int mg_cycle_top(nf_mg* mg, int kind, bool* norm_fused, int part = 0, boo
     NF_CHECK_CUDA(ctx, cudaGraphLaunch(mg->graph_exec, ctx->stream));
     ctx->launches += mg->graph_nodes;
     *norm_fused = mg->graph_norm_fused;
+    mg->norm_reduced = mg->graph_norm_reduced;
     if (mg->graph_swapped) { double* t = S.x; S.x = S.x2; S.x2 = t; }  // what the launches did to the host's pointers
     return NF_OK;
   }
@@ -861,6 +987,7 @@ static int mg_cycle_top(nf_mg* mg, int kind, bool* norm_fused, int part = 0, boo
   }
   mg->graph_nodes = ctx->launches - l0;
   mg->graph_norm_fused = nf;
+  mg->graph_norm_reduced = mg->norm_reduced;
   mg->graph_swapped = (S.x != key[0]);
   ctx->launches = l0;
   ce = cudaGraphInstantiate(&mg->graph_exec, graph, 0);
@@ -893,12 +1020,15 @@ static int mg_rel_residual(nf_mg* mg, int l, double* r_norm, double* b_norm, int
   int with_b = (*b_norm < 0.0) ? 1 : 0;
   if (have_norms) {
     with_b = 1;
-    if (L.geom.dist) NF_TRY(nf_team_allreduce(team, mg->scal.data(), 2));
+    MgProf prof_(mg, l, PH_ALLREDUCE);
+    if (L.geom.dist && !mg->norm_reduced) NF_TRY(nf_team_allreduce(team, mg->scal.data(), 2));
   } else {
     for (int k = 0; k < nl; ++k) {
+      MgProf prof_(mg, l, PH_NORM);
       const nf_grid g = L.geom.grid(team->local[k]);
       NF_TRY(nfi_residual_norms(ctx, &g, L.s[k].x, L.s[k].b, L.s[k].d_u, L.s[k].d_v, L.s[k].r, with_b, mg->scal[k]));
     }
+    MgProf prof_(mg, l, PH_ALLREDUCE);
     if (L.geom.dist) NF_TRY(nf_team_allreduce(team, mg->scal.data(), with_b ? 2 : 1));
   }
   if (!sync) return NF_OK;
@@ -941,7 +1071,7 @@ static int mg_device_loop(nf_mg* mg, int* cycles, double* rn, double* bn, bool* 
   // decision because the all-reduced norms are bit-identical); NCCL inside a WHILE body only on request (=2)
   const bool dist_ok = !L.geom.dist || (!(envd && envd[0] == '0') && team->nccl != nullptr && (nf_p2p_active(team) || force));
   const bool allowed = mg->use_loop && mg->use_graph && !(env && env[0] == '0') && !(envg && envg[0] == '0') &&
-                       nlocal(mg) == 1 && dist_ok && mg->cfg.smoother == 0 && !mg->timing && mg->cfg.max_iterations >= 1 &&
+                       nlocal(mg) == 1 && dist_ok && mg->cfg.smoother == 0 && !mg->timing && !mg->prof && mg->cfg.max_iterations >= 1 &&
                        mg->warm_cycles >= 1 && (mg->cfg.cycle_type == 0 || mg->cfg.cycle_type == 1) &&
                        ((mg->cfg.pre + 2) / 3 + (mg->cfg.post + 2) / 3) % 2 == 0;
   if (!allowed) return NF_OK;
@@ -980,7 +1110,7 @@ static int mg_device_loop(nf_mg* mg, int* cycles, double* rn, double* bn, bool* 
           const nf_grid g = L.geom.grid(team->local[0]);
           st = nfi_residual_norms(ctx, &g, S.x, S.b, S.d_u, S.d_v, S.r, 1, mg->scal[0]);
         }
-        if (st == NF_OK && L.geom.dist) st = nf_team_allreduce(team, mg->scal.data(), 2);
+        if (st == NF_OK && L.geom.dist && !(nf && mg->norm_reduced)) st = nf_team_allreduce(team, mg->scal.data(), 2);
         if (st == NF_OK) {
           k_mg_loop_check<<<1, 1, 0, mg->cap_stream>>>(handle, mg->scal[0], mg->cfg.tolerance, mg->cfg.max_iterations);
           ctx->launches++;
@@ -1202,6 +1332,12 @@ int nfi_mg_solve(nf_mg* mg, double* const* b, double* const* x, double* const* r
     }
   } while (0);
   int st2 = mg_unbind_level0(mg, x, k2, kr);
+  if (mg->prof && !status && sync) {
+    cudaStreamSynchronize(ctx->stream);
+    mg_prof_harvest(mg);
+    mg->psolves++;
+    mg->pcycles += cycles;
+  }
   if (status) return status;
   if (st2) return st2;
   if (info) {

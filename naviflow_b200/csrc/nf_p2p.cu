@@ -106,51 +106,36 @@ __device__ __forceinline__ double ll_load(const uint4* src, unsigned int seq, in
   }
 }
 
-struct HaloSide {
-  const double* src;         // my owned boundary rows
+struct HaloSeg {
+  const double* src;  // my owned boundary rows
+  double* dst;        // my halo rows
+  size_t count;       // doubles; 0 = nothing
+};
+struct HaloSide {            // one neighbour; up to two fields travel in one exchange (segment 1's packets follow segment 0's)
+  HaloSeg seg[2];
+  double* zero;              // optional: halo rows of a third field that are cleared (coarse iterate of a cycle)
+  size_t zero_count;
   uint4* remote_stage;       // neighbour's staging area for packets coming from me (slot 0)
   const uint4* local_stage;  // my staging area for packets coming from this neighbour (slot 0)
-  double* dst;               // my halo rows
-  size_t count;              // doubles; 0 = no neighbour on this side
 };
-
-__global__ void __launch_bounds__(256) k_p2p_halo(HaloSide lo, HaloSide hi, nf_p2p_ctrl* ctrl, size_t stage_elems) {
-  __shared__ unsigned long long s_c;
-  const int tid = threadIdx.x;
-  if (tid == 0) s_c = *(volatile unsigned long long*)&ctrl->halo_count;
-  __syncthreads();
-  const unsigned long long c = s_c;
-  const unsigned int seq = (unsigned int)(c + 1);
-  const size_t slot = (size_t)(c & 1) * stage_elems;
-  const size_t g0 = (size_t)blockIdx.x * blockDim.x + tid, gs = (size_t)gridDim.x * blockDim.x;
-  // 1. push my boundary rows into the neighbours' staging slots
-  for (size_t k = g0; k < lo.count; k += gs) ll_store(lo.remote_stage + slot + k, lo.src[k], seq);
-  for (size_t k = g0; k < hi.count; k += gs) ll_store(hi.remote_stage + slot + k, hi.src[k], seq);
-  // 2. receive the neighbours' rows
-  for (size_t k = g0; k < lo.count; k += gs) lo.dst[k] = ll_load(lo.local_stage + slot + k, seq, &ctrl->error);
-  for (size_t k = g0; k < hi.count; k += gs) hi.dst[k] = ll_load(hi.local_stage + slot + k, seq, &ctrl->error);
-  __syncthreads();
-  if (tid == 0) {
-    __threadfence();
-    const unsigned int t = atomicAdd(&ctrl->ticket[1], 1u);
-    if (t == gridDim.x - 1) {  // everybody has read `c` and finished: advance the sequence, re-arm the ticket
-      ctrl->ticket[1] = 0u;
-      *(volatile unsigned long long*)&ctrl->halo_count = c + 1;
-    }
-  }
-}
 
 struct RedPeers {
   uint4* stage[NF_P2P_MAX_WORLD];  // rank q's red_stage (slot 0, row 0)
 };
+struct RedArgs {  // optional scalar all-reduce riding on a halo exchange (the LAST block of the launch does it)
+  double* buf;
+  int count, rank, world;
+  RedPeers peers;
+};
 
-// sums `count` (<= 8) doubles over the ranks in rank order: identical bits on every rank
-__global__ void k_p2p_allreduce(double* buf, int count, nf_p2p_ctrl* ctrl, RedPeers peers, int rank, int world) {
-  __shared__ unsigned long long s_c;
+// sums `count` (<= 8) doubles over the ranks in rank order: identical bits on every rank.  One block.
+__device__ __forceinline__ void p2p_allreduce_block(double* buf, int count, nf_p2p_ctrl* ctrl, const RedPeers& peers, int rank,
+                                                    int world) {
+  __shared__ unsigned long long s_rc;
   const int tid = threadIdx.x;
-  if (tid == 0) s_c = *(volatile unsigned long long*)&ctrl->red_count;
+  if (tid == 0) s_rc = *(volatile unsigned long long*)&ctrl->red_count;
   __syncthreads();
-  const unsigned long long c = s_c;
+  const unsigned long long c = s_rc;
   const unsigned int seq = (unsigned int)(c + 1);
   const int slot = (int)(c & 1);
   if (tid < count) {
@@ -163,6 +148,56 @@ __global__ void k_p2p_allreduce(double* buf, int count, nf_p2p_ctrl* ctrl, RedPe
   }
   __syncthreads();
   if (tid == 0) *(volatile unsigned long long*)&ctrl->red_count = c + 1;
+}
+
+__global__ void __launch_bounds__(256) k_p2p_halo(HaloSide lo, HaloSide hi, nf_p2p_ctrl* ctrl, size_t stage_elems, RedArgs red) {
+  __shared__ unsigned long long s_c;
+  const int tid = threadIdx.x;
+  unsigned int nb = gridDim.x;  // blocks that move halo rows
+  if (red.count > 0) {
+    --nb;
+    if (blockIdx.x == nb) {
+      p2p_allreduce_block(red.buf, red.count, ctrl, red.peers, red.rank, red.world);
+      return;
+    }
+  }
+  if (tid == 0) s_c = *(volatile unsigned long long*)&ctrl->halo_count;
+  __syncthreads();
+  const unsigned long long c = s_c;
+  const unsigned int seq = (unsigned int)(c + 1);
+  const size_t slot = (size_t)(c & 1) * stage_elems;
+  const size_t g0 = (size_t)blockIdx.x * blockDim.x + tid, gs = (size_t)nb * blockDim.x;
+  // 1. push my boundary rows into the neighbours' staging slots
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const size_t off_lo = q ? lo.seg[0].count : 0, off_hi = q ? hi.seg[0].count : 0;
+    for (size_t k = g0; k < lo.seg[q].count; k += gs) ll_store(lo.remote_stage + slot + off_lo + k, lo.seg[q].src[k], seq);
+    for (size_t k = g0; k < hi.seg[q].count; k += gs) ll_store(hi.remote_stage + slot + off_hi + k, hi.seg[q].src[k], seq);
+  }
+  for (size_t k = g0; k < lo.zero_count; k += gs) lo.zero[k] = 0.0;
+  for (size_t k = g0; k < hi.zero_count; k += gs) hi.zero[k] = 0.0;
+  // 2. receive the neighbours' rows
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const size_t off_lo = q ? lo.seg[0].count : 0, off_hi = q ? hi.seg[0].count : 0;
+    for (size_t k = g0; k < lo.seg[q].count; k += gs)
+      lo.seg[q].dst[k] = ll_load(lo.local_stage + slot + off_lo + k, seq, &ctrl->error);
+    for (size_t k = g0; k < hi.seg[q].count; k += gs)
+      hi.seg[q].dst[k] = ll_load(hi.local_stage + slot + off_hi + k, seq, &ctrl->error);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    const unsigned int t = atomicAdd(&ctrl->ticket[1], 1u);
+    if (t == nb - 1) {  // everybody has read `c` and finished: advance the sequence, re-arm the ticket
+      ctrl->ticket[1] = 0u;
+      *(volatile unsigned long long*)&ctrl->halo_count = c + 1;
+    }
+  }
+}
+
+__global__ void k_p2p_allreduce(double* buf, int count, nf_p2p_ctrl* ctrl, RedPeers peers, int rank, int world) {
+  p2p_allreduce_block(buf, count, ctrl, peers, rank, world);
 }
 
 struct SharePeers {
@@ -388,11 +423,35 @@ void nf_team_release(nf_team* team, void* ptr) {
 }
 
 // ---- the three collectives ------------------------------------------------------------------------------------------
-// returns NF_ERR_UNSUPPORTED when this call cannot take the peer path (caller falls back to NCCL)
-int nf_p2p_exchange(nf_team* team, const LevelGeom& geom, double* field, int depth) {
+static int p2p_red_peers(nf_p2p* P, RedPeers* peers) {
+  memset(peers, 0, sizeof(*peers));
+  for (int q = 0; q < P->world; ++q) {
+    char* rctrl = p2p_translate(P, P->ctrl, q);
+    if (!rctrl) return NF_ERR_UNSUPPORTED;
+    nf_p2p_ctrl* rc = (nf_p2p_ctrl*)rctrl;
+    peers->stage[q] = &rc->red_stage[0][0][0];
+  }
+  return NF_OK;
+}
+
+// rows exchanged across the boundary between ranks lo and lo+1 (symmetric: both sides compute the same number)
+static int p2p_depth(const LevelGeom& geom, int lo, int depth) {
+  int d = depth;
+  if (d > geom.halo) d = geom.halo;
+  if (d > geom.ge[lo] - geom.gb[lo]) d = geom.ge[lo] - geom.gb[lo];
+  if (d > geom.ge[lo + 1] - geom.gb[lo + 1]) d = geom.ge[lo + 1] - geom.gb[lo + 1];
+  return d;
+}
+
+// One kernel: halo rows of up to two fields (possibly of different levels), optionally the halo rows of `zero` (same
+// geometry as field 1... of `zgeom`) cleared, optionally `red_count` scalars summed over all ranks.
+// returns NF_ERR_UNSUPPORTED when this call cannot take the peer path (caller falls back to separate collectives)
+int nf_p2p_exchange_multi(nf_team* team, int nfields, const LevelGeom* const* geoms, double* const* fields, const int* depths,
+                          const LevelGeom* zgeom, double* zero, double* red_buf, int red_count) {
   nf_ctx* ctx = team->ctx;
   nf_p2p* P = team->p2p;
   const int r = P->rank;
+  if (nfields < 1 || nfields > 2 || red_count > NF_P2P_RED_MAX) return NF_ERR_UNSUPPORTED;
   HaloSide side[2];
   memset(side, 0, sizeof(side));
   size_t total = 0;
@@ -400,39 +459,60 @@ int nf_p2p_exchange(nf_team* team, const LevelGeom& geom, double* field, int dep
     const int q = s == 0 ? r - 1 : r + 1;
     if (q < 0 || q >= team->world) continue;
     const int lo = s == 0 ? q : r;  // the boundary lies between ranks lo and lo+1
-    const int B = geom.ge[lo];
-    int d = depth;
-    if (d > geom.ge[lo] - geom.gb[lo]) d = geom.ge[lo] - geom.gb[lo];
-    if (d > geom.ge[lo + 1] - geom.gb[lo + 1]) d = geom.ge[lo + 1] - geom.gb[lo + 1];
-    const size_t count = (size_t)d * geom.ld;
-    if (count == 0) continue;
-    if (count > P->stage_elems) return NF_ERR_UNSUPPORTED;
     HaloSide& H = side[s];
-    H.count = count;
-    // rows [B-d, B) are owned by lo, rows [B, B+d) by lo+1
-    if (s == 0) {  // I am lo+1: send my first d owned rows, receive rows [B-d, B)
-      H.src = field + (size_t)(B - geom.row0(r)) * geom.ld;
-      H.dst = field + (size_t)(B - d - geom.row0(r)) * geom.ld;
-    } else {       // I am lo: send my last d owned rows, receive rows [B, B+d)
-      H.src = field + (size_t)(B - d - geom.row0(r)) * geom.ld;
-      H.dst = field + (size_t)(B - geom.row0(r)) * geom.ld;
+    size_t staged = 0;
+    for (int f = 0; f < nfields; ++f) {
+      const LevelGeom& geom = *geoms[f];
+      const int B = geom.ge[lo];
+      const int d = p2p_depth(geom, lo, depths[f]);
+      const size_t count = (size_t)d * geom.ld;
+      H.seg[f].count = count;
+      if (count == 0) continue;
+      // rows [B-d, B) are owned by lo, rows [B, B+d) by lo+1
+      if (s == 0) {  // I am lo+1: send my first d owned rows, receive rows [B-d, B)
+        H.seg[f].src = fields[f] + (size_t)(B - geom.row0(r)) * geom.ld;
+        H.seg[f].dst = fields[f] + (size_t)(B - d - geom.row0(r)) * geom.ld;
+      } else {       // I am lo: send my last d owned rows, receive rows [B, B+d)
+        H.seg[f].src = fields[f] + (size_t)(B - d - geom.row0(r)) * geom.ld;
+        H.seg[f].dst = fields[f] + (size_t)(B - geom.row0(r)) * geom.ld;
+      }
+      staged += count;
     }
+    if (zero && zgeom) {
+      const int B = zgeom->ge[lo];
+      const int d = p2p_depth(*zgeom, lo, zgeom->halo);
+      H.zero_count = (size_t)d * zgeom->ld;
+      H.zero = zero + (size_t)((s == 0 ? B - d : B) - zgeom->row0(r)) * zgeom->ld;
+    }
+    if (staged > P->stage_elems) return NF_ERR_UNSUPPORTED;
+    if (staged == 0 && H.zero_count == 0) continue;
     // the neighbour stages what comes from me in its "from upper" area when I am above it (s == 0), else "from lower"
     char* rstage = p2p_translate(P, P->stage + (size_t)(s == 0 ? 1 : 0) * 2 * P->stage_elems, q);
     if (!rstage) return NF_ERR_UNSUPPORTED;
     H.remote_stage = (uint4*)rstage;
     H.local_stage = P->stage + (size_t)s * 2 * P->stage_elems;
-    total += count;
+    total += staged + H.zero_count;
   }
-  if (total == 0) return NF_OK;
+  RedArgs red;
+  memset(&red, 0, sizeof(red));
+  if (red_count > 0 && red_buf) {
+    if (p2p_red_peers(P, &red.peers) != NF_OK) return NF_ERR_UNSUPPORTED;
+    red.buf = red_buf; red.count = red_count; red.rank = P->rank; red.world = P->world;
+  }
+  if (total == 0 && red.count == 0) return NF_OK;
   static const int per_block = getenv("NF_P2P_BLOCK_BYTES") ? atoi(getenv("NF_P2P_BLOCK_BYTES")) : 8192;
   static const int max_blocks = getenv("NF_P2P_MAX_BLOCKS") ? atoi(getenv("NF_P2P_MAX_BLOCKS")) : 96;
   int blocks = (int)((total * sizeof(double) + per_block - 1) / per_block);
   if (blocks < 1) blocks = 1;
   if (blocks > max_blocks) blocks = max_blocks;
-  k_p2p_halo<<<blocks, 256, 0, ctx->stream>>>(side[0], side[1], P->ctrl, P->stage_elems);
+  k_p2p_halo<<<blocks + (red.count > 0 ? 1 : 0), 256, 0, ctx->stream>>>(side[0], side[1], P->ctrl, P->stage_elems, red);
   NF_LAUNCH_CHECK(ctx);
   return NF_OK;
+}
+
+int nf_p2p_exchange(nf_team* team, const LevelGeom& geom, double* field, int depth) {
+  const LevelGeom* g = &geom;
+  return nf_p2p_exchange_multi(team, 1, &g, &field, &depth, nullptr, nullptr, nullptr, 0);
 }
 
 int nf_p2p_allreduce(nf_team* team, double* buf, size_t count) {
@@ -440,13 +520,7 @@ int nf_p2p_allreduce(nf_team* team, double* buf, size_t count) {
   nf_p2p* P = team->p2p;
   if (count > NF_P2P_RED_MAX) return NF_ERR_UNSUPPORTED;
   RedPeers peers;
-  memset(&peers, 0, sizeof(peers));
-  for (int q = 0; q < P->world; ++q) {
-    char* rctrl = p2p_translate(P, P->ctrl, q);
-    if (!rctrl) return NF_ERR_UNSUPPORTED;
-    nf_p2p_ctrl* rc = (nf_p2p_ctrl*)rctrl;
-    peers.stage[q] = &rc->red_stage[0][0][0];
-  }
+  if (p2p_red_peers(P, &peers) != NF_OK) return NF_ERR_UNSUPPORTED;
   k_p2p_allreduce<<<1, 32, 0, ctx->stream>>>(buf, (int)count, P->ctrl, peers, P->rank, P->world);
   NF_LAUNCH_CHECK(ctx);
   return NF_OK;

@@ -96,6 +96,10 @@ void nf_p2p_destroy(nf_team* team);
 bool nf_p2p_active(const nf_team* team);
 int nf_p2p_exchange(nf_team* team, const LevelGeom& geom, double* field, int depth);
 int nf_p2p_allreduce(nf_team* team, double* buf, size_t count);
+// one launch: halo rows of up to two fields (levels may differ), optionally `zero`'s halo rows (geometry zgeom) cleared and
+// red_count (<= 8) scalars summed over the ranks; NF_ERR_UNSUPPORTED = not possible here, use the separate collectives
+int nf_p2p_exchange_multi(nf_team* team, int nfields, const LevelGeom* const* geoms, double* const* fields, const int* depths,
+                          const LevelGeom* zgeom, double* zero, double* red_buf, int red_count);
 int nf_p2p_share_rows(nf_team* team, int ld, int nx, const std::vector<int>& gb, const std::vector<int>& ge, double* array,
                       int utype);
 int nf_p2p_error(nf_team* team);
