@@ -55,6 +55,39 @@ struct nf_ctx {
     }                                                                                   \
   } while (0)
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------------
+// The kernels of a multigrid cycle are short (a few microseconds on the coarse levels) and strictly ordered, so the gap
+// between two of them -- drain, flush, grid launch, parameter fetch, CTA dispatch: ~2-3 us -- is a sizeable share of the
+// cycle.  A kernel that begins with nf_pdl_entry() may be launched with nf_launch(..., pdl = true): its CTAs are
+// dispatched while the previous kernel of the stream still runs (that one has released them with
+// griddepcontrol.launch_dependents) and block in griddepcontrol.wait until the previous grid has completed and its
+// writes are visible.  Nothing before the wait touches global memory, every thread executes it, and a kernel launched
+// without the attribute (or after a copy / memset) keeps the full dependency, so the order of all memory effects is
+// unchanged.  Stream capture turns the attribute into a programmatic edge of the CUDA graph.  NF_PDL=0 switches it off.
+__device__ __forceinline__ void nf_pdl_entry() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#ifdef NF_PDL_EARLY_TRIGGER
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+bool nfi_pdl_enabled();
+
+template <class... KArgs, class... Args>
+inline cudaError_t nf_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl,
+                             Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl && nfi_pdl_enabled()) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // element [i][j] of a field stored from global row g.row0 with pitch g.ld
 __device__ __forceinline__ size_t nf_idx(const nf_grid& g, int i, int j) {
   return (size_t)(i - g.row0) * (size_t)g.ld + (size_t)j;

@@ -1,4 +1,6 @@
 // nf_ctx.cu -- context object of libnaviflow_b200 (stream, reduction scratch, error text).
+#include <stdlib.h>
+
 #include "nf_common.cuh"
 
 #define NF_VERSION 100
@@ -79,4 +81,13 @@ int nf_read_scalars(nf_ctx* ctx, int first, int count, double* out_host) {
   NF_CHECK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   for (int k = 0; k < count; ++k) out_host[k] = ctx->scalars_host[first + k];
   return NF_OK;
+}
+
+// NF_PDL=0: launch every kernel with the full stream dependency (see nf_common.cuh)
+bool nfi_pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("NF_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
 }

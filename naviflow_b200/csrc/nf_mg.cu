@@ -190,6 +190,7 @@ __global__ void k_coarse_invert(nf_grid g, const double* __restrict__ d_u, const
 // x = Inv * b on the coarsest level (b, x pitched 2-D arrays); one warp per row
 __global__ void k_coarse_apply(nf_grid g, const double* __restrict__ Inv, const double* __restrict__ b,
                                double* __restrict__ x, int N) {
+  nf_pdl_entry();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= N) return;
   double acc = 0.0;
@@ -747,7 +748,7 @@ static int mg_coarse_solve(nf_mg* mg, int l) {
   const int threads = 128, blocks = (N * 32 + threads - 1) / threads;
   MgProf prof_(mg, l, PH_COARSE);
   for (int k = 0; k < nlocal(mg); ++k) {
-    k_coarse_apply<<<blocks, threads, 0, ctx->stream>>>(L.geom.grid(mg->team->local[k]), mg->coarse_inv[k], L.s[k].b,
+    nf_launch(k_coarse_apply, blocks, threads, 0, ctx->stream, true, L.geom.grid(mg->team->local[k]), mg->coarse_inv[k], L.s[k].b,
                                                         L.s[k].x, N);
     NF_LAUNCH_CHECK(ctx);
   }
@@ -1049,6 +1050,7 @@ static int mg_rel_residual(nf_mg* mg, int l, double* r_norm, double* b_norm, int
 // reads {sum r^2, sum b^2, cycles} once: no per-cycle D2H + synchronisation, no per-cycle graph launch.
 // scal[0][4] is the cycle counter (a double so that one 40-byte copy brings everything back).
 __global__ void k_mg_loop_check(cudaGraphConditionalHandle handle, double* scal, double tol, int max_it) {
+  nf_pdl_entry();
   const double c = scal[4] + 1.0;
   scal[4] = c;
   const double rn = sqrt(scal[0]), bn = sqrt(scal[1]);
@@ -1112,7 +1114,7 @@ static int mg_device_loop(nf_mg* mg, int* cycles, double* rn, double* bn, bool* 
         }
         if (st == NF_OK && L.geom.dist && !(nf && mg->norm_reduced)) st = nf_team_allreduce(team, mg->scal.data(), 2);
         if (st == NF_OK) {
-          k_mg_loop_check<<<1, 1, 0, mg->cap_stream>>>(handle, mg->scal[0], mg->cfg.tolerance, mg->cfg.max_iterations);
+          nf_launch(k_mg_loop_check, 1, 1, 0, mg->cap_stream, true, handle, mg->scal[0], mg->cfg.tolerance, mg->cfg.max_iterations);
           ctx->launches++;
         }
         ctx->stream = orig;

@@ -64,6 +64,7 @@ __device__ __forceinline__ double tail_res(const TailSm& L, int i, int j) {
 }
 
 __global__ void __launch_bounds__(TAIL_THREADS, 1) k_mg_tail(nf_tail_args a) {
+  nf_pdl_entry();
   extern __shared__ __align__(16) double sm[];
   __shared__ TailSm lv[NF_TAIL_MAX_LEVELS];
   const int tid = threadIdx.x;
@@ -173,7 +174,7 @@ int nfi_mg_tail(nf_ctx* ctx, const nf_tail_args* a) {
     NF_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_mg_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
-  k_mg_tail<<<1, TAIL_THREADS, smem, ctx->stream>>>(*a);
+  nf_launch(k_mg_tail, 1, TAIL_THREADS, smem, ctx->stream, true, *a);
   NF_LAUNCH_CHECK(ctx);
   return NF_OK;
 }

@@ -151,6 +151,7 @@ __device__ __forceinline__ void p2p_allreduce_block(double* buf, int count, nf_p
 }
 
 __global__ void __launch_bounds__(256) k_p2p_halo(HaloSide lo, HaloSide hi, nf_p2p_ctrl* ctrl, size_t stage_elems, RedArgs red) {
+  nf_pdl_entry();
   __shared__ unsigned long long s_c;
   const int tid = threadIdx.x;
   unsigned int nb = gridDim.x;  // blocks that move halo rows
@@ -197,6 +198,7 @@ __global__ void __launch_bounds__(256) k_p2p_halo(HaloSide lo, HaloSide hi, nf_p
 }
 
 __global__ void k_p2p_allreduce(double* buf, int count, nf_p2p_ctrl* ctrl, RedPeers peers, int rank, int world) {
+  nf_pdl_entry();
   p2p_allreduce_block(buf, count, ctrl, peers, rank, world);
 }
 
@@ -505,7 +507,7 @@ int nf_p2p_exchange_multi(nf_team* team, int nfields, const LevelGeom* const* ge
   int blocks = (int)((total * sizeof(double) + per_block - 1) / per_block);
   if (blocks < 1) blocks = 1;
   if (blocks > max_blocks) blocks = max_blocks;
-  k_p2p_halo<<<blocks + (red.count > 0 ? 1 : 0), 256, 0, ctx->stream>>>(side[0], side[1], P->ctrl, P->stage_elems, red);
+  nf_launch(k_p2p_halo, blocks + (red.count > 0 ? 1 : 0), 256, 0, ctx->stream, true, side[0], side[1], P->ctrl, P->stage_elems, red);
   NF_LAUNCH_CHECK(ctx);
   return NF_OK;
 }
@@ -521,7 +523,7 @@ int nf_p2p_allreduce(nf_team* team, double* buf, size_t count) {
   if (count > NF_P2P_RED_MAX) return NF_ERR_UNSUPPORTED;
   RedPeers peers;
   if (p2p_red_peers(P, &peers) != NF_OK) return NF_ERR_UNSUPPORTED;
-  k_p2p_allreduce<<<1, 32, 0, ctx->stream>>>(buf, (int)count, P->ctrl, peers, P->rank, P->world);
+  nf_launch(k_p2p_allreduce, 1, 32, 0, ctx->stream, true, buf, (int)count, P->ctrl, peers, P->rank, P->world);
   NF_LAUNCH_CHECK(ctx);
   return NF_OK;
 }

@@ -147,6 +147,7 @@ template <bool WITH_B>
 __global__ void k_residual_norms(nf_grid g, const double* __restrict__ p, const double* __restrict__ b,
                                  const double* __restrict__ d_u, const double* __restrict__ d_v,
                                  double* __restrict__ r, double* partials, unsigned int* ticket, double* out) {
+  nf_pdl_entry();
   double acc[WITH_B ? 2 : 1];
   acc[0] = 0.0;
   if (WITH_B) acc[WITH_B ? 1 : 0] = 0.0;
@@ -341,9 +342,9 @@ int nfi_residual_norms(nf_ctx* ctx, const nf_grid* g, const double* p, const dou
                        const double* d_v, double* r, int with_b, double* out) {
   NfLaunch2D l = nf_launch_reduce(g->ge - g->gb, g->ny);
   if (with_b)
-    k_residual_norms<true><<<l.grid, l.block, 0, ctx->stream>>>(*g, p, b, d_u, d_v, r, ctx->partials, ctx->ticket, out);
+    nf_launch(k_residual_norms<true>, l.grid, l.block, 0, ctx->stream, true, *g, p, b, d_u, d_v, r, ctx->partials, ctx->ticket, out);
   else
-    k_residual_norms<false><<<l.grid, l.block, 0, ctx->stream>>>(*g, p, b, d_u, d_v, r, ctx->partials, ctx->ticket, out);
+    nf_launch(k_residual_norms<false>, l.grid, l.block, 0, ctx->stream, true, *g, p, b, d_u, d_v, r, ctx->partials, ctx->ticket, out);
   NF_LAUNCH_CHECK(ctx);
   return NF_OK;
 }
@@ -360,6 +361,7 @@ int nfi_sumsq_dev(nf_ctx* ctx, const nf_grid* g, const double* x, int interior_o
 }
 
 __global__ void k_fill(double* __restrict__ x, size_t n, double v) {
+  nf_pdl_entry();
   for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x)
     x[k] = v;
 }
@@ -372,7 +374,7 @@ int nfi_fill(nf_ctx* ctx, double* x, size_t count, double value) {
   }
   size_t blocks = (count + 255) / 256;
   if (blocks > (size_t)NF_SM_COUNT * 16) blocks = (size_t)NF_SM_COUNT * 16;
-  k_fill<<<(unsigned)blocks, 256, 0, ctx->stream>>>(x, count, value);
+  nf_launch(k_fill, (unsigned)blocks, 256, 0, ctx->stream, true, x, count, value);
   NF_LAUNCH_CHECK(ctx);
   return NF_OK;
 }

@@ -185,6 +185,7 @@ __global__ void __launch_bounds__(32 * NYT, 1)
 k_rbsor_fused(nf_grid g, const double* __restrict__ pin, double* __restrict__ pout, const double* __restrict__ b,
               const double* __restrict__ d_u, const double* __restrict__ d_v, const double* __restrict__ inv,
               double omega) {
+  nf_pdl_entry();
   constexpr int H = 2 * NS;
   constexpr int TR = RRW - 2 * H;
   constexpr int TC = RCW - 2 * H;
@@ -270,8 +271,8 @@ int launch_fused(nf_ctx* ctx, const nf_grid* g, const double* pin, double* pout,
   constexpr int TR = RRW - 2 * H, TC = RCW - 2 * H;
   dim3 block(32, NYT, 1);
   dim3 grid((g->ny + TC - 1) / TC, (g->ge - g->gb + TR - 1) / TR, 1);
-  if (inv) k_rbsor_fused<NS, true><<<grid, block, 0, ctx->stream>>>(*g, pin, pout, b, d_u, d_v, inv, omega);
-  else k_rbsor_fused<NS, false><<<grid, block, 0, ctx->stream>>>(*g, pin, pout, b, d_u, d_v, nullptr, omega);
+  if (inv) nf_launch(k_rbsor_fused<NS, true>, grid, block, 0, ctx->stream, true, *g, pin, pout, b, d_u, d_v, inv, omega);
+  else nf_launch(k_rbsor_fused<NS, false>, grid, block, 0, ctx->stream, true, *g, pin, pout, b, d_u, d_v, nullptr, omega);
   NF_LAUNCH_CHECK(ctx);
   return NF_OK;
 }
@@ -352,6 +353,7 @@ k_rbsor_tma(nf_grid g, const __grid_constant__ CUtensorMap map_p, const __grid_c
             const __grid_constant__ CUtensorMap map_du, const __grid_constant__ CUtensorMap map_dv,
             const __grid_constant__ CUtensorMap map_inv, double* __restrict__ pout, double omega, int tiles_x,
             int n_tiles, TmaExtra ex) {
+  nf_pdl_entry();
   constexpr unsigned TX_BYTES = HAS_INV ? ST_END : ST_INV;
   using TG = TileGeom<NS, EXTRA>;
   constexpr int HR = TG::HR, HC = TG::HC, TR = TG::TR, TC = TG::TC;
@@ -646,7 +648,7 @@ int launch_tma(nf_ctx* ctx, const nf_grid* g, const double* pin, double* pout, c
     attr_set = true;
   }
   const int grid = n_tiles < NF_SM_COUNT ? n_tiles : NF_SM_COUNT;
-  k_rbsor_tma<NS, HAS_INV, EXTRA><<<grid, dim3(32, NYT, 1), SMEM, ctx->stream>>>(*g, mp, mb, mu, mv, mi, pout, omega,
+  nf_launch(k_rbsor_tma<NS, HAS_INV, EXTRA>, grid, dim3(32, NYT, 1), SMEM, ctx->stream, true, *g, mp, mb, mu, mv, mi, pout, omega,
                                                                                  tiles_x, n_tiles, ex);
   NF_LAUNCH_CHECK(ctx);
   *used = true;

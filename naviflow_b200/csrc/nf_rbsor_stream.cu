@@ -427,7 +427,7 @@ k_rbsor_stream(nf_grid g, const __grid_constant__ StreamMaps maps, double* __res
   extern __shared__ __align__(128) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int job = blockIdx.x * WPC + warp;
-  if (job >= plan.njobs) return;
+  if (job >= plan.njobs) { nf_pdl_entry(); return; }
   unsigned char* ring = smem + (size_t)warp * (NSTG * SG_BYTES);
   const unsigned bar0 = s_u32(smem + (size_t)WPC * NSTG * SG_BYTES + warp * NSTG * 8);
   const unsigned ring_u = s_u32(ring);
@@ -463,6 +463,7 @@ k_rbsor_stream(nf_grid g, const __grid_constant__ StreamMaps maps, double* __res
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
+  nf_pdl_entry();  // everything above is launch-independent set-up; the first TMA load follows
 
   auto issue = [&](int s) {  // stage of steps s .. s+RB-1: rows s.. of p, d_u; rows s-1.. of d_v, b, 1/aP
     const int q = ((s - jb.r0) / RB) & (NSTG - 1);
@@ -644,7 +645,7 @@ int launch_stream(nf_ctx* ctx, const nf_grid* g, const double* pin, double* pout
     attr_set = true;
   }
   const int grid = (plan.njobs + WPC - 1) / WPC;
-  k_rbsor_stream<NS, WPC, EXTRA, PRL><<<grid, 32 * WPC, SMEM, ctx->stream>>>(*g, m, pout, omega, plan, ex);
+  nf_launch(k_rbsor_stream<NS, WPC, EXTRA, PRL>, grid, 32 * WPC, SMEM, ctx->stream, true, *g, m, pout, omega, plan, ex);
   NF_LAUNCH_CHECK(ctx);
   *used = true;
   return NF_OK;

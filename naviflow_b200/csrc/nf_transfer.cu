@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(256)
 k_residual_restrict_fw(nf_grid gf, const double* __restrict__ p, const double* __restrict__ b,
                        const double* __restrict__ d_u, const double* __restrict__ d_v, nf_grid gc,
                        double* __restrict__ c, double* __restrict__ x0) {
+  nf_pdl_entry();
   __shared__ double sR[2 * RR_CR + 1][2 * RR_CC + 2];
   const int tx = threadIdx.x, ty = threadIdx.y;  // 128 x 2
   const int I0 = gc.gb + blockIdx.y * RR_CR, J0 = blockIdx.x * RR_CC;
@@ -130,6 +131,7 @@ template <bool ADD>
 __global__ void __launch_bounds__(256)
 k_prolong_linear(nf_grid gc, const double* __restrict__ c, nf_grid gf, double* __restrict__ f, int nI, int nJ,
                  int nby_fast, int I_lo, int I_hi) {
+  nf_pdl_entry();
   if ((int)blockIdx.y < nby_fast) {
     const int J = blockIdx.x * 32 + threadIdx.x;
     const int I = I_lo + blockIdx.y * 8 + threadIdx.y;
@@ -225,7 +227,7 @@ int nfi_restrict_fw(nf_ctx* ctx, const nf_grid* gf, const double* f, const nf_gr
 int nfi_residual_restrict_fw(nf_ctx* ctx, const nf_grid* gf, const double* p, const double* b, const double* d_u,
                              const double* d_v, const nf_grid* gc, double* c, double* x0) {
   dim3 grid((gc->ny + RR_CC - 1) / RR_CC, (gc->ge - gc->gb + RR_CR - 1) / RR_CR, 1);
-  k_residual_restrict_fw<<<grid, dim3(128, 2, 1), 0, ctx->stream>>>(*gf, p, b, d_u, d_v, *gc, c, x0);
+  nf_launch(k_residual_restrict_fw, grid, dim3(128, 2, 1), 0, ctx->stream, true, *gf, p, b, d_u, d_v, *gc, c, x0);
   NF_LAUNCH_CHECK(ctx);
   return NF_OK;
 }
@@ -281,8 +283,8 @@ int nfi_prolong_linear(nf_ctx* ctx, const nf_grid* gc, const double* c, const nf
   const long long strip = (long long)(1 + gf->nx - (2 * nI + 1)) * gf->ny + (long long)(1 + gf->ny - (2 * nJ + 1)) * (2 * nI);
   const int nby_strip = (int)((strip + (long long)gx * 256 - 1) / ((long long)gx * 256));
   dim3 grid(gx, nby_fast + nby_strip, 1), block(32, 8, 1);
-  if (add) k_prolong_linear<true><<<grid, block, 0, ctx->stream>>>(*gc, c, *gf, f, nI, nJ, nby_fast, I_lo, I_hi);
-  else k_prolong_linear<false><<<grid, block, 0, ctx->stream>>>(*gc, c, *gf, f, nI, nJ, nby_fast, I_lo, I_hi);
+  if (add) nf_launch(k_prolong_linear<true>, grid, block, 0, ctx->stream, true, *gc, c, *gf, f, nI, nJ, nby_fast, I_lo, I_hi);
+  else nf_launch(k_prolong_linear<false>, grid, block, 0, ctx->stream, true, *gc, c, *gf, f, nI, nJ, nby_fast, I_lo, I_hi);
   NF_LAUNCH_CHECK(ctx);
   return NF_OK;
 }
