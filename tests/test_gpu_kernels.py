@@ -265,11 +265,17 @@ def test_fused_rbsor_large_grid_matches_unfused(n, path, monkeypatch):
         np.testing.assert_array_equal(d.down(p), d.down(p2))
 
 
-@pytest.mark.parametrize("n", [9, 31, 40, 64, 65, 130, 257])
-def test_fused_momentum_sweeps_are_bit_identical(n):
-    """Temporally blocked Jacobi momentum sweeps + fused residual against the sweep-by-sweep kernels."""
+@pytest.mark.parametrize("n,tma", [(9, "-1"), (31, "-1"), (40, "-1"), (64, "-1"), (65, "-1"), (130, "-1"), (257, "-1"),
+                                   (9, "0"), (40, "0"), (65, "0"), (130, "0"), (257, "0"), (1200, None)])
+def test_fused_momentum_sweeps_are_bit_identical(n, tma, monkeypatch):
+    """Temporally blocked Jacobi momentum sweeps + fused residual against the sweep-by-sweep kernels; both operand paths of
+    the fused kernel (NF_MOMENTUM_TMA=-1: loads by the threads, =0: TMA prefetch stage on every grid, default: on large grids)."""
     from gpu_util import Dev, NfLinks, bc_program_struct, ptr
     from naviflow_b200.host import practice_b_sides
+    if tma is None:
+        monkeypatch.delenv("NF_MOMENTUM_TMA", raising=False)
+    else:
+        monkeypatch.setenv("NF_MOMENTUM_TMA", tma)
     s = synth(n, 3000 + n)
     bc = cavity_bc()
     d = Dev(n)
