@@ -694,7 +694,11 @@ int nfi_rbsor_fused_x(nf_ctx* ctx, const nf_grid* g, double** p, double** palt, 
   }
   // TMA path: 16-byte aligned arrays, pitch a multiple of 2 doubles, enough rows for a persistent pipeline
   const char* env = getenv("NF_RBSOR_TMA");
-  const int tma_min_rows = env ? atoi(env) : 600;  // NF_RBSOR_TMA=0 forces TMA everywhere, a huge value disables it
+  // NF_RBSOR_TMA=rows: minimum level size (a huge value disables the kernel).  Default: every level a CTA can tile (>= 64
+  // rows).  Round 1 used it from 600 rows up "for the pipeline"; what pays on the small levels is the FUSION that comes with
+  // it (residual + restriction / norms inside the smoother launch instead of a 13-17 us latency-bound kernel of their own):
+  // 15.25 -> 14.83 ms per outer iteration at 4097^2 (levels 511, 255, 127)
+  const int tma_min_rows = env ? atoi(env) : 64;
   const bool use_tma = g->nx >= tma_min_rows && (g->ge - g->gb) >= 64;
   const char* envx = getenv("NF_RBSOR_EXTRA");
   const bool allow_extra = !(envx && envx[0] == '0');

@@ -738,8 +738,12 @@ def test_multigrid_device_side_convergence_loop_equals_host_loop(n, kw, monkeypa
         outs.append((p, info, ps.last_info.cycles))
     assert outs[0][2] == outs[1][2] and outs[0][2] >= 1
     np.testing.assert_array_equal(outs[0][0], outs[1][0])
-    assert outs[0][1]["rel_norm"] == outs[1][1]["rel_norm"]
-    np.testing.assert_array_equal(outs[0][1]["field"], outs[1][1]["field"])
+    # the iterate is the same bit for bit; the NORM may differ in the last place: below 1500 rows the host loop takes it
+    # from the next cycle's pre-smoothing launch ("lookahead"), the device loop from the post-smoothing launch -- two
+    # summation orders of the same residual
+    assert abs(outs[0][1]["rel_norm"] - outs[1][1]["rel_norm"]) <= 1e-12 * outs[1][1]["rel_norm"]
+    np.testing.assert_allclose(outs[0][1]["field"], outs[1][1]["field"], rtol=0,
+                               atol=1e-18 + 1e-12 * np.abs(outs[1][1]["field"]).max())
 
 
 def test_multigrid_lookahead_norm_on_slabs(monkeypatch):
@@ -985,6 +989,28 @@ def test_outer_iteration_at_1025_vs_oracle():
     alg.solve(max_iterations=2, tolerance=0.0)
     cfg = O.MGConfig(omega=1.5, pre=3, post=3, max_iterations=3, tolerance=1e-30)
     st, _ = O.simple_solve(n, n, Re, O.make_pressure_solver("mg", cfg=cfg), n_sweeps=k, max_iterations=2, tolerance=0.0)
+    for fld in ("u", "v", "p"):
+        e = rel(getattr(alg, fld), getattr(st, fld))
+        assert e < 1e-10, (fld, e)
+
+
+def test_four_slab_outer_iteration_at_2049_vs_oracle():
+    """One SIMPLE outer iteration at 2049^2 cut into 4 row slabs (two multigrid levels cut, the rest replicated; streaming
+    smoother with fused restriction / norms on the slabs) against the ORACLE port, not against the single-slab GPU run:
+    u, v, p <= 1e-10 (2 V(3,3) cycles in the pressure solve keep the port at ~20 s)."""
+    import naviflow_b200 as nb
+    n, Re, k = 2049, 1000, 3
+    mesh, fluid = cavity(n, Re)
+    ps = nb.GpuMultiGridSolver(smoother=nb.GpuGaussSeidelSolver(omega=1.5), max_iterations=2, tolerance=1e-30,
+                               pre_smoothing=3, post_smoothing=3)
+    alg = nb.GpuSimpleSolver(mesh, fluid, ps, nb.GpuJacobiMomentumSolver(n_jacobi_sweeps=k), alpha_p=0.3, alpha_u=0.7,
+                             virtual_ranks=4)
+    alg.set_boundary_condition("top", "velocity", {"u": 1.0, "v": 0.0})
+    for b in ("bottom", "left", "right"):
+        alg.set_boundary_condition(b, "wall")
+    alg.solve(max_iterations=1, tolerance=0.0)
+    cfg = O.MGConfig(omega=1.5, pre=3, post=3, max_iterations=2, tolerance=1e-30)
+    st, _ = O.simple_solve(n, n, Re, O.make_pressure_solver("mg", cfg=cfg), n_sweeps=k, max_iterations=1, tolerance=0.0)
     for fld in ("u", "v", "p"):
         e = rel(getattr(alg, fld), getattr(st, fld))
         assert e < 1e-10, (fld, e)
