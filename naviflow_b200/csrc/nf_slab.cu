@@ -270,8 +270,15 @@ extern "C" int nf_team_create_nccl(nf_ctx* ctx, int world, int rank, const void*
     t->nccl = comm;
     // exchanges by the ranks' own kernels over NVLink peer memory unless NF_P2P=0 (then, or when cudaIpc is not
     // available, grouped ncclSend/ncclRecv)
+    // The ranks must take the same branch (nf_p2p_enable is a sequence of collectives): agree on the switch first, so that
+    // an environment that differs between the ranks selects NCCL everywhere instead of deadlocking.
     const char* env = getenv("NF_P2P");
-    if (!(env && env[0] == '0') && api->AllGather) {
+    int want = (!(env && env[0] == '0') && api->AllGather) ? 1 : 0, all_want = 0;
+    {
+      int st = nf_nccl_all_ok(t, want, &all_want);
+      if (st != NF_OK) { nf_team_destroy(t); return st; }
+    }
+    if (all_want) {
       int st = nf_p2p_enable(t, rank);
       if (st != NF_OK) { nf_team_destroy(t); return st; }
     }
