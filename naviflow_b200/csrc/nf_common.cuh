@@ -265,5 +265,5 @@ int nfi_rbsor_stream(nf_ctx*, const nf_grid*, const double* pin, double* pout, c
                      const double* d_v, const double* inv, double omega, int ns, int mode, const nf_smooth_extra* extra,
                      bool* used);
 bool nfi_rbsor_stream_enabled(const nf_grid* g);
-bool nfi_rbsor_can_fuse_prolong(const nf_grid* g, int n_sweeps, bool has_inv);
+int nfi_rbsor_can_fuse_prolong(const nf_grid* g, int n_sweeps, bool has_inv);
 void nfi_prolong_block_extent(const nf_grid* gc, const nf_grid* gf, int* nI, int* nJ);

@@ -906,12 +906,17 @@ static int mg_cycle(nf_mg* mg, int l, int kind, bool want_norm = false, bool* no
   const bool want_post = want_norm && mg->cfg.smoother == 0;
   // x += P x_coarse (multigrid.py:405-415): a pass of its own, or -- bilinear prolongation, streaming smoother -- added
   // to the iterate on the way into the first post-smoothing launch
-  bool fuse_prolong = mg->cfg.smoother == 0 && mg->cfg.interpolation == 0;
-  for (int k = 0; k < nl && fuse_prolong; ++k) {
+  // (streaming kernel: block rule at load + a strips-only launch; TMA kernel: every cell at tile set-up, no launch)
+  int fuse_kind = (mg->cfg.smoother == 0 && mg->cfg.interpolation == 0) ? -1 : 0;
+  for (int k = 0; k < nl && fuse_kind != 0; ++k) {
     const nf_grid g = L.geom.grid(team->local[k]);
-    fuse_prolong = nfi_rbsor_can_fuse_prolong(&g, mg->cfg.post, L.s[k].inv != nullptr);
+    const int kd = nfi_rbsor_can_fuse_prolong(&g, mg->cfg.post, L.s[k].inv != nullptr);
+    fuse_kind = (fuse_kind == -1 || fuse_kind == kd) ? kd : 0;  // the slabs of a process must agree
   }
-  NF_TRY(mg_prolong(mg, l, mg->cfg.interpolation, fuse_prolong ? 2 : 1));  // 2: only the strips outside the block rule
+  if (fuse_kind < 0) fuse_kind = 0;
+  const bool fuse_prolong = fuse_kind != 0;
+  if (fuse_kind != 2)
+    NF_TRY(mg_prolong(mg, l, mg->cfg.interpolation, fuse_kind == 1 ? 2 : 1));  // 2: only the strips outside the block rule
   if (want_post || fuse_prolong)
     for (int k = 0; k < nl; ++k) {
       if (want_post) {

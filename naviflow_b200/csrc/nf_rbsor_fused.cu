@@ -331,6 +331,12 @@ struct TmaExtra {
   unsigned int* ticket;
   double* out;
   int in_norm;              // mode 2: also sum (b - A p_in)^2 and sum b^2 of the INPUT iterate -> out[0..1]
+  // Fused prolongation + correction (multigrid.py:405-415): p_in = x + P x_coarse evaluated while the tile is set up
+  // (nf_prolong_linear_value per region cell from the coarse array, which is L2 resident on the levels this kernel serves);
+  // replaces a k_prolong_linear<ADD> pass.  NULL = off.  Rows [prl_r0, prl_r1) only: what the stand-alone pass covers on a slab.
+  const double* prl_c;
+  nf_grid prl_gc;
+  int prl_r0, prl_r1;
 };
 
 template <int NS, int EXTRA>
@@ -417,7 +423,14 @@ k_rbsor_tma(nf_grid g, const __grid_constant__ CUtensorMap map_p, const __grid_c
 #pragma unroll
       for (int k = 0; k < KS; ++k) {
         const int r = slot_row(ty, k);
-        const double2 pp = *reinterpret_cast<const double2*>(stP + r * RCW + c0);
+        double2 pp = *reinterpret_cast<const double2*>(stP + r * RCW + c0);
+        if (ex.prl_c) {
+          const int gi = i0 + r;
+          if (gi >= ex.prl_r0 && gi < ex.prl_r1) {
+            pp.x = pp.x + nf_prolong_linear_value(ex.prl_gc, ex.prl_c, g.nx, g.ny, gi, gj0);
+            pp.y = pp.y + nf_prolong_linear_value(ex.prl_gc, ex.prl_c, g.nx, g.ny, gi, gj0 + 1);
+          }
+        }
         const double2 bb = *reinterpret_cast<const double2*>(stB + r * RCW + c0);
         const double2 ua = *reinterpret_cast<const double2*>(stDU + r * RCW + c0);
         const double2 ub = *reinterpret_cast<const double2*>(stDU + (r + 1) * RCW + c0);
@@ -443,7 +456,13 @@ k_rbsor_tma(nf_grid g, const __grid_constant__ CUtensorMap map_p, const __grid_c
         const bool row_in = (gi >= 0 && gi < g.nx);
         const bool in0 = row_in && gj0 >= 0 && gj0 < g.ny;
         const bool in1 = row_in && gj0 + 1 >= 0 && gj0 + 1 < g.ny;
-        const double2 pp = *reinterpret_cast<const double2*>(stP + r * RCW + c0);
+        double2 pp = *reinterpret_cast<const double2*>(stP + r * RCW + c0);
+        if (ex.prl_c) {
+          if (gi >= ex.prl_r0 && gi < ex.prl_r1) {
+            if (in0) pp.x = pp.x + nf_prolong_linear_value(ex.prl_gc, ex.prl_c, g.nx, g.ny, gi, gj0);
+            if (in1) pp.y = pp.y + nf_prolong_linear_value(ex.prl_gc, ex.prl_c, g.nx, g.ny, gi, gj0 + 1);
+          }
+        }
         const double2 bb = *reinterpret_cast<const double2*>(stB + r * RCW + c0);
         const double2 ua = *reinterpret_cast<const double2*>(stDU + r * RCW + c0);
         const double2 ub = *reinterpret_cast<const double2*>(stDU + (r + 1) * RCW + c0);
@@ -678,10 +697,25 @@ bool nfi_rbsor_stream_enabled(const nf_grid* g) {
 
 // Can a smoothing call of n_sweeps on this level take the prolongation of the coarse correction into its first launch?
 // (streaming kernel, a 3-sweep first launch; NF_MG_PROLONG_FUSED=0 switches it off)
-bool nfi_rbsor_can_fuse_prolong(const nf_grid* g, int n_sweeps, bool has_inv) {
+// Returns 0: no (stand-alone pass); 1: streaming kernel (block rule at load + a strips-only launch of k_prolong_linear for
+// the ring / trailing cells); 2: TMA kernel (every cell at tile set-up, no launch at all).
+constexpr int NF_SMOOTH_ROWS_BEYOND = 8;  // == NF_HALO (nf_slab.cuh): rows around a slab the stand-alone prolongation covers
+static bool tma_smoother_enabled(const nf_grid* g) {
+  const char* env = getenv("NF_RBSOR_TMA");
+  // NF_RBSOR_TMA=rows: minimum level size (a huge value disables the kernel).  Default: every level a CTA can tile (>= 64
+  // rows).  Round 1 used it from 600 rows up "for the pipeline"; what pays on the small levels is the FUSION that comes with
+  // it (residual + restriction / norms inside the smoother launch instead of a 13-17 us latency-bound kernel of their own):
+  // 15.25 -> 14.83 ms per outer iteration at 4097^2 (levels 511, 255, 127)
+  const int tma_min_rows = env ? atoi(env) : 64;
+  return g->nx >= tma_min_rows && (g->ge - g->gb) >= 64;
+}
+int nfi_rbsor_can_fuse_prolong(const nf_grid* g, int n_sweeps, bool has_inv) {
   const char* env = getenv("NF_MG_PROLONG_FUSED");
-  if (env && env[0] == '0') return false;
-  return has_inv && n_sweeps >= 3 && nfi_rbsor_stream_enabled(g);
+  if (env && env[0] == '0') return 0;
+  if (!has_inv || n_sweeps < 1) return 0;
+  if (nfi_rbsor_stream_enabled(g)) return n_sweeps >= 3 ? 1 : 0;
+  if (env && env[0] == '1') return 0;  // NF_MG_PROLONG_FUSED=1: streaming kernel only (round-2 behaviour before the TMA form)
+  return tma_smoother_enabled(g) ? 2 : 0;
 }
 
 // inv (optional): precomputed 1/aP of this level (nfi_inv_diag); NULL = divide inside the kernel
@@ -692,14 +726,8 @@ int nfi_rbsor_fused_x(nf_ctx* ctx, const nf_grid* g, double** p, double** palt, 
     if (g->row0 == 0 && g->gb == 0) NF_CHECK_CUDA(ctx, cudaMemsetAsync(*p, 0, sizeof(double), ctx->stream));
     return NF_OK;
   }
-  // TMA path: 16-byte aligned arrays, pitch a multiple of 2 doubles, enough rows for a persistent pipeline
-  const char* env = getenv("NF_RBSOR_TMA");
-  // NF_RBSOR_TMA=rows: minimum level size (a huge value disables the kernel).  Default: every level a CTA can tile (>= 64
-  // rows).  Round 1 used it from 600 rows up "for the pipeline"; what pays on the small levels is the FUSION that comes with
-  // it (residual + restriction / norms inside the smoother launch instead of a 13-17 us latency-bound kernel of their own):
-  // 15.25 -> 14.83 ms per outer iteration at 4097^2 (levels 511, 255, 127)
-  const int tma_min_rows = env ? atoi(env) : 64;
-  const bool use_tma = g->nx >= tma_min_rows && (g->ge - g->gb) >= 64;
+  // TMA path: 16-byte aligned arrays, pitch a multiple of 2 doubles, enough rows for a tile
+  const bool use_tma = tma_smoother_enabled(g);
   const char* envx = getenv("NF_RBSOR_EXTRA");
   const bool allow_extra = !(envx && envx[0] == '0');
   int left = n_sweeps;
@@ -711,6 +739,7 @@ int nfi_rbsor_fused_x(nf_ctx* ctx, const nf_grid* g, double** p, double** palt, 
     ex.coarse_b = nullptr; ex.coarse_x0 = nullptr; ex.partials = ctx->partials; ex.ticket = ctx->ticket; ex.out = nullptr;
     ex.in_norm = 0;
     ex.gc = *g;
+    ex.prl_c = nullptr; ex.prl_gc = *g; ex.prl_r0 = 0; ex.prl_r1 = 0;
     int mode = 0;
     // extra work rides on the last launch; it needs the precomputed 1/aP, an unsplit grid and even tile origins
     if (extra && extra->mode != 0 && allow_extra && left == ns && use_tma && inv &&
@@ -739,9 +768,17 @@ int nfi_rbsor_fused_x(nf_ctx* ctx, const nf_grid* g, double** p, double** palt, 
       if (used && want_prl) extra->prolong_fused = true;
       if (used) mode = 0;
     }
-    if (want_prl && !used) {
-      ctx->err = "fused prolongation was requested for a launch the streaming smoother does not serve";
+    if (want_prl && !used && !(use_tma && inv)) {
+      ctx->err = "fused prolongation was requested for a launch neither the streaming nor the TMA smoother serves";
       return NF_ERR_UNSUPPORTED;
+    }
+    if (want_prl && !used) {  // TMA kernel: p_in = x + P x_coarse at tile set-up, rows the stand-alone pass covers on a slab
+      ex.prl_c = extra->prolong_c;
+      ex.prl_gc = extra->prolong_gc;
+      const int lo = g->gb - NF_SMOOTH_ROWS_BEYOND, hi = g->ge + NF_SMOOTH_ROWS_BEYOND;
+      const bool cut = !(g->gb == 0 && g->ge == g->nx);
+      ex.prl_r0 = cut ? (lo > 0 ? lo : 0) : 0;
+      ex.prl_r1 = cut ? (hi < g->nx ? hi : g->nx) : g->nx;
     }
     if (use_tma && !used) {  // persistent TMA pipeline: pays off once every SM gets several tiles
       if (ns == 3) st = launch_tma_any<3>(ctx, g, *p, *palt, b, d_u, d_v, inv, omega, mode, ex, &used);
@@ -750,6 +787,13 @@ int nfi_rbsor_fused_x(nf_ctx* ctx, const nf_grid* g, double** p, double** palt, 
       if (st != NF_OK) return st;
       if (used && mode != 0) extra->fused = true;
       if (used && mode == 2 && ex.in_norm) extra->in_norm_fused = true;
+      if (want_prl) {
+        if (!used) {
+          ctx->err = "fused prolongation: the TMA smoother could not be launched (tensor-map encoder missing?)";
+          return NF_ERR_UNSUPPORTED;
+        }
+        extra->prolong_fused = true;
+      }
     }
     if (!used) {
       if (ns == 3) st = launch_fused<3>(ctx, g, *p, *palt, b, d_u, d_v, inv, omega);
