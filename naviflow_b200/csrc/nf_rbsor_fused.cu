@@ -702,12 +702,12 @@ bool nfi_rbsor_stream_enabled(const nf_grid* g) {
 constexpr int NF_SMOOTH_ROWS_BEYOND = 8;  // == NF_HALO (nf_slab.cuh): rows around a slab the stand-alone prolongation covers
 static bool tma_smoother_enabled(const nf_grid* g) {
   const char* env = getenv("NF_RBSOR_TMA");
-  // NF_RBSOR_TMA=rows: minimum level size (a huge value disables the kernel).  Default: every level a CTA can tile (>= 64
-  // rows).  Round 1 used it from 600 rows up "for the pipeline"; what pays on the small levels is the FUSION that comes with
+  // NF_RBSOR_TMA=rows: minimum level size (a huge value disables the kernel).  Default: every level of >= 32
+  // rows.  Round 1 used it from 600 rows up "for the pipeline"; what pays on the small levels is the FUSION that comes with
   // it (residual + restriction / norms inside the smoother launch instead of a 13-17 us latency-bound kernel of their own):
   // 15.25 -> 14.83 ms per outer iteration at 4097^2 (levels 511, 255, 127)
-  const int tma_min_rows = env ? atoi(env) : 64;
-  return g->nx >= tma_min_rows && (g->ge - g->gb) >= 64;
+  const int tma_min_rows = env ? atoi(env) : 32;
+  return g->nx >= tma_min_rows && (g->ge - g->gb) >= 32;  // (the levels of <= 31 rows are the single-kernel coarse end's)
 }
 int nfi_rbsor_can_fuse_prolong(const nf_grid* g, int n_sweeps, bool has_inv) {
   const char* env = getenv("NF_MG_PROLONG_FUSED");
