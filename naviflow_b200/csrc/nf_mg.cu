@@ -113,12 +113,18 @@ struct nf_mg {
 // K13 coarsest-level matrix (helpers/coeff_matrix.py:6-121 with the pin row :114-119), unknown
 //     numbering r = i*ny + j, and its inverse.  One block.
 // ---------------------------------------------------------------------------------------------
+// use_smem: the two N x N work matrices live in dynamic shared memory (2 N^2 doubles; N = 49 for the default 7 x 7 coarsest
+// level) and only the inverse is written back: the ~7 barrier phases per column each waited on global-memory round trips
+// before (203 us per set-up = per outer iteration at N = 49; same operations in the same order, same bits).
 __global__ void k_coarse_invert(nf_grid g, const double* __restrict__ d_u, const double* __restrict__ d_v,
-                                double* __restrict__ A, double* __restrict__ Inv, int N) {
+                                double* __restrict__ A_glob, double* __restrict__ Inv_glob, int N, int use_smem) {
   const int tid = threadIdx.x, nt = blockDim.x;
+  extern __shared__ __align__(16) double s_work[];
   __shared__ double s_val[32];
   __shared__ int s_idx[32];
   __shared__ int s_piv;
+  double* A = use_smem ? s_work : A_glob;
+  double* Inv = use_smem ? s_work + (size_t)N * N : Inv_glob;
   for (size_t k = tid; k < (size_t)N * N; k += nt) { A[k] = 0.0; Inv[k] = 0.0; }
   __syncthreads();
   for (int r = tid; r < N; r += nt) {
@@ -185,6 +191,8 @@ __global__ void k_coarse_invert(nf_grid g, const double* __restrict__ d_u, const
       if (r != col) A[(size_t)r * N + col] = 0.0;
     __syncthreads();
   }
+  if (use_smem)
+    for (size_t k = tid; k < (size_t)N * N; k += nt) Inv_glob[k] = Inv[k];
 }
 
 // x = Inv * b on the coarsest level (b, x pitched 2-D arrays); one warp per row
@@ -636,8 +644,15 @@ int nfi_mg_setup(nf_mg* mg, double* const* d_u, double* const* d_v) {
   MgLevel& C = mg->lv.back();
   if (C.geom.nx <= mg->cfg.coarsest)
     for (int k = 0; k < nl; ++k) {
-      k_coarse_invert<<<1, 1024, 0, ctx->stream>>>(C.geom.grid(team->local[k]), C.s[k].d_u, C.s[k].d_v,
-                                                   mg->coarse_A[k], mg->coarse_inv[k], mg->coarse_N);
+      const size_t work = 2 * (size_t)mg->coarse_N * mg->coarse_N * sizeof(double);
+      const int use_smem = work <= 200 * 1024 ? 1 : 0;
+      static size_t attr = 48 * 1024;
+      if (use_smem && work > attr) {
+        NF_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_coarse_invert, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)work));
+        attr = work;
+      }
+      k_coarse_invert<<<1, 1024, use_smem ? work : 0, ctx->stream>>>(C.geom.grid(team->local[k]), C.s[k].d_u, C.s[k].d_v,
+                                                                     mg->coarse_A[k], mg->coarse_inv[k], mg->coarse_N, use_smem);
       NF_LAUNCH_CHECK(ctx);
     }
   mg->setup_done = true;
@@ -1233,7 +1248,9 @@ extern "C" int nf_mg_cycle(nf_mg* mg, double* x, const double* b, int kind) {
 
 // MultiGridSolver.solve without get_rhs, per local slab arrays.  sync == 0 (FMG mode only): the final ||r||^2,
 // ||b||^2 stay in mg->scal[k][0..1] and no host synchronisation happens.
-int nfi_mg_solve(nf_mg* mg, double* const* b, double* const* x, double* const* r, nf_mg_info* info, int sync) {
+// want_field == 0: the caller does not read the residual FIELD (info['field'] of the reference): when the norms came
+// out of the smoother the extra b - A x pass at the end is skipped
+int nfi_mg_solve(nf_mg* mg, double* const* b, double* const* x, double* const* r, nf_mg_info* info, int sync, int want_field) {
   nf_ctx* ctx = mg->ctx;
   NF_REQUIRE(ctx, mg->setup_done, "nf_mg_setup has not been called");
   MgLevel& L = mg->lv[0];
@@ -1331,7 +1348,7 @@ int nfi_mg_solve(nf_mg* mg, double* const* b, double* const* x, double* const* r
       }
       if (!status && lookahead && !have_final_norm && cycles > 0)  // ran out of cycles: the norm after the last one
         status = mg_rel_residual(mg, 0, &rn, &bn, 1);
-      if (!status && fused_any)  // the residual field itself (info['field']) once, at the end
+      if (!status && fused_any && want_field)  // the residual field itself (info['field']) once, at the end
         for (int k = 0; k < nlocal(mg) && !status; ++k) {
           const nf_grid g0 = L.geom.grid(mg->team->local[k]);
           status = nfi_residual(ctx, &g0, L.s[k].x, L.s[k].b, L.s[k].d_u, L.s[k].d_v, L.s[k].r);
@@ -1407,7 +1424,7 @@ extern "C" int nf_mg_solve(nf_mg* mg, const double* b, double* x, double* r, nf_
   NF_REQUIRE(mg->ctx, nlocal(mg) == 1, "nf_mg_solve is the single-slab entry point");
   NF_REQUIRE(mg->ctx, b && x, "NULL argument");
   double* bb = const_cast<double*>(b);
-  return nfi_mg_solve(mg, &bb, &x, &r, info, 1);
+  return nfi_mg_solve(mg, &bb, &x, &r, info, 1, 1);
 }
 
 // Device workspace of the stand-alone entry points that need scratch memory (the header's rule: no allocation inside hot

@@ -44,7 +44,7 @@ int nfi_krylov_team(nf_team* team, const LevelGeom& geom, int kind, double* cons
                     double* const* state, nf_krylov_info* info);
 int nfi_mg_create(nf_team* team, nf_mg** out, int nx, int ny, int ld, const nf_mg_config* cfg);
 int nfi_mg_setup(nf_mg* mg, double* const* d_u, double* const* d_v);
-int nfi_mg_solve(nf_mg* mg, double* const* b, double* const* x, double* const* r, nf_mg_info* info, int sync);
+int nfi_mg_solve(nf_mg* mg, double* const* b, double* const* x, double* const* r, nf_mg_info* info, int sync, int want_field);
 double* nfi_mg_scalars(nf_mg* mg, int k);
 LevelGeom nf_level0_geom(const nf_team* team, int nx, int ny, int ld, double length, double height, double rho);
 
@@ -81,6 +81,7 @@ struct nf_simple {
   double* hist_host = nullptr;  // pinned
   int hist_cap = 0;
   bool bc_clean = false;
+  int want_fields = 1;  // this call of nf_simple_iterate returns residual fields (else the pressure solver skips its field pass)
   // optional phase timing (nf_simple_phase_timing): 4 events per outer iteration on the context's stream
   bool phase_timing = false;
   std::vector<cudaEvent_t> pev;
@@ -671,7 +672,7 @@ static int pressure_correction(nf_simple* s, int slot, double alpha, bool correc
       NF_TRY(nfi_mg_setup(s->mg, du.data(), dv.data()));
       nf_mg_info mi;
       const int fmg = (c.mg.cycle_type == 2);
-      NF_TRY(nfi_mg_solve(s->mg, b.data(), x.data(), r.data(), &mi, fmg ? 0 : 1));
+      NF_TRY(nfi_mg_solve(s->mg, b.data(), x.data(), r.data(), &mi, fmg ? 0 : 1, s->want_fields));
       if (fmg) { p_from_scalars = 1; pscal = nfi_mg_scalars(s->mg, 0); }
       else { pa = mi.r_norm * mi.r_norm; pb = mi.b_norm * mi.b_norm; }
       iters = mi.cycles;
@@ -846,6 +847,7 @@ static int pressure_correction(nf_simple* s, int slot, double alpha, bool correc
 // corrected (u, v, p) without relaxation, their norms are discarded (:92-104).
 static int simple_step(nf_simple* s, int slot, int want_fields) {
   const nf_simple_config& c = s->cfg;
+  s->want_fields = want_fields;
   // phase marks per (predictor, correction) pair: start, end of predictor, end of pressure solve, end of corrections
   phase_mark(s);
   if (c.piso_corrections == -1) {
