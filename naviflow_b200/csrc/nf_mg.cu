@@ -195,6 +195,89 @@ __global__ void k_coarse_invert(nf_grid g, const double* __restrict__ d_u, const
     for (size_t k = tid; k < (size_t)N * N; k += nt) Inv_glob[k] = Inv[k];
 }
 
+// The same inverse for N <= 52 (the default 7 x 7 coarsest level: N = 49) at a fraction of the latency: both matrices in
+// static shared memory, thread <-> (row group, column), the pivot search in one warp, four barriers per column.  Per element
+// the operations and their order are k_coarse_invert's (swap, divide the pivot row by the pivot, subtract fct x pivot row,
+// rows with fct == 0 untouched), so Inv has the same bits; A's finished columns are scratch there and are simply not
+// maintained here.  203 -> ~35 us per set-up, i.e. per outer iteration.
+constexpr int CI_MAX = 52;  // 2 x 52^2 doubles of static shared memory (48 KB limit); N = 49, 25, 9 for coarsest 7, 5, 3
+__global__ void __launch_bounds__(1024, 1)
+k_coarse_invert_small(nf_grid g, const double* __restrict__ d_u, const double* __restrict__ d_v, double* __restrict__ Inv_glob,
+                      int N) {
+  __shared__ double A[CI_MAX * CI_MAX], Iv[CI_MAX * CI_MAX], rowA[CI_MAX], rowI[CI_MAX];
+  __shared__ double s_pv;
+  __shared__ int s_piv;
+  const int tid = threadIdx.x, c2 = tid & 63, rg = tid >> 6;  // 16 row groups x 64 columns
+  for (int k = tid; k < N * N; k += 1024) { A[k] = 0.0; Iv[k] = 0.0; }
+  __syncthreads();
+  for (int r = tid; r < N; r += 1024) {
+    const int i = r / g.ny, j = r % g.ny;
+    Iv[r * N + r] = 1.0;
+    if (r == 0) { A[0] = 1.0; continue; }
+    const PCoef c = nf_pcoef(g, d_u, d_v, i, j);
+    A[r * N + r] = c.diag;
+    if (i < g.nx - 1) A[r * N + r + g.ny] = -c.e;
+    if (i > 0) A[r * N + r - g.ny] = -c.w;
+    if (j < g.ny - 1) A[r * N + r + 1] = -c.n;
+    if (j > 0) A[r * N + r - 1] = -c.s;
+  }
+  __syncthreads();
+  for (int col = 0; col < N; ++col) {
+    if (tid < 32) {  // pivot: max |A[r,col]|, r >= col, ties -> smallest r
+      double best = -1.0;
+      int bi = col;
+      for (int r = col + tid; r < N; r += 32) {
+        const double v = fabs(A[r * N + col]);
+        if (v > best) { best = v; bi = r; }
+      }
+      for (int off = 16; off > 0; off >>= 1) {
+        const double ov = __shfl_down_sync(0xffffffffu, best, off);
+        const int oi = __shfl_down_sync(0xffffffffu, bi, off);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+      }
+      if (tid == 0) s_piv = bi;
+    }
+    __syncthreads();
+    const int piv = s_piv;
+    double a = 0.0, ai = 0.0;
+    if (rg == 0 && c2 < N) {  // row swap in registers; the new pivot row stays in (a, ai)
+      a = A[col * N + c2];
+      ai = Iv[col * N + c2];
+      if (piv != col) {
+        const double b = A[piv * N + c2], bi = Iv[piv * N + c2];
+        A[piv * N + c2] = a;
+        Iv[piv * N + c2] = ai;
+        a = b;
+        ai = bi;
+      }
+      if (c2 == col) s_pv = a;
+    }
+    __syncthreads();
+    if (rg == 0 && c2 < N) {
+      const double pv = s_pv;
+      a = a / pv;
+      ai = ai / pv;
+      A[col * N + c2] = a;
+      Iv[col * N + c2] = ai;
+      rowA[c2] = a;
+      rowI[c2] = ai;
+    }
+    __syncthreads();
+    if (c2 < N) {
+      const double ra = rowA[c2], ri = rowI[c2];
+      for (int r = rg; r < N; r += 16) {
+        if (r == col) continue;
+        const double fct = A[r * N + col];
+        if (fct == 0.0) continue;
+        if (c2 > col) A[r * N + c2] -= fct * ra;
+        Iv[r * N + c2] -= fct * ri;
+      }
+    }
+    __syncthreads();
+  }
+  for (int k = tid; k < N * N; k += 1024) Inv_glob[k] = Iv[k];
+}
+
 // x = Inv * b on the coarsest level (b, x pitched 2-D arrays); one warp per row
 __global__ void k_coarse_apply(nf_grid g, const double* __restrict__ Inv, const double* __restrict__ b,
                                double* __restrict__ x, int N) {
@@ -644,6 +727,13 @@ int nfi_mg_setup(nf_mg* mg, double* const* d_u, double* const* d_v) {
   MgLevel& C = mg->lv.back();
   if (C.geom.nx <= mg->cfg.coarsest)
     for (int k = 0; k < nl; ++k) {
+      const char* envs = getenv("NF_COARSE_INVERT_SMALL");  // =0: the general kernel for every N (tests compare the two)
+      if (mg->coarse_N <= CI_MAX && !(envs && envs[0] == '0')) {
+        k_coarse_invert_small<<<1, 1024, 0, ctx->stream>>>(C.geom.grid(team->local[k]), C.s[k].d_u, C.s[k].d_v,
+                                                           mg->coarse_inv[k], mg->coarse_N);
+        NF_LAUNCH_CHECK(ctx);
+        continue;
+      }
       const size_t work = 2 * (size_t)mg->coarse_N * mg->coarse_N * sizeof(double);
       const int use_smem = work <= 200 * 1024 ? 1 : 0;
       static size_t attr = 48 * 1024;

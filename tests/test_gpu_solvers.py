@@ -746,6 +746,25 @@ def test_multigrid_device_side_convergence_loop_equals_host_loop(n, kw, monkeypa
                                atol=1e-18 + 1e-12 * np.abs(outs[1][1]["field"]).max())
 
 
+@pytest.mark.parametrize("n,coarsest", [(63, 7), (129, 7), (40, 5), (257, 3)])
+def test_coarsest_level_inverse_small_kernel_equals_general_kernel(n, coarsest, monkeypatch):
+    """The shared-memory Gauss-Jordan kernel for <= 52 coarsest unknowns (k_coarse_invert_small) yields the same inverse, bit
+    for bit, as the general kernel (NF_COARSE_INVERT_SMALL=0): whole solves agree exactly."""
+    import naviflow_b200 as nb
+    from oracle.make_golden import synth_pressure_inputs
+    s = synth_pressure_inputs(n, 4400 + n)
+    mesh, _ = cavity(n, 1000)
+    outs = []
+    for small in ("1", "0"):
+        monkeypatch.setenv("NF_COARSE_INVERT_SMALL", small)
+        ps = nb.GpuMultiGridSolver(smoother=nb.GpuGaussSeidelSolver(omega=1.5), max_iterations=6, tolerance=1e-30,
+                                   pre_smoothing=3, post_smoothing=3, coarsest_grid_size=coarsest)
+        p, info = ps.solve(mesh, s["u_star"], s["v_star"], s["d_u"], s["d_v"], None)
+        outs.append((p, info["rel_norm"]))
+    np.testing.assert_array_equal(outs[0][0], outs[1][0])
+    assert outs[0][1] == outs[1][1]
+
+
 def test_multigrid_lookahead_norm_on_slabs(monkeypatch):
     """Same on row slabs (the input norms of the slabs are all-reduced): identical fields and cycle counts."""
     runs = []
