@@ -199,7 +199,7 @@ __global__ void k_coarse_invert(nf_grid g, const double* __restrict__ d_u, const
 // static shared memory, thread <-> (row group, column), the pivot search in one warp, four barriers per column.  Per element
 // the operations and their order are k_coarse_invert's (swap, divide the pivot row by the pivot, subtract fct x pivot row,
 // rows with fct == 0 untouched), so Inv has the same bits; A's finished columns are scratch there and are simply not
-// maintained here.  203 -> ~35 us per set-up, i.e. per outer iteration.
+// maintained here.  203 -> 76 us (ncu) per set-up, i.e. per outer iteration.
 constexpr int CI_MAX = 52;  // 2 x 52^2 doubles of static shared memory (48 KB limit); N = 49, 25, 9 for coarsest 7, 5, 3
 __global__ void __launch_bounds__(1024, 1)
 k_coarse_invert_small(nf_grid g, const double* __restrict__ d_u, const double* __restrict__ d_v, double* __restrict__ Inv_glob,
