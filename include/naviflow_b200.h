@@ -213,6 +213,18 @@ int nf_momentum_jacobi_fused(nf_ctx*, const nf_grid*, int is_u, nf_links L, doub
 int nf_momentum_residual(nf_ctx*, const nf_grid*, int is_u, nf_links L, const double* x, double* field_out,
                          double* rel_norm_host);
 
+/* ---- higher-order convection schemes: discretization/quick.py:27-219 (QUICKDiscretization),
+ *      discretization/second_order_upwind.py:26-325 (SecondOrderUpwindDiscretization) ----
+ * Ten same-shape coefficient arrays of one component: the 5-point links, the second-neighbour links a_ee / a_ww / a_nn /
+ * a_ss, a_p and the source (pressure gradient + Practice-B boundary terms), exactly what calculate_u_coefficients /
+ * calculate_v_coefficients return.  No relaxation (the reference applies none here).  Single slab. */
+typedef struct nf_links_ext {
+  double *a_e, *a_w, *a_n, *a_s, *a_ee, *a_ww, *a_nn, *a_ss, *a_p, *src;
+} nf_links_ext;
+enum nf_scheme { NF_SCHEME_QUICK = 1, NF_SCHEME_SOU = 2 };
+int nf_momentum_links_ext(nf_ctx*, const nf_grid*, int is_u, int scheme, const double* u_bc, const double* v_bc,
+                          const double* p, double mu, int sides, nf_links_ext out);
+
 /* ---- a7 MatrixFreeMomentumSolver (momentum_solver/matrix_free_momentum.py:403-544): Krylov momentum predictor ----
  * Coefficients with that class's relaxation (a_P clamped to 1e-12 then /alpha, source relaxed with the relaxed a_P,
  * d = 0 where a_P vanishes); u_bc/v_bc carry the BCs as that class applies them (caller's nx+1).  The unrelaxed a_P and

@@ -6,7 +6,8 @@ fallback: using a solver without the built library or without a CUDA device rais
 """
 from .host import (BoundaryConditionManager, FluidProperties, SimulationResult, StructuredMesh, ghia_errors,
                    ghia_table)
-from .momentum import GpuJacobiMomentumSolver, GpuMatrixFreeMomentumSolver
+from .momentum import (GpuJacobiMomentumSolver, GpuMatrixFreeMomentumSolver, GpuQUICKDiscretization,
+                       GpuSecondOrderUpwindDiscretization)
 from .pressure import (GpuBiCGSTABSolver, GpuCGSolver, GpuGaussSeidelSolver, GpuGeoMultigridPrecondCGSolver,
                        GpuJacobiSolver, GpuMultiGridSolver)
 from .profiler import Profiler, load_profile
@@ -16,7 +17,8 @@ from .velocity import GpuVelocityUpdater
 __all__ = ["StructuredMesh", "FluidProperties", "BoundaryConditionManager", "SimulationResult", "ghia_errors",
            "ghia_table", "GpuJacobiMomentumSolver", "GpuJacobiSolver", "GpuGaussSeidelSolver",
            "GpuMultiGridSolver", "GpuGeoMultigridPrecondCGSolver", "GpuCGSolver", "GpuBiCGSTABSolver", "GpuVelocityUpdater", "GpuSimpleSolver",
-           "GpuPisoSolver", "GpuSimplerSolver", "GpuSimplecSolver", "GpuMatrixFreeMomentumSolver", "Profiler",
+           "GpuPisoSolver", "GpuSimplerSolver", "GpuSimplecSolver", "GpuMatrixFreeMomentumSolver", "GpuQUICKDiscretization",
+           "GpuSecondOrderUpwindDiscretization", "Profiler",
            "load_profile"]
 
 

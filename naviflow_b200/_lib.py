@@ -54,6 +54,10 @@ class NfLinks(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("a_e", "a_w", "a_n", "a_s", "a_p", "src")]
 
 
+class NfLinksExt(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("a_e", "a_w", "a_n", "a_s", "a_ee", "a_ww", "a_nn", "a_ss", "a_p", "src")]
+
+
 class NfSimpleConfig(C.Structure):
     _fields_ = [("nx", C.c_int32), ("ny", C.c_int32), ("n_momentum_sweeps", C.c_int32),
                 ("pressure_solver", C.c_int32), ("pressure_iterations", C.c_int32),
@@ -124,6 +128,7 @@ SIGNATURES = {
                                  C.POINTER(NfKrylovInfo)]),
     "nf_momentum_links_u": (C.c_int, [CTX, GP, P, P, P, C.c_double, C.c_double, C.c_int, NfLinks, P]),
     "nf_momentum_links_v": (C.c_int, [CTX, GP, P, P, P, C.c_double, C.c_double, C.c_int, NfLinks, P]),
+    "nf_momentum_links_ext": (C.c_int, [CTX, GP, C.c_int, C.c_int, P, P, P, C.c_double, C.c_int, NfLinksExt]),
     "nf_momentum_jacobi": (C.c_int, [CTX, GP, C.c_int, NfLinks, P, P, C.c_int]),
     "nf_momentum_jacobi_fused": (C.c_int, [CTX, GP, C.c_int, NfLinks, P, P, C.c_int, P, DBL_OUT]),
     "nf_momentum_residual": (C.c_int, [CTX, GP, C.c_int, NfLinks, P, P, DBL_OUT]),

@@ -158,3 +158,59 @@ class GpuMatrixFreeMomentumSolver:
                          return_dict=True):
         vs, dv, res = self._solve(False, mesh, fluid, u, v, p, relaxation_factor, boundary_conditions)
         return (vs, dv, res) if return_dict else (vs, dv, res["rel_norm"])
+
+
+class _GpuExtendedStencilDiscretization:
+    """Twin of the reference's higher-order discretization objects: ``calculate_u_coefficients`` /
+    ``calculate_v_coefficients`` return the same dict of ten arrays (a_e, a_w, a_n, a_s, a_ee, a_ww, a_nn, a_ss, a_p,
+    source), evaluated by ``nf_momentum_links_ext`` (csrc/nf_links_ext.cu).  As in the reference the velocities are used as
+    passed (the caller applies the boundary conditions first) and nothing is relaxed."""
+    _scheme = 0
+    _KEYS = ("a_e", "a_w", "a_n", "a_s", "a_ee", "a_ww", "a_nn", "a_ss", "a_p", "source")
+
+    def __init__(self, device=None):
+        self._device = device
+        self._ctx = None
+
+    @property
+    def ctx(self):
+        if self._ctx is None:
+            self._ctx = get_context(self._device)
+        return self._ctx
+
+    def _coefficients(self, is_u, mesh, fluid, u, v, p, bc):
+        from ._lib import NfLinksExt
+        ctx = self.ctx
+        nx, ny = mesh.get_dimensions()
+        dx, dy = mesh.get_cell_sizes()
+        g = ctx.grid(nx, ny, dx, dy, fluid.get_density())
+        ud, vd, pd = ctx.upload(u, nx, ny), ctx.upload(v, nx, ny), ctx.upload(p, nx, ny)
+        arrays = [ctx.empty(nx, ny) for _ in range(10)]
+        out = NfLinksExt(*[a.data_ptr() for a in arrays])
+        sides = practice_b_sides(bc) if bc is not None else 0
+        ctx.check(ctx.lib.nf_momentum_links_ext(ctx.handle, C.byref(g), int(is_u), int(self._scheme), ptr(ud), ptr(vd), ptr(pd),
+                                                float(fluid.get_viscosity()), int(sides), out), "nf_momentum_links_ext")
+        rows, cols = (nx + 1, ny) if is_u else (nx, ny + 1)
+        return {k: ctx.download(a, rows, cols) for k, a in zip(self._KEYS, arrays)}
+
+
+class GpuQUICKDiscretization(_GpuExtendedStencilDiscretization):
+    """``QUICKDiscretization`` (discretization/quick.py:27-219)."""
+    _scheme = 1
+
+    def calculate_u_coefficients(self, mesh, fluid, u, v, p, bc=None):
+        return self._coefficients(1, mesh, fluid, u, v, p, bc)
+
+    def calculate_v_coefficients(self, mesh, fluid, u, v, p, bc=None):
+        return self._coefficients(0, mesh, fluid, u, v, p, bc)
+
+
+class GpuSecondOrderUpwindDiscretization(_GpuExtendedStencilDiscretization):
+    """``SecondOrderUpwindDiscretization`` (discretization/second_order_upwind.py:26-325)."""
+    _scheme = 2
+
+    def calculate_u_coefficients(self, mesh, fluid, u, v, p, bc_manager=None):
+        return self._coefficients(1, mesh, fluid, u, v, p, bc_manager)
+
+    def calculate_v_coefficients(self, mesh, fluid, u, v, p, bc_manager=None):
+        return self._coefficients(0, mesh, fluid, u, v, p, bc_manager)

@@ -422,6 +422,37 @@ def gs_lex_kats(R):
     return out
 
 
+def ext_links_kats(R):
+    """QUICKDiscretization / SecondOrderUpwindDiscretization outputs (quick.py, second_order_upwind.py) on seeded fields:
+    square and rectangular grids, with the cavity's boundary conditions (Practice B on all four sides) and with bc=None."""
+    out = {}
+    cases = []
+    for nx, ny, seed in ((9, 9, 901), (16, 16, 902), (31, 31, 903), (12, 20, 904), (5, 4, 905)):
+        rng = np.random.default_rng(seed)
+        mesh = R.StructuredMesh(nx, ny, 1.0, 0.7 if nx != ny else 1.0)
+        fluid = R.FluidProperties(density=1.3, reynolds_number=400, characteristic_velocity=1.0)
+        u = 0.5 * rng.standard_normal((nx + 1, ny))
+        v = 0.5 * rng.standard_normal((nx, ny + 1))
+        p = rng.standard_normal((nx, ny))
+        bc = cavity_bc(R)
+        ub, vb = bc.apply_velocity_boundary_conditions(u.copy(), v.copy(), nx, ny)
+        tag = f"{nx}x{ny}"
+        cases.append(tag)
+        out[f"{tag}_u"], out[f"{tag}_v"], out[f"{tag}_p"] = ub, vb, p
+        out[f"{tag}_dims"] = np.array([nx, ny], dtype=np.int64)
+        dx, dy = mesh.get_cell_sizes()
+        out[f"{tag}_scal"] = np.array([dx, dy, fluid.get_density(), fluid.get_viscosity()])
+        for sname, cls in (("quick", R.QUICKDiscretization), ("sou", R.SecondOrderUpwindDiscretization)):
+            for bname, b in (("bc", bc), ("nobc", None)):
+                d = cls()
+                for comp, c in (("u", d.calculate_u_coefficients(mesh, fluid, ub, vb, p, b)),
+                                ("v", d.calculate_v_coefficients(mesh, fluid, ub, vb, p, b))):
+                    for k, a in c.items():
+                        out[f"{tag}_{sname}_{bname}_{comp}_{k}"] = a
+    out["cases"] = np.array(cases)
+    return out
+
+
 def main():
     warnings.filterwarnings("ignore")
     R = rl.ref()
@@ -445,6 +476,7 @@ def main():
     np.savez_compressed(os.path.join(GOLD, "bicgstab_mg.npz"), **bicgstab_mg_kats(R))
     np.savez_compressed(os.path.join(GOLD, "rect_runs.npz"), **rect_runs(R))
     np.savez_compressed(os.path.join(GOLD, "cg_mg_kats.npz"), **cg_mg_kats(R))
+    np.savez_compressed(os.path.join(GOLD, "ext_links_kats.npz"), **ext_links_kats(R))
     cf = R.cavity_flow.BenchmarkData
     tables = {}
     for Re in (100, 400, 1000, 3200, 5000, 7500, 10000):

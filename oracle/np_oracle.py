@@ -1293,3 +1293,99 @@ def max_interior_divergence(u, v, dx, dy):
     """get_max_divergence (base_algorithm.py:134-159, cavity_flow.py:147-175)."""
     div = (u[1:, :] - u[:-1, :]) / dx + (v[:, 1:] - v[:, :-1]) / dy
     return np.max(np.abs(div[1:-1, 1:-1]))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Extended-stencil convection schemes (SURVEY 8f rank 4): QUICKDiscretization (discretization/quick.py:27-219) and
+# SecondOrderUpwindDiscretization (discretization/second_order_upwind.py:26-325).  TEST INFRASTRUCTURE.
+# A scheme is a list of accumulation steps (target, face, flux part, coefficient, diffusion term, stencil mask); the steps of
+# one target are in the reference's statement order so that every sum rounds identically.
+# ---------------------------------------------------------------------------------------------------------------------
+EXT_KEYS = ("a_e", "a_w", "a_n", "a_s", "a_ee", "a_ww", "a_nn", "a_ss", "a_p", "source")
+
+
+def _quick_face(first, second, opposite, face, diff, mask):
+    return [(first, face, "pos", 0.75, diff, mask), ("a_p", face, "pos", 0.375, None, mask),
+            (second, face, "pos", -0.125, None, mask), (first, face, "neg", 0.375, diff, mask),
+            ("a_p", face, "neg", 0.75, None, mask), (opposite, face, "neg", -0.125, None, mask)]
+
+
+_EXT_STEPS = {
+    # quick.py:62-112 (u) / :149-194 (v): the same statements for both components
+    ("quick", True): (_quick_face("a_e", "a_ee", "a_w", "e", "De", "EE") + _quick_face("a_w", "a_ww", "a_e", "w", "De", "WW") +
+                      _quick_face("a_n", "a_nn", "a_s", "n", "Dn", "NN") + _quick_face("a_s", "a_ss", "a_n", "s", "Dn", "SS")),
+    # second_order_upwind.py:88-127
+    ("sou", True): [("a_e", None, None, 0.0, "De", None), ("a_w", None, None, 0.0, "De", None),
+                    ("a_n", None, None, 0.0, "Dn", None), ("a_s", None, None, 0.0, "Dn", None),
+                    ("a_p", "e", "pos", 1.5, None, None), ("a_w", "e", "pos", 0.5, None, None), ("a_ww", "e", "pos", -0.5, None, None),
+                    ("a_e", "e", "neg", 1.5, None, None), ("a_ee", "e", "neg", 0.5, None, None),
+                    ("a_w", "w", "pos", 1.5, None, None), ("a_ww", "w", "pos", -0.5, None, None),
+                    ("a_p", "w", "neg", 1.5, None, None), ("a_e", "w", "neg", 0.5, None, None),
+                    ("a_p", "n", "pos", 1.5, None, None), ("a_s", "n", "pos", -0.5, None, None),
+                    ("a_n", "n", "neg", 1.5, None, None), ("a_nn", "n", "neg", 0.5, None, None),
+                    ("a_s", "s", "pos", 1.5, None, None), ("a_ss", "s", "pos", -0.5, None, None),
+                    ("a_p", "s", "neg", 1.5, None, None), ("a_n", "s", "neg", 0.5, None, None)],
+    # second_order_upwind.py:234-266
+    ("sou", False): [("a_e", None, None, 0.0, "De", None), ("a_w", None, None, 0.0, "De", None),
+                     ("a_n", None, None, 0.0, "Dn", None), ("a_s", None, None, 0.0, "Dn", None),
+                     ("a_e", "e", "pos", 1.5, None, None), ("a_ee", "e", "pos", 0.5, None, None),
+                     ("a_p", "e", "neg", 1.5, None, None), ("a_w", "e", "neg", 0.5, None, None),
+                     ("a_p", "w", "pos", 1.5, None, None), ("a_e", "w", "pos", 0.5, None, None),
+                     ("a_w", "w", "neg", 1.5, None, None), ("a_ww", "w", "neg", 0.5, None, None),
+                     ("a_n", "n", "pos", 1.5, None, None), ("a_nn", "n", "pos", 0.5, None, None),
+                     ("a_p", "n", "neg", 1.5, None, None), ("a_s", "n", "neg", 0.5, None, None),
+                     ("a_p", "s", "pos", 1.5, None, None), ("a_n", "s", "pos", 0.5, None, None),
+                     ("a_s", "s", "neg", 1.5, None, None), ("a_ss", "s", "neg", 0.5, None, None)],
+}
+_EXT_STEPS[("quick", False)] = _EXT_STEPS[("quick", True)]
+
+
+def ext_links(scheme, is_u, nx, ny, dx, dy, rho, mu, u, v, p, sides):
+    """The ten coefficient arrays of calculate_u_coefficients (is_u) / calculate_v_coefficients of the 'quick' / 'sou' scheme;
+    sides: bit mask 1 left, 2 right, 4 bottom, 8 top of the boundaries with a registered condition (0 = bc None)."""
+    shape = (nx + 1, ny) if is_u else (nx, ny + 1)
+    out = {k: np.zeros(shape) for k in EXT_KEYS}
+    i = np.arange(1, nx) if is_u else np.arange(1, nx - 1)
+    j = np.arange(1, ny - 1) if is_u else np.arange(1, ny)
+    I, J = np.meshgrid(i, j, indexing="ij")
+    cdy, cdx = 0.5 * rho * dy, 0.5 * rho * dx
+    if is_u:
+        F = {"e": cdy * (u[I + 1, J] + u[I, J]), "w": cdy * (u[I - 1, J] + u[I, J]),
+             "n": cdx * (v[I, J + 1] + v[I - 1, J + 1]), "s": cdx * (v[I, J] + v[I - 1, J])}
+    else:
+        F = {"e": cdy * (u[I + 1, J] + u[I + 1, J - 1]), "w": cdy * (u[I, J] + u[I, J - 1]),
+             "n": cdx * (v[I, J + 1] + v[I, J]), "s": cdx * (v[I, J] + v[I, J - 1])}
+    D = {"De": mu * dy / dx, "Dn": mu * dx / dy}
+    has = {None: np.ones(I.shape, bool), "EE": I <= (nx - 2 if is_u else nx - 3), "WW": I >= 2,
+           "NN": J <= (ny - 3 if is_u else ny - 2), "SS": J >= 2}
+    blk = {k: np.zeros(I.shape) for k in EXT_KEYS}
+    for dst, face, part, coef, diff, mask in _EXT_STEPS[(scheme, bool(is_u))]:
+        if face is None:
+            term = np.full(I.shape, D[diff])
+        else:
+            term = coef * (np.maximum(F[face], 0.0) if part == "pos" else np.maximum(-F[face], 0.0))
+            if diff is not None:
+                term = term + D[diff]
+        blk[dst] = np.where(has[mask], blk[dst] + term, blk[dst])
+    blk["source"] = ((p[I - 1, J] - p[I, J]) * dy) if is_u else ((p[I, J - 1] - p[I, J]) * dx)
+    if scheme == "sou":
+        s = blk["a_e"] + blk["a_w"]
+        for k in ("a_n", "a_s", "a_ee", "a_ww", "a_nn", "a_ss"):
+            s = s + blk[k]
+        s = s + (F["e"] - F["w"])
+        s = s + (F["n"] - F["s"])
+        blk["a_p"] = blk["a_p"] + s
+    for k in EXT_KEYS:
+        out[k][I, J] = blk[k]
+    S = out["source"]
+    if is_u:   # Practice B: left, right, bottom, top (quick.py:199-209)
+        if sides & 1: S[1, :] += out["a_w"][1, :] * u[0, :]; out["a_w"][1, :] = 0.0
+        if sides & 2: S[nx - 1, :] += out["a_e"][nx - 1, :] * u[nx, :]; out["a_e"][nx - 1, :] = 0.0
+        if sides & 4: S[1:nx, 1] += out["a_s"][1:nx, 1] * u[1:nx, 0]; out["a_s"][1:nx, 1] = 0.0
+        if sides & 8: S[1:nx, ny - 2] += out["a_n"][1:nx, ny - 2] * u[1:nx, ny - 1]; out["a_n"][1:nx, ny - 2] = 0.0
+    else:      # bottom, top, left, right (quick.py:211-219)
+        if sides & 4: S[:, 1] += out["a_s"][:, 1] * v[:, 0]; out["a_s"][:, 1] = 0.0
+        if sides & 8: S[:, ny - 1] += out["a_n"][:, ny - 1] * v[:, ny]; out["a_n"][:, ny - 1] = 0.0
+        if sides & 1: S[1, 1:ny] += out["a_w"][1, 1:ny] * v[0, 1:ny]; out["a_w"][1, 1:ny] = 0.0
+        if sides & 2: S[nx - 2, 1:ny] += out["a_e"][nx - 2, 1:ny] * v[nx - 1, 1:ny]; out["a_e"][nx - 2, 1:ny] = 0.0
+    return out

@@ -112,6 +112,8 @@ def ref():
     from naviflow_oo.constructor.properties.fluid import FluidProperties
     from naviflow_oo.constructor.boundary_conditions import BoundaryConditionManager
     from naviflow_oo.solver.momentum_solver.discretization.power_law import PowerLawDiscretization
+    from naviflow_oo.solver.momentum_solver.discretization.quick import QUICKDiscretization
+    from naviflow_oo.solver.momentum_solver.discretization.second_order_upwind import SecondOrderUpwindDiscretization
     from naviflow_oo.solver.momentum_solver.jacobi_matrix_solver import JacobiMatrixMomentumSolver
     from naviflow_oo.solver.momentum_solver.matrix_free_momentum import MatrixFreeMomentumSolver
     from naviflow_oo.solver.pressure_solver.helpers.rhs_construction import get_rhs

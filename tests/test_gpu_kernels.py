@@ -299,3 +299,34 @@ def test_fused_momentum_sweeps_are_bit_identical(n, tma, monkeypatch):
             np.testing.assert_array_equal(d.down(xb, *shape), d.down(xa, *shape), err_msg=f"n={n} u={is_u} k={sweeps}")
             np.testing.assert_array_equal(d.down(fb, *shape), d.down(fa, *shape))
             assert abs(na.value - nbv.value) <= 1e-12 * abs(na.value)
+
+
+@pytest.mark.gpu
+def test_quick_and_second_order_upwind_links_vs_reference_golden(golden_dir):
+    """nf_momentum_links_ext through the plugin twins of QUICKDiscretization / SecondOrderUpwindDiscretization
+    (quick.py:27-219, second_order_upwind.py:26-325) against the reference's outputs: all ten arrays of both components,
+    with the cavity's boundary conditions and with bc=None, square / rectangular / minimal grids -- bit-exact."""
+    import naviflow_b200 as nb
+    G = np.load(os.path.join(golden_dir, "ext_links_kats.npz"))
+    bc = nb.BoundaryConditionManager()
+    bc.set_condition("top", "velocity", {"u": 1.0, "v": 0.0})
+    for b in ("bottom", "left", "right"):
+        bc.set_condition(b, "wall")
+    keys = ("a_e", "a_w", "a_n", "a_s", "a_ee", "a_ww", "a_nn", "a_ss", "a_p", "source")
+    for tag in G["cases"]:
+        tag = str(tag)
+        nx, ny = (int(x) for x in G[f"{tag}_dims"])
+        dx, dy, rho, mu = (float(x) for x in G[f"{tag}_scal"])
+        mesh = nb.StructuredMesh(nx, ny, 1.0, 0.7 if nx != ny else 1.0)   # as oracle/make_golden.py:ext_links_kats
+        assert mesh.get_cell_sizes() == (dx, dy)
+        fluid = nb.FluidProperties(density=rho, viscosity=mu)
+        u, v, p = G[f"{tag}_u"], G[f"{tag}_v"], G[f"{tag}_p"]
+        for sch, cls in (("quick", nb.GpuQUICKDiscretization), ("sou", nb.GpuSecondOrderUpwindDiscretization)):
+            d = cls()
+            for bname, b in (("bc", bc), ("nobc", None)):
+                for comp, got in (("u", d.calculate_u_coefficients(mesh, fluid, u, v, p, b)),
+                                  ("v", d.calculate_v_coefficients(mesh, fluid, u, v, p, b))):
+                    assert tuple(sorted(got)) == tuple(sorted(keys))
+                    for k in keys:
+                        np.testing.assert_array_equal(got[k], G[f"{tag}_{sch}_{bname}_{comp}_{k}"],
+                                                      err_msg=f"{tag} {sch} {bname} {comp} {k}")

@@ -56,6 +56,9 @@ def _pairs():
         (nb.GpuPisoSolver, R.PisoSolver, ["__init__", "solve"]),
         (nb.GpuSimplerSolver, R.SimplerSolver, ["__init__", "solve"]),
         (nb.GpuSimplecSolver, SimplecSolver, ["__init__", "solve"]),
+        (nb.GpuQUICKDiscretization, R.QUICKDiscretization, ["calculate_u_coefficients", "calculate_v_coefficients"]),
+        (nb.GpuSecondOrderUpwindDiscretization, R.SecondOrderUpwindDiscretization,
+         ["calculate_u_coefficients", "calculate_v_coefficients"]),
         (nb.Profiler, __import__("naviflow_oo.utils.profiler", fromlist=["Profiler"]).Profiler,
          ["__init__", "start", "end", "start_section", "end_section", "set_iterations", "set_convergence_info",
           "add_residual_data", "set_pressure_solver_info", "save"]),
