@@ -37,7 +37,8 @@ def test_ctypes_struct_layouts_match_the_header(tmp_path):
     from naviflow_b200 import _lib
     pairs = [("nf_grid", _lib.NfGrid), ("nf_bc_program", _lib.NfBcProgram), ("nf_mg_config", _lib.NfMgConfig),
              ("nf_simple_config", _lib.NfSimpleConfig), ("nf_simple_info", _lib.NfSimpleInfo),
-             ("nf_krylov_info", _lib.NfKrylovInfo), ("nf_links", _lib.NfLinks)]
+             ("nf_krylov_info", _lib.NfKrylovInfo), ("nf_links", _lib.NfLinks), ("nf_links_ext", _lib.NfLinksExt),
+             ("nf_mg_info", _lib.NfMgInfo)]
     header = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "naviflow_b200.h")
     src = tmp_path / "sizes.c"
     src.write_text('#include <stdio.h>\n#include "%s"\nint main(void){printf("%s\\n", %s);return 0;}\n'
