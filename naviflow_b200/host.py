@@ -133,10 +133,21 @@ def conditions_of(bc):
 
 
 class BoundaryConditionManager:
-    """Registry of boundary conditions; insertion order is significant (it decides the lid corners)."""
+    """Registry of boundary conditions; insertion order is significant (it decides the lid corners).
+
+    ``items()`` / ``len()`` give the ``{location: {type: values}}`` mapping view: the reference's solvers treat every
+    boundary-condition object that is not an instance of their own manager class as such a mapping and rebuild a manager
+    from it (jacobi_matrix_solver.py:162-170, standard.py), which is what makes this class usable inside the reference's
+    own loop (tests/test_reference_api.py)."""
 
     def __init__(self):
         self.conditions = {}
+
+    def items(self):
+        return self.conditions.items()
+
+    def __len__(self):
+        return len(self.conditions)
 
     def set_condition(self, location, bc_type, values=None):
         loc = getattr(location, "name", location).lower()

@@ -98,3 +98,35 @@ def test_virtual_subclass_registration():
     from naviflow_oo.solver.pressure_solver.base_pressure_solver import PressureSolver
     from naviflow_oo.solver.Algorithms.base_algorithm import BaseAlgorithm
     assert issubclass(nb.GpuMultiGridSolver, PressureSolver) and issubclass(nb.GpuSimpleSolver, BaseAlgorithm)
+
+
+def test_host_objects_drop_into_the_reference_simple_solver(golden_dir):
+    """INTEGRATION.md path A from the other side: the reference's own SimpleSolver loop (simple.py:78-269) runs with THIS
+    package's StructuredMesh, FluidProperties and BoundaryConditionManager in place of its own (and the reference's CPU
+    solvers) and reproduces the golden run bit for bit -- the host objects are drop-in, method for method."""
+    import contextlib
+    import io
+    import os
+    import numpy as np
+    import naviflow_b200 as nb
+    R = RL.ref()
+    n, Re, k, N = 31, 100, 5, 40
+    mesh = nb.StructuredMesh(n, n, 1.0, 1.0)
+    fluid = nb.FluidProperties(density=1.0, reynolds_number=Re, characteristic_velocity=1.0)
+    bc = nb.BoundaryConditionManager()
+    ps = R.GaussSeidelSolver(tolerance=0.0, max_iterations=30, omega=1.5, method_type="red_black")
+    alg = R.SimpleSolver(mesh, fluid, ps, R.JacobiMatrixMomentumAdapter(n_jacobi_sweeps=k), R.StandardVelocityUpdater(),
+                         alpha_p=0.3, alpha_u=0.7)
+    # base_algorithm.py:51-54 accepts only instances of the reference's own (non-abstract) manager class in the constructor,
+    # so the foreign manager is attached afterwards; every later use goes through self.bc_manager
+    alg.bc_manager = bc
+    alg.set_boundary_condition("top", "velocity", {"u": 1.0, "v": 0.0})
+    for b in ("bottom", "left", "right"):
+        alg.set_boundary_condition(b, "wall")
+    assert alg.bc_manager is bc and set(bc.conditions) == {"top", "bottom", "left", "right"}
+    with contextlib.redirect_stdout(io.StringIO()):
+        alg.solve(max_iterations=N, tolerance=0.0, save_profile=False, track_infinity_norm=False)
+    G = np.load(os.path.join(golden_dir, "simple_runs.npz"))
+    key = f"n{n}_Re{Re}_k{k}_N{N}_rbsor"
+    for f in ("u", "v", "p"):
+        np.testing.assert_array_equal(getattr(alg, f), G[f"{key}_{f}"])
